@@ -1,0 +1,272 @@
+// HBM-bound helper kernels around the tensor-core convs: tile gather + stem im2col, max/avg pooling with the
+// pre-activation BN, the naive head, and the slide-plane kernels (stitch / normalise / threshold / pyramid).
+// All activations are NHWC fp16 with an explicit channel stride so that concat buffers are written in place.
+#pragma once
+#include <cuda_fp16.h>
+#include <stdint.h>
+#include "d4.cuh"
+
+namespace dp {
+
+// ---------------------------------------------------------------------------------------------------------
+// Tile gather + (v-128)/128 + forward TTA + ZeroPadding2D(3) + im2col for the 7x7/2 stem conv
+// (dataloader.py:357-388 crop/transposed layout/normalise; utils.py:487-501 TTA; densenet.py:116-117 stem).
+// slide is uint8 [Wslide][Hslide][3] in the reference's [x][y] orientation; tile b has origin coords[b] = (x,y).
+// out is fp16 [B][P/2][P/2][160], column k = (ky*7 + kx)*3 + c for k < 147, zero above.
+__global__ void stem_im2col_kernel(const uint8_t* __restrict__ slide, long long slide_h,
+                                   const int* __restrict__ coords, int B, int P, int tta_code,
+                                   __half* __restrict__ out) {
+  const int OH = P / 2;
+  const long long total = static_cast<long long>(B) * OH * OH * 20;
+  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int q = idx % 20;
+    long long r = idx / 20;
+    const int ow = r % OH; r /= OH;
+    const int oh = r % OH;
+    const int b = r / OH;
+    const long long x0 = coords[2 * b], y0 = coords[2 * b + 1];
+    __align__(16) __half vals[8];
+#pragma unroll
+    for (int t = 0; t < 8; ++t) {
+      const int k = q * 8 + t;
+      float v = 0.f;
+      if (k < 147) {
+        const int ky = k / 21, rem = k - ky * 21;
+        const int kx = rem / 3, c = rem - kx * 3;
+        const int i = 2 * oh + ky - 3, j = 2 * ow + kx - 3;
+        if (i >= 0 && i < P && j >= 0 && j < P) {
+          int ti, tj;
+          d4_src(tta_code, i, j, P, ti, tj);
+          const uint8_t px = slide[((x0 + ti) * slide_h + (y0 + tj)) * 3 + c];
+          v = (static_cast<float>(px) - 128.f) * (1.f / 128.f);  // exact in fp16
+        }
+      }
+      vals[t] = __float2half_rn(v);
+    }
+    *reinterpret_cast<uint4*>(out + idx * 8) = *reinterpret_cast<const uint4*>(vals);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// ZeroPadding2D(1) + MaxPooling2D(3, strides=2) (densenet.py:122-123). 8 channels per thread.
+__global__ void maxpool3s2_kernel(const __half* __restrict__ in, int in_ctot, int in_choff,
+                                  __half* __restrict__ out, int out_ctot, int out_choff, int n_img, int H, int W,
+                                  int C) {
+  const int OH = H / 2, OW = W / 2, CG = C / 8;
+  const long long total = static_cast<long long>(n_img) * OH * OW * CG;
+  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int cg = idx % CG;
+    long long r = idx / CG;
+    const int ow = r % OW; r /= OW;
+    const int oh = r % OH;
+    const int n = r / OH;
+    float m[8];
+#pragma unroll
+    for (int t = 0; t < 8; ++t) m[t] = -INFINITY;
+    for (int ky = 0; ky < 3; ++ky)
+      for (int kx = 0; kx < 3; ++kx) {
+        const int ih = 2 * oh - 1 + ky, iw = 2 * ow - 1 + kx;
+        if (ih < 0 || ih >= H || iw < 0 || iw >= W) {
+#pragma unroll
+          for (int t = 0; t < 8; ++t) m[t] = fmaxf(m[t], 0.f);  // explicit zero padding takes part in the max
+        } else {
+          const uint4 raw = *reinterpret_cast<const uint4*>(
+              in + ((static_cast<long long>(n) * H + ih) * W + iw) * in_ctot + in_choff + cg * 8);
+          const __half2* hv = reinterpret_cast<const __half2*>(&raw);
+#pragma unroll
+          for (int t = 0; t < 4; ++t) {
+            const float2 f = __half22float2(hv[t]);
+            m[2 * t] = fmaxf(m[2 * t], f.x);
+            m[2 * t + 1] = fmaxf(m[2 * t + 1], f.y);
+          }
+        }
+      }
+    __align__(16) __half2 o[4];
+#pragma unroll
+    for (int t = 0; t < 4; ++t) o[t] = __floats2half2_rn(m[2 * t], m[2 * t + 1]);
+    *reinterpret_cast<uint4*>(out + ((static_cast<long long>(n) * OH + oh) * OW + ow) * out_ctot + out_choff +
+                              cg * 8) = *reinterpret_cast<const uint4*>(o);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// y = scale*x + shift [, ReLU] [, AveragePooling2D(2,2)]   (transition_block densenet.py:101-107 with the
+// pool commuted in front of the 1x1 conv -- both are linear -- and the final `bn` densenet.py:134).
+__global__ void bn_act_pool_kernel(const __half* __restrict__ in, int in_ctot, int in_choff,
+                                   __half* __restrict__ out, int out_ctot, int out_choff, int n_img, int H, int W,
+                                   int C, const float* __restrict__ scale, const float* __restrict__ shift,
+                                   int relu, int pool) {
+  const int OH = pool ? H / 2 : H, OW = pool ? W / 2 : W, CG = C / 8;
+  const long long total = static_cast<long long>(n_img) * OH * OW * CG;
+  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int cg = idx % CG;
+    long long r = idx / CG;
+    const int ow = r % OW; r /= OW;
+    const int oh = r % OH;
+    const int n = r / OH;
+    float sc[8], sh[8], acc[8];
+#pragma unroll
+    for (int t = 0; t < 8; ++t) { sc[t] = scale[cg * 8 + t]; sh[t] = shift[cg * 8 + t]; acc[t] = 0.f; }
+    const int np = pool ? 2 : 1;
+    for (int dy = 0; dy < np; ++dy)
+      for (int dx = 0; dx < np; ++dx) {
+        const int ih = pool ? 2 * oh + dy : oh, iw = pool ? 2 * ow + dx : ow;
+        const uint4 raw = *reinterpret_cast<const uint4*>(
+            in + ((static_cast<long long>(n) * H + ih) * W + iw) * in_ctot + in_choff + cg * 8);
+        const __half2* hv = reinterpret_cast<const __half2*>(&raw);
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          const float2 f = __half22float2(hv[t]);
+          float a = fmaf(f.x, sc[2 * t], sh[2 * t]), b = fmaf(f.y, sc[2 * t + 1], sh[2 * t + 1]);
+          if (relu) { a = fmaxf(a, 0.f); b = fmaxf(b, 0.f); }
+          acc[2 * t] += a;
+          acc[2 * t + 1] += b;
+        }
+      }
+    const float inv = pool ? 0.25f : 1.f;
+    __align__(16) __half2 o[4];
+#pragma unroll
+    for (int t = 0; t < 4; ++t) o[t] = __floats2half2_rn(acc[2 * t] * inv, acc[2 * t + 1] * inv);
+    *reinterpret_cast<uint4*>(out + ((static_cast<long long>(n) * OH + oh) * OW + ow) * out_ctot + out_choff +
+                              cg * 8) = *reinterpret_cast<const uint4*>(o);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Head for the naive (debug) path: 1x1 conv C->2 + softmax channel 1 + inverse TTA (densenet.py:156).
+__global__ void head_naive_kernel(const __half* __restrict__ in, int in_ctot, int in_choff, int C, int n_img,
+                                  int P, const float* __restrict__ w, float bias, int tta_code,
+                                  float* __restrict__ out) {
+  const long long total = static_cast<long long>(n_img) * P * P;
+  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int wq = idx % P;
+    const int h = (idx / P) % P;
+    const int n = idx / (static_cast<long long>(P) * P);
+    const __half* a = in + idx * in_ctot + in_choff;
+    float z = 0.f;
+    for (int c = 0; c < C; ++c) z = fmaf(__half2float(a[c]), w[c], z);
+    z += bias;
+    int di, dj;
+    d4_src(tta_code, h, wq, P, di, dj);
+    out[(static_cast<long long>(n) * P + di) * P + dj] = 1.f / (1.f + expf(-z));
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// TTA/ensemble statistics + overlap accumulate (Segmentation.py:162-173).
+// probs is fp32 [N][B][P][P] (N = |tta| * |models| passes of this batch), planes are [W][H] (x-major).
+// For every plane pixel touched by this batch exactly ONE thread (the lowest-index covering tile's thread)
+// walks the covering tiles in ascending tile order and does the reference's sequential `+=`, so the result
+// is bit-identical to the numpy loop given identical probabilities; no atomics.
+// numpy semantics reproduced: mean = (sequential fp32 sum over N) / N; var = sum((p-mean)^2)/N (ddof 0);
+// count is uint8 and wraps.
+__global__ void stitch_kernel(const float* __restrict__ probs, int N, int B, int P,
+                              const int* __restrict__ coords, float* __restrict__ mean,
+                              float* __restrict__ var, uint8_t* __restrict__ count, long long plane_h,
+                              int x_lo) {
+  extern __shared__ int s_xy[];  // [B][2]
+  for (int i = threadIdx.x; i < 2 * B; i += blockDim.x) s_xy[i] = coords[i];
+  __syncthreads();
+  const int i = blockIdx.y;
+  const int xi = s_xy[2 * i], yi = s_xy[2 * i + 1];
+  for (int pix = blockIdx.x * blockDim.x + threadIdx.x; pix < P * P; pix += gridDim.x * blockDim.x) {
+    const int a = pix / P, b = pix - a * P;
+    const int gx = xi + a, gy = yi + b;
+    bool owner = true;
+    for (int j = 0; j < i; ++j) {
+      const int dx = gx - s_xy[2 * j], dy = gy - s_xy[2 * j + 1];
+      if (dx >= 0 && dx < P && dy >= 0 && dy < P) { owner = false; break; }
+    }
+    if (!owner) continue;
+    const long long off = static_cast<long long>(gx - x_lo) * plane_h + gy;
+    float m = mean[off], v = var[off];
+    uint8_t cnt = count[off];
+    for (int j = i; j < B; ++j) {
+      const int dx = gx - s_xy[2 * j], dy = gy - s_xy[2 * j + 1];
+      if (dx < 0 || dx >= P || dy < 0 || dy >= P) continue;
+      const float* pp = probs + (static_cast<long long>(j) * P + dx) * P + dy;
+      const long long pass_stride = static_cast<long long>(B) * P * P;
+      float s = pp[0];
+      for (int k = 1; k < N; ++k) s = __fadd_rn(s, pp[k * pass_stride]);
+      const float mu = __fdiv_rn(s, static_cast<float>(N));
+      float d0 = __fsub_rn(pp[0], mu);
+      float ss = __fmul_rn(d0, d0);
+      for (int k = 1; k < N; ++k) {
+        const float d = __fsub_rn(pp[k * pass_stride], mu);
+        ss = __fadd_rn(ss, __fmul_rn(d, d));
+      }
+      const float vr = __fdiv_rn(ss, static_cast<float>(N));
+      m = __fadd_rn(m, mu);
+      v = __fadd_rn(v, vr);
+      cnt = static_cast<uint8_t>(cnt + 1);
+    }
+    mean[off] = m;
+    var[off] = v;
+    count[off] = cnt;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// count==0 -> 1; mean /= count; var /= count^2 (Segmentation.py:175-177); label = mean >= thr ? 255 : 0
+// (Segmentation.py:336-337).  16 pixels per thread step (count is the narrowest type: 16 B vectors).
+__global__ void finalize_kernel(float* __restrict__ mean, float* __restrict__ var, uint8_t* __restrict__ count,
+                                long long n, float thr, uint8_t* __restrict__ label) {
+  const long long nvec = n / 16;
+  for (long long v = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; v < nvec;
+       v += static_cast<long long>(gridDim.x) * blockDim.x) {
+    uint4 craw = reinterpret_cast<uint4*>(count)[v];
+    uint8_t* c = reinterpret_cast<uint8_t*>(&craw);
+    __align__(16) uint8_t lab[16];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      float4 m4 = reinterpret_cast<float4*>(mean)[v * 4 + q];
+      float4 v4 = reinterpret_cast<float4*>(var)[v * 4 + q];
+      float* mp = reinterpret_cast<float*>(&m4);
+      float* vp = reinterpret_cast<float*>(&v4);
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        uint8_t cc = c[q * 4 + t];
+        if (cc == 0) cc = 1;
+        c[q * 4 + t] = cc;
+        const float cf = static_cast<float>(cc);
+        mp[t] = __fdiv_rn(mp[t], cf);
+        vp[t] = __fdiv_rn(vp[t], __fmul_rn(cf, cf));
+        lab[q * 4 + t] = (mp[t] >= thr) ? 255 : 0;
+      }
+      reinterpret_cast<float4*>(mean)[v * 4 + q] = m4;
+      reinterpret_cast<float4*>(var)[v * 4 + q] = v4;
+    }
+    reinterpret_cast<uint4*>(count)[v] = craw;
+    if (label) reinterpret_cast<uint4*>(label)[v] = *reinterpret_cast<const uint4*>(lab);
+  }
+  // tail
+  const long long t0 = nvec * 16 + blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (t0 < n) {
+    uint8_t cc = count[t0];
+    if (cc == 0) cc = 1;
+    count[t0] = cc;
+    const float cf = static_cast<float>(cc);
+    const float m = __fdiv_rn(mean[t0], cf);
+    mean[t0] = m;
+    var[t0] = __fdiv_rn(var[t0], __fmul_rn(cf, cf));
+    if (label) label[t0] = (m >= thr) ? 255 : 0;
+  }
+}
+
+// 2x mean-pool of an [W][H] fp32 plane -> [W/2][H/2] (in-HBM probability pyramid, BASELINE config 3).
+__global__ void pyramid_down2_kernel(const float* __restrict__ in, long long W, long long H,
+                                     float* __restrict__ out) {
+  const long long OW = W / 2, OH = H / 2, total = OW * OH;
+  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long oy = idx % OH, ox = idx / OH;
+    const float* p = in + (2 * ox) * H + 2 * oy;
+    out[idx] = 0.25f * ((p[0] + p[1]) + (p[H] + p[H + 1]));
+  }
+}
+
+}  // namespace dp

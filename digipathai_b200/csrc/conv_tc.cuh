@@ -1,0 +1,496 @@
+// Implicit-GEMM convolution on the 5th-gen tensor cores (tcgen05.mma, accumulators in TMEM), NHWC fp16
+// activations, fp32 accumulate.  One kernel covers every conv of the DenseNet-121 U-Net
+// (reference graph: DigiPathAI/models/densenet.py:37-159):
+//
+//   GEMM view   D[pixels, Cout] = sum over (tap entry e, channel chunk c)  A_e,c[pixels, 64] * W_e,c[Cout, 64]^T
+//
+//   MODE_D  1x1 conv: A tiles are flat [128 pixels x 64 ch] boxes of a 2-D [pixels, C] view.
+//   MODE_T  3x3 conv on maps too small for a halo region (8x8): one shifted 4-D TMA box per tap;
+//           out-of-bounds pixels are zero-filled by TMA == Keras padding='same'.
+//   MODE_H  3x3 conv with a shared-memory resident halo: ONE 4-D TMA box [(16+2) x (8*SUB+2) pixels x 64 ch]
+//           per channel chunk; the 9 taps are 9 UMMA descriptors into that box at different row offsets
+//           (an 8-pixel row segment is one 8-row swizzle group; consecutive image rows are SBO apart).
+//           This is what keeps the L2->SMEM traffic at ~1.3x the activation bytes instead of 9x.
+//   up2     UpSampling2D()+conv3x3 (densenet.py:138-155) is evaluated as 4 sub-pixel phases, each a 2x2 conv
+//           on the LOW-resolution map with pre-summed weights (2.25x fewer MACs, no upsampled tensor in HBM).
+//
+// Warp roles (1 CTA / SM, persistent over work items):
+//   warp 0 lane 0 : TMA producer (A ring + B ring)      warp 1 lane 0 : tcgen05.mma issuer
+//   warp 2        : TMEM allocator                      warps 4-7     : epilogue (tcgen05.ld -> BN/ReLU -> HBM)
+//   warps 8-11    : (PROLOGUE only) pre-activation BN+ReLU applied to the A tile in shared memory
+//                   (dense-layer `_0_bn/_0_relu`, densenet.py:59-63) before the MMA reads it.
+#pragma once
+#include "ptx.cuh"
+#include "d4.cuh"
+
+namespace dp {
+
+enum : int { MODE_D = 0, MODE_T = 1, MODE_H = 2 };
+enum : int { EPI_STORE = 0, EPI_HEAD = 1 };
+
+constexpr int kMaxEntries = 16;
+constexpr int kMaxAStages = 8;
+constexpr int kMaxBStages = 16;
+constexpr int kTmemCols = 512;
+constexpr int kATileBytes = 128 * 128;  // 128 pixel rows x 64 fp16
+
+struct TapEntry {
+  int8_t dy, dx;   // input offset relative to the (low-res) output pixel
+  int8_t group;    // accumulator group (sub-pixel phase in MODE_H up2, else 0)
+  int8_t pad;
+};
+
+struct ConvParams {
+  int mode, sub, n_tile, n_ntiles;
+  int n_img, H, W, Cin;  // input grid per image and channels visible through the A tensor map
+  int n_chunks;          // ceil(Cin / 64)
+  int n_entries;         // tap entries per work item
+  int n_groups;          // accumulator groups per work item
+  int n_phase_items;     // MODE_T up2: 4 (phase is part of the work item), else 1
+  int up2;               // output grid is (2H, 2W)
+  int box_w, box_h, box_n;  // MODE_T: TMA box; MODE_H: halo box (WW, HH, 1)
+  int tiles_w, tiles_h;     // tile grid per image (MODE_T: per box_n images)
+  int m_total;              // MODE_D: total pixels
+  int n_mtiles, n_items;
+  int a_stage_bytes, b_stage_bytes, a_stages, b_stages, acc_stages, a_tx_bytes;
+  int epi_mode, relu;
+  int out_ctot, out_choff;  // output NHWC buffer: channel stride and channel offset (elements)
+  int desc_base_mode;       // 0: descriptor base_offset field = 0; 1: (addr >> 7) & 7
+  int pro_relu;
+  int tta_code, P;          // EPI_HEAD: D4 code whose source-map scatters the prediction back; tile side
+  float head_b;
+  TapEntry entries[kMaxEntries];
+  const float* epi_scale;
+  const float* epi_shift;
+  const float* pro_scale;
+  const float* pro_shift;
+  __half* out;
+  const float* head_w;
+  float* head_out;
+};
+
+struct ConvSmemLayout {
+  // offsets from the 1024-aligned base
+  static constexpr int kBarBytes = 1024;
+  int a_off, b_off, epi_off, pro_off, head_off, total;
+};
+
+__host__ __device__ inline ConvSmemLayout conv_smem_layout(const ConvParams& p) {
+  ConvSmemLayout L;
+  L.a_off = ConvSmemLayout::kBarBytes;
+  L.b_off = L.a_off + p.a_stages * p.a_stage_bytes;
+  L.epi_off = L.b_off + p.b_stages * p.b_stage_bytes;
+  int cout = p.n_tile * p.n_ntiles;
+  L.pro_off = L.epi_off + 2 * cout * 4;
+  L.head_off = L.pro_off + 2 * p.n_chunks * 64 * 4;
+  L.total = L.head_off + 256 * 4 + 1024;  // + alignment slack
+  return L;
+}
+
+struct WorkItem {
+  int nt, ph;
+  int n0, h0, w0;  // T/H: tile origin on the input grid
+  int m0;          // D: first pixel
+};
+
+__device__ __forceinline__ WorkItem decode_item(const ConvParams& p, int item) {
+  WorkItem wi;
+  int mt = item % p.n_mtiles;
+  int rest = item / p.n_mtiles;
+  wi.nt = rest % p.n_ntiles;
+  wi.ph = rest / p.n_ntiles;
+  wi.m0 = 0; wi.n0 = 0; wi.h0 = 0; wi.w0 = 0;
+  if (p.mode == MODE_D) {
+    wi.m0 = mt * p.sub * 128;
+  } else if (p.mode == MODE_T) {
+    int tw = mt % p.tiles_w;
+    int r = mt / p.tiles_w;
+    int th = r % p.tiles_h;
+    int tn = r / p.tiles_h;
+    wi.w0 = tw * p.box_w; wi.h0 = th * p.box_h; wi.n0 = tn * p.box_n;
+  } else {
+    int tw = mt % p.tiles_w;
+    int r = mt / p.tiles_w;
+    int th = r % p.tiles_h;
+    wi.n0 = r / p.tiles_h;
+    wi.w0 = tw * 8 * p.sub; wi.h0 = th * 16;
+  }
+  return wi;
+}
+
+template <bool PROLOGUE>
+__global__ void __launch_bounds__(PROLOGUE ? 384 : 256, 1)
+conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+               const __grid_constant__ ConvParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
+
+  uint64_t* a_full = reinterpret_cast<uint64_t*>(smem);
+  uint64_t* a_ready = a_full + kMaxAStages;
+  uint64_t* a_empty = a_ready + kMaxAStages;
+  uint64_t* b_full = a_empty + kMaxAStages;
+  uint64_t* b_empty = b_full + kMaxBStages;
+  uint64_t* acc_full = b_empty + kMaxBStages;
+  uint64_t* acc_empty = acc_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+
+  const ConvSmemLayout L = conv_smem_layout(p);
+  uint8_t* a_base = smem + L.a_off;
+  uint8_t* b_base = smem + L.b_off;
+  float* s_epi_scale = reinterpret_cast<float*>(smem + L.epi_off);
+  float* s_epi_shift = s_epi_scale + p.n_tile * p.n_ntiles;
+  float* s_pro_scale = reinterpret_cast<float*>(smem + L.pro_off);
+  float* s_pro_shift = s_pro_scale + p.n_chunks * 64;
+  float* s_head_w = reinterpret_cast<float*>(smem + L.head_off);
+
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5;
+  const int lane = tid & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&map_a);
+    tma_prefetch_desc(&map_b);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < kMaxAStages; ++i) {
+      mbar_init(&a_full[i], 1);
+      mbar_init(&a_ready[i], 128);
+      mbar_init(&a_empty[i], 1);
+    }
+    for (int i = 0; i < kMaxBStages; ++i) {
+      mbar_init(&b_full[i], 1);
+      mbar_init(&b_empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&acc_full[i], 1);
+      mbar_init(&acc_empty[i], 128);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_slot, kTmemCols);
+    tmem_relinquish();
+  }
+  {
+    const int cout = p.n_tile * p.n_ntiles;
+    for (int i = tid; i < cout; i += blockDim.x) {
+      s_epi_scale[i] = p.epi_scale ? p.epi_scale[i] : 1.f;
+      s_epi_shift[i] = p.epi_shift ? p.epi_shift[i] : 0.f;
+    }
+    if (PROLOGUE) {
+      for (int i = tid; i < p.n_chunks * 64; i += blockDim.x) {
+        s_pro_scale[i] = p.pro_scale[i];
+        s_pro_shift[i] = p.pro_shift[i];
+      }
+    }
+    if (p.epi_mode == EPI_HEAD) {
+      for (int i = tid; i < cout; i += blockDim.x) s_head_w[i] = p.head_w[i];
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      uint32_t a_it = 0, b_it = 0;
+      for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+        const WorkItem wi = decode_item(p, item);
+        const int ebase = wi.ph * p.n_entries;
+        for (int c = 0; c < p.n_chunks; ++c) {
+          const int c0 = c * 64;
+          if (p.mode != MODE_T) {
+            const uint32_t sa = a_it % p.a_stages, pa = (a_it / p.a_stages) & 1;
+            mbar_wait(&a_empty[sa], pa ^ 1);
+            mbar_expect_tx(&a_full[sa], p.a_tx_bytes);
+            uint8_t* dst = a_base + sa * p.a_stage_bytes;
+            if (p.mode == MODE_D) {
+              for (int s = 0; s < p.sub; ++s)
+                tma_load_2d(&map_a, &a_full[sa], dst + s * kATileBytes, c0, wi.m0 + s * 128);
+            } else {
+              tma_load_4d(&map_a, &a_full[sa], dst, c0, wi.w0 - 1, wi.h0 - 1, wi.n0);
+            }
+            ++a_it;
+          }
+          for (int e = 0; e < p.n_entries; ++e) {
+            if (p.mode == MODE_T) {
+              const TapEntry ent = p.entries[ebase + e];
+              const uint32_t sa = a_it % p.a_stages, pa = (a_it / p.a_stages) & 1;
+              mbar_wait(&a_empty[sa], pa ^ 1);
+              mbar_expect_tx(&a_full[sa], p.a_tx_bytes);
+              tma_load_4d(&map_a, &a_full[sa], a_base + sa * p.a_stage_bytes, c0, wi.w0 + ent.dx,
+                          wi.h0 + ent.dy, wi.n0);
+              ++a_it;
+            }
+            const uint32_t sb = b_it % p.b_stages, pb = (b_it / p.b_stages) & 1;
+            mbar_wait(&b_empty[sb], pb ^ 1);
+            mbar_expect_tx(&b_full[sb], p.b_stage_bytes);
+            tma_load_3d(&map_b, &b_full[sb], b_base + sb * p.b_stage_bytes, c0, wi.nt * p.n_tile, ebase + e);
+            ++b_it;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_f16(p.n_tile);
+      const uint32_t a_sbo = (p.mode == MODE_H) ? p.box_w * 128 : 1024;
+      uint32_t a_it = 0, b_it = 0, acc_it = 0;
+      for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+        const WorkItem wi = decode_item(p, item);
+        const int ebase = wi.ph * p.n_entries;
+        const uint32_t as = acc_it % p.acc_stages, ap = (acc_it / p.acc_stages) & 1;
+        mbar_wait(&acc_empty[as], ap ^ 1);
+        tc_fence_after();
+        uint32_t inited = 0;
+        for (int c = 0; c < p.n_chunks; ++c) {
+          int ks = (p.Cin - c * 64 + 15) >> 4;
+          ks = ks > 4 ? 4 : ks;
+          uint32_t sa = 0;
+          if (p.mode != MODE_T) {
+            sa = a_it % p.a_stages;
+            const uint32_t pa = (a_it / p.a_stages) & 1;
+            mbar_wait(PROLOGUE ? &a_ready[sa] : &a_full[sa], pa);
+            tc_fence_after();
+          }
+          for (int e = 0; e < p.n_entries; ++e) {
+            const TapEntry ent = p.entries[ebase + e];
+            if (p.mode == MODE_T) {
+              sa = a_it % p.a_stages;
+              const uint32_t pa = (a_it / p.a_stages) & 1;
+              mbar_wait(&a_full[sa], pa);
+            }
+            const uint32_t sb = b_it % p.b_stages, pb = (b_it / p.b_stages) & 1;
+            mbar_wait(&b_full[sb], pb);
+            tc_fence_after();
+            const uint32_t a_stage_addr = smem_u32(a_base + sa * p.a_stage_bytes);
+            const uint32_t b_addr = smem_u32(b_base + sb * p.b_stage_bytes);
+            const uint32_t row_off = (p.mode == MODE_H) ? ((ent.dy + 1) * p.box_w + (ent.dx + 1)) : 0;
+            const uint32_t acc_flag0 = (inited >> ent.group) & 1u;
+            for (int s = 0; s < p.sub; ++s) {
+              const uint32_t a_addr =
+                  a_stage_addr + ((p.mode == MODE_D) ? s * kATileBytes : (row_off + 8 * s) * 128);
+              const uint32_t d_tmem = tmem_base + ((as * p.n_groups + ent.group) * p.sub + s) * p.n_tile;
+              for (int k = 0; k < ks; ++k) {
+                const uint32_t aa = a_addr + k * 32, bb = b_addr + k * 32;
+                const uint64_t adesc = make_sw128_desc(aa, a_sbo, p.desc_base_mode ? ((aa >> 7) & 7) : 0);
+                const uint64_t bdesc = make_sw128_desc(bb, 1024, 0);
+                umma_f16_ss(d_tmem, adesc, bdesc, idesc, (k > 0) ? 1u : acc_flag0);
+              }
+            }
+            inited |= 1u << ent.group;
+            umma_commit(&b_empty[sb]);
+            ++b_it;
+            if (p.mode == MODE_T) {
+              umma_commit(&a_empty[sa]);
+              ++a_it;
+            }
+          }
+          if (p.mode != MODE_T) {
+            umma_commit(&a_empty[sa]);
+            ++a_it;
+          }
+        }
+        umma_commit(&acc_full[as]);
+        ++acc_it;
+      }
+    }
+  } else if (warp >= 4 && warp < 8) {
+    // ------------------------------------------------------------------ epilogue
+    const int q = warp & 3;
+    const int r = q * 32 + lane;  // accumulator row == TMEM lane == pixel within the sub-tile
+    uint32_t acc_it = 0;
+    for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+      const WorkItem wi = decode_item(p, item);
+      const uint32_t as = acc_it % p.acc_stages, ap = (acc_it / p.acc_stages) & 1;
+      mbar_wait(&acc_full[as], ap);
+      tc_fence_after();
+      const int ch0 = wi.nt * p.n_tile;
+      for (int g = 0; g < p.n_groups; ++g) {
+        const int ph = (p.mode == MODE_H) ? g : wi.ph;
+        for (int s = 0; s < p.sub; ++s) {
+          // ---- where does this accumulator row land?
+          bool valid;
+          long long opix;  // output pixel index (flat over n, oh, ow)
+          int n, h, w;
+          if (p.mode == MODE_D) {
+            const int m = wi.m0 + s * 128 + r;
+            valid = m < p.m_total;
+            opix = m;
+            n = 0; h = 0; w = 0;
+            if (p.epi_mode == EPI_HEAD) {
+              n = m / (p.H * p.W);
+              const int rem = m - n * p.H * p.W;
+              h = rem / p.W; w = rem - h * p.W;
+            }
+          } else {
+            if (p.mode == MODE_T) {
+              w = wi.w0 + r % p.box_w;
+              const int t = r / p.box_w;
+              h = wi.h0 + t % p.box_h;
+              n = wi.n0 + t / p.box_h;
+            } else {
+              w = wi.w0 + 8 * s + (r & 7);
+              h = wi.h0 + (r >> 3);
+              n = wi.n0;
+            }
+            valid = (n < p.n_img) && (h < p.H) && (w < p.W);
+            if (p.up2) {
+              h = 2 * h + (ph >> 1);
+              w = 2 * w + (ph & 1);
+              opix = (static_cast<long long>(n) * (2 * p.H) + h) * (2 * p.W) + w;
+            } else {
+              opix = (static_cast<long long>(n) * p.H + h) * p.W + w;
+            }
+          }
+          const uint32_t taddr =
+              tmem_base + (static_cast<uint32_t>(q * 32) << 16) + ((as * p.n_groups + g) * p.sub + s) * p.n_tile;
+          float head_acc = 0.f;
+          __half* orow = p.out ? p.out + opix * p.out_ctot + p.out_choff + ch0 : nullptr;
+          for (int cc = 0; cc < p.n_tile; cc += 16) {
+            uint32_t v[16];
+            tmem_ld16(taddr + cc, v);
+            tmem_ld_wait();
+            float f[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              float x = __uint_as_float(v[i]);
+              x = fmaf(x, s_epi_scale[ch0 + cc + i], s_epi_shift[ch0 + cc + i]);
+              f[i] = p.relu ? fmaxf(x, 0.f) : x;
+            }
+            if (p.epi_mode == EPI_HEAD) {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) head_acc = fmaf(f[i], s_head_w[ch0 + cc + i], head_acc);
+            } else if (valid) {
+              uint32_t pk[8];
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                __half2 h2 = __floats2half2_rn(f[2 * i], f[2 * i + 1]);
+                pk[i] = *reinterpret_cast<uint32_t*>(&h2);
+              }
+              uint4* dst = reinterpret_cast<uint4*>(orow + cc);
+              dst[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+              dst[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+            }
+          }
+          if (p.epi_mode == EPI_HEAD && valid) {
+            // softmax over 2 logits, channel 1 == sigmoid(z1 - z0) (Segmentation.py:167 uses [..., 1] only)
+            const float z = head_acc + p.head_b;
+            const float prob = 1.f / (1.f + expf(-z));
+            int di, dj;
+            d4_src(p.tta_code, h, w, p.P, di, dj);
+            p.head_out[(static_cast<long long>(n) * p.P + di) * p.P + dj] = prob;
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&acc_empty[as]);
+      ++acc_it;
+    }
+  } else if (PROLOGUE && warp >= 8) {
+    // ------------------------------------------------------------------ A-tile pre-activation (MODE_D only)
+    const int t = tid - 256;
+    uint32_t a_it = 0;
+    for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+      for (int c = 0; c < p.n_chunks; ++c) {
+        const uint32_t sa = a_it % p.a_stages, pa = (a_it / p.a_stages) & 1;
+        mbar_wait(&a_full[sa], pa);
+        for (int s = 0; s < p.sub; ++s) {
+          uint8_t* row = a_base + sa * p.a_stage_bytes + s * kATileBytes + t * 128;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            // logical 16-byte chunk i of row t sits at physical chunk i ^ (t & 7) (128B swizzle);
+            // all lanes work on the same 8 channels -> scale/shift reads broadcast, no bank conflicts.
+            uint4* ptr = reinterpret_cast<uint4*>(row + ((i ^ (t & 7)) << 4));
+            uint4 raw = *ptr;
+            __half2* hv = reinterpret_cast<__half2*>(&raw);
+            const int ch = c * 64 + i * 8;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              float2 x = __half22float2(hv[j]);
+              x.x = fmaf(x.x, s_pro_scale[ch + 2 * j], s_pro_shift[ch + 2 * j]);
+              x.y = fmaf(x.y, s_pro_scale[ch + 2 * j + 1], s_pro_shift[ch + 2 * j + 1]);
+              if (p.pro_relu) { x.x = fmaxf(x.x, 0.f); x.y = fmaxf(x.y, 0.f); }
+              hv[j] = __floats2half2_rn(x.x, x.y);
+            }
+            *ptr = raw;
+          }
+        }
+        fence_proxy_async_smem();
+        mbar_arrive(&a_ready[sa]);
+        ++a_it;
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Naive reference of the SAME packed problem (same tap table, same packed weights, same buffers), one thread
+// per output value on CUDA cores.  Debug/bisect tool only (DP_NAIVE_CONV=1): lets a GPU run compare the
+// tcgen05 path against an obviously-correct evaluation layer by layer without shipping tensors back.
+struct NaiveConvParams {
+  int n_img, H, W, Cin, in_ctot, in_choff;
+  int Cout, out_ctot, out_choff;
+  int n_entries_total, n_groups, entries_per_group, up2;
+  int relu, pro_mode;  // pro_mode: 0 none, 1 affine, 2 affine+relu
+  TapEntry entries[kMaxEntries];
+  const __half* in;
+  const __half* w;  // [entries][Cout][Cin]
+  const float* epi_scale;
+  const float* epi_shift;
+  const float* pro_scale;
+  const float* pro_shift;
+  __half* out;
+};
+
+__global__ void conv_naive_kernel(const NaiveConvParams p) {
+  const long long total = static_cast<long long>(p.n_img) * p.H * p.W * p.n_groups * p.Cout;
+  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int co = idx % p.Cout;
+    long long r = idx / p.Cout;
+    const int g = r % p.n_groups; r /= p.n_groups;
+    const int w = r % p.W; r /= p.W;
+    const int h = r % p.H;
+    const int n = r / p.H;
+    float acc = 0.f;
+    for (int e = 0; e < p.n_entries_total; ++e) {
+      const TapEntry ent = p.entries[e];
+      if (ent.group != g) continue;
+      const int ih = h + ent.dy, iw = w + ent.dx;
+      if (ih < 0 || ih >= p.H || iw < 0 || iw >= p.W) continue;
+      const __half* a = p.in + ((static_cast<long long>(n) * p.H + ih) * p.W + iw) * p.in_ctot + p.in_choff;
+      const __half* wt = p.w + (static_cast<long long>(e) * p.Cout + co) * p.Cin;
+      for (int ci = 0; ci < p.Cin; ++ci) {
+        float x = __half2float(a[ci]);
+        if (p.pro_mode) {
+          x = fmaf(x, p.pro_scale[ci], p.pro_shift[ci]);
+          if (p.pro_mode == 2) x = fmaxf(x, 0.f);
+          x = __half2float(__float2half_rn(x));  // the tensor-core path rounds the activated tile to fp16
+        }
+        acc = fmaf(x, __half2float(wt[ci]), acc);
+      }
+    }
+    float y = fmaf(acc, p.epi_scale ? p.epi_scale[co] : 1.f, p.epi_shift ? p.epi_shift[co] : 0.f);
+    if (p.relu) y = fmaxf(y, 0.f);
+    long long opix;
+    if (p.up2)
+      opix = (static_cast<long long>(n) * 2 * p.H + 2 * h + (g >> 1)) * (2 * p.W) + 2 * w + (g & 1);
+    else
+      opix = (static_cast<long long>(n) * p.H + h) * p.W + w;
+    p.out[opix * p.out_ctot + p.out_choff + co] = __float2half_rn(y);
+  }
+}
+
+}  // namespace dp

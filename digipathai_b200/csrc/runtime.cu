@@ -1,0 +1,681 @@
+// Runtime behind include/digipath_b200.h: parses the flat "DPB1" model container, owns the NHWC fp16
+// activation buffers, turns every op of the layer program into a launch plan (TMA tensor maps + tile shapes
+// chosen per layer geometry) and replays the plan on the caller's stream.
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <cudaTypedefs.h>
+
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/digipath_b200.h"
+#include "aux.cuh"
+#include "conv_tc.cuh"
+
+namespace {
+
+thread_local std::string g_err;
+std::atomic<uint64_t> g_launches{0};
+
+int fail(const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  g_err = buf;
+  return 1;
+}
+
+#define CU_OK(expr)                                                                           \
+  do {                                                                                        \
+    cudaError_t e__ = (expr);                                                                 \
+    if (e__ != cudaSuccess)                                                                   \
+      return fail("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__); \
+  } while (0)
+
+#define LAUNCH_OK()                                                                                        \
+  do {                                                                                                     \
+    cudaError_t e__ = cudaGetLastError();                                                                  \
+    if (e__ != cudaSuccess) return fail("kernel launch failed: %s (%s:%d)", cudaGetErrorString(e__), __FILE__, __LINE__); \
+    g_launches.fetch_add(1, std::memory_order_relaxed);                                                    \
+  } while (0)
+
+PFN_cuTensorMapEncodeTiled_v12000 get_encode() {
+  static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(p);
+  });
+  return fn;
+}
+
+// fp16 tensor map, 128-byte swizzle, zero fill out of bounds. dims/strides innermost first; strides in bytes
+// for dims 1..rank-1.
+int make_map(CUtensorMap* map, const void* base, int rank, const uint64_t* dims, const uint64_t* strides,
+             const uint32_t* box) {
+  auto enc = get_encode();
+  if (!enc) return fail("cuTensorMapEncodeTiled entry point not available (driver too old?)");
+  uint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, rank, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return fail("cuTensorMapEncodeTiled failed (%d): rank %d dims %llu,%llu,%llu,%llu box %u,%u,%u,%u", (int)r, rank,
+                (unsigned long long)dims[0], (unsigned long long)(rank > 1 ? dims[1] : 0),
+                (unsigned long long)(rank > 2 ? dims[2] : 0), (unsigned long long)(rank > 3 ? dims[3] : 0), box[0],
+                rank > 1 ? box[1] : 0, rank > 2 ? box[2] : 0, rank > 3 ? box[3] : 0);
+  return 0;
+}
+
+// ---------------------------------------------------------------- container format (see weights.py)
+struct BlobHeader {
+  char magic[4];
+  uint32_t version, n_bufs, n_ops, patch, reserved0;
+  uint64_t data_off, total_bytes;
+  uint64_t reserved1[4];
+};
+static_assert(sizeof(BlobHeader) == 72, "header layout");
+struct BlobBuf {
+  int32_t H, W, C, pad;
+};
+enum : int { OP_STEM_IM2COL = 1, OP_MAXPOOL = 2, OP_CONV = 3, OP_BNPOOL = 4 };
+struct BlobOp {
+  int32_t type, in_buf, in_choff, cin, out_buf, out_choff, cout, kind, relu, pro, head, pool;
+  float head_b;
+  int32_t rsv[3];
+  int64_t w_off, epi_scale_off, epi_shift_off, pro_scale_off, pro_shift_off, head_w_off, rsv64[2];
+};
+static_assert(sizeof(BlobOp) == 128, "op layout");
+
+struct Launch {
+  int type = 0;
+  // conv
+  bool prologue = false;
+  CUtensorMap map_a, map_b;
+  dp::ConvParams cp;
+  dp::NaiveConvParams np;
+  int grid = 0, smem = 0;
+  uint64_t macs = 0;
+  // head (naive path)
+  int head_C = 0;
+};
+
+struct Plan {
+  std::vector<Launch> launches;  // one per op
+};
+
+}  // namespace
+
+struct dp_model {
+  int device = 0, max_batch = 0, patch = 0, num_sms = 148;
+  std::vector<BlobBuf> bufs;
+  std::vector<BlobOp> ops;
+  uint8_t* data_dev = nullptr;
+  size_t data_bytes = 0;
+  std::vector<__half*> buf_dev;
+  __half* scratch_head = nullptr;  // naive path: output of the head-fused conv
+  uint64_t device_bytes = 0;
+  int naive_conv = 0, desc_base_mode = 0, halo_pad8 = 0;
+  std::map<int, Plan> plans;
+  std::mutex mu;
+};
+
+namespace {
+
+template <typename T>
+const T* dptr(const dp_model* m, int64_t off) {
+  return off < 0 ? nullptr : reinterpret_cast<const T*>(m->data_dev + off);
+}
+
+int round_up(int a, int b) { return (a + b - 1) / b * b; }
+
+void fill_entries(int kind, dp::TapEntry* e, int* n) {
+  if (kind == 1) {
+    e[0] = {0, 0, 0, 0};
+    *n = 1;
+  } else if (kind == 3) {
+    for (int ky = 0; ky < 3; ++ky)
+      for (int kx = 0; kx < 3; ++kx) e[ky * 3 + kx] = {(int8_t)(ky - 1), (int8_t)(kx - 1), 0, 0};
+    *n = 9;
+  } else {  // up2: phase (a,b), tap (ty,tx): input offset (a-1+ty, b-1+tx)
+    for (int ph = 0; ph < 4; ++ph)
+      for (int t = 0; t < 4; ++t) {
+        const int a = ph >> 1, b = ph & 1, ty = t >> 1, tx = t & 1;
+        e[ph * 4 + t] = {(int8_t)(a - 1 + ty), (int8_t)(b - 1 + tx), (int8_t)ph, 0};
+      }
+    *n = 16;
+  }
+}
+
+int plan_conv(dp_model* m, const BlobOp& op, int B, Launch& L) {
+  using namespace dp;
+  const BlobBuf& ib = m->bufs[op.in_buf];
+  const int H = ib.H, W = ib.W;
+  const bool up2 = op.kind == 4;
+  ConvParams& p = L.cp;
+  memset(&p, 0, sizeof p);
+  int n_entries_total = 0;
+  TapEntry table[kMaxEntries];
+  fill_entries(op.kind, table, &n_entries_total);
+
+  // ---- naive description (always built; used when the naive_conv option is on)
+  NaiveConvParams& q = L.np;
+  memset(&q, 0, sizeof q);
+  q.n_img = B; q.H = H; q.W = W; q.Cin = op.cin; q.in_ctot = ib.C; q.in_choff = op.in_choff;
+  q.Cout = op.cout;
+  q.n_entries_total = n_entries_total; q.n_groups = up2 ? 4 : 1; q.up2 = up2;
+  q.relu = op.relu; q.pro_mode = op.pro;
+  memcpy(q.entries, table, sizeof table);
+  q.in = m->buf_dev[op.in_buf];
+  q.w = dptr<__half>(m, op.w_off);
+  q.epi_scale = dptr<float>(m, op.epi_scale_off);
+  q.epi_shift = dptr<float>(m, op.epi_shift_off);
+  q.pro_scale = dptr<float>(m, op.pro_scale_off);
+  q.pro_shift = dptr<float>(m, op.pro_shift_off);
+  if (op.head) {
+    q.out = m->scratch_head; q.out_ctot = op.cout; q.out_choff = 0;
+  } else {
+    q.out = m->buf_dev[op.out_buf]; q.out_ctot = m->bufs[op.out_buf].C; q.out_choff = op.out_choff;
+  }
+  L.head_C = op.cout;
+
+  // ---- tensor-core plan
+  p.n_img = B; p.H = H; p.W = W; p.Cin = op.cin;
+  p.n_chunks = (op.cin + 63) / 64;
+  p.up2 = up2;
+  p.relu = op.relu;
+  p.pro_relu = op.pro == 2;
+  p.desc_base_mode = m->desc_base_mode;
+  p.epi_mode = op.head ? EPI_HEAD : EPI_STORE;
+  p.epi_scale = q.epi_scale; p.epi_shift = q.epi_shift;
+  p.pro_scale = q.pro_scale; p.pro_shift = q.pro_shift;
+  p.head_w = dptr<float>(m, op.head_w_off);
+  p.head_b = op.head_b;
+  p.P = m->patch;
+  if (!op.head) {
+    p.out = m->buf_dev[op.out_buf];
+    p.out_ctot = m->bufs[op.out_buf].C;
+    p.out_choff = op.out_choff;
+  }
+  L.prologue = op.pro != 0;
+  if (op.cout % 16) return fail("conv: Cout %d not a multiple of 16", op.cout);
+  if (op.cin % 8) return fail("conv: Cin %d not a multiple of 8", op.cin);
+
+  const int groups_if_h = up2 ? 4 : 1;
+  if (op.kind == 1) {
+    p.mode = MODE_D;
+  } else if (H >= 16 && H % 16 == 0 && W % 8 == 0) {
+    p.mode = MODE_H;
+  } else {
+    if (H * W > 128 || 128 % (H * W)) return fail("conv: map %dx%d unsupported (need H*W | 128 or H %% 16 == 0)", H, W);
+    p.mode = MODE_T;
+  }
+  if (L.prologue && p.mode != MODE_D) return fail("conv: pre-activation prologue only supported for 1x1 convs");
+  if (op.head && (up2 || op.cout > 256)) return fail("conv: fused head needs a plain conv with Cout <= 256");
+
+  p.n_groups = (p.mode == MODE_H) ? groups_if_h : 1;
+  p.n_phase_items = (p.mode == MODE_T && up2) ? 4 : 1;
+  p.n_entries = (p.mode == MODE_T && up2) ? 4 : n_entries_total;
+  memcpy(p.entries, table, sizeof table);
+  if (p.mode == MODE_T)
+    for (int i = 0; i < kMaxEntries; ++i) p.entries[i].group = 0;
+
+  // N tile: whole Cout if the accumulators fit, otherwise the largest multiple-of-16 divisor that does.
+  int n_tile = op.cout;
+  int max_cols = kTmemCols / p.n_groups;
+  if (op.head) max_cols = max_cols < 256 ? max_cols : 256;
+  while (n_tile > 256 || n_tile > max_cols || op.cout % n_tile || n_tile % 16) {
+    n_tile -= 16;
+    if (n_tile < 16) return fail("conv: no valid N tile for Cout %d", op.cout);
+  }
+  p.n_tile = n_tile;
+  p.n_ntiles = op.cout / n_tile;
+
+  // sub-tiles per CTA tile
+  const long long m_total = (long long)B * H * W;
+  if (p.mode == MODE_D) {
+    p.m_total = (int)m_total;
+    int sub = 4;
+    while (sub > 1 && (sub * n_tile > kTmemCols ||
+                       ((m_total + sub * 128 - 1) / (sub * 128)) * p.n_ntiles < m->num_sms))
+      sub >>= 1;
+    p.sub = sub;
+    p.n_mtiles = (int)((m_total + sub * 128 - 1) / (sub * 128));
+    p.a_stage_bytes = sub * kATileBytes;
+    p.a_tx_bytes = p.a_stage_bytes;
+  } else if (p.mode == MODE_T) {
+    p.sub = 1;
+    p.box_w = W; p.box_h = H; p.box_n = 128 / (H * W);
+    p.tiles_w = 1; p.tiles_h = 1;
+    p.n_mtiles = (B + p.box_n - 1) / p.box_n;
+    p.a_stage_bytes = kATileBytes;
+    p.a_tx_bytes = kATileBytes;
+  } else {
+    int sub = (W % 16 == 0) ? 2 : 1;
+    while (sub > 1 && (p.n_groups * sub * n_tile > kTmemCols)) sub >>= 1;
+    // prefer more CTAs over wider regions when the layer cannot fill the GPU
+    if (sub == 2 && (long long)B * (H / 16) * (W / 16) * p.n_ntiles < m->num_sms) sub = 1;
+    p.sub = sub;
+    p.box_w = m->halo_pad8 ? round_up(8 * sub + 2, 8) : 8 * sub + 2;
+    p.box_h = 18; p.box_n = 1;
+    p.tiles_w = W / (8 * sub); p.tiles_h = H / 16;
+    p.n_mtiles = B * p.tiles_w * p.tiles_h;
+    p.a_tx_bytes = p.box_w * p.box_h * 128;
+    p.a_stage_bytes = round_up(p.a_tx_bytes, 1024);
+  }
+  p.n_items = p.n_mtiles * p.n_ntiles * p.n_phase_items;
+  p.b_stage_bytes = n_tile * 128;
+  p.acc_stages = (2 * p.n_groups * p.sub * n_tile <= kTmemCols) ? 2 : 1;
+
+  // shared-memory ring depths
+  const int budget = 227 * 1024 - ConvSmemLayout::kBarBytes - 2 * op.cout * 4 - 2 * p.n_chunks * 64 * 4 - 256 * 4 -
+                     1024;
+  int a_stages = (p.mode == MODE_H) ? 2 : 4;
+  while (a_stages > 1 && a_stages * p.a_stage_bytes + 2 * p.b_stage_bytes > budget) --a_stages;
+  int b_stages = (budget - a_stages * p.a_stage_bytes) / p.b_stage_bytes;
+  if (b_stages > kMaxBStages) b_stages = kMaxBStages;
+  if (p.mode != MODE_H && b_stages > 6) b_stages = 6;
+  if (b_stages < 2) return fail("conv: shared memory budget exceeded (A %d B %d)", p.a_stage_bytes, p.b_stage_bytes);
+  // spend what is left on deeper A rings for the flat modes
+  if (p.mode != MODE_H) {
+    while (a_stages < kMaxAStages && (a_stages + 1) * p.a_stage_bytes + b_stages * p.b_stage_bytes <= budget &&
+           a_stages < 6)
+      ++a_stages;
+  }
+  p.a_stages = a_stages;
+  p.b_stages = b_stages;
+  L.smem = conv_smem_layout(p).total;
+  if (L.smem > 227 * 1024) return fail("conv: smem %d too large", L.smem);
+  const int rounds = (p.n_items + m->num_sms - 1) / m->num_sms;
+  L.grid = (p.n_items + rounds - 1) / rounds;
+
+  // executed MACs (tensor-core work actually issued, 16-wide K steps)
+  {
+    uint64_t ksteps = 0;
+    for (int c = 0; c < p.n_chunks; ++c) {
+      int ks = (op.cin - c * 64 + 15) / 16;
+      ksteps += ks > 4 ? 4 : ks;
+    }
+    L.macs = (uint64_t)m_total * op.cout * ksteps * 16 * (up2 ? 16 : n_entries_total);
+  }
+
+  // ---- tensor maps
+  const __half* in_base = m->buf_dev[op.in_buf] + op.in_choff;
+  const uint64_t cstride = (uint64_t)ib.C * 2;
+  if (p.mode == MODE_D) {
+    uint64_t dims[2] = {(uint64_t)op.cin, (uint64_t)m_total};
+    uint64_t str[1] = {cstride};
+    uint32_t box[2] = {64, 128};
+    if (make_map(&L.map_a, in_base, 2, dims, str, box)) return 1;
+  } else {
+    uint64_t dims[4] = {(uint64_t)op.cin, (uint64_t)W, (uint64_t)H, (uint64_t)B};
+    uint64_t str[3] = {cstride, cstride * W, cstride * W * H};
+    uint32_t box[4] = {64, (uint32_t)p.box_w, (uint32_t)p.box_h, (uint32_t)p.box_n};
+    if (make_map(&L.map_a, in_base, 4, dims, str, box)) return 1;
+  }
+  {
+    uint64_t dims[3] = {(uint64_t)op.cin, (uint64_t)op.cout, (uint64_t)n_entries_total};
+    uint64_t str[2] = {(uint64_t)op.cin * 2, (uint64_t)op.cin * 2 * op.cout};
+    uint32_t box[3] = {64, (uint32_t)n_tile, 1};
+    if (make_map(&L.map_b, q.w, 3, dims, str, box)) return 1;
+  }
+  return 0;
+}
+
+int get_plan(dp_model* m, int B, Plan** out) {
+  std::lock_guard<std::mutex> lk(m->mu);
+  auto it = m->plans.find(B);
+  if (it != m->plans.end()) {
+    *out = &it->second;
+    return 0;
+  }
+  Plan plan;
+  plan.launches.resize(m->ops.size());
+  for (size_t i = 0; i < m->ops.size(); ++i) {
+    plan.launches[i].type = m->ops[i].type;
+    if (m->ops[i].type == OP_CONV)
+      if (plan_conv(m, m->ops[i], B, plan.launches[i])) {
+        g_err = "op " + std::to_string(i) + ": " + g_err;
+        return 1;
+      }
+  }
+  auto res = m->plans.emplace(B, std::move(plan));
+  *out = &res.first->second;
+  return 0;
+}
+
+int grid_for(long long total, int threads) {
+  long long g = (total + threads - 1) / threads;
+  const long long cap = 148LL * 32;
+  return (int)(g < 1 ? 1 : (g > cap ? cap : g));
+}
+
+struct PassArgs {
+  const uint8_t* slide = nullptr;
+  long long slide_h = 0;
+  const int32_t* coords = nullptr;
+  int tta_in = 0, tta_out = 0;
+  float* probs_out = nullptr;
+};
+
+int run_op(dp_model* m, Plan* plan, int i, int B, const PassArgs& a, cudaStream_t st) {
+  const BlobOp& op = m->ops[i];
+  Launch& L = plan->launches[i];
+  switch (op.type) {
+    case OP_STEM_IM2COL: {
+      if (!a.slide || !a.coords) return fail("stem op needs a slide and tile coordinates");
+      const BlobBuf& ob = m->bufs[op.out_buf];
+      if (ob.C != 160 || ob.H != m->patch / 2) return fail("stem im2col buffer must be [P/2][P/2][160]");
+      const long long total = (long long)B * ob.H * ob.W * 20;
+      dp::stem_im2col_kernel<<<grid_for(total, 256), 256, 0, st>>>(a.slide, a.slide_h, a.coords, B, m->patch,
+                                                                   a.tta_in, m->buf_dev[op.out_buf]);
+      LAUNCH_OK();
+      return 0;
+    }
+    case OP_MAXPOOL: {
+      const BlobBuf& ib = m->bufs[op.in_buf];
+      const BlobBuf& ob = m->bufs[op.out_buf];
+      const long long total = (long long)B * (ib.H / 2) * (ib.W / 2) * (op.cin / 8);
+      dp::maxpool3s2_kernel<<<grid_for(total, 256), 256, 0, st>>>(m->buf_dev[op.in_buf], ib.C, op.in_choff,
+                                                                  m->buf_dev[op.out_buf], ob.C, op.out_choff, B,
+                                                                  ib.H, ib.W, op.cin);
+      LAUNCH_OK();
+      return 0;
+    }
+    case OP_BNPOOL: {
+      const BlobBuf& ib = m->bufs[op.in_buf];
+      const BlobBuf& ob = m->bufs[op.out_buf];
+      const int OH = op.pool ? ib.H / 2 : ib.H, OW = op.pool ? ib.W / 2 : ib.W;
+      const long long total = (long long)B * OH * OW * (op.cin / 8);
+      dp::bn_act_pool_kernel<<<grid_for(total, 256), 256, 0, st>>>(
+          m->buf_dev[op.in_buf], ib.C, op.in_choff, m->buf_dev[op.out_buf], ob.C, op.out_choff, B, ib.H, ib.W,
+          op.cin, dptr<float>(m, op.epi_scale_off), dptr<float>(m, op.epi_shift_off), op.relu, op.pool);
+      LAUNCH_OK();
+      return 0;
+    }
+    case OP_CONV: {
+      if (op.head && !a.probs_out) return fail("head op needs a probability output buffer");
+      if (m->naive_conv) {
+        const long long total = (long long)B * L.np.H * L.np.W * L.np.n_groups * L.np.Cout;
+        dp::conv_naive_kernel<<<grid_for(total, 256), 256, 0, st>>>(L.np);
+        LAUNCH_OK();
+        if (op.head) {
+          const long long tot = (long long)B * m->patch * m->patch;
+          dp::head_naive_kernel<<<grid_for(tot, 256), 256, 0, st>>>(m->scratch_head, op.cout, 0, op.cout, B,
+                                                                    m->patch, dptr<float>(m, op.head_w_off),
+                                                                    op.head_b, a.tta_out, a.probs_out);
+          LAUNCH_OK();
+        }
+        return 0;
+      }
+      dp::ConvParams cp = L.cp;
+      cp.desc_base_mode = m->desc_base_mode;
+      if (op.head) {
+        cp.tta_code = a.tta_out;
+        cp.head_out = a.probs_out;
+      }
+      if (L.prologue) {
+        CU_OK(cudaFuncSetAttribute(dp::conv_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, L.smem));
+        dp::conv_tc_kernel<true><<<L.grid, 384, L.smem, st>>>(L.map_a, L.map_b, cp);
+      } else {
+        CU_OK(cudaFuncSetAttribute(dp::conv_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, L.smem));
+        dp::conv_tc_kernel<false><<<L.grid, 256, L.smem, st>>>(L.map_a, L.map_b, cp);
+      }
+      LAUNCH_OK();
+      return 0;
+    }
+    default:
+      return fail("unknown op type %d", op.type);
+  }
+}
+
+int check_model(const dp_model* m) {
+  if (!m) return fail("null model");
+  return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int dp_abi_version(void) { return 1; }
+
+const char* dp_last_error(void) { return g_err.c_str(); }
+
+uint64_t dp_kernel_launch_count(void) { return g_launches.load(); }
+
+void dp_d4_src(int code, int i, int j, int P, int* a, int* b) { dp::d4_src(code, i, j, P, *a, *b); }
+
+int dp_model_create(const void* blob, size_t nbytes, int device, int max_batch, dp_model** out) {
+  if (!blob || !out) return fail("null argument");
+  if (nbytes < sizeof(BlobHeader)) return fail("container too small");
+  const uint8_t* bytes = static_cast<const uint8_t*>(blob);
+  BlobHeader h;
+  memcpy(&h, bytes, sizeof h);
+  if (memcmp(h.magic, "DPB1", 4) || h.version != 1) return fail("not a DPB1 v1 container");
+  if (h.total_bytes != nbytes) return fail("container size mismatch: header says %llu, got %zu",
+                                           (unsigned long long)h.total_bytes, nbytes);
+  const size_t tab = sizeof h + (size_t)h.n_bufs * sizeof(BlobBuf) + (size_t)h.n_ops * sizeof(BlobOp);
+  if (tab > h.data_off || h.data_off > nbytes) return fail("container tables out of range");
+  if (max_batch < 1) return fail("max_batch must be >= 1");
+  int ndev = 0;
+  CU_OK(cudaGetDeviceCount(&ndev));
+  if (device < 0 || device >= ndev) return fail("CUDA device %d not available (%d devices)", device, ndev);
+  CU_OK(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CU_OK(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10) return fail("this library is built for sm_100a only; device is sm_%d%d", prop.major, prop.minor);
+
+  dp_model* m = new dp_model;
+  m->device = device;
+  m->max_batch = max_batch;
+  m->patch = (int)h.patch;
+  m->num_sms = prop.multiProcessorCount;
+  m->bufs.resize(h.n_bufs);
+  m->ops.resize(h.n_ops);
+  memcpy(m->bufs.data(), bytes + sizeof h, h.n_bufs * sizeof(BlobBuf));
+  memcpy(m->ops.data(), bytes + sizeof h + h.n_bufs * sizeof(BlobBuf), h.n_ops * sizeof(BlobOp));
+  for (const BlobOp& op : m->ops) {
+    if (op.in_buf >= (int)h.n_bufs || op.out_buf >= (int)h.n_bufs) {
+      delete m;
+      return fail("op references a buffer out of range");
+    }
+  }
+  m->data_bytes = nbytes - h.data_off;
+  auto cleanup = [&]() { dp_model_destroy(m); };
+  cudaError_t e = cudaMalloc(&m->data_dev, m->data_bytes ? m->data_bytes : 256);
+  if (e != cudaSuccess) { cleanup(); return fail("cudaMalloc weights: %s", cudaGetErrorString(e)); }
+  m->device_bytes += m->data_bytes;
+  e = cudaMemcpy(m->data_dev, bytes + h.data_off, m->data_bytes, cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) { cleanup(); return fail("cudaMemcpy weights: %s", cudaGetErrorString(e)); }
+  m->buf_dev.assign(h.n_bufs, nullptr);
+  for (uint32_t i = 0; i < h.n_bufs; ++i) {
+    const BlobBuf& b = m->bufs[i];
+    if (b.C % 8) { cleanup(); return fail("buffer %u: channel count %d not a multiple of 8", i, b.C); }
+    const size_t sz = (size_t)max_batch * b.H * b.W * b.C * 2;
+    e = cudaMalloc(&m->buf_dev[i], sz);
+    if (e != cudaSuccess) { cleanup(); return fail("cudaMalloc buffer %u (%zu B): %s", i, sz, cudaGetErrorString(e)); }
+    cudaMemset(m->buf_dev[i], 0, sz);
+    m->device_bytes += sz;
+  }
+  {
+    size_t sz = 0;
+    for (const BlobOp& op : m->ops)
+      if (op.type == OP_CONV && op.head) sz = (size_t)max_batch * m->patch * m->patch * op.cout * 2;
+    if (sz) {
+      e = cudaMalloc(&m->scratch_head, sz);
+      if (e != cudaSuccess) { cleanup(); return fail("cudaMalloc head scratch: %s", cudaGetErrorString(e)); }
+      m->device_bytes += sz;
+    }
+  }
+  const char* env = getenv("DP_NAIVE_CONV");
+  if (env && atoi(env)) m->naive_conv = 1;
+  env = getenv("DP_DESC_BASE_MODE");
+  if (env) m->desc_base_mode = atoi(env);
+  *out = m;
+  return 0;
+}
+
+int dp_model_destroy(dp_model* m) {
+  if (!m) return 0;
+  cudaSetDevice(m->device);
+  cudaDeviceSynchronize();
+  for (__half* p : m->buf_dev)
+    if (p) cudaFree(p);
+  if (m->scratch_head) cudaFree(m->scratch_head);
+  if (m->data_dev) cudaFree(m->data_dev);
+  delete m;
+  return 0;
+}
+
+int dp_model_info(const dp_model* m, int* patch, int* max_batch, uint64_t* device_bytes) {
+  if (check_model(m)) return 1;
+  if (patch) *patch = m->patch;
+  if (max_batch) *max_batch = m->max_batch;
+  if (device_bytes) *device_bytes = m->device_bytes;
+  return 0;
+}
+
+int dp_model_set_option(dp_model* m, const char* key, int value) {
+  if (check_model(m) || !key) return fail("null argument");
+  if (!strcmp(key, "naive_conv")) m->naive_conv = value;
+  else if (!strcmp(key, "desc_base_mode")) m->desc_base_mode = value;
+  else if (!strcmp(key, "halo_pad8")) {
+    std::lock_guard<std::mutex> lk(m->mu);
+    m->halo_pad8 = value;
+    m->plans.clear();  // tile shapes depend on it
+  }
+  else return fail("unknown option '%s'", key);
+  return 0;
+}
+
+int dp_model_program_size(const dp_model* m, int* n_ops, int* n_bufs) {
+  if (check_model(m)) return 1;
+  if (n_ops) *n_ops = (int)m->ops.size();
+  if (n_bufs) *n_bufs = (int)m->bufs.size();
+  return 0;
+}
+
+int dp_model_buffer_shape(const dp_model* m, int buf, int* h, int* w, int* c) {
+  if (check_model(m)) return 1;
+  if (buf < 0 || buf >= (int)m->bufs.size()) return fail("buffer %d out of range", buf);
+  if (h) *h = m->bufs[buf].H;
+  if (w) *w = m->bufs[buf].W;
+  if (c) *c = m->bufs[buf].C;
+  return 0;
+}
+
+static int run_range(dp_model* m, int B, int op_begin, int op_end, const PassArgs& a, void* stream) {
+  if (check_model(m)) return 1;
+  if (B < 1 || B > m->max_batch) return fail("n_tiles %d outside [1, %d]", B, m->max_batch);
+  if (op_begin < 0 || op_end > (int)m->ops.size() || op_begin > op_end) return fail("op range out of bounds");
+  CU_OK(cudaSetDevice(m->device));
+  Plan* plan = nullptr;
+  if (get_plan(m, B, &plan)) return 1;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  for (int i = op_begin; i < op_end; ++i)
+    if (run_op(m, plan, i, B, a, st)) {
+      g_err = "op " + std::to_string(i) + ": " + g_err;
+      return 1;
+    }
+  return 0;
+}
+
+int dp_forward_tiles(dp_model* m, const uint8_t* slide, int64_t slide_w, int64_t slide_h, const int32_t* coords,
+                     int n_tiles, int tta_in, int tta_out, float* probs_out, void* stream) {
+  if (!slide || !coords || !probs_out) return fail("null argument");
+  if (slide_w < 1 || slide_h < 1) return fail("bad slide extent");
+  if ((tta_in | tta_out) & ~7) return fail("D4 codes must be in [0, 8)");
+  PassArgs a;
+  a.slide = slide; a.slide_h = slide_h; a.coords = coords;
+  a.tta_in = tta_in; a.tta_out = tta_out; a.probs_out = probs_out;
+  return run_range(m, n_tiles, 0, m ? (int)m->ops.size() : 0, a, stream);
+}
+
+int dp_debug_run_ops(dp_model* m, int n_tiles, int op_begin, int op_end, int tta_out, float* probs_out,
+                     void* stream) {
+  PassArgs a;
+  a.tta_out = tta_out; a.probs_out = probs_out;
+  return run_range(m, n_tiles, op_begin, op_end, a, stream);
+}
+
+int dp_debug_read_buffer(dp_model* m, int buf, int n_tiles, void* host, size_t nbytes) {
+  if (check_model(m) || !host) return fail("null argument");
+  if (buf < 0 || buf >= (int)m->bufs.size()) return fail("buffer %d out of range", buf);
+  const BlobBuf& b = m->bufs[buf];
+  const size_t need = (size_t)n_tiles * b.H * b.W * b.C * 2;
+  if (n_tiles > m->max_batch || nbytes != need) return fail("size mismatch: need %zu bytes, got %zu", need, nbytes);
+  CU_OK(cudaSetDevice(m->device));
+  CU_OK(cudaDeviceSynchronize());
+  CU_OK(cudaMemcpy(host, m->buf_dev[buf], need, cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+int dp_debug_write_buffer(dp_model* m, int buf, int n_tiles, const void* host, size_t nbytes) {
+  if (check_model(m) || !host) return fail("null argument");
+  if (buf < 0 || buf >= (int)m->bufs.size()) return fail("buffer %d out of range", buf);
+  const BlobBuf& b = m->bufs[buf];
+  const size_t need = (size_t)n_tiles * b.H * b.W * b.C * 2;
+  if (n_tiles > m->max_batch || nbytes != need) return fail("size mismatch: need %zu bytes, got %zu", need, nbytes);
+  CU_OK(cudaSetDevice(m->device));
+  CU_OK(cudaDeviceSynchronize());
+  CU_OK(cudaMemcpy(m->buf_dev[buf], host, need, cudaMemcpyHostToDevice));
+  return 0;
+}
+
+int dp_model_executed_macs(const dp_model* m, int n_tiles, uint64_t* macs) {
+  if (check_model(m) || !macs) return fail("null argument");
+  Plan* plan = nullptr;
+  if (get_plan(const_cast<dp_model*>(m), n_tiles, &plan)) return 1;
+  uint64_t t = 0;
+  for (const Launch& L : plan->launches) t += L.macs;
+  *macs = t;
+  return 0;
+}
+
+int dp_stitch(const float* probs, int n_pass, int n_tiles, int patch, const int32_t* coords, float* mean,
+              float* var, uint8_t* count, int64_t plane_w, int64_t plane_h, int64_t x_lo, void* stream) {
+  if (!probs || !coords || !mean || !var || !count) return fail("null argument");
+  if (n_pass < 1 || n_tiles < 1 || patch < 1 || plane_w < patch || plane_h < patch) return fail("bad stitch geometry");
+  if (n_tiles > 4096) return fail("at most 4096 tiles per stitch call");
+  dim3 grid((patch * patch + 255) / 256, n_tiles);
+  dp::stitch_kernel<<<grid, 256, 2 * n_tiles * sizeof(int), static_cast<cudaStream_t>(stream)>>>(
+      probs, n_pass, n_tiles, patch, coords, mean, var, count, plane_h, (int)x_lo);
+  LAUNCH_OK();
+  return 0;
+}
+
+int dp_finalize(float* mean, float* var, uint8_t* count, int64_t n, float threshold, uint8_t* label, void* stream) {
+  if (!mean || !var || !count) return fail("null argument");
+  if (n < 1) return fail("empty plane");
+  if ((reinterpret_cast<uintptr_t>(mean) | reinterpret_cast<uintptr_t>(var) | reinterpret_cast<uintptr_t>(count) |
+       reinterpret_cast<uintptr_t>(label)) & 15)
+    return fail("plane pointers must be 16-byte aligned");
+  dp::finalize_kernel<<<grid_for((n + 15) / 16, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      mean, var, count, n, threshold, label);
+  LAUNCH_OK();
+  return 0;
+}
+
+int dp_pyramid_down2(const float* in, int64_t w, int64_t h, float* out, void* stream) {
+  if (!in || !out) return fail("null argument");
+  if (w < 2 || h < 2) return fail("plane too small");
+  dp::pyramid_down2_kernel<<<grid_for((w / 2) * (h / 2), 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(in, w, h,
+                                                                                                          out);
+  LAUNCH_OK();
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,171 @@
+"""Device-side tile model: the object that stands where the reference's Keras ``Model`` stood.
+
+``TileModel.predict`` mirrors ``models[name].predict(image_patches, batch_size=...)``
+(DigiPathAI/Segmentation.py:154-156): host float32 ``[B,P,P,3]`` in [-1,1] in, host float32 ``[B,P,P,2]``
+softmax out.  ``forward_tiles`` is the resident path the B200 ``get_prediction`` loop uses: tiles are cropped
+from the slide raster already in HBM, and the softmax channel-1 plane stays on the device for the stitch.
+
+PyTorch is used for device memory and streams only; all arithmetic happens in libdigipath_b200.so.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+from .program import Program, serialize
+
+
+def _stream_ptr():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+class TileModel:
+    def __init__(self, program: Program | bytes, device: int = 0, max_batch: int = 32):
+        if not torch.cuda.is_available():
+            raise RuntimeError("digipathai_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+        blob = program if isinstance(program, (bytes, bytearray)) else serialize(program)
+        self.program = program if isinstance(program, Program) else None
+        self.device = int(device)
+        self.max_batch = int(max_batch)
+        self._h = _lib.c_model_p()
+        buf = (C.c_char * len(blob)).from_buffer_copy(blob)
+        _lib.check(_lib.lib.dp_model_create(buf, len(blob), self.device, self.max_batch, C.byref(self._h)),
+                   "dp_model_create")
+        p, mb, nb = C.c_int(), C.c_int(), C.c_uint64()
+        _lib.check(_lib.lib.dp_model_info(self._h, C.byref(p), C.byref(mb), C.byref(nb)))
+        self.patch, self.device_bytes = p.value, nb.value
+        self._tile_coords = {}
+
+    # ------------------------------------------------------------------ lifetime
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            _lib.lib.dp_model_destroy(self._h)
+            self._h = _lib.c_model_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------ hot path
+    def forward_tiles(self, slide: torch.Tensor, coords: torch.Tensor, tta_in: int = 0, tta_out: int = 0,
+                      out: torch.Tensor | None = None) -> torch.Tensor:
+        """slide: cuda uint8 [W,H,3] ([x,y,c]); coords: cuda int32 [B,2]; returns cuda float32 [B,P,P]."""
+        assert slide.is_cuda and slide.dtype == torch.uint8 and slide.dim() == 3 and slide.shape[2] == 3
+        assert slide.is_contiguous() and coords.is_cuda and coords.dtype == torch.int32 and coords.is_contiguous()
+        B = coords.shape[0]
+        if out is None:
+            out = torch.empty((B, self.patch, self.patch), dtype=torch.float32, device=slide.device)
+        assert out.is_contiguous() and out.dtype == torch.float32 and out.numel() == B * self.patch * self.patch
+        _lib.check(
+            _lib.lib.dp_forward_tiles(self._h, C.c_void_p(slide.data_ptr()), slide.shape[0], slide.shape[1],
+                                      C.c_void_p(coords.data_ptr()), B, int(tta_in), int(tta_out),
+                                      C.c_void_p(out.data_ptr()), _stream_ptr()),
+            "dp_forward_tiles")
+        return out
+
+    def _coords_for_batch(self, B: int, device) -> torch.Tensor:
+        key = (B, str(device))
+        if key not in self._tile_coords:
+            c = torch.zeros((B, 2), dtype=torch.int32)
+            c[:, 0] = torch.arange(B, dtype=torch.int32) * self.patch
+            self._tile_coords[key] = c.to(device)
+        return self._tile_coords[key]
+
+    def forward_tile_batch(self, tiles: torch.Tensor, tta_in: int = 0, tta_out: int = 0,
+                           out: torch.Tensor | None = None) -> torch.Tensor:
+        """tiles: cuda uint8 [B,P,P,3] already gathered -> cuda float32 [B,P,P]."""
+        B, P = tiles.shape[0], self.patch
+        assert tiles.shape[1:] == (P, P, 3)
+        return self.forward_tiles(tiles.reshape(B * P, P, 3), self._coords_for_batch(B, tiles.device), tta_in,
+                                  tta_out, out)
+
+    def predict(self, image_patches, batch_size=None, verbose=0, steps=None) -> np.ndarray:
+        """Keras-``Model.predict``-shaped entry: host array in, host softmax ``[B,P,P,2]`` out.
+
+        Accepts the reference's float32 tiles in [-1,1] (exact multiples of 1/128, as produced by
+        ``(img - 128.0)/128.0`` in dataloader.py:383-388) or the raw uint8 tiles.
+        """
+        x = np.asarray(image_patches)
+        if x.dtype != np.uint8:
+            u = np.rint(x.astype(np.float32) * 128.0 + 128.0)
+            if np.abs(u - (x * 128.0 + 128.0)).max() > 1e-3 or u.min() < 0 or u.max() > 255:
+                raise ValueError("predict() expects tiles normalised as (uint8 - 128)/128")
+            x = u.astype(np.uint8)
+        dev = torch.device("cuda", self.device)
+        out = np.empty(x.shape[:3] + (2,), dtype=np.float32)
+        step = self.max_batch
+        for s in range(0, x.shape[0], step):
+            t = torch.from_numpy(np.ascontiguousarray(x[s:s + step])).pin_memory().to(dev, non_blocking=True)
+            p1 = self.forward_tile_batch(t).cpu().numpy()
+            out[s:s + step, ..., 1] = p1
+            out[s:s + step, ..., 0] = 1.0 - p1
+        return out
+
+    # ------------------------------------------------------------------ introspection / debugging
+    def set_option(self, key: str, value: int):
+        _lib.check(_lib.lib.dp_model_set_option(self._h, key.encode(), int(value)))
+
+    def buffer_shape(self, buf: int):
+        h, w, c = C.c_int(), C.c_int(), C.c_int()
+        _lib.check(_lib.lib.dp_model_buffer_shape(self._h, buf, C.byref(h), C.byref(w), C.byref(c)))
+        return h.value, w.value, c.value
+
+    def read_buffer(self, buf: int, n_tiles: int) -> np.ndarray:
+        h, w, c = self.buffer_shape(buf)
+        a = np.empty((n_tiles, h, w, c), dtype=np.float16)
+        _lib.check(_lib.lib.dp_debug_read_buffer(self._h, buf, n_tiles, a.ctypes.data_as(C.c_void_p), a.nbytes))
+        return a
+
+    def write_buffer(self, buf: int, arr: np.ndarray):
+        a = np.ascontiguousarray(arr, dtype=np.float16)
+        _lib.check(_lib.lib.dp_debug_write_buffer(self._h, buf, a.shape[0], a.ctypes.data_as(C.c_void_p), a.nbytes))
+
+    def run_ops(self, n_tiles: int, op_begin: int, op_end: int, tta_out: int = 0, probs: torch.Tensor | None = None):
+        ptr = C.c_void_p(probs.data_ptr()) if probs is not None else C.c_void_p(None)
+        _lib.check(_lib.lib.dp_debug_run_ops(self._h, n_tiles, op_begin, op_end, int(tta_out), ptr, _stream_ptr()),
+                   "dp_debug_run_ops")
+
+    def executed_macs(self, n_tiles: int) -> int:
+        v = C.c_uint64()
+        _lib.check(_lib.lib.dp_model_executed_macs(self._h, n_tiles, C.byref(v)))
+        return v.value
+
+
+# ---------------------------------------------------------------------- slide-plane kernels
+def stitch(probs: torch.Tensor, coords: torch.Tensor, mean: torch.Tensor, var: torch.Tensor, count: torch.Tensor,
+           x_lo: int = 0):
+    """probs cuda f32 [N,B,P,P]; coords cuda int32 [B,2]; planes cuda [w,h] (Segmentation.py:162-173)."""
+    N, B, P, _ = probs.shape
+    assert probs.is_contiguous() and mean.is_contiguous() and var.is_contiguous() and count.is_contiguous()
+    assert mean.dtype == torch.float32 and var.dtype == torch.float32 and count.dtype == torch.uint8
+    _lib.check(
+        _lib.lib.dp_stitch(C.c_void_p(probs.data_ptr()), N, B, P, C.c_void_p(coords.data_ptr()),
+                           C.c_void_p(mean.data_ptr()), C.c_void_p(var.data_ptr()), C.c_void_p(count.data_ptr()),
+                           mean.shape[0], mean.shape[1], int(x_lo), _stream_ptr()),
+        "dp_stitch")
+
+
+def finalize(mean: torch.Tensor, var: torch.Tensor, count: torch.Tensor, threshold: float,
+             label: torch.Tensor | None = None):
+    """In-place normalise (Segmentation.py:175-177) and optional threshold to {0,255} (:336-337)."""
+    lp = C.c_void_p(label.data_ptr()) if label is not None else C.c_void_p(None)
+    _lib.check(
+        _lib.lib.dp_finalize(C.c_void_p(mean.data_ptr()), C.c_void_p(var.data_ptr()), C.c_void_p(count.data_ptr()),
+                             mean.numel(), float(np.float32(threshold)), lp, _stream_ptr()),
+        "dp_finalize")
+
+
+def pyramid_down2(plane: torch.Tensor) -> torch.Tensor:
+    w, h = plane.shape
+    out = torch.empty((w // 2, h // 2), dtype=torch.float32, device=plane.device)
+    _lib.check(_lib.lib.dp_pyramid_down2(C.c_void_p(plane.data_ptr()), w, h, C.c_void_p(out.data_ptr()), _stream_ptr()))
+    return out
+
+
+def kernel_launch_count() -> int:
+    return int(_lib.lib.dp_kernel_launch_count())

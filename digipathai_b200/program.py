@@ -1,0 +1,183 @@
+"""Layer program + flat model container ("DPB1").
+
+The reference builds Keras graphs in Python (DigiPathAI/models/*.py) and loads ``.h5`` weights into them
+(DigiPathAI/helpers/utils.py:427-448).  Here a graph builder emits a *layer program* -- a list of ops over
+NHWC fp16 buffers -- and this module packs it, together with the fp16 weights and the folded BatchNorm
+affine terms, into one flat little-endian container that ``dp_model_create`` (csrc/runtime.cu) executes.
+
+Container layout (must match ``BlobHeader`` / ``BlobBuf`` / ``BlobOp`` in csrc/runtime.cu)::
+
+    header  72 B : 'DPB1' | u32 version=1 | u32 n_bufs | u32 n_ops | u32 patch | u32 0 | u64 data_off
+                   | u64 total_bytes | 4 x u64 0
+    n_bufs x 16 B: i32 H, W, C, 0                      (per-image activation buffer geometry)
+    n_ops  x 128 B: 12 x i32 (type in_buf in_choff cin out_buf out_choff cout kind relu pro head pool)
+                   | f32 head_b | 3 x i32 0 | 8 x i64 offsets into the data section (-1 = absent):
+                     w, epi_scale, epi_shift, pro_scale, pro_shift, head_w, 0, 0
+    data section : 256-byte aligned arrays (fp16 weights [entries][Cout][Cin]; fp32 vectors)
+"""
+from __future__ import annotations
+
+import struct
+from dataclasses import dataclass, field
+from typing import List, Optional
+
+import numpy as np
+
+OP_STEM_IM2COL, OP_MAXPOOL, OP_CONV, OP_BNPOOL = 1, 2, 3, 4
+KIND_1X1, KIND_3X3, KIND_UP2 = 1, 3, 4
+PRO_NONE, PRO_AFFINE, PRO_AFFINE_RELU = 0, 1, 2
+
+
+@dataclass
+class Op:
+    type: int
+    in_buf: int = 0
+    in_choff: int = 0
+    cin: int = 0
+    out_buf: int = 0
+    out_choff: int = 0
+    cout: int = 0
+    kind: int = 0
+    relu: int = 0
+    pro: int = 0
+    head: int = 0
+    pool: int = 0
+    head_b: float = 0.0
+    w: Optional[np.ndarray] = None          # fp16 [entries, cout, cin]
+    epi_scale: Optional[np.ndarray] = None  # fp32 [cout]  (BNPOOL: [cin])
+    epi_shift: Optional[np.ndarray] = None
+    pro_scale: Optional[np.ndarray] = None  # fp32 [ceil(cin/64)*64]
+    pro_shift: Optional[np.ndarray] = None
+    head_w: Optional[np.ndarray] = None     # fp32 [cout]
+    name: str = ""
+
+
+@dataclass
+class Program:
+    patch: int
+    bufs: List[tuple] = field(default_factory=list)  # (H, W, C)
+    ops: List[Op] = field(default_factory=list)
+    buf_names: List[str] = field(default_factory=list)
+
+    def add_buf(self, name: str, h: int, w: int, c: int) -> int:
+        assert c % 8 == 0, "channel strides must keep 16-byte alignment"
+        self.bufs.append((h, w, c))
+        self.buf_names.append(name)
+        return len(self.bufs) - 1
+
+    def buf(self, name: str) -> int:
+        return self.buf_names.index(name)
+
+    def op_index(self, name: str) -> int:
+        return [o.name for o in self.ops].index(name)
+
+
+# ----------------------------------------------------------------------------------------------- packing
+_UP2_ROWS = {(0, 0): (0,), (0, 1): (1, 2), (1, 0): (0, 1), (1, 1): (2,)}
+
+
+def pack_conv_weights(k_hwio: np.ndarray, kind: int) -> np.ndarray:
+    """HWIO Keras kernel -> fp16 [entries][Cout][Cin] in the tap order of csrc/runtime.cu:fill_entries.
+
+    KIND_UP2 implements ``UpSampling2D()`` followed by a 3x3 'same' conv (densenet.py:138-155) as four
+    sub-pixel phases: output pixel (2h+a, 2w+b) only ever sees input rows {h+a-1, h+a} and columns
+    {w+b-1, w+b}, so the 3x3 kernel collapses to a 2x2 kernel per phase whose taps are sums of the original
+    taps (summed in fp32, rounded once to fp16).
+    """
+    k = np.asarray(k_hwio, dtype=np.float32)
+    if kind == KIND_1X1:
+        assert k.shape[:2] == (1, 1)
+        w = k[0, 0].T[None]
+    elif kind == KIND_3X3:
+        assert k.shape[:2] == (3, 3)
+        w = np.stack([k[ky, kx].T for ky in range(3) for kx in range(3)])
+    elif kind == KIND_UP2:
+        assert k.shape[:2] == (3, 3)
+        ents = []
+        for ph in range(4):
+            a, b = ph >> 1, ph & 1
+            for t in range(4):
+                ty, tx = t >> 1, t & 1
+                acc = np.zeros(k.shape[2:], dtype=np.float32)
+                for ky in _UP2_ROWS[(a, ty)]:
+                    for kx in _UP2_ROWS[(b, tx)]:
+                        acc += k[ky, kx]
+                ents.append(acc.T)
+        w = np.stack(ents)
+    else:
+        raise ValueError(kind)
+    return np.ascontiguousarray(w).astype(np.float16)
+
+
+def pack_stem_weights(k_hwio: np.ndarray, kpad: int = 160) -> np.ndarray:
+    """7x7x3xCout stem kernel -> fp16 [1][Cout][kpad]; column (ky*7+kx)*3+c matches stem_im2col_kernel."""
+    k = np.asarray(k_hwio, dtype=np.float32)
+    kh, kw, ci, co = k.shape
+    w = np.zeros((1, co, kpad), dtype=np.float32)
+    w[0, :, : kh * kw * ci] = k.reshape(kh * kw * ci, co).T
+    return w.astype(np.float16)
+
+
+def bn_affine(gamma, beta, mean, var, eps):
+    """Inference BatchNorm as y = scale*x + shift (Keras: gamma*(x-mean)/sqrt(var+eps)+beta)."""
+    scale = (np.asarray(gamma, np.float64) / np.sqrt(np.asarray(var, np.float64) + eps))
+    shift = np.asarray(beta, np.float64) - np.asarray(mean, np.float64) * scale
+    return scale.astype(np.float32), shift.astype(np.float32)
+
+
+def pad64(v: np.ndarray) -> np.ndarray:
+    n = (len(v) + 63) // 64 * 64
+    out = np.zeros(n, dtype=np.float32)
+    out[: len(v)] = v
+    return out
+
+
+def serialize(prog: Program) -> bytes:
+    data = bytearray()
+
+    def put(arr: Optional[np.ndarray], dtype) -> int:
+        if arr is None:
+            return -1
+        a = np.ascontiguousarray(arr, dtype=dtype)
+        pad = (-len(data)) % 256
+        data.extend(b"\0" * pad)
+        off = len(data)
+        data.extend(a.tobytes())
+        return off
+
+    op_recs = []
+    for o in prog.ops:
+        if o.type == OP_CONV:
+            ents = {KIND_1X1: 1, KIND_3X3: 9, KIND_UP2: 16}[o.kind]
+            assert o.w is not None and o.w.shape == (ents, o.cout, o.cin), (o.name, o.w.shape, (ents, o.cout, o.cin))
+            assert o.cout % 16 == 0 and o.cin % 8 == 0, o.name
+            if o.pro:
+                assert o.pro_scale is not None and len(o.pro_scale) == (o.cin + 63) // 64 * 64, o.name
+            if o.head:
+                assert o.head_w is not None and len(o.head_w) == o.cout, o.name
+        offs = [
+            put(o.w, np.float16), put(o.epi_scale, np.float32), put(o.epi_shift, np.float32),
+            put(o.pro_scale, np.float32), put(o.pro_shift, np.float32), put(o.head_w, np.float32), 0, 0,
+        ]
+        op_recs.append(
+            struct.pack(
+                "<12if3i8q", o.type, o.in_buf, o.in_choff, o.cin, o.out_buf, o.out_choff, o.cout, o.kind, o.relu,
+                o.pro, o.head, o.pool, float(o.head_b), 0, 0, 0, *offs,
+            )
+        )
+    buf_recs = [struct.pack("<4i", h, w, c, 0) for (h, w, c) in prog.bufs]
+    tab = 72 + 16 * len(buf_recs) + 128 * len(op_recs)
+    data_off = (tab + 255) // 256 * 256
+    total = data_off + len(data)
+    header = struct.pack("<4s5I2Q4Q", b"DPB1", 1, len(buf_recs), len(op_recs), prog.patch, 0, data_off, total, 0, 0, 0, 0)
+    assert len(header) == 72
+    blob = bytearray(header)
+    for r in buf_recs:
+        blob.extend(r)
+    for r in op_recs:
+        assert len(r) == 128
+        blob.extend(r)
+    blob.extend(b"\0" * (data_off - len(blob)))
+    blob.extend(data)
+    assert len(blob) == total
+    return bytes(blob)

@@ -1,0 +1,126 @@
+/*
+ * digipath_b200.h -- C ABI of the B200-native replacement for DigiPathAI's tile-segmentation hot path.
+ *
+ * The reference (haranrk/DigiPathAI, pure Python on TensorFlow 1.x) has exactly one operator seam on this path:
+ *
+ *     prediction = models[model_name].predict(image_patches, batch_size=batch_size, ...)
+ *                                                            DigiPathAI/Segmentation.py:154-156
+ *
+ * surrounded by numpy glue for TTA (DigiPathAI/helpers/utils.py:487-522), the overlap accumulate
+ * (Segmentation.py:164-173), normalise (:175-177) and threshold (:336-337).  Each entry point below replaces
+ * one of those call sites; the citation on each says which.  The reference-side binding a maintainer would
+ * add (a ctypes stub inside DigiPathAI/Segmentation.py) is shown in INTEGRATION.md.
+ *
+ * Conventions
+ *   - plain C types only; every pointer documented as "device" is a CUDA device pointer owned by the caller
+ *     (e.g. a torch tensor's data_ptr()); "host" pointers are ordinary host memory.
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream). Calls are asynchronous on
+ *     that stream unless stated otherwise. No hidden allocation happens after dp_model_create/dp_model_reserve.
+ *   - every function returns 0 on success, non-zero on failure; dp_last_error() returns a thread-local,
+ *     human-readable message for the last failure on the calling thread.
+ *   - orientation follows the reference: planes and tiles are indexed [x][y] (width-major), see
+ *     DigiPathAI/loaders/dataloader.py:357-358 and Segmentation.py:116-129.
+ */
+#ifndef DIGIPATH_B200_H
+#define DIGIPATH_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct dp_model dp_model;
+
+/* Library/ABI version (bumped when a signature changes). */
+int dp_abi_version(void);
+
+/* Thread-local message of the last failed call on this thread ("" if none). */
+const char* dp_last_error(void);
+
+/*
+ * Replaces load_trained_models(model, path, patch_size)      DigiPathAI/helpers/utils.py:427-448
+ * `blob` is a host pointer to a flat "DPB1" model container (layer program + packed fp16 weights + folded
+ * BatchNorm affine terms) produced by digipathai_b200.weights.pack_*; see DESIGN.md "Model container".
+ * Allocates all activation buffers for up to `max_batch` tiles of `patch` x `patch` on CUDA device `device`.
+ */
+int dp_model_create(const void* blob, size_t nbytes, int device, int max_batch, dp_model** out);
+
+/* Frees everything owned by the model (synchronises the device first). */
+int dp_model_destroy(dp_model* m);
+
+/* Model facts: patch side the container was built for, max batch, bytes of HBM held. */
+int dp_model_info(const dp_model* m, int* patch, int* max_batch, uint64_t* device_bytes);
+
+/*
+ * Replaces  apply_tta(image_patches, tta_) -> models[name].predict(image_patches) -> transform_prob(pred, tta_)
+ *                                        Segmentation.py:150-158, utils.py:487-522, dataloader.py:340-390
+ * for ONE pass over ONE batch, including the tile crop + (v-128)/128 normalisation of __getitem__.
+ *
+ *   slide      device, uint8 [slide_w][slide_h][3] raster in [x][y][c] order (the reference transposes every
+ *              tile to this orientation, dataloader.py:357-358). For a pre-gathered batch of tiles pass the
+ *              tiles as [n_tiles*P][P][3] with slide_h = P and coords[b] = (b*P, 0).
+ *   coords     device, int32 [n_tiles][2] = (x, y) level-0 tile origins (already clamped, dataloader.py:348-353)
+ *   tta_in     D4 code (see dp_d4_*) of the CUMULATIVE forward transform the network input has undergone
+ *              (the reference applies TTAs in place, so pass k sees T_k o ... o T_1; Segmentation.py:151)
+ *   tta_out    D4 code of the transform whose inverse is applied to the prediction (transform_prob)
+ *   probs_out  device, float32 [n_tiles][P][P]: softmax channel 1 (the only channel the reference consumes,
+ *              Segmentation.py:167), already inverse-transformed.
+ */
+int dp_forward_tiles(dp_model* m, const uint8_t* slide, int64_t slide_w, int64_t slide_h, const int32_t* coords,
+                     int n_tiles, int tta_in, int tta_out, float* probs_out, void* stream);
+
+/*
+ * Replaces the statistics + overlap accumulate of one batch          Segmentation.py:162-173
+ *   probs      device, float32 [n_pass][n_tiles][P][P] (n_pass = |tta_list| * |models| results of dp_forward_tiles)
+ *   mean,var   device, float32 planes [x_hi - x_lo][plane_h]; count device uint8, same shape.
+ *              x_lo is the level-0 x of plane row 0 (0 for a whole-slide plane; >0 for a rank's stripe).
+ * Adds np.mean / np.var (ddof 0) over the pass axis into the planes and 1 into count (uint8, wraps), tile by
+ * tile in ascending tile order -- bit-identical to the reference's sequential loop for identical probs.
+ */
+int dp_stitch(const float* probs, int n_pass, int n_tiles, int patch, const int32_t* coords, float* mean,
+              float* var, uint8_t* count, int64_t plane_w, int64_t plane_h, int64_t x_lo, void* stream);
+
+/*
+ * Replaces normalise + threshold                              Segmentation.py:175-177 and :336-337
+ *   count==0 -> 1; mean /= count; var /= count^2 (in place);  label[i] = mean[i] >= threshold ? 255 : 0
+ * `label` (device uint8, n elements) may be NULL to skip the threshold. All pointers 16-byte aligned.
+ */
+int dp_finalize(float* mean, float* var, uint8_t* count, int64_t n, float threshold, uint8_t* label, void* stream);
+
+/* One 2x mean-pool level of an [w][h] float32 plane into [w/2][h/2] (in-HBM probability pyramid). */
+int dp_pyramid_down2(const float* in, int64_t w, int64_t h, float* out, void* stream);
+
+/* D4 helpers shared with the host code: source map of transform `code` on a P x P tile. */
+void dp_d4_src(int code, int i, int j, int P, int* a, int* b);
+
+/* ---- instrumentation / debugging (not on the hot path) ------------------------------------------------ */
+
+/* Number of kernels this library has launched since load (all models, all threads). */
+uint64_t dp_kernel_launch_count(void);
+
+/* Options: "naive_conv" (0/1: evaluate convs with the CUDA-core reference kernel),
+ *          "desc_base_mode" (0/1: UMMA descriptor base_offset policy, bring-up only), "halo_pad8" (0/1: pad halo pitch to 8 pixels, bring-up only). */
+int dp_model_set_option(dp_model* m, const char* key, int value);
+
+/* Number of ops / buffers in the layer program; buffer geometry (per-image H, W, C; fp16 NHWC). */
+int dp_model_program_size(const dp_model* m, int* n_ops, int* n_bufs);
+int dp_model_buffer_shape(const dp_model* m, int buf, int* h, int* w, int* c);
+
+/* Copy an activation buffer (first n_tiles images) to / from host fp16 memory; synchronous. */
+int dp_debug_read_buffer(dp_model* m, int buf, int n_tiles, void* host_fp16, size_t nbytes);
+int dp_debug_write_buffer(dp_model* m, int buf, int n_tiles, const void* host_fp16, size_t nbytes);
+
+/* Run ops [op_begin, op_end) of the layer program on n_tiles images already resident in the buffers.
+ * Head ops write to probs_out (may be NULL if the range has no head). */
+int dp_debug_run_ops(dp_model* m, int n_tiles, int op_begin, int op_end, int tta_out, float* probs_out,
+                     void* stream);
+
+/* Executed tensor-core MACs of one forward pass over n_tiles tiles (after the sub-pixel rewrite). */
+int dp_model_executed_macs(const dp_model* m, int n_tiles, uint64_t* macs);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DIGIPATH_B200_H */

@@ -1,0 +1,53 @@
+"""Single-op layer programs used by the GPU parity tests and the bring-up script (test infrastructure)."""
+from __future__ import annotations
+
+import numpy as np
+
+from digipathai_b200.program import (KIND_1X1, KIND_3X3, KIND_UP2, OP_CONV, PRO_AFFINE_RELU, Op, Program,
+                                     pack_conv_weights, pad64)
+
+# name: (kind, H, W, Cin, Cout, B, in_ctot, in_choff, out_ctot, out_choff, prologue, relu, head)
+CASES = {
+    "d_1x1_plain":   (KIND_1X1, 16, 16, 64, 128, 2, 64, 0, 128, 0, False, True, False),
+    "d_1x1_pro_tail": (KIND_1X1, 16, 16, 96, 128, 3, 160, 32, 128, 0, True, True, False),
+    "d_1x1_stem":    (KIND_1X1, 32, 32, 160, 64, 2, 160, 0, 160, 96, False, True, False),
+    "d_1x1_wide":    (KIND_1X1, 8, 8, 1024, 512, 4, 1024, 0, 1024, 0, False, False, False),
+    "d_1x1_msub":    (KIND_1X1, 64, 64, 64, 128, 12, 64, 0, 128, 0, True, True, False),
+    "t_3x3_8x8":     (KIND_3X3, 8, 8, 128, 32, 5, 128, 0, 1024, 512, False, False, False),
+    "t_up2_8x8":     (KIND_UP2, 8, 8, 128, 320, 4, 128, 0, 384, 0, False, True, False),
+    "h_3x3_16":      (KIND_3X3, 16, 16, 128, 32, 3, 128, 0, 1344, 320, False, False, False),
+    "h_3x3_64":      (KIND_3X3, 64, 64, 64, 64, 2, 64, 0, 64, 0, False, True, False),
+    "h_3x3_big":     (KIND_3X3, 32, 32, 768, 256, 6, 768, 0, 256, 0, False, True, False),
+    "h_3x3_n320":    (KIND_3X3, 16, 16, 96, 320, 2, 96, 0, 320, 0, False, True, False),
+    "h_up2_16":      (KIND_UP2, 16, 16, 64, 64, 2, 64, 0, 96, 32, False, True, False),
+    "h_up2_n256":    (KIND_UP2, 16, 16, 320, 256, 2, 320, 0, 768, 0, False, True, False),
+    "h_up2_n96":     (KIND_UP2, 32, 32, 128, 96, 2, 128, 0, 160, 0, False, True, False),
+    "h_head":        (KIND_3X3, 64, 64, 64, 64, 3, 64, 0, 64, 0, False, True, True),
+}
+
+
+def build_case(name: str, seed: int = 0):
+    kind, H, W, cin, cout, B, ictot, ioff, octot, ooff, pro, relu, head = CASES[name]
+    rng = np.random.default_rng(seed)
+    patch = H if head else 64
+    pr = Program(patch=patch)
+    ib = pr.add_buf("in", H, W, ictot)
+    up = 2 if kind == KIND_UP2 else 1
+    ob = pr.add_buf("out", H * up, W * up, octot)
+    k = {KIND_1X1: 1, KIND_3X3: 3, KIND_UP2: 3}[kind]
+    kern = (rng.standard_normal((k, k, cin, cout)) * np.sqrt(2.0 / (k * k * cin))).astype(np.float32)
+    op = Op(OP_CONV, in_buf=ib, in_choff=ioff, cin=cin, out_buf=ob, out_choff=ooff, cout=cout, kind=kind,
+            relu=int(relu), w=pack_conv_weights(kern, kind), name=name,
+            epi_scale=rng.uniform(0.5, 1.5, cout).astype(np.float32),
+            epi_shift=(0.2 * rng.standard_normal(cout)).astype(np.float32))
+    if pro:
+        op.pro = PRO_AFFINE_RELU
+        op.pro_scale = pad64(rng.uniform(0.5, 1.5, cin).astype(np.float32))
+        op.pro_shift = pad64((0.3 * rng.standard_normal(cin)).astype(np.float32))
+    if head:
+        op.head = 1
+        op.head_w = (rng.standard_normal(cout) * 0.3).astype(np.float32)
+        op.head_b = 0.1
+    pr.ops.append(op)
+    x = rng.standard_normal((B, H, W, ictot)).astype(np.float16)
+    return pr, x, B

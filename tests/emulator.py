@@ -1,0 +1,112 @@
+"""CPU emulator of the layer program (digipathai_b200/program.py) -- test infrastructure.
+
+Executes exactly what csrc/runtime.cu executes (same tap tables, same packed fp16 weights, same buffer plan,
+same fp16 rounding points) with torch-CPU fp32 arithmetic.  It validates the graph builder / weight packer
+against the oracle without a GPU, and predicts the fp16-storage error the CUDA path should show.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from digipathai_b200 import tta
+from digipathai_b200.program import (KIND_1X1, KIND_3X3, KIND_UP2, OP_BNPOOL, OP_CONV, OP_MAXPOOL, OP_STEM_IM2COL,
+                                     Program)
+
+
+def entries(kind):
+    if kind == KIND_1X1:
+        return [(0, 0, 0)]
+    if kind == KIND_3X3:
+        return [(ky - 1, kx - 1, 0) for ky in range(3) for kx in range(3)]
+    out = []
+    for ph in range(4):
+        a, b = ph >> 1, ph & 1
+        for t in range(4):
+            ty, tx = t >> 1, t & 1
+            out.append((a - 1 + ty, b - 1 + tx, ph))
+    return out
+
+
+def _shift(x, dy, dx):
+    """x[n,h,w,c] -> y[n,h,w,c] = x[n,h+dy,w+dx,c] with zero fill."""
+    n, h, w, c = x.shape
+    y = torch.zeros_like(x)
+    hs, he = max(0, -dy), min(h, h - dy)
+    ws, we = max(0, -dx), min(w, w - dx)
+    y[:, hs:he, ws:we] = x[:, hs + dy:he + dy, ws + dx:we + dx]
+    return y
+
+
+def stem_im2col(tiles_u8: np.ndarray, code: int) -> torch.Tensor:
+    """tiles uint8 [B,P,P,3] (reference [x,y,c] orientation) -> fp32 [B,P/2,P/2,160]."""
+    B, P = tiles_u8.shape[:2]
+    x = torch.from_numpy(np.stack([tta.apply(code, t) for t in tiles_u8]).astype(np.float32))
+    x = (x - 128.0) / 128.0
+    xp = torch.zeros(B, P + 6, P + 6, 3)
+    xp[:, 3:P + 3, 3:P + 3] = x
+    cols = []
+    for ky in range(7):
+        for kx in range(7):
+            cols.append(xp[:, ky:ky + P:2, kx:kx + P:2, :])
+    out = torch.cat(cols, dim=-1)
+    return torch.cat([out, torch.zeros(B, P // 2, P // 2, 160 - 147)], dim=-1)
+
+
+def run(prog: Program, tiles_u8: np.ndarray, tta_in: int = 0, tta_out: int = 0, fp16_storage: bool = True,
+        keep: bool = False):
+    """Returns probs float32 [B,P,P] (and the buffer dict when keep=True)."""
+    B, P = tiles_u8.shape[0], prog.patch
+    q = (lambda t: t.half().float()) if fp16_storage else (lambda t: t)
+    bufs = [torch.zeros(B, h, w, c) for (h, w, c) in prog.bufs]
+    probs = None
+    f = lambda a: torch.from_numpy(np.asarray(a, dtype=np.float32))
+    for op in prog.ops:
+        if op.type == OP_STEM_IM2COL:
+            bufs[op.out_buf][:] = q(stem_im2col(tiles_u8, tta_in))
+        elif op.type == OP_MAXPOOL:
+            x = bufs[op.in_buf][..., op.in_choff:op.in_choff + op.cin].permute(0, 3, 1, 2)
+            y = torch.nn.functional.max_pool2d(torch.nn.functional.pad(x, (1, 1, 1, 1)), 3, stride=2)
+            bufs[op.out_buf][..., op.out_choff:op.out_choff + op.cin] = y.permute(0, 2, 3, 1)
+        elif op.type == OP_BNPOOL:
+            x = bufs[op.in_buf][..., op.in_choff:op.in_choff + op.cin]
+            y = x * f(op.epi_scale) + f(op.epi_shift)
+            if op.relu:
+                y = torch.relu(y)
+            if op.pool:
+                y = torch.nn.functional.avg_pool2d(y.permute(0, 3, 1, 2), 2, stride=2).permute(0, 2, 3, 1)
+            bufs[op.out_buf][..., op.out_choff:op.out_choff + op.cin] = q(y)
+        elif op.type == OP_CONV:
+            x = bufs[op.in_buf][..., op.in_choff:op.in_choff + op.cin]
+            if op.pro:
+                x = x * f(op.pro_scale[:op.cin]) + f(op.pro_shift[:op.cin])
+                if op.pro == 2:
+                    x = torch.relu(x)
+                x = q(x)
+            w = torch.from_numpy(op.w.astype(np.float32))  # [e, co, ci]
+            ents = entries(op.kind)
+            ng = 4 if op.kind == KIND_UP2 else 1
+            n, h, wd, _ = x.shape
+            acc = torch.zeros(ng, n, h, wd, op.cout)
+            for e, (dy, dx, g) in enumerate(ents):
+                acc[g] += _shift(x, dy, dx) @ w[e].T
+            sc = f(op.epi_scale) if op.epi_scale is not None else torch.ones(op.cout)
+            sh = f(op.epi_shift) if op.epi_shift is not None else torch.zeros(op.cout)
+            acc = acc * sc + sh
+            if op.relu:
+                acc = torch.relu(acc)
+            if op.kind == KIND_UP2:
+                y = torch.zeros(n, 2 * h, 2 * wd, op.cout)
+                for g in range(4):
+                    y[:, (g >> 1)::2, (g & 1)::2] = acc[g]
+            else:
+                y = acc[0]
+            if op.head:
+                z = y @ f(op.head_w) + op.head_b
+                pr = torch.sigmoid(z).numpy()
+                probs = np.stack([tta.apply(tta.inverse(tta_out), t) for t in pr])
+            else:
+                bufs[op.out_buf][..., op.out_choff:op.out_choff + op.cout] = q(y)
+        else:
+            raise ValueError(op.type)
+    return (probs, bufs) if keep else probs

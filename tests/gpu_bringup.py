@@ -1,0 +1,150 @@
+"""GPU bring-up / bisect script (not a pytest file).  Each case runs in its own process so that a trapped
+kernel (sticky CUDA error) cannot poison the next one.
+
+    python tests/gpu_bringup.py            # all cases, each under `timeout`
+    python tests/gpu_bringup.py --case X   # one case in this process
+"""
+from __future__ import annotations
+
+import argparse
+import os
+import subprocess
+import sys
+import time
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(HERE))
+sys.path.insert(0, HERE)
+
+
+def emu_single(pr, x, tta_out=0):
+    """Reference for a one-op program on CPU (fp32 math on the fp16 operands)."""
+    import numpy as np
+    import torch
+    import emulator
+    from digipathai_b200 import tta
+    from digipathai_b200.program import KIND_UP2
+    op = pr.ops[0]
+    f = lambda a: torch.from_numpy(np.asarray(a, dtype=np.float32))
+    xs = f(x.astype(np.float32))[..., op.in_choff:op.in_choff + op.cin]
+    if op.pro:
+        xs = torch.relu(xs * f(op.pro_scale[:op.cin]) + f(op.pro_shift[:op.cin])).half().float()
+    w = f(op.w.astype(np.float32))
+    ng = 4 if op.kind == KIND_UP2 else 1
+    n, h, wd, _ = xs.shape
+    acc = torch.zeros(ng, n, h, wd, op.cout)
+    for e, (dy, dx, g) in enumerate(emulator.entries(op.kind)):
+        acc[g] += emulator._shift(xs, dy, dx) @ w[e].T
+    acc = acc * f(op.epi_scale) + f(op.epi_shift)
+    if op.relu:
+        acc = torch.relu(acc)
+    if op.kind == KIND_UP2:
+        y = torch.zeros(n, 2 * h, 2 * wd, op.cout)
+        for g in range(4):
+            y[:, (g >> 1)::2, (g & 1)::2] = acc[g]
+    else:
+        y = acc[0]
+    if op.head:
+        p = torch.sigmoid(y @ f(op.head_w) + op.head_b).numpy()
+        return np.stack([tta.apply(tta.inverse(tta_out), t) for t in p])
+    return y.numpy()
+
+
+def run_conv_case(name):
+    import numpy as np
+    import torch
+    import conv_cases
+    from digipathai_b200.engine import TileModel
+    pr, x, B = conv_cases.build_case(name)
+    op = pr.ops[0]
+    tta_out = 5 if op.head else 0
+    ref = emu_single(pr, x, tta_out)
+    m = TileModel(pr, device=0, max_batch=B)
+    res = {}
+    combos = [("naive", 1, 0, 0), ("tc_b0", 0, 0, 0), ("tc_b1", 0, 1, 0)]
+    if name.startswith("h_"):
+        combos += [("tc_b0_pad8", 0, 0, 1), ("tc_b1_pad8", 0, 1, 1)]
+    for label, naive, dmode, pad8 in combos:
+        m.set_option("naive_conv", naive)
+        m.set_option("desc_base_mode", dmode)
+        m.set_option("halo_pad8", pad8)
+        m.write_buffer(0, x)
+        m.write_buffer(1, np.zeros((B,) + pr.bufs[1], dtype=np.float16))
+        probs = torch.zeros((B, pr.patch, pr.patch), dtype=torch.float32, device="cuda") if op.head else None
+        t0 = time.time()
+        m.run_ops(B, 0, 1, tta_out, probs)
+        torch.cuda.synchronize()
+        dt = time.time() - t0
+        if op.head:
+            got = probs.cpu().numpy()
+            err = np.abs(got - ref).max()
+        else:
+            got = m.read_buffer(1, B).astype(np.float32)[..., op.out_choff:op.out_choff + op.cout]
+            err = np.abs(got - ref).max()
+            # channels outside the written range must stay zero
+            full = m.read_buffer(1, B).astype(np.float32)
+            full[..., op.out_choff:op.out_choff + op.cout] = 0
+            if np.abs(full).max() != 0:
+                print(f"  {label}: WROTE OUTSIDE ITS CHANNEL RANGE")
+        res[label] = err
+        print(f"  {name:16s} {label:9s} max_abs_err {err:.3e}  ref_max {np.abs(ref).max():.2f}  ({dt*1e3:.1f} ms)", flush=True)
+    return res
+
+
+def run_full(batch=2, naive_too=True):
+    import numpy as np
+    import torch
+    import emulator
+    from digipathai_b200.engine import TileModel
+    from digipathai_b200.models.densenet import densenet121_unet_program, init_densenet_weights
+    from oracle import densenet_ref as R
+    rng = np.random.default_rng(1)
+    tiles = rng.integers(0, 256, (batch, 256, 256, 3)).astype(np.uint8)
+    w = init_densenet_weights(0)
+    x = (tiles.astype(np.float32) - 128) / 128
+    R.calibrate_bn(w, x)
+    y = R.forward(w, x)[..., 1]
+    prog = densenet121_unet_program(w, 256)
+    emu, ebufs = emulator.run(prog, tiles, keep=True)
+    print(f"  emulator(fp16 storage) vs oracle: {np.abs(emu - y).max():.3e}", flush=True)
+    m = TileModel(prog, device=0, max_batch=batch)
+    t = torch.from_numpy(tiles).cuda()
+    for label, naive in (("naive", 1), ("tc", 0)) if naive_too else (("tc", 0),):
+        m.set_option("naive_conv", naive)
+        p = m.forward_tile_batch(t).cpu().numpy()
+        print(f"  full forward {label:5s}: vs oracle {np.abs(p - y).max():.3e}  vs emulator {np.abs(p - emu).max():.3e}", flush=True)
+        # per-buffer drift against the emulator (where does an error first appear?)
+        for bi, nm in enumerate(prog.buf_names):
+            got = m.read_buffer(bi, batch).astype(np.float32)
+            want = ebufs[bi].numpy()
+            d = np.abs(got - want).max()
+            print(f"     buf {nm:12s} max_abs_diff {d:.3e} (ref max {np.abs(want).max():.2f})", flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--case")
+    ap.add_argument("--timeout", type=int, default=240)
+    args = ap.parse_args()
+    if args.case:
+        if args.case == "full":
+            run_full()
+        else:
+            run_conv_case(args.case)
+        return
+    import conv_cases
+    for name in list(conv_cases.CASES) + ["full"]:
+        print(f"== {name}", flush=True)
+        try:
+            r = subprocess.run(["timeout", str(args.timeout), sys.executable, os.path.abspath(__file__), "--case", name],
+                               capture_output=True, text=True)
+            out = (r.stdout + r.stderr).strip().splitlines()
+            keep = [l for l in out if l.startswith("  ") or "rror" in l or "dp:" in l or "Traceback" in l]
+            print("\n".join(keep[-40:]), flush=True)
+            print(f"   exit {r.returncode}", flush=True)
+        except Exception as e:  # noqa: BLE001
+            print("   launcher error", e, flush=True)
+
+
+if __name__ == "__main__":
+    main()
