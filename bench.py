@@ -1,0 +1,361 @@
+#!/usr/bin/env python
+"""Benchmark of the getSegmentation hot path (metric of BASELINE.json: tiles/s, 256x256, batch 32).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]            # this repo's CUDA path
+    python bench.py --impl reference ...                           # the reference's CPU path (oracle port)
+    python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
+
+A *step* is one pass of the hot path over one batch of 32 synthetic 256x256x3 uint8 tiles:
+tile crop + normalise + DenseNet-121 U-Net forward + softmax channel 1 (dp_forward_tiles), i.e. BASELINE.json
+configs[1].  `value` is device-timed with the slide raster already resident in HBM; `e2e` is the same step
+through the Keras-``predict``-shaped host API (pinned host uint8 tiles -> H2D -> forward -> D2H of the
+probabilities) with the copies inside the timed region.  `--workload slide` instead runs the whole
+get_prediction loop (forward x TTA passes + stitch + normalise) on a synthetic slide, sharded by tile range
+with one halo exchange when N > 1.
+
+The oracle (oracle/) is executed here only for the `cpu_baseline` leg and for `--impl reference`.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "tiles_per_sec_256x256_b32"
+UNIT = "tiles/s"
+PATCH, BATCH = 256, 32
+REF_FLOP_PER_TILE = 42316333056  # 21 158 166 528 conv MACs x 2 (reference graph)
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d, "measured"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu, self.rows, self.proc = gpu_index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i",
+                 str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:  # noqa: BLE001
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def dist_env():
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    return rank, world, local
+
+
+def oracle_tiles_per_sec(n_tiles: int, threads: int, seed: int = 0):
+    """Times the CPU oracle (fp32 PyTorch-CPU restatement of the reference graph + crop/normalise) on a sample."""
+    import torch
+    from digipathai_b200.models.densenet import init_densenet_weights
+    from oracle import densenet_ref
+    torch.set_num_threads(threads)
+    rng = np.random.default_rng(seed)
+    w = init_densenet_weights(0)
+    tiles = rng.integers(0, 256, (n_tiles, PATCH, PATCH, 3)).astype(np.uint8)
+    densenet_ref.forward(w, (tiles[:1].astype(np.float32) - 128.0) / 128.0)  # warm-up (thread pools, allocs)
+    t0 = time.perf_counter()
+    done = 0
+    for s in range(0, n_tiles, 4):   # the reference's own CPU-runnable case uses batch 4 (BASELINE configs[0])
+        x = (tiles[s:s + 4].astype(np.float32) - 128.0) / 128.0
+        densenet_ref.forward(w, x)
+        done += len(x)
+    dt = time.perf_counter() - t0
+    return done / dt, dt
+
+
+def run_reference(args):
+    rank, world, _ = dist_env()
+    if rank != 0:
+        return
+    import torch
+    cores = os.cpu_count() or 1
+    sample = 8
+    vals = []
+    for _ in range(max(1, args.warmup and 1)):
+        oracle_tiles_per_sec(4, cores)
+    t_all = 0.0
+    for _ in range(args.steps):
+        v, dt = oracle_tiles_per_sec(sample, cores)
+        vals.append(v); t_all += dt
+    value = float(np.mean(vals))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * t_all / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "configs[1]: DenseNet-121 U-Net forward, 256x256x3 uint8 tiles",
+                   "note": "reference CPU path = oracle port (fp32 torch-CPU restatement of densenet.py; the "
+                           "reference itself needs TensorFlow 1.x and cannot be installed offline)"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+                         "sample": f"{sample} tiles per step in batches of 4, {args.steps} steps"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="forward", choices=["forward", "slide"])
+    ap.add_argument("--slide", type=int, default=8192, help="--workload slide: side of the synthetic slide")
+    ap.add_argument("--tta", default="", help="--workload slide: comma separated tta_list")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    if args.warmup < 3:
+        args.warmup = 3
+
+    import torch
+    import torch.distributed as dist
+    from digipathai_b200 import engine
+    from digipathai_b200.models.densenet import densenet121_unet_program, init_densenet_weights
+
+    rank, world, local = dist_env()
+    if world != args.gpus and world > 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    peaks, peak_src = load_peaks()
+    weights = init_densenet_weights(0)
+    model = engine.TileModel(densenet121_unet_program(weights, PATCH), device=local, max_batch=BATCH)
+
+    if args.workload == "slide":
+        return run_slide(args, model, rank, world, local, dev, barrier, max_over_ranks, peaks, peak_src)
+
+    # ---------------------------------------------------------------- synthetic input, resident in HBM
+    g = torch.Generator(device=dev); g.manual_seed(1234 + rank)
+    SW = SH = 4096
+    slide = torch.randint(0, 256, (SW, SH, 3), dtype=torch.uint8, device=dev, generator=g)   # [x, y, c]
+    n_coord_sets = args.steps + args.warmup + 8
+    cg = torch.Generator(); cg.manual_seed(99 + rank)
+    coords_all = torch.randint(0, SW - PATCH, (n_coord_sets, BATCH, 2), generator=cg, dtype=torch.int32).to(dev)
+    probs = torch.empty((BATCH, PATCH, PATCH), dtype=torch.float32, device=dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)          # > 126 MB L2
+
+    def step(i):
+        model.forward_tiles(slide, coords_all[i % n_coord_sets], 0, 0, out=probs)
+
+    for i in range(args.warmup):
+        step(i)
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    n0 = engine.kernel_launch_count()
+    barrier()
+    for k in range(args.steps):
+        flush.zero_()                       # L2 flush between timed iterations (not timed)
+        ev[k][0].record()
+        step(args.warmup + k)
+        ev[k][1].record()
+    barrier()
+    launches = engine.kernel_launch_count() - n0
+    clocks = sampler.stop() if rank == 0 else None
+    ms_total = sum(a.elapsed_time(b) for a, b in ev)
+    ms_total = max_over_ranks(ms_total)
+    ms_per_step = ms_total / args.steps
+    value = world * BATCH * args.steps / (ms_total * 1e-3)
+
+    # ---------------------------------------------------------------- end to end through the host API
+    host_in = torch.randint(0, 256, (BATCH, PATCH, PATCH, 3), dtype=torch.uint8).pin_memory()
+    host_out = torch.empty((BATCH, PATCH, PATCH), dtype=torch.float32).pin_memory()
+    dev_in = torch.empty((BATCH, PATCH, PATCH, 3), dtype=torch.uint8, device=dev)
+
+    def e2e_step():
+        dev_in.copy_(host_in, non_blocking=True)
+        model.forward_tile_batch(dev_in, 0, 0, out=probs)
+        host_out.copy_(probs, non_blocking=True)
+
+    for _ in range(3):
+        e2e_step()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        e2e_step()
+    e1.record()
+    barrier()
+    e2e_ms = max_over_ranks(e0.elapsed_time(e1))
+    e2e_value = world * BATCH * args.steps / (e2e_ms * 1e-3)
+
+    # ---------------------------------------------------------------- per-kernel roofline (instrumented pass)
+    model.set_option("profile", 1)
+    n_prof = min(10, args.steps)
+    acc = None
+    for k in range(n_prof):
+        flush.zero_()
+        step(k)
+        t = model.op_times_ms()
+        acc = t if acc is None else acc + t
+    model.set_option("profile", 0)
+    per_op = acc / n_prof
+    infos = [model.op_info(i) for i in range(model.n_ops())]
+    conv_ms = float(sum(t for t, inf in zip(per_op, infos) if inf["type"] == 3))
+    all_ms = float(per_op.sum())
+    n_conv = sum(1 for inf in infos if inf["type"] == 3)
+    flop_step = REF_FLOP_PER_TILE * BATCH
+    achieved_tf = flop_step / (conv_ms * 1e-3) / 1e12
+    exec_macs = model.executed_macs(BATCH)
+    peak_tf = peaks["bf16_tflops_sustained"]
+    top = sorted(range(len(per_op)), key=lambda i: -per_op[i])[:5]
+    top_desc = [{"op": i, "kind": infos[i]["kind"], "cin": infos[i]["cin"], "cout": infos[i]["cout"],
+                 "hw": infos[i]["h"], "ms": round(float(per_op[i]), 4),
+                 "exec_tflops": round(2 * infos[i]["macs_per_tile"] * BATCH / (per_op[i] * 1e-3) / 1e12, 1)
+                 if per_op[i] > 0 and infos[i]["macs_per_tile"] else None} for i in top]
+
+    cpu_baseline = None
+    if rank == 0 and not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        v, dt = oracle_tiles_per_sec(32, threads)
+        cpu_baseline = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
+                        "sample": f"32 tiles (8 batches of 4) of the same workload, {dt:.1f} s of CPU work"}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f16 (fp32 accumulate)", "data": "synthetic",
+            "config": {"workload": "configs[1]: DenseNet-121 U-Net forward on synthetic 256x256x3 uint8 tiles, "
+                                   "batch 32 per GPU, tiles cropped from an HBM-resident raster",
+                       "l2": "flushed between timed steps (256 MiB memset, untimed)",
+                       "weights": "random-init (He-normal), BN stats (0,1)",
+                       "executed_gflop_per_tile": 2 * exec_macs / BATCH / 1e9,
+                       "reference_gflop_per_tile": REF_FLOP_PER_TILE / 1e9},
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(host_in.numel()),
+                    "d2h_bytes_per_step": int(host_out.numel() * 4)},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "tensor", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
+                         "frac": achieved_tf / peak_tf, "traffic": None,
+                         "kernel": f"conv_tc_kernel ({n_conv} launches per step; algorithmic FLOPs of the "
+                                   f"reference graph / summed CUDA-event time of those launches)",
+                         "peak_source": f"{peak_src} bf16_tflops_sustained",
+                         "conv_ms_per_step": conv_ms, "all_ops_ms_per_step": all_ms, "top_ops": top_desc},
+            "cpu_baseline": cpu_baseline,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_slide(args, model, rank, world, local, dev, barrier, max_over_ranks, peaks, peak_src):
+    """Whole get_prediction loop on a synthetic slide (BASELINE configs[2]/[3] at a chosen size)."""
+    import torch
+    import torch.distributed as dist
+    from digipathai_b200 import engine
+    from digipathai_b200.Segmentation import get_prediction
+    from digipathai_b200.dist import sharded_get_prediction
+    from digipathai_b200.slide import synthetic_slide
+    S = args.slide
+    levels = 1
+    while S // (2 ** (levels - 1)) > 2500 and levels < 5:
+        levels += 1
+    slide = synthetic_slide(S, S, seed=0, n_levels=levels)
+    tta_list = [t for t in args.tta.split(",") if t] or None
+    n_pass = 1 + (len(tta_list) if tta_list else 0)
+    times, n_tiles, halo = [], 0, 0
+    n0 = engine.kernel_launch_count()
+    for it in range(args.warmup + args.steps if args.steps < 3 else 1 + min(args.steps, 3)):
+        barrier()
+        t0 = time.perf_counter()
+        if world > 1:
+            grid, out, info = sharded_get_prediction(slide, {"dense": model}, BATCH, tta_list, PATCH, 128, device=local)
+            halo = info["halo_bytes_sent"]
+        else:
+            s, out = get_prediction(slide, batch_size=BATCH, models={"dense": model}, tta_list=tta_list,
+                                    patch_size=PATCH, stride_size=128, device=local, return_device=True)
+            from digipathai_b200.tissue import TileGrid
+        barrier()
+        times.append(time.perf_counter() - t0)
+    from digipathai_b200.tissue import TileGrid
+    if rank == 0:
+        g = TileGrid(slide, PATCH, 128, BATCH)
+        n_tiles = len(g.coords)
+        best = min(times[1:]) if len(times) > 1 else times[0]
+        print(json.dumps({"metric": METRIC, "value": n_tiles * n_pass / best, "unit": UNIT, "n_gpus": world,
+                          "steps": len(times) - 1, "warmup": 1, "ms_per_step": best * 1e3, "higher_is_better": True,
+                          "scaling": "strong", "vs_baseline": None, "dtype": "f16 (fp32 accumulate)",
+                          "data": "synthetic",
+                          "config": {"workload": f"get_prediction on a synthetic {S}x{S} slide, patch 256 stride 128 "
+                                                 f"batch 32, {n_pass} pass(es), {n_tiles} tiles, host wall clock "
+                                                 "incl. tissue mask, H2D of the raster, stitch and normalise",
+                                     "halo_bytes_sent_rank0": halo},
+                          "gpu_launches": int(engine.kernel_launch_count() - n0)}))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

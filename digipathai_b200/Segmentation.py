@@ -1,0 +1,275 @@
+"""B200-native drop-in for ``DigiPathAI/Segmentation.py``: ``getSegmentation`` and ``get_prediction``.
+
+Same call signatures, ``status`` protocol, return values and error behaviour as the reference
+(DigiPathAI/Segmentation.py:65-76,192-205 and README.md:79-87 -- the union of the three signatures the
+reference ships), but the batch loop runs on the GPU through ``libdigipath_b200.so``:
+
+    reference (per batch, host)                              here (per batch, device-resident)
+    ---------------------------------------------------      ------------------------------------------------
+    DataLoader workers: read_region + (v-128)/128            tile crop + normalise fused into the stem gather
+    apply_tta -> Model.predict -> transform_prob  (x N)      dp_forward_tiles(tta_in, tta_out)            (x N)
+    np.mean / np.var over passes, `+=` into 3 memmaps        dp_stitch (deterministic, reference add order)
+    count==0 -> 1, mean /= count, var /= count**2            dp_finalize
+    mean >= 0.3 -> 255 else 0                                dp_finalize (label plane)
+
+Reference quirks kept on purpose: cumulative in-place TTA (Q1), unknown TTA names are identity
+passes (Q2), ``drop_last`` (Q3), [x, y] plane orientation (Q4), clamped tile origins (Q5), uint8 count that
+wraps and var / count**2 (Q6), levels > 4 raise (Q7), ``quick`` meaning and ignored ``crf`` / ``mask_level``
+(Q8), only softmax channel 1 is used (Q9).
+"""
+from __future__ import annotations
+
+import os
+from os.path import expanduser
+
+import numpy as np
+
+from . import tta as _tta
+from .slide import level0_xy_raster, open_slide
+from .tissue import TileGrid
+
+home = expanduser("~")
+
+_MODEL_SETS = {  # Segmentation.py:232-278
+    "colon": ("digestpath_models", "digestpath"),
+    "liver": ("paip_models", "paip"),
+    "breast": ("camelyon_models", "camelyon"),
+}
+
+
+def _torch():
+    import torch
+    if not torch.cuda.is_available():
+        raise RuntimeError("digipathai_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+    return torch
+
+
+def get_prediction(wsi_path, mask_path=None, label_path=None, batch_size=64, models=None, tta_list=None,
+                   num_workers=8, verbose=0, patch_size=256, stride_size=256, mask_level=-1, status=None,
+                   *, device=0, tile_range=None, return_device=False, finalize=True, tissue_mask=None):
+    """Patch based segmentor (reference: Segmentation.py:65-189).
+
+    ``models`` maps a name to a ``TileModel`` (engine.py) -- the object that replaces the Keras model.
+    Returns ``(slide, {'mean': [W,H] float32, 'var': [W,H] float32})`` like the reference (numpy arrays instead
+    of memmaps).  Keyword-only extensions: ``device`` (CUDA ordinal), ``tile_range=(lo, hi)`` restricts the run
+    to a slice of the post-``drop_last`` tile list (multi-GPU sharding, dist.py), ``return_device`` keeps the
+    planes as torch CUDA tensors, ``finalize=False`` skips the normalisation (sharded runs normalise after the
+    halo exchange), ``tissue_mask`` supplies a precomputed [x, y] mask instead of the Otsu/HSV heuristic.
+    ``mask_path`` / ``label_path`` / ``num_workers`` / ``mask_level`` are accepted for signature
+    compatibility; the live reference passes None for the first two and ignores the last (dataloader.py:240-241).
+    """
+    from . import engine
+    torch = _torch()
+    if not models:
+        raise ValueError("get_prediction needs at least one model")
+    slide = open_slide(wsi_path)
+    grid = TileGrid(slide, patch_size=patch_size, stride_size=stride_size, batch_size=batch_size,
+                    roi_masking=True, mask=tissue_mask)
+    n_batches = len(grid)
+    print("Length of DataLoader: {}".format(n_batches))
+    passes = _tta.pass_codes(tta_list)
+    names = list(models.keys())
+    for nm in names:
+        if models[nm].patch != patch_size:
+            raise ValueError(f"model '{nm}' was built for patch {models[nm].patch}, not {patch_size}")
+        if models[nm].max_batch < batch_size:
+            raise ValueError(f"model '{nm}' holds buffers for {models[nm].max_batch} tiles, batch is {batch_size}")
+    W, H = slide.level_dimensions[0]
+    dev = torch.device("cuda", device)
+    P = int(patch_size)
+
+    coords_all = grid.coords
+    b_lo, b_hi = 0, n_batches
+    if tile_range is not None:
+        lo, hi = tile_range
+        if lo % batch_size or hi % batch_size:
+            raise ValueError("tile_range must be aligned to the batch size")
+        b_lo, b_hi = lo // batch_size, hi // batch_size
+    # stripe of the planes this call owns: [x_lo, x_hi)
+    if tile_range is None or b_hi <= b_lo:
+        x_lo, x_hi = 0, W
+    else:
+        sel = coords_all[b_lo * batch_size:b_hi * batch_size, 0]
+        x_lo, x_hi = int(sel.min()), int(sel.max()) + P
+    with torch.cuda.device(dev):
+        raster = torch.from_numpy(level0_xy_raster(slide)[x_lo:x_hi]).to(dev)      # uint8 [x, y, c] stripe in HBM
+        mean = torch.zeros((x_hi - x_lo, H), dtype=torch.float32, device=dev)
+        var = torch.zeros_like(mean)
+        count = torch.zeros((x_hi - x_lo, H), dtype=torch.uint8, device=dev)
+        n_pass = len(passes) * len(names)
+        probs = torch.empty((n_pass, batch_size, P, P), dtype=torch.float32, device=dev)
+        coords_dev = torch.from_numpy(coords_all - np.array([x_lo, 0], np.int32)).to(dev) if len(coords_all) else None
+        coords_abs = torch.from_numpy(coords_all).to(dev) if len(coords_all) else None
+        for ii in range(b_lo, b_hi):
+            if status is not None:
+                # same arithmetic as Segmentation.py:139 (an ensemble therefore tops out below 100 %)
+                status['progress'] = int(ii * 100.0 / (len(names) * n_batches))
+            c_local = coords_dev[ii * batch_size:(ii + 1) * batch_size]
+            k = 0
+            for (t_in, t_out) in passes:            # Segmentation.py:150-160: tta outer, model inner
+                for nm in names:
+                    models[nm].forward_tiles(raster, c_local, t_in, t_out, out=probs[k])
+                    k += 1
+            engine.stitch(probs, coords_abs[ii * batch_size:(ii + 1) * batch_size], mean, var, count, x_lo=x_lo)
+        if finalize:
+            engine.finalize(mean, var, count, 0.0, None)
+        torch.cuda.synchronize(dev)
+    out = {'mean': mean, 'var': var}
+    if not finalize:
+        out['count'] = count
+    out['x_range'] = (x_lo, x_hi)
+    if not return_device:
+        out = {k: (v.cpu().numpy() if hasattr(v, 'cpu') else v) for k, v in out.items()}
+    return (slide, out)
+
+
+def _default_weight_path(mode, model):
+    folder, prefix = _MODEL_SETS[mode]
+    suffix = {'dense': 'densenet', 'inception': 'inception', 'deeplabv3': 'deeplabv3'}[model]
+    return os.path.join(home, '.DigiPathAI', folder, f'{prefix}_{suffix}.npz')
+
+
+def load_trained_models(model, path, patch_size=256, *, device=0, max_batch=32):
+    """Counterpart of utils.py:427-448: build the graph and load its weights; returns a ``TileModel``.
+
+    ``path`` is a flat ``.npz`` of Keras-named arrays (the reference's ``.h5`` files converted off-box with
+    tools/h5_to_npz.py -- h5py/TensorFlow are not available here) or an in-memory weight dict.
+    """
+    from .engine import TileModel
+    from .models.densenet import densenet121_unet_program
+    if model.__contains__('dense'):
+        weights = path if isinstance(path, dict) else _load_npz(path)
+        return TileModel(densenet121_unet_program(weights, patch_size), device=device, max_batch=max_batch)
+    if model.__contains__('inception') or model.__contains__('deeplabv3'):
+        raise NotImplementedError(
+            f"model '{model}': only the DenseNet-121 U-Net graph is built for sm_100a so far "
+            "(Inception-ResNet-v2 U-Net and DeepLabv3+ are SURVEY.md rows a8'/a8'')")
+    raise ValueError("Unknown model provided, allowed models ['dense', 'inception', 'deeplabv3']")
+
+
+def _load_npz(path):
+    if not os.path.exists(path):
+        raise FileNotFoundError(
+            f"{path} not found. The reference downloads Keras .h5 weights at this point "
+            "(DigiPathAI/helpers/utils.py:58-98); convert them once with tools/h5_to_npz.py, or pass "
+            "weights=<dict> to getSegmentation.")
+    z = np.load(path)
+    out = {}
+    for k in z.files:
+        if k.endswith('::gamma'):
+            b = k[:-7]
+            out[b] = (z[b + '::gamma'], z[b + '::beta'], z[b + '::mean'], z[b + '::var'])
+        elif '::' not in k:
+            out[k] = z[k]
+    return out
+
+
+def save_npz(weights: dict, path: str):
+    flat = {}
+    for k, v in weights.items():
+        if isinstance(v, tuple):
+            for nm, a in zip(('gamma', 'beta', 'mean', 'var'), v):
+                flat[f'{k}::{nm}'] = a
+        else:
+            flat[k] = v
+    np.savez(path, **flat)
+
+
+def getSegmentation(img_path,
+                    patch_size=256,
+                    stride_size=128,
+                    batch_size=32,
+                    quick=True,
+                    tta_list=None,
+                    crf=False,
+                    save_path=None,
+                    status=None,
+                    *,
+                    probs_path=None,
+                    mask_path=None,
+                    uncertainty_path=None,
+                    mask_level=-1,
+                    model='dense',
+                    mode='colon',
+                    weights=None,
+                    device=0,
+                    return_device=False):
+    """Whole-slide segmentation (reference: Segmentation.py:192-356, README.md:79-87).
+
+    Returns the thresholded map -- float32 ``[W, H]`` of {0, 255}, NOT transposed -- exactly what the reference
+    returns (Segmentation.py:336-337,356); writes probs / mask / uncertainty TIFFs when paths are given
+    (``save_path`` is the README's name for ``mask_path``).  ``crf`` and ``mask_level`` are accepted and
+    ignored, as in the live reference (Segmentation.py:327-331, dataloader.py:240-241).
+    Extensions (keyword only): ``weights`` = dict / ``.npz`` path per model name or a single dict for
+    ``model``; ``device``; ``return_device`` returns the uint8 label plane as a CUDA tensor instead.
+    """
+    from . import engine
+    torch = _torch()
+    mode = mode.lower()
+    print("==================================================")
+    print(mode)
+    if mode not in ['colon', 'liver', 'breast']:
+        raise ValueError("Unknown mode found, allowed fields are: ['colon', 'liver', 'breast']")
+    if mask_path is None:
+        mask_path = save_path
+
+    print("---------------------- {}, {} ---------------".format(model, quick))
+    if not quick:
+        names = ['dense', 'inception', 'deeplabv3']          # Segmentation.py:288-291
+    else:
+        if model not in ('dense', 'inception', 'deeplabv3'):
+            raise ValueError("Unknown model provided, allowed models ['dense', 'inception', 'deeplabv3']")
+        names = [model]
+
+    def weight_source(nm):
+        if isinstance(weights, dict) and nm in weights and not isinstance(weights[nm], np.ndarray):
+            return weights[nm]
+        if isinstance(weights, dict) and 'conv1/conv' in weights:
+            return weights
+        if isinstance(weights, str):
+            return weights
+        return _default_weight_path(mode, nm)
+
+    missing = [nm for nm in names if isinstance(weight_source(nm), str) and not os.path.exists(weight_source(nm))]
+    if status is not None:
+        status['status'] = "Downloading Trained Models" if missing else "Found Trained Models, Skipping download"
+    if status is not None:
+        status['status'] = "Loading Trained weights"
+    models = {}
+    for nm in names:
+        models[nm] = load_trained_models(nm, weight_source(nm), patch_size=patch_size, device=device,
+                                         max_batch=batch_size)
+
+    threshold = 0.3
+    if status is not None:
+        status['status'] = "Running segmentation"
+    slide, probs_map = get_prediction(img_path, mask_path=None, mask_level=mask_level, label_path=None,
+                                      batch_size=batch_size, tta_list=tta_list, models=models,
+                                      patch_size=patch_size, stride_size=stride_size, status=status,
+                                      device=device, return_device=True, finalize=False)
+    mean, var, count = probs_map['mean'], probs_map['var'], probs_map['count']
+    label = torch.empty(mean.shape, dtype=torch.uint8, device=mean.device)
+    with torch.cuda.device(mean.device):
+        engine.finalize(mean, var, count, threshold, label)
+        torch.cuda.synchronize()
+    for m in models.values():
+        m.close()
+
+    from .tiffio import save_plane
+    if probs_path:
+        save_plane(probs_path, mean.T)                                   # Segmentation.py:333
+    if status is not None:
+        status['progress'] = 100
+    if status is not None:
+        status['status'] = "Saving Prediction Mask..."
+    if mask_path:
+        save_plane(mask_path, label.T)                                   # Segmentation.py:345
+    if status is not None:
+        status['status'] = "Saving Prediction Uncertanity..."
+    if uncertainty_path:
+        save_plane(uncertainty_path, var.T * 255)                        # Segmentation.py:351
+    if status is not None:
+        status['progress'] = 0
+    if return_device:
+        return label
+    return label.cpu().numpy().astype(np.float32)

@@ -127,7 +127,9 @@ struct dp_model {
   std::vector<__half*> buf_dev;
   __half* scratch_head = nullptr;  // naive path: output of the head-fused conv
   uint64_t device_bytes = 0;
-  int naive_conv = 0, desc_base_mode = 0, halo_pad8 = 0;
+  int naive_conv = 0, desc_base_mode = 0, halo_pad8 = 0, profile = 0;
+  std::vector<cudaEvent_t> ev;  // profile option: 2 events per op of the last run
+  int ev_begin = 0, ev_end = 0;
   std::map<int, Plan> plans;
   std::mutex mu;
 };
@@ -532,6 +534,7 @@ int dp_model_destroy(dp_model* m) {
   if (!m) return 0;
   cudaSetDevice(m->device);
   cudaDeviceSynchronize();
+  for (cudaEvent_t e : m->ev) cudaEventDestroy(e);
   for (__half* p : m->buf_dev)
     if (p) cudaFree(p);
   if (m->scratch_head) cudaFree(m->scratch_head);
@@ -552,6 +555,7 @@ int dp_model_set_option(dp_model* m, const char* key, int value) {
   if (check_model(m) || !key) return fail("null argument");
   if (!strcmp(key, "naive_conv")) m->naive_conv = value;
   else if (!strcmp(key, "desc_base_mode")) m->desc_base_mode = value;
+  else if (!strcmp(key, "profile")) m->profile = value;
   else if (!strcmp(key, "halo_pad8")) {
     std::lock_guard<std::mutex> lk(m->mu);
     m->halo_pad8 = value;
@@ -585,11 +589,19 @@ static int run_range(dp_model* m, int B, int op_begin, int op_end, const PassArg
   Plan* plan = nullptr;
   if (get_plan(m, B, &plan)) return 1;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  for (int i = op_begin; i < op_end; ++i)
+  if (m->profile && m->ev.empty()) {
+    m->ev.resize(2 * m->ops.size());
+    for (auto& e : m->ev) CU_OK(cudaEventCreate(&e));
+  }
+  for (int i = op_begin; i < op_end; ++i) {
+    if (m->profile) CU_OK(cudaEventRecord(m->ev[2 * i], st));
     if (run_op(m, plan, i, B, a, st)) {
       g_err = "op " + std::to_string(i) + ": " + g_err;
       return 1;
     }
+    if (m->profile) CU_OK(cudaEventRecord(m->ev[2 * i + 1], st));
+  }
+  if (m->profile) { m->ev_begin = op_begin; m->ev_end = op_end; }
   return 0;
 }
 
@@ -632,6 +644,41 @@ int dp_debug_write_buffer(dp_model* m, int buf, int n_tiles, const void* host, s
   CU_OK(cudaSetDevice(m->device));
   CU_OK(cudaDeviceSynchronize());
   CU_OK(cudaMemcpy(m->buf_dev[buf], host, need, cudaMemcpyHostToDevice));
+  return 0;
+}
+
+int dp_model_op_times(dp_model* m, float* ms, int n) {
+  if (check_model(m) || !ms) return fail("null argument");
+  if (n != (int)m->ops.size()) return fail("expected room for %zu ops", m->ops.size());
+  if (m->ev.empty()) return fail("no profiled run yet (set option 'profile' and run a forward)");
+  CU_OK(cudaSetDevice(m->device));
+  for (int i = 0; i < n; ++i) ms[i] = 0.f;
+  for (int i = m->ev_begin; i < m->ev_end; ++i) {
+    CU_OK(cudaEventSynchronize(m->ev[2 * i + 1]));
+    CU_OK(cudaEventElapsedTime(&ms[i], m->ev[2 * i], m->ev[2 * i + 1]));
+  }
+  return 0;
+}
+
+int dp_model_op_info(const dp_model* m, int op, int* type, int* kind, int* cin, int* cout, int* h, int* w,
+                     uint64_t* macs_per_tile) {
+  if (check_model(m)) return 1;
+  if (op < 0 || op >= (int)m->ops.size()) return fail("op %d out of range", op);
+  const BlobOp& o = m->ops[op];
+  if (type) *type = o.type;
+  if (kind) *kind = o.kind;
+  if (cin) *cin = o.cin;
+  if (cout) *cout = o.cout;
+  if (h) *h = m->bufs[o.in_buf].H;
+  if (w) *w = m->bufs[o.in_buf].W;
+  if (macs_per_tile) {
+    *macs_per_tile = 0;
+    if (o.type == OP_CONV) {
+      Plan* plan = nullptr;
+      if (get_plan(const_cast<dp_model*>(m), 1, &plan)) return 1;
+      *macs_per_tile = plan->launches[op].macs;
+    }
+  }
   return 0;
 }
 

@@ -1,0 +1,171 @@
+"""Multi-GPU sharding of one slide: contiguous tile ranges per rank + one halo exchange of boundary stripes.
+
+The reference is single-GPU (``CUDA_VISIBLE_DEVICES='0'``, DigiPathAI/Segmentation.py:62); this module adds
+the one strategy the path admits: tiles are independent, coupling exists only through the
+``+=`` into overlapping plane windows (Segmentation.py:164-173).  Tiles are ordered x-major
+(``np.where``, dataloader.py:311), so a contiguous range of the post-``drop_last`` tile list is an x-stripe.
+
+  partition_batches   equal numbers of batches per rank (balances tissue tiles, not slide area)
+  stripe_of           the [x_lo, x_hi) plane stripe a tile range touches
+  halo_exchange       every pair of ranks whose stripes intersect swaps its partial sums over the
+                      intersection (P2P send/recv, NCCL on GPUs / gloo in the CPU tests); each rank then adds
+                      the contributions in ascending rank order, so all ranks hold bit-identical totals.
+                      fp32 addition is not associative: (rank0 partial) + (rank1 partial) can differ from the
+                      single-GPU sequential order in the last ulp (SURVEY.md 8(e) determinism caveat).
+  gather_planes       disjoint "owned" sub-stripes to rank 0 -> full [W, H] planes
+"""
+from __future__ import annotations
+
+import numpy as np
+
+
+def partition_batches(n_batches: int, world_size: int):
+    """[(b_lo, b_hi)] per rank; earlier ranks take the remainder."""
+    base, rem = divmod(n_batches, world_size)
+    out, lo = [], 0
+    for r in range(world_size):
+        hi = lo + base + (1 if r < rem else 0)
+        out.append((lo, hi))
+        lo = hi
+    return out
+
+
+def stripe_of(coords: np.ndarray, t_lo: int, t_hi: int, patch: int):
+    """[x_lo, x_hi) covered by tiles t_lo..t_hi-1 (empty range -> (0, 0))."""
+    if t_hi <= t_lo:
+        return (0, 0)
+    xs = coords[t_lo:t_hi, 0]
+    return (int(xs.min()), int(xs.max()) + patch)
+
+
+def stripes_for(coords: np.ndarray, batch_size: int, world_size: int, patch: int):
+    n_batches = len(coords) // batch_size
+    parts = partition_batches(n_batches, world_size)
+    return parts, [stripe_of(coords, lo * batch_size, hi * batch_size, patch) for lo, hi in parts]
+
+
+def halo_exchange(planes, stripes, rank: int, group=None):
+    """In-place: add every other rank's partial sums over the intersection of its stripe with mine.
+
+    ``planes`` is a list of torch tensors shaped [x_hi - x_lo, H] (float32 mean, float32 var, uint8 count);
+    ``stripes`` the [x_lo, x_hi) of every rank.  Returns the number of bytes this rank sent.
+    """
+    import torch
+    import torch.distributed as dist
+    my_lo, my_hi = stripes[rank]
+    peers = []
+    for s, (lo, hi) in enumerate(stripes):
+        if s == rank:
+            continue
+        a, b = max(lo, my_lo), min(hi, my_hi)
+        if b > a:
+            peers.append((s, a, b))
+    if not peers:
+        return 0
+    own = {s: [p[a - my_lo:b - my_lo].clone() for p in planes] for (s, a, b) in peers}   # my partials, pre-sum
+    recv = {s: [torch.empty_like(t) for t in own[s]] for s in own}
+    ops, sent = [], 0
+    for (s, a, b) in peers:
+        for t_send, t_recv in zip(own[s], recv[s]):
+            ops.append(dist.P2POp(dist.isend, t_send, s, group))
+            ops.append(dist.P2POp(dist.irecv, t_recv, s, group))
+            sent += t_send.numel() * t_send.element_size()
+    for w in dist.batch_isend_irecv(ops):
+        w.wait()
+    # ascending-rank summation over every intersected region; regions of different peers may overlap each
+    # other (stripes narrower than a patch), so rebuild each peer region from the ORIGINAL partials.
+    mine = [p.clone() for p in planes]
+    order = sorted([s for (s, _, _) in peers] + [rank])
+    bounds = {s: (a, b) for (s, a, b) in peers}
+    xs = sorted({my_lo, my_hi, *[v for ab in bounds.values() for v in ab]})
+    for x0, x1 in zip(xs[:-1], xs[1:]):
+        contributors = [s for s in order if s == rank or (bounds[s][0] <= x0 and x1 <= bounds[s][1])]
+        if contributors == [rank]:
+            continue
+        for k, p in enumerate(planes):
+            acc = None
+            for s in contributors:
+                if s == rank:
+                    part = mine[k][x0 - my_lo:x1 - my_lo]
+                else:
+                    a, _ = bounds[s]
+                    part = recv[s][k][x0 - a:x1 - a]
+                acc = part.clone() if acc is None else acc + part   # uint8 adds wrap like the reference's
+            p[x0 - my_lo:x1 - my_lo] = acc
+    return sent
+
+
+def owned_ranges(stripes):
+    """Disjoint [lo, hi) per rank: a rank owns its stripe minus what a lower rank already owns."""
+    out, covered = [], 0
+    for (lo, hi) in stripes:
+        a = max(lo, covered)
+        out.append((a, max(a, hi)))
+        covered = max(covered, hi)
+    return out
+
+
+def gather_planes(planes, stripes, rank: int, world_size: int, W: int, group=None):
+    """Rank 0 returns full [W, H] planes (zeros where no tile touched), other ranks None."""
+    import torch
+    import torch.distributed as dist
+    own = owned_ranges(stripes)
+    my_lo = stripes[rank][0]
+    if rank == 0:
+        full = [torch.zeros((W,) + tuple(p.shape[1:]), dtype=p.dtype, device=p.device) for p in planes]
+        a, b = own[0]
+        for f, p in zip(full, planes):
+            f[a:b] = p[a - my_lo:b - my_lo]
+        for s in range(1, world_size):
+            a, b = own[s]
+            if b <= a:
+                continue
+            for f in full:
+                buf = torch.empty((b - a,) + tuple(f.shape[1:]), dtype=f.dtype, device=f.device)
+                dist.recv(buf, s, group)
+                f[a:b] = buf
+        return full
+    a, b = own[rank]
+    if b > a:
+        for p in planes:
+            dist.send(p[a - my_lo:b - my_lo].contiguous(), 0, group)
+    return None
+
+
+def sharded_get_prediction(wsi_path, models, batch_size=32, tta_list=None, patch_size=256, stride_size=128,
+                           status=None, device=None, gather=False, tissue_mask=None):
+    """``get_prediction`` across the ranks of the default process group (one process per GPU).
+
+    Every rank computes the same tile grid (cheap, deterministic), takes its contiguous range of batches, runs
+    the device loop on its stripe, swaps halos, then normalises its stripe.  Returns
+    ``(grid, planes_dict, info)``; with ``gather=True`` rank 0's dict holds the full planes.
+    """
+    import torch
+    import torch.distributed as dist
+    from . import engine
+    from .Segmentation import get_prediction
+    from .slide import open_slide
+    from .tissue import TileGrid
+    rank, world = dist.get_rank(), dist.get_world_size()
+    if device is None:
+        device = torch.cuda.current_device()
+    slide = open_slide(wsi_path)
+    grid = TileGrid(slide, patch_size, stride_size, batch_size, True, tissue_mask)
+    parts, stripes = stripes_for(grid.coords, batch_size, world, patch_size)
+    lo, hi = parts[rank]
+    _, out = get_prediction(slide, batch_size=batch_size, models=models, tta_list=tta_list,
+                            patch_size=patch_size, stride_size=stride_size, status=status, device=device,
+                            tile_range=(lo * batch_size, hi * batch_size), return_device=True, finalize=False,
+                            tissue_mask=grid.mask if tissue_mask is None else tissue_mask)
+    planes = [out['mean'], out['var'], out['count']]
+    sent = halo_exchange(planes, stripes, rank) if hi > lo else 0
+    with torch.cuda.device(planes[0].device):
+        engine.finalize(planes[0], planes[1], planes[2], 0.0, None)
+    info = {'rank': rank, 'world': world, 'batches': (lo, hi), 'stripe': stripes[rank], 'halo_bytes_sent': sent}
+    res = {'mean': planes[0], 'var': planes[1], 'x_range': stripes[rank]}
+    if gather:
+        W = slide.level_dimensions[0][0]
+        full = gather_planes(planes[:2], stripes, rank, world, W)
+        if rank == 0:
+            res = {'mean': full[0], 'var': full[1], 'x_range': (0, W)}
+    return grid, res, info

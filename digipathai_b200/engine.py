@@ -130,6 +130,26 @@ class TileModel:
         _lib.check(_lib.lib.dp_debug_run_ops(self._h, n_tiles, op_begin, op_end, int(tta_out), ptr, _stream_ptr()),
                    "dp_debug_run_ops")
 
+    def n_ops(self) -> int:
+        a, b = C.c_int(), C.c_int()
+        _lib.check(_lib.lib.dp_model_program_size(self._h, C.byref(a), C.byref(b)))
+        return a.value
+
+    def op_times_ms(self) -> np.ndarray:
+        n = self.n_ops()
+        arr = (C.c_float * n)()
+        _lib.check(_lib.lib.dp_model_op_times(self._h, arr, n))
+        return np.array(arr[:], dtype=np.float64)
+
+    def op_info(self, op: int) -> dict:
+        v = [C.c_int() for _ in range(6)]
+        macs = C.c_uint64()
+        _lib.check(_lib.lib.dp_model_op_info(self._h, op, *[C.byref(x) for x in v], C.byref(macs)))
+        keys = ("type", "kind", "cin", "cout", "h", "w")
+        d = {k: x.value for k, x in zip(keys, v)}
+        d["macs_per_tile"] = macs.value
+        return d
+
     def executed_macs(self, n_tiles: int) -> int:
         v = C.c_uint64()
         _lib.check(_lib.lib.dp_model_executed_macs(self._h, n_tiles, C.byref(v)))

@@ -1,0 +1,112 @@
+"""Slide sources: what stands where ``openslide.OpenSlide`` stood (DigiPathAI/loaders/dataloader.py:239).
+
+The hot path only uses four things of an OpenSlide handle -- ``level_dimensions``, ``level_downsamples``,
+``level_count`` and ``read_region`` (dataloader.py:241-246,357; utils.py:337) -- so any object with those works.
+
+``ArraySlide`` holds a level-0 RGB raster in host memory (``uint8 [H, W, 3]``, ordinary image layout) with a
+*virtual* pyramid: level ``k`` is the level-0 raster sub-sampled with stride ``2**k``.  OpenSlide is not
+available in this image; when it is importable, ``open_slide`` hands real WSI files to it and decodes level 0
+into an ``ArraySlide`` so that tiles can be cropped on the GPU (real-slide ingest proper is SURVEY.md N2).
+"""
+from __future__ import annotations
+
+import os
+
+import numpy as np
+
+
+class ArraySlide:
+    def __init__(self, raster_hwc: np.ndarray, n_levels: int = 1):
+        a = np.asarray(raster_hwc)
+        if a.ndim != 3 or a.shape[2] != 3 or a.dtype != np.uint8:
+            raise ValueError("ArraySlide wants a uint8 [H, W, 3] raster")
+        self.raster = a
+        H, W = a.shape[:2]
+        self.level_count = int(n_levels)
+        self.level_downsamples = tuple(float(2 ** k) for k in range(n_levels))
+        self.level_dimensions = tuple((W // 2 ** k, H // 2 ** k) for k in range(n_levels))
+        self.dimensions = self.level_dimensions[0]
+
+    def read_region(self, location, level, size) -> np.ndarray:
+        """RGB ``uint8 [h, w, 3]`` of the region whose level-0 top-left corner is ``location = (x, y)``.
+
+        Like OpenSlide, pixels outside the slide are background; the reference converts OpenSlide's transparent
+        RGBA to RGB via PIL (dataloader.py:357), which yields black there.
+        """
+        x, y = int(location[0]), int(location[1])
+        w, h = int(size[0]), int(size[1])
+        s = 2 ** int(level)
+        lvl = self.raster[::s, ::s]
+        lx, ly = x // s, y // s
+        out = np.zeros((h, w, 3), dtype=np.uint8)
+        H, W = lvl.shape[:2]
+        x0, y0, x1, y1 = max(lx, 0), max(ly, 0), min(lx + w, W), min(ly + h, H)
+        if x1 > x0 and y1 > y0:
+            out[y0 - ly:y1 - ly, x0 - lx:x1 - lx] = lvl[y0:y1, x0:x1]
+        return out
+
+    def close(self):
+        pass
+
+
+def open_slide(path_or_obj, n_levels: int | None = None):
+    """Path (``.npy`` raster, any PIL-readable image, or a WSI if openslide is installed) or slide-like object."""
+    if hasattr(path_or_obj, "read_region") and hasattr(path_or_obj, "level_dimensions"):
+        return path_or_obj
+    if isinstance(path_or_obj, np.ndarray):
+        return ArraySlide(path_or_obj, n_levels or 1)
+    path = os.fspath(path_or_obj)
+    if not os.path.exists(path):
+        raise FileNotFoundError(path)
+    if path.endswith(".npy"):
+        return ArraySlide(np.load(path, mmap_mode="r"), n_levels or 1)
+    try:
+        import openslide  # noqa: F401  (absent in the build image; present on a DigiPathAI deployment)
+    except ImportError:
+        openslide = None
+    if openslide is not None:
+        try:
+            return openslide.OpenSlide(path)
+        except Exception:  # noqa: BLE001 -- fall through to PIL for plain images
+            pass
+    from PIL import Image
+    Image.MAX_IMAGE_PIXELS = None
+    with Image.open(path) as im:
+        return ArraySlide(np.asarray(im.convert("RGB")), n_levels or 1)
+
+
+def level0_xy_raster(slide) -> np.ndarray:
+    """Level-0 raster in the reference's tile orientation ``[x, y, c]`` (dataloader.py:357-358), host uint8."""
+    if isinstance(slide, ArraySlide):
+        return np.ascontiguousarray(np.transpose(slide.raster, (1, 0, 2)))
+    W, H = slide.level_dimensions[0]
+    img = slide.read_region((0, 0), 0, (W, H))
+    arr = np.asarray(img.convert("RGB") if hasattr(img, "convert") else img)
+    return np.ascontiguousarray(np.transpose(arr, (1, 0, 2)))
+
+
+def synthetic_slide(width: int, height: int, seed: int = 0, n_levels: int = 1, n_blobs: int = 4) -> ArraySlide:
+    """Synthetic H&E-like slide: white background 240+-3, elliptical 'tissue' (170, 90, 160) +- 20 covering ~50 %.
+
+    Recipe from SURVEY.md 8(d) config 1; built blockwise so that 40k x 40k needs no float64 temporaries.
+    """
+    rng = np.random.default_rng(seed)
+    img = np.empty((height, width, 3), dtype=np.uint8)
+    cy = rng.uniform(0.25, 0.75, n_blobs) * height
+    cx = rng.uniform(0.25, 0.75, n_blobs) * width
+    ry = rng.uniform(0.18, 0.30, n_blobs) * height
+    rx = rng.uniform(0.18, 0.30, n_blobs) * width
+    tissue_rgb = np.array([170.0, 90.0, 160.0], dtype=np.float32)
+    step = 1024
+    xs_all = np.arange(width, dtype=np.float32)
+    for y0 in range(0, height, step):
+        y1 = min(height, y0 + step)
+        ys = np.arange(y0, y1, dtype=np.float32)[:, None]
+        inside = np.zeros((y1 - y0, width), dtype=bool)
+        for k in range(n_blobs):
+            inside |= ((ys - cy[k]) / ry[k]) ** 2 + ((xs_all[None, :] - cx[k]) / rx[k]) ** 2 <= 1.0
+        blk = 240.0 + 3.0 * rng.standard_normal((y1 - y0, width, 3), dtype=np.float32)
+        tis = tissue_rgb + 20.0 * rng.standard_normal((y1 - y0, width, 3), dtype=np.float32)
+        blk[inside] = tis[inside]
+        img[y0:y1] = np.clip(np.rint(blk), 0, 255).astype(np.uint8)
+    return ArraySlide(img, n_levels)

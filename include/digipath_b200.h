@@ -101,7 +101,8 @@ void dp_d4_src(int code, int i, int j, int P, int* a, int* b);
 uint64_t dp_kernel_launch_count(void);
 
 /* Options: "naive_conv" (0/1: evaluate convs with the CUDA-core reference kernel),
- *          "desc_base_mode" (0/1: UMMA descriptor base_offset policy, bring-up only), "halo_pad8" (0/1: pad halo pitch to 8 pixels, bring-up only). */
+ *          "desc_base_mode" (0/1: UMMA descriptor base_offset policy, bring-up only), "halo_pad8" (0/1: pad halo pitch to 8 pixels, bring-up only),
+ *          "profile" (0/1: record CUDA events around every op for dp_model_op_times). */
 int dp_model_set_option(dp_model* m, const char* key, int value);
 
 /* Number of ops / buffers in the layer program; buffer geometry (per-image H, W, C; fp16 NHWC). */
@@ -116,6 +117,13 @@ int dp_debug_write_buffer(dp_model* m, int buf, int n_tiles, const void* host_fp
  * Head ops write to probs_out (may be NULL if the range has no head). */
 int dp_debug_run_ops(dp_model* m, int n_tiles, int op_begin, int op_end, int tta_out, float* probs_out,
                      void* stream);
+
+/* Per-op device time (ms, CUDA events around each op's launches) of the last run made with option
+ * "profile" = 1; `n` must equal the number of ops.  dp_model_op_info describes op `op` of the layer program
+ * (type: 1 stem gather/im2col, 2 maxpool, 3 conv, 4 bn/pool; conv kind: 1 = 1x1, 3 = 3x3, 4 = upsample+3x3). */
+int dp_model_op_times(dp_model* m, float* ms, int n);
+int dp_model_op_info(const dp_model* m, int op, int* type, int* kind, int* cin, int* cout, int* h, int* w,
+                     uint64_t* macs_per_tile);
 
 /* Executed tensor-core MACs of one forward pass over n_tiles tiles (after the sub-pixel rewrite). */
 int dp_model_executed_macs(const dp_model* m, int n_tiles, uint64_t* macs);

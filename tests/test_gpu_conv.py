@@ -1,0 +1,40 @@
+"""GPU parity: every mode of the tcgen05 implicit-GEMM conv kernel against a CPU evaluation of the same
+packed problem (fp32 math on the fp16 operands), through the C ABI (dp_debug_run_ops)."""
+import numpy as np
+import pytest
+
+import conv_cases
+from gpu_bringup import emu_single
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("name", list(conv_cases.CASES))
+def test_conv_case(name):
+    import torch
+    from digipathai_b200.engine import TileModel
+    pr, x, B = conv_cases.build_case(name)
+    op = pr.ops[0]
+    tta_out = 5 if op.head else 0
+    ref = emu_single(pr, x, tta_out)
+    m = TileModel(pr, device=0, max_batch=B)
+    got = {}
+    for label, naive in (("naive", 1), ("tc", 0)):
+        m.set_option("naive_conv", naive)
+        m.write_buffer(0, x)
+        m.write_buffer(1, np.zeros((B,) + pr.bufs[1], dtype=np.float16))
+        probs = torch.zeros((B, pr.patch, pr.patch), dtype=torch.float32, device="cuda") if op.head else None
+        m.run_ops(B, 0, 1, tta_out, probs)
+        torch.cuda.synchronize()
+        if op.head:
+            got[label] = probs.cpu().numpy()
+        else:
+            full = m.read_buffer(1, B).astype(np.float32)
+            got[label] = full[..., op.out_choff:op.out_choff + op.cout].copy()
+            full[..., op.out_choff:op.out_choff + op.cout] = 0
+            assert np.abs(full).max() == 0, "wrote outside its channel range of the concat buffer"
+    # tolerance: one fp16 rounding of the output (half an ulp at |ref|max) + fp32 accumulation-order noise
+    tol = 1e-5 if op.head else float(np.abs(ref).max()) * 2.0 ** -10
+    assert np.abs(got["tc"] - ref).max() <= tol, (name, np.abs(got["tc"] - ref).max(), tol)
+    assert np.abs(got["naive"] - ref).max() <= tol
+    m.close()

@@ -1,0 +1,74 @@
+"""GPU parity of the drop-in entry points (get_prediction / getSegmentation) against the oracle pipeline."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def env(calibrated_weights):
+    from digipathai_b200.slide import synthetic_slide
+    from oracle import densenet_ref
+    w, _ = calibrated_weights
+    slide = synthetic_slide(1024, 768, seed=5)
+    return w, slide, {"dense": densenet_ref.OracleModel(w)}
+
+
+def test_get_prediction_matches_oracle_pipeline(env):
+    from digipathai_b200.Segmentation import get_prediction, load_trained_models
+    from oracle import pipeline_ref
+    w, slide, omodels = env
+    kw = dict(batch_size=4, patch_size=256, stride_size=128, tta_list=['FLIP_LEFT_RIGHT'])
+    _, want = pipeline_ref.get_prediction(slide, models=omodels, **kw)
+    model = load_trained_models('dense', w, 256, max_batch=4)
+    status = {}
+    _, got = get_prediction(slide, models={'dense': model}, status=status, **kw)
+    assert got['mean'].shape == want['mean'].shape == (1024, 768)
+    d = np.abs(got['mean'] - want['mean'])
+    touched = want['count'] > 0
+    print(f"\nget_prediction: max|mean-oracle| {d.max():.3e} mean {d[touched].mean():.3e}; "
+          f"max|var-oracle| {np.abs(got['var'] - want['var']).max():.3e}")
+    assert d.max() <= 5e-2 and d[touched].mean() <= 5e-3
+    assert np.abs(got['var'] - want['var']).max() <= 5e-3
+    # pixels no tile touched stay exactly zero on both sides; zero pattern of the planes is identical
+    zero_w, zero_g = want['mean'] == 0, got['mean'] == 0
+    assert np.array_equal(zero_w, zero_g)
+    assert 0 <= status['progress'] < 100
+    model.close()
+
+
+def test_get_segmentation_drop_in(env, tmp_path):
+    from digipathai_b200.Segmentation import getSegmentation
+    from oracle import pipeline_ref
+    w, slide, omodels = env
+    want_thr, want_mean, _ = pipeline_ref.getSegmentation(slide, omodels, 256, 128, 4)
+    status = {}
+    mask_path = str(tmp_path / "mask.tiff")
+    probs_path = str(tmp_path / "probs.tiff")
+    got = getSegmentation(slide, patch_size=256, stride_size=128, batch_size=4, quick=True, tta_list=None,
+                          crf=False, save_path=mask_path, status=status, probs_path=probs_path, weights=w)
+    assert got.dtype == np.float32 and got.shape == want_thr.shape and set(np.unique(got)) <= {0.0, 255.0}
+    mism = got != want_thr
+    # labels may only differ where the oracle probability is within the fp16 band of the 0.3 threshold
+    assert (np.abs(want_mean - 0.3)[mism] <= 5e-2).all()
+    print(f"\ngetSegmentation: {int(mism.sum())} / {mism.size} label mismatches, all inside the +-5e-2 band "
+          f"({int((np.abs(want_mean - 0.3) <= 5e-2).sum())} pixels in band)")
+    assert mism.mean() < 0.02
+    assert status['status'] == "Saving Prediction Uncertanity..." and status['progress'] == 0
+    from PIL import Image
+    Image.MAX_IMAGE_PIXELS = None
+    saved = np.asarray(Image.open(mask_path))
+    assert saved.shape == (768, 1024) and np.array_equal(saved, got.T.astype(np.uint8))   # saved transposed (:345)
+
+
+def test_errors_match_the_reference(env):
+    from digipathai_b200.Segmentation import getSegmentation
+    w, slide, _ = env
+    with pytest.raises(ValueError, match="Unknown mode"):
+        getSegmentation(slide, mode='kidney', weights=w)
+    with pytest.raises(ValueError, match="Unknown model"):
+        getSegmentation(slide, model='resnet', weights=w)
+    with pytest.raises(NotImplementedError):
+        getSegmentation(slide, quick=False, weights=w)
+    with pytest.raises(FileNotFoundError):
+        getSegmentation(slide, batch_size=4)          # no converted weights under ~/.DigiPathAI
