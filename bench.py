@@ -155,6 +155,7 @@ def main():
     ap.add_argument("--slide", type=int, default=8192, help="--workload slide: side of the synthetic slide")
     ap.add_argument("--tta", default="", help="--workload slide: comma separated tta_list")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--dump-ops", default="", help="write the per-op device-time table (instrumented pass) here")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -274,6 +275,15 @@ def main():
                  "hw": infos[i]["h"], "ms": round(float(per_op[i]), 4),
                  "exec_tflops": round(2 * infos[i]["macs_per_tile"] * BATCH / (per_op[i] * 1e-3) / 1e12, 1)
                  if per_op[i] > 0 and infos[i]["macs_per_tile"] else None} for i in top]
+
+    if args.dump_ops and rank == 0:
+        names = [o.name for o in model.program.ops]
+        with open(args.dump_ops, "w") as f:
+            f.write("op,name,type,kind,cin,cout,hw,ms,exec_tflops\n")
+            for i, (t, inf) in enumerate(zip(per_op, infos)):
+                tf = 2 * inf["macs_per_tile"] * BATCH / (t * 1e-3) / 1e12 if t > 0 and inf["macs_per_tile"] else 0
+                f.write(f"{i},{names[i]},{inf['type']},{inf['kind']},{inf['cin']},{inf['cout']},{inf['h']},"
+                        f"{t:.4f},{tf:.1f}\n")
 
     cpu_baseline = None
     if rank == 0 and not args.no_cpu_baseline:

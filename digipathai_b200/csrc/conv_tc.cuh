@@ -53,6 +53,7 @@ struct ConvParams {
   int m_total;              // MODE_D: total pixels
   int n_mtiles, n_items;
   int a_stage_bytes, b_stage_bytes, a_stages, b_stages, acc_stages, a_tx_bytes;
+  int b_group;              // tap entries carried by one B stage (TMA box depth)
   int epi_mode, relu;
   int out_ctot, out_choff;  // output NHWC buffer: channel stride and channel offset (elements)
   int desc_base_mode;       // 0: descriptor base_offset field = 0; 1: (addr >> 7) & 7
@@ -118,7 +119,7 @@ __device__ __forceinline__ WorkItem decode_item(const ConvParams& p, int item) {
   return wi;
 }
 
-template <bool PROLOGUE>
+template <int MODE, bool PROLOGUE>
 __global__ void __launch_bounds__(PROLOGUE ? 384 : 256, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                const __grid_constant__ ConvParams p) {
@@ -134,6 +135,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   uint64_t* acc_full = b_empty + kMaxBStages;
   uint64_t* acc_empty = acc_full + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  uint32_t* s_rowoff = tmem_slot + 4;  // [kMaxEntries] A-descriptor offset (16-byte units) of every tap entry
 
   const ConvSmemLayout L = conv_smem_layout(p);
   uint8_t* a_base = smem + L.a_off;
@@ -153,12 +155,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     tma_prefetch_desc(&map_b);
   }
   if (warp == 1 && lane == 0) {
-    for (int i = 0; i < kMaxAStages; ++i) {
+    for (int i = 0; i < p.a_stages; ++i) {
       mbar_init(&a_full[i], 1);
       mbar_init(&a_ready[i], 128);
       mbar_init(&a_empty[i], 1);
     }
-    for (int i = 0; i < kMaxBStages; ++i) {
+    for (int i = 0; i < p.b_stages; ++i) {
       mbar_init(&b_full[i], 1);
       mbar_init(&b_empty[i], 1);
     }
@@ -171,6 +173,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   if (warp == 2) {
     tmem_alloc(tmem_slot, kTmemCols);
     tmem_relinquish();
+  }
+  if (warp == 3 && lane < kMaxEntries) {
+    const TapEntry ent = p.entries[lane];
+    s_rowoff[lane] = (MODE == MODE_H) ? static_cast<uint32_t>(((ent.dy + 1) * p.box_w + (ent.dx + 1)) * 8) : 0u;
   }
   {
     const int cout = p.n_tile * p.n_ntiles;
@@ -192,143 +198,144 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  const int n_bgroups = p.n_entries / p.b_group;  // B stages per (work item, channel chunk)
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
     if (lane == 0) {
-      uint32_t a_it = 0, b_it = 0;
+      uint32_t sa = 0, pa = 0, sb = 0, pb = 0;  // ring slot + phase parity
       for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
         const WorkItem wi = decode_item(p, item);
         const int ebase = wi.ph * p.n_entries;
+        const int n0 = wi.nt * p.n_tile;
         for (int c = 0; c < p.n_chunks; ++c) {
           const int c0 = c * 64;
-          if (p.mode != MODE_T) {
-            const uint32_t sa = a_it % p.a_stages, pa = (a_it / p.a_stages) & 1;
+          if (MODE != MODE_T) {
             mbar_wait(&a_empty[sa], pa ^ 1);
             mbar_expect_tx(&a_full[sa], p.a_tx_bytes);
             uint8_t* dst = a_base + sa * p.a_stage_bytes;
-            if (p.mode == MODE_D) {
+            if (MODE == MODE_D) {
               for (int s = 0; s < p.sub; ++s)
                 tma_load_2d(&map_a, &a_full[sa], dst + s * kATileBytes, c0, wi.m0 + s * 128);
             } else {
               tma_load_4d(&map_a, &a_full[sa], dst, c0, wi.w0 - 1, wi.h0 - 1, wi.n0);
             }
-            ++a_it;
+            if (++sa == p.a_stages) { sa = 0; pa ^= 1; }
           }
-          for (int e = 0; e < p.n_entries; ++e) {
-            if (p.mode == MODE_T) {
-              const TapEntry ent = p.entries[ebase + e];
-              const uint32_t sa = a_it % p.a_stages, pa = (a_it / p.a_stages) & 1;
+          for (int g = 0; g < n_bgroups; ++g) {
+            if (MODE == MODE_T) {  // b_group == 1: one shifted A box per tap
+              const TapEntry ent = p.entries[ebase + g];
               mbar_wait(&a_empty[sa], pa ^ 1);
               mbar_expect_tx(&a_full[sa], p.a_tx_bytes);
               tma_load_4d(&map_a, &a_full[sa], a_base + sa * p.a_stage_bytes, c0, wi.w0 + ent.dx,
                           wi.h0 + ent.dy, wi.n0);
-              ++a_it;
+              if (++sa == p.a_stages) { sa = 0; pa ^= 1; }
             }
-            const uint32_t sb = b_it % p.b_stages, pb = (b_it / p.b_stages) & 1;
             mbar_wait(&b_empty[sb], pb ^ 1);
             mbar_expect_tx(&b_full[sb], p.b_stage_bytes);
-            tma_load_3d(&map_b, &b_full[sb], b_base + sb * p.b_stage_bytes, c0, wi.nt * p.n_tile, ebase + e);
-            ++b_it;
+            tma_load_3d(&map_b, &b_full[sb], b_base + sb * p.b_stage_bytes, c0, n0, ebase + g * p.b_group);
+            if (++sb == p.b_stages) { sb = 0; pb ^= 1; }
           }
         }
       }
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
+    // One thread feeds the tensor core; at N = 32 an MMA retires every 16-40 clocks, so the loop body is kept
+    // to a couple of integer adds per tcgen05.mma (descriptor halves precomputed, +2 per 16-wide K step).
     if (lane == 0) {
       const uint32_t idesc = make_idesc_f16(p.n_tile);
-      const uint32_t a_sbo = (p.mode == MODE_H) ? p.box_w * 128 : 1024;
-      uint32_t a_it = 0, b_it = 0, acc_it = 0;
+      const uint32_t a_hi = sw128_desc_hi((MODE == MODE_H) ? p.box_w * 128 : 1024);
+      const uint32_t b_hi = sw128_desc_hi(1024);
+      const uint32_t a_lo0 = sw128_desc_lo(smem_u32(a_base));
+      const uint32_t b_lo0 = sw128_desc_lo(smem_u32(b_base));
+      const uint32_t a_stage_u = p.a_stage_bytes >> 4, b_stage_u = p.b_stage_bytes >> 4;
+      const uint32_t b_ent_u = (p.n_tile * 128) >> 4;
+      const uint32_t a_sub_u = (MODE == MODE_D) ? (kATileBytes >> 4) : 64u;  // H: 8 pixels = 8 rows of 128 B
+      const uint32_t n_tile = p.n_tile, sub = p.sub, bgroup = p.b_group;
+      const uint32_t d_group_stride = sub * n_tile;
+      uint32_t sa = 0, pa = 0, sb = 0, pb = 0, as = 0, ap = 0;
       for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
-        const WorkItem wi = decode_item(p, item);
-        const int ebase = wi.ph * p.n_entries;
-        const uint32_t as = acc_it % p.acc_stages, ap = (acc_it / p.acc_stages) & 1;
+        const int ebase = (MODE == MODE_T) ? (item / (p.n_mtiles * p.n_ntiles)) * p.n_entries : 0;
         mbar_wait(&acc_empty[as], ap ^ 1);
         tc_fence_after();
+        const uint32_t d_stage = tmem_base + as * p.n_groups * d_group_stride;
         uint32_t inited = 0;
         for (int c = 0; c < p.n_chunks; ++c) {
           int ks = (p.Cin - c * 64 + 15) >> 4;
           ks = ks > 4 ? 4 : ks;
-          uint32_t sa = 0;
-          if (p.mode != MODE_T) {
-            sa = a_it % p.a_stages;
-            const uint32_t pa = (a_it / p.a_stages) & 1;
+          uint32_t a_lo_stage = 0;
+          if (MODE != MODE_T) {
             mbar_wait(PROLOGUE ? &a_ready[sa] : &a_full[sa], pa);
-            tc_fence_after();
+            a_lo_stage = a_lo0 + sa * a_stage_u;
           }
-          for (int e = 0; e < p.n_entries; ++e) {
-            const TapEntry ent = p.entries[ebase + e];
-            if (p.mode == MODE_T) {
-              sa = a_it % p.a_stages;
-              const uint32_t pa = (a_it / p.a_stages) & 1;
+          int e = 0;
+          for (int g = 0; g < n_bgroups; ++g) {
+            if (MODE == MODE_T) {
               mbar_wait(&a_full[sa], pa);
+              a_lo_stage = a_lo0 + sa * a_stage_u;
             }
-            const uint32_t sb = b_it % p.b_stages, pb = (b_it / p.b_stages) & 1;
             mbar_wait(&b_full[sb], pb);
             tc_fence_after();
-            const uint32_t a_stage_addr = smem_u32(a_base + sa * p.a_stage_bytes);
-            const uint32_t b_addr = smem_u32(b_base + sb * p.b_stage_bytes);
-            const uint32_t row_off = (p.mode == MODE_H) ? ((ent.dy + 1) * p.box_w + (ent.dx + 1)) : 0;
-            const uint32_t acc_flag0 = (inited >> ent.group) & 1u;
-            for (int s = 0; s < p.sub; ++s) {
-              const uint32_t a_addr =
-                  a_stage_addr + ((p.mode == MODE_D) ? s * kATileBytes : (row_off + 8 * s) * 128);
-              const uint32_t d_tmem = tmem_base + ((as * p.n_groups + ent.group) * p.sub + s) * p.n_tile;
-              for (int k = 0; k < ks; ++k) {
-                const uint32_t aa = a_addr + k * 32, bb = b_addr + k * 32;
-                const uint64_t adesc = make_sw128_desc(aa, a_sbo, p.desc_base_mode ? ((aa >> 7) & 7) : 0);
-                const uint64_t bdesc = make_sw128_desc(bb, 1024, 0);
-                umma_f16_ss(d_tmem, adesc, bdesc, idesc, (k > 0) ? 1u : acc_flag0);
+            uint32_t b_lo = b_lo0 + sb * b_stage_u;
+            for (uint32_t j = 0; j < bgroup; ++j, ++e, b_lo += b_ent_u) {
+              uint32_t grp = 0;
+              if (MODE == MODE_H) grp = static_cast<uint32_t>(p.entries[e].group);
+              const uint32_t flag0 = (inited >> grp) & 1u;
+              uint32_t a_lo = a_lo_stage + ((MODE == MODE_H) ? s_rowoff[ebase + e] : 0u);
+              uint32_t d = d_stage + grp * d_group_stride;
+              for (uint32_t s = 0; s < sub; ++s, a_lo += a_sub_u, d += n_tile) {
+                umma_f16_ss_parts(d, a_lo, a_hi, b_lo, b_hi, idesc, flag0);
+                if (ks > 1) umma_f16_ss_parts(d, a_lo + 2, a_hi, b_lo + 2, b_hi, idesc, 1u);
+                if (ks > 2) umma_f16_ss_parts(d, a_lo + 4, a_hi, b_lo + 4, b_hi, idesc, 1u);
+                if (ks > 3) umma_f16_ss_parts(d, a_lo + 6, a_hi, b_lo + 6, b_hi, idesc, 1u);
               }
+              inited |= 1u << grp;
             }
-            inited |= 1u << ent.group;
             umma_commit(&b_empty[sb]);
-            ++b_it;
-            if (p.mode == MODE_T) {
+            if (++sb == p.b_stages) { sb = 0; pb ^= 1; }
+            if (MODE == MODE_T) {
               umma_commit(&a_empty[sa]);
-              ++a_it;
+              if (++sa == p.a_stages) { sa = 0; pa ^= 1; }
             }
           }
-          if (p.mode != MODE_T) {
+          if (MODE != MODE_T) {
             umma_commit(&a_empty[sa]);
-            ++a_it;
+            if (++sa == p.a_stages) { sa = 0; pa ^= 1; }
           }
         }
         umma_commit(&acc_full[as]);
-        ++acc_it;
+        if (++as == p.acc_stages) { as = 0; ap ^= 1; }
       }
     }
   } else if (warp >= 4 && warp < 8) {
     // ------------------------------------------------------------------ epilogue
     const int q = warp & 3;
     const int r = q * 32 + lane;  // accumulator row == TMEM lane == pixel within the sub-tile
-    uint32_t acc_it = 0;
+    uint32_t as = 0, ap = 0;
     for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
       const WorkItem wi = decode_item(p, item);
-      const uint32_t as = acc_it % p.acc_stages, ap = (acc_it / p.acc_stages) & 1;
       mbar_wait(&acc_full[as], ap);
       tc_fence_after();
       const int ch0 = wi.nt * p.n_tile;
       for (int g = 0; g < p.n_groups; ++g) {
-        const int ph = (p.mode == MODE_H) ? g : wi.ph;
+        const int ph = (MODE == MODE_H) ? g : wi.ph;
         for (int s = 0; s < p.sub; ++s) {
           // ---- where does this accumulator row land?
           bool valid;
           long long opix;  // output pixel index (flat over n, oh, ow)
-          int n, h, w;
-          if (p.mode == MODE_D) {
+          int n = 0, h = 0, w = 0;
+          if (MODE == MODE_D) {
             const int m = wi.m0 + s * 128 + r;
             valid = m < p.m_total;
             opix = m;
-            n = 0; h = 0; w = 0;
             if (p.epi_mode == EPI_HEAD) {
               n = m / (p.H * p.W);
               const int rem = m - n * p.H * p.W;
               h = rem / p.W; w = rem - h * p.W;
             }
           } else {
-            if (p.mode == MODE_T) {
+            if (MODE == MODE_T) {
               w = wi.w0 + r % p.box_w;
               const int t = r / p.box_w;
               h = wi.h0 + t % p.box_h;
@@ -351,30 +358,37 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
               tmem_base + (static_cast<uint32_t>(q * 32) << 16) + ((as * p.n_groups + g) * p.sub + s) * p.n_tile;
           float head_acc = 0.f;
           __half* orow = p.out ? p.out + opix * p.out_ctot + p.out_choff + ch0 : nullptr;
-          for (int cc = 0; cc < p.n_tile; cc += 16) {
-            uint32_t v[16];
-            tmem_ld16(taddr + cc, v);
+          for (int cc = 0; cc < p.n_tile; cc += 32) {
+            uint32_t v[2][16];
+            const bool two = cc + 16 < p.n_tile;
+            tmem_ld16(taddr + cc, v[0]);
+            if (two) tmem_ld16(taddr + cc + 16, v[1]);
             tmem_ld_wait();
-            float f[16];
 #pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              float x = __uint_as_float(v[i]);
-              x = fmaf(x, s_epi_scale[ch0 + cc + i], s_epi_shift[ch0 + cc + i]);
-              f[i] = p.relu ? fmaxf(x, 0.f) : x;
-            }
-            if (p.epi_mode == EPI_HEAD) {
+            for (int hsel = 0; hsel < 2; ++hsel) {
+              if (hsel == 1 && !two) break;
+              const int cb = cc + 16 * hsel;
+              float f[16];
 #pragma unroll
-              for (int i = 0; i < 16; ++i) head_acc = fmaf(f[i], s_head_w[ch0 + cc + i], head_acc);
-            } else if (valid) {
-              uint32_t pk[8];
-#pragma unroll
-              for (int i = 0; i < 8; ++i) {
-                __half2 h2 = __floats2half2_rn(f[2 * i], f[2 * i + 1]);
-                pk[i] = *reinterpret_cast<uint32_t*>(&h2);
+              for (int i = 0; i < 16; ++i) {
+                float x = __uint_as_float(v[hsel][i]);
+                x = fmaf(x, s_epi_scale[ch0 + cb + i], s_epi_shift[ch0 + cb + i]);
+                f[i] = p.relu ? fmaxf(x, 0.f) : x;
               }
-              uint4* dst = reinterpret_cast<uint4*>(orow + cc);
-              dst[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-              dst[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+              if (p.epi_mode == EPI_HEAD) {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) head_acc = fmaf(f[i], s_head_w[ch0 + cb + i], head_acc);
+              } else if (valid) {
+                uint32_t pk[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                  __half2 h2 = __floats2half2_rn(f[2 * i], f[2 * i + 1]);
+                  pk[i] = *reinterpret_cast<uint32_t*>(&h2);
+                }
+                uint4* dst = reinterpret_cast<uint4*>(orow + cb);
+                dst[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                dst[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+              }
             }
           }
           if (p.epi_mode == EPI_HEAD && valid) {
@@ -389,15 +403,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       }
       tc_fence_before();
       mbar_arrive(&acc_empty[as]);
-      ++acc_it;
+      if (++as == p.acc_stages) { as = 0; ap ^= 1; }
     }
   } else if (PROLOGUE && warp >= 8) {
     // ------------------------------------------------------------------ A-tile pre-activation (MODE_D only)
     const int t = tid - 256;
-    uint32_t a_it = 0;
+    uint32_t sa = 0, pa = 0;
     for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
       for (int c = 0; c < p.n_chunks; ++c) {
-        const uint32_t sa = a_it % p.a_stages, pa = (a_it / p.a_stages) & 1;
         mbar_wait(&a_full[sa], pa);
         for (int s = 0; s < p.sub; ++s) {
           uint8_t* row = a_base + sa * p.a_stage_bytes + s * kATileBytes + t * 128;
@@ -422,7 +435,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         }
         fence_proxy_async_smem();
         mbar_arrive(&a_ready[sa]);
-        ++a_it;
+        if (++sa == p.a_stages) { sa = 0; pa ^= 1; }
       }
     }
   }

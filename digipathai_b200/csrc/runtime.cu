@@ -278,7 +278,12 @@ int plan_conv(dp_model* m, const BlobOp& op, int B, Launch& L) {
     p.a_stage_bytes = round_up(p.a_tx_bytes, 1024);
   }
   p.n_items = p.n_mtiles * p.n_ntiles * p.n_phase_items;
-  p.b_stage_bytes = n_tile * 128;
+  // several taps per B stage for small N: keeps the single producer / MMA-issue threads off the critical path
+  p.b_group = 1;
+  if (p.mode != MODE_T)
+    for (int g = p.n_entries; g >= 1; --g)
+      if (p.n_entries % g == 0 && g * n_tile * 128 <= 36 * 1024) { p.b_group = g; break; }
+  p.b_stage_bytes = p.b_group * n_tile * 128;
   p.acc_stages = (2 * p.n_groups * p.sub * n_tile <= kTmemCols) ? 2 : 1;
 
   // shared-memory ring depths
@@ -330,7 +335,7 @@ int plan_conv(dp_model* m, const BlobOp& op, int B, Launch& L) {
   {
     uint64_t dims[3] = {(uint64_t)op.cin, (uint64_t)op.cout, (uint64_t)n_entries_total};
     uint64_t str[2] = {(uint64_t)op.cin * 2, (uint64_t)op.cin * 2 * op.cout};
-    uint32_t box[3] = {64, (uint32_t)n_tile, 1};
+    uint32_t box[3] = {64, (uint32_t)n_tile, (uint32_t)p.b_group};
     if (make_map(&L.map_b, q.w, 3, dims, str, box)) return 1;
   }
   return 0;
@@ -428,12 +433,17 @@ int run_op(dp_model* m, Plan* plan, int i, int B, const PassArgs& a, cudaStream_
         cp.tta_code = a.tta_out;
         cp.head_out = a.probs_out;
       }
-      if (L.prologue) {
-        CU_OK(cudaFuncSetAttribute(dp::conv_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, L.smem));
-        dp::conv_tc_kernel<true><<<L.grid, 384, L.smem, st>>>(L.map_a, L.map_b, cp);
-      } else {
-        CU_OK(cudaFuncSetAttribute(dp::conv_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, L.smem));
-        dp::conv_tc_kernel<false><<<L.grid, 256, L.smem, st>>>(L.map_a, L.map_b, cp);
+      switch (cp.mode) {
+        case dp::MODE_D:
+          if (L.prologue) dp::conv_tc_kernel<dp::MODE_D, true><<<L.grid, 384, L.smem, st>>>(L.map_a, L.map_b, cp);
+          else dp::conv_tc_kernel<dp::MODE_D, false><<<L.grid, 256, L.smem, st>>>(L.map_a, L.map_b, cp);
+          break;
+        case dp::MODE_T:
+          dp::conv_tc_kernel<dp::MODE_T, false><<<L.grid, 256, L.smem, st>>>(L.map_a, L.map_b, cp);
+          break;
+        default:
+          dp::conv_tc_kernel<dp::MODE_H, false><<<L.grid, 256, L.smem, st>>>(L.map_a, L.map_b, cp);
+          break;
       }
       LAUNCH_OK();
       return 0;
@@ -520,6 +530,17 @@ int dp_model_create(const void* blob, size_t nbytes, int device, int max_batch, 
       e = cudaMalloc(&m->scratch_head, sz);
       if (e != cudaSuccess) { cleanup(); return fail("cudaMalloc head scratch: %s", cudaGetErrorString(e)); }
       m->device_bytes += sz;
+    }
+  }
+  {
+    const int kMaxSmem = 227 * 1024;
+    cudaError_t e1 = cudaFuncSetAttribute(dp::conv_tc_kernel<dp::MODE_D, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
+    cudaError_t e2 = cudaFuncSetAttribute(dp::conv_tc_kernel<dp::MODE_D, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
+    cudaError_t e3 = cudaFuncSetAttribute(dp::conv_tc_kernel<dp::MODE_T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
+    cudaError_t e4 = cudaFuncSetAttribute(dp::conv_tc_kernel<dp::MODE_H, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
+    if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess || e4 != cudaSuccess) {
+      cleanup();
+      return fail("cudaFuncSetAttribute(MaxDynamicSharedMemorySize) failed: %s", cudaGetErrorString(cudaGetLastError()));
     }
   }
   const char* env = getenv("DP_NAIVE_CONV");

