@@ -13,9 +13,12 @@ namespace dp {
 // (dataloader.py:357-388 crop/transposed layout/normalise; utils.py:487-501 TTA; densenet.py:116-117 stem).
 // slide is uint8 [Wslide][Hslide][3] in the reference's [x][y] orientation; tile b has origin coords[b] = (x,y).
 // out is fp16 [B][P/2][P/2][160], column k = (ky*7 + kx)*3 + c for k < 147, zero above.
-__global__ void stem_im2col_kernel(const uint8_t* __restrict__ slide, long long slide_h,
-                                   const int* __restrict__ coords, int B, int P, int tta_code,
+__global__ void stem_im2col_kernel(const PassDesc* __restrict__ pass, int img0, int B, int P,
                                    __half* __restrict__ out) {
+  const uint8_t* __restrict__ slide = pass->slide;
+  const long long slide_h = pass->slide_h;
+  const int* __restrict__ coords = pass->coords + 2 * img0;
+  const int tta_code = pass->tta_in;
   const int OH = P / 2;
   const long long total = static_cast<long long>(B) * OH * OH * 20;
   for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
@@ -138,8 +141,10 @@ __global__ void bn_act_pool_kernel(const __half* __restrict__ in, int in_ctot, i
 // ---------------------------------------------------------------------------------------------------------
 // Head for the naive (debug) path: 1x1 conv C->2 + softmax channel 1 + inverse TTA (densenet.py:156).
 __global__ void head_naive_kernel(const __half* __restrict__ in, int in_ctot, int in_choff, int C, int n_img,
-                                  int P, const float* __restrict__ w, float bias, int tta_code,
-                                  float* __restrict__ out) {
+                                  int P, const float* __restrict__ w, float bias,
+                                  const PassDesc* __restrict__ pass, int img0) {
+  const int tta_code = pass->tta_out;
+  float* __restrict__ out = pass->probs_out + static_cast<long long>(img0) * P * P;
   const long long total = static_cast<long long>(n_img) * P * P;
   for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
        idx += static_cast<long long>(gridDim.x) * blockDim.x) {

@@ -16,4 +16,14 @@ __host__ __device__ __forceinline__ void d4_src(int code, int i, int j, int P, i
   b = (code & 4) ? (P - 1 - v) : v;
 }
 
+// Per-call arguments of one forward pass, resident in device memory so that a captured CUDA graph can be
+// replayed for any slide / tile batch / TTA pass: only this 48-byte record is rewritten (stream-ordered copy).
+struct PassDesc {
+  const unsigned char* slide;  // uint8 [x][y][3]
+  long long slide_h;
+  const int* coords;           // int32 [n_tiles][2]
+  float* probs_out;            // float32 [n_tiles][P][P]
+  int tta_in, tta_out;
+};
+
 }  // namespace dp

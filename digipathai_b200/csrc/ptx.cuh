@@ -140,6 +140,31 @@ __device__ __forceinline__ void umma_f16_ss_parts(uint32_t d_tmem, uint32_t a_lo
       ::"r"(d_tmem), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// Four K-steps (4 x 16 fp16 = one 128-byte swizzled row) of one (A tile, B tile) pair in a single asm block:
+// descriptors advance by 2 (32 bytes) per step.  Issued from an `elect_one()` region ptxas emits these as
+// back-to-back UTCHMMA with one UIADD3.64 each in between.
+__device__ __forceinline__ void umma_f16_ss_k4(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                               uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p, q;\n\t"
+      ".reg .b64 a1, b1, a2, b2, a3, b3;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "setp.eq.b32 q, 0, 0;\n\t"
+      "add.u64 a1, %1, 2;\n\t"
+      "add.u64 b1, %2, 2;\n\t"
+      "add.u64 a2, %1, 4;\n\t"
+      "add.u64 b2, %2, 4;\n\t"
+      "add.u64 a3, %1, 6;\n\t"
+      "add.u64 b3, %2, 6;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], a1, b1, %3, q;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], a2, b2, %3, q;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], a3, b3, %3, q;\n\t"
+      "}\n"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 // hi word of a K-major SWIZZLE_128B descriptor: SBO>>4 [0,14), version=1 [14,16), layout=2 [29,32)
 __device__ __forceinline__ uint32_t sw128_desc_hi(uint32_t sbo_bytes) {
   return ((sbo_bytes >> 4) & 0x3FFF) | (1u << 14) | (2u << 29);

@@ -45,7 +45,11 @@ int fail(const char* fmt, ...) {
   do {                                                                                                     \
     cudaError_t e__ = cudaGetLastError();                                                                  \
     if (e__ != cudaSuccess) return fail("kernel launch failed: %s (%s:%d)", cudaGetErrorString(e__), __FILE__, __LINE__); \
-    g_launches.fetch_add(1, std::memory_order_relaxed);                                                    \
+    {                                                                                                      \
+      cudaStreamCaptureStatus cs__ = cudaStreamCaptureStatusNone;                                          \
+      cudaStreamIsCapturing(st, &cs__);                                                                    \
+      if (cs__ == cudaStreamCaptureStatusNone) g_launches.fetch_add(1, std::memory_order_relaxed);         \
+    }                                                                                                      \
   } while (0)
 
 PFN_cuTensorMapEncodeTiled_v12000 get_encode() {
@@ -112,8 +116,18 @@ struct Launch {
   int head_C = 0;
 };
 
-struct Plan {
+struct SubPlan {
+  int img0 = 0, n_img = 0;       // slice of the call's tile batch this sub-plan covers
   std::vector<Launch> launches;  // one per op
+};
+
+// A plan for one tile count: the batch is cut into `subs.size()` independent sub-batches whose op chains are
+// captured as parallel branches of one CUDA graph -- the ~100 latency-bound small-map kernels of the encoder
+// (16x16 / 8x8 maps) then overlap across branches instead of running back to back.
+struct Plan {
+  std::vector<SubPlan> subs;
+  cudaGraphExec_t exec = nullptr;
+  cudaGraph_t graph = nullptr;
 };
 
 }  // namespace
@@ -128,9 +142,17 @@ struct dp_model {
   __half* scratch_head = nullptr;  // naive path: output of the head-fused conv
   uint64_t device_bytes = 0;
   int naive_conv = 0, desc_base_mode = 0, halo_pad8 = 0, profile = 0;
+  int use_graph = 1, split = 4;
+  unsigned long long* trace_dev = nullptr;  // debug timeline buffer (option "trace_op")
+  int trace_op = -1;
+  dp::PassDesc* pass_dev = nullptr;          // per-call arguments read by the stem and head kernels
+  std::vector<cudaStream_t> branch_streams;  // capture-time fork/join streams
+  std::vector<cudaEvent_t> branch_events;
+  cudaStream_t cap_stream = nullptr;
+  cudaEvent_t fork_event = nullptr;
   std::vector<cudaEvent_t> ev;  // profile option: 2 events per op of the last run
   int ev_begin = 0, ev_end = 0;
-  std::map<int, Plan> plans;
+  std::map<std::pair<int, int>, Plan> plans;  // key: (n_tiles, split)
   std::mutex mu;
 };
 
@@ -161,7 +183,7 @@ void fill_entries(int kind, dp::TapEntry* e, int* n) {
   }
 }
 
-int plan_conv(dp_model* m, const BlobOp& op, int B, Launch& L) {
+int plan_conv(dp_model* m, const BlobOp& op, int img0, int B, Launch& L) {
   using namespace dp;
   const BlobBuf& ib = m->bufs[op.in_buf];
   const int H = ib.H, W = ib.W;
@@ -180,16 +202,20 @@ int plan_conv(dp_model* m, const BlobOp& op, int B, Launch& L) {
   q.n_entries_total = n_entries_total; q.n_groups = up2 ? 4 : 1; q.up2 = up2;
   q.relu = op.relu; q.pro_mode = op.pro;
   memcpy(q.entries, table, sizeof table);
-  q.in = m->buf_dev[op.in_buf];
+  auto buf_at = [&](int buf) {
+    const BlobBuf& bb = m->bufs[buf];
+    return m->buf_dev[buf] + (size_t)img0 * bb.H * bb.W * bb.C;
+  };
+  q.in = buf_at(op.in_buf);
   q.w = dptr<__half>(m, op.w_off);
   q.epi_scale = dptr<float>(m, op.epi_scale_off);
   q.epi_shift = dptr<float>(m, op.epi_shift_off);
   q.pro_scale = dptr<float>(m, op.pro_scale_off);
   q.pro_shift = dptr<float>(m, op.pro_shift_off);
   if (op.head) {
-    q.out = m->scratch_head; q.out_ctot = op.cout; q.out_choff = 0;
+    q.out = m->scratch_head + (size_t)img0 * m->patch * m->patch * op.cout; q.out_ctot = op.cout; q.out_choff = 0;
   } else {
-    q.out = m->buf_dev[op.out_buf]; q.out_ctot = m->bufs[op.out_buf].C; q.out_choff = op.out_choff;
+    q.out = buf_at(op.out_buf); q.out_ctot = m->bufs[op.out_buf].C; q.out_choff = op.out_choff;
   }
   L.head_C = op.cout;
 
@@ -206,8 +232,10 @@ int plan_conv(dp_model* m, const BlobOp& op, int B, Launch& L) {
   p.head_w = dptr<float>(m, op.head_w_off);
   p.head_b = op.head_b;
   p.P = m->patch;
+  p.img0 = img0;
+  p.pass = m->pass_dev;
   if (!op.head) {
-    p.out = m->buf_dev[op.out_buf];
+    p.out = buf_at(op.out_buf);
     p.out_ctot = m->bufs[op.out_buf].C;
     p.out_choff = op.out_choff;
   }
@@ -288,7 +316,7 @@ int plan_conv(dp_model* m, const BlobOp& op, int B, Launch& L) {
 
   // shared-memory ring depths
   const int budget = 227 * 1024 - ConvSmemLayout::kBarBytes - 2 * op.cout * 4 - 2 * p.n_chunks * 64 * 4 - 256 * 4 -
-                     1024;
+                     4 * kEpiStageBytes - 1024;
   int a_stages = (p.mode == MODE_H) ? 2 : 4;
   while (a_stages > 1 && a_stages * p.a_stage_bytes + 2 * p.b_stage_bytes > budget) --a_stages;
   int b_stages = (budget - a_stages * p.a_stage_bytes) / p.b_stage_bytes;
@@ -319,7 +347,7 @@ int plan_conv(dp_model* m, const BlobOp& op, int B, Launch& L) {
   }
 
   // ---- tensor maps
-  const __half* in_base = m->buf_dev[op.in_buf] + op.in_choff;
+  const __half* in_base = buf_at(op.in_buf) + op.in_choff;
   const uint64_t cstride = (uint64_t)ib.C * 2;
   if (p.mode == MODE_D) {
     uint64_t dims[2] = {(uint64_t)op.cin, (uint64_t)m_total};
@@ -341,24 +369,33 @@ int plan_conv(dp_model* m, const BlobOp& op, int B, Launch& L) {
   return 0;
 }
 
-int get_plan(dp_model* m, int B, Plan** out) {
+int get_plan(dp_model* m, int B, int split, Plan** out) {
   std::lock_guard<std::mutex> lk(m->mu);
-  auto it = m->plans.find(B);
+  if (split < 1 || B % split || B / split < 1) split = 1;
+  auto key = std::make_pair(B, split);
+  auto it = m->plans.find(key);
   if (it != m->plans.end()) {
     *out = &it->second;
     return 0;
   }
   Plan plan;
-  plan.launches.resize(m->ops.size());
-  for (size_t i = 0; i < m->ops.size(); ++i) {
-    plan.launches[i].type = m->ops[i].type;
-    if (m->ops[i].type == OP_CONV)
-      if (plan_conv(m, m->ops[i], B, plan.launches[i])) {
-        g_err = "op " + std::to_string(i) + ": " + g_err;
-        return 1;
-      }
+  plan.subs.resize(split);
+  const int bs = B / split;
+  for (int s = 0; s < split; ++s) {
+    SubPlan& sp = plan.subs[s];
+    sp.img0 = s * bs;
+    sp.n_img = bs;
+    sp.launches.resize(m->ops.size());
+    for (size_t i = 0; i < m->ops.size(); ++i) {
+      sp.launches[i].type = m->ops[i].type;
+      if (m->ops[i].type == OP_CONV)
+        if (plan_conv(m, m->ops[i], sp.img0, bs, sp.launches[i])) {
+          g_err = "op " + std::to_string(i) + ": " + g_err;
+          return 1;
+        }
+    }
   }
-  auto res = m->plans.emplace(B, std::move(plan));
+  auto res = m->plans.emplace(key, std::move(plan));
   *out = &res.first->second;
   return 0;
 }
@@ -369,25 +406,21 @@ int grid_for(long long total, int threads) {
   return (int)(g < 1 ? 1 : (g > cap ? cap : g));
 }
 
-struct PassArgs {
-  const uint8_t* slide = nullptr;
-  long long slide_h = 0;
-  const int32_t* coords = nullptr;
-  int tta_in = 0, tta_out = 0;
-  float* probs_out = nullptr;
-};
-
-int run_op(dp_model* m, Plan* plan, int i, int B, const PassArgs& a, cudaStream_t st) {
+int run_op(dp_model* m, SubPlan* sp, int i, cudaStream_t st) {
   const BlobOp& op = m->ops[i];
-  Launch& L = plan->launches[i];
+  Launch& L = sp->launches[i];
+  const int B = sp->n_img, img0 = sp->img0;
+  auto buf_at = [&](int buf) {
+    const BlobBuf& bb = m->bufs[buf];
+    return m->buf_dev[buf] + (size_t)img0 * bb.H * bb.W * bb.C;
+  };
   switch (op.type) {
     case OP_STEM_IM2COL: {
-      if (!a.slide || !a.coords) return fail("stem op needs a slide and tile coordinates");
       const BlobBuf& ob = m->bufs[op.out_buf];
       if (ob.C != 160 || ob.H != m->patch / 2) return fail("stem im2col buffer must be [P/2][P/2][160]");
       const long long total = (long long)B * ob.H * ob.W * 20;
-      dp::stem_im2col_kernel<<<grid_for(total, 256), 256, 0, st>>>(a.slide, a.slide_h, a.coords, B, m->patch,
-                                                                   a.tta_in, m->buf_dev[op.out_buf]);
+      dp::stem_im2col_kernel<<<grid_for(total, 256), 256, 0, st>>>(m->pass_dev, img0, B, m->patch,
+                                                                   buf_at(op.out_buf));
       LAUNCH_OK();
       return 0;
     }
@@ -395,9 +428,9 @@ int run_op(dp_model* m, Plan* plan, int i, int B, const PassArgs& a, cudaStream_
       const BlobBuf& ib = m->bufs[op.in_buf];
       const BlobBuf& ob = m->bufs[op.out_buf];
       const long long total = (long long)B * (ib.H / 2) * (ib.W / 2) * (op.cin / 8);
-      dp::maxpool3s2_kernel<<<grid_for(total, 256), 256, 0, st>>>(m->buf_dev[op.in_buf], ib.C, op.in_choff,
-                                                                  m->buf_dev[op.out_buf], ob.C, op.out_choff, B,
-                                                                  ib.H, ib.W, op.cin);
+      dp::maxpool3s2_kernel<<<grid_for(total, 256), 256, 0, st>>>(buf_at(op.in_buf), ib.C, op.in_choff,
+                                                                  buf_at(op.out_buf), ob.C, op.out_choff, B, ib.H,
+                                                                  ib.W, op.cin);
       LAUNCH_OK();
       return 0;
     }
@@ -407,32 +440,28 @@ int run_op(dp_model* m, Plan* plan, int i, int B, const PassArgs& a, cudaStream_
       const int OH = op.pool ? ib.H / 2 : ib.H, OW = op.pool ? ib.W / 2 : ib.W;
       const long long total = (long long)B * OH * OW * (op.cin / 8);
       dp::bn_act_pool_kernel<<<grid_for(total, 256), 256, 0, st>>>(
-          m->buf_dev[op.in_buf], ib.C, op.in_choff, m->buf_dev[op.out_buf], ob.C, op.out_choff, B, ib.H, ib.W,
-          op.cin, dptr<float>(m, op.epi_scale_off), dptr<float>(m, op.epi_shift_off), op.relu, op.pool);
+          buf_at(op.in_buf), ib.C, op.in_choff, buf_at(op.out_buf), ob.C, op.out_choff, B, ib.H, ib.W, op.cin,
+          dptr<float>(m, op.epi_scale_off), dptr<float>(m, op.epi_shift_off), op.relu, op.pool);
       LAUNCH_OK();
       return 0;
     }
     case OP_CONV: {
-      if (op.head && !a.probs_out) return fail("head op needs a probability output buffer");
       if (m->naive_conv) {
         const long long total = (long long)B * L.np.H * L.np.W * L.np.n_groups * L.np.Cout;
         dp::conv_naive_kernel<<<grid_for(total, 256), 256, 0, st>>>(L.np);
         LAUNCH_OK();
         if (op.head) {
           const long long tot = (long long)B * m->patch * m->patch;
-          dp::head_naive_kernel<<<grid_for(tot, 256), 256, 0, st>>>(m->scratch_head, op.cout, 0, op.cout, B,
-                                                                    m->patch, dptr<float>(m, op.head_w_off),
-                                                                    op.head_b, a.tta_out, a.probs_out);
+          dp::head_naive_kernel<<<grid_for(tot, 256), 256, 0, st>>>(L.np.out, op.cout, 0, op.cout, B, m->patch,
+                                                                    dptr<float>(m, op.head_w_off), op.head_b,
+                                                                    m->pass_dev, img0);
           LAUNCH_OK();
         }
         return 0;
       }
       dp::ConvParams cp = L.cp;
       cp.desc_base_mode = m->desc_base_mode;
-      if (op.head) {
-        cp.tta_code = a.tta_out;
-        cp.head_out = a.probs_out;
-      }
+      cp.trace = (m->trace_op == i) ? m->trace_dev : nullptr;
       switch (cp.mode) {
         case dp::MODE_D:
           if (L.prologue) dp::conv_tc_kernel<dp::MODE_D, true><<<L.grid, 384, L.smem, st>>>(L.map_a, L.map_b, cp);
@@ -512,6 +541,7 @@ int dp_model_create(const void* blob, size_t nbytes, int device, int max_batch, 
   m->device_bytes += m->data_bytes;
   e = cudaMemcpy(m->data_dev, bytes + h.data_off, m->data_bytes, cudaMemcpyHostToDevice);
   if (e != cudaSuccess) { cleanup(); return fail("cudaMemcpy weights: %s", cudaGetErrorString(e)); }
+  const char* env = nullptr;
   m->buf_dev.assign(h.n_bufs, nullptr);
   for (uint32_t i = 0; i < h.n_bufs; ++i) {
     const BlobBuf& b = m->bufs[i];
@@ -532,6 +562,11 @@ int dp_model_create(const void* blob, size_t nbytes, int device, int max_batch, 
       m->device_bytes += sz;
     }
   }
+  e = cudaMalloc(&m->pass_dev, sizeof(dp::PassDesc));
+  if (e != cudaSuccess) { cleanup(); return fail("cudaMalloc pass descriptor: %s", cudaGetErrorString(e)); }
+  cudaMemset(m->pass_dev, 0, sizeof(dp::PassDesc));
+  env = getenv("DP_SPLIT");
+  if (env && atoi(env) > 0) m->split = atoi(env);
   {
     const int kMaxSmem = 227 * 1024;
     cudaError_t e1 = cudaFuncSetAttribute(dp::conv_tc_kernel<dp::MODE_D, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
@@ -543,7 +578,7 @@ int dp_model_create(const void* blob, size_t nbytes, int device, int max_batch, 
       return fail("cudaFuncSetAttribute(MaxDynamicSharedMemorySize) failed: %s", cudaGetErrorString(cudaGetLastError()));
     }
   }
-  const char* env = getenv("DP_NAIVE_CONV");
+  env = getenv("DP_NAIVE_CONV");
   if (env && atoi(env)) m->naive_conv = 1;
   env = getenv("DP_DESC_BASE_MODE");
   if (env) m->desc_base_mode = atoi(env);
@@ -556,6 +591,16 @@ int dp_model_destroy(dp_model* m) {
   cudaSetDevice(m->device);
   cudaDeviceSynchronize();
   for (cudaEvent_t e : m->ev) cudaEventDestroy(e);
+  for (auto& kv : m->plans) {
+    if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
+    if (kv.second.graph) cudaGraphDestroy(kv.second.graph);
+  }
+  for (cudaStream_t bs : m->branch_streams) cudaStreamDestroy(bs);
+  for (cudaEvent_t be : m->branch_events) cudaEventDestroy(be);
+  if (m->cap_stream) cudaStreamDestroy(m->cap_stream);
+  if (m->fork_event) cudaEventDestroy(m->fork_event);
+  if (m->pass_dev) cudaFree(m->pass_dev);
+  if (m->trace_dev) cudaFree(m->trace_dev);
   for (__half* p : m->buf_dev)
     if (p) cudaFree(p);
   if (m->scratch_head) cudaFree(m->scratch_head);
@@ -577,9 +622,20 @@ int dp_model_set_option(dp_model* m, const char* key, int value) {
   if (!strcmp(key, "naive_conv")) m->naive_conv = value;
   else if (!strcmp(key, "desc_base_mode")) m->desc_base_mode = value;
   else if (!strcmp(key, "profile")) m->profile = value;
+  else if (!strcmp(key, "use_graph")) m->use_graph = value;
+  else if (!strcmp(key, "trace_op")) {
+    if (!m->trace_dev) CU_OK(cudaMalloc(&m->trace_dev, 10016 * sizeof(unsigned long long)));
+    CU_OK(cudaMemset(m->trace_dev, 0, 10016 * sizeof(unsigned long long)));
+    m->trace_op = value;
+  }
+  else if (!strcmp(key, "split")) m->split = value < 1 ? 1 : value;
   else if (!strcmp(key, "halo_pad8")) {
     std::lock_guard<std::mutex> lk(m->mu);
     m->halo_pad8 = value;
+    for (auto& kv : m->plans) {
+      if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
+      if (kv.second.graph) cudaGraphDestroy(kv.second.graph);
+    }
     m->plans.clear();  // tile shapes depend on it
   }
   else return fail("unknown option '%s'", key);
@@ -602,21 +658,32 @@ int dp_model_buffer_shape(const dp_model* m, int buf, int* h, int* w, int* c) {
   return 0;
 }
 
-static int run_range(dp_model* m, int B, int op_begin, int op_end, const PassArgs& a, void* stream) {
+static int upload_pass(dp_model* m, const dp::PassDesc& d, cudaStream_t st) {
+  // pageable-host source: the runtime stages the 48 bytes before returning, so `d` may live on the stack
+  CU_OK(cudaMemcpyAsync(m->pass_dev, &d, sizeof d, cudaMemcpyHostToDevice, st));
+  return 0;
+}
+
+// Direct (un-captured) execution of ops [op_begin, op_end) on the whole batch: profiling, naive and debug paths.
+static int run_range(dp_model* m, int B, int op_begin, int op_end, const dp::PassDesc& d, void* stream) {
   if (check_model(m)) return 1;
   if (B < 1 || B > m->max_batch) return fail("n_tiles %d outside [1, %d]", B, m->max_batch);
   if (op_begin < 0 || op_end > (int)m->ops.size() || op_begin > op_end) return fail("op range out of bounds");
   CU_OK(cudaSetDevice(m->device));
   Plan* plan = nullptr;
-  if (get_plan(m, B, &plan)) return 1;
+  if (get_plan(m, B, 1, &plan)) return 1;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (upload_pass(m, d, st)) return 1;
   if (m->profile && m->ev.empty()) {
     m->ev.resize(2 * m->ops.size());
     for (auto& e : m->ev) CU_OK(cudaEventCreate(&e));
   }
   for (int i = op_begin; i < op_end; ++i) {
+    const BlobOp& op = m->ops[i];
+    if (op.type == OP_STEM_IM2COL && (!d.slide || !d.coords)) return fail("op %d: stem needs a slide and coordinates", i);
+    if (op.type == OP_CONV && op.head && !d.probs_out) return fail("op %d: head needs a probability output buffer", i);
     if (m->profile) CU_OK(cudaEventRecord(m->ev[2 * i], st));
-    if (run_op(m, plan, i, B, a, st)) {
+    if (run_op(m, &plan->subs[0], i, st)) {
       g_err = "op " + std::to_string(i) + ": " + g_err;
       return 1;
     }
@@ -626,22 +693,80 @@ static int run_range(dp_model* m, int B, int op_begin, int op_end, const PassArg
   return 0;
 }
 
+// Whole forward as one CUDA-graph launch: `split` parallel branches, one per sub-batch.
+static int run_graph(dp_model* m, int B, const dp::PassDesc& d, void* stream) {
+  CU_OK(cudaSetDevice(m->device));
+  Plan* plan = nullptr;
+  if (get_plan(m, B, m->split, &plan)) return 1;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (!plan->exec) {
+    std::lock_guard<std::mutex> lk(m->mu);
+    if (!plan->exec) {
+      const int ns = (int)plan->subs.size();
+      if (!m->cap_stream) {
+        CU_OK(cudaStreamCreateWithFlags(&m->cap_stream, cudaStreamNonBlocking));
+        CU_OK(cudaEventCreateWithFlags(&m->fork_event, cudaEventDisableTiming));
+      }
+      while ((int)m->branch_streams.size() < ns) {
+        cudaStream_t bs; cudaEvent_t be;
+        CU_OK(cudaStreamCreateWithFlags(&bs, cudaStreamNonBlocking));
+        CU_OK(cudaEventCreateWithFlags(&be, cudaEventDisableTiming));
+        m->branch_streams.push_back(bs);
+        m->branch_events.push_back(be);
+      }
+      CU_OK(cudaStreamBeginCapture(m->cap_stream, cudaStreamCaptureModeThreadLocal));
+      int rc = 0;
+      cudaError_t ce = cudaEventRecord(m->fork_event, m->cap_stream);
+      for (int s = 0; s < ns && !rc && ce == cudaSuccess; ++s) {
+        cudaStream_t bs = (s == 0) ? m->cap_stream : m->branch_streams[s];
+        if (s) ce = cudaStreamWaitEvent(bs, m->fork_event, 0);
+        for (int i = 0; i < (int)m->ops.size() && !rc && ce == cudaSuccess; ++i) rc = run_op(m, &plan->subs[s], i, bs);
+        if (s && !rc && ce == cudaSuccess) {
+          ce = cudaEventRecord(m->branch_events[s], bs);
+          if (ce == cudaSuccess) ce = cudaStreamWaitEvent(m->cap_stream, m->branch_events[s], 0);
+        }
+      }
+      cudaGraph_t g = nullptr;
+      cudaError_t ee = cudaStreamEndCapture(m->cap_stream, &g);
+      if (rc) return 1;
+      if (ce != cudaSuccess) return fail("graph capture failed: %s", cudaGetErrorString(ce));
+      if (ee != cudaSuccess) return fail("cudaStreamEndCapture failed: %s", cudaGetErrorString(ee));
+      cudaGraphExec_t ex = nullptr;
+      CU_OK(cudaGraphInstantiate(&ex, g, 0));
+      plan->graph = g;
+      plan->exec = ex;
+    }
+  }
+  if (upload_pass(m, d, st)) return 1;
+  CU_OK(cudaGraphLaunch(plan->exec, st));
+  {
+    uint64_t n = 0;
+    for (const SubPlan& sp : plan->subs) n += sp.launches.size();
+    g_launches.fetch_add(n, std::memory_order_relaxed);
+  }
+  return 0;
+}
+
 int dp_forward_tiles(dp_model* m, const uint8_t* slide, int64_t slide_w, int64_t slide_h, const int32_t* coords,
                      int n_tiles, int tta_in, int tta_out, float* probs_out, void* stream) {
+  if (check_model(m)) return 1;
   if (!slide || !coords || !probs_out) return fail("null argument");
   if (slide_w < 1 || slide_h < 1) return fail("bad slide extent");
   if ((tta_in | tta_out) & ~7) return fail("D4 codes must be in [0, 8)");
-  PassArgs a;
-  a.slide = slide; a.slide_h = slide_h; a.coords = coords;
-  a.tta_in = tta_in; a.tta_out = tta_out; a.probs_out = probs_out;
-  return run_range(m, n_tiles, 0, m ? (int)m->ops.size() : 0, a, stream);
+  if (n_tiles < 1 || n_tiles > m->max_batch) return fail("n_tiles %d outside [1, %d]", n_tiles, m->max_batch);
+  dp::PassDesc d;
+  d.slide = slide; d.slide_h = slide_h; d.coords = coords; d.probs_out = probs_out;
+  d.tta_in = tta_in; d.tta_out = tta_out;
+  if (m->use_graph && !m->profile && !m->naive_conv) return run_graph(m, n_tiles, d, stream);
+  return run_range(m, n_tiles, 0, (int)m->ops.size(), d, stream);
 }
 
 int dp_debug_run_ops(dp_model* m, int n_tiles, int op_begin, int op_end, int tta_out, float* probs_out,
                      void* stream) {
-  PassArgs a;
-  a.tta_out = tta_out; a.probs_out = probs_out;
-  return run_range(m, n_tiles, op_begin, op_end, a, stream);
+  dp::PassDesc d;
+  memset(&d, 0, sizeof d);
+  d.tta_out = tta_out; d.probs_out = probs_out;
+  return run_range(m, n_tiles, op_begin, op_end, d, stream);
 }
 
 int dp_debug_read_buffer(dp_model* m, int buf, int n_tiles, void* host, size_t nbytes) {
@@ -681,6 +806,16 @@ int dp_model_op_times(dp_model* m, float* ms, int n) {
   return 0;
 }
 
+int dp_debug_read_trace(dp_model* m, unsigned long long* out, int n) {
+  if (check_model(m) || !out) return fail("null argument");
+  if (!m->trace_dev) return fail("no trace buffer (set option 'trace_op')");
+  if (n > 10016) n = 10016;
+  CU_OK(cudaSetDevice(m->device));
+  CU_OK(cudaDeviceSynchronize());
+  CU_OK(cudaMemcpy(out, m->trace_dev, (size_t)n * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+  return 0;
+}
+
 int dp_model_op_info(const dp_model* m, int op, int* type, int* kind, int* cin, int* cout, int* h, int* w,
                      uint64_t* macs_per_tile) {
   if (check_model(m)) return 1;
@@ -696,8 +831,8 @@ int dp_model_op_info(const dp_model* m, int op, int* type, int* kind, int* cin, 
     *macs_per_tile = 0;
     if (o.type == OP_CONV) {
       Plan* plan = nullptr;
-      if (get_plan(const_cast<dp_model*>(m), 1, &plan)) return 1;
-      *macs_per_tile = plan->launches[op].macs;
+      if (get_plan(const_cast<dp_model*>(m), 1, 1, &plan)) return 1;
+      *macs_per_tile = plan->subs[0].launches[op].macs;
     }
   }
   return 0;
@@ -706,41 +841,44 @@ int dp_model_op_info(const dp_model* m, int op, int* type, int* kind, int* cin, 
 int dp_model_executed_macs(const dp_model* m, int n_tiles, uint64_t* macs) {
   if (check_model(m) || !macs) return fail("null argument");
   Plan* plan = nullptr;
-  if (get_plan(const_cast<dp_model*>(m), n_tiles, &plan)) return 1;
+  if (get_plan(const_cast<dp_model*>(m), n_tiles, 1, &plan)) return 1;
   uint64_t t = 0;
-  for (const Launch& L : plan->launches) t += L.macs;
+  for (const Launch& L : plan->subs[0].launches) t += L.macs;
   *macs = t;
   return 0;
 }
 
 int dp_stitch(const float* probs, int n_pass, int n_tiles, int patch, const int32_t* coords, float* mean,
               float* var, uint8_t* count, int64_t plane_w, int64_t plane_h, int64_t x_lo, void* stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (!probs || !coords || !mean || !var || !count) return fail("null argument");
   if (n_pass < 1 || n_tiles < 1 || patch < 1 || plane_w < patch || plane_h < patch) return fail("bad stitch geometry");
   if (n_tiles > 4096) return fail("at most 4096 tiles per stitch call");
   dim3 grid((patch * patch + 255) / 256, n_tiles);
-  dp::stitch_kernel<<<grid, 256, 2 * n_tiles * sizeof(int), static_cast<cudaStream_t>(stream)>>>(
+  dp::stitch_kernel<<<grid, 256, 2 * n_tiles * sizeof(int), st>>>(
       probs, n_pass, n_tiles, patch, coords, mean, var, count, plane_h, (int)x_lo);
   LAUNCH_OK();
   return 0;
 }
 
 int dp_finalize(float* mean, float* var, uint8_t* count, int64_t n, float threshold, uint8_t* label, void* stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (!mean || !var || !count) return fail("null argument");
   if (n < 1) return fail("empty plane");
   if ((reinterpret_cast<uintptr_t>(mean) | reinterpret_cast<uintptr_t>(var) | reinterpret_cast<uintptr_t>(count) |
        reinterpret_cast<uintptr_t>(label)) & 15)
     return fail("plane pointers must be 16-byte aligned");
-  dp::finalize_kernel<<<grid_for((n + 15) / 16, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  dp::finalize_kernel<<<grid_for((n + 15) / 16, 256), 256, 0, st>>>(
       mean, var, count, n, threshold, label);
   LAUNCH_OK();
   return 0;
 }
 
 int dp_pyramid_down2(const float* in, int64_t w, int64_t h, float* out, void* stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (!in || !out) return fail("null argument");
   if (w < 2 || h < 2) return fail("plane too small");
-  dp::pyramid_down2_kernel<<<grid_for((w / 2) * (h / 2), 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(in, w, h,
+  dp::pyramid_down2_kernel<<<grid_for((w / 2) * (h / 2), 256), 256, 0, st>>>(in, w, h,
                                                                                                           out);
   LAUNCH_OK();
   return 0;

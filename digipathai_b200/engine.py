@@ -150,6 +150,18 @@ class TileModel:
         d["macs_per_tile"] = macs.value
         return d
 
+    def read_trace(self):
+        """[(role, event, item, clock32)] of CTA 0 for the op selected with set_option('trace_op', i)."""
+        arr = (C.c_uint64 * 10016)()
+        _lib.check(_lib.lib.dp_debug_read_trace(self._h, arr, 10016))
+        out = []
+        for role in range(5):
+            n = min(int(arr[role]), 2000)
+            base = 8 + 2000 * role
+            for v in arr[base:base + n]:
+                out.append((9 if role == 4 else role, (v >> 48) & 0xFF, (v >> 32) & 0xFFFF, v & 0xFFFFFFFF))
+        return out
+
     def executed_macs(self, n_tiles: int) -> int:
         v = C.c_uint64()
         _lib.check(_lib.lib.dp_model_executed_macs(self._h, n_tiles, C.byref(v)))

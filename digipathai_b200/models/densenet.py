@@ -95,9 +95,11 @@ def densenet121_unet_program(weights: dict, patch: int = 256) -> Program:
     ops = pr.ops
     # ---- stem: pad3 + conv7x7/2 + BN + ReLU (densenet.py:116-120), as im2col + one GEMM
     ops.append(Op(OP_STEM_IM2COL, out_buf=S, cout=160, name="stem_im2col"))
+    # BatchNorm scales that follow a conv are folded into its weights in fp32 before the single rounding to
+    # fp16 (same relative error as rounding the raw weights); the epilogue then only adds the shift.
     sc, sh = bn_affine(*weights["conv1/bn"], EPS_ENC)
     ops.append(Op(OP_CONV, in_buf=S, cin=160, out_buf=D1, out_choff=96, cout=64, kind=KIND_1X1, relu=1,
-                  w=pack_stem_weights(weights["conv1/conv"]), epi_scale=sc, epi_shift=sh, name="conv1"))
+                  w=pack_stem_weights(weights["conv1/conv"] * sc), epi_shift=sh, name="conv1"))
     # ---- pad1 + maxpool3/2 (densenet.py:122-123) straight into block2's concat buffer
     ops.append(Op(OP_MAXPOOL, in_buf=D1, in_choff=96, cin=64, out_buf=D2, out_choff=128, cout=64, name="pool1"))
 
@@ -111,8 +113,8 @@ def densenet121_unet_program(weights: dict, patch: int = 256) -> Program:
             es, esh = bn_affine(*weights[p + "_1_bn"], EPS_ENC)
             # BN-ReLU (pre-activation, in the A-tile prologue) -> 1x1 -> BN-ReLU (epilogue)   densenet.py:59-69
             ops.append(Op(OP_CONV, in_buf=D, in_choff=base, cin=c, out_buf=T[b], cout=128, kind=KIND_1X1, relu=1,
-                          pro=PRO_AFFINE_RELU, pro_scale=pad64(ps), pro_shift=pad64(psh), epi_scale=es,
-                          epi_shift=esh, w=pack_conv_weights(weights[p + "_1_conv"], KIND_1X1), name=p + "_1_conv"))
+                          pro=PRO_AFFINE_RELU, pro_scale=pad64(ps), pro_shift=pad64(psh), epi_shift=esh,
+                          w=pack_conv_weights(weights[p + "_1_conv"] * es, KIND_1X1), name=p + "_1_conv"))
             # 3x3 -> its 32 channels land at the tail of the concat buffer               densenet.py:70-74
             ops.append(Op(OP_CONV, in_buf=T[b], cin=128, out_buf=D, out_choff=base + c, cout=GROWTH, kind=KIND_3X3,
                           w=pack_conv_weights(weights[p + "_2_conv"], KIND_3X3), name=p + "_2_conv"))
@@ -136,7 +138,7 @@ def densenet121_unet_program(weights: dict, patch: int = 256) -> Program:
         s, t = bn_affine(g, be, mu, var, EPS_DEC)
         t = (t + weights[name + "_conv_bias"].astype(np.float32) * s).astype(np.float32)  # conv bias folded
         o = Op(OP_CONV, in_buf=ib, in_choff=ioff, cin=cin, out_buf=ob, out_choff=ooff, cout=cout, kind=kind, relu=1,
-               epi_scale=s, epi_shift=t, w=pack_conv_weights(weights[name + "_conv"], kind), name=name)
+               epi_shift=t, w=pack_conv_weights(weights[name + "_conv"] * s, kind), name=name)
         if head:
             # Conv2D(2, 1x1, softmax) (densenet.py:156): only channel 1 is consumed downstream
             # (Segmentation.py:167), and softmax(z)[1] == sigmoid(z1 - z0).

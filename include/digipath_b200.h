@@ -67,6 +67,8 @@ int dp_model_info(const dp_model* m, int* patch, int* max_batch, uint64_t* devic
  *   tta_out    D4 code of the transform whose inverse is applied to the prediction (transform_prob)
  *   probs_out  device, float32 [n_tiles][P][P]: softmax channel 1 (the only channel the reference consumes,
  *              Segmentation.py:167), already inverse-transformed.
+ * A model serves one stream at a time: the per-call arguments live in one device-side record that is rewritten
+ * (stream-ordered) before each captured graph replay.
  */
 int dp_forward_tiles(dp_model* m, const uint8_t* slide, int64_t slide_w, int64_t slide_h, const int32_t* coords,
                      int n_tiles, int tta_in, int tta_out, float* probs_out, void* stream);
@@ -102,7 +104,9 @@ uint64_t dp_kernel_launch_count(void);
 
 /* Options: "naive_conv" (0/1: evaluate convs with the CUDA-core reference kernel),
  *          "desc_base_mode" (0/1: UMMA descriptor base_offset policy, bring-up only), "halo_pad8" (0/1: pad halo pitch to 8 pixels, bring-up only),
- *          "profile" (0/1: record CUDA events around every op for dp_model_op_times). */
+ *          "profile" (0/1: record CUDA events around every op for dp_model_op_times; implies direct launches),
+ *          "use_graph" (0/1, default 1: replay dp_forward_tiles as one captured CUDA graph),
+ *          "split" (default 4: number of sub-batches captured as parallel graph branches). */
 int dp_model_set_option(dp_model* m, const char* key, int value);
 
 /* Number of ops / buffers in the layer program; buffer geometry (per-image H, W, C; fp16 NHWC). */
@@ -124,6 +128,11 @@ int dp_debug_run_ops(dp_model* m, int n_tiles, int op_begin, int op_end, int tta
 int dp_model_op_times(dp_model* m, float* ms, int n);
 int dp_model_op_info(const dp_model* m, int op, int* type, int* kind, int* cin, int* cout, int* h, int* w,
                      uint64_t* macs_per_tile);
+
+/* Debug timeline of CTA 0 of the conv op selected with option "trace_op" (direct-launch path only):
+ * out[r] = entries of role r (0 producer, 1 MMA, 2 epilogue, 3 transform, 4 setup); role r's entries start at
+ * out[8 + 2000 r], each event<<48 | item<<32 | clock32. */
+int dp_debug_read_trace(dp_model* m, unsigned long long* out, int n);
 
 /* Executed tensor-core MACs of one forward pass over n_tiles tiles (after the sub-pixel rewrite). */
 int dp_model_executed_macs(const dp_model* m, int n_tiles, uint64_t* macs);

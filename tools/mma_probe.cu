@@ -1,0 +1,67 @@
+// Micro-probe (bring-up tool, not product): cycles per tcgen05.mma (M=128, K=16, fp16, SS mode) as a function of
+// N, of the A-descriptor start alignment (halo mode uses starts that are not 1024-byte aligned) and of the
+// 8-row-group stride (SBO).  Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o mma_probe mma_probe.cu
+#include <cstdio>
+#include <cuda_runtime.h>
+#include "../digipathai_b200/csrc/ptx.cuh"
+using namespace dp;
+
+__global__ void probe(int n, int a_row_off, int sbo, int iters, int unroll_k, long long* out) {
+  extern __shared__ uint8_t raw[];
+  const uint32_t ra = smem_u32(raw);
+  uint8_t* smem = raw + (((ra + 1023u) & ~1023u) - ra);
+  __shared__ uint64_t bar;
+  __shared__ uint32_t slot;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int i = threadIdx.x; i < 180 * 1024 / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem)[i] = 0x3c003c00u;
+  if (warp == 0) { tmem_alloc(&slot, 512); tmem_relinquish(); }
+  if (threadIdx.x == 32) { mbar_init(&bar, 1); fence_barrier_init(); }
+  fence_proxy_async_smem();
+  tc_fence_before(); __syncthreads(); tc_fence_after();
+  const uint32_t tm = slot;
+  if (warp == 1 && lane == 0) {
+    const uint32_t idesc = make_idesc_f16(n);
+    const uint32_t a_hi = sw128_desc_hi(sbo), b_hi = sw128_desc_hi(1024);
+    const uint32_t a_lo = sw128_desc_lo(smem_u32(smem) + a_row_off * 128);
+    const uint32_t b_lo = sw128_desc_lo(smem_u32(smem) + 96 * 1024);
+    // warm
+    umma_f16_ss_parts(tm, a_lo, a_hi, b_lo, b_hi, idesc, 0);
+    umma_commit(&bar); mbar_wait(&bar, 0);
+    long long t0 = clock64();
+    for (int i = 0; i < iters; ++i) {
+      umma_f16_ss_parts(tm, a_lo, a_hi, b_lo, b_hi, idesc, 1);
+      if (unroll_k) {
+        umma_f16_ss_parts(tm, a_lo + 2, a_hi, b_lo + 2, b_hi, idesc, 1);
+        umma_f16_ss_parts(tm, a_lo + 4, a_hi, b_lo + 4, b_hi, idesc, 1);
+        umma_f16_ss_parts(tm, a_lo + 6, a_hi, b_lo + 6, b_hi, idesc, 1);
+      }
+    }
+    long long t1 = clock64();
+    umma_commit(&bar); mbar_wait(&bar, 1);
+    long long t2 = clock64();
+    out[0] = t1 - t0; out[1] = t2 - t0;
+  }
+  tc_fence_before(); __syncthreads();
+  if (warp == 0) { tc_fence_after(); tmem_dealloc(tm, 512); }
+}
+
+int main() {
+  long long* d; cudaMalloc(&d, 16);
+  cudaFuncSetAttribute(probe, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  const int iters = 2000;
+  printf("%5s %8s %6s %4s | %10s %10s\n", "N", "a_rowoff", "sbo", "k4", "issue/mma", "done/mma");
+  int ns[] = {32, 64, 96, 128, 160, 256};
+  for (int n : ns)
+    for (int k4 = 0; k4 < 2; ++k4)
+      for (int cfg = 0; cfg < 4; ++cfg) {
+        int off = (cfg == 0) ? 0 : (cfg == 1 ? 1 : (cfg == 2 ? 0 : 19));
+        int sbo = (cfg < 2) ? 1024 : 2304;
+        probe<<<1, 128, 200 * 1024>>>(n, off, sbo, iters, k4, d);
+        long long h[2];
+        cudaError_t e = cudaMemcpy(h, d, 16, cudaMemcpyDeviceToHost);
+        if (e != cudaSuccess) { printf("error %s\n", cudaGetErrorString(e)); return 1; }
+        const double m = (double)iters * (k4 ? 4 : 1);
+        printf("%5d %8d %6d %4d | %10.1f %10.1f\n", n, off, sbo, k4, h[0] / m, h[1] / m);
+      }
+  return 0;
+}
