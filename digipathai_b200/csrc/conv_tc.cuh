@@ -479,14 +479,27 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
               __syncwarp();
               const int k = pw >> 3;            // 16-byte chunks per row: 8 (64-channel panel) or 4 (32)
               const int ksh = (k == 8) ? 3 : 2;
-              for (int it = 0; it < k; ++it) {
-                const int idx = it * 32 + lane;
-                const int row = idx >> ksh, j = idx & (k - 1);
-                const unsigned long long rp = __shfl_sync(0xffffffffu, my_row, row);
-                const int rv = __shfl_sync(0xffffffffu, static_cast<int>(valid), row);
-                if (rv) {
-                  const uint4 val = *reinterpret_cast<const uint4*>(stage + row * kEpiRowBytes + j * 16);
-                  *reinterpret_cast<uint4*>(reinterpret_cast<__half*>(rp) + cc + j * 8) = val;
+              for (int it0 = 0; it0 < k; it0 += 4) {   // 4 independent row-pointer / load / store chains at a time
+                unsigned long long rp[4];
+                int rv[4];
+                uint4 val[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                  const int row = ((it0 + u) * 32 + lane) >> ksh;
+                  rp[u] = __shfl_sync(0xffffffffu, my_row, row);
+                  rv[u] = __shfl_sync(0xffffffffu, static_cast<int>(valid), row);
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                  const int idx = (it0 + u) * 32 + lane;
+                  val[u] = *reinterpret_cast<const uint4*>(stage + (idx >> ksh) * kEpiRowBytes + (idx & (k - 1)) * 16);
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                  if (rv[u]) {
+                    const int j = ((it0 + u) * 32 + lane) & (k - 1);
+                    *reinterpret_cast<uint4*>(reinterpret_cast<__half*>(rp[u]) + cc + j * 8) = val[u];
+                  }
                 }
               }
               __syncwarp();
@@ -517,22 +530,24 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
       for (int c = 0; c < p.n_chunks; ++c) {
         mbar_wait(&a_full[sa], pa);
-        uint8_t* row0 = a_base + sa * p.a_stage_bytes + t * 128;
         const __half2 zero2 = __float2half2_rn(0.f);
+        for (int s = 0; s < p.sub; ++s) {
+          // Row t of sub-tile s: read all eight 16-byte chunks first, then transform, then write back -- the
+          // in-place stores may alias the loads as far as the compiler knows, so interleaving them would
+          // serialise every shared-memory round trip.  Logical chunk i sits at physical chunk i ^ (t & 7)
+          // (128B swizzle); all lanes touch the same 8 channels per step, so BN terms are broadcast loads.
+          uint8_t* row = a_base + sa * p.a_stage_bytes + s * kATileBytes + t * 128;
+          uint4 raw[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          // logical 16-byte chunk i of row t sits at physical chunk i ^ (t & 7) (128B swizzle); every lane works
-          // on the same 8 channels, so the BN terms are broadcast 16-byte loads shared by all sub-tiles.
-          const int ch = c * 64 + i * 8;
-          const float4 sc0 = *reinterpret_cast<const float4*>(s_pro_scale + ch);
-          const float4 sc1 = *reinterpret_cast<const float4*>(s_pro_scale + ch + 4);
-          const float4 sh0 = *reinterpret_cast<const float4*>(s_pro_shift + ch);
-          const float4 sh1 = *reinterpret_cast<const float4*>(s_pro_shift + ch + 4);
-          const int off = (i ^ (t & 7)) << 4;
-          for (int s = 0; s < p.sub; ++s) {
-            uint4* ptr = reinterpret_cast<uint4*>(row0 + s * kATileBytes + off);
-            uint4 raw = *ptr;
-            __half2* hv = reinterpret_cast<__half2*>(&raw);
+          for (int i = 0; i < 8; ++i) raw[i] = *reinterpret_cast<const uint4*>(row + ((i ^ (t & 7)) << 4));
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int ch = c * 64 + i * 8;
+            const float4 sc0 = *reinterpret_cast<const float4*>(s_pro_scale + ch);
+            const float4 sc1 = *reinterpret_cast<const float4*>(s_pro_scale + ch + 4);
+            const float4 sh0 = *reinterpret_cast<const float4*>(s_pro_shift + ch);
+            const float4 sh1 = *reinterpret_cast<const float4*>(s_pro_shift + ch + 4);
+            __half2* hv = reinterpret_cast<__half2*>(&raw[i]);
             float2 x;
             x = __half22float2(hv[0]);
             hv[0] = __floats2half2_rn(fmaf(x.x, sc0.x, sh0.x), fmaf(x.y, sc0.y, sh0.y));
@@ -546,8 +561,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
               hv[0] = __hmax2(hv[0], zero2); hv[1] = __hmax2(hv[1], zero2);
               hv[2] = __hmax2(hv[2], zero2); hv[3] = __hmax2(hv[3], zero2);
             }
-            *ptr = raw;
           }
+#pragma unroll
+          for (int i = 0; i < 8; ++i) *reinterpret_cast<uint4*>(row + ((i ^ (t & 7)) << 4)) = raw[i];
         }
         fence_proxy_async_smem();
         mbar_arrive(&a_ready[sa]);

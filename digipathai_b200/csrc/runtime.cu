@@ -295,6 +295,8 @@ int plan_conv(dp_model* m, const BlobOp& op, int img0, int B, Launch& L) {
   } else {
     int sub = (W % 16 == 0) ? 2 : 1;
     while (sub > 1 && (p.n_groups * sub * n_tile > kTmemCols)) sub >>= 1;
+    // prefer two accumulator stages (epilogue of item i overlaps the MMAs of item i+1) over a wider region
+    if (sub == 2 && 2 * p.n_groups * sub * n_tile > kTmemCols && 2 * p.n_groups * n_tile <= kTmemCols) sub = 1;
     // prefer more CTAs over wider regions when the layer cannot fill the GPU
     if (sub == 2 && (long long)B * (H / 16) * (W / 16) * p.n_ntiles < m->num_sms) sub = 1;
     p.sub = sub;
