@@ -157,6 +157,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--split", type=int, default=0, help="sub-batches captured as parallel graph branches (0 = library default)")
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--no-pdl", action="store_true")
     ap.add_argument("--dump-ops", default="", help="write the per-op device-time table (instrumented pass) here")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -197,6 +198,8 @@ def main():
         model.set_option("split", args.split)
     if args.no_graph:
         model.set_option("use_graph", 0)
+    if args.no_pdl:
+        model.set_option("use_pdl", 0)
 
     if args.workload == "slide":
         return run_slide(args, model, rank, world, local, dev, barrier, max_over_ranks, peaks, peak_src)
@@ -308,7 +311,7 @@ def main():
                                    "batch 32 per GPU, tiles cropped from an HBM-resident raster",
                        "l2": "flushed between timed steps (256 MiB memset, untimed)",
                        "weights": "random-init (He-normal), BN stats (0,1)",
-                       "graph": "off" if args.no_graph else f"one CUDA graph per step, {args.split or 4} parallel sub-batch branches",
+                       "graph": "off" if args.no_graph else f"one CUDA graph per step, {args.split or 1} sub-batch branch(es), PDL between conv kernels",
                        "executed_gflop_per_tile": 2 * exec_macs / BATCH / 1e9,
                        "reference_gflop_per_tile": REF_FLOP_PER_TILE / 1e9},
             "clocks": clocks,

@@ -52,6 +52,50 @@ __global__ void stem_im2col_kernel(const PassDesc* __restrict__ pass, int img0, 
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// Stem input, space-to-depth form.  The 7x7 stride-2 conv on 3 channels (densenet.py:116-117) equals a 4x4
+// stride-1 conv on the 2x2 space-to-depth image (12 channels).  To keep 128-byte (64-channel) operand rows for
+// the tensor-core kernel, the 4 column taps are unrolled into the channel axis here, leaving 4 row taps:
+//   out[b][r][q][dq*16 + (a*2+b2)*3 + c] = net_in[2r+a][2(q+dq-2)+b2][c]     (0 outside the tile / ch >= 12)
+// with net_in = forward-TTA'd, (v-128)/128-normalised tile cropped from the slide raster.  fp16 [B][P/2][P/2][64].
+__global__ void stem_s2d_kernel(const PassDesc* __restrict__ pass, int img0, int B, int P, __half* __restrict__ out) {
+  const uint8_t* __restrict__ slide = pass->slide;
+  const long long slide_h = pass->slide_h;
+  const int* __restrict__ coords = pass->coords + 2 * img0;
+  const int tta_code = pass->tta_in;
+  const int OH = P / 2;
+  const long long total = static_cast<long long>(B) * OH * OH * 4;
+  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int dq = idx & 3;
+    long long r0 = idx >> 2;
+    const int q = r0 % OH; r0 /= OH;
+    const int r = r0 % OH;
+    const int b = r0 / OH;
+    const long long x0 = coords[2 * b], y0 = coords[2 * b + 1];
+    __align__(16) __half vals[16];
+#pragma unroll
+    for (int t = 0; t < 16; ++t) vals[t] = __float2half_rn(0.f);
+    const int jq = q + dq - 2;
+    if (jq >= 0 && jq < OH) {
+#pragma unroll
+      for (int a = 0; a < 2; ++a)
+#pragma unroll
+        for (int b2 = 0; b2 < 2; ++b2) {
+          int ti, tj;
+          d4_src(tta_code, 2 * r + a, 2 * jq + b2, P, ti, tj);
+          const uint8_t* px = slide + ((x0 + ti) * slide_h + (y0 + tj)) * 3;
+#pragma unroll
+          for (int c = 0; c < 3; ++c)
+            vals[(a * 2 + b2) * 3 + c] = __float2half_rn((static_cast<float>(px[c]) - 128.f) * (1.f / 128.f));
+        }
+    }
+    uint4* dst = reinterpret_cast<uint4*>(out + idx * 16);
+    dst[0] = reinterpret_cast<const uint4*>(vals)[0];
+    dst[1] = reinterpret_cast<const uint4*>(vals)[1];
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // ZeroPadding2D(1) + MaxPooling2D(3, strides=2) (densenet.py:122-123). 8 channels per thread.
 __global__ void maxpool3s2_kernel(const __half* __restrict__ in, int in_ctot, int in_choff,
                                   __half* __restrict__ out, int out_ctot, int out_choff, int n_img, int H, int W,

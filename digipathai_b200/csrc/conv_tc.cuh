@@ -15,8 +15,9 @@
 //           on the LOW-resolution map with pre-summed weights (2.25x fewer MACs, no upsampled tensor in HBM).
 //
 // Warp roles (1 CTA / SM, persistent over work items):
-//   warp 0 lane 0 : TMA producer (A ring + B ring)      warp 1 lane 0 : tcgen05.mma issuer
-//   warp 2        : TMEM allocator                      warps 4-7     : epilogue (tcgen05.ld -> BN/ReLU -> HBM)
+//   warp 0 : TMA producer, activations (A ring)        warp 1 : tcgen05.mma issuer (one elected lane each)
+//   warp 2 : TMEM allocator                             warp 3 : TMA producer, weights (B ring)
+//   warps 4-7 : epilogue (tcgen05.ld -> BN shift/ReLU -> staged, coalesced stores to HBM)
 //   warps 8-11    : (PROLOGUE only) pre-activation BN+ReLU applied to the A tile in shared memory
 //                   (dense-layer `_0_bn/_0_relu`, densenet.py:59-63) before the MMA reads it.
 #pragma once
@@ -56,6 +57,7 @@ struct ConvParams {
   int n_mtiles, n_items;
   int a_stage_bytes, b_stage_bytes, a_stages, b_stages, acc_stages, a_tx_bytes;
   int b_group;              // tap entries carried by one B stage (TMA box depth)
+  int halo_top;             // MODE_H: rows of halo above the region (1 for 3x3 / up2, 2 for the 4x4 stem)
   int epi_mode, relu;
   int out_ctot, out_choff;  // output NHWC buffer: channel stride and channel offset (elements)
   int desc_base_mode;       // 0: descriptor base_offset field = 0; 1: (addr >> 7) & 7
@@ -63,6 +65,12 @@ struct ConvParams {
   int img0, P;              // EPI_HEAD: first image of this sub-batch within the call; tile side
   float head_b;
   TapEntry entries[kMaxEntries];
+  // host-precomputed per tap entry (kernel parameters live in the constant bank, so the issue loop reads these
+  // straight into uniform registers): A-descriptor offset in 16-byte units, accumulator column offset, and a
+  // bitmask of entries that are the first of their accumulator group
+  uint32_t tap_a[kMaxEntries];
+  uint32_t tap_d[kMaxEntries];
+  uint32_t tap_first_mask;
   const float* epi_scale;
   const float* epi_shift;
   const float* pro_scale;
@@ -182,7 +190,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   uint64_t* acc_full = b_empty + kMaxBStages;
   uint64_t* acc_empty = acc_full + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
-  uint32_t* s_rowoff = tmem_slot + 4;  // [kMaxEntries] A-descriptor offset (16-byte units) of every tap entry
 
   const ConvSmemLayout L = conv_smem_layout(p);
   uint8_t* a_base = smem + L.a_off;
@@ -222,42 +229,46 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     tmem_alloc(tmem_slot, kTmemCols);
     tmem_relinquish();
   }
-  if (warp == 3 && lane < kMaxEntries) {
-    const TapEntry ent = p.entries[lane];
-    s_rowoff[lane] = (MODE == MODE_H) ? static_cast<uint32_t>(((ent.dy + 1) * p.box_w + (ent.dx + 1)) * 8) : 0u;
-  }
   {
+    // Per-layer constants -> smem. They are weights-side data (never produced by a preceding kernel), so this
+    // runs BEFORE griddepcontrol.wait and overlaps the previous layer's tail under programmatic dependent
+    // launch.  All global loads are issued before the first dependent store.
     const int cout = p.n_tile * p.n_ntiles;
-    for (int i = tid; i < cout; i += blockDim.x) {
-      s_epi_scale[i] = p.epi_scale ? p.epi_scale[i] : 1.f;
-      s_epi_shift[i] = p.epi_shift ? p.epi_shift[i] : 0.f;
-    }
-    if (PROLOGUE) {
-      for (int i = tid; i < p.n_chunks * 64; i += blockDim.x) {
-        s_pro_scale[i] = p.pro_scale[i];
-        s_pro_shift[i] = p.pro_shift[i];
+    const int npro = PROLOGUE ? p.n_chunks * 64 : 0;
+    const bool head = p.epi_mode == EPI_HEAD;
+    for (int i0 = 0; i0 < cout || i0 < npro; i0 += blockDim.x) {
+      const int i = i0 + tid;
+      float es = 1.f, eh = 0.f, ps = 0.f, ph = 0.f, hw = 0.f;
+      if (i < cout) {
+        if (p.epi_scale) es = p.epi_scale[i];
+        if (p.epi_shift) eh = p.epi_shift[i];
+        if (head) hw = p.head_w[i];
       }
-    }
-    if (p.epi_mode == EPI_HEAD) {
-      for (int i = tid; i < cout; i += blockDim.x) s_head_w[i] = p.head_w[i];
+      if (i < npro) { ps = p.pro_scale[i]; ph = p.pro_shift[i]; }
+      if (i < cout) {
+        s_epi_scale[i] = es; s_epi_shift[i] = eh;
+        if (head) s_head_w[i] = hw;
+      }
+      if (i < npro) { s_pro_scale[i] = ps; s_pro_shift[i] = ph; }
     }
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  pdl_launch_dependents();  // the next layer may begin its own setup as SMs drain
+  pdl_wait();               // activations written by the previous layer are complete and visible from here on
   const uint32_t tmem_base = *tmem_slot;
   if (tid == 0 && p.trace && blockIdx.x == 0) { p.trace[8 + 2000 * 4] = clock64() & 0xFFFFFFFFull; p.trace[4] = 2; }
   const int n_bgroups = p.n_entries / p.b_group;  // B stages per (work item, channel chunk)
 
   if (warp == 0) {
-    // ------------------------------------------------------------------ TMA producer
+    // ------------------------------------------------------------------ TMA producer: activations (A ring)
     if (elect_one()) {
       TraceCursor tc = trace_open(p, 0);
-      uint32_t sa = 0, pa = 0, sb = 0, pb = 0;  // ring slot + phase parity
+      uint32_t sa = 0, pa = 0;  // ring slot + phase parity
       for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
         const WorkItem wi = decode_item(p, item);
         const int ebase = wi.ph * p.n_entries;
-        const int n0 = wi.nt * p.n_tile;
         for (int c = 0; c < p.n_chunks; ++c) {
           const int c0 = c * 64;
           if (MODE != MODE_T) {
@@ -268,29 +279,42 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
               for (int s = 0; s < p.sub; ++s)
                 tma_load_2d(&map_a, &a_full[sa], dst + s * kATileBytes, c0, wi.m0 + s * 128);
             } else {
-              tma_load_4d(&map_a, &a_full[sa], dst, c0, wi.w0 - 1, wi.h0 - 1, wi.n0);
+              tma_load_4d(&map_a, &a_full[sa], dst, c0, wi.w0 - 1, wi.h0 - p.halo_top, wi.n0);
             }
             trace_ev(tc, 1, item);
             if (++sa == p.a_stages) { sa = 0; pa ^= 1; }
-          }
-          for (int g = 0; g < n_bgroups; ++g) {
-            if (MODE == MODE_T) {  // b_group == 1: one shifted A box per tap
+          } else {
+            for (int g = 0; g < n_bgroups; ++g) {  // one shifted A box per tap
               const TapEntry ent = p.entries[ebase + g];
               mbar_wait(&a_empty[sa], pa ^ 1);
               mbar_expect_tx(&a_full[sa], p.a_tx_bytes);
               tma_load_4d(&map_a, &a_full[sa], a_base + sa * p.a_stage_bytes, c0, wi.w0 + ent.dx,
                           wi.h0 + ent.dy, wi.n0);
+              trace_ev(tc, 1, item);
               if (++sa == p.a_stages) { sa = 0; pa ^= 1; }
             }
-            mbar_wait(&b_empty[sb], pb ^ 1);
-            mbar_expect_tx(&b_full[sb], p.b_stage_bytes);
-            tma_load_3d(&map_b, &b_full[sb], b_base + sb * p.b_stage_bytes, c0, n0, ebase + g * p.b_group);
-            trace_ev(tc, 2, item);
-            if (++sb == p.b_stages) { sb = 0; pb ^= 1; }
           }
         }
       }
       trace_close(p, tc, 0);
+    }
+  } else if (warp == 3) {
+    // ------------------------------------------------------------------ TMA producer: weights (B ring)
+    if (elect_one()) {
+      uint32_t sb = 0, pb = 0;
+      for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+        const int rest = item / p.n_mtiles;
+        const int n0 = (rest % p.n_ntiles) * p.n_tile;
+        const int ebase = (rest / p.n_ntiles) * p.n_entries;
+        for (int c = 0; c < p.n_chunks; ++c) {
+          for (int g = 0; g < n_bgroups; ++g) {
+            mbar_wait(&b_empty[sb], pb ^ 1);
+            mbar_expect_tx(&b_full[sb], p.b_stage_bytes);
+            tma_load_3d(&map_b, &b_full[sb], b_base + sb * p.b_stage_bytes, c * 64, n0, ebase + g * p.b_group);
+            if (++sb == p.b_stages) { sb = 0; pb ^= 1; }
+          }
+        }
+      }
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
@@ -315,7 +339,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         tc_fence_after();
         trace_ev(tc, 0, item);
         const uint32_t d_stage = tmem_base + as * p.n_groups * d_group_stride;
-        uint32_t inited = 0;
+        const int ebase = (MODE == MODE_T) ? (item / (p.n_mtiles * p.n_ntiles)) * p.n_entries : 0;
         for (int c = 0; c < p.n_chunks; ++c) {
           int ks = (p.Cin - c * 64 + 15) >> 4;
           ks = ks > 4 ? 4 : ks;
@@ -325,7 +349,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             trace_ev(tc, 1, item);
             a_stage_desc = a_desc0 + sa * a_stage_u;
           }
-          int e = 0;
+          int e = ebase;
+          const uint32_t first_mask = (c == 0) ? p.tap_first_mask : 0u;
           for (int g = 0; g < n_bgroups; ++g) {
             if (MODE == MODE_T) {
               mbar_wait(&a_full[sa], pa);
@@ -335,21 +360,23 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             tc_fence_after();
             trace_ev(tc, 2, item);
             uint64_t b_desc = b_desc0 + sb * b_stage_u;
-            for (uint32_t j = 0; j < bgroup; ++j, ++e, b_desc += b_ent_u) {
-              uint32_t grp = 0;
-              if (MODE == MODE_H) grp = static_cast<uint32_t>(p.entries[e].group);
-              const uint32_t flag0 = (inited >> grp) & 1u;
-              uint64_t a_desc = a_stage_desc + ((MODE == MODE_H) ? s_rowoff[e] : 0u);
-              uint32_t d = d_stage + grp * d_group_stride;
-              if (ks == 4) {
+            if (ks == 4) {
+              for (uint32_t j = 0; j < bgroup; ++j, ++e, b_desc += b_ent_u) {
+                const uint32_t flag0 = ((first_mask >> e) & 1u) ^ 1u;
+                uint64_t a_desc = a_stage_desc + p.tap_a[e];
+                uint32_t d = d_stage + p.tap_d[e];
                 for (uint32_t s = 0; s < sub; ++s, a_desc += a_sub_u, d += n_tile)
                   umma_f16_ss_k4(d, a_desc, b_desc, idesc, flag0);
-              } else {  // channel tail (Cin % 64 != 0): 1-3 K-steps
+              }
+            } else {  // channel tail (Cin % 64 != 0): 1-3 K-steps
+              for (uint32_t j = 0; j < bgroup; ++j, ++e, b_desc += b_ent_u) {
+                const uint32_t flag0 = ((first_mask >> e) & 1u) ^ 1u;
+                uint64_t a_desc = a_stage_desc + p.tap_a[e];
+                uint32_t d = d_stage + p.tap_d[e];
                 for (uint32_t s = 0; s < sub; ++s, a_desc += a_sub_u, d += n_tile)
                   for (int k = 0; k < ks; ++k)
                     umma_f16_ss(d, a_desc + 2 * k, b_desc + 2 * k, idesc, k ? 1u : flag0);
               }
-              inited |= 1u << grp;
             }
             umma_commit(&b_empty[sb]);
             if (++sb == p.b_stages) { sb = 0; pb ^= 1; }
@@ -593,6 +620,12 @@ struct NaiveConvParams {
   int n_entries_total, n_groups, entries_per_group, up2;
   int relu, pro_mode;  // pro_mode: 0 none, 1 affine, 2 affine+relu
   TapEntry entries[kMaxEntries];
+  // host-precomputed per tap entry (kernel parameters live in the constant bank, so the issue loop reads these
+  // straight into uniform registers): A-descriptor offset in 16-byte units, accumulator column offset, and a
+  // bitmask of entries that are the first of their accumulator group
+  uint32_t tap_a[kMaxEntries];
+  uint32_t tap_d[kMaxEntries];
+  uint32_t tap_first_mask;
   const __half* in;
   const __half* w;  // [entries][Cout][Cin]
   const float* epi_scale;

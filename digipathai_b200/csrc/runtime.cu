@@ -94,7 +94,7 @@ static_assert(sizeof(BlobHeader) == 72, "header layout");
 struct BlobBuf {
   int32_t H, W, C, pad;
 };
-enum : int { OP_STEM_IM2COL = 1, OP_MAXPOOL = 2, OP_CONV = 3, OP_BNPOOL = 4 };
+enum : int { OP_STEM_IM2COL = 1, OP_MAXPOOL = 2, OP_CONV = 3, OP_BNPOOL = 4, OP_STEM_S2D = 5 };
 struct BlobOp {
   int32_t type, in_buf, in_choff, cin, out_buf, out_choff, cout, kind, relu, pro, head, pool;
   float head_b;
@@ -142,7 +142,7 @@ struct dp_model {
   __half* scratch_head = nullptr;  // naive path: output of the head-fused conv
   uint64_t device_bytes = 0;
   int naive_conv = 0, desc_base_mode = 0, halo_pad8 = 0, profile = 0;
-  int use_graph = 1, split = 4;
+  int use_graph = 1, split = 1, use_pdl = 1;
   unsigned long long* trace_dev = nullptr;  // debug timeline buffer (option "trace_op")
   int trace_op = -1;
   dp::PassDesc* pass_dev = nullptr;          // per-call arguments read by the stem and head kernels
@@ -173,6 +173,9 @@ void fill_entries(int kind, dp::TapEntry* e, int* n) {
     for (int ky = 0; ky < 3; ++ky)
       for (int kx = 0; kx < 3; ++kx) e[ky * 3 + kx] = {(int8_t)(ky - 1), (int8_t)(kx - 1), 0, 0};
     *n = 9;
+  } else if (kind == 5) {  // stem as a 4-row-tap conv on the width-unrolled space-to-depth image
+    for (int t = 0; t < 4; ++t) e[t] = {(int8_t)(t - 2), 0, 0, 0};
+    *n = 4;
   } else {  // up2: phase (a,b), tap (ty,tx): input offset (a-1+ty, b-1+tx)
     for (int ph = 0; ph < 4; ++ph)
       for (int t = 0; t < 4; ++t) {
@@ -301,11 +304,24 @@ int plan_conv(dp_model* m, const BlobOp& op, int img0, int B, Launch& L) {
     if (sub == 2 && (long long)B * (H / 16) * (W / 16) * p.n_ntiles < m->num_sms) sub = 1;
     p.sub = sub;
     p.box_w = m->halo_pad8 ? round_up(8 * sub + 2, 8) : 8 * sub + 2;
-    p.box_h = 18; p.box_n = 1;
+    p.halo_top = (op.kind == 5) ? 2 : 1;
+    p.box_h = 16 + p.halo_top + 1; p.box_n = 1;
     p.tiles_w = W / (8 * sub); p.tiles_h = H / 16;
     p.n_mtiles = B * p.tiles_w * p.tiles_h;
     p.a_tx_bytes = p.box_w * p.box_h * 128;
     p.a_stage_bytes = round_up(p.a_tx_bytes, 1024);
+  }
+  // per-tap constants for the issue loop (see ConvParams::tap_a)
+  p.tap_first_mask = 0;
+  for (int e = 0; e < n_entries_total; ++e) {
+    const TapEntry& te = p.entries[e];
+    const int base = (e / p.n_entries) * p.n_entries;
+    bool first = true;
+    for (int f = base; f < e; ++f)
+      if (p.entries[f].group == te.group) first = false;
+    if (first) p.tap_first_mask |= 1u << e;
+    p.tap_a[e] = (p.mode == MODE_H) ? (uint32_t)(((te.dy + p.halo_top) * p.box_w + (te.dx + 1)) * 8) : 0u;
+    p.tap_d[e] = (p.mode == MODE_H) ? (uint32_t)(te.group * p.sub * n_tile) : 0u;
   }
   p.n_items = p.n_mtiles * p.n_ntiles * p.n_phase_items;
   // several taps per B stage for small N: keeps the single producer / MMA-issue threads off the critical path
@@ -426,6 +442,14 @@ int run_op(dp_model* m, SubPlan* sp, int i, cudaStream_t st) {
       LAUNCH_OK();
       return 0;
     }
+    case OP_STEM_S2D: {
+      const BlobBuf& ob = m->bufs[op.out_buf];
+      if (ob.C != 64 || ob.H != m->patch / 2) return fail("stem s2d buffer must be [P/2][P/2][64]");
+      const long long total = (long long)B * ob.H * ob.W * 4;
+      dp::stem_s2d_kernel<<<grid_for(total, 256), 256, 0, st>>>(m->pass_dev, img0, B, m->patch, buf_at(op.out_buf));
+      LAUNCH_OK();
+      return 0;
+    }
     case OP_MAXPOOL: {
       const BlobBuf& ib = m->bufs[op.in_buf];
       const BlobBuf& ob = m->bufs[op.out_buf];
@@ -464,18 +488,33 @@ int run_op(dp_model* m, SubPlan* sp, int i, cudaStream_t st) {
       dp::ConvParams cp = L.cp;
       cp.desc_base_mode = m->desc_base_mode;
       cp.trace = (m->trace_op == i) ? m->trace_dev : nullptr;
+      // Programmatic dependent launch: the kernel's setup (barrier init, TMEM alloc, BN constants -> smem)
+      // runs before its griddepcontrol.wait and so overlaps the tail of the preceding kernel in the stream.
+      cudaLaunchConfig_t cfg;
+      memset(&cfg, 0, sizeof cfg);
+      cfg.gridDim = dim3(L.grid);
+      cfg.blockDim = dim3(L.prologue ? 384 : 256);
+      cfg.dynamicSmemBytes = L.smem;
+      cfg.stream = st;
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+      attr[0].val.programmaticStreamSerializationAllowed = 1;
+      cfg.attrs = attr;
+      cfg.numAttrs = m->use_pdl ? 1 : 0;
+      cudaError_t le;
       switch (cp.mode) {
         case dp::MODE_D:
-          if (L.prologue) dp::conv_tc_kernel<dp::MODE_D, true><<<L.grid, 384, L.smem, st>>>(L.map_a, L.map_b, cp);
-          else dp::conv_tc_kernel<dp::MODE_D, false><<<L.grid, 256, L.smem, st>>>(L.map_a, L.map_b, cp);
+          if (L.prologue) le = cudaLaunchKernelEx(&cfg, dp::conv_tc_kernel<dp::MODE_D, true>, L.map_a, L.map_b, cp);
+          else le = cudaLaunchKernelEx(&cfg, dp::conv_tc_kernel<dp::MODE_D, false>, L.map_a, L.map_b, cp);
           break;
         case dp::MODE_T:
-          dp::conv_tc_kernel<dp::MODE_T, false><<<L.grid, 256, L.smem, st>>>(L.map_a, L.map_b, cp);
+          le = cudaLaunchKernelEx(&cfg, dp::conv_tc_kernel<dp::MODE_T, false>, L.map_a, L.map_b, cp);
           break;
         default:
-          dp::conv_tc_kernel<dp::MODE_H, false><<<L.grid, 256, L.smem, st>>>(L.map_a, L.map_b, cp);
+          le = cudaLaunchKernelEx(&cfg, dp::conv_tc_kernel<dp::MODE_H, false>, L.map_a, L.map_b, cp);
           break;
       }
+      if (le != cudaSuccess) return fail("conv launch failed: %s", cudaGetErrorString(le));
       LAUNCH_OK();
       return 0;
     }
@@ -625,6 +664,14 @@ int dp_model_set_option(dp_model* m, const char* key, int value) {
   else if (!strcmp(key, "desc_base_mode")) m->desc_base_mode = value;
   else if (!strcmp(key, "profile")) m->profile = value;
   else if (!strcmp(key, "use_graph")) m->use_graph = value;
+  else if (!strcmp(key, "use_pdl")) {
+    std::lock_guard<std::mutex> lk(m->mu);
+    m->use_pdl = value;
+    for (auto& kv : m->plans) {   // captured graphs bake the launch attribute
+      if (kv.second.exec) { cudaGraphExecDestroy(kv.second.exec); kv.second.exec = nullptr; }
+      if (kv.second.graph) { cudaGraphDestroy(kv.second.graph); kv.second.graph = nullptr; }
+    }
+  }
   else if (!strcmp(key, "trace_op")) {
     if (!m->trace_dev) CU_OK(cudaMalloc(&m->trace_dev, 10016 * sizeof(unsigned long long)));
     CU_OK(cudaMemset(m->trace_dev, 0, 10016 * sizeof(unsigned long long)));
@@ -682,7 +729,7 @@ static int run_range(dp_model* m, int B, int op_begin, int op_end, const dp::Pas
   }
   for (int i = op_begin; i < op_end; ++i) {
     const BlobOp& op = m->ops[i];
-    if (op.type == OP_STEM_IM2COL && (!d.slide || !d.coords)) return fail("op %d: stem needs a slide and coordinates", i);
+    if ((op.type == OP_STEM_IM2COL || op.type == OP_STEM_S2D) && (!d.slide || !d.coords)) return fail("op %d: stem needs a slide and coordinates", i);
     if (op.type == OP_CONV && op.head && !d.probs_out) return fail("op %d: head needs a probability output buffer", i);
     if (m->profile) CU_OK(cudaEventRecord(m->ev[2 * i], st));
     if (run_op(m, &plan->subs[0], i, st)) {

@@ -9,13 +9,14 @@ exactly this order).  Conv kernels are HWIO float32; BN entries are (gamma, beta
 Buffer plan (per image; every `concatenate` of the reference is a channel range of one buffer, so no concat
 copies exist): D1 = [dec9a 96 | conv1 64] @128^2, D2 = [dec8a 128 | block2 256] @64^2,
 D3 = [dec7a 256 | block3 512] @32^2, D4 = [dec6a 320 | block4 1024] @16^2, D5 = block5 1024 @8^2.
+The stem conv runs in halo mode, which needs maps at least 16 rows high: patch >= 64.
 """
 from __future__ import annotations
 
 import numpy as np
 
-from ..program import (KIND_1X1, KIND_3X3, KIND_UP2, OP_BNPOOL, OP_CONV, OP_MAXPOOL, OP_STEM_IM2COL,
-                       PRO_AFFINE_RELU, Op, Program, bn_affine, pack_conv_weights, pack_stem_weights, pad64)
+from ..program import (KIND_1X1, KIND_3X3, KIND_STEM4, KIND_UP2, OP_BNPOOL, OP_CONV, OP_MAXPOOL, OP_STEM_S2D,
+                       PRO_AFFINE_RELU, Op, Program, bn_affine, pack_conv_weights, pack_stem4_weights, pad64)
 
 DENSENET_BLOCKS = (6, 12, 24, 16)
 GROWTH = 32
@@ -76,7 +77,7 @@ def densenet121_unet_program(weights: dict, patch: int = 256) -> Program:
         raise ValueError("patch_size must be a power of two >= 64 for the B200 tile kernels")
     P = patch
     pr = Program(patch=P)
-    S = pr.add_buf("stem_im2col", P // 2, P // 2, 160)
+    S = pr.add_buf("stem_s2d", P // 2, P // 2, 64)
     D1 = pr.add_buf("D1", P // 2, P // 2, 160)
     D2 = pr.add_buf("D2", P // 4, P // 4, 384)
     D3 = pr.add_buf("D3", P // 8, P // 8, 768)
@@ -93,13 +94,14 @@ def densenet121_unet_program(weights: dict, patch: int = 256) -> Program:
     E10 = pr.add_buf("E10", P, P, 64)
 
     ops = pr.ops
-    # ---- stem: pad3 + conv7x7/2 + BN + ReLU (densenet.py:116-120), as im2col + one GEMM
-    ops.append(Op(OP_STEM_IM2COL, out_buf=S, cout=160, name="stem_im2col"))
+    # ---- stem: pad3 + conv7x7/2 + BN + ReLU (densenet.py:116-120) as a 4x4 conv on the space-to-depth image;
+    # the gather kernel unrolls the 4 column taps into 64 channels, the tensor-core kernel does the 4 row taps.
     # BatchNorm scales that follow a conv are folded into its weights in fp32 before the single rounding to
     # fp16 (same relative error as rounding the raw weights); the epilogue then only adds the shift.
+    ops.append(Op(OP_STEM_S2D, out_buf=S, cout=64, name="stem_s2d"))
     sc, sh = bn_affine(*weights["conv1/bn"], EPS_ENC)
-    ops.append(Op(OP_CONV, in_buf=S, cin=160, out_buf=D1, out_choff=96, cout=64, kind=KIND_1X1, relu=1,
-                  w=pack_stem_weights(weights["conv1/conv"] * sc), epi_shift=sh, name="conv1"))
+    ops.append(Op(OP_CONV, in_buf=S, cin=64, out_buf=D1, out_choff=96, cout=64, kind=KIND_STEM4, relu=1,
+                  w=pack_stem4_weights(weights["conv1/conv"] * sc), epi_shift=sh, name="conv1"))
     # ---- pad1 + maxpool3/2 (densenet.py:122-123) straight into block2's concat buffer
     ops.append(Op(OP_MAXPOOL, in_buf=D1, in_choff=96, cin=64, out_buf=D2, out_choff=128, cout=64, name="pool1"))
 

@@ -23,8 +23,8 @@ from typing import List, Optional
 
 import numpy as np
 
-OP_STEM_IM2COL, OP_MAXPOOL, OP_CONV, OP_BNPOOL = 1, 2, 3, 4
-KIND_1X1, KIND_3X3, KIND_UP2 = 1, 3, 4
+OP_STEM_IM2COL, OP_MAXPOOL, OP_CONV, OP_BNPOOL, OP_STEM_S2D = 1, 2, 3, 4, 5
+KIND_1X1, KIND_3X3, KIND_UP2, KIND_STEM4 = 1, 3, 4, 5
 PRO_NONE, PRO_AFFINE, PRO_AFFINE_RELU = 0, 1, 2
 
 
@@ -118,6 +118,27 @@ def pack_stem_weights(k_hwio: np.ndarray, kpad: int = 160) -> np.ndarray:
     return w.astype(np.float16)
 
 
+def pack_stem4_weights(k_hwio: np.ndarray) -> np.ndarray:
+    """7x7x3xCout stem kernel -> fp16 [4 row taps][Cout][64] for the space-to-depth stem (stem_s2d_kernel).
+
+    Row tap t <-> dr = t-2; input channel dq*16 + (a*2+b)*3 + c multiplies original tap
+    (ky, kx) = (2*dr + a + 3, 2*(dq-2) + b + 3); combinations that fall outside the 7x7 kernel are zero.
+    """
+    k = np.asarray(k_hwio, dtype=np.float32)
+    assert k.shape[:3] == (7, 7, 3)
+    co = k.shape[3]
+    w = np.zeros((4, co, 64), dtype=np.float32)
+    for t in range(4):
+        for dq in range(4):
+            for a in range(2):
+                for b in range(2):
+                    ky, kx = 2 * (t - 2) + a + 3, 2 * (dq - 2) + b + 3
+                    if 0 <= ky < 7 and 0 <= kx < 7:
+                        for c in range(3):
+                            w[t, :, dq * 16 + (a * 2 + b) * 3 + c] = k[ky, kx, c, :]
+    return w.astype(np.float16)
+
+
 def bn_affine(gamma, beta, mean, var, eps):
     """Inference BatchNorm as y = scale*x + shift (Keras: gamma*(x-mean)/sqrt(var+eps)+beta)."""
     scale = (np.asarray(gamma, np.float64) / np.sqrt(np.asarray(var, np.float64) + eps))
@@ -148,7 +169,7 @@ def serialize(prog: Program) -> bytes:
     op_recs = []
     for o in prog.ops:
         if o.type == OP_CONV:
-            ents = {KIND_1X1: 1, KIND_3X3: 9, KIND_UP2: 16}[o.kind]
+            ents = {KIND_1X1: 1, KIND_3X3: 9, KIND_UP2: 16, KIND_STEM4: 4}[o.kind]
             assert o.w is not None and o.w.shape == (ents, o.cout, o.cin), (o.name, o.w.shape, (ents, o.cout, o.cin))
             assert o.cout % 16 == 0 and o.cin % 8 == 0, o.name
             if o.pro:

@@ -106,7 +106,8 @@ uint64_t dp_kernel_launch_count(void);
  *          "desc_base_mode" (0/1: UMMA descriptor base_offset policy, bring-up only), "halo_pad8" (0/1: pad halo pitch to 8 pixels, bring-up only),
  *          "profile" (0/1: record CUDA events around every op for dp_model_op_times; implies direct launches),
  *          "use_graph" (0/1, default 1: replay dp_forward_tiles as one captured CUDA graph),
- *          "split" (default 4: number of sub-batches captured as parallel graph branches). */
+ *          "use_pdl" (0/1, default 1: conv kernels use programmatic dependent launch),
+ *          "split" (default 1: number of sub-batches captured as parallel graph branches). */
 int dp_model_set_option(dp_model* m, const char* key, int value);
 
 /* Number of ops / buffers in the layer program; buffer geometry (per-image H, W, C; fp16 NHWC). */

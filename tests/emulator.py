@@ -10,8 +10,8 @@ import numpy as np
 import torch
 
 from digipathai_b200 import tta
-from digipathai_b200.program import (KIND_1X1, KIND_3X3, KIND_UP2, OP_BNPOOL, OP_CONV, OP_MAXPOOL, OP_STEM_IM2COL,
-                                     Program)
+from digipathai_b200.program import (KIND_1X1, KIND_3X3, KIND_STEM4, KIND_UP2, OP_BNPOOL, OP_CONV, OP_MAXPOOL,
+                                     OP_STEM_IM2COL, OP_STEM_S2D, Program)
 
 
 def entries(kind):
@@ -19,6 +19,8 @@ def entries(kind):
         return [(0, 0, 0)]
     if kind == KIND_3X3:
         return [(ky - 1, kx - 1, 0) for ky in range(3) for kx in range(3)]
+    if kind == KIND_STEM4:
+        return [(t - 2, 0, 0) for t in range(4)]
     out = []
     for ph in range(4):
         a, b = ph >> 1, ph & 1
@@ -53,6 +55,24 @@ def stem_im2col(tiles_u8: np.ndarray, code: int) -> torch.Tensor:
     return torch.cat([out, torch.zeros(B, P // 2, P // 2, 160 - 147)], dim=-1)
 
 
+def stem_s2d(tiles_u8: np.ndarray, code: int) -> torch.Tensor:
+    """tiles uint8 [B,P,P,3] -> fp32 [B,P/2,P/2,64] exactly as stem_s2d_kernel lays it out."""
+    B, P = tiles_u8.shape[:2]
+    x = torch.from_numpy(np.stack([tta.apply(code, t) for t in tiles_u8]).astype(np.float32))
+    x = (x - 128.0) / 128.0
+    OH = P // 2
+    out = torch.zeros(B, OH, OH, 64)
+    for dq in range(4):
+        for a in range(2):
+            for b in range(2):
+                # columns jq = q + dq - 2 in [0, OH)
+                q_lo, q_hi = max(0, 2 - dq), min(OH, OH + 2 - dq)
+                src = x[:, a::2, b::2, :]                      # [B, OH, OH, 3] indexed [r][jq]
+                ch = dq * 16 + (a * 2 + b) * 3
+                out[:, :, q_lo:q_hi, ch:ch + 3] = src[:, :, q_lo + dq - 2:q_hi + dq - 2, :]
+    return out
+
+
 def run(prog: Program, tiles_u8: np.ndarray, tta_in: int = 0, tta_out: int = 0, fp16_storage: bool = True,
         keep: bool = False):
     """Returns probs float32 [B,P,P] (and the buffer dict when keep=True)."""
@@ -64,6 +84,8 @@ def run(prog: Program, tiles_u8: np.ndarray, tta_in: int = 0, tta_out: int = 0, 
     for op in prog.ops:
         if op.type == OP_STEM_IM2COL:
             bufs[op.out_buf][:] = q(stem_im2col(tiles_u8, tta_in))
+        elif op.type == OP_STEM_S2D:
+            bufs[op.out_buf][:] = q(stem_s2d(tiles_u8, tta_in))
         elif op.type == OP_MAXPOOL:
             x = bufs[op.in_buf][..., op.in_choff:op.in_choff + op.cin].permute(0, 3, 1, 2)
             y = torch.nn.functional.max_pool2d(torch.nn.functional.pad(x, (1, 1, 1, 1)), 3, stride=2)

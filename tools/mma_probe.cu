@@ -6,16 +6,17 @@
 #include "../digipathai_b200/csrc/ptx.cuh"
 using namespace dp;
 
-__global__ void probe(int n, int a_row_off, int sbo, int iters, int unroll_k, long long* out) {
+__global__ void probe(int n, int a_row_off, int sbo, int iters, int unroll_k, int spin_mode, long long* out) {
   extern __shared__ uint8_t raw[];
   const uint32_t ra = smem_u32(raw);
   uint8_t* smem = raw + (((ra + 1023u) & ~1023u) - ra);
   __shared__ uint64_t bar;
+  __shared__ uint64_t done_bar;
   __shared__ uint32_t slot;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   for (int i = threadIdx.x; i < 180 * 1024 / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem)[i] = 0x3c003c00u;
   if (warp == 0) { tmem_alloc(&slot, 512); tmem_relinquish(); }
-  if (threadIdx.x == 32) { mbar_init(&bar, 1); fence_barrier_init(); }
+  if (threadIdx.x == 32) { mbar_init(&bar, 1); mbar_init(&done_bar, 1); fence_barrier_init(); }
   fence_proxy_async_smem();
   tc_fence_before(); __syncthreads(); tc_fence_after();
   const uint32_t tm = slot;
@@ -40,6 +41,11 @@ __global__ void probe(int n, int a_row_off, int sbo, int iters, int unroll_k, lo
     umma_commit(&bar); mbar_wait(&bar, 1);
     long long t2 = clock64();
     out[0] = t1 - t0; out[1] = t2 - t0;
+    mbar_arrive(&done_bar);
+  } else if (warp >= 4 && spin_mode) {
+    // waiting roles as in the conv kernel: spin_mode 1 = all 32 lanes poll, 2 = lane 0 polls then __syncwarp
+    if (spin_mode == 1) mbar_wait(&done_bar, 0);
+    else { if (lane == 0) mbar_wait(&done_bar, 0); __syncwarp(); }
   }
   tc_fence_before(); __syncthreads();
   if (warp == 0) { tc_fence_after(); tmem_dealloc(tm, 512); }
@@ -49,19 +55,20 @@ int main() {
   long long* d; cudaMalloc(&d, 16);
   cudaFuncSetAttribute(probe, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
   const int iters = 2000;
-  printf("%5s %8s %6s %4s | %10s %10s\n", "N", "a_rowoff", "sbo", "k4", "issue/mma", "done/mma");
-  int ns[] = {32, 64, 96, 128, 160, 256};
+  printf("%5s %8s %6s %4s %4s | %10s %10s\n", "N", "a_rowoff", "sbo", "k4", "spin", "issue/mma", "done/mma");
+  int ns[] = {32, 64, 128};
   for (int n : ns)
-    for (int k4 = 0; k4 < 2; ++k4)
-      for (int cfg = 0; cfg < 4; ++cfg) {
-        int off = (cfg == 0) ? 0 : (cfg == 1 ? 1 : (cfg == 2 ? 0 : 19));
-        int sbo = (cfg < 2) ? 1024 : 2304;
-        probe<<<1, 128, 200 * 1024>>>(n, off, sbo, iters, k4, d);
+    for (int k4 = 1; k4 < 2; ++k4)
+      for (int cfg = 0; cfg < 9; ++cfg) {
+        int off = (cfg % 3 == 0) ? 0 : (cfg % 3 == 1 ? 11 : 19);
+        int sbo = (cfg % 3 == 0) ? 1024 : (cfg % 3 == 1 ? 1280 : 2304);
+        int spin = cfg / 3;
+        probe<<<1, 128 + (spin ? 256 : 0), 200 * 1024>>>(n, off, sbo, iters, k4, spin, d);
         long long h[2];
         cudaError_t e = cudaMemcpy(h, d, 16, cudaMemcpyDeviceToHost);
         if (e != cudaSuccess) { printf("error %s\n", cudaGetErrorString(e)); return 1; }
         const double m = (double)iters * (k4 ? 4 : 1);
-        printf("%5d %8d %6d %4d | %10.1f %10.1f\n", n, off, sbo, k4, h[0] / m, h[1] / m);
+        printf("%5d %8d %6d %4d %4d | %10.1f %10.1f\n", n, off, sbo, k4, spin, h[0] / m, h[1] / m);
       }
   return 0;
 }
