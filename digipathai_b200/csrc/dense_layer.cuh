@@ -1,0 +1,383 @@
+// One DenseNet layer per kernel: BN-ReLU -> 1x1 conv (C -> 128) -> BN-ReLU -> 3x3 conv (128 -> 32) -> concat
+// (reference: dense_conv_block, DigiPathAI/models/densenet.py:50-75), with the 128-channel bottleneck kept in
+// shared memory instead of a round trip through HBM and a second launch.
+//
+// Work item = one 16 x 8 pixel region of one image.  Per item:
+//   phase 1  for every 64-channel chunk of the concat buffer: TMA-load the region WITH its 1-pixel halo
+//            (18 x 10 pixels = 180 rows of 128 B), pre-activation BN+ReLU in place (4 transform warps), then
+//            tcgen05.mma M = 2 x 128 rows (rows >= 180 are don't-care), N = 128, accumulating in TMEM.
+//            The halo pixels' bottleneck values are recomputed by every region that needs them (1.41x the
+//            1x1 MACs) -- that is the price of not synchronising neighbouring CTAs.
+//   mid      epilogue warps: TMEM -> +BN shift -> ReLU -> zero outside the image (the 3x3's `same` padding is
+//            applied to the bottleneck, AFTER its BN-ReLU) -> fp16 -> written as two swizzled K-major operand
+//            tiles T[2][180 rows][64 ch] in shared memory, fence.proxy.async.
+//   phase 2  the 3x3 conv as 9 taps x 2 chunks of UMMA descriptors into T (row offset (dy+1)*10 + dx+1,
+//            SBO = 10 * 128 B), N = 32.
+//   final    TMEM -> fp16 -> the layer's 32 new channels in the concat buffer (coalesced via staging rows).
+//
+// Warp roles: 0 = TMA producer (activation halo chunks), 1 = MMA issuer, 2 = TMEM allocator, 3 = TMA producer
+// (W1 chunks, then W2 tap groups, one ring), 4-7 = epilogue (mid + final), 8-11 = pre-activation transform.
+#pragma once
+#include "conv_tc.cuh"
+
+namespace dp {
+
+constexpr int kDlHaloW = 10, kDlHaloH = 18, kDlRows = kDlHaloW * kDlHaloH;  // 180 halo pixels
+constexpr int kDlAStage = 256 * 128;   // 2 M-blocks of 128 rows x 128 B (rows 180..255 unused)
+constexpr int kDlBStage = 128 * 128;   // W1 chunk [128 x 64]; W2 groups (3 taps x [32 x 64] = 12 KB) fit too
+constexpr int kDlTBytes = 2 * kDlAStage;  // bottleneck operand: 2 chunks x 256 rows x 128 B
+constexpr int kDlW2Group = 3;          // taps per W2 stage
+
+struct DenseLayerParams {
+  int n_img, H, W, C;        // map size, input channels of this layer
+  int n_chunks;              // ceil(C / 64)
+  int tiles_w, tiles_h, n_items;
+  int a_stages, b_stages;
+  int out_ctot, out_choff;   // concat buffer channel stride, offset of the 32 new channels
+  const float* pro_scale;    // BN1 [n_chunks * 64]
+  const float* pro_shift;
+  const float* mid_shift;    // BN2 shift [128] (scale folded into W1)
+  __half* out;               // concat buffer base (same tensor the A map reads)
+  unsigned long long* trace;
+};
+
+struct DenseLayerSmem {
+  static constexpr int kBarBytes = 1024;
+  int a_off, b_off, t_off, pro_off, mid_off, stage_off, total;
+};
+
+__host__ __device__ inline DenseLayerSmem dense_layer_smem(const DenseLayerParams& p) {
+  DenseLayerSmem L;
+  L.a_off = DenseLayerSmem::kBarBytes;
+  L.b_off = L.a_off + p.a_stages * kDlAStage;
+  L.t_off = L.b_off + p.b_stages * kDlBStage;
+  L.pro_off = L.t_off + kDlTBytes;
+  L.mid_off = L.pro_off + 2 * p.n_chunks * 64 * 4;
+  L.stage_off = L.mid_off + 128 * 4;
+  L.total = L.stage_off + 4 * kEpiStageBytes + 1024;
+  return L;
+}
+
+__global__ void __launch_bounds__(384, 1)
+dense_layer_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w1,
+                   const __grid_constant__ CUtensorMap map_w2, const __grid_constant__ DenseLayerParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
+
+  uint64_t* a_full = reinterpret_cast<uint64_t*>(smem);
+  uint64_t* a_ready = a_full + kMaxAStages;
+  uint64_t* a_empty = a_ready + kMaxAStages;
+  uint64_t* b_full = a_empty + kMaxAStages;
+  uint64_t* b_empty = b_full + kMaxBStages;
+  uint64_t* acc1_full = b_empty + kMaxBStages;
+  uint64_t* acc1_empty = acc1_full + 1;
+  uint64_t* t_ready = acc1_empty + 1;
+  uint64_t* t_empty = t_ready + 1;
+  uint64_t* acc2_full = t_empty + 1;
+  uint64_t* acc2_empty = acc2_full + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc2_empty + 1);
+
+  const DenseLayerSmem L = dense_layer_smem(p);
+  uint8_t* a_base = smem + L.a_off;
+  uint8_t* b_base = smem + L.b_off;
+  uint8_t* t_base = smem + L.t_off;
+  float* s_pro_scale = reinterpret_cast<float*>(smem + L.pro_off);
+  float* s_pro_shift = s_pro_scale + p.n_chunks * 64;
+  float* s_mid_shift = reinterpret_cast<float*>(smem + L.mid_off);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&map_x);
+    tma_prefetch_desc(&map_w1);
+    tma_prefetch_desc(&map_w2);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < p.a_stages; ++i) {
+      mbar_init(&a_full[i], 1);
+      mbar_init(&a_ready[i], 128);
+      mbar_init(&a_empty[i], 1);
+    }
+    for (int i = 0; i < p.b_stages; ++i) {
+      mbar_init(&b_full[i], 1);
+      mbar_init(&b_empty[i], 1);
+    }
+    mbar_init(acc1_full, 1);
+    mbar_init(acc1_empty, 128);
+    mbar_init(t_ready, 128);
+    mbar_init(t_empty, 1);
+    mbar_init(acc2_full, 1);
+    mbar_init(acc2_empty, 128);
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_slot, kTmemCols);
+    tmem_relinquish();
+  }
+  {
+    const int npro = p.n_chunks * 64;
+    for (int i0 = 0; i0 < npro || i0 < 128; i0 += blockDim.x) {
+      const int i = i0 + tid;
+      float ps = 0.f, ph = 0.f, ms = 0.f;
+      if (i < npro) { ps = p.pro_scale[i]; ph = p.pro_shift[i]; }
+      if (i < 128) ms = p.mid_shift[i];
+      if (i < npro) { s_pro_scale[i] = ps; s_pro_shift[i] = ph; }
+      if (i < 128) s_mid_shift[i] = ms;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  pdl_launch_dependents();
+  pdl_wait();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t acc1_col = tmem_base;         // 2 M-blocks x 128 columns
+  const uint32_t acc2_col = tmem_base + 256;   // 32 columns
+
+  auto item_origin = [&](int item, int& n0, int& h0, int& w0) {
+    const int tw = item % p.tiles_w;
+    const int r = item / p.tiles_w;
+    w0 = tw * 8;
+    h0 = (r % p.tiles_h) * 16;
+    n0 = r / p.tiles_h;
+  };
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ producer: activation halo chunks
+    if (elect_one()) {
+      uint32_t sa = 0, pa = 0;
+      for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+        int n0, h0, w0;
+        item_origin(item, n0, h0, w0);
+        for (int c = 0; c < p.n_chunks; ++c) {
+          mbar_wait(&a_empty[sa], pa ^ 1);
+          mbar_expect_tx(&a_full[sa], kDlRows * 128);
+          tma_load_4d(&map_x, &a_full[sa], a_base + sa * kDlAStage, c * 64, w0 - 1, h0 - 1, n0);
+          if (++sa == p.a_stages) { sa = 0; pa ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 3) {
+    // ------------------------------------------------------------------ producer: W1 chunks, then W2 tap groups
+    if (elect_one()) {
+      uint32_t sb = 0, pb = 0;
+      for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+        for (int c = 0; c < p.n_chunks; ++c) {
+          mbar_wait(&b_empty[sb], pb ^ 1);
+          mbar_expect_tx(&b_full[sb], 128 * 128);
+          tma_load_3d(&map_w1, &b_full[sb], b_base + sb * kDlBStage, c * 64, 0, 0);
+          if (++sb == p.b_stages) { sb = 0; pb ^= 1; }
+        }
+        for (int c = 0; c < 2; ++c)
+          for (int g = 0; g < 9 / kDlW2Group; ++g) {
+            mbar_wait(&b_empty[sb], pb ^ 1);
+            mbar_expect_tx(&b_full[sb], kDlW2Group * 32 * 128);
+            tma_load_3d(&map_w2, &b_full[sb], b_base + sb * kDlBStage, c * 64, 0, g * kDlW2Group);
+            if (++sb == p.b_stages) { sb = 0; pb ^= 1; }
+          }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (elect_one()) {
+      const uint32_t idesc1 = make_idesc_f16(128), idesc2 = make_idesc_f16(32);
+      const uint64_t hi_dense = static_cast<uint64_t>(sw128_desc_hi(1024)) << 32;
+      const uint64_t hi_halo = static_cast<uint64_t>(sw128_desc_hi(kDlHaloW * 128)) << 32;
+      const uint64_t a_desc0 = hi_dense | sw128_desc_lo(smem_u32(a_base));
+      const uint64_t b_desc0 = hi_dense | sw128_desc_lo(smem_u32(b_base));
+      const uint64_t t_desc0 = hi_halo | sw128_desc_lo(smem_u32(t_base));
+      uint32_t sa = 0, pa = 0, sb = 0, pb = 0, ph = 0;  // ph: per-item phase parity of the single-stage barriers
+      for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ph ^= 1) {
+        // ---- phase 1: bottleneck = W1 * relu(bn(x)) over the halo region
+        mbar_wait(acc1_empty, ph ^ 1);
+        tc_fence_after();
+        for (int c = 0; c < p.n_chunks; ++c) {
+          int ks = (p.C - c * 64 + 15) >> 4;
+          ks = ks > 4 ? 4 : ks;
+          mbar_wait(&a_ready[sa], pa);
+          mbar_wait(&b_full[sb], pb);
+          tc_fence_after();
+          const uint64_t a_desc = a_desc0 + sa * (kDlAStage >> 4);
+          const uint64_t b_desc = b_desc0 + sb * (kDlBStage >> 4);
+          const uint32_t acc = (c > 0) ? 1u : 0u;
+          if (ks == 4) {
+            umma_f16_ss_k4(acc1_col, a_desc, b_desc, idesc1, acc);
+            umma_f16_ss_k4(acc1_col + 128, a_desc + (kATileBytes >> 4), b_desc, idesc1, acc);
+          } else {
+            for (int k = 0; k < ks; ++k) {
+              umma_f16_ss(acc1_col, a_desc + 2 * k, b_desc + 2 * k, idesc1, k ? 1u : acc);
+              umma_f16_ss(acc1_col + 128, a_desc + (kATileBytes >> 4) + 2 * k, b_desc + 2 * k, idesc1, k ? 1u : acc);
+            }
+          }
+          umma_commit(&a_empty[sa]);
+          umma_commit(&b_empty[sb]);
+          if (++sa == p.a_stages) { sa = 0; pa ^= 1; }
+          if (++sb == p.b_stages) { sb = 0; pb ^= 1; }
+        }
+        umma_commit(acc1_full);
+        // ---- phase 2: 3x3 conv over the bottleneck tile in shared memory
+        mbar_wait(t_ready, ph);
+        mbar_wait(acc2_empty, ph ^ 1);
+        tc_fence_after();
+        for (int c = 0; c < 2; ++c) {
+          const uint64_t t_desc = t_desc0 + c * (kDlAStage >> 4);
+          for (int g = 0; g < 9 / kDlW2Group; ++g) {
+            mbar_wait(&b_full[sb], pb);
+            tc_fence_after();
+            uint64_t b_desc = b_desc0 + sb * (kDlBStage >> 4);
+#pragma unroll
+            for (int j = 0; j < kDlW2Group; ++j, b_desc += (32 * 128) >> 4) {
+              const int tap = g * kDlW2Group + j;
+              const int dy = tap / 3, dx = tap - dy * 3;  // (dy+1, dx+1) with dy,dx in -1..1
+              umma_f16_ss_k4(acc2_col, t_desc + (dy * kDlHaloW + dx) * 8, b_desc, idesc2, (c | tap) ? 1u : 0u);
+            }
+            umma_commit(&b_empty[sb]);
+            if (++sb == p.b_stages) { sb = 0; pb ^= 1; }
+          }
+        }
+        umma_commit(t_empty);
+        umma_commit(acc2_full);
+      }
+    }
+  } else if (warp >= 4 && warp < 8) {
+    // ------------------------------------------------------------------ epilogue warps: mid + final
+    const int q = warp & 3;
+    const int r = q * 32 + lane;
+    uint8_t* stage = smem + L.stage_off + q * kEpiStageBytes;
+    uint32_t ph = 0;
+    for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ph ^= 1) {
+      int n0, h0, w0;
+      item_origin(item, n0, h0, w0);
+      // ---- mid: acc1 -> +shift -> ReLU -> zero padding -> fp16 -> swizzled operand tile T
+      mbar_wait(acc1_full, ph);
+      mbar_wait(t_empty, ph ^ 1);   // previous item's 3x3 MMAs no longer read T
+      tc_fence_after();
+#pragma unroll 1
+      for (int mb = 0; mb < 2; ++mb) {
+        const int prow = mb * 128 + r;                 // halo pixel index
+        const int hh = prow / kDlHaloW, ww = prow - hh * kDlHaloW;
+        const int ih = h0 - 1 + hh, iw = w0 - 1 + ww;
+        const bool inside = prow < kDlRows && ih >= 0 && ih < p.H && iw >= 0 && iw < p.W;
+        const uint32_t taddr = acc1_col + mb * 128 + (static_cast<uint32_t>(q * 32) << 16);
+#pragma unroll 1
+        for (int cc = 0; cc < 128; cc += 32) {
+          uint32_t v[2][16];
+          tmem_ld16(taddr + cc, v[0]);
+          tmem_ld16(taddr + cc + 16, v[1]);
+          tmem_ld_wait();
+          if (prow < kDlRows) {
+#pragma unroll
+            for (int hsel = 0; hsel < 2; ++hsel) {
+              const int cb = cc + 16 * hsel;
+              float f[16];
+              epi_affine16(v[hsel], nullptr, s_mid_shift + cb, false, true, f);
+              uint32_t pk[8];
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                __half2 h2 = inside ? __floats2half2_rn(f[2 * i], f[2 * i + 1]) : __float2half2_rn(0.f);
+                pk[i] = *reinterpret_cast<uint32_t*>(&h2);
+              }
+              // channels cb..cb+15 = 16-byte chunks j, j+1 of 64-channel chunk (cb / 64)
+              uint8_t* row = t_base + (cb >> 6) * kDlAStage + prow * 128;
+              const int j = (cb & 63) >> 3;
+              *reinterpret_cast<uint4*>(row + (((j) ^ (prow & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+              *reinterpret_cast<uint4*>(row + (((j + 1) ^ (prow & 7)) << 4)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      fence_proxy_async_smem();
+      mbar_arrive(acc1_empty);
+      mbar_arrive(t_ready);
+      // ---- final: acc2 -> fp16 -> 32 new channels of the concat buffer
+      mbar_wait(acc2_full, ph);
+      tc_fence_after();
+      {
+        const int w = w0 + (r & 7), h = h0 + (r >> 3);
+        const bool valid = (n0 < p.n_img) && (h < p.H) && (w < p.W);
+        const long long opix = (static_cast<long long>(n0) * p.H + h) * p.W + w;
+        const unsigned long long my_row = reinterpret_cast<unsigned long long>(p.out + opix * p.out_ctot + p.out_choff);
+        uint32_t v[2][16];
+        const uint32_t taddr = acc2_col + (static_cast<uint32_t>(q * 32) << 16);
+        tmem_ld16(taddr, v[0]);
+        tmem_ld16(taddr + 16, v[1]);
+        tmem_ld_wait();
+#pragma unroll
+        for (int hsel = 0; hsel < 2; ++hsel) {
+          uint32_t pk[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            __half2 h2 = __floats2half2_rn(__uint_as_float(v[hsel][2 * i]), __uint_as_float(v[hsel][2 * i + 1]));
+            pk[i] = *reinterpret_cast<uint32_t*>(&h2);
+          }
+          uint4* dst = reinterpret_cast<uint4*>(stage + lane * kEpiRowBytes + hsel * 32);
+          dst[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+          dst[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+        }
+        __syncwarp();
+#pragma unroll
+        for (int it = 0; it < 4; ++it) {   // 32 rows x 4 chunks of 16 B; 4 lanes cover one pixel's 64 bytes
+          const int idx = it * 32 + lane;
+          const int row = idx >> 2, j = idx & 3;
+          const unsigned long long rp = __shfl_sync(0xffffffffu, my_row, row);
+          const int rv = __shfl_sync(0xffffffffu, static_cast<int>(valid), row);
+          const uint4 val = *reinterpret_cast<const uint4*>(stage + row * kEpiRowBytes + j * 16);
+          if (rv) *reinterpret_cast<uint4*>(reinterpret_cast<__half*>(rp) + j * 8) = val;
+        }
+        __syncwarp();
+      }
+      tc_fence_before();
+      mbar_arrive(acc2_empty);
+    }
+  } else if (warp >= 8) {
+    // ------------------------------------------------------------------ pre-activation BN + ReLU on the halo rows
+    const int t = tid - 256;
+    const __half2 zero2 = __float2half2_rn(0.f);
+    uint32_t sa = 0, pa = 0;
+    for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+      for (int c = 0; c < p.n_chunks; ++c) {
+        mbar_wait(&a_full[sa], pa);
+        for (int rr = t; rr < kDlRows; rr += 128) {
+          uint8_t* row = a_base + sa * kDlAStage + rr * 128;
+          uint4 raw[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) raw[i] = *reinterpret_cast<const uint4*>(row + ((i ^ (rr & 7)) << 4));
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int ch = c * 64 + i * 8;
+            const float4 sc0 = *reinterpret_cast<const float4*>(s_pro_scale + ch);
+            const float4 sc1 = *reinterpret_cast<const float4*>(s_pro_scale + ch + 4);
+            const float4 sh0 = *reinterpret_cast<const float4*>(s_pro_shift + ch);
+            const float4 sh1 = *reinterpret_cast<const float4*>(s_pro_shift + ch + 4);
+            __half2* hv = reinterpret_cast<__half2*>(&raw[i]);
+            float2 x;
+            x = __half22float2(hv[0]);
+            hv[0] = __hmax2(__floats2half2_rn(fmaf(x.x, sc0.x, sh0.x), fmaf(x.y, sc0.y, sh0.y)), zero2);
+            x = __half22float2(hv[1]);
+            hv[1] = __hmax2(__floats2half2_rn(fmaf(x.x, sc0.z, sh0.z), fmaf(x.y, sc0.w, sh0.w)), zero2);
+            x = __half22float2(hv[2]);
+            hv[2] = __hmax2(__floats2half2_rn(fmaf(x.x, sc1.x, sh1.x), fmaf(x.y, sc1.y, sh1.y)), zero2);
+            x = __half22float2(hv[3]);
+            hv[3] = __hmax2(__floats2half2_rn(fmaf(x.x, sc1.z, sh1.z), fmaf(x.y, sc1.w, sh1.w)), zero2);
+          }
+#pragma unroll
+          for (int i = 0; i < 8; ++i) *reinterpret_cast<uint4*>(row + ((i ^ (rr & 7)) << 4)) = raw[i];
+        }
+        fence_proxy_async_smem();
+        mbar_arrive(&a_ready[sa]);
+        if (++sa == p.a_stages) { sa = 0; pa ^= 1; }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+}  // namespace dp
