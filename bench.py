@@ -273,9 +273,9 @@ def main():
     model.set_option("profile", 0)
     per_op = acc / n_prof
     infos = [model.op_info(i) for i in range(model.n_ops())]
-    conv_ms = float(sum(t for t, inf in zip(per_op, infos) if inf["type"] == 3))
+    conv_ms = float(sum(t for t, inf in zip(per_op, infos) if inf["type"] in (3, 6)))
     all_ms = float(per_op.sum())
-    n_conv = sum(1 for inf in infos if inf["type"] == 3)
+    n_conv = sum(1 for inf in infos if inf["type"] in (3, 6))
     flop_step = REF_FLOP_PER_TILE * BATCH
     achieved_tf = flop_step / (conv_ms * 1e-3) / 1e12
     exec_macs = model.executed_macs(BATCH)
@@ -320,7 +320,7 @@ def main():
             "gpu_launches": int(launches),
             "roofline": {"bound": "tensor", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
                          "frac": achieved_tf / peak_tf, "traffic": None,
-                         "kernel": f"conv_tc_kernel ({n_conv} launches per step; algorithmic FLOPs of the "
+                         "kernel": f"conv_tc_kernel + dense_layer_kernel, tcgen05 implicit-GEMM family ({n_conv} launches per step; algorithmic FLOPs of the "
                                    f"reference graph / summed CUDA-event time of those launches)",
                          "peak_source": f"{peak_src} bf16_tflops_sustained",
                          "conv_ms_per_step": conv_ms, "all_ops_ms_per_step": all_ms, "top_ops": top_desc},

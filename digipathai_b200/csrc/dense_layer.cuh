@@ -16,7 +16,8 @@
 //   final    TMEM -> fp16 -> the layer's 32 new channels in the concat buffer (coalesced via staging rows).
 //
 // Warp roles: 0 = TMA producer (activation halo chunks), 1 = MMA issuer, 2 = TMEM allocator, 3 = TMA producer
-// (W1 chunks, then W2 tap groups, one ring), 4-7 = epilogue (mid + final), 8-11 = pre-activation transform.
+// (W1 chunks, then W2 tap groups, one ring), 4-7 = epilogue (mid + final), 8-15 = pre-activation transform
+// (the transform, not the MMA, paces phase 1: ~3.5 ALU instructions per fp16 element in fp32 arithmetic).
 #pragma once
 #include "conv_tc.cuh"
 
@@ -58,7 +59,7 @@ __host__ __device__ inline DenseLayerSmem dense_layer_smem(const DenseLayerParam
   return L;
 }
 
-__global__ void __launch_bounds__(384, 1)
+__global__ void __launch_bounds__(512, 1)
 dense_layer_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w1,
                    const __grid_constant__ CUtensorMap map_w2, const __grid_constant__ DenseLayerParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -96,7 +97,7 @@ dense_layer_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < p.a_stages; ++i) {
       mbar_init(&a_full[i], 1);
-      mbar_init(&a_ready[i], 128);
+      mbar_init(&a_ready[i], 256);
       mbar_init(&a_empty[i], 1);
     }
     for (int i = 0; i < p.b_stages; ++i) {
@@ -339,7 +340,7 @@ dense_layer_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
     for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
       for (int c = 0; c < p.n_chunks; ++c) {
         mbar_wait(&a_full[sa], pa);
-        for (int rr = t; rr < kDlRows; rr += 128) {
+        for (int rr = t; rr < kDlRows; rr += 256) {   // 8 warps: one halo row per thread
           uint8_t* row = a_base + sa * kDlAStage + rr * 128;
           uint4 raw[8];
 #pragma unroll

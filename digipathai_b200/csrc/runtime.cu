@@ -18,6 +18,7 @@
 #include "../../include/digipath_b200.h"
 #include "aux.cuh"
 #include "conv_tc.cuh"
+#include "dense_layer.cuh"
 
 namespace {
 
@@ -94,7 +95,7 @@ static_assert(sizeof(BlobHeader) == 72, "header layout");
 struct BlobBuf {
   int32_t H, W, C, pad;
 };
-enum : int { OP_STEM_IM2COL = 1, OP_MAXPOOL = 2, OP_CONV = 3, OP_BNPOOL = 4, OP_STEM_S2D = 5 };
+enum : int { OP_STEM_IM2COL = 1, OP_MAXPOOL = 2, OP_CONV = 3, OP_BNPOOL = 4, OP_STEM_S2D = 5, OP_DENSE_LAYER = 6 };
 struct BlobOp {
   int32_t type, in_buf, in_choff, cin, out_buf, out_choff, cout, kind, relu, pro, head, pool;
   float head_b;
@@ -114,6 +115,10 @@ struct Launch {
   uint64_t macs = 0;
   // head (naive path)
   int head_C = 0;
+  // fused dense layer
+  CUtensorMap map_w2;
+  dp::DenseLayerParams dl;
+  dp::NaiveConvParams np2;  // debug path: the 3x3 half (np holds the 1x1 half)
 };
 
 struct SubPlan {
@@ -387,6 +392,93 @@ int plan_conv(dp_model* m, const BlobOp& op, int img0, int B, Launch& L) {
   return 0;
 }
 
+int plan_dense_layer(dp_model* m, const BlobOp& op, int img0, int B, Launch& L) {
+  using namespace dp;
+  const BlobBuf& ib = m->bufs[op.in_buf];
+  const int H = ib.H, W = ib.W;
+  // maps lower than one 16-row region (8x8) run as a single region whose lower rows are out of bounds:
+  // TMA zero-fills them, the mid-epilogue keeps them zero and the final epilogue never stores them
+  if ((H % 16 && H != 8) || W % 8) return fail("dense layer: map %dx%d needs H %% 16 == 0 (or H == 8) and W %% 8 == 0", H, W);
+  if (op.cout != 32 || op.cin % 8) return fail("dense layer: growth must be 32 and Cin a multiple of 8");
+  const int mid_buf = op.rsv[0];
+  if (mid_buf < 0 || mid_buf >= (int)m->bufs.size() || m->bufs[mid_buf].C != 128 || m->bufs[mid_buf].H != H)
+    return fail("dense layer: bad bottleneck buffer");
+  auto buf_at = [&](int buf) {
+    const BlobBuf& bb = m->bufs[buf];
+    return m->buf_dev[buf] + (size_t)img0 * bb.H * bb.W * bb.C;
+  };
+  // ---- debug path: the same layer as two naive convs through the bottleneck buffer
+  TapEntry t1[kMaxEntries], t3[kMaxEntries];
+  int n1 = 0, n3 = 0;
+  fill_entries(1, t1, &n1);
+  fill_entries(3, t3, &n3);
+  NaiveConvParams& a = L.np;
+  memset(&a, 0, sizeof a);
+  a.n_img = B; a.H = H; a.W = W; a.Cin = op.cin; a.in_ctot = ib.C; a.in_choff = op.in_choff;
+  a.Cout = 128; a.out_ctot = 128; a.out_choff = 0; a.n_entries_total = 1; a.n_groups = 1;
+  a.relu = 1; a.pro_mode = 2;
+  memcpy(a.entries, t1, sizeof t1);
+  a.in = buf_at(op.in_buf); a.w = dptr<__half>(m, op.w_off);
+  a.epi_shift = dptr<float>(m, op.epi_shift_off);
+  a.pro_scale = dptr<float>(m, op.pro_scale_off); a.pro_shift = dptr<float>(m, op.pro_shift_off);
+  a.out = buf_at(mid_buf);
+  NaiveConvParams& b = L.np2;
+  memset(&b, 0, sizeof b);
+  b.n_img = B; b.H = H; b.W = W; b.Cin = 128; b.in_ctot = 128; b.in_choff = 0;
+  b.Cout = 32; b.out_ctot = ib.C; b.out_choff = op.out_choff; b.n_entries_total = 9; b.n_groups = 1;
+  memcpy(b.entries, t3, sizeof t3);
+  b.in = buf_at(mid_buf); b.w = dptr<__half>(m, op.rsv64[0]); b.out = buf_at(op.in_buf);
+
+  // ---- fused tensor-core plan
+  DenseLayerParams& p = L.dl;
+  memset(&p, 0, sizeof p);
+  p.n_img = B; p.H = H; p.W = W; p.C = op.cin;
+  p.n_chunks = (op.cin + 63) / 64;
+  p.tiles_w = W / 8; p.tiles_h = (H + 15) / 16;
+  p.n_items = B * p.tiles_w * p.tiles_h;
+  p.out_ctot = ib.C; p.out_choff = op.out_choff;
+  p.pro_scale = a.pro_scale; p.pro_shift = a.pro_shift; p.mid_shift = a.epi_shift;
+  p.out = buf_at(op.in_buf);
+  const int budget = 227 * 1024 - DenseLayerSmem::kBarBytes - kDlTBytes - 2 * p.n_chunks * 64 * 4 - 128 * 4 -
+                     4 * kEpiStageBytes - 1024;
+  p.a_stages = 3; p.b_stages = 3;
+  while (p.a_stages * kDlAStage + p.b_stages * kDlBStage > budget && p.a_stages > 2) --p.a_stages;
+  while (p.a_stages * kDlAStage + p.b_stages * kDlBStage > budget && p.b_stages > 2) --p.b_stages;
+  if (p.a_stages * kDlAStage + p.b_stages * kDlBStage > budget) return fail("dense layer: shared memory budget exceeded");
+  L.smem = dense_layer_smem(p).total;
+  const int rounds = (p.n_items + m->num_sms - 1) / m->num_sms;
+  L.grid = (p.n_items + rounds - 1) / rounds;
+  {
+    uint64_t ksteps = 0;
+    for (int c = 0; c < p.n_chunks; ++c) {
+      int ks = (op.cin - c * 64 + 15) / 16;
+      ksteps += ks > 4 ? 4 : ks;
+    }
+    // executed: 1x1 on 256 rows per 128-pixel region (halo recompute + padding rows), 3x3 on 128 rows
+    L.macs = (uint64_t)p.n_items * (256ull * 128 * ksteps * 16 + 128ull * 32 * 9 * 128);
+  }
+  {
+    uint64_t dims[4] = {(uint64_t)op.cin, (uint64_t)W, (uint64_t)H, (uint64_t)B};
+    const uint64_t cs = (uint64_t)ib.C * 2;
+    uint64_t str[3] = {cs, cs * W, cs * W * H};
+    uint32_t box[4] = {64, (uint32_t)kDlHaloW, (uint32_t)kDlHaloH, 1};
+    if (make_map(&L.map_a, buf_at(op.in_buf) + op.in_choff, 4, dims, str, box)) return 1;
+  }
+  {
+    uint64_t dims[3] = {(uint64_t)op.cin, 128, 1};
+    uint64_t str[2] = {(uint64_t)op.cin * 2, (uint64_t)op.cin * 2 * 128};
+    uint32_t box[3] = {64, 128, 1};
+    if (make_map(&L.map_b, a.w, 3, dims, str, box)) return 1;
+  }
+  {
+    uint64_t dims[3] = {128, 32, 9};
+    uint64_t str[2] = {128 * 2, 128 * 2 * 32};
+    uint32_t box[3] = {64, 32, (uint32_t)kDlW2Group};
+    if (make_map(&L.map_w2, b.w, 3, dims, str, box)) return 1;
+  }
+  return 0;
+}
+
 int get_plan(dp_model* m, int B, int split, Plan** out) {
   std::lock_guard<std::mutex> lk(m->mu);
   if (split < 1 || B % split || B / split < 1) split = 1;
@@ -406,11 +498,13 @@ int get_plan(dp_model* m, int B, int split, Plan** out) {
     sp.launches.resize(m->ops.size());
     for (size_t i = 0; i < m->ops.size(); ++i) {
       sp.launches[i].type = m->ops[i].type;
-      if (m->ops[i].type == OP_CONV)
-        if (plan_conv(m, m->ops[i], sp.img0, bs, sp.launches[i])) {
-          g_err = "op " + std::to_string(i) + ": " + g_err;
-          return 1;
-        }
+      int prc = 0;
+      if (m->ops[i].type == OP_CONV) prc = plan_conv(m, m->ops[i], sp.img0, bs, sp.launches[i]);
+      if (m->ops[i].type == OP_DENSE_LAYER) prc = plan_dense_layer(m, m->ops[i], sp.img0, bs, sp.launches[i]);
+      if (prc) {
+        g_err = "op " + std::to_string(i) + ": " + g_err;
+        return 1;
+      }
     }
   }
   auto res = m->plans.emplace(key, std::move(plan));
@@ -518,6 +612,33 @@ int run_op(dp_model* m, SubPlan* sp, int i, cudaStream_t st) {
       LAUNCH_OK();
       return 0;
     }
+    case OP_DENSE_LAYER: {
+      if (m->naive_conv) {
+        long long total = (long long)B * L.np.H * L.np.W * L.np.Cout;
+        dp::conv_naive_kernel<<<grid_for(total, 256), 256, 0, st>>>(L.np);
+        LAUNCH_OK();
+        total = (long long)B * L.np2.H * L.np2.W * L.np2.Cout;
+        dp::conv_naive_kernel<<<grid_for(total, 256), 256, 0, st>>>(L.np2);
+        LAUNCH_OK();
+        return 0;
+      }
+      dp::DenseLayerParams dl = L.dl;
+      cudaLaunchConfig_t cfg;
+      memset(&cfg, 0, sizeof cfg);
+      cfg.gridDim = dim3(L.grid);
+      cfg.blockDim = dim3(512);
+      cfg.dynamicSmemBytes = L.smem;
+      cfg.stream = st;
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+      attr[0].val.programmaticStreamSerializationAllowed = 1;
+      cfg.attrs = attr;
+      cfg.numAttrs = m->use_pdl ? 1 : 0;
+      cudaError_t le = cudaLaunchKernelEx(&cfg, dp::dense_layer_kernel, L.map_a, L.map_b, L.map_w2, dl);
+      if (le != cudaSuccess) return fail("dense layer launch failed: %s", cudaGetErrorString(le));
+      LAUNCH_OK();
+      return 0;
+    }
     default:
       return fail("unknown op type %d", op.type);
   }
@@ -614,7 +735,8 @@ int dp_model_create(const void* blob, size_t nbytes, int device, int max_batch, 
     cudaError_t e2 = cudaFuncSetAttribute(dp::conv_tc_kernel<dp::MODE_D, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
     cudaError_t e3 = cudaFuncSetAttribute(dp::conv_tc_kernel<dp::MODE_T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
     cudaError_t e4 = cudaFuncSetAttribute(dp::conv_tc_kernel<dp::MODE_H, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
-    if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess || e4 != cudaSuccess) {
+    cudaError_t e5 = cudaFuncSetAttribute(dp::dense_layer_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
+    if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess || e4 != cudaSuccess || e5 != cudaSuccess) {
       cleanup();
       return fail("cudaFuncSetAttribute(MaxDynamicSharedMemorySize) failed: %s", cudaGetErrorString(cudaGetLastError()));
     }
@@ -878,7 +1000,7 @@ int dp_model_op_info(const dp_model* m, int op, int* type, int* kind, int* cin, 
   if (w) *w = m->bufs[o.in_buf].W;
   if (macs_per_tile) {
     *macs_per_tile = 0;
-    if (o.type == OP_CONV) {
+    if (o.type == OP_CONV || o.type == OP_DENSE_LAYER) {
       Plan* plan = nullptr;
       if (get_plan(const_cast<dp_model*>(m), 1, 1, &plan)) return 1;
       *macs_per_tile = plan->subs[0].launches[op].macs;

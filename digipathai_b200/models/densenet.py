@@ -15,7 +15,8 @@ from __future__ import annotations
 
 import numpy as np
 
-from ..program import (KIND_1X1, KIND_3X3, KIND_STEM4, KIND_UP2, OP_BNPOOL, OP_CONV, OP_MAXPOOL, OP_STEM_S2D,
+from ..program import (KIND_1X1, KIND_3X3, KIND_STEM4, KIND_UP2, OP_BNPOOL, OP_CONV, OP_DENSE_LAYER, OP_MAXPOOL,
+                       OP_STEM_S2D,
                        PRO_AFFINE_RELU, Op, Program, bn_affine, pack_conv_weights, pack_stem4_weights, pad64)
 
 DENSENET_BLOCKS = (6, 12, 24, 16)
@@ -72,7 +73,7 @@ def init_densenet_weights(seed: int = 0) -> dict:
     return w
 
 
-def densenet121_unet_program(weights: dict, patch: int = 256) -> Program:
+def densenet121_unet_program(weights: dict, patch: int = 256, fuse_dense: bool = True) -> Program:
     if patch < 64 or patch & (patch - 1):
         raise ValueError("patch_size must be a power of two >= 64 for the B200 tile kernels")
     P = patch
@@ -113,6 +114,13 @@ def densenet121_unet_program(weights: dict, patch: int = 256) -> Program:
             c = c0 + GROWTH * (i - 1)
             ps, psh = bn_affine(*weights[p + "_0_bn"], EPS_ENC)
             es, esh = bn_affine(*weights[p + "_1_bn"], EPS_ENC)
+            if fuse_dense and (P // 2 ** b) >= 8:
+                # whole dense layer in one kernel, bottleneck kept in shared memory (csrc/dense_layer.cuh)
+                ops.append(Op(OP_DENSE_LAYER, in_buf=D, in_choff=base, cin=c, out_buf=D, out_choff=base + c,
+                              cout=GROWTH, mid_buf=T[b], pro=PRO_AFFINE_RELU, pro_scale=pad64(ps), pro_shift=pad64(psh),
+                              epi_shift=esh, w=pack_conv_weights(weights[p + "_1_conv"] * es, KIND_1X1),
+                              w2=pack_conv_weights(weights[p + "_2_conv"], KIND_3X3), name=p))
+                continue
             # BN-ReLU (pre-activation, in the A-tile prologue) -> 1x1 -> BN-ReLU (epilogue)   densenet.py:59-69
             ops.append(Op(OP_CONV, in_buf=D, in_choff=base, cin=c, out_buf=T[b], cout=128, kind=KIND_1X1, relu=1,
                           pro=PRO_AFFINE_RELU, pro_scale=pad64(ps), pro_shift=pad64(psh), epi_shift=esh,

@@ -12,7 +12,8 @@ Container layout (must match ``BlobHeader`` / ``BlobBuf`` / ``BlobOp`` in csrc/r
     n_bufs x 16 B: i32 H, W, C, 0                      (per-image activation buffer geometry)
     n_ops  x 128 B: 12 x i32 (type in_buf in_choff cin out_buf out_choff cout kind relu pro head pool)
                    | f32 head_b | 3 x i32 0 | 8 x i64 offsets into the data section (-1 = absent):
-                     w, epi_scale, epi_shift, pro_scale, pro_shift, head_w, 0, 0
+                     w, epi_scale, epi_shift, pro_scale, pro_shift, head_w, w2, 0
+                   (rsv i32 #0 = mid_buf for OP_DENSE_LAYER)
     data section : 256-byte aligned arrays (fp16 weights [entries][Cout][Cin]; fp32 vectors)
 """
 from __future__ import annotations
@@ -23,7 +24,7 @@ from typing import List, Optional
 
 import numpy as np
 
-OP_STEM_IM2COL, OP_MAXPOOL, OP_CONV, OP_BNPOOL, OP_STEM_S2D = 1, 2, 3, 4, 5
+OP_STEM_IM2COL, OP_MAXPOOL, OP_CONV, OP_BNPOOL, OP_STEM_S2D, OP_DENSE_LAYER = 1, 2, 3, 4, 5, 6
 KIND_1X1, KIND_3X3, KIND_UP2, KIND_STEM4 = 1, 3, 4, 5
 PRO_NONE, PRO_AFFINE, PRO_AFFINE_RELU = 0, 1, 2
 
@@ -49,6 +50,8 @@ class Op:
     pro_scale: Optional[np.ndarray] = None  # fp32 [ceil(cin/64)*64]
     pro_shift: Optional[np.ndarray] = None
     head_w: Optional[np.ndarray] = None     # fp32 [cout]
+    w2: Optional[np.ndarray] = None         # OP_DENSE_LAYER: fp16 [9, 32, 128] 3x3 weights (w = [1, 128, cin])
+    mid_buf: int = 0                        # OP_DENSE_LAYER: bottleneck buffer (only the debug path writes it)
     name: str = ""
 
 
@@ -178,12 +181,16 @@ def serialize(prog: Program) -> bytes:
                 assert o.head_w is not None and len(o.head_w) == o.cout, o.name
         offs = [
             put(o.w, np.float16), put(o.epi_scale, np.float32), put(o.epi_shift, np.float32),
-            put(o.pro_scale, np.float32), put(o.pro_shift, np.float32), put(o.head_w, np.float32), 0, 0,
+            put(o.pro_scale, np.float32), put(o.pro_shift, np.float32), put(o.head_w, np.float32),
+            put(o.w2, np.float16), 0,
         ]
+        if o.type == OP_DENSE_LAYER:
+            assert o.w is not None and o.w.shape == (1, 128, o.cin) and o.w2 is not None and o.w2.shape == (9, 32, 128)
+            assert o.cout == 32 and o.in_buf == o.out_buf and o.pro_scale is not None and o.epi_shift is not None
         op_recs.append(
             struct.pack(
                 "<12if3i8q", o.type, o.in_buf, o.in_choff, o.cin, o.out_buf, o.out_choff, o.cout, o.kind, o.relu,
-                o.pro, o.head, o.pool, float(o.head_b), 0, 0, 0, *offs,
+                o.pro, o.head, o.pool, float(o.head_b), o.mid_buf, 0, 0, *offs,
             )
         )
     buf_recs = [struct.pack("<4i", h, w, c, 0) for (h, w, c) in prog.bufs]

@@ -3,8 +3,8 @@ from __future__ import annotations
 
 import numpy as np
 
-from digipathai_b200.program import (KIND_1X1, KIND_3X3, KIND_UP2, OP_CONV, PRO_AFFINE_RELU, Op, Program,
-                                     pack_conv_weights, pad64)
+from digipathai_b200.program import (KIND_1X1, KIND_3X3, KIND_UP2, OP_CONV, OP_DENSE_LAYER, PRO_AFFINE_RELU, Op,
+                                     Program, pack_conv_weights, pad64)
 
 # name: (kind, H, W, Cin, Cout, B, in_ctot, in_choff, out_ctot, out_choff, prologue, relu, head)
 CASES = {
@@ -50,4 +50,32 @@ def build_case(name: str, seed: int = 0):
         op.head_b = 0.1
     pr.ops.append(op)
     x = rng.standard_normal((B, H, W, ictot)).astype(np.float16)
+    return pr, x, B
+
+
+# fused dense layer: name -> (H, W, Cin, B, ctot, base)
+DENSE_CASES = {
+    "dl_16x16_c256": (16, 16, 256, 3, 1344, 320),
+    "dl_32x32_c160": (32, 32, 160, 2, 768, 256),     # channel tail chunk (160 = 2.5 x 64)
+    "dl_64x64_c64":  (64, 64, 64, 2, 384, 128),
+    "dl_16x16_c992": (16, 16, 992, 5, 1344, 320),    # last layer of block 4, odd batch
+    "dl_8x8_c512":   (8, 8, 512, 4, 1024, 0),        # block 5: map lower than the 16-row region
+}
+
+
+def build_dense_case(name: str, seed: int = 0):
+    H, W, cin, B, ctot, base = DENSE_CASES[name]
+    rng = np.random.default_rng(seed)
+    pr = Program(patch=64)
+    D = pr.add_buf("D", H, W, ctot)
+    T = pr.add_buf("T", H, W, 128)
+    k1 = (rng.standard_normal((1, 1, cin, 128)) * np.sqrt(2.0 / cin)).astype(np.float32)
+    k3 = (rng.standard_normal((3, 3, 128, 32)) * np.sqrt(2.0 / (9 * 128))).astype(np.float32)
+    op = Op(OP_DENSE_LAYER, in_buf=D, in_choff=base, cin=cin, out_buf=D, out_choff=base + cin, cout=32, mid_buf=T,
+            pro=PRO_AFFINE_RELU, pro_scale=pad64(rng.uniform(0.5, 1.5, cin).astype(np.float32)),
+            pro_shift=pad64((0.3 * rng.standard_normal(cin)).astype(np.float32)),
+            epi_shift=(0.2 * rng.standard_normal(128)).astype(np.float32),
+            w=pack_conv_weights(k1, KIND_1X1), w2=pack_conv_weights(k3, KIND_3X3), name=name)
+    pr.ops.append(op)
+    x = rng.standard_normal((B, H, W, ctot)).astype(np.float16)
     return pr, x, B

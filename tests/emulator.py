@@ -11,7 +11,7 @@ import torch
 
 from digipathai_b200 import tta
 from digipathai_b200.program import (KIND_1X1, KIND_3X3, KIND_STEM4, KIND_UP2, OP_BNPOOL, OP_CONV, OP_MAXPOOL,
-                                     OP_STEM_IM2COL, OP_STEM_S2D, Program)
+                                     OP_DENSE_LAYER, OP_STEM_IM2COL, OP_STEM_S2D, Program)
 
 
 def entries(kind):
@@ -98,6 +98,16 @@ def run(prog: Program, tiles_u8: np.ndarray, tta_in: int = 0, tta_out: int = 0, 
             if op.pool:
                 y = torch.nn.functional.avg_pool2d(y.permute(0, 3, 1, 2), 2, stride=2).permute(0, 2, 3, 1)
             bufs[op.out_buf][..., op.out_choff:op.out_choff + op.cin] = q(y)
+        elif op.type == OP_DENSE_LAYER:
+            x = bufs[op.in_buf][..., op.in_choff:op.in_choff + op.cin]
+            x = q(torch.relu(x * f(op.pro_scale[:op.cin]) + f(op.pro_shift[:op.cin])))
+            t = q(torch.relu(x @ torch.from_numpy(op.w[0].astype(np.float32)).T + f(op.epi_shift)))
+            w2 = torch.from_numpy(op.w2.astype(np.float32))
+            y = torch.zeros(*t.shape[:3], op.cout)
+            for e, (dy, dx, g) in enumerate(entries(KIND_3X3)):
+                y += _shift(t, dy, dx) @ w2[e].T
+            bufs[op.mid_buf][:] = t
+            bufs[op.out_buf][..., op.out_choff:op.out_choff + op.cout] = q(y)
         elif op.type == OP_CONV:
             x = bufs[op.in_buf][..., op.in_choff:op.in_choff + op.cin]
             if op.pro:

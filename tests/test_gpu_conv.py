@@ -39,3 +39,38 @@ def test_conv_case(name):
     # the naive path rounds the conv output to fp16 before its separate head kernel
     assert np.abs(got["naive"] - ref).max() <= (2e-3 if op.head else tol)
     m.close()
+
+
+@pytest.mark.parametrize("name", list(conv_cases.DENSE_CASES))
+def test_fused_dense_layer(name):
+    """dense_layer_kernel (1x1 -> bottleneck in smem -> 3x3) against fp32 math on the same fp16 operands."""
+    import torch
+    import emulator
+    from digipathai_b200.engine import TileModel
+    pr, x, B = conv_cases.build_dense_case(name)
+    op = pr.ops[0]
+    f = lambda a: torch.from_numpy(np.asarray(a, dtype=np.float32))
+    xs = f(x.astype(np.float32))[..., op.in_choff:op.in_choff + op.cin]
+    a = torch.relu(xs * f(op.pro_scale[:op.cin]) + f(op.pro_shift[:op.cin])).half().float()
+    t = torch.relu(a @ f(op.w[0].astype(np.float32)).T + f(op.epi_shift)).half().float()
+    w2 = f(op.w2.astype(np.float32))
+    ref = torch.zeros(*t.shape[:3], 32)
+    for e, (dy, dx, g) in enumerate(emulator.entries(3)):
+        ref += emulator._shift(t, dy, dx) @ w2[e].T
+    ref = ref.numpy()
+    m = TileModel(pr, device=0, max_batch=B)
+    for label, naive in (("naive", 1), ("tc", 0)):
+        m.set_option("naive_conv", naive)
+        m.write_buffer(0, x)
+        m.run_ops(B, 0, 1)
+        torch.cuda.synchronize()
+        full = m.read_buffer(0, B).astype(np.float32)
+        got = full[..., op.out_choff:op.out_choff + 32]
+        tol = float(np.abs(ref).max()) * 2.0 ** -9   # two fp16 rounding points (bottleneck, output)
+        assert np.abs(got - ref).max() <= tol, (name, label, np.abs(got - ref).max(), tol)
+        # everything outside the 32 new channels is untouched
+        keep = x.astype(np.float32).copy()
+        full[..., op.out_choff:op.out_choff + 32] = 0
+        keep[..., op.out_choff:op.out_choff + 32] = 0
+        assert np.array_equal(full, keep), (name, label, "wrote outside its channel range")
+    m.close()

@@ -99,5 +99,6 @@ def test_executed_macs_accounting(setup):
     from digipathai_b200.models.densenet import reference_macs_per_tile
     ref = reference_macs_per_tile(256)
     ex = setup["model"].executed_macs(1)
-    # sub-pixel rewrite removes 5/9 of the five up-conv layers; stem K is padded 147 -> 160; head is fused
-    assert 0.75 * ref < ex < 0.82 * ref, (ex, ref)
+    # sub-pixel rewrite removes 5/9 of the five up-conv layers (-21 %); the fused dense layers recompute the 1x1
+    # conv on their halo rows (2x on blocks 2-4, +6 % overall); the stem runs as a zero-padded 4x4 conv
+    assert 0.75 * ref < ex < 0.90 * ref, (ex, ref)
