@@ -558,39 +558,48 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       for (int c = 0; c < p.n_chunks; ++c) {
         mbar_wait(&a_full[sa], pa);
         const __half2 zero2 = __float2half2_rn(0.f);
-        for (int s = 0; s < p.sub; ++s) {
-          // Row t of sub-tile s: read all eight 16-byte chunks first, then transform, then write back -- the
-          // in-place stores may alias the loads as far as the compiler knows, so interleaving them would
-          // serialise every shared-memory round trip.  Logical chunk i sits at physical chunk i ^ (t & 7)
-          // (128B swizzle); all lanes touch the same 8 channels per step, so BN terms are broadcast loads.
-          uint8_t* row = a_base + sa * p.a_stage_bytes + s * kATileBytes + t * 128;
-          uint4 raw[8];
+        {
+          // Thread t owns logical 16-byte chunk i = t & 7 (8 channels) of rows (t >> 3) + 16 k of every sub-tile:
+          // its 16 BN terms stay in registers for the whole stage, so shared-memory traffic is the data itself
+          // (a quarter-warp covers one full 128-byte row: conflict-free under the 128B swizzle).  Loads of a
+          // batch are issued before its stores: the in-place stores may alias as far as the compiler knows.
+          const int i = t & 7;
+          const int ch = c * 64 + i * 8;
+          const float4 sc0 = *reinterpret_cast<const float4*>(s_pro_scale + ch);
+          const float4 sc1 = *reinterpret_cast<const float4*>(s_pro_scale + ch + 4);
+          const float4 sh0 = *reinterpret_cast<const float4*>(s_pro_shift + ch);
+          const float4 sh1 = *reinterpret_cast<const float4*>(s_pro_shift + ch + 4);
+          for (int s = 0; s < p.sub; ++s) {
+            uint8_t* tile = a_base + sa * p.a_stage_bytes + s * kATileBytes;
+            uint4 raw[8];
 #pragma unroll
-          for (int i = 0; i < 8; ++i) raw[i] = *reinterpret_cast<const uint4*>(row + ((i ^ (t & 7)) << 4));
+            for (int k = 0; k < 8; ++k) {
+              const int rr = (t >> 3) + 16 * k;
+              raw[k] = *reinterpret_cast<const uint4*>(tile + rr * 128 + ((i ^ (rr & 7)) << 4));
+            }
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const int ch = c * 64 + i * 8;
-            const float4 sc0 = *reinterpret_cast<const float4*>(s_pro_scale + ch);
-            const float4 sc1 = *reinterpret_cast<const float4*>(s_pro_scale + ch + 4);
-            const float4 sh0 = *reinterpret_cast<const float4*>(s_pro_shift + ch);
-            const float4 sh1 = *reinterpret_cast<const float4*>(s_pro_shift + ch + 4);
-            __half2* hv = reinterpret_cast<__half2*>(&raw[i]);
-            float2 x;
-            x = __half22float2(hv[0]);
-            hv[0] = __floats2half2_rn(fmaf(x.x, sc0.x, sh0.x), fmaf(x.y, sc0.y, sh0.y));
-            x = __half22float2(hv[1]);
-            hv[1] = __floats2half2_rn(fmaf(x.x, sc0.z, sh0.z), fmaf(x.y, sc0.w, sh0.w));
-            x = __half22float2(hv[2]);
-            hv[2] = __floats2half2_rn(fmaf(x.x, sc1.x, sh1.x), fmaf(x.y, sc1.y, sh1.y));
-            x = __half22float2(hv[3]);
-            hv[3] = __floats2half2_rn(fmaf(x.x, sc1.z, sh1.z), fmaf(x.y, sc1.w, sh1.w));
-            if (p.pro_relu) {
-              hv[0] = __hmax2(hv[0], zero2); hv[1] = __hmax2(hv[1], zero2);
-              hv[2] = __hmax2(hv[2], zero2); hv[3] = __hmax2(hv[3], zero2);
+            for (int k = 0; k < 8; ++k) {
+              __half2* hv = reinterpret_cast<__half2*>(&raw[k]);
+              float2 x;
+              x = __half22float2(hv[0]);
+              hv[0] = __floats2half2_rn(fmaf(x.x, sc0.x, sh0.x), fmaf(x.y, sc0.y, sh0.y));
+              x = __half22float2(hv[1]);
+              hv[1] = __floats2half2_rn(fmaf(x.x, sc0.z, sh0.z), fmaf(x.y, sc0.w, sh0.w));
+              x = __half22float2(hv[2]);
+              hv[2] = __floats2half2_rn(fmaf(x.x, sc1.x, sh1.x), fmaf(x.y, sc1.y, sh1.y));
+              x = __half22float2(hv[3]);
+              hv[3] = __floats2half2_rn(fmaf(x.x, sc1.z, sh1.z), fmaf(x.y, sc1.w, sh1.w));
+              if (p.pro_relu) {
+                hv[0] = __hmax2(hv[0], zero2); hv[1] = __hmax2(hv[1], zero2);
+                hv[2] = __hmax2(hv[2], zero2); hv[3] = __hmax2(hv[3], zero2);
+              }
+            }
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+              const int rr = (t >> 3) + 16 * k;
+              *reinterpret_cast<uint4*>(tile + rr * 128 + ((i ^ (rr & 7)) << 4)) = raw[k];
             }
           }
-#pragma unroll
-          for (int i = 0; i < 8; ++i) *reinterpret_cast<uint4*>(row + ((i ^ (t & 7)) << 4)) = raw[i];
         }
         fence_proxy_async_smem();
         mbar_arrive(&a_ready[sa]);

@@ -59,6 +59,24 @@ __host__ __device__ inline DenseLayerSmem dense_layer_smem(const DenseLayerParam
   return L;
 }
 
+struct DlTrace {
+  unsigned long long* base = nullptr;
+  unsigned n = 0;
+};
+__device__ __forceinline__ DlTrace dl_trace_open(unsigned long long* trace, unsigned role) {
+  DlTrace c;
+  if (trace && blockIdx.x == 0) c.base = trace + 8 + 2000 * role;
+  return c;
+}
+__device__ __forceinline__ void dl_trace_ev(DlTrace& c, unsigned ev, unsigned item) {
+  if (c.base && c.n < 2000)
+    c.base[c.n++] = (static_cast<unsigned long long>(ev) << 48) | (static_cast<unsigned long long>(item & 0xFFFF) << 32) |
+                    (static_cast<unsigned long long>(clock64()) & 0xFFFFFFFFull);
+}
+__device__ __forceinline__ void dl_trace_close(unsigned long long* trace, const DlTrace& c, unsigned role) {
+  if (c.base) trace[role] = c.n;
+}
+
 __global__ void __launch_bounds__(512, 1)
 dense_layer_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w1,
                    const __grid_constant__ CUtensorMap map_w2, const __grid_constant__ DenseLayerParams p) {
@@ -88,6 +106,7 @@ dense_layer_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
   float* s_mid_shift = reinterpret_cast<float*>(smem + L.mid_off);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid == 0 && p.trace && blockIdx.x == 0) p.trace[8 + 2000 * 4 + 1] = (2ull << 48) | (clock64() & 0xFFFFFFFFull);
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&map_x);
@@ -133,6 +152,7 @@ dense_layer_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
   pdl_launch_dependents();
   pdl_wait();
   const uint32_t tmem_base = *tmem_slot;
+  if (tid == 0 && p.trace && blockIdx.x == 0) { p.trace[8 + 2000 * 4] = clock64() & 0xFFFFFFFFull; p.trace[4] = 2; }
   const uint32_t acc1_col = tmem_base;         // 2 M-blocks x 128 columns
   const uint32_t acc2_col = tmem_base + 256;   // 32 columns
 
@@ -147,6 +167,7 @@ dense_layer_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
   if (warp == 0) {
     // ------------------------------------------------------------------ producer: activation halo chunks
     if (elect_one()) {
+      DlTrace tc = dl_trace_open(p.trace, 0);
       uint32_t sa = 0, pa = 0;
       for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
         int n0, h0, w0;
@@ -155,9 +176,11 @@ dense_layer_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
           mbar_wait(&a_empty[sa], pa ^ 1);
           mbar_expect_tx(&a_full[sa], kDlRows * 128);
           tma_load_4d(&map_x, &a_full[sa], a_base + sa * kDlAStage, c * 64, w0 - 1, h0 - 1, n0);
+          dl_trace_ev(tc, 1, item);
           if (++sa == p.a_stages) { sa = 0; pa ^= 1; }
         }
       }
+      dl_trace_close(p.trace, tc, 0);
     }
   } else if (warp == 3) {
     // ------------------------------------------------------------------ producer: W1 chunks, then W2 tap groups
@@ -182,6 +205,7 @@ dense_layer_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
     if (elect_one()) {
+      DlTrace tc = dl_trace_open(p.trace, 1);
       const uint32_t idesc1 = make_idesc_f16(128), idesc2 = make_idesc_f16(32);
       const uint64_t hi_dense = static_cast<uint64_t>(sw128_desc_hi(1024)) << 32;
       const uint64_t hi_halo = static_cast<uint64_t>(sw128_desc_hi(kDlHaloW * 128)) << 32;
@@ -197,8 +221,10 @@ dense_layer_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
           int ks = (p.C - c * 64 + 15) >> 4;
           ks = ks > 4 ? 4 : ks;
           mbar_wait(&a_ready[sa], pa);
+          dl_trace_ev(tc, 1, item);
           mbar_wait(&b_full[sb], pb);
           tc_fence_after();
+          dl_trace_ev(tc, 2, item);
           const uint64_t a_desc = a_desc0 + sa * (kDlAStage >> 4);
           const uint64_t b_desc = b_desc0 + sb * (kDlBStage >> 4);
           const uint32_t acc = (c > 0) ? 1u : 0u;
@@ -217,10 +243,12 @@ dense_layer_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
           if (++sb == p.b_stages) { sb = 0; pb ^= 1; }
         }
         umma_commit(acc1_full);
+        dl_trace_ev(tc, 3, item);
         // ---- phase 2: 3x3 conv over the bottleneck tile in shared memory
         mbar_wait(t_ready, ph);
         mbar_wait(acc2_empty, ph ^ 1);
         tc_fence_after();
+        dl_trace_ev(tc, 4, item);
         for (int c = 0; c < 2; ++c) {
           const uint64_t t_desc = t_desc0 + c * (kDlAStage >> 4);
           for (int g = 0; g < 9 / kDlW2Group; ++g) {
@@ -239,13 +267,17 @@ dense_layer_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
         }
         umma_commit(t_empty);
         umma_commit(acc2_full);
+        dl_trace_ev(tc, 5, item);
       }
+      dl_trace_close(p.trace, tc, 1);
     }
   } else if (warp >= 4 && warp < 8) {
     // ------------------------------------------------------------------ epilogue warps: mid + final
     const int q = warp & 3;
     const int r = q * 32 + lane;
     uint8_t* stage = smem + L.stage_off + q * kEpiStageBytes;
+    DlTrace tc;
+    if (r == 0) tc = dl_trace_open(p.trace, 2);
     uint32_t ph = 0;
     for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ph ^= 1) {
       int n0, h0, w0;
@@ -254,6 +286,7 @@ dense_layer_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
       mbar_wait(acc1_full, ph);
       mbar_wait(t_empty, ph ^ 1);   // previous item's 3x3 MMAs no longer read T
       tc_fence_after();
+      dl_trace_ev(tc, 0, item);
 #pragma unroll 1
       for (int mb = 0; mb < 2; ++mb) {
         const int prow = mb * 128 + r;                 // halo pixel index
@@ -292,9 +325,11 @@ dense_layer_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
       fence_proxy_async_smem();
       mbar_arrive(acc1_empty);
       mbar_arrive(t_ready);
+      dl_trace_ev(tc, 2, item);
       // ---- final: acc2 -> fp16 -> 32 new channels of the concat buffer
       mbar_wait(acc2_full, ph);
       tc_fence_after();
+      dl_trace_ev(tc, 3, item);
       {
         const int w = w0 + (r & 7), h = h0 + (r >> 3);
         const bool valid = (n0 < p.n_img) && (h < p.H) && (w < p.W);
@@ -331,28 +366,42 @@ dense_layer_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
       }
       tc_fence_before();
       mbar_arrive(acc2_empty);
+      dl_trace_ev(tc, 1, item);
     }
+    if (r == 0) dl_trace_close(p.trace, tc, 2);
   } else if (warp >= 8) {
     // ------------------------------------------------------------------ pre-activation BN + ReLU on the halo rows
     const int t = tid - 256;
     const __half2 zero2 = __float2half2_rn(0.f);
+    DlTrace tc;
+    if (t == 0) tc = dl_trace_open(p.trace, 3);
     uint32_t sa = 0, pa = 0;
     for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
       for (int c = 0; c < p.n_chunks; ++c) {
         mbar_wait(&a_full[sa], pa);
-        for (int rr = t; rr < kDlRows; rr += 256) {   // 8 warps: one halo row per thread
-          uint8_t* row = a_base + sa * kDlAStage + rr * 128;
-          uint4 raw[8];
+        dl_trace_ev(tc, 1, item);
+        {
+          // Thread t owns logical 16-byte chunk i = t & 7 (8 channels) of rows (t >> 3) + 32 k: its 16 BN terms
+          // stay in registers for the whole stage, so shared-memory traffic is the data itself (a quarter-warp
+          // covers one full 128-byte row: conflict-free under the 128B swizzle) instead of 32 broadcast
+          // parameter loads per row.
+          const int i = t & 7;
+          const int ch = c * 64 + i * 8;
+          const float4 sc0 = *reinterpret_cast<const float4*>(s_pro_scale + ch);
+          const float4 sc1 = *reinterpret_cast<const float4*>(s_pro_scale + ch + 4);
+          const float4 sh0 = *reinterpret_cast<const float4*>(s_pro_shift + ch);
+          const float4 sh1 = *reinterpret_cast<const float4*>(s_pro_shift + ch + 4);
+          uint8_t* stage_base = a_base + sa * kDlAStage;
+          constexpr int kIter = (kDlRows + 31) / 32;   // 6
+          uint4 raw[kIter];
 #pragma unroll
-          for (int i = 0; i < 8; ++i) raw[i] = *reinterpret_cast<const uint4*>(row + ((i ^ (rr & 7)) << 4));
+          for (int k = 0; k < kIter; ++k) {
+            const int rr = (t >> 3) + 32 * k;
+            if (rr < kDlRows) raw[k] = *reinterpret_cast<const uint4*>(stage_base + rr * 128 + ((i ^ (rr & 7)) << 4));
+          }
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const int ch = c * 64 + i * 8;
-            const float4 sc0 = *reinterpret_cast<const float4*>(s_pro_scale + ch);
-            const float4 sc1 = *reinterpret_cast<const float4*>(s_pro_scale + ch + 4);
-            const float4 sh0 = *reinterpret_cast<const float4*>(s_pro_shift + ch);
-            const float4 sh1 = *reinterpret_cast<const float4*>(s_pro_shift + ch + 4);
-            __half2* hv = reinterpret_cast<__half2*>(&raw[i]);
+          for (int k = 0; k < kIter; ++k) {
+            __half2* hv = reinterpret_cast<__half2*>(&raw[k]);
             float2 x;
             x = __half22float2(hv[0]);
             hv[0] = __hmax2(__floats2half2_rn(fmaf(x.x, sc0.x, sh0.x), fmaf(x.y, sc0.y, sh0.y)), zero2);
@@ -364,13 +413,18 @@ dense_layer_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
             hv[3] = __hmax2(__floats2half2_rn(fmaf(x.x, sc1.z, sh1.z), fmaf(x.y, sc1.w, sh1.w)), zero2);
           }
 #pragma unroll
-          for (int i = 0; i < 8; ++i) *reinterpret_cast<uint4*>(row + ((i ^ (rr & 7)) << 4)) = raw[i];
+          for (int k = 0; k < kIter; ++k) {
+            const int rr = (t >> 3) + 32 * k;
+            if (rr < kDlRows) *reinterpret_cast<uint4*>(stage_base + rr * 128 + ((i ^ (rr & 7)) << 4)) = raw[k];
+          }
         }
         fence_proxy_async_smem();
         mbar_arrive(&a_ready[sa]);
+        dl_trace_ev(tc, 0, item);
         if (++sa == p.a_stages) { sa = 0; pa ^= 1; }
       }
     }
+    if (t == 0) dl_trace_close(p.trace, tc, 3);
   }
 
   tc_fence_before();
@@ -378,6 +432,7 @@ dense_layer_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
   if (warp == 2) {
     tc_fence_after();
     tmem_dealloc(tmem_base, kTmemCols);
+    if (lane == 0 && p.trace && blockIdx.x == 0) { p.trace[8 + 2000 * 4 + 2] = (1ull << 48) | (clock64() & 0xFFFFFFFFull); p.trace[4] = 3; }
   }
 }
 

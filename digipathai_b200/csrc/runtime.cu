@@ -623,6 +623,7 @@ int run_op(dp_model* m, SubPlan* sp, int i, cudaStream_t st) {
         return 0;
       }
       dp::DenseLayerParams dl = L.dl;
+      dl.trace = (m->trace_op == i) ? m->trace_dev : nullptr;
       cudaLaunchConfig_t cfg;
       memset(&cfg, 0, sizeof cfg);
       cfg.gridDim = dim3(L.grid);

@@ -14,6 +14,9 @@ for _ in range(2):
     m.forward_tile_batch(tiles)
 torch.cuda.synchronize()
 ROLE = {0: "prod", 1: "mma", 2: "epi", 3: "xform", 9: "setup"}
+EV_DL = {(0, 1): "A_issued", (1, 1): "A_ready", (1, 2): "B_ready", (1, 3): "ph1_issued", (1, 4): "ph2_start",
+         (1, 5): "ph2_issued", (2, 0): "mid_start", (2, 2): "mid_done", (2, 3): "final_start", (2, 1): "final_done",
+         (3, 1): "xf_start", (3, 0): "xf_done", (9, 0): "setup_done", (9, 2): "kernel_entry", (9, 1): "kernel_end"}
 EV = {(0, 1): "A_issued", (0, 2): "B_issued", (1, 0): "acc_free", (1, 1): "A_ready", (1, 2): "B_ready",
       (1, 3): "item_issued", (2, 0): "acc_full", (2, 1): "epi_done", (3, 0): "xform_done", (9, 0): "setup_done", (9, 2): "kernel_entry", (9, 1): "kernel_end"}
 for op in ops:
@@ -27,13 +30,14 @@ for op in ops:
     t0 = min(t for _, _, _, t in tr)
     tr = sorted(tr, key=lambda e: (e[3] - t0) & 0xFFFFFFFF)
     print(f"=== op {op} {prog.ops[op].name}: {len(tr)} events")
+    evmap = EV_DL if prog.ops[op].type == 6 else EV
     items = sorted({it for r, e, it, t in tr if r != 9})
     show = set(items[:3] + items[-2:])
     last = {}
     for r, e, it, t in tr:
         dt = (t - t0) & 0xFFFFFFFF
         if r == 9 or it in show:
-            print(f"  {dt:9d} clk  {ROLE.get(r, r):6s} {EV.get((r, e), e):12s} item {it}")
+            print(f"  {dt:9d} clk  {ROLE.get(r, r):6s} {evmap.get((r, e), e):12s} item {it}")
     # per-item period on the mma role
     iss = [((t - t0) & 0xFFFFFFFF) for r, e, it, t in tr if (r, e) == (1, 3)]
     if len(iss) > 2:
