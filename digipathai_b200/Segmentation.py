@@ -25,7 +25,7 @@ from os.path import expanduser
 import numpy as np
 
 from . import tta as _tta
-from .slide import level0_xy_raster, open_slide
+from .slide import open_slide, upload_xy_raster
 from .tissue import TileGrid
 
 home = expanduser("~")
@@ -92,7 +92,7 @@ def get_prediction(wsi_path, mask_path=None, label_path=None, batch_size=64, mod
         sel = coords_all[b_lo * batch_size:b_hi * batch_size, 0]
         x_lo, x_hi = int(sel.min()), int(sel.max()) + P
     with torch.cuda.device(dev):
-        raster = torch.from_numpy(level0_xy_raster(slide)[x_lo:x_hi]).to(dev)      # uint8 [x, y, c] stripe in HBM
+        raster = upload_xy_raster(slide, x_lo, x_hi, dev)                          # uint8 [x, y, c] stripe in HBM
         mean = torch.zeros((x_hi - x_lo, H), dtype=torch.float32, device=dev)
         var = torch.zeros_like(mean)
         count = torch.zeros((x_hi - x_lo, H), dtype=torch.uint8, device=dev)

@@ -58,6 +58,7 @@ struct ConvParams {
   int a_stage_bytes, b_stage_bytes, a_stages, b_stages, acc_stages, a_tx_bytes;
   int b_group;              // tap entries carried by one B stage (TMA box depth)
   int halo_top;             // MODE_H: rows of halo above the region (1 for 3x3 / up2, 2 for the 4x4 stem)
+  int epi_direct;           // 1: epilogue stores 32-byte vectors straight from registers (no smem staging)
   int epi_mode, relu;
   int out_ctot, out_choff;  // output NHWC buffer: channel stride and channel offset (elements)
   int desc_base_mode;       // 0: descriptor base_offset field = 0; 1: (addr >> 7) & 7
@@ -368,7 +369,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 for (uint32_t s = 0; s < sub; ++s, a_desc += a_sub_u, d += n_tile)
                   umma_f16_ss_k4(d, a_desc, b_desc, idesc, flag0);
               }
-            } else {  // channel tail (Cin % 64 != 0): 1-3 K-steps
+            } else if (ks == 2) {  // 32-channel tail chunk
+              for (uint32_t j = 0; j < bgroup; ++j, ++e, b_desc += b_ent_u) {
+                const uint32_t flag0 = ((first_mask >> e) & 1u) ^ 1u;
+                uint64_t a_desc = a_stage_desc + p.tap_a[e];
+                uint32_t d = d_stage + p.tap_d[e];
+                for (uint32_t s = 0; s < sub; ++s, a_desc += a_sub_u, d += n_tile)
+                  umma_f16_ss_k2(d, a_desc, b_desc, idesc, flag0);
+              }
+            } else {  // other channel tails (Cin % 64 in {16, 48})
               for (uint32_t j = 0; j < bgroup; ++j, ++e, b_desc += b_ent_u) {
                 const uint32_t flag0 = ((first_mask >> e) & 1u) ^ 1u;
                 uint64_t a_desc = a_stage_desc + p.tap_a[e];
@@ -471,6 +480,28 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                   head_acc = fmaf(f[4 * i4 + 2], hw.z, head_acc);
                   head_acc = fmaf(f[4 * i4 + 3], hw.w, head_acc);
                 }
+              }
+            }
+          } else if (p.epi_direct) {
+            // 32 columns per step: TMEM -> registers -> BN shift/ReLU -> fp16 -> two 256-bit stores per thread
+            // (each a full 32-byte sector of this pixel's channel run); no shared-memory round trip.
+            for (int cc = 0; cc < p.n_tile; cc += 32) {
+              uint32_t v[2][16];
+              tmem_ld16(taddr + cc, v[0]);
+              tmem_ld16(taddr + cc + 16, v[1]);
+              tmem_ld_wait();
+#pragma unroll
+              for (int hsel = 0; hsel < 2; ++hsel) {
+                const int cb = ch0 + cc + 16 * hsel;
+                float f[16];
+                epi_affine16(v[hsel], s_epi_scale + cb, s_epi_shift + cb, has_scale, p.relu != 0, f);
+                uint32_t pk[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                  __half2 h2 = __floats2half2_rn(f[2 * i], f[2 * i + 1]);
+                  pk[i] = *reinterpret_cast<uint32_t*>(&h2);
+                }
+                if (valid) st_global_v8(orow + cc + 16 * hsel, pk);
               }
             }
           } else {

@@ -74,6 +74,13 @@ __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;"
 // launch_dependents: lets the next kernel in the stream start its prologue on SMs this grid has vacated.
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
+// 256-bit global store (sm_100+): one full 32-byte sector per thread per instruction.
+__device__ __forceinline__ void st_global_v8(void* ptr, const uint32_t (&v)[8]) {
+  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(ptr), "r"(v[0]), "r"(v[1]), "r"(v[2]),
+               "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+               : "memory");
+}
+
 // ---------------------------------------------------------------- TMA
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* m) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");
@@ -167,6 +174,23 @@ __device__ __forceinline__ void umma_f16_ss_k4(uint32_t d_tmem, uint64_t a_desc,
       "tcgen05.mma.cta_group::1.kind::f16 [%0], a1, b1, %3, q;\n\t"
       "tcgen05.mma.cta_group::1.kind::f16 [%0], a2, b2, %3, q;\n\t"
       "tcgen05.mma.cta_group::1.kind::f16 [%0], a3, b3, %3, q;\n\t"
+      "}\n"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// Two K-steps (a 32-channel tail chunk).
+__device__ __forceinline__ void umma_f16_ss_k2(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                               uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p, q;\n\t"
+      ".reg .b64 a1, b1;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "setp.eq.b32 q, 0, 0;\n\t"
+      "add.u64 a1, %1, 2;\n\t"
+      "add.u64 b1, %2, 2;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], a1, b1, %3, q;\n\t"
       "}\n"
       ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");

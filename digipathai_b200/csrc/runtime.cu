@@ -147,7 +147,7 @@ struct dp_model {
   __half* scratch_head = nullptr;  // naive path: output of the head-fused conv
   uint64_t device_bytes = 0;
   int naive_conv = 0, desc_base_mode = 0, halo_pad8 = 0, profile = 0;
-  int use_graph = 1, split = 1, use_pdl = 1;
+  int use_graph = 1, split = 1, use_pdl = 1, epi_direct = 1;
   unsigned long long* trace_dev = nullptr;  // debug timeline buffer (option "trace_op")
   int trace_op = -1;
   dp::PassDesc* pass_dev = nullptr;          // per-call arguments read by the stem and head kernels
@@ -581,6 +581,7 @@ int run_op(dp_model* m, SubPlan* sp, int i, cudaStream_t st) {
       }
       dp::ConvParams cp = L.cp;
       cp.desc_base_mode = m->desc_base_mode;
+      cp.epi_direct = m->epi_direct && ((cp.out_choff % 16) == 0) && ((cp.out_ctot % 16) == 0);
       cp.trace = (m->trace_op == i) ? m->trace_dev : nullptr;
       // Programmatic dependent launch: the kernel's setup (barrier init, TMEM alloc, BN constants -> smem)
       // runs before its griddepcontrol.wait and so overlaps the tail of the preceding kernel in the stream.
@@ -787,6 +788,14 @@ int dp_model_set_option(dp_model* m, const char* key, int value) {
   else if (!strcmp(key, "desc_base_mode")) m->desc_base_mode = value;
   else if (!strcmp(key, "profile")) m->profile = value;
   else if (!strcmp(key, "use_graph")) m->use_graph = value;
+  else if (!strcmp(key, "epi_direct")) {
+    std::lock_guard<std::mutex> lk(m->mu);
+    m->epi_direct = value;
+    for (auto& kv : m->plans) {
+      if (kv.second.exec) { cudaGraphExecDestroy(kv.second.exec); kv.second.exec = nullptr; }
+      if (kv.second.graph) { cudaGraphDestroy(kv.second.graph); kv.second.graph = nullptr; }
+    }
+  }
   else if (!strcmp(key, "use_pdl")) {
     std::lock_guard<std::mutex> lk(m->mu);
     m->use_pdl = value;

@@ -85,6 +85,27 @@ def level0_xy_raster(slide) -> np.ndarray:
     return np.ascontiguousarray(np.transpose(arr, (1, 0, 2)))
 
 
+def upload_xy_raster(slide, x_lo: int, x_hi: int, device, rows_per_chunk: int = 4096):
+    """Level-0 stripe ``[x_lo, x_hi)`` as a CUDA ``uint8 [x, y, c]`` tensor (the layout the stem gather reads).
+
+    The ``[y, x, c] -> [x, y, c]`` transposition the reference does per tile on the host
+    (dataloader.py:357-358) happens once, on the device, while the raster is uploaded in row chunks.
+    """
+    import torch
+    W, H = slide.level_dimensions[0]
+    out = torch.empty((x_hi - x_lo, H, 3), dtype=torch.uint8, device=device)
+    for y0 in range(0, H, rows_per_chunk):
+        y1 = min(H, y0 + rows_per_chunk)
+        if isinstance(slide, ArraySlide):
+            blk = slide.raster[y0:y1, x_lo:x_hi]
+        else:
+            img = slide.read_region((x_lo, y0), 0, (x_hi - x_lo, y1 - y0))
+            blk = np.asarray(img.convert("RGB") if hasattr(img, "convert") else img)
+        t = torch.from_numpy(np.ascontiguousarray(blk)).to(device, non_blocking=False)
+        out[:, y0:y1] = t.permute(1, 0, 2)
+    return out
+
+
 def synthetic_slide(width: int, height: int, seed: int = 0, n_levels: int = 1, n_blobs: int = 4) -> ArraySlide:
     """Synthetic H&E-like slide: white background 240+-3, elliptical 'tissue' (170, 90, 160) +- 20 covering ~50 %.
 

@@ -47,18 +47,48 @@ def saturation(img_rgb_u8: np.ndarray) -> np.ndarray:
     return s
 
 
+def _otsu_from_hist(hist: np.ndarray, centers: np.ndarray) -> float:
+    hist = hist.astype(np.float64)
+    w1 = np.cumsum(hist)
+    w2 = np.cumsum(hist[::-1])[::-1]
+    with np.errstate(divide="ignore", invalid="ignore"):
+        m1 = np.cumsum(hist * centers) / w1
+        m2 = (np.cumsum((hist * centers)[::-1]) / w2[::-1])[::-1]
+    var12 = w1[:-1] * w2[1:] * (m1[:-1] - m2[1:]) ** 2
+    return float(centers[:-1][int(np.argmax(var12))])
+
+
 def tissue_mask(slide, level: int, rgb_min: int = 50) -> np.ndarray:
-    """bool [x, y] mask at pyramid ``level`` (utils.py:336-354)."""
+    """bool [x, y] mask at pyramid ``level`` (utils.py:336-354).
+
+    Same result as the literal float64 evaluation (``saturation`` + ``threshold_otsu`` above, asserted in
+    tests/test_host_pipeline.py), computed without float64 images: for uint8 RGB the saturation
+    ``(max-min)/max`` takes one of 65 536 values indexed by ``(max, max-min)``, so its 256-bin histogram, the
+    Otsu threshold and the ``S > t`` mask all follow from one joint histogram and a lookup table.
+    """
     region = slide.read_region((0, 0), level, slide.level_dimensions[level])
     rgb = np.asarray(region.convert("RGB") if hasattr(region, "convert") else region)
-    rgb = np.transpose(rgb, (1, 0, 2))
     bg = np.ones(rgb.shape[:2], dtype=bool)
     for c in range(3):
         bg &= rgb[:, :, c] > threshold_otsu(rgb[:, :, c])
-    sat = saturation(rgb)
-    tissue_s = sat > threshold_otsu(sat)
+    v = rgb.max(-1)
+    delta = v - rgb.min(-1)
+    idx = v.astype(np.uint16) * 256 + delta
+    joint = np.bincount(idx.ravel(), minlength=65536)
+    vv, dd = np.divmod(np.arange(65536), 256)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        lut = (dd / 255.0) / (vv / 255.0)        # identical float64 arithmetic to saturation()
+    lut[dd == 0] = 0.0
+    lut[np.isnan(lut)] = 0.0
+    present = joint > 0
+    lo, hi = lut[present].min(), lut[present].max()
+    if lo == hi:
+        raise ValueError("threshold_otsu is expected to work with images having more than one color")
+    hist, edges = np.histogram(lut[present], bins=256, range=(lo, hi), weights=joint[present])
+    thr = _otsu_from_hist(hist, (edges[:-1] + edges[1:]) / 2.0)
+    tissue_s = (lut > thr)[idx]
     above = (rgb[:, :, 0] > rgb_min) & (rgb[:, :, 1] > rgb_min) & (rgb[:, :, 2] > rgb_min)
-    return tissue_s & ~bg & above
+    return np.ascontiguousarray((tissue_s & ~bg & above).T)
 
 
 def morpho_process(mask_u8: np.ndarray, level: int) -> np.ndarray:

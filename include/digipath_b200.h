@@ -107,6 +107,7 @@ uint64_t dp_kernel_launch_count(void);
  *          "profile" (0/1: record CUDA events around every op for dp_model_op_times; implies direct launches),
  *          "use_graph" (0/1, default 1: replay dp_forward_tiles as one captured CUDA graph),
  *          "use_pdl" (0/1, default 1: conv kernels use programmatic dependent launch),
+ *          "epi_direct" (0/1, default 1: epilogue writes 256-bit vectors from registers instead of staging in smem),
  *          "split" (default 1: number of sub-batches captured as parallel graph branches). */
 int dp_model_set_option(dp_model* m, const char* key, int value);
 
