@@ -23,8 +23,8 @@
 
 namespace dp {
 
-constexpr int kDlHaloW = 10, kDlHaloH = 18, kDlRows = kDlHaloW * kDlHaloH;  // 180 halo pixels
-constexpr int kDlAStage = 256 * 128;   // 2 M-blocks of 128 rows x 128 B (rows 180..255 unused)
+constexpr int kDlHaloW = 10;           // 8-pixel-wide regions + 1-pixel halo each side
+constexpr int kDlAStage = 256 * 128;   // up to 2 M-blocks of 128 rows x 128 B (rows beyond the halo box unused)
 constexpr int kDlBStage = 128 * 128;   // W1 chunk [128 x 64]; W2 groups (3 taps x [32 x 64] = 12 KB) fit too
 constexpr int kDlTBytes = 2 * kDlAStage;  // bottleneck operand: 2 chunks x 256 rows x 128 B
 constexpr int kDlW2Group = 3;          // taps per W2 stage
@@ -33,6 +33,7 @@ struct DenseLayerParams {
   int n_img, H, W, C;        // map size, input channels of this layer
   int n_chunks;              // ceil(C / 64)
   int tiles_w, tiles_h, n_items;
+  int rh;                    // region height: 16 (180 halo rows, 2 M-blocks) or 8 (100 halo rows, 1 M-block)
   int a_stages, b_stages;
   int out_ctot, out_choff;   // concat buffer channel stride, offset of the 32 new channels
   const float* pro_scale;    // BN1 [n_chunks * 64]
@@ -77,9 +78,14 @@ __device__ __forceinline__ void dl_trace_close(unsigned long long* trace, const 
   if (c.base) trace[role] = c.n;
 }
 
+// RH = region height in pixels.  RH = 8 halves the halo box (100 rows, one 128-row M-block in phase 1) and is used
+// where 16-row regions would leave SMs idle (16x16 and 8x8 maps at batch 32); phase 2 still issues M = 128 MMAs,
+// whose upper 64 rows are don't-care.
+template <int RH>
 __global__ void __launch_bounds__(512, 1)
 dense_layer_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w1,
                    const __grid_constant__ CUtensorMap map_w2, const __grid_constant__ DenseLayerParams p) {
+  constexpr int kDlHaloH = RH + 2, kDlRows = kDlHaloW * kDlHaloH, kMBlk = (kDlRows + 127) / 128;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
@@ -160,7 +166,7 @@ dense_layer_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
     const int tw = item % p.tiles_w;
     const int r = item / p.tiles_w;
     w0 = tw * 8;
-    h0 = (r % p.tiles_h) * 16;
+    h0 = (r % p.tiles_h) * RH;
     n0 = r / p.tiles_h;
   };
 
@@ -230,11 +236,12 @@ dense_layer_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
           const uint32_t acc = (c > 0) ? 1u : 0u;
           if (ks == 4) {
             umma_f16_ss_k4(acc1_col, a_desc, b_desc, idesc1, acc);
-            umma_f16_ss_k4(acc1_col + 128, a_desc + (kATileBytes >> 4), b_desc, idesc1, acc);
+            if (kMBlk > 1) umma_f16_ss_k4(acc1_col + 128, a_desc + (kATileBytes >> 4), b_desc, idesc1, acc);
           } else {
             for (int k = 0; k < ks; ++k) {
               umma_f16_ss(acc1_col, a_desc + 2 * k, b_desc + 2 * k, idesc1, k ? 1u : acc);
-              umma_f16_ss(acc1_col + 128, a_desc + (kATileBytes >> 4) + 2 * k, b_desc + 2 * k, idesc1, k ? 1u : acc);
+              if (kMBlk > 1)
+                umma_f16_ss(acc1_col + 128, a_desc + (kATileBytes >> 4) + 2 * k, b_desc + 2 * k, idesc1, k ? 1u : acc);
             }
           }
           umma_commit(&a_empty[sa]);
@@ -288,7 +295,7 @@ dense_layer_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
       tc_fence_after();
       dl_trace_ev(tc, 0, item);
 #pragma unroll 1
-      for (int mb = 0; mb < 2; ++mb) {
+      for (int mb = 0; mb < kMBlk; ++mb) {
         const int prow = mb * 128 + r;                 // halo pixel index
         const int hh = prow / kDlHaloW, ww = prow - hh * kDlHaloW;
         const int ih = h0 - 1 + hh, iw = w0 - 1 + ww;
@@ -332,7 +339,7 @@ dense_layer_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
       dl_trace_ev(tc, 3, item);
       {
         const int w = w0 + (r & 7), h = h0 + (r >> 3);
-        const bool valid = (n0 < p.n_img) && (h < p.H) && (w < p.W);
+        const bool valid = (n0 < p.n_img) && ((r >> 3) < RH) && (h < p.H) && (w < p.W);
         const long long opix = (static_cast<long long>(n0) * p.H + h) * p.W + w;
         const unsigned long long my_row = reinterpret_cast<unsigned long long>(p.out + opix * p.out_ctot + p.out_choff);
         uint32_t v[2][16];

@@ -396,9 +396,7 @@ int plan_dense_layer(dp_model* m, const BlobOp& op, int img0, int B, Launch& L) 
   using namespace dp;
   const BlobBuf& ib = m->bufs[op.in_buf];
   const int H = ib.H, W = ib.W;
-  // maps lower than one 16-row region (8x8) run as a single region whose lower rows are out of bounds:
-  // TMA zero-fills them, the mid-epilogue keeps them zero and the final epilogue never stores them
-  if ((H % 16 && H != 8) || W % 8) return fail("dense layer: map %dx%d needs H %% 16 == 0 (or H == 8) and W %% 8 == 0", H, W);
+  if (H % 8 || W % 8) return fail("dense layer: map %dx%d needs H %% 8 == 0 and W %% 8 == 0", H, W);
   if (op.cout != 32 || op.cin % 8) return fail("dense layer: growth must be 32 and Cin a multiple of 8");
   const int mid_buf = op.rsv[0];
   if (mid_buf < 0 || mid_buf >= (int)m->bufs.size() || m->bufs[mid_buf].C != 128 || m->bufs[mid_buf].H != H)
@@ -434,7 +432,9 @@ int plan_dense_layer(dp_model* m, const BlobOp& op, int img0, int B, Launch& L) 
   memset(&p, 0, sizeof p);
   p.n_img = B; p.H = H; p.W = W; p.C = op.cin;
   p.n_chunks = (op.cin + 63) / 64;
-  p.tiles_w = W / 8; p.tiles_h = (H + 15) / 16;
+  p.rh = 16;
+  if (H % 16 || (long long)B * (W / 8) * (H / 16) < m->num_sms) p.rh = 8;   // more, smaller regions when SMs would idle
+  p.tiles_w = W / 8; p.tiles_h = H / p.rh;
   p.n_items = B * p.tiles_w * p.tiles_h;
   p.out_ctot = ib.C; p.out_choff = op.out_choff;
   p.pro_scale = a.pro_scale; p.pro_shift = a.pro_shift; p.mid_shift = a.epi_shift;
@@ -455,13 +455,13 @@ int plan_dense_layer(dp_model* m, const BlobOp& op, int img0, int B, Launch& L) 
       ksteps += ks > 4 ? 4 : ks;
     }
     // executed: 1x1 on 256 rows per 128-pixel region (halo recompute + padding rows), 3x3 on 128 rows
-    L.macs = (uint64_t)p.n_items * (256ull * 128 * ksteps * 16 + 128ull * 32 * 9 * 128);
+    L.macs = (uint64_t)p.n_items * ((p.rh == 16 ? 256ull : 128ull) * 128 * ksteps * 16 + 128ull * 32 * 9 * 128);
   }
   {
     uint64_t dims[4] = {(uint64_t)op.cin, (uint64_t)W, (uint64_t)H, (uint64_t)B};
     const uint64_t cs = (uint64_t)ib.C * 2;
     uint64_t str[3] = {cs, cs * W, cs * W * H};
-    uint32_t box[4] = {64, (uint32_t)kDlHaloW, (uint32_t)kDlHaloH, 1};
+    uint32_t box[4] = {64, (uint32_t)kDlHaloW, (uint32_t)(p.rh + 2), 1};
     if (make_map(&L.map_a, buf_at(op.in_buf) + op.in_choff, 4, dims, str, box)) return 1;
   }
   {
@@ -636,7 +636,8 @@ int run_op(dp_model* m, SubPlan* sp, int i, cudaStream_t st) {
       attr[0].val.programmaticStreamSerializationAllowed = 1;
       cfg.attrs = attr;
       cfg.numAttrs = m->use_pdl ? 1 : 0;
-      cudaError_t le = cudaLaunchKernelEx(&cfg, dp::dense_layer_kernel, L.map_a, L.map_b, L.map_w2, dl);
+      cudaError_t le = (dl.rh == 16) ? cudaLaunchKernelEx(&cfg, dp::dense_layer_kernel<16>, L.map_a, L.map_b, L.map_w2, dl)
+                                     : cudaLaunchKernelEx(&cfg, dp::dense_layer_kernel<8>, L.map_a, L.map_b, L.map_w2, dl);
       if (le != cudaSuccess) return fail("dense layer launch failed: %s", cudaGetErrorString(le));
       LAUNCH_OK();
       return 0;
@@ -737,8 +738,9 @@ int dp_model_create(const void* blob, size_t nbytes, int device, int max_batch, 
     cudaError_t e2 = cudaFuncSetAttribute(dp::conv_tc_kernel<dp::MODE_D, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
     cudaError_t e3 = cudaFuncSetAttribute(dp::conv_tc_kernel<dp::MODE_T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
     cudaError_t e4 = cudaFuncSetAttribute(dp::conv_tc_kernel<dp::MODE_H, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
-    cudaError_t e5 = cudaFuncSetAttribute(dp::dense_layer_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
-    if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess || e4 != cudaSuccess || e5 != cudaSuccess) {
+    cudaError_t e5 = cudaFuncSetAttribute(dp::dense_layer_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
+    cudaError_t e6 = cudaFuncSetAttribute(dp::dense_layer_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
+    if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess || e4 != cudaSuccess || e5 != cudaSuccess || e6 != cudaSuccess) {
       cleanup();
       return fail("cudaFuncSetAttribute(MaxDynamicSharedMemorySize) failed: %s", cudaGetErrorString(cudaGetLastError()));
     }

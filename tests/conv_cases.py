@@ -59,7 +59,8 @@ DENSE_CASES = {
     "dl_32x32_c160": (32, 32, 160, 2, 768, 256),     # channel tail chunk (160 = 2.5 x 64)
     "dl_64x64_c64":  (64, 64, 64, 2, 384, 128),
     "dl_16x16_c992": (16, 16, 992, 5, 1344, 320),    # last layer of block 4, odd batch
-    "dl_8x8_c512":   (8, 8, 512, 4, 1024, 0),        # block 5: map lower than the 16-row region
+    "dl_8x8_c512":   (8, 8, 512, 4, 1024, 0),        # block 5: 8-row regions
+    "dl_64x64_c96_b12": (64, 64, 96, 12, 384, 128),  # enough regions to keep 16-row regions (RH = 16)
 }
 
 

@@ -100,5 +100,6 @@ def test_executed_macs_accounting(setup):
     ref = reference_macs_per_tile(256)
     ex = setup["model"].executed_macs(1)
     # sub-pixel rewrite removes 5/9 of the five up-conv layers (-21 %); the fused dense layers recompute the 1x1
-    # conv on their halo rows (2x on blocks 2-4, +6 % overall); the stem runs as a zero-padded 4x4 conv
-    assert 0.75 * ref < ex < 0.90 * ref, (ex, ref)
+    # conv on their halo rows and, with 8-row regions, issue half-empty M = 128 MMAs for the 3x3 (+14 % overall);
+    # the stem runs as a zero-padded 4x4 conv.  Executed work stays below the reference graph's.
+    assert 0.75 * ref < ex < 1.0 * ref, (ex, ref)
