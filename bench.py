@@ -159,6 +159,7 @@ def main():
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-pdl", action="store_true")
     ap.add_argument("--epi-direct", action="store_true")
+    ap.add_argument("--no-overlap", action="store_true")
     ap.add_argument("--dump-ops", default="", help="write the per-op device-time table (instrumented pass) here")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -203,6 +204,8 @@ def main():
         model.set_option("use_pdl", 0)
     if args.epi_direct:
         model.set_option("epi_direct", 1)
+    if args.no_overlap:
+        model.set_option("use_overlap", 0)
 
     if args.workload == "slide":
         return run_slide(args, model, rank, world, local, dev, barrier, max_over_ranks, peaks, peak_src)

@@ -79,6 +79,7 @@ struct ConvParams {
   __half* out;
   const float* head_w;
   const PassDesc* pass;     // EPI_HEAD: tta_out + probability output of the current call
+  unsigned long long* gt;     // debug: [0]/[1] receive %globaltimer at entry / exit of CTA 0
   unsigned long long* trace;  // debug: [0] = entry counter, then (role<<56 | event<<48 | item<<32 | clock32)
 };
 
@@ -205,6 +206,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   const int warp = tid >> 5;
   const int lane = tid & 31;
   if (tid == 0 && p.trace && blockIdx.x == 0) p.trace[8 + 2000 * 4 + 1] = (2ull << 48) | (clock64() & 0xFFFFFFFFull);
+  if (tid == 0 && p.gt && blockIdx.x == 0) p.gt[0] = globaltimer_ns();
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&map_a);
@@ -256,8 +258,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  pdl_launch_dependents();  // the next layer may begin its own setup as SMs drain
   pdl_wait();               // activations written by the previous layer are complete and visible from here on
+  // Trigger only AFTER our own wait: a dependent that starts now can rely on every kernel before this one
+  // being complete (dense_layer_kernel reads older channels of the concat buffer ahead of its own wait).
+  pdl_launch_dependents();
   const uint32_t tmem_base = *tmem_slot;
   if (tid == 0 && p.trace && blockIdx.x == 0) { p.trace[8 + 2000 * 4] = clock64() & 0xFFFFFFFFull; p.trace[4] = 2; }
   const int n_bgroups = p.n_entries / p.b_group;  // B stages per (work item, channel chunk)
@@ -646,6 +650,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   if (warp == 2) {
     tc_fence_after();
     tmem_dealloc(tmem_base, kTmemCols);
+    if (lane == 0 && p.gt && blockIdx.x == 0) p.gt[1] = globaltimer_ns();
     if (lane == 0 && p.trace && blockIdx.x == 0) { p.trace[8 + 2000 * 4 + 2] = (1ull << 48) | (clock64() & 0xFFFFFFFFull); p.trace[4] = 3; }
   }
 }

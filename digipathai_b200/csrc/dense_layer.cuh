@@ -33,6 +33,8 @@ struct DenseLayerParams {
   int n_img, H, W, C;        // map size, input channels of this layer
   int n_chunks;              // ceil(C / 64)
   int tiles_w, tiles_h, n_items;
+  int n_safe_chunks;         // leading channel chunks not written by the immediately preceding kernel: they are
+                             // consumed BEFORE griddepcontrol.wait, i.e. while the previous layer still runs
   int rh;                    // region height: 16 (180 halo rows, 2 M-blocks) or 8 (100 halo rows, 1 M-block)
   int a_stages, b_stages;
   int out_ctot, out_choff;   // concat buffer channel stride, offset of the 32 new channels
@@ -41,6 +43,7 @@ struct DenseLayerParams {
   const float* mid_shift;    // BN2 shift [128] (scale folded into W1)
   __half* out;               // concat buffer base (same tensor the A map reads)
   unsigned long long* trace;
+  unsigned long long* gt;    // debug: [0]/[1] receive %globaltimer at entry / exit of CTA 0
 };
 
 struct DenseLayerSmem {
@@ -113,6 +116,7 @@ dense_layer_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (tid == 0 && p.trace && blockIdx.x == 0) p.trace[8 + 2000 * 4 + 1] = (2ull << 48) | (clock64() & 0xFFFFFFFFull);
+  if (tid == 0 && p.gt && blockIdx.x == 0) p.gt[0] = globaltimer_ns();
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&map_x);
@@ -155,8 +159,8 @@ dense_layer_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  pdl_launch_dependents();
-  pdl_wait();
+  // No grid-dependency wait here: only the activation producer needs it, and only before the first chunk that
+  // contains channels written by the preceding kernel (see below).
   const uint32_t tmem_base = *tmem_slot;
   if (tid == 0 && p.trace && blockIdx.x == 0) { p.trace[8 + 2000 * 4] = clock64() & 0xFFFFFFFFull; p.trace[4] = 2; }
   const uint32_t acc1_col = tmem_base;         // 2 M-blocks x 128 columns
@@ -175,10 +179,20 @@ dense_layer_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
     if (elect_one()) {
       DlTrace tc = dl_trace_open(p.trace, 0);
       uint32_t sa = 0, pa = 0;
+      bool waited = false;
       for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
         int n0, h0, w0;
         item_origin(item, n0, h0, w0);
         for (int c = 0; c < p.n_chunks; ++c) {
+          if (!waited && c >= p.n_safe_chunks) {
+            // Cross-layer overlap: within a dense block, layer l+1's 1x1 conv over the channels that existed
+            // before layer l does not depend on layer l.  Those chunks were loaded above while the preceding
+            // kernel was still running (it triggered this launch only after its OWN wait, so everything older
+            // is complete); from here on we need its 32 new channels.
+            pdl_wait();
+            pdl_launch_dependents();
+            waited = true;
+          }
           mbar_wait(&a_empty[sa], pa ^ 1);
           mbar_expect_tx(&a_full[sa], kDlRows * 128);
           tma_load_4d(&map_x, &a_full[sa], a_base + sa * kDlAStage, c * 64, w0 - 1, h0 - 1, n0);
@@ -186,6 +200,7 @@ dense_layer_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
           if (++sa == p.a_stages) { sa = 0; pa ^= 1; }
         }
       }
+      if (!waited) { pdl_wait(); pdl_launch_dependents(); }
       dl_trace_close(p.trace, tc, 0);
     }
   } else if (warp == 3) {
@@ -439,6 +454,7 @@ dense_layer_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
   if (warp == 2) {
     tc_fence_after();
     tmem_dealloc(tmem_base, kTmemCols);
+    if (lane == 0 && p.gt && blockIdx.x == 0) p.gt[1] = globaltimer_ns();
     if (lane == 0 && p.trace && blockIdx.x == 0) { p.trace[8 + 2000 * 4 + 2] = (1ull << 48) | (clock64() & 0xFFFFFFFFull); p.trace[4] = 3; }
   }
 }

@@ -147,7 +147,9 @@ struct dp_model {
   __half* scratch_head = nullptr;  // naive path: output of the head-fused conv
   uint64_t device_bytes = 0;
   int naive_conv = 0, desc_base_mode = 0, halo_pad8 = 0, profile = 0;
-  int use_graph = 1, split = 1, use_pdl = 1, epi_direct = 1;
+  int use_graph = 1, split = 1, use_pdl = 1, epi_direct = 1, use_overlap = 1;
+  unsigned long long* gt_dev = nullptr;     // debug: per-op %globaltimer stamps (option "stamp")
+  int stamp = 0;
   unsigned long long* trace_dev = nullptr;  // debug timeline buffer (option "trace_op")
   int trace_op = -1;
   dp::PassDesc* pass_dev = nullptr;          // per-call arguments read by the stem and head kernels
@@ -437,6 +439,8 @@ int plan_dense_layer(dp_model* m, const BlobOp& op, int img0, int B, Launch& L) 
   p.tiles_w = W / 8; p.tiles_h = H / p.rh;
   p.n_items = B * p.tiles_w * p.tiles_h;
   p.out_ctot = ib.C; p.out_choff = op.out_choff;
+  p.n_safe_chunks = m->use_overlap ? op.rsv[1] / 64 : 0;   // rsv[1] = channels older than the preceding kernel's output
+  if (p.n_safe_chunks > p.n_chunks) p.n_safe_chunks = p.n_chunks;
   p.pro_scale = a.pro_scale; p.pro_shift = a.pro_shift; p.mid_shift = a.epi_shift;
   p.out = buf_at(op.in_buf);
   const int budget = 227 * 1024 - DenseLayerSmem::kBarBytes - kDlTBytes - 2 * p.n_chunks * 64 * 4 - 128 * 4 -
@@ -583,6 +587,7 @@ int run_op(dp_model* m, SubPlan* sp, int i, cudaStream_t st) {
       cp.desc_base_mode = m->desc_base_mode;
       cp.epi_direct = m->epi_direct && ((cp.out_choff % 16) == 0) && ((cp.out_ctot % 16) == 0);
       cp.trace = (m->trace_op == i) ? m->trace_dev : nullptr;
+      cp.gt = (m->stamp && m->gt_dev) ? m->gt_dev + 2 * i : nullptr;
       // Programmatic dependent launch: the kernel's setup (barrier init, TMEM alloc, BN constants -> smem)
       // runs before its griddepcontrol.wait and so overlaps the tail of the preceding kernel in the stream.
       cudaLaunchConfig_t cfg;
@@ -625,6 +630,7 @@ int run_op(dp_model* m, SubPlan* sp, int i, cudaStream_t st) {
       }
       dp::DenseLayerParams dl = L.dl;
       dl.trace = (m->trace_op == i) ? m->trace_dev : nullptr;
+      dl.gt = (m->stamp && m->gt_dev) ? m->gt_dev + 2 * i : nullptr;
       cudaLaunchConfig_t cfg;
       memset(&cfg, 0, sizeof cfg);
       cfg.gridDim = dim3(L.grid);
@@ -768,6 +774,7 @@ int dp_model_destroy(dp_model* m) {
   if (m->fork_event) cudaEventDestroy(m->fork_event);
   if (m->pass_dev) cudaFree(m->pass_dev);
   if (m->trace_dev) cudaFree(m->trace_dev);
+  if (m->gt_dev) cudaFree(m->gt_dev);
   for (__half* p : m->buf_dev)
     if (p) cudaFree(p);
   if (m->scratch_head) cudaFree(m->scratch_head);
@@ -790,6 +797,20 @@ int dp_model_set_option(dp_model* m, const char* key, int value) {
   else if (!strcmp(key, "desc_base_mode")) m->desc_base_mode = value;
   else if (!strcmp(key, "profile")) m->profile = value;
   else if (!strcmp(key, "use_graph")) m->use_graph = value;
+  else if (!strcmp(key, "stamp")) {
+    if (!m->gt_dev) CU_OK(cudaMalloc(&m->gt_dev, 2 * m->ops.size() * sizeof(unsigned long long)));
+    CU_OK(cudaMemset(m->gt_dev, 0, 2 * m->ops.size() * sizeof(unsigned long long)));
+    m->stamp = value;
+  }
+  else if (!strcmp(key, "use_overlap")) {
+    std::lock_guard<std::mutex> lk(m->mu);
+    m->use_overlap = value;
+    for (auto& kv : m->plans) {
+      if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
+      if (kv.second.graph) cudaGraphDestroy(kv.second.graph);
+    }
+    m->plans.clear();
+  }
   else if (!strcmp(key, "epi_direct")) {
     std::lock_guard<std::mutex> lk(m->mu);
     m->epi_direct = value;
@@ -986,6 +1007,16 @@ int dp_model_op_times(dp_model* m, float* ms, int n) {
     CU_OK(cudaEventSynchronize(m->ev[2 * i + 1]));
     CU_OK(cudaEventElapsedTime(&ms[i], m->ev[2 * i], m->ev[2 * i + 1]));
   }
+  return 0;
+}
+
+int dp_debug_read_stamps(dp_model* m, unsigned long long* out, int n) {
+  if (check_model(m) || !out) return fail("null argument");
+  if (!m->gt_dev) return fail("no stamps (set option 'stamp')");
+  if (n != 2 * (int)m->ops.size()) return fail("expected room for %zu values", 2 * m->ops.size());
+  CU_OK(cudaSetDevice(m->device));
+  CU_OK(cudaDeviceSynchronize());
+  CU_OK(cudaMemcpy(out, m->gt_dev, (size_t)n * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
   return 0;
 }
 

@@ -150,6 +150,12 @@ class TileModel:
         d["macs_per_tile"] = macs.value
         return d
 
+    def read_stamps(self) -> np.ndarray:
+        n = 2 * self.n_ops()
+        arr = (C.c_uint64 * n)()
+        _lib.check(_lib.lib.dp_debug_read_stamps(self._h, arr, n))
+        return np.array(arr[:], dtype=np.int64).reshape(-1, 2)
+
     def read_trace(self):
         """[(role, event, item, clock32)] of CTA 0 for the op selected with set_option('trace_op', i)."""
         arr = (C.c_uint64 * 10016)()

@@ -117,7 +117,7 @@ def densenet121_unet_program(weights: dict, patch: int = 256, fuse_dense: bool =
             if fuse_dense and (P // 2 ** b) >= 8:
                 # whole dense layer in one kernel, bottleneck kept in shared memory (csrc/dense_layer.cuh)
                 ops.append(Op(OP_DENSE_LAYER, in_buf=D, in_choff=base, cin=c, out_buf=D, out_choff=base + c,
-                              cout=GROWTH, mid_buf=T[b], pro=PRO_AFFINE_RELU, pro_scale=pad64(ps), pro_shift=pad64(psh),
+                              cout=GROWTH, mid_buf=T[b], safe_cin=(c - GROWTH if i > 1 else 0), pro=PRO_AFFINE_RELU, pro_scale=pad64(ps), pro_shift=pad64(psh),
                               epi_shift=esh, w=pack_conv_weights(weights[p + "_1_conv"] * es, KIND_1X1),
                               w2=pack_conv_weights(weights[p + "_2_conv"], KIND_3X3), name=p))
                 continue

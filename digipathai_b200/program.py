@@ -13,7 +13,7 @@ Container layout (must match ``BlobHeader`` / ``BlobBuf`` / ``BlobOp`` in csrc/r
     n_ops  x 128 B: 12 x i32 (type in_buf in_choff cin out_buf out_choff cout kind relu pro head pool)
                    | f32 head_b | 3 x i32 0 | 8 x i64 offsets into the data section (-1 = absent):
                      w, epi_scale, epi_shift, pro_scale, pro_shift, head_w, w2, 0
-                   (rsv i32 #0 = mid_buf for OP_DENSE_LAYER)
+                   (rsv i32 #0 = mid_buf, #1 = safe_cin for OP_DENSE_LAYER)
     data section : 256-byte aligned arrays (fp16 weights [entries][Cout][Cin]; fp32 vectors)
 """
 from __future__ import annotations
@@ -52,6 +52,7 @@ class Op:
     head_w: Optional[np.ndarray] = None     # fp32 [cout]
     w2: Optional[np.ndarray] = None         # OP_DENSE_LAYER: fp16 [9, 32, 128] 3x3 weights (w = [1, 128, cin])
     mid_buf: int = 0                        # OP_DENSE_LAYER: bottleneck buffer (only the debug path writes it)
+    safe_cin: int = 0                       # OP_DENSE_LAYER: leading input channels NOT written by the preceding op
     name: str = ""
 
 
@@ -190,7 +191,7 @@ def serialize(prog: Program) -> bytes:
         op_recs.append(
             struct.pack(
                 "<12if3i8q", o.type, o.in_buf, o.in_choff, o.cin, o.out_buf, o.out_choff, o.cout, o.kind, o.relu,
-                o.pro, o.head, o.pool, float(o.head_b), o.mid_buf, 0, 0, *offs,
+                o.pro, o.head, o.pool, float(o.head_b), o.mid_buf, o.safe_cin, 0, *offs,
             )
         )
     buf_recs = [struct.pack("<4i", h, w, c, 0) for (h, w, c) in prog.bufs]

@@ -107,6 +107,8 @@ uint64_t dp_kernel_launch_count(void);
  *          "profile" (0/1: record CUDA events around every op for dp_model_op_times; implies direct launches),
  *          "use_graph" (0/1, default 1: replay dp_forward_tiles as one captured CUDA graph),
  *          "use_pdl" (0/1, default 1: conv kernels use programmatic dependent launch),
+ *          "use_overlap" (0/1, default 1: a dense layer consumes the channels older than its predecessor's output
+ *                         before its grid-dependency wait, overlapping consecutive layers),
  *          "epi_direct" (0/1, default 1: epilogue writes 256-bit vectors from registers instead of staging in smem),
  *          "split" (default 1: number of sub-batches captured as parallel graph branches). */
 int dp_model_set_option(dp_model* m, const char* key, int value);
@@ -135,6 +137,10 @@ int dp_model_op_info(const dp_model* m, int op, int* type, int* kind, int* cin, 
  * out[r] = entries of role r (0 producer, 1 MMA, 2 epilogue, 3 transform, 4 setup); role r's entries start at
  * out[8 + 2000 r], each event<<48 | item<<32 | clock32. */
 int dp_debug_read_trace(dp_model* m, unsigned long long* out, int n);
+
+/* %globaltimer (ns) at entry / exit of CTA 0 of every tensor-core op of the last direct-launch run made with
+ * option "stamp" = 1: out[2*op], out[2*op+1]; n must be 2 * number of ops. */
+int dp_debug_read_stamps(dp_model* m, unsigned long long* out, int n);
 
 /* Executed tensor-core MACs of one forward pass over n_tiles tiles (after the sub-pixel rewrite). */
 int dp_model_executed_macs(const dp_model* m, int n_tiles, uint64_t* macs);
