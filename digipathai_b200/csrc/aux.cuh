@@ -5,6 +5,7 @@
 #include <cuda_fp16.h>
 #include <stdint.h>
 #include "d4.cuh"
+#include "ptx.cuh"
 
 namespace dp {
 
@@ -58,6 +59,8 @@ __global__ void stem_im2col_kernel(const PassDesc* __restrict__ pass, int img0, 
 //   out[b][r][q][dq*16 + (a*2+b2)*3 + c] = net_in[2r+a][2(q+dq-2)+b2][c]     (0 outside the tile / ch >= 12)
 // with net_in = forward-TTA'd, (v-128)/128-normalised tile cropped from the slide raster.  fp16 [B][P/2][P/2][64].
 __global__ void stem_s2d_kernel(const PassDesc* __restrict__ pass, int img0, int B, int P, __half* __restrict__ out) {
+  pdl_wait();               // launched with programmatic stream serialization: inputs complete from here
+  pdl_launch_dependents();
   const uint8_t* __restrict__ slide = pass->slide;
   const long long slide_h = pass->slide_h;
   const int* __restrict__ coords = pass->coords + 2 * img0;
@@ -100,6 +103,8 @@ __global__ void stem_s2d_kernel(const PassDesc* __restrict__ pass, int img0, int
 __global__ void maxpool3s2_kernel(const __half* __restrict__ in, int in_ctot, int in_choff,
                                   __half* __restrict__ out, int out_ctot, int out_choff, int n_img, int H, int W,
                                   int C) {
+  pdl_wait();               // launched with programmatic stream serialization: inputs complete from here
+  pdl_launch_dependents();
   const int OH = H / 2, OW = W / 2, CG = C / 8;
   const long long total = static_cast<long long>(n_img) * OH * OW * CG;
   for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
@@ -145,6 +150,8 @@ __global__ void bn_act_pool_kernel(const __half* __restrict__ in, int in_ctot, i
                                    __half* __restrict__ out, int out_ctot, int out_choff, int n_img, int H, int W,
                                    int C, const float* __restrict__ scale, const float* __restrict__ shift,
                                    int relu, int pool) {
+  pdl_wait();               // launched with programmatic stream serialization: inputs complete from here
+  pdl_launch_dependents();
   const int OH = pool ? H / 2 : H, OW = pool ? W / 2 : W, CG = C / 8;
   const long long total = static_cast<long long>(n_img) * OH * OW * CG;
   for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;

@@ -2,32 +2,46 @@
 // (reference: dense_conv_block, DigiPathAI/models/densenet.py:50-75), with the 128-channel bottleneck kept in
 // shared memory instead of a round trip through HBM and a second launch.
 //
-// Work item = one 16 x 8 pixel region of one image.  Per item:
+// Work item = one RH x 8 pixel region of one image (RH = 16 or 8).  Per item:
 //   phase 1  for every 64-channel chunk of the concat buffer: TMA-load the region WITH its 1-pixel halo
-//            (18 x 10 pixels = 180 rows of 128 B), pre-activation BN+ReLU in place (4 transform warps), then
-//            tcgen05.mma M = 2 x 128 rows (rows >= 180 are don't-care), N = 128, accumulating in TMEM.
-//            The halo pixels' bottleneck values are recomputed by every region that needs them (1.41x the
-//            1x1 MACs) -- that is the price of not synchronising neighbouring CTAs.
+//            ((RH+2) x 10 pixels = 180 / 100 rows of 128 B), pre-activation BN+ReLU in place (8 transform
+//            warps), then tcgen05.mma over the halo rows (2 / 1 M-blocks of 128 rows, rows beyond the box are
+//            don't-care), N = 128, accumulating in TMEM.  The halo pixels' bottleneck values are recomputed by
+//            every region that needs them (1.4-1.6x the 1x1 MACs) -- the price of not synchronising CTAs.
 //   mid      epilogue warps: TMEM -> +BN shift -> ReLU -> zero outside the image (the 3x3's `same` padding is
 //            applied to the bottleneck, AFTER its BN-ReLU) -> fp16 -> written as two swizzled K-major operand
-//            tiles T[2][180 rows][64 ch] in shared memory, fence.proxy.async.
+//            tiles T[2 chunks][rows][64 ch] in shared memory, fence.proxy.async.
 //   phase 2  the 3x3 conv as 9 taps x 2 chunks of UMMA descriptors into T (row offset (dy+1)*10 + dx+1,
-//            SBO = 10 * 128 B), N = 32.
-//   final    TMEM -> fp16 -> the layer's 32 new channels in the concat buffer (coalesced via staging rows).
+//            SBO = 10 * 128 B), N = 32 (for RH = 8 the upper 64 accumulator rows are don't-care).
+//   final    TMEM -> fp16 -> the layer's 32 new channels in the concat buffer (256-bit stores).
+//
+// Items are software-pipelined: T and the 3x3 accumulator are double-buffered, so the MMA warp issues
+//   ph1(0) | ph1(1) ph2(0) | ph1(2) ph2(1) | ...      and the epilogue warps run   mid(0) | mid(1) fin(0) | ...
+// i.e. the tensor pipe works on item k+1's 1x1 while the epilogue warps turn item k's accumulator into T, and
+// on item k's 3x3 while they do mid(k+1).
+//
+// Cross-layer overlap: only the activation producer executes griddepcontrol.wait, and only before the first
+// chunk that contains the preceding layer's 32 new channels; older chunks are consumed while that layer runs.
 //
 // Warp roles: 0 = TMA producer (activation halo chunks), 1 = MMA issuer, 2 = TMEM allocator, 3 = TMA producer
-// (W1 chunks, then W2 tap groups, one ring), 4-7 = epilogue (mid + final), 8-15 = pre-activation transform
-// (the transform, not the MMA, paces phase 1: ~3.5 ALU instructions per fp16 element in fp32 arithmetic).
+// (W1 chunks / W2 tap groups, one ring, in MMA order), 4-7 = epilogue (mid + final), 8-15 = pre-activation
+// transform (BN terms of a thread's 8 channels stay in registers).
 #pragma once
 #include "conv_tc.cuh"
 
 namespace dp {
 
-constexpr int kDlHaloW = 10;           // 8-pixel-wide regions + 1-pixel halo each side
-constexpr int kDlAStage = 256 * 128;   // up to 2 M-blocks of 128 rows x 128 B (rows beyond the halo box unused)
-constexpr int kDlBStage = 128 * 128;   // W1 chunk [128 x 64]; W2 groups (3 taps x [32 x 64] = 12 KB) fit too
-constexpr int kDlTBytes = 2 * kDlAStage;  // bottleneck operand: 2 chunks x 256 rows x 128 B
-constexpr int kDlW2Group = 3;          // taps per W2 stage
+constexpr int kDlHaloW = 10;              // 8-pixel-wide regions + 1-pixel halo each side
+constexpr int kDlBStage = 128 * 128;      // W1 chunk [128 x 64]; W2 groups (3 taps x [32 x 64] = 12 KB) fit too
+constexpr int kDlTChunk = 23 * 1024;      // one 64-channel chunk of the bottleneck tile: 180 rows x 128 B, 1 KB aligned
+constexpr int kDlTBuf = 2 * kDlTChunk;    // 128 channels
+constexpr int kDlTBytes = 2 * kDlTBuf;    // double-buffered
+constexpr int kDlW2Group = 3;             // taps per W2 stage
+
+__host__ __device__ constexpr int dl_rows(int rh) { return kDlHaloW * (rh + 2); }
+// A-stage stride: the halo box rounded up to 1 KB.  The last M-block reads 128 rows regardless, i.e. up to 9 KB
+// past the stage end -- into the next stage or the weight ring, always inside the allocation, never used.
+__host__ __device__ constexpr int dl_a_stage(int rh) { return (dl_rows(rh) * 128 + 1023) / 1024 * 1024; }
 
 struct DenseLayerParams {
   int n_img, H, W, C;        // map size, input channels of this layer
@@ -48,18 +62,17 @@ struct DenseLayerParams {
 
 struct DenseLayerSmem {
   static constexpr int kBarBytes = 1024;
-  int a_off, b_off, t_off, pro_off, mid_off, stage_off, total;
+  int a_off, b_off, t_off, pro_off, mid_off, total;
 };
 
 __host__ __device__ inline DenseLayerSmem dense_layer_smem(const DenseLayerParams& p) {
   DenseLayerSmem L;
   L.a_off = DenseLayerSmem::kBarBytes;
-  L.b_off = L.a_off + p.a_stages * kDlAStage;
+  L.b_off = L.a_off + p.a_stages * dl_a_stage(p.rh);
   L.t_off = L.b_off + p.b_stages * kDlBStage;
   L.pro_off = L.t_off + kDlTBytes;
   L.mid_off = L.pro_off + 2 * p.n_chunks * 64 * 4;
-  L.stage_off = L.mid_off + 128 * 4;
-  L.total = L.stage_off + 4 * kEpiStageBytes + 1024;
+  L.total = L.mid_off + 128 * 4 + 1024;
   return L;
 }
 
@@ -81,14 +94,11 @@ __device__ __forceinline__ void dl_trace_close(unsigned long long* trace, const 
   if (c.base) trace[role] = c.n;
 }
 
-// RH = region height in pixels.  RH = 8 halves the halo box (100 rows, one 128-row M-block in phase 1) and is used
-// where 16-row regions would leave SMs idle (16x16 and 8x8 maps at batch 32); phase 2 still issues M = 128 MMAs,
-// whose upper 64 rows are don't-care.
 template <int RH>
 __global__ void __launch_bounds__(512, 1)
 dense_layer_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w1,
                    const __grid_constant__ CUtensorMap map_w2, const __grid_constant__ DenseLayerParams p) {
-  constexpr int kDlHaloH = RH + 2, kDlRows = kDlHaloW * kDlHaloH, kMBlk = (kDlRows + 127) / 128;
+  constexpr int kRows = dl_rows(RH), kMBlk = (kRows + 127) / 128, kAStage = dl_a_stage(RH);
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
@@ -100,11 +110,11 @@ dense_layer_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
   uint64_t* b_empty = b_full + kMaxBStages;
   uint64_t* acc1_full = b_empty + kMaxBStages;
   uint64_t* acc1_empty = acc1_full + 1;
-  uint64_t* t_ready = acc1_empty + 1;
-  uint64_t* t_empty = t_ready + 1;
-  uint64_t* acc2_full = t_empty + 1;
-  uint64_t* acc2_empty = acc2_full + 1;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc2_empty + 1);
+  uint64_t* t_ready = acc1_empty + 1;    // [2]
+  uint64_t* t_empty = t_ready + 2;       // [2]
+  uint64_t* acc2_full = t_empty + 2;     // [2]
+  uint64_t* acc2_empty = acc2_full + 2;  // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc2_empty + 2);
 
   const DenseLayerSmem L = dense_layer_smem(p);
   uint8_t* a_base = smem + L.a_off;
@@ -135,10 +145,12 @@ dense_layer_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
     }
     mbar_init(acc1_full, 1);
     mbar_init(acc1_empty, 128);
-    mbar_init(t_ready, 128);
-    mbar_init(t_empty, 1);
-    mbar_init(acc2_full, 1);
-    mbar_init(acc2_empty, 128);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&t_ready[i], 128);
+      mbar_init(&t_empty[i], 1);
+      mbar_init(&acc2_full[i], 1);
+      mbar_init(&acc2_empty[i], 128);
+    }
     fence_barrier_init();
   }
   if (warp == 2) {
@@ -159,12 +171,13 @@ dense_layer_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  // No grid-dependency wait here: only the activation producer needs it, and only before the first chunk that
-  // contains channels written by the preceding kernel (see below).
+  // No grid-dependency wait here: only the activation producer needs it (see header).
   const uint32_t tmem_base = *tmem_slot;
   if (tid == 0 && p.trace && blockIdx.x == 0) { p.trace[8 + 2000 * 4] = clock64() & 0xFFFFFFFFull; p.trace[4] = 2; }
-  const uint32_t acc1_col = tmem_base;         // 2 M-blocks x 128 columns
-  const uint32_t acc2_col = tmem_base + 256;   // 32 columns
+  const uint32_t acc1_col = tmem_base;        // kMBlk x 128 columns
+  const uint32_t acc2_col = tmem_base + 256;  // 2 x 32 columns
+  const int first = blockIdx.x;
+  const int n_local = (first < p.n_items) ? (p.n_items - first + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x) : 0;
 
   auto item_origin = [&](int item, int& n0, int& h0, int& w0) {
     const int tw = item % p.tiles_w;
@@ -180,22 +193,21 @@ dense_layer_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
       DlTrace tc = dl_trace_open(p.trace, 0);
       uint32_t sa = 0, pa = 0;
       bool waited = false;
-      for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+      for (int k = 0; k < n_local; ++k) {
+        const int item = first + k * gridDim.x;
         int n0, h0, w0;
         item_origin(item, n0, h0, w0);
         for (int c = 0; c < p.n_chunks; ++c) {
           if (!waited && c >= p.n_safe_chunks) {
-            // Cross-layer overlap: within a dense block, layer l+1's 1x1 conv over the channels that existed
-            // before layer l does not depend on layer l.  Those chunks were loaded above while the preceding
-            // kernel was still running (it triggered this launch only after its OWN wait, so everything older
-            // is complete); from here on we need its 32 new channels.
+            // From here on we need the preceding layer's 32 new channels.  It triggered this launch only after
+            // its OWN wait, so everything older was already complete when we started.
             pdl_wait();
             pdl_launch_dependents();
             waited = true;
           }
           mbar_wait(&a_empty[sa], pa ^ 1);
-          mbar_expect_tx(&a_full[sa], kDlRows * 128);
-          tma_load_4d(&map_x, &a_full[sa], a_base + sa * kDlAStage, c * 64, w0 - 1, h0 - 1, n0);
+          mbar_expect_tx(&a_full[sa], kRows * 128);
+          tma_load_4d(&map_x, &a_full[sa], a_base + sa * kAStage, c * 64, w0 - 1, h0 - 1, n0);
           dl_trace_ev(tc, 1, item);
           if (++sa == p.a_stages) { sa = 0; pa ^= 1; }
         }
@@ -204,16 +216,18 @@ dense_layer_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
       dl_trace_close(p.trace, tc, 0);
     }
   } else if (warp == 3) {
-    // ------------------------------------------------------------------ producer: W1 chunks, then W2 tap groups
+    // ------------------------------------------------------------------ producer: weights, in MMA order
     if (elect_one()) {
       uint32_t sb = 0, pb = 0;
-      for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+      auto load_w1 = [&]() {
         for (int c = 0; c < p.n_chunks; ++c) {
           mbar_wait(&b_empty[sb], pb ^ 1);
           mbar_expect_tx(&b_full[sb], 128 * 128);
           tma_load_3d(&map_w1, &b_full[sb], b_base + sb * kDlBStage, c * 64, 0, 0);
           if (++sb == p.b_stages) { sb = 0; pb ^= 1; }
         }
+      };
+      auto load_w2 = [&]() {
         for (int c = 0; c < 2; ++c)
           for (int g = 0; g < 9 / kDlW2Group; ++g) {
             mbar_wait(&b_empty[sb], pb ^ 1);
@@ -221,6 +235,11 @@ dense_layer_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
             tma_load_3d(&map_w2, &b_full[sb], b_base + sb * kDlBStage, c * 64, 0, g * kDlW2Group);
             if (++sb == p.b_stages) { sb = 0; pb ^= 1; }
           }
+      };
+      if (n_local > 0) load_w1();
+      for (int k = 0; k < n_local; ++k) {
+        if (k + 1 < n_local) load_w1();
+        load_w2();
       }
     }
   } else if (warp == 1) {
@@ -233,30 +252,32 @@ dense_layer_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
       const uint64_t a_desc0 = hi_dense | sw128_desc_lo(smem_u32(a_base));
       const uint64_t b_desc0 = hi_dense | sw128_desc_lo(smem_u32(b_base));
       const uint64_t t_desc0 = hi_halo | sw128_desc_lo(smem_u32(t_base));
-      uint32_t sa = 0, pa = 0, sb = 0, pb = 0, ph = 0;  // ph: per-item phase parity of the single-stage barriers
-      for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ph ^= 1) {
-        // ---- phase 1: bottleneck = W1 * relu(bn(x)) over the halo region
-        mbar_wait(acc1_empty, ph ^ 1);
+      uint32_t sa = 0, pa = 0, sb = 0, pb = 0;
+      // ---- phase 1 of local item k: bottleneck accumulator = W1 * relu(bn(x)) over the halo rows
+      auto ph1 = [&](int k) {
+        mbar_wait(acc1_empty, (k & 1) ^ 1);
         tc_fence_after();
         for (int c = 0; c < p.n_chunks; ++c) {
           int ks = (p.C - c * 64 + 15) >> 4;
           ks = ks > 4 ? 4 : ks;
           mbar_wait(&a_ready[sa], pa);
-          dl_trace_ev(tc, 1, item);
+          dl_trace_ev(tc, 1, k);
           mbar_wait(&b_full[sb], pb);
           tc_fence_after();
-          dl_trace_ev(tc, 2, item);
-          const uint64_t a_desc = a_desc0 + sa * (kDlAStage >> 4);
+          const uint64_t a_desc = a_desc0 + sa * (kAStage >> 4);
           const uint64_t b_desc = b_desc0 + sb * (kDlBStage >> 4);
           const uint32_t acc = (c > 0) ? 1u : 0u;
           if (ks == 4) {
             umma_f16_ss_k4(acc1_col, a_desc, b_desc, idesc1, acc);
             if (kMBlk > 1) umma_f16_ss_k4(acc1_col + 128, a_desc + (kATileBytes >> 4), b_desc, idesc1, acc);
+          } else if (ks == 2) {
+            umma_f16_ss_k2(acc1_col, a_desc, b_desc, idesc1, acc);
+            if (kMBlk > 1) umma_f16_ss_k2(acc1_col + 128, a_desc + (kATileBytes >> 4), b_desc, idesc1, acc);
           } else {
-            for (int k = 0; k < ks; ++k) {
-              umma_f16_ss(acc1_col, a_desc + 2 * k, b_desc + 2 * k, idesc1, k ? 1u : acc);
+            for (int kk = 0; kk < ks; ++kk) {
+              umma_f16_ss(acc1_col, a_desc + 2 * kk, b_desc + 2 * kk, idesc1, kk ? 1u : acc);
               if (kMBlk > 1)
-                umma_f16_ss(acc1_col + 128, a_desc + (kATileBytes >> 4) + 2 * k, b_desc + 2 * k, idesc1, k ? 1u : acc);
+                umma_f16_ss(acc1_col + 128, a_desc + (kATileBytes >> 4) + 2 * kk, b_desc + 2 * kk, idesc1, kk ? 1u : acc);
             }
           }
           umma_commit(&a_empty[sa]);
@@ -265,14 +286,19 @@ dense_layer_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
           if (++sb == p.b_stages) { sb = 0; pb ^= 1; }
         }
         umma_commit(acc1_full);
-        dl_trace_ev(tc, 3, item);
-        // ---- phase 2: 3x3 conv over the bottleneck tile in shared memory
-        mbar_wait(t_ready, ph);
-        mbar_wait(acc2_empty, ph ^ 1);
+        dl_trace_ev(tc, 3, k);
+      };
+      // ---- phase 2 of local item k: 3x3 conv over the bottleneck tile T[k & 1]
+      auto ph2 = [&](int k) {
+        const int tb = k & 1;
+        const uint32_t u = (k >> 1) & 1;
+        mbar_wait(&t_ready[tb], u);
+        mbar_wait(&acc2_empty[tb], u ^ 1);
         tc_fence_after();
-        dl_trace_ev(tc, 4, item);
+        dl_trace_ev(tc, 4, k);
+        const uint32_t d2 = acc2_col + tb * 32;
         for (int c = 0; c < 2; ++c) {
-          const uint64_t t_desc = t_desc0 + c * (kDlAStage >> 4);
+          const uint64_t t_desc = t_desc0 + ((tb * kDlTBuf + c * kDlTChunk) >> 4);
           for (int g = 0; g < 9 / kDlW2Group; ++g) {
             mbar_wait(&b_full[sb], pb);
             tc_fence_after();
@@ -281,15 +307,20 @@ dense_layer_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
             for (int j = 0; j < kDlW2Group; ++j, b_desc += (32 * 128) >> 4) {
               const int tap = g * kDlW2Group + j;
               const int dy = tap / 3, dx = tap - dy * 3;  // (dy+1, dx+1) with dy,dx in -1..1
-              umma_f16_ss_k4(acc2_col, t_desc + (dy * kDlHaloW + dx) * 8, b_desc, idesc2, (c | tap) ? 1u : 0u);
+              umma_f16_ss_k4(d2, t_desc + (dy * kDlHaloW + dx) * 8, b_desc, idesc2, (c | tap) ? 1u : 0u);
             }
             umma_commit(&b_empty[sb]);
             if (++sb == p.b_stages) { sb = 0; pb ^= 1; }
           }
         }
-        umma_commit(t_empty);
-        umma_commit(acc2_full);
-        dl_trace_ev(tc, 5, item);
+        umma_commit(&t_empty[tb]);
+        umma_commit(&acc2_full[tb]);
+        dl_trace_ev(tc, 5, k);
+      };
+      if (n_local > 0) ph1(0);
+      for (int k = 0; k < n_local; ++k) {
+        if (k + 1 < n_local) ph1(k + 1);
+        ph2(k);
       }
       dl_trace_close(p.trace, tc, 1);
     }
@@ -297,24 +328,26 @@ dense_layer_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
     // ------------------------------------------------------------------ epilogue warps: mid + final
     const int q = warp & 3;
     const int r = q * 32 + lane;
-    uint8_t* stage = smem + L.stage_off + q * kEpiStageBytes;
     DlTrace tc;
     if (r == 0) tc = dl_trace_open(p.trace, 2);
-    uint32_t ph = 0;
-    for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ph ^= 1) {
+    // ---- mid(k): acc1 -> +shift -> ReLU -> zero padding -> fp16 -> swizzled operand tile T[k & 1]
+    auto mid = [&](int k) {
+      const int item = first + k * gridDim.x;
       int n0, h0, w0;
       item_origin(item, n0, h0, w0);
-      // ---- mid: acc1 -> +shift -> ReLU -> zero padding -> fp16 -> swizzled operand tile T
-      mbar_wait(acc1_full, ph);
-      mbar_wait(t_empty, ph ^ 1);   // previous item's 3x3 MMAs no longer read T
+      const int tb = k & 1;
+      const uint32_t u = (k >> 1) & 1;
+      mbar_wait(acc1_full, k & 1);
+      mbar_wait(&t_empty[tb], u ^ 1);   // the 3x3 MMAs of item k-2 no longer read this buffer
       tc_fence_after();
-      dl_trace_ev(tc, 0, item);
+      dl_trace_ev(tc, 0, k);
+      uint8_t* tbuf = t_base + tb * kDlTBuf;
 #pragma unroll 1
       for (int mb = 0; mb < kMBlk; ++mb) {
         const int prow = mb * 128 + r;                 // halo pixel index
         const int hh = prow / kDlHaloW, ww = prow - hh * kDlHaloW;
         const int ih = h0 - 1 + hh, iw = w0 - 1 + ww;
-        const bool inside = prow < kDlRows && ih >= 0 && ih < p.H && iw >= 0 && iw < p.W;
+        const bool inside = prow < kRows && ih >= 0 && ih < p.H && iw >= 0 && iw < p.W;
         const uint32_t taddr = acc1_col + mb * 128 + (static_cast<uint32_t>(q * 32) << 16);
 #pragma unroll 1
         for (int cc = 0; cc < 128; cc += 32) {
@@ -322,7 +355,7 @@ dense_layer_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
           tmem_ld16(taddr + cc, v[0]);
           tmem_ld16(taddr + cc + 16, v[1]);
           tmem_ld_wait();
-          if (prow < kDlRows) {
+          if (prow < kRows) {
 #pragma unroll
             for (int hsel = 0; hsel < 2; ++hsel) {
               const int cb = cc + 16 * hsel;
@@ -335,7 +368,7 @@ dense_layer_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
                 pk[i] = *reinterpret_cast<uint32_t*>(&h2);
               }
               // channels cb..cb+15 = 16-byte chunks j, j+1 of 64-channel chunk (cb / 64)
-              uint8_t* row = t_base + (cb >> 6) * kDlAStage + prow * 128;
+              uint8_t* row = tbuf + (cb >> 6) * kDlTChunk + prow * 128;
               const int j = (cb & 63) >> 3;
               *reinterpret_cast<uint4*>(row + (((j) ^ (prow & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
               *reinterpret_cast<uint4*>(row + (((j + 1) ^ (prow & 7)) << 4)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
@@ -346,49 +379,46 @@ dense_layer_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
       tc_fence_before();
       fence_proxy_async_smem();
       mbar_arrive(acc1_empty);
-      mbar_arrive(t_ready);
-      dl_trace_ev(tc, 2, item);
-      // ---- final: acc2 -> fp16 -> 32 new channels of the concat buffer
-      mbar_wait(acc2_full, ph);
+      mbar_arrive(&t_ready[tb]);
+      dl_trace_ev(tc, 2, k);
+    };
+    // ---- fin(k): acc2[k & 1] -> fp16 -> the 32 new channels of the concat buffer
+    auto fin = [&](int k) {
+      const int item = first + k * gridDim.x;
+      int n0, h0, w0;
+      item_origin(item, n0, h0, w0);
+      const int tb = k & 1;
+      const uint32_t u = (k >> 1) & 1;
+      mbar_wait(&acc2_full[tb], u);
       tc_fence_after();
-      dl_trace_ev(tc, 3, item);
-      {
-        const int w = w0 + (r & 7), h = h0 + (r >> 3);
-        const bool valid = (n0 < p.n_img) && ((r >> 3) < RH) && (h < p.H) && (w < p.W);
-        const long long opix = (static_cast<long long>(n0) * p.H + h) * p.W + w;
-        const unsigned long long my_row = reinterpret_cast<unsigned long long>(p.out + opix * p.out_ctot + p.out_choff);
-        uint32_t v[2][16];
-        const uint32_t taddr = acc2_col + (static_cast<uint32_t>(q * 32) << 16);
-        tmem_ld16(taddr, v[0]);
-        tmem_ld16(taddr + 16, v[1]);
-        tmem_ld_wait();
+      dl_trace_ev(tc, 3, k);
+      const int w = w0 + (r & 7), h = h0 + (r >> 3);
+      const bool valid = (n0 < p.n_img) && ((r >> 3) < RH) && (h < p.H) && (w < p.W);
+      const long long opix = (static_cast<long long>(n0) * p.H + h) * p.W + w;
+      __half* orow = p.out + opix * p.out_ctot + p.out_choff;
+      uint32_t v[2][16];
+      const uint32_t taddr = acc2_col + tb * 32 + (static_cast<uint32_t>(q * 32) << 16);
+      tmem_ld16(taddr, v[0]);
+      tmem_ld16(taddr + 16, v[1]);
+      tmem_ld_wait();
 #pragma unroll
-        for (int hsel = 0; hsel < 2; ++hsel) {
-          uint32_t pk[8];
+      for (int hsel = 0; hsel < 2; ++hsel) {
+        uint32_t pk[8];
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            __half2 h2 = __floats2half2_rn(__uint_as_float(v[hsel][2 * i]), __uint_as_float(v[hsel][2 * i + 1]));
-            pk[i] = *reinterpret_cast<uint32_t*>(&h2);
-          }
-          uint4* dst = reinterpret_cast<uint4*>(stage + lane * kEpiRowBytes + hsel * 32);
-          dst[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-          dst[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+        for (int i = 0; i < 8; ++i) {
+          __half2 h2 = __floats2half2_rn(__uint_as_float(v[hsel][2 * i]), __uint_as_float(v[hsel][2 * i + 1]));
+          pk[i] = *reinterpret_cast<uint32_t*>(&h2);
         }
-        __syncwarp();
-#pragma unroll
-        for (int it = 0; it < 4; ++it) {   // 32 rows x 4 chunks of 16 B; 4 lanes cover one pixel's 64 bytes
-          const int idx = it * 32 + lane;
-          const int row = idx >> 2, j = idx & 3;
-          const unsigned long long rp = __shfl_sync(0xffffffffu, my_row, row);
-          const int rv = __shfl_sync(0xffffffffu, static_cast<int>(valid), row);
-          const uint4 val = *reinterpret_cast<const uint4*>(stage + row * kEpiRowBytes + j * 16);
-          if (rv) *reinterpret_cast<uint4*>(reinterpret_cast<__half*>(rp) + j * 8) = val;
-        }
-        __syncwarp();
+        if (valid) st_global_v8(orow + 16 * hsel, pk);
       }
       tc_fence_before();
-      mbar_arrive(acc2_empty);
-      dl_trace_ev(tc, 1, item);
+      mbar_arrive(&acc2_empty[tb]);
+      dl_trace_ev(tc, 1, k);
+    };
+    if (n_local > 0) mid(0);
+    for (int k = 0; k < n_local; ++k) {
+      if (k + 1 < n_local) mid(k + 1);
+      fin(k);
     }
     if (r == 0) dl_trace_close(p.trace, tc, 2);
   } else if (warp >= 8) {
@@ -398,32 +428,31 @@ dense_layer_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
     DlTrace tc;
     if (t == 0) tc = dl_trace_open(p.trace, 3);
     uint32_t sa = 0, pa = 0;
-    for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+    for (int k = 0; k < n_local; ++k) {
       for (int c = 0; c < p.n_chunks; ++c) {
         mbar_wait(&a_full[sa], pa);
-        dl_trace_ev(tc, 1, item);
+        dl_trace_ev(tc, 1, k);
         {
-          // Thread t owns logical 16-byte chunk i = t & 7 (8 channels) of rows (t >> 3) + 32 k: its 16 BN terms
+          // Thread t owns logical 16-byte chunk i = t & 7 (8 channels) of rows (t >> 3) + 32 j: its 16 BN terms
           // stay in registers for the whole stage, so shared-memory traffic is the data itself (a quarter-warp
-          // covers one full 128-byte row: conflict-free under the 128B swizzle) instead of 32 broadcast
-          // parameter loads per row.
+          // covers one full 128-byte row: conflict-free under the 128B swizzle).
           const int i = t & 7;
           const int ch = c * 64 + i * 8;
           const float4 sc0 = *reinterpret_cast<const float4*>(s_pro_scale + ch);
           const float4 sc1 = *reinterpret_cast<const float4*>(s_pro_scale + ch + 4);
           const float4 sh0 = *reinterpret_cast<const float4*>(s_pro_shift + ch);
           const float4 sh1 = *reinterpret_cast<const float4*>(s_pro_shift + ch + 4);
-          uint8_t* stage_base = a_base + sa * kDlAStage;
-          constexpr int kIter = (kDlRows + 31) / 32;   // 6
+          uint8_t* stage_base = a_base + sa * kAStage;
+          constexpr int kIter = (kRows + 31) / 32;
           uint4 raw[kIter];
 #pragma unroll
-          for (int k = 0; k < kIter; ++k) {
-            const int rr = (t >> 3) + 32 * k;
-            if (rr < kDlRows) raw[k] = *reinterpret_cast<const uint4*>(stage_base + rr * 128 + ((i ^ (rr & 7)) << 4));
+          for (int j = 0; j < kIter; ++j) {
+            const int rr = (t >> 3) + 32 * j;
+            if (rr < kRows) raw[j] = *reinterpret_cast<const uint4*>(stage_base + rr * 128 + ((i ^ (rr & 7)) << 4));
           }
 #pragma unroll
-          for (int k = 0; k < kIter; ++k) {
-            __half2* hv = reinterpret_cast<__half2*>(&raw[k]);
+          for (int j = 0; j < kIter; ++j) {
+            __half2* hv = reinterpret_cast<__half2*>(&raw[j]);
             float2 x;
             x = __half22float2(hv[0]);
             hv[0] = __hmax2(__floats2half2_rn(fmaf(x.x, sc0.x, sh0.x), fmaf(x.y, sc0.y, sh0.y)), zero2);
@@ -435,14 +464,14 @@ dense_layer_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
             hv[3] = __hmax2(__floats2half2_rn(fmaf(x.x, sc1.z, sh1.z), fmaf(x.y, sc1.w, sh1.w)), zero2);
           }
 #pragma unroll
-          for (int k = 0; k < kIter; ++k) {
-            const int rr = (t >> 3) + 32 * k;
-            if (rr < kDlRows) *reinterpret_cast<uint4*>(stage_base + rr * 128 + ((i ^ (rr & 7)) << 4)) = raw[k];
+          for (int j = 0; j < kIter; ++j) {
+            const int rr = (t >> 3) + 32 * j;
+            if (rr < kRows) *reinterpret_cast<uint4*>(stage_base + rr * 128 + ((i ^ (rr & 7)) << 4)) = raw[j];
           }
         }
         fence_proxy_async_smem();
         mbar_arrive(&a_ready[sa]);
-        dl_trace_ev(tc, 0, item);
+        dl_trace_ev(tc, 0, k);
         if (++sa == p.a_stages) { sa = 0; pa ^= 1; }
       }
     }

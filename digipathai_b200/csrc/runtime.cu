@@ -443,12 +443,13 @@ int plan_dense_layer(dp_model* m, const BlobOp& op, int img0, int B, Launch& L) 
   if (p.n_safe_chunks > p.n_chunks) p.n_safe_chunks = p.n_chunks;
   p.pro_scale = a.pro_scale; p.pro_shift = a.pro_shift; p.mid_shift = a.epi_shift;
   p.out = buf_at(op.in_buf);
-  const int budget = 227 * 1024 - DenseLayerSmem::kBarBytes - kDlTBytes - 2 * p.n_chunks * 64 * 4 - 128 * 4 -
-                     4 * kEpiStageBytes - 1024;
-  p.a_stages = 3; p.b_stages = 3;
-  while (p.a_stages * kDlAStage + p.b_stages * kDlBStage > budget && p.a_stages > 2) --p.a_stages;
-  while (p.a_stages * kDlAStage + p.b_stages * kDlBStage > budget && p.b_stages > 2) --p.b_stages;
-  if (p.a_stages * kDlAStage + p.b_stages * kDlBStage > budget) return fail("dense layer: shared memory budget exceeded");
+  const int budget = 227 * 1024 - DenseLayerSmem::kBarBytes - kDlTBytes - 2 * p.n_chunks * 64 * 4 - 128 * 4 - 1024 -
+                     10 * 1024;   // the last A stage's M-block over-read must stay inside the allocation
+  const int a_stage = dl_a_stage(p.rh);
+  p.a_stages = 4; p.b_stages = 4;
+  while (p.a_stages * a_stage + p.b_stages * kDlBStage > budget && p.a_stages > 2) --p.a_stages;
+  while (p.a_stages * a_stage + p.b_stages * kDlBStage > budget && p.b_stages > 2) --p.b_stages;
+  if (p.a_stages * a_stage + p.b_stages * kDlBStage > budget) return fail("dense layer: shared memory budget exceeded");
   L.smem = dense_layer_smem(p).total;
   const int rounds = (p.n_items + m->num_sms - 1) / m->num_sms;
   L.grid = (p.n_items + rounds - 1) / rounds;
@@ -522,6 +523,21 @@ int grid_for(long long total, int threads) {
   return (int)(g < 1 ? 1 : (g > cap ? cap : g));
 }
 
+template <typename... KArgs, typename... Args>
+cudaError_t launch_pdl(void (*kernel)(KArgs...), int grid, int block, cudaStream_t st, bool pdl, Args... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof cfg);
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(block);
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 int run_op(dp_model* m, SubPlan* sp, int i, cudaStream_t st) {
   const BlobOp& op = m->ops[i];
   Launch& L = sp->launches[i];
@@ -544,7 +560,9 @@ int run_op(dp_model* m, SubPlan* sp, int i, cudaStream_t st) {
       const BlobBuf& ob = m->bufs[op.out_buf];
       if (ob.C != 64 || ob.H != m->patch / 2) return fail("stem s2d buffer must be [P/2][P/2][64]");
       const long long total = (long long)B * ob.H * ob.W * 4;
-      dp::stem_s2d_kernel<<<grid_for(total, 256), 256, 0, st>>>(m->pass_dev, img0, B, m->patch, buf_at(op.out_buf));
+      cudaError_t le = launch_pdl(dp::stem_s2d_kernel, grid_for(total, 256), 256, st, m->use_pdl != 0, m->pass_dev, img0, B,
+                                  m->patch, buf_at(op.out_buf));
+      if (le != cudaSuccess) return fail("stem launch failed: %s", cudaGetErrorString(le));
       LAUNCH_OK();
       return 0;
     }
@@ -552,9 +570,10 @@ int run_op(dp_model* m, SubPlan* sp, int i, cudaStream_t st) {
       const BlobBuf& ib = m->bufs[op.in_buf];
       const BlobBuf& ob = m->bufs[op.out_buf];
       const long long total = (long long)B * (ib.H / 2) * (ib.W / 2) * (op.cin / 8);
-      dp::maxpool3s2_kernel<<<grid_for(total, 256), 256, 0, st>>>(buf_at(op.in_buf), ib.C, op.in_choff,
-                                                                  buf_at(op.out_buf), ob.C, op.out_choff, B, ib.H,
-                                                                  ib.W, op.cin);
+      cudaError_t le = launch_pdl(dp::maxpool3s2_kernel, grid_for(total, 256), 256, st, m->use_pdl != 0,
+                                  buf_at(op.in_buf), ib.C, op.in_choff, buf_at(op.out_buf), ob.C, op.out_choff, B, ib.H,
+                                  ib.W, op.cin);
+      if (le != cudaSuccess) return fail("maxpool launch failed: %s", cudaGetErrorString(le));
       LAUNCH_OK();
       return 0;
     }
@@ -563,9 +582,11 @@ int run_op(dp_model* m, SubPlan* sp, int i, cudaStream_t st) {
       const BlobBuf& ob = m->bufs[op.out_buf];
       const int OH = op.pool ? ib.H / 2 : ib.H, OW = op.pool ? ib.W / 2 : ib.W;
       const long long total = (long long)B * OH * OW * (op.cin / 8);
-      dp::bn_act_pool_kernel<<<grid_for(total, 256), 256, 0, st>>>(
-          buf_at(op.in_buf), ib.C, op.in_choff, buf_at(op.out_buf), ob.C, op.out_choff, B, ib.H, ib.W, op.cin,
-          dptr<float>(m, op.epi_scale_off), dptr<float>(m, op.epi_shift_off), op.relu, op.pool);
+      cudaError_t le = launch_pdl(dp::bn_act_pool_kernel, grid_for(total, 256), 256, st, m->use_pdl != 0,
+                                  buf_at(op.in_buf), ib.C, op.in_choff, buf_at(op.out_buf), ob.C, op.out_choff, B, ib.H,
+                                  ib.W, op.cin, dptr<float>(m, op.epi_scale_off), dptr<float>(m, op.epi_shift_off),
+                                  op.relu, op.pool);
+      if (le != cudaSuccess) return fail("bn/pool launch failed: %s", cudaGetErrorString(le));
       LAUNCH_OK();
       return 0;
     }
