@@ -24,8 +24,8 @@
 // chunk that contains the preceding layer's 32 new channels; older chunks are consumed while that layer runs.
 //
 // Warp roles: 0 = TMA producer (activation halo chunks), 1 = MMA issuer, 2 = TMEM allocator, 3 = TMA producer
-// (W1 chunks / W2 tap groups, one ring, in MMA order), 4-7 = epilogue (mid + final), 8-15 = pre-activation
-// transform (BN terms of a thread's 8 channels stay in registers).
+// (W1 chunks / W2 tap groups, one ring, in MMA order), 4-7 and 16-19 = epilogue (mid + final), 8-15 =
+// pre-activation transform (BN terms of a thread's 8 channels stay in registers).
 #pragma once
 #include "conv_tc.cuh"
 
@@ -95,7 +95,7 @@ __device__ __forceinline__ void dl_trace_close(unsigned long long* trace, const 
 }
 
 template <int RH>
-__global__ void __launch_bounds__(512, 1)
+__global__ void __launch_bounds__(640, 1)
 dense_layer_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w1,
                    const __grid_constant__ CUtensorMap map_w2, const __grid_constant__ DenseLayerParams p) {
   constexpr int kRows = dl_rows(RH), kMBlk = (kRows + 127) / 128, kAStage = dl_a_stage(RH);
@@ -144,12 +144,12 @@ dense_layer_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
       mbar_init(&b_empty[i], 1);
     }
     mbar_init(acc1_full, 1);
-    mbar_init(acc1_empty, 128);
+    mbar_init(acc1_empty, 256);
     for (int i = 0; i < 2; ++i) {
-      mbar_init(&t_ready[i], 128);
+      mbar_init(&t_ready[i], 256);
       mbar_init(&t_empty[i], 1);
       mbar_init(&acc2_full[i], 1);
-      mbar_init(&acc2_empty[i], 128);
+      mbar_init(&acc2_empty[i], 256);
     }
     fence_barrier_init();
   }
@@ -324,12 +324,16 @@ dense_layer_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
       }
       dl_trace_close(p.trace, tc, 1);
     }
-  } else if (warp >= 4 && warp < 8) {
+  } else if ((warp >= 4 && warp < 8) || warp >= 16) {
     // ------------------------------------------------------------------ epilogue warps: mid + final
+    // Two groups of four warps (a warp may only touch TMEM lanes 32 (w % 4) .. +31): group 0 (warps 4-7) takes
+    // bottleneck channels 0-63 and output channels 0-15, group 1 (warps 16-19) channels 64-127 and 16-31.  The
+    // mid step sits on the acc1 -> T -> acc1 critical loop of the item pipeline, hence eight warps.
     const int q = warp & 3;
+    const int half = (warp >= 16) ? 1 : 0;
     const int r = q * 32 + lane;
     DlTrace tc;
-    if (r == 0) tc = dl_trace_open(p.trace, 2);
+    if (r == 0 && half == 0) tc = dl_trace_open(p.trace, 2);
     // ---- mid(k): acc1 -> +shift -> ReLU -> zero padding -> fp16 -> swizzled operand tile T[k & 1]
     auto mid = [&](int k) {
       const int item = first + k * gridDim.x;
@@ -350,7 +354,7 @@ dense_layer_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
         const bool inside = prow < kRows && ih >= 0 && ih < p.H && iw >= 0 && iw < p.W;
         const uint32_t taddr = acc1_col + mb * 128 + (static_cast<uint32_t>(q * 32) << 16);
 #pragma unroll 1
-        for (int cc = 0; cc < 128; cc += 32) {
+        for (int cc = half * 64; cc < half * 64 + 64; cc += 32) {
           uint32_t v[2][16];
           tmem_ld16(taddr + cc, v[0]);
           tmem_ld16(taddr + cc + 16, v[1]);
@@ -396,20 +400,18 @@ dense_layer_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
       const bool valid = (n0 < p.n_img) && ((r >> 3) < RH) && (h < p.H) && (w < p.W);
       const long long opix = (static_cast<long long>(n0) * p.H + h) * p.W + w;
       __half* orow = p.out + opix * p.out_ctot + p.out_choff;
-      uint32_t v[2][16];
-      const uint32_t taddr = acc2_col + tb * 32 + (static_cast<uint32_t>(q * 32) << 16);
-      tmem_ld16(taddr, v[0]);
-      tmem_ld16(taddr + 16, v[1]);
+      uint32_t v[16];
+      const uint32_t taddr = acc2_col + tb * 32 + half * 16 + (static_cast<uint32_t>(q * 32) << 16);
+      tmem_ld16(taddr, v);
       tmem_ld_wait();
-#pragma unroll
-      for (int hsel = 0; hsel < 2; ++hsel) {
+      {
         uint32_t pk[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-          __half2 h2 = __floats2half2_rn(__uint_as_float(v[hsel][2 * i]), __uint_as_float(v[hsel][2 * i + 1]));
+          __half2 h2 = __floats2half2_rn(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1]));
           pk[i] = *reinterpret_cast<uint32_t*>(&h2);
         }
-        if (valid) st_global_v8(orow + 16 * hsel, pk);
+        if (valid) st_global_v8(orow + 16 * half, pk);
       }
       tc_fence_before();
       mbar_arrive(&acc2_empty[tb]);
@@ -420,7 +422,7 @@ dense_layer_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
       if (k + 1 < n_local) mid(k + 1);
       fin(k);
     }
-    if (r == 0) dl_trace_close(p.trace, tc, 2);
+    if (r == 0 && half == 0) dl_trace_close(p.trace, tc, 2);
   } else if (warp >= 8) {
     // ------------------------------------------------------------------ pre-activation BN + ReLU on the halo rows
     const int t = tid - 256;

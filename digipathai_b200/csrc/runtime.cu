@@ -655,7 +655,7 @@ int run_op(dp_model* m, SubPlan* sp, int i, cudaStream_t st) {
       cudaLaunchConfig_t cfg;
       memset(&cfg, 0, sizeof cfg);
       cfg.gridDim = dim3(L.grid);
-      cfg.blockDim = dim3(512);
+      cfg.blockDim = dim3(640);
       cfg.dynamicSmemBytes = L.smem;
       cfg.stream = st;
       cudaLaunchAttribute attr[1];
