@@ -66,11 +66,10 @@ __global__ void stem_s2d_kernel(const PassDesc* __restrict__ pass, int img0, int
   const int* __restrict__ coords = pass->coords + 2 * img0;
   const int tta_code = pass->tta_in;
   const int OH = P / 2;
-  const long long total = static_cast<long long>(B) * OH * OH * 4;
-  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
-       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+  const unsigned total = static_cast<unsigned>(B) * OH * OH * 4;   // < 2^31 for any supported batch / patch
+  for (unsigned idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
     const int dq = idx & 3;
-    long long r0 = idx >> 2;
+    unsigned r0 = idx >> 2;
     const int q = r0 % OH; r0 /= OH;
     const int r = r0 % OH;
     const int b = r0 / OH;
@@ -92,7 +91,7 @@ __global__ void stem_s2d_kernel(const PassDesc* __restrict__ pass, int img0, int
             vals[(a * 2 + b2) * 3 + c] = __float2half_rn((static_cast<float>(px[c]) - 128.f) * (1.f / 128.f));
         }
     }
-    uint4* dst = reinterpret_cast<uint4*>(out + idx * 16);
+    uint4* dst = reinterpret_cast<uint4*>(out + static_cast<size_t>(idx) * 16);
     dst[0] = reinterpret_cast<const uint4*>(vals)[0];
     dst[1] = reinterpret_cast<const uint4*>(vals)[1];
   }
@@ -106,11 +105,10 @@ __global__ void maxpool3s2_kernel(const __half* __restrict__ in, int in_ctot, in
   pdl_wait();               // launched with programmatic stream serialization: inputs complete from here
   pdl_launch_dependents();
   const int OH = H / 2, OW = W / 2, CG = C / 8;
-  const long long total = static_cast<long long>(n_img) * OH * OW * CG;
-  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
-       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+  const unsigned total = static_cast<unsigned>(n_img) * OH * OW * CG;
+  for (unsigned idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
     const int cg = idx % CG;
-    long long r = idx / CG;
+    unsigned r = idx / CG;
     const int ow = r % OW; r /= OW;
     const int oh = r % OH;
     const int n = r / OH;
@@ -153,11 +151,10 @@ __global__ void bn_act_pool_kernel(const __half* __restrict__ in, int in_ctot, i
   pdl_wait();               // launched with programmatic stream serialization: inputs complete from here
   pdl_launch_dependents();
   const int OH = pool ? H / 2 : H, OW = pool ? W / 2 : W, CG = C / 8;
-  const long long total = static_cast<long long>(n_img) * OH * OW * CG;
-  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
-       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+  const unsigned total = static_cast<unsigned>(n_img) * OH * OW * CG;
+  for (unsigned idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
     const int cg = idx % CG;
-    long long r = idx / CG;
+    unsigned r = idx / CG;
     const int ow = r % OW; r /= OW;
     const int oh = r % OH;
     const int n = r / OH;

@@ -58,6 +58,8 @@ struct ConvParams {
   int a_stage_bytes, b_stage_bytes, a_stages, b_stages, acc_stages, a_tx_bytes;
   int b_group;              // tap entries carried by one B stage (TMA box depth)
   int halo_top;             // MODE_H: rows of halo above the region (1 for 3x3 / up2, 2 for the 4x4 stem)
+  int b_resident;           // 1: all weight tiles of the layer are loaded once per CTA and stay in shared memory
+                            //    (stage c holds every tap of channel chunk c); no re-streaming from L2 per item
   int epi_direct;           // 1: epilogue stores 32-byte vectors straight from registers (no smem staging)
   int epi_mode, relu;
   int out_ctot, out_choff;  // output NHWC buffer: channel stride and channel offset (elements)
@@ -307,16 +309,26 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     // ------------------------------------------------------------------ TMA producer: weights (B ring)
     if (elect_one()) {
       uint32_t sb = 0, pb = 0;
-      for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
-        const int rest = item / p.n_mtiles;
-        const int n0 = (rest % p.n_ntiles) * p.n_tile;
-        const int ebase = (rest / p.n_ntiles) * p.n_entries;
-        for (int c = 0; c < p.n_chunks; ++c) {
-          for (int g = 0; g < n_bgroups; ++g) {
-            mbar_wait(&b_empty[sb], pb ^ 1);
-            mbar_expect_tx(&b_full[sb], p.b_stage_bytes);
-            tma_load_3d(&map_b, &b_full[sb], b_base + sb * p.b_stage_bytes, c * 64, n0, ebase + g * p.b_group);
-            if (++sb == p.b_stages) { sb = 0; pb ^= 1; }
+      if (p.b_resident) {
+        // Weight-stationary: the high-resolution decoder layers are L2->SM bandwidth bound when every CTA
+        // re-streams the layer's weights for every 128/256-pixel item; when they fit, load them exactly once.
+        if (blockIdx.x < p.n_items)
+          for (int c = 0; c < p.n_chunks; ++c) {
+            mbar_expect_tx(&b_full[c], p.b_stage_bytes);
+            tma_load_3d(&map_b, &b_full[c], b_base + c * p.b_stage_bytes, c * 64, 0, 0);
+          }
+      } else {
+        for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+          const int rest = item / p.n_mtiles;
+          const int n0 = (rest % p.n_ntiles) * p.n_tile;
+          const int ebase = (rest / p.n_ntiles) * p.n_entries;
+          for (int c = 0; c < p.n_chunks; ++c) {
+            for (int g = 0; g < n_bgroups; ++g) {
+              mbar_wait(&b_empty[sb], pb ^ 1);
+              mbar_expect_tx(&b_full[sb], p.b_stage_bytes);
+              tma_load_3d(&map_b, &b_full[sb], b_base + sb * p.b_stage_bytes, c * 64, n0, ebase + g * p.b_group);
+              if (++sb == p.b_stages) { sb = 0; pb ^= 1; }
+            }
           }
         }
       }
@@ -339,6 +351,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       const uint32_t n_tile = p.n_tile, sub = p.sub, bgroup = p.b_group;
       const uint32_t d_group_stride = sub * n_tile;
       uint32_t sa = 0, pa = 0, sb = 0, pb = 0, as = 0, ap = 0;
+      bool b_loaded = false;
       for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
         mbar_wait(&acc_empty[as], ap ^ 1);
         tc_fence_after();
@@ -361,7 +374,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
               mbar_wait(&a_full[sa], pa);
               a_stage_desc = a_desc0 + sa * a_stage_u;
             }
-            mbar_wait(&b_full[sb], pb);
+            if (p.b_resident) {
+              sb = c;                                   // stage c == channel chunk c, filled once
+              if (!b_loaded) mbar_wait(&b_full[sb], 0);
+            } else {
+              mbar_wait(&b_full[sb], pb);
+            }
             tc_fence_after();
             trace_ev(tc, 2, item);
             uint64_t b_desc = b_desc0 + sb * b_stage_u;
@@ -391,8 +409,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                     umma_f16_ss(d, a_desc + 2 * k, b_desc + 2 * k, idesc, k ? 1u : flag0);
               }
             }
-            umma_commit(&b_empty[sb]);
-            if (++sb == p.b_stages) { sb = 0; pb ^= 1; }
+            if (!p.b_resident) {
+              umma_commit(&b_empty[sb]);
+              if (++sb == p.b_stages) { sb = 0; pb ^= 1; }
+            }
             if (MODE == MODE_T) {
               umma_commit(&a_empty[sa]);
               if (++sa == p.a_stages) { sa = 0; pa ^= 1; }
@@ -403,6 +423,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             if (++sa == p.a_stages) { sa = 0; pa ^= 1; }
           }
         }
+        b_loaded = true;
         umma_commit(&acc_full[as]);
         trace_ev(tc, 3, item);
         if (++as == p.acc_stages) { as = 0; ap ^= 1; }

@@ -147,7 +147,7 @@ struct dp_model {
   __half* scratch_head = nullptr;  // naive path: output of the head-fused conv
   uint64_t device_bytes = 0;
   int naive_conv = 0, desc_base_mode = 0, halo_pad8 = 0, profile = 0;
-  int use_graph = 1, split = 1, use_pdl = 1, epi_direct = 1, use_overlap = 1;
+  int use_graph = 1, split = 1, use_pdl = 1, epi_direct = 1, use_overlap = 1, b_resident = 1;
   unsigned long long* gt_dev = nullptr;     // debug: per-op %globaltimer stamps (option "stamp")
   int stamp = 0;
   unsigned long long* trace_dev = nullptr;  // debug timeline buffer (option "trace_op")
@@ -337,17 +337,30 @@ int plan_conv(dp_model* m, const BlobOp& op, int img0, int B, Launch& L) {
     for (int g = p.n_entries; g >= 1; --g)
       if (p.n_entries % g == 0 && g * n_tile * 128 <= 36 * 1024) { p.b_group = g; break; }
   p.b_stage_bytes = p.b_group * n_tile * 128;
+  // weight-stationary when the whole layer fits beside the activation ring
+  p.b_resident = 0;
+  if (m->b_resident && p.mode != MODE_T && p.n_ntiles == 1 && p.n_phase_items == 1 && p.n_chunks <= kMaxBStages &&
+      (long long)p.n_chunks * p.n_entries * n_tile * 128 <= 96 * 1024) {
+    p.b_resident = 1;
+    p.b_group = p.n_entries;
+    p.b_stage_bytes = p.n_entries * n_tile * 128;
+  }
   p.acc_stages = (2 * p.n_groups * p.sub * n_tile <= kTmemCols) ? 2 : 1;
 
   // shared-memory ring depths
   const int budget = 227 * 1024 - ConvSmemLayout::kBarBytes - 2 * op.cout * 4 - 2 * p.n_chunks * 64 * 4 - 256 * 4 -
                      4 * kEpiStageBytes - 1024;
   int a_stages = (p.mode == MODE_H) ? 2 : 4;
-  while (a_stages > 1 && a_stages * p.a_stage_bytes + 2 * p.b_stage_bytes > budget) --a_stages;
+  const int b_min = p.b_resident ? p.n_chunks : 2;
+  while (a_stages > 1 && a_stages * p.a_stage_bytes + b_min * p.b_stage_bytes > budget) --a_stages;
   int b_stages = (budget - a_stages * p.a_stage_bytes) / p.b_stage_bytes;
   if (b_stages > kMaxBStages) b_stages = kMaxBStages;
   if (p.mode != MODE_H && b_stages > 6) b_stages = 6;
-  if (b_stages < 2) return fail("conv: shared memory budget exceeded (A %d B %d)", p.a_stage_bytes, p.b_stage_bytes);
+  if (p.b_resident) {
+    if (b_stages < p.n_chunks) return fail("conv: resident weights do not fit (%d stages of %d B)", p.n_chunks, p.b_stage_bytes);
+    b_stages = p.n_chunks;
+  }
+  if (b_stages < 2 && !p.b_resident) return fail("conv: shared memory budget exceeded (A %d B %d)", p.a_stage_bytes, p.b_stage_bytes);
   // spend what is left on deeper A rings for the flat modes
   if (p.mode != MODE_H) {
     while (a_stages < kMaxAStages && (a_stages + 1) * p.a_stage_bytes + b_stages * p.b_stage_bytes <= budget &&
@@ -822,6 +835,15 @@ int dp_model_set_option(dp_model* m, const char* key, int value) {
     if (!m->gt_dev) CU_OK(cudaMalloc(&m->gt_dev, 2 * m->ops.size() * sizeof(unsigned long long)));
     CU_OK(cudaMemset(m->gt_dev, 0, 2 * m->ops.size() * sizeof(unsigned long long)));
     m->stamp = value;
+  }
+  else if (!strcmp(key, "b_resident")) {
+    std::lock_guard<std::mutex> lk(m->mu);
+    m->b_resident = value;
+    for (auto& kv : m->plans) {
+      if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
+      if (kv.second.graph) cudaGraphDestroy(kv.second.graph);
+    }
+    m->plans.clear();
   }
   else if (!strcmp(key, "use_overlap")) {
     std::lock_guard<std::mutex> lk(m->mu);

@@ -85,6 +85,66 @@ def level0_xy_raster(slide) -> np.ndarray:
     return np.ascontiguousarray(np.transpose(arr, (1, 0, 2)))
 
 
+class DeviceSlide:
+    """Slide whose level-0 raster already lives in HBM as ``uint8 [W, H, 3]`` ([x, y, c], the layout the stem
+    gather reads).  OpenSlide-shaped like ``ArraySlide`` (virtual stride-2**k pyramid); ``read_region`` copies
+    only the requested (sub-sampled) window back to the host -- the tissue mask needs the lowest level only.
+    """
+
+    def __init__(self, raster_xy, n_levels: int = 1):
+        assert raster_xy.is_cuda and raster_xy.dim() == 3 and raster_xy.shape[2] == 3
+        self.raster_xy = raster_xy
+        W, H = int(raster_xy.shape[0]), int(raster_xy.shape[1])
+        self.level_count = int(n_levels)
+        self.level_downsamples = tuple(float(2 ** k) for k in range(n_levels))
+        self.level_dimensions = tuple((W // 2 ** k, H // 2 ** k) for k in range(n_levels))
+        self.dimensions = self.level_dimensions[0]
+
+    def read_region(self, location, level, size) -> np.ndarray:
+        x, y = int(location[0]), int(location[1])
+        w, h = int(size[0]), int(size[1])
+        s = 2 ** int(level)
+        lvl = self.raster_xy[::s, ::s]
+        lx, ly = x // s, y // s
+        out = np.zeros((h, w, 3), dtype=np.uint8)
+        W, H = lvl.shape[0], lvl.shape[1]
+        x0, y0, x1, y1 = max(lx, 0), max(ly, 0), min(lx + w, W), min(ly + h, H)
+        if x1 > x0 and y1 > y0:
+            win = lvl[x0:x1, y0:y1].permute(1, 0, 2).contiguous().cpu().numpy()
+            out[y0 - ly:y1 - ly, x0 - lx:x1 - lx] = win
+        return out
+
+    def close(self):
+        pass
+
+
+def synthetic_slide_device(width: int, height: int, device, seed: int = 0, n_levels: int = 1, n_blobs: int = 4):
+    """``synthetic_slide`` generated directly in HBM (same recipe, torch RNG instead of numpy's, so the pixels
+    differ from the host version): white background 240+-3, elliptical tissue (170, 90, 160)+-20."""
+    import torch
+    rng = np.random.default_rng(seed)
+    cy = rng.uniform(0.25, 0.75, n_blobs) * height
+    cx = rng.uniform(0.25, 0.75, n_blobs) * width
+    ry = rng.uniform(0.18, 0.30, n_blobs) * height
+    rx = rng.uniform(0.18, 0.30, n_blobs) * width
+    g = torch.Generator(device=device)
+    g.manual_seed(seed)
+    out = torch.empty((width, height, 3), dtype=torch.uint8, device=device)
+    ys = torch.arange(height, dtype=torch.float32, device=device)[None, :]
+    tissue = torch.tensor([170.0, 90.0, 160.0], device=device)
+    step = 2048
+    for x0 in range(0, width, step):
+        x1 = min(width, x0 + step)
+        xs = torch.arange(x0, x1, dtype=torch.float32, device=device)[:, None]
+        inside = torch.zeros((x1 - x0, height), dtype=torch.bool, device=device)
+        for k in range(n_blobs):
+            inside |= ((ys - cy[k]) / ry[k]) ** 2 + ((xs - cx[k]) / rx[k]) ** 2 <= 1.0
+        noise = torch.randn((x1 - x0, height, 3), generator=g, device=device)
+        blk = torch.where(inside[..., None], tissue + 20.0 * noise, 240.0 + 3.0 * noise)
+        out[x0:x1] = blk.round_().clamp_(0, 255).to(torch.uint8)
+    return DeviceSlide(out, n_levels)
+
+
 def upload_xy_raster(slide, x_lo: int, x_hi: int, device, rows_per_chunk: int = 4096):
     """Level-0 stripe ``[x_lo, x_hi)`` as a CUDA ``uint8 [x, y, c]`` tensor (the layout the stem gather reads).
 
@@ -92,6 +152,10 @@ def upload_xy_raster(slide, x_lo: int, x_hi: int, device, rows_per_chunk: int = 
     (dataloader.py:357-358) happens once, on the device, while the raster is uploaded in row chunks.
     """
     import torch
+    if isinstance(slide, DeviceSlide):
+        if slide.raster_xy.device != torch.device(device):
+            return slide.raster_xy[x_lo:x_hi].to(device)
+        return slide.raster_xy[x_lo:x_hi]      # contiguous row slice of the resident raster: no copy
     W, H = slide.level_dimensions[0]
     out = torch.empty((x_hi - x_lo, H, 3), dtype=torch.uint8, device=device)
     for y0 in range(0, H, rows_per_chunk):
