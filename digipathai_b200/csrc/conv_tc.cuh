@@ -58,6 +58,9 @@ struct ConvParams {
   int a_stage_bytes, b_stage_bytes, a_stages, b_stages, acc_stages, a_tx_bytes;
   int b_group;              // tap entries carried by one B stage (TMA box depth)
   int halo_top;             // MODE_H: rows of halo above the region (1 for 3x3 / up2, 2 for the 4x4 stem)
+  int b_pair;               // 1: launched as 2-CTA clusters; each CTA fetches half of every weight tile and TMA
+                            //    multicasts it to both (halves the L2->SM weight traffic that bounds the
+                            //    high-resolution decoder layers)
   int b_resident;           // 1: all weight tiles of the layer are loaded once per CTA and stay in shared memory
                             //    (stage c holds every tap of channel chunk c); no re-streaming from L2 per item
   int epi_direct;           // 1: epilogue stores 32-byte vectors straight from registers (no smem staging)
@@ -222,7 +225,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     }
     for (int i = 0; i < p.b_stages; ++i) {
       mbar_init(&b_full[i], 1);
-      mbar_init(&b_empty[i], 1);
+      mbar_init(&b_empty[i], p.b_pair ? 2 : 1);
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&acc_full[i], 1);
@@ -260,6 +263,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  if (p.b_pair) cluster_sync_all();   // peer's barriers are initialised before anything remote can arrive on them
   pdl_wait();               // activations written by the previous layer are complete and visible from here on
   // Trigger only AFTER our own wait: a dependent that starts now can rely on every kernel before this one
   // being complete (dense_layer_kernel reads older channels of the concat buffer ahead of its own wait).
@@ -317,6 +321,29 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             mbar_expect_tx(&b_full[c], p.b_stage_bytes);
             tma_load_3d(&map_b, &b_full[c], b_base + c * p.b_stage_bytes, c * 64, 0, 0);
           }
+      } else if (p.b_pair) {
+        // CTA pair: both CTAs walk the same (n-tile, phase, chunk, tap) sequence on neighbouring M tiles.  Each
+        // fetches rows [rank * N/2, +N/2) of every tap's weight tile and multicasts them into both CTAs, so the
+        // pair pulls each weight byte out of L2 once.  A slot is refilled only after BOTH MMA warps released it
+        // (b_empty counts 2, arrived by multicast tcgen05.commit).
+        const uint32_t rank = cluster_ctarank();
+        const int half_rows = p.n_tile >> 1;
+        for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+          const int rest = item / p.n_mtiles;
+          const int n0 = (rest % p.n_ntiles) * p.n_tile;
+          const int ebase = (rest / p.n_ntiles) * p.n_entries;
+          for (int c = 0; c < p.n_chunks; ++c) {
+            for (int g = 0; g < n_bgroups; ++g) {
+              mbar_wait(&b_empty[sb], pb ^ 1);
+              mbar_expect_tx(&b_full[sb], p.b_stage_bytes);
+              uint8_t* dst = b_base + sb * p.b_stage_bytes + rank * half_rows * 128;
+              for (int j = 0; j < p.b_group; ++j)
+                tma_load_3d_mcast(&map_b, &b_full[sb], dst + j * p.n_tile * 128, c * 64, n0 + rank * half_rows,
+                                  ebase + g * p.b_group + j, 3);
+              if (++sb == p.b_stages) { sb = 0; pb ^= 1; }
+            }
+          }
+        }
       } else {
         for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
           const int rest = item / p.n_mtiles;
@@ -410,7 +437,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
               }
             }
             if (!p.b_resident) {
-              umma_commit(&b_empty[sb]);
+              if (p.b_pair) umma_commit_mcast(&b_empty[sb], 3);
+              else umma_commit(&b_empty[sb]);
               if (++sb == p.b_stages) { sb = 0; pb ^= 1; }
             }
             if (MODE == MODE_T) {
@@ -668,6 +696,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 
   tc_fence_before();
   __syncthreads();
+  if (p.b_pair) cluster_sync_all();   // do not exit while the peer may still multicast into this CTA
   if (warp == 2) {
     tc_fence_after();
     tmem_dealloc(tmem_base, kTmemCols);

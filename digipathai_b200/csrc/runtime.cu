@@ -147,7 +147,7 @@ struct dp_model {
   __half* scratch_head = nullptr;  // naive path: output of the head-fused conv
   uint64_t device_bytes = 0;
   int naive_conv = 0, desc_base_mode = 0, halo_pad8 = 0, profile = 0;
-  int use_graph = 1, split = 1, use_pdl = 1, epi_direct = 1, use_overlap = 1, b_resident = 1;
+  int use_graph = 1, split = 1, use_pdl = 1, epi_direct = 1, use_overlap = 1, b_resident = 1, b_pair = 0;
   unsigned long long* gt_dev = nullptr;     // debug: per-op %globaltimer stamps (option "stamp")
   int stamp = 0;
   unsigned long long* trace_dev = nullptr;  // debug timeline buffer (option "trace_op")
@@ -306,7 +306,9 @@ int plan_conv(dp_model* m, const BlobOp& op, int img0, int B, Launch& L) {
     int sub = (W % 16 == 0) ? 2 : 1;
     while (sub > 1 && (p.n_groups * sub * n_tile > kTmemCols)) sub >>= 1;
     // prefer two accumulator stages (epilogue of item i overlaps the MMAs of item i+1) over a wider region
-    if (sub == 2 && 2 * p.n_groups * sub * n_tile > kTmemCols && 2 * p.n_groups * n_tile <= kTmemCols) sub = 1;
+    if (sub == 2 && 2 * p.n_groups * sub * n_tile > kTmemCols && 2 * p.n_groups * n_tile <= kTmemCols &&
+        !getenv("DP_PREFER_SUB2"))
+      sub = 1;
     // prefer more CTAs over wider regions when the layer cannot fill the GPU
     if (sub == 2 && (long long)B * (H / 16) * (W / 16) * p.n_ntiles < m->num_sms) sub = 1;
     p.sub = sub;
@@ -373,6 +375,14 @@ int plan_conv(dp_model* m, const BlobOp& op, int img0, int B, Launch& L) {
   if (L.smem > 227 * 1024) return fail("conv: smem %d too large", L.smem);
   const int rounds = (p.n_items + m->num_sms - 1) / m->num_sms;
   L.grid = (p.n_items + rounds - 1) / rounds;
+  // CTA pairs with multicast weights: worthwhile where weights are re-streamed per item (not resident) and there
+  // is more than one item per CTA; needs lock-step pairs (even items / M tiles / grid) and 1 KB-aligned halves.
+  p.b_pair = 0;
+  if (m->b_pair && !p.b_resident && p.mode != MODE_T && p.n_items % 2 == 0 && p.n_mtiles % 2 == 0 && n_tile % 16 == 0 &&
+      p.n_items >= 2 * m->num_sms) {
+    p.b_pair = 1;
+    if (L.grid % 2) L.grid -= 1;
+  }
 
   // executed MACs (tensor-core work actually issued, 16-wide K steps)
   {
@@ -402,6 +412,7 @@ int plan_conv(dp_model* m, const BlobOp& op, int img0, int B, Launch& L) {
     uint64_t dims[3] = {(uint64_t)op.cin, (uint64_t)op.cout, (uint64_t)n_entries_total};
     uint64_t str[2] = {(uint64_t)op.cin * 2, (uint64_t)op.cin * 2 * op.cout};
     uint32_t box[3] = {64, (uint32_t)n_tile, (uint32_t)p.b_group};
+    if (p.b_pair) { box[1] = (uint32_t)n_tile / 2; box[2] = 1; }
     if (make_map(&L.map_b, q.w, 3, dims, str, box)) return 1;
   }
   return 0;
@@ -630,11 +641,18 @@ int run_op(dp_model* m, SubPlan* sp, int i, cudaStream_t st) {
       cfg.blockDim = dim3(L.prologue ? 384 : 256);
       cfg.dynamicSmemBytes = L.smem;
       cfg.stream = st;
-      cudaLaunchAttribute attr[1];
+      cudaLaunchAttribute attr[2];
       attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
       attr[0].val.programmaticStreamSerializationAllowed = 1;
       cfg.attrs = attr;
       cfg.numAttrs = m->use_pdl ? 1 : 0;
+      if (cp.b_pair) {
+        attr[cfg.numAttrs].id = cudaLaunchAttributeClusterDimension;
+        attr[cfg.numAttrs].val.clusterDim.x = 2;
+        attr[cfg.numAttrs].val.clusterDim.y = 1;
+        attr[cfg.numAttrs].val.clusterDim.z = 1;
+        ++cfg.numAttrs;
+      }
       cudaError_t le;
       switch (cp.mode) {
         case dp::MODE_D:
@@ -836,9 +854,9 @@ int dp_model_set_option(dp_model* m, const char* key, int value) {
     CU_OK(cudaMemset(m->gt_dev, 0, 2 * m->ops.size() * sizeof(unsigned long long)));
     m->stamp = value;
   }
-  else if (!strcmp(key, "b_resident")) {
+  else if (!strcmp(key, "b_resident") || !strcmp(key, "b_pair")) {
     std::lock_guard<std::mutex> lk(m->mu);
-    m->b_resident = value;
+    if (!strcmp(key, "b_pair")) m->b_pair = value; else m->b_resident = value;
     for (auto& kv : m->plans) {
       if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
       if (kv.second.graph) cudaGraphDestroy(kv.second.graph);

@@ -109,6 +109,8 @@ uint64_t dp_kernel_launch_count(void);
  *          "use_pdl" (0/1, default 1: conv kernels use programmatic dependent launch),
  *          "use_overlap" (0/1, default 1: a dense layer consumes the channels older than its predecessor's output
  *                         before its grid-dependency wait, overlapping consecutive layers),
+ *          "b_pair" (0/1, default 0: 2-CTA clusters with TMA-multicast weight tiles; measured no gain on B200, where
+ *                    L2 already de-duplicates unicast requests of up to 4 neighbouring SMs -- kept for experiments),
  *          "b_resident" (0/1, default 1: layers whose weights fit keep them in shared memory for the whole kernel),
  *          "epi_direct" (0/1, default 1: epilogue writes 256-bit vectors from registers instead of staging in smem),
  *          "split" (default 1: number of sub-batches captured as parallel graph branches). */
