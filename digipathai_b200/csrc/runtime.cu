@@ -459,7 +459,13 @@ int plan_dense_layer(dp_model* m, const BlobOp& op, int img0, int B, Launch& L) 
   p.n_img = B; p.H = H; p.W = W; p.C = op.cin;
   p.n_chunks = (op.cin + 63) / 64;
   p.rh = 16;
-  if (H % 16 || (long long)B * (W / 8) * (H / 16) < m->num_sms) p.rh = 8;   // more, smaller regions when SMs would idle
+  {
+    // 8-row regions when 16-row regions would leave most SMs idle.  With cross-layer overlap a half-empty GPU is
+    // not wasted (the next layer's early chunks run on the free SMs), so the threshold is a tunable.
+    const char* env = getenv("DP_DL_MIN_ITEMS16");
+    const long long min_items = env ? atoll(env) : m->num_sms;
+    if (H % 16 || (long long)B * (W / 8) * (H / 16) < min_items) p.rh = 8;
+  }
   p.tiles_w = W / 8; p.tiles_h = H / p.rh;
   p.n_items = B * p.tiles_w * p.tiles_h;
   p.out_ctot = ib.C; p.out_choff = op.out_choff;
