@@ -161,6 +161,7 @@ def main():
     ap.add_argument("--epi-direct", action="store_true")
     ap.add_argument("--no-overlap", action="store_true")
     ap.add_argument("--no-pair", action="store_true")
+    ap.add_argument("--no-resident", action="store_true")
     ap.add_argument("--dump-ops", default="", help="write the per-op device-time table (instrumented pass) here")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -209,6 +210,8 @@ def main():
         model.set_option("use_overlap", 0)
     if args.no_pair:
         model.set_option("b_pair", 0)
+    if args.no_resident:
+        model.set_option("b_resident", 0)
 
     if args.workload == "slide":
         return run_slide(args, model, rank, world, local, dev, barrier, max_over_ranks, peaks, peak_src)
