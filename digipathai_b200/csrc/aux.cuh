@@ -98,10 +98,14 @@ __global__ void stem_s2d_kernel(const PassDesc* __restrict__ pass, int img0, int
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// ZeroPadding2D(1) + MaxPooling2D(3, strides=2) (densenet.py:122-123). 8 channels per thread.
+// mode 0: ZeroPadding2D(1) + MaxPooling2D(3, strides=2) (densenet.py:122-123): window starts at 2*o - 1 and the
+//         explicit zero padding takes part in the max.
+// mode 1: MaxPooling2D(3, strides=2, padding='same') (inception.py:178,182,211,231) on an even-sized map:
+//         TensorFlow pads 0 in front / 1 behind, window starts at 2*o, padded cells never win.
+// 8 channels per thread.
 __global__ void maxpool3s2_kernel(const __half* __restrict__ in, int in_ctot, int in_choff,
                                   __half* __restrict__ out, int out_ctot, int out_choff, int n_img, int H, int W,
-                                  int C) {
+                                  int C, int mode) {
   pdl_wait();               // launched with programmatic stream serialization: inputs complete from here
   pdl_launch_dependents();
   const int OH = H / 2, OW = W / 2, CG = C / 8;
@@ -117,8 +121,9 @@ __global__ void maxpool3s2_kernel(const __half* __restrict__ in, int in_ctot, in
     for (int t = 0; t < 8; ++t) m[t] = -INFINITY;
     for (int ky = 0; ky < 3; ++ky)
       for (int kx = 0; kx < 3; ++kx) {
-        const int ih = 2 * oh - 1 + ky, iw = 2 * ow - 1 + kx;
+        const int ih = 2 * oh - (mode ? 0 : 1) + ky, iw = 2 * ow - (mode ? 0 : 1) + kx;
         if (ih < 0 || ih >= H || iw < 0 || iw >= W) {
+          if (mode) continue;
 #pragma unroll
           for (int t = 0; t < 8; ++t) m[t] = fmaxf(m[t], 0.f);  // explicit zero padding takes part in the max
         } else {
@@ -138,6 +143,49 @@ __global__ void maxpool3s2_kernel(const __half* __restrict__ in, int in_ctot, in
     for (int t = 0; t < 4; ++t) o[t] = __floats2half2_rn(m[2 * t], m[2 * t + 1]);
     *reinterpret_cast<uint4*>(out + ((static_cast<long long>(n) * OH + oh) * OW + ow) * out_ctot + out_choff +
                               cg * 8) = *reinterpret_cast<const uint4*>(o);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// AveragePooling2D(3, strides=1, padding='same') (inception.py:193): mean over the VALID cells of the window.
+__global__ void avgpool3s1_kernel(const __half* __restrict__ in, int in_ctot, int in_choff,
+                                  __half* __restrict__ out, int out_ctot, int out_choff, int n_img, int H, int W,
+                                  int C) {
+  pdl_wait();
+  pdl_launch_dependents();
+  const int CG = C / 8;
+  const unsigned total = static_cast<unsigned>(n_img) * H * W * CG;
+  for (unsigned idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+    const int cg = idx % CG;
+    unsigned r = idx / CG;
+    const int ow = r % W; r /= W;
+    const int oh = r % H;
+    const int n = r / H;
+    float acc[8];
+#pragma unroll
+    for (int t = 0; t < 8; ++t) acc[t] = 0.f;
+    int cnt = 0;
+    for (int ky = -1; ky <= 1; ++ky)
+      for (int kx = -1; kx <= 1; ++kx) {
+        const int ih = oh + ky, iw = ow + kx;
+        if (ih < 0 || ih >= H || iw < 0 || iw >= W) continue;
+        ++cnt;
+        const uint4 raw = *reinterpret_cast<const uint4*>(
+            in + ((static_cast<long long>(n) * H + ih) * W + iw) * in_ctot + in_choff + cg * 8);
+        const __half2* hv = reinterpret_cast<const __half2*>(&raw);
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          const float2 f = __half22float2(hv[t]);
+          acc[2 * t] += f.x;
+          acc[2 * t + 1] += f.y;
+        }
+      }
+    const float inv = 1.f / static_cast<float>(cnt);
+    __align__(16) __half2 o[4];
+#pragma unroll
+    for (int t = 0; t < 4; ++t) o[t] = __floats2half2_rn(acc[2 * t] * inv, acc[2 * t + 1] * inv);
+    *reinterpret_cast<uint4*>(out + ((static_cast<long long>(n) * H + oh) * W + ow) * out_ctot + out_choff + cg * 8) =
+        *reinterpret_cast<const uint4*>(o);
   }
 }
 

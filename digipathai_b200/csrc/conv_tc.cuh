@@ -29,7 +29,7 @@ namespace dp {
 enum : int { MODE_D = 0, MODE_T = 1, MODE_H = 2 };
 enum : int { EPI_STORE = 0, EPI_HEAD = 1 };
 
-constexpr int kMaxEntries = 16;
+constexpr int kMaxEntries = 32;   // 5x5 taps; tap_first_mask is 32 bits
 constexpr int kMaxAStages = 8;
 constexpr int kMaxBStages = 16;
 constexpr int kTmemCols = 512;
@@ -46,6 +46,13 @@ struct TapEntry {
 struct ConvParams {
   int mode, sub, n_tile, n_ntiles;
   int n_img, H, W, Cin;  // input grid per image and channels visible through the A tensor map
+  int OH, OW;            // grid the work items tile: the output grid (== input grid for stride 1; for up2 the
+                         // low-resolution grid, the output being 2x that)
+  int stride;            // MODE_T only: input pixel = stride * output pixel + tap offset (TMA element strides)
+  int cout;              // true Cout; n_tile * n_ntiles may exceed it (weight rows beyond it are TMA zero fill,
+                         // the epilogue clips the store)
+  int residual;          // out = act(out_old + acc + shift): Inception-ResNet block tail (inception.py:152-160)
+  int halo_left;         // MODE_H: columns of halo left of the region
   int n_chunks;          // ceil(Cin / 64)
   int n_entries;         // tap entries per work item
   int n_groups;          // accumulator groups per work item
@@ -247,7 +254,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     for (int i0 = 0; i0 < cout || i0 < npro; i0 += blockDim.x) {
       const int i = i0 + tid;
       float es = 1.f, eh = 0.f, ps = 0.f, ph = 0.f, hw = 0.f;
-      if (i < cout) {
+      if (i < p.cout) {
         if (p.epi_scale) es = p.epi_scale[i];
         if (p.epi_shift) eh = p.epi_shift[i];
         if (head) hw = p.head_w[i];
@@ -290,7 +297,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
               for (int s = 0; s < p.sub; ++s)
                 tma_load_2d(&map_a, &a_full[sa], dst + s * kATileBytes, c0, wi.m0 + s * 128);
             } else {
-              tma_load_4d(&map_a, &a_full[sa], dst, c0, wi.w0 - 1, wi.h0 - p.halo_top, wi.n0);
+              tma_load_4d(&map_a, &a_full[sa], dst, c0, wi.w0 - p.halo_left, wi.h0 - p.halo_top, wi.n0);
             }
             trace_ev(tc, 1, item);
             if (++sa == p.a_stages) { sa = 0; pa ^= 1; }
@@ -299,8 +306,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
               const TapEntry ent = p.entries[ebase + g];
               mbar_wait(&a_empty[sa], pa ^ 1);
               mbar_expect_tx(&a_full[sa], p.a_tx_bytes);
-              tma_load_4d(&map_a, &a_full[sa], a_base + sa * p.a_stage_bytes, c0, wi.w0 + ent.dx,
-                          wi.h0 + ent.dy, wi.n0);
+              tma_load_4d(&map_a, &a_full[sa], a_base + sa * p.a_stage_bytes, c0, wi.w0 * p.stride + ent.dx,
+                          wi.h0 * p.stride + ent.dy, wi.n0);
               trace_ev(tc, 1, item);
               if (++sa == p.a_stages) { sa = 0; pa ^= 1; }
             }
@@ -499,13 +506,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
               h = wi.h0 + (r >> 3);
               n = wi.n0;
             }
-            valid = (n < p.n_img) && (h < p.H) && (w < p.W);
+            valid = (n < p.n_img) && (h < p.OH) && (w < p.OW);
             if (p.up2) {
               h = 2 * h + (ph >> 1);
               w = 2 * w + (ph & 1);
-              opix = (static_cast<long long>(n) * (2 * p.H) + h) * (2 * p.W) + w;
+              opix = (static_cast<long long>(n) * (2 * p.OH) + h) * (2 * p.OW) + w;
             } else {
-              opix = (static_cast<long long>(n) * p.H + h) * p.W + w;
+              opix = (static_cast<long long>(n) * p.OH + h) * p.OW + w;
             }
           }
           const uint32_t taddr =
@@ -538,16 +545,29 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           } else if (p.epi_direct) {
             // 32 columns per step: TMEM -> registers -> BN shift/ReLU -> fp16 -> two 256-bit stores per thread
             // (each a full 32-byte sector of this pixel's channel run); no shared-memory round trip.
-            for (int cc = 0; cc < p.n_tile; cc += 32) {
+            for (int cc = 0; cc < p.n_tile && ch0 + cc < p.cout; cc += 32) {
               uint32_t v[2][16];
+              const bool two = cc + 16 < p.n_tile && ch0 + cc + 16 < p.cout;
               tmem_ld16(taddr + cc, v[0]);
-              tmem_ld16(taddr + cc + 16, v[1]);
+              if (two) tmem_ld16(taddr + cc + 16, v[1]);
               tmem_ld_wait();
 #pragma unroll
               for (int hsel = 0; hsel < 2; ++hsel) {
+                if (hsel == 1 && !two) break;
                 const int cb = ch0 + cc + 16 * hsel;
                 float f[16];
-                epi_affine16(v[hsel], s_epi_scale + cb, s_epi_shift + cb, has_scale, p.relu != 0, f);
+                epi_affine16(v[hsel], s_epi_scale + cb, s_epi_shift + cb, has_scale, p.relu != 0 && !p.residual, f);
+                if (p.residual) {
+                  // the running tensor of the residual chain is updated in place: this thread owns these 16 values
+                  uint32_t old[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+                  if (valid) ld_global_v8(orow + cc + 16 * hsel, old);
+#pragma unroll
+                  for (int i = 0; i < 8; ++i) {
+                    const float2 o2 = __half22float2(*reinterpret_cast<const __half2*>(&old[i]));
+                    f[2 * i] += o2.x; f[2 * i + 1] += o2.y;
+                    if (p.relu) { f[2 * i] = fmaxf(f[2 * i], 0.f); f[2 * i + 1] = fmaxf(f[2 * i + 1], 0.f); }
+                  }
+                }
                 uint32_t pk[8];
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
@@ -711,6 +731,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 // tcgen05 path against an obviously-correct evaluation layer by layer without shipping tensors back.
 struct NaiveConvParams {
   int n_img, H, W, Cin, in_ctot, in_choff;
+  int OH, OW, stride, residual;
   int Cout, out_ctot, out_choff;
   int n_entries_total, n_groups, entries_per_group, up2;
   int relu, pro_mode;  // pro_mode: 0 none, 1 affine, 2 affine+relu
@@ -731,20 +752,20 @@ struct NaiveConvParams {
 };
 
 __global__ void conv_naive_kernel(const NaiveConvParams p) {
-  const long long total = static_cast<long long>(p.n_img) * p.H * p.W * p.n_groups * p.Cout;
+  const long long total = static_cast<long long>(p.n_img) * p.OH * p.OW * p.n_groups * p.Cout;
   for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
        idx += static_cast<long long>(gridDim.x) * blockDim.x) {
     const int co = idx % p.Cout;
     long long r = idx / p.Cout;
     const int g = r % p.n_groups; r /= p.n_groups;
-    const int w = r % p.W; r /= p.W;
-    const int h = r % p.H;
-    const int n = r / p.H;
+    const int w = r % p.OW; r /= p.OW;
+    const int h = r % p.OH;
+    const int n = r / p.OH;
     float acc = 0.f;
     for (int e = 0; e < p.n_entries_total; ++e) {
       const TapEntry ent = p.entries[e];
       if (ent.group != g) continue;
-      const int ih = h + ent.dy, iw = w + ent.dx;
+      const int ih = h * p.stride + ent.dy, iw = w * p.stride + ent.dx;
       if (ih < 0 || ih >= p.H || iw < 0 || iw >= p.W) continue;
       const __half* a = p.in + ((static_cast<long long>(n) * p.H + ih) * p.W + iw) * p.in_ctot + p.in_choff;
       const __half* wt = p.w + (static_cast<long long>(e) * p.Cout + co) * p.Cin;
@@ -759,12 +780,13 @@ __global__ void conv_naive_kernel(const NaiveConvParams p) {
       }
     }
     float y = fmaf(acc, p.epi_scale ? p.epi_scale[co] : 1.f, p.epi_shift ? p.epi_shift[co] : 0.f);
-    if (p.relu) y = fmaxf(y, 0.f);
     long long opix;
     if (p.up2)
       opix = (static_cast<long long>(n) * 2 * p.H + 2 * h + (g >> 1)) * (2 * p.W) + 2 * w + (g & 1);
     else
-      opix = (static_cast<long long>(n) * p.H + h) * p.W + w;
+      opix = (static_cast<long long>(n) * p.OH + h) * p.OW + w;
+    if (p.residual) y += __half2float(p.out[opix * p.out_ctot + p.out_choff + co]);
+    if (p.relu) y = fmaxf(y, 0.f);
     p.out[opix * p.out_ctot + p.out_choff + co] = __float2half_rn(y);
   }
 }

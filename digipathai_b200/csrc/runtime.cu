@@ -68,11 +68,14 @@ PFN_cuTensorMapEncodeTiled_v12000 get_encode() {
 
 // fp16 tensor map, 128-byte swizzle, zero fill out of bounds. dims/strides innermost first; strides in bytes
 // for dims 1..rank-1.
+// `pix_stride` > 1 sets the traversal (element) stride of dims 1 and 2 (W, H of an NHWC map): the box then
+// covers box[i] input elements and delivers ceil(box[i] / pix_stride) of them -- a strided conv's operand tile.
 int make_map(CUtensorMap* map, const void* base, int rank, const uint64_t* dims, const uint64_t* strides,
-             const uint32_t* box) {
+             const uint32_t* box, int pix_stride = 1) {
   auto enc = get_encode();
   if (!enc) return fail("cuTensorMapEncodeTiled entry point not available (driver too old?)");
   uint32_t estr[5] = {1, 1, 1, 1, 1};
+  if (pix_stride > 1 && rank >= 3) estr[1] = estr[2] = (uint32_t)pix_stride;
   CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, rank, const_cast<void*>(base), dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -95,7 +98,8 @@ static_assert(sizeof(BlobHeader) == 72, "header layout");
 struct BlobBuf {
   int32_t H, W, C, pad;
 };
-enum : int { OP_STEM_IM2COL = 1, OP_MAXPOOL = 2, OP_CONV = 3, OP_BNPOOL = 4, OP_STEM_S2D = 5, OP_DENSE_LAYER = 6 };
+enum : int { OP_STEM_IM2COL = 1, OP_MAXPOOL = 2, OP_CONV = 3, OP_BNPOOL = 4, OP_STEM_S2D = 5, OP_DENSE_LAYER = 6,
+              OP_AVGPOOL3 = 7 };
 struct BlobOp {
   int32_t type, in_buf, in_choff, cin, out_buf, out_choff, cout, kind, relu, pro, head, pool;
   float head_b;
@@ -172,10 +176,26 @@ const T* dptr(const dp_model* m, int64_t off) {
 
 int round_up(int a, int b) { return (a + b - 1) / b * b; }
 
-void fill_entries(int kind, dp::TapEntry* e, int* n) {
+// TensorFlow padding='same': leading pad along one axis (the odd cell goes behind).
+int same_pad_before(int size, int k, int stride) {
+  const int out = (size + stride - 1) / stride;
+  int total = (out - 1) * stride + k - size;
+  if (total < 0) total = 0;
+  return total / 2;
+}
+
+struct Halo {
+  int top = 1, bottom = 1, left = 1, right = 1;
+};
+
+// Tap table of a conv kind (kind 6 = generic kh x kw 'same' conv, stride 1 or 2, taps ky-major) and the halo the
+// taps reach around a stride-1 region.
+void fill_entries(int kind, int H, int W, int kh, int kw, int stride, dp::TapEntry* e, int* n, Halo* halo) {
+  Halo hl;
   if (kind == 1) {
     e[0] = {0, 0, 0, 0};
     *n = 1;
+    hl = {0, 0, 0, 0};
   } else if (kind == 3) {
     for (int ky = 0; ky < 3; ++ky)
       for (int kx = 0; kx < 3; ++kx) e[ky * 3 + kx] = {(int8_t)(ky - 1), (int8_t)(kx - 1), 0, 0};
@@ -183,6 +203,20 @@ void fill_entries(int kind, dp::TapEntry* e, int* n) {
   } else if (kind == 5) {  // stem as a 4-row-tap conv on the width-unrolled space-to-depth image
     for (int t = 0; t < 4; ++t) e[t] = {(int8_t)(t - 2), 0, 0, 0};
     *n = 4;
+    hl.top = 2;
+  } else if (kind == 6) {
+    const int ph = same_pad_before(H, kh, stride), pw = same_pad_before(W, kw, stride);
+    hl = {0, 0, 0, 0};
+    for (int ky = 0; ky < kh; ++ky)
+      for (int kx = 0; kx < kw; ++kx) {
+        const int dy = ky - ph, dx = kx - pw;
+        e[ky * kw + kx] = {(int8_t)dy, (int8_t)dx, 0, 0};
+        if (-dy > hl.top) hl.top = -dy;
+        if (dy > hl.bottom) hl.bottom = dy;
+        if (-dx > hl.left) hl.left = -dx;
+        if (dx > hl.right) hl.right = dx;
+      }
+    *n = kh * kw;
   } else {  // up2: phase (a,b), tap (ty,tx): input offset (a-1+ty, b-1+tx)
     for (int ph = 0; ph < 4; ++ph)
       for (int t = 0; t < 4; ++t) {
@@ -191,6 +225,7 @@ void fill_entries(int kind, dp::TapEntry* e, int* n) {
       }
     *n = 16;
   }
+  if (halo) *halo = hl;
 }
 
 int plan_conv(dp_model* m, const BlobOp& op, int img0, int B, Launch& L) {
@@ -202,12 +237,23 @@ int plan_conv(dp_model* m, const BlobOp& op, int img0, int B, Launch& L) {
   memset(&p, 0, sizeof p);
   int n_entries_total = 0;
   TapEntry table[kMaxEntries];
-  fill_entries(op.kind, table, &n_entries_total);
+  memset(table, 0, sizeof table);
+  const int kh = op.rsv[0] & 0xff, kw = (op.rsv[0] >> 8) & 0xff;
+  const int stride = (op.kind == 6) ? ((op.rsv[0] >> 16) & 0xff) : 1;
+  if (op.kind == 6 && (kh < 1 || kw < 1 || kh * kw > kMaxEntries || (stride != 1 && stride != 2)))
+    return fail("conv: generic tap kernel %dx%d stride %d unsupported", kh, kw, stride);
+  if (op.kind != 1 && op.kind != 3 && op.kind != 4 && op.kind != 5 && op.kind != 6) return fail("conv: unknown kind %d", op.kind);
+  Halo halo;
+  fill_entries(op.kind, H, W, kh, kw, stride, table, &n_entries_total, &halo);
+  const int OH = (H + stride - 1) / stride, OW = (W + stride - 1) / stride;  // work grid (up2: the low-res grid)
+  const int residual = (op.rsv[1] != 0) ? 1 : 0;
+  if (residual && (up2 || op.head)) return fail("conv: residual epilogue needs a plain conv");
 
   // ---- naive description (always built; used when the naive_conv option is on)
   NaiveConvParams& q = L.np;
   memset(&q, 0, sizeof q);
   q.n_img = B; q.H = H; q.W = W; q.Cin = op.cin; q.in_ctot = ib.C; q.in_choff = op.in_choff;
+  q.OH = OH; q.OW = OW; q.stride = stride; q.residual = residual;
   q.Cout = op.cout;
   q.n_entries_total = n_entries_total; q.n_groups = up2 ? 4 : 1; q.up2 = up2;
   q.relu = op.relu; q.pro_mode = op.pro;
@@ -231,6 +277,7 @@ int plan_conv(dp_model* m, const BlobOp& op, int img0, int B, Launch& L) {
 
   // ---- tensor-core plan
   p.n_img = B; p.H = H; p.W = W; p.Cin = op.cin;
+  p.OH = OH; p.OW = OW; p.stride = stride; p.cout = op.cout; p.residual = residual;
   p.n_chunks = (op.cin + 63) / 64;
   p.up2 = up2;
   p.relu = op.relu;
@@ -256,10 +303,14 @@ int plan_conv(dp_model* m, const BlobOp& op, int img0, int B, Launch& L) {
   const int groups_if_h = up2 ? 4 : 1;
   if (op.kind == 1) {
     p.mode = MODE_D;
-  } else if (H >= 16 && H % 16 == 0 && W % 8 == 0) {
+  } else if (stride == 1 && H >= 16 && H % 16 == 0 && W % 8 == 0) {
     p.mode = MODE_H;
   } else {
-    if (H * W > 128 || 128 % (H * W)) return fail("conv: map %dx%d unsupported (need H*W | 128 or H %% 16 == 0)", H, W);
+    // one (element-strided) TMA box per tap; a work item is 128 output pixels: whole images of a small map or
+    // a band of rows of a larger one
+    if (OH * OW <= 128 ? (128 % (OH * OW) != 0) : (OW > 128 || 128 % OW != 0 || OH % (128 / OW) != 0))
+      return fail("conv: output map %dx%d unsupported by the per-tap mode", OH, OW);
+    if (stride == 2 && (H % 2 || W % 2)) return fail("conv: stride 2 needs an even map, got %dx%d", H, W);
     p.mode = MODE_T;
   }
   if (L.prologue && p.mode != MODE_D) return fail("conv: pre-activation prologue only supported for 1x1 convs");
@@ -272,19 +323,33 @@ int plan_conv(dp_model* m, const BlobOp& op, int img0, int B, Launch& L) {
   if (p.mode == MODE_T)
     for (int i = 0; i < kMaxEntries; ++i) p.entries[i].group = 0;
 
-  // N tile: whole Cout if the accumulators fit, otherwise the largest multiple-of-16 divisor that does.
-  int n_tile = op.cout;
+  // N tile: whole Cout if the accumulators fit; otherwise k equal tiles (multiples of 16) chosen for the least
+  // padding, ties to fewer tiles.  A padded last tile (Cout 1088 -> 5 x 224) reads TMA-zero-filled weight rows
+  // and its store is clipped in the epilogue.
   int max_cols = kTmemCols / p.n_groups;
-  if (op.head) max_cols = max_cols < 256 ? max_cols : 256;
-  while (n_tile > 256 || n_tile > max_cols || op.cout % n_tile || n_tile % 16) {
-    n_tile -= 16;
-    if (n_tile < 16) return fail("conv: no valid N tile for Cout %d", op.cout);
+  if (max_cols > 256) max_cols = 256;
+  int n_tile = 0, n_ntiles = 0;
+  {
+    const int kmin = (op.cout + max_cols - 1) / max_cols;
+    long best = -1;
+    for (int k = kmin; k <= kmin + 8; ++k) {
+      const int nt = round_up((op.cout + k - 1) / k, 16);
+      if (nt > max_cols || nt < 16) continue;
+      const int kk = (op.cout + nt - 1) / nt;
+      const long cost = (long)kk * nt;
+      if (best < 0 || cost < best) { best = cost; n_tile = nt; n_ntiles = kk; }
+    }
+    if (best < 0) return fail("conv: no valid N tile for Cout %d", op.cout);
   }
+  if (op.head && n_ntiles != 1) return fail("conv: fused head needs a single N tile");
   p.n_tile = n_tile;
-  p.n_ntiles = op.cout / n_tile;
+  p.n_ntiles = n_ntiles;
+  const bool out_aligned = op.head || ((op.out_choff % 16) == 0 && (m->bufs[op.out_buf].C % 16) == 0);
+  if ((residual || n_tile * n_ntiles != op.cout) && !out_aligned)
+    return fail("conv: residual / clipped-N epilogue needs 16-channel aligned output placement");
 
   // sub-tiles per CTA tile
-  const long long m_total = (long long)B * H * W;
+  const long long m_total = (long long)B * OH * OW;
   if (p.mode == MODE_D) {
     p.m_total = (int)m_total;
     int sub = 4;
@@ -297,9 +362,10 @@ int plan_conv(dp_model* m, const BlobOp& op, int img0, int B, Launch& L) {
     p.a_tx_bytes = p.a_stage_bytes;
   } else if (p.mode == MODE_T) {
     p.sub = 1;
-    p.box_w = W; p.box_h = H; p.box_n = 128 / (H * W);
-    p.tiles_w = 1; p.tiles_h = 1;
-    p.n_mtiles = (B + p.box_n - 1) / p.box_n;
+    if (OH * OW <= 128) { p.box_w = OW; p.box_h = OH; p.box_n = 128 / (OH * OW); }
+    else { p.box_w = OW; p.box_h = 128 / OW; p.box_n = 1; }
+    p.tiles_w = 1; p.tiles_h = OH / p.box_h;
+    p.n_mtiles = ((B + p.box_n - 1) / p.box_n) * p.tiles_h;
     p.a_stage_bytes = kATileBytes;
     p.a_tx_bytes = kATileBytes;
   } else {
@@ -312,9 +378,10 @@ int plan_conv(dp_model* m, const BlobOp& op, int img0, int B, Launch& L) {
     // prefer more CTAs over wider regions when the layer cannot fill the GPU
     if (sub == 2 && (long long)B * (H / 16) * (W / 16) * p.n_ntiles < m->num_sms) sub = 1;
     p.sub = sub;
-    p.box_w = m->halo_pad8 ? round_up(8 * sub + 2, 8) : 8 * sub + 2;
-    p.halo_top = (op.kind == 5) ? 2 : 1;
-    p.box_h = 16 + p.halo_top + 1; p.box_n = 1;
+    p.box_w = m->halo_pad8 ? round_up(8 * sub + halo.left + halo.right, 8) : 8 * sub + halo.left + halo.right;
+    p.halo_top = halo.top;
+    p.halo_left = halo.left;
+    p.box_h = 16 + halo.top + halo.bottom; p.box_n = 1;
     p.tiles_w = W / (8 * sub); p.tiles_h = H / 16;
     p.n_mtiles = B * p.tiles_w * p.tiles_h;
     p.a_tx_bytes = p.box_w * p.box_h * 128;
@@ -329,7 +396,7 @@ int plan_conv(dp_model* m, const BlobOp& op, int img0, int B, Launch& L) {
     for (int f = base; f < e; ++f)
       if (p.entries[f].group == te.group) first = false;
     if (first) p.tap_first_mask |= 1u << e;
-    p.tap_a[e] = (p.mode == MODE_H) ? (uint32_t)(((te.dy + p.halo_top) * p.box_w + (te.dx + 1)) * 8) : 0u;
+    p.tap_a[e] = (p.mode == MODE_H) ? (uint32_t)(((te.dy + p.halo_top) * p.box_w + (te.dx + p.halo_left)) * 8) : 0u;
     p.tap_d[e] = (p.mode == MODE_H) ? (uint32_t)(te.group * p.sub * n_tile) : 0u;
   }
   p.n_items = p.n_mtiles * p.n_ntiles * p.n_phase_items;
@@ -350,7 +417,7 @@ int plan_conv(dp_model* m, const BlobOp& op, int img0, int B, Launch& L) {
   p.acc_stages = (2 * p.n_groups * p.sub * n_tile <= kTmemCols) ? 2 : 1;
 
   // shared-memory ring depths
-  const int budget = 227 * 1024 - ConvSmemLayout::kBarBytes - 2 * op.cout * 4 - 2 * p.n_chunks * 64 * 4 - 256 * 4 -
+  const int budget = 227 * 1024 - ConvSmemLayout::kBarBytes - 2 * n_tile * n_ntiles * 4 - 2 * p.n_chunks * 64 * 4 - 256 * 4 -
                      4 * kEpiStageBytes - 1024;
   int a_stages = (p.mode == MODE_H) ? 2 : 4;
   const int b_min = p.b_resident ? p.n_chunks : 2;
@@ -405,8 +472,8 @@ int plan_conv(dp_model* m, const BlobOp& op, int img0, int B, Launch& L) {
   } else {
     uint64_t dims[4] = {(uint64_t)op.cin, (uint64_t)W, (uint64_t)H, (uint64_t)B};
     uint64_t str[3] = {cstride, cstride * W, cstride * W * H};
-    uint32_t box[4] = {64, (uint32_t)p.box_w, (uint32_t)p.box_h, (uint32_t)p.box_n};
-    if (make_map(&L.map_a, in_base, 4, dims, str, box)) return 1;
+    uint32_t box[4] = {64, (uint32_t)(p.box_w * stride), (uint32_t)(p.box_h * stride), (uint32_t)p.box_n};
+    if (make_map(&L.map_a, in_base, 4, dims, str, box, stride)) return 1;
   }
   {
     uint64_t dims[3] = {(uint64_t)op.cin, (uint64_t)op.cout, (uint64_t)n_entries_total};
@@ -434,11 +501,12 @@ int plan_dense_layer(dp_model* m, const BlobOp& op, int img0, int B, Launch& L) 
   // ---- debug path: the same layer as two naive convs through the bottleneck buffer
   TapEntry t1[kMaxEntries], t3[kMaxEntries];
   int n1 = 0, n3 = 0;
-  fill_entries(1, t1, &n1);
-  fill_entries(3, t3, &n3);
+  fill_entries(1, H, W, 1, 1, 1, t1, &n1, nullptr);
+  fill_entries(3, H, W, 3, 3, 1, t3, &n3, nullptr);
   NaiveConvParams& a = L.np;
   memset(&a, 0, sizeof a);
   a.n_img = B; a.H = H; a.W = W; a.Cin = op.cin; a.in_ctot = ib.C; a.in_choff = op.in_choff;
+  a.OH = H; a.OW = W; a.stride = 1;
   a.Cout = 128; a.out_ctot = 128; a.out_choff = 0; a.n_entries_total = 1; a.n_groups = 1;
   a.relu = 1; a.pro_mode = 2;
   memcpy(a.entries, t1, sizeof t1);
@@ -449,6 +517,7 @@ int plan_dense_layer(dp_model* m, const BlobOp& op, int img0, int B, Launch& L) 
   NaiveConvParams& b = L.np2;
   memset(&b, 0, sizeof b);
   b.n_img = B; b.H = H; b.W = W; b.Cin = 128; b.in_ctot = 128; b.in_choff = 0;
+  b.OH = H; b.OW = W; b.stride = 1;
   b.Cout = 32; b.out_ctot = ib.C; b.out_choff = op.out_choff; b.n_entries_total = 9; b.n_groups = 1;
   memcpy(b.entries, t3, sizeof t3);
   b.in = buf_at(mid_buf); b.w = dptr<__half>(m, op.rsv64[0]); b.out = buf_at(op.in_buf);
@@ -602,8 +671,19 @@ int run_op(dp_model* m, SubPlan* sp, int i, cudaStream_t st) {
       const long long total = (long long)B * (ib.H / 2) * (ib.W / 2) * (op.cin / 8);
       cudaError_t le = launch_pdl(dp::maxpool3s2_kernel, grid_for(total, 256), 256, st, m->use_pdl != 0,
                                   buf_at(op.in_buf), ib.C, op.in_choff, buf_at(op.out_buf), ob.C, op.out_choff, B, ib.H,
-                                  ib.W, op.cin);
+                                  ib.W, op.cin, op.pool);
       if (le != cudaSuccess) return fail("maxpool launch failed: %s", cudaGetErrorString(le));
+      LAUNCH_OK();
+      return 0;
+    }
+    case OP_AVGPOOL3: {
+      const BlobBuf& ib = m->bufs[op.in_buf];
+      const BlobBuf& ob = m->bufs[op.out_buf];
+      const long long total = (long long)B * ib.H * ib.W * (op.cin / 8);
+      cudaError_t le = launch_pdl(dp::avgpool3s1_kernel, grid_for(total, 256), 256, st, m->use_pdl != 0,
+                                  buf_at(op.in_buf), ib.C, op.in_choff, buf_at(op.out_buf), ob.C, op.out_choff, B, ib.H,
+                                  ib.W, op.cin);
+      if (le != cudaSuccess) return fail("avgpool launch failed: %s", cudaGetErrorString(le));
       LAUNCH_OK();
       return 0;
     }
@@ -622,7 +702,7 @@ int run_op(dp_model* m, SubPlan* sp, int i, cudaStream_t st) {
     }
     case OP_CONV: {
       if (m->naive_conv) {
-        const long long total = (long long)B * L.np.H * L.np.W * L.np.n_groups * L.np.Cout;
+        const long long total = (long long)B * L.np.OH * L.np.OW * L.np.n_groups * L.np.Cout;
         dp::conv_naive_kernel<<<grid_for(total, 256), 256, 0, st>>>(L.np);
         LAUNCH_OK();
         if (op.head) {
@@ -636,7 +716,8 @@ int run_op(dp_model* m, SubPlan* sp, int i, cudaStream_t st) {
       }
       dp::ConvParams cp = L.cp;
       cp.desc_base_mode = m->desc_base_mode;
-      cp.epi_direct = m->epi_direct && ((cp.out_choff % 16) == 0) && ((cp.out_ctot % 16) == 0);
+      cp.epi_direct = (m->epi_direct || cp.residual || cp.n_tile * cp.n_ntiles != cp.cout) &&
+                      ((cp.out_choff % 16) == 0) && ((cp.out_ctot % 16) == 0);
       cp.trace = (m->trace_op == i) ? m->trace_dev : nullptr;
       cp.gt = (m->stamp && m->gt_dev) ? m->gt_dev + 2 * i : nullptr;
       // Programmatic dependent launch: the kernel's setup (barrier init, TMEM alloc, BN constants -> smem)

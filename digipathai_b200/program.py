@@ -13,7 +13,8 @@ Container layout (must match ``BlobHeader`` / ``BlobBuf`` / ``BlobOp`` in csrc/r
     n_ops  x 128 B: 12 x i32 (type in_buf in_choff cin out_buf out_choff cout kind relu pro head pool)
                    | f32 head_b | 3 x i32 0 | 8 x i64 offsets into the data section (-1 = absent):
                      w, epi_scale, epi_shift, pro_scale, pro_shift, head_w, w2, 0
-                   (rsv i32 #0 = mid_buf, #1 = safe_cin for OP_DENSE_LAYER)
+                   (rsv i32 #0 = mid_buf, #1 = safe_cin for OP_DENSE_LAYER;
+                    OP_CONV: #0 = kh | kw << 8 | stride << 16 for KIND_TAPS, #1 = residual flag)
     data section : 256-byte aligned arrays (fp16 weights [entries][Cout][Cin]; fp32 vectors)
 """
 from __future__ import annotations
@@ -24,8 +25,9 @@ from typing import List, Optional
 
 import numpy as np
 
-OP_STEM_IM2COL, OP_MAXPOOL, OP_CONV, OP_BNPOOL, OP_STEM_S2D, OP_DENSE_LAYER = 1, 2, 3, 4, 5, 6
-KIND_1X1, KIND_3X3, KIND_UP2, KIND_STEM4 = 1, 3, 4, 5
+OP_STEM_IM2COL, OP_MAXPOOL, OP_CONV, OP_BNPOOL, OP_STEM_S2D, OP_DENSE_LAYER, OP_AVGPOOL3 = 1, 2, 3, 4, 5, 6, 7
+KIND_1X1, KIND_3X3, KIND_UP2, KIND_STEM4, KIND_TAPS = 1, 3, 4, 5, 6
+POOL_PAD1_ZERO, POOL_TF_SAME = 0, 1   # OP_MAXPOOL `pool` field: ZeroPadding2D(1)+valid (densenet.py:122-123) / padding='same'
 PRO_NONE, PRO_AFFINE, PRO_AFFINE_RELU = 0, 1, 2
 
 
@@ -53,6 +55,10 @@ class Op:
     w2: Optional[np.ndarray] = None         # OP_DENSE_LAYER: fp16 [9, 32, 128] 3x3 weights (w = [1, 128, cin])
     mid_buf: int = 0                        # OP_DENSE_LAYER: bottleneck buffer (only the debug path writes it)
     safe_cin: int = 0                       # OP_DENSE_LAYER: leading input channels NOT written by the preceding op
+    kh: int = 0                             # KIND_TAPS: kernel height / width / stride ('same' padding, TF rule)
+    kw: int = 0
+    stride: int = 1
+    residual: int = 0                       # OP_CONV: out = act(out_old + conv + shift), in place (inception.py:152-160)
     name: str = ""
 
 
@@ -108,9 +114,25 @@ def pack_conv_weights(k_hwio: np.ndarray, kind: int) -> np.ndarray:
                         acc += k[ky, kx]
                 ents.append(acc.T)
         w = np.stack(ents)
+    elif kind == KIND_TAPS:
+        kh, kw = k.shape[:2]
+        w = np.stack([k[ky, kx].T for ky in range(kh) for kx in range(kw)])
     else:
         raise ValueError(kind)
     return np.ascontiguousarray(w).astype(np.float16)
+
+
+def same_pad_before(size: int, k: int, stride: int) -> int:
+    """Leading padding of TensorFlow's padding='same' along one axis (extra cell goes after)."""
+    out = -(-size // stride)
+    total = max((out - 1) * stride + k - size, 0)
+    return total // 2
+
+
+def tap_offsets(kh: int, kw: int, stride: int, H: int, W: int):
+    """(dy, dx) of every tap of a 'same' conv, ky-major: input pixel = stride * output pixel + (dy, dx)."""
+    ph, pw = same_pad_before(H, kh, stride), same_pad_before(W, kw, stride)
+    return [(ky - ph, kx - pw) for ky in range(kh) for kx in range(kw)]
 
 
 def pack_stem_weights(k_hwio: np.ndarray, kpad: int = 160) -> np.ndarray:
@@ -122,22 +144,26 @@ def pack_stem_weights(k_hwio: np.ndarray, kpad: int = 160) -> np.ndarray:
     return w.astype(np.float16)
 
 
-def pack_stem4_weights(k_hwio: np.ndarray) -> np.ndarray:
-    """7x7x3xCout stem kernel -> fp16 [4 row taps][Cout][64] for the space-to-depth stem (stem_s2d_kernel).
+def pack_stem4_weights(k_hwio: np.ndarray, pad: int = 3) -> np.ndarray:
+    """k x k x 3 x Cout stride-2 stem kernel (k <= 7) -> fp16 [4 row taps][Cout][64] for the space-to-depth stem
+    (stem_s2d_kernel).  ``pad`` = leading zero padding: 3 for ZeroPadding2D(3)+7x7/2 (densenet.py:116-117), 0 for
+    a 3x3/2 padding='same' conv on an even-sized tile (inception.py:174).
 
     Row tap t <-> dr = t-2; input channel dq*16 + (a*2+b)*3 + c multiplies original tap
-    (ky, kx) = (2*dr + a + 3, 2*(dq-2) + b + 3); combinations that fall outside the 7x7 kernel are zero.
+    (ky, kx) = (2*dr + a + pad, 2*(dq-2) + b + pad); combinations that fall outside the kernel are zero.
     """
     k = np.asarray(k_hwio, dtype=np.float32)
-    assert k.shape[:3] == (7, 7, 3)
+    assert k.shape[2] == 3 and k.shape[0] == k.shape[1]
+    K = k.shape[0]
+    assert pad <= 4 and K - 1 - pad <= 3, "kernel does not fit the 4x4 space-to-depth window"
     co = k.shape[3]
     w = np.zeros((4, co, 64), dtype=np.float32)
     for t in range(4):
         for dq in range(4):
             for a in range(2):
                 for b in range(2):
-                    ky, kx = 2 * (t - 2) + a + 3, 2 * (dq - 2) + b + 3
-                    if 0 <= ky < 7 and 0 <= kx < 7:
+                    ky, kx = 2 * (t - 2) + a + pad, 2 * (dq - 2) + b + pad
+                    if 0 <= ky < K and 0 <= kx < K:
                         for c in range(3):
                             w[t, :, dq * 16 + (a * 2 + b) * 3 + c] = k[ky, kx, c, :]
     return w.astype(np.float16)
@@ -173,7 +199,9 @@ def serialize(prog: Program) -> bytes:
     op_recs = []
     for o in prog.ops:
         if o.type == OP_CONV:
-            ents = {KIND_1X1: 1, KIND_3X3: 9, KIND_UP2: 16, KIND_STEM4: 4}[o.kind]
+            ents = {KIND_1X1: 1, KIND_3X3: 9, KIND_UP2: 16, KIND_STEM4: 4, KIND_TAPS: o.kh * o.kw}[o.kind]
+            if o.kind == KIND_TAPS:
+                assert 1 <= ents <= 32 and o.stride in (1, 2), o.name
             assert o.w is not None and o.w.shape == (ents, o.cout, o.cin), (o.name, o.w.shape, (ents, o.cout, o.cin))
             assert o.cout % 16 == 0 and o.cin % 8 == 0, o.name
             if o.pro:
@@ -191,7 +219,9 @@ def serialize(prog: Program) -> bytes:
         op_recs.append(
             struct.pack(
                 "<12if3i8q", o.type, o.in_buf, o.in_choff, o.cin, o.out_buf, o.out_choff, o.cout, o.kind, o.relu,
-                o.pro, o.head, o.pool, float(o.head_b), o.mid_buf, o.safe_cin, 0, *offs,
+                o.pro, o.head, o.pool, float(o.head_b),
+                (o.kh | (o.kw << 8) | (o.stride << 16)) if o.type == OP_CONV else o.mid_buf,
+                o.residual if o.type == OP_CONV else o.safe_cin, 0, *offs,
             )
         )
     buf_recs = [struct.pack("<4i", h, w, c, 0) for (h, w, c) in prog.bufs]

@@ -10,11 +10,14 @@ import numpy as np
 import torch
 
 from digipathai_b200 import tta
-from digipathai_b200.program import (KIND_1X1, KIND_3X3, KIND_STEM4, KIND_UP2, OP_BNPOOL, OP_CONV, OP_MAXPOOL,
-                                     OP_DENSE_LAYER, OP_STEM_IM2COL, OP_STEM_S2D, Program)
+from digipathai_b200.program import (KIND_1X1, KIND_3X3, KIND_STEM4, KIND_TAPS, KIND_UP2, OP_AVGPOOL3, OP_BNPOOL,
+                                     OP_CONV, OP_MAXPOOL, OP_DENSE_LAYER, OP_STEM_IM2COL, OP_STEM_S2D,
+                                     POOL_TF_SAME, Program, tap_offsets)
 
 
-def entries(kind):
+def entries(kind, op=None, H=0, W=0):
+    if kind == KIND_TAPS:
+        return [(dy, dx, 0) for dy, dx in tap_offsets(op.kh, op.kw, op.stride, H, W)]
     if kind == KIND_1X1:
         return [(0, 0, 0)]
     if kind == KIND_3X3:
@@ -38,6 +41,39 @@ def _shift(x, dy, dx):
     ws, we = max(0, -dx), min(w, w - dx)
     y[:, hs:he, ws:we] = x[:, hs + dy:he + dy, ws + dx:we + dx]
     return y
+
+
+def conv_eval(op, x: torch.Tensor) -> torch.Tensor:
+    """x fp32 [n,h,w,cin] (already pre-activated / quantised) -> fp32 conv output incl. BN affine, BEFORE the
+    residual add / ReLU / output rounding.  Stride-2 'same' convs (KIND_TAPS) subsample the stride-1 tap sums."""
+    f = lambda a: torch.from_numpy(np.asarray(a, dtype=np.float32))
+    w = torch.from_numpy(op.w.astype(np.float32))  # [e, co, ci]
+    n, h, wd, _ = x.shape
+    ents = entries(op.kind, op, h, wd)
+    ng = 4 if op.kind == KIND_UP2 else 1
+    s = op.stride if op.kind == KIND_TAPS else 1
+    acc = torch.zeros(ng, n, -(-h // s), -(-wd // s), op.cout)
+    for e, (dy, dx, g) in enumerate(ents):
+        acc[g] += (_shift(x, dy, dx)[:, ::s, ::s] @ w[e].T)
+    sc = f(op.epi_scale) if op.epi_scale is not None else torch.ones(op.cout)
+    sh = f(op.epi_shift) if op.epi_shift is not None else torch.zeros(op.cout)
+    acc = acc * sc + sh
+    if op.kind == KIND_UP2:
+        y = torch.zeros(n, 2 * h, 2 * wd, op.cout)
+        for g in range(4):
+            y[:, (g >> 1)::2, (g & 1)::2] = acc[g]
+        return y
+    return acc[0]
+
+
+def maxpool_same(x_nchw: torch.Tensor) -> torch.Tensor:
+    """MaxPooling2D(3, strides=2, padding='same') with TensorFlow's padding rule (padded cells never win)."""
+    h, w = x_nchw.shape[2:]
+    from digipathai_b200.program import same_pad_before
+    ph, pw = same_pad_before(h, 3, 2), same_pad_before(w, 3, 2)
+    oh, ow = -(-h // 2), -(-w // 2)
+    pad = (pw, (ow - 1) * 2 + 3 - w - pw, ph, (oh - 1) * 2 + 3 - h - ph)
+    return torch.nn.functional.max_pool2d(torch.nn.functional.pad(x_nchw, pad, value=float("-inf")), 3, stride=2)
 
 
 def stem_im2col(tiles_u8: np.ndarray, code: int) -> torch.Tensor:
@@ -88,8 +124,16 @@ def run(prog: Program, tiles_u8: np.ndarray, tta_in: int = 0, tta_out: int = 0, 
             bufs[op.out_buf][:] = q(stem_s2d(tiles_u8, tta_in))
         elif op.type == OP_MAXPOOL:
             x = bufs[op.in_buf][..., op.in_choff:op.in_choff + op.cin].permute(0, 3, 1, 2)
-            y = torch.nn.functional.max_pool2d(torch.nn.functional.pad(x, (1, 1, 1, 1)), 3, stride=2)
+            if op.pool == POOL_TF_SAME:
+                y = maxpool_same(x)
+            else:
+                y = torch.nn.functional.max_pool2d(torch.nn.functional.pad(x, (1, 1, 1, 1)), 3, stride=2)
             bufs[op.out_buf][..., op.out_choff:op.out_choff + op.cin] = y.permute(0, 2, 3, 1)
+        elif op.type == OP_AVGPOOL3:
+            # AveragePooling2D(3, strides=1, padding='same'): mean over the VALID cells of each window
+            x = bufs[op.in_buf][..., op.in_choff:op.in_choff + op.cin].permute(0, 3, 1, 2)
+            y = torch.nn.functional.avg_pool2d(x, 3, stride=1, padding=1, count_include_pad=False)
+            bufs[op.out_buf][..., op.out_choff:op.out_choff + op.cin] = q(y.permute(0, 2, 3, 1))
         elif op.type == OP_BNPOOL:
             x = bufs[op.in_buf][..., op.in_choff:op.in_choff + op.cin]
             y = x * f(op.epi_scale) + f(op.epi_shift)
@@ -115,24 +159,11 @@ def run(prog: Program, tiles_u8: np.ndarray, tta_in: int = 0, tta_out: int = 0, 
                 if op.pro == 2:
                     x = torch.relu(x)
                 x = q(x)
-            w = torch.from_numpy(op.w.astype(np.float32))  # [e, co, ci]
-            ents = entries(op.kind)
-            ng = 4 if op.kind == KIND_UP2 else 1
-            n, h, wd, _ = x.shape
-            acc = torch.zeros(ng, n, h, wd, op.cout)
-            for e, (dy, dx, g) in enumerate(ents):
-                acc[g] += _shift(x, dy, dx) @ w[e].T
-            sc = f(op.epi_scale) if op.epi_scale is not None else torch.ones(op.cout)
-            sh = f(op.epi_shift) if op.epi_shift is not None else torch.zeros(op.cout)
-            acc = acc * sc + sh
+            y = conv_eval(op, x)
+            if op.residual:
+                y = y + bufs[op.out_buf][..., op.out_choff:op.out_choff + op.cout]
             if op.relu:
-                acc = torch.relu(acc)
-            if op.kind == KIND_UP2:
-                y = torch.zeros(n, 2 * h, 2 * wd, op.cout)
-                for g in range(4):
-                    y[:, (g >> 1)::2, (g & 1)::2] = acc[g]
-            else:
-                y = acc[0]
+                y = torch.relu(y)
             if op.head:
                 z = y @ f(op.head_w) + op.head_b
                 pr = torch.sigmoid(z).numpy()

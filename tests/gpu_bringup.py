@@ -17,7 +17,7 @@ sys.path.insert(0, os.path.dirname(HERE))
 sys.path.insert(0, HERE)
 
 
-def emu_single(pr, x, tta_out=0):
+def emu_single(pr, x, tta_out=0, residual=None):
     """Reference for a one-op program on CPU (fp32 math on the fp16 operands)."""
     import numpy as np
     import torch
@@ -29,21 +29,11 @@ def emu_single(pr, x, tta_out=0):
     xs = f(x.astype(np.float32))[..., op.in_choff:op.in_choff + op.cin]
     if op.pro:
         xs = torch.relu(xs * f(op.pro_scale[:op.cin]) + f(op.pro_shift[:op.cin])).half().float()
-    w = f(op.w.astype(np.float32))
-    ng = 4 if op.kind == KIND_UP2 else 1
-    n, h, wd, _ = xs.shape
-    acc = torch.zeros(ng, n, h, wd, op.cout)
-    for e, (dy, dx, g) in enumerate(emulator.entries(op.kind)):
-        acc[g] += emulator._shift(xs, dy, dx) @ w[e].T
-    acc = acc * f(op.epi_scale) + f(op.epi_shift)
+    y = emulator.conv_eval(op, xs)
+    if op.residual:
+        y = y + f(np.asarray(residual, dtype=np.float32))[..., op.out_choff:op.out_choff + op.cout]
     if op.relu:
-        acc = torch.relu(acc)
-    if op.kind == KIND_UP2:
-        y = torch.zeros(n, 2 * h, 2 * wd, op.cout)
-        for g in range(4):
-            y[:, (g >> 1)::2, (g & 1)::2] = acc[g]
-    else:
-        y = acc[0]
+        y = torch.relu(y)
     if op.head:
         p = torch.sigmoid(y @ f(op.head_w) + op.head_b).numpy()
         return np.stack([tta.apply(tta.inverse(tta_out), t) for t in p])
@@ -91,6 +81,61 @@ def run_conv_case(name):
     return res
 
 
+def run_tap_case(name):
+    import numpy as np
+    import torch
+    import conv_cases
+    from digipathai_b200.engine import TileModel
+    pr, x, out0, B = conv_cases.build_tap_case(name)
+    op = pr.ops[0]
+    ref = emu_single(pr, x, 0, residual=out0.astype(np.float32))
+    m = TileModel(pr, device=0, max_batch=B)
+    for label, naive in (("naive", 1), ("tc", 0)):
+        m.set_option("naive_conv", naive)
+        m.write_buffer(0, x)
+        m.write_buffer(1, out0)
+        t0 = time.time()
+        m.run_ops(B, 0, 1)
+        torch.cuda.synchronize()
+        dt = time.time() - t0
+        full = m.read_buffer(1, B).astype(np.float32)
+        err = np.abs(full[..., op.out_choff:op.out_choff + op.cout] - ref).max()
+        keep = out0.astype(np.float32).copy()
+        full[..., op.out_choff:op.out_choff + op.cout] = 0
+        keep[..., op.out_choff:op.out_choff + op.cout] = 0
+        outside = "" if np.array_equal(full, keep) else "  WROTE OUTSIDE ITS CHANNEL RANGE"
+        print(f"  {name:16s} {label:9s} max_abs_err {err:.3e}  ref_max {np.abs(ref).max():.2f}  ({dt*1e3:.1f} ms){outside}", flush=True)
+
+
+def run_full_inception(batch=2, patch=256):
+    import numpy as np
+    import torch
+    import emulator
+    from digipathai_b200.engine import TileModel
+    from digipathai_b200.models.inception import inception_resnet_v2_unet_program, init_inception_weights
+    from oracle import inception_ref as R
+    rng = np.random.default_rng(1)
+    tiles = rng.integers(0, 256, (batch, patch, patch, 3)).astype(np.uint8)
+    w = init_inception_weights(0)
+    x = (tiles.astype(np.float32) - 128) / 128
+    R.calibrate_bn(w, x)
+    y = R.forward(w, x)[..., 1]
+    prog = inception_resnet_v2_unet_program(w, patch)
+    emu, ebufs = emulator.run(prog, tiles, keep=True)
+    print(f"  emulator(fp16 storage) vs oracle: {np.abs(emu - y).max():.3e}", flush=True)
+    m = TileModel(prog, device=0, max_batch=batch)
+    t = torch.from_numpy(tiles).cuda()
+    for label, naive in (("naive", 1), ("tc", 0)):
+        m.set_option("naive_conv", naive)
+        p = m.forward_tile_batch(t).cpu().numpy()
+        print(f"  inception forward {label:5s}: vs oracle {np.abs(p - y).max():.3e}  vs emulator {np.abs(p - emu).max():.3e}", flush=True)
+        for bi, nm in enumerate(prog.buf_names):
+            got = m.read_buffer(bi, batch).astype(np.float32)
+            want = ebufs[bi].numpy()
+            d = np.abs(got - want)
+            print(f"     buf {nm:12s} max_abs_diff {d.max():.3e} mean {d.mean():.3e} (ref max {np.abs(want).max():.2f})", flush=True)
+
+
 def run_full(batch=2, naive_too=True):
     import numpy as np
     import torch
@@ -125,15 +170,25 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--case")
     ap.add_argument("--timeout", type=int, default=240)
+    ap.add_argument("--set", default="dense", choices=["dense", "inception"])
     args = ap.parse_args()
     if args.case:
+        import conv_cases
         if args.case == "full":
             run_full()
+        elif args.case == "full_inception":
+            run_full_inception()
+        elif args.case == "full_inception64":
+            run_full_inception(3, 64)
+        elif args.case in conv_cases.TAP_CASES:
+            run_tap_case(args.case)
         else:
             run_conv_case(args.case)
         return
     import conv_cases
-    for name in list(conv_cases.CASES) + ["full"]:
+    names = list(conv_cases.CASES) + ["full"] if args.set == "dense" else \
+        list(conv_cases.TAP_CASES) + ["full_inception64", "full_inception"]
+    for name in names:
         print(f"== {name}", flush=True)
         try:
             r = subprocess.run(["timeout", str(args.timeout), sys.executable, os.path.abspath(__file__), "--case", name],

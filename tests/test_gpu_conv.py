@@ -41,6 +41,34 @@ def test_conv_case(name):
     m.close()
 
 
+@pytest.mark.parametrize("name", list(conv_cases.TAP_CASES))
+def test_tap_conv_case(name):
+    """Generic tap tables (1x7, 7x1, 5x5, ...), stride-2 'same' convs through element-strided TMA boxes, the
+    in-place residual epilogue and clipped N tiles (Inception-ResNet-v2 shapes) against the CPU evaluation."""
+    import torch
+    from digipathai_b200.engine import TileModel
+    pr, x, out0, B = conv_cases.build_tap_case(name)
+    op = pr.ops[0]
+    ref = emu_single(pr, x, 0, residual=out0.astype(np.float32))
+    m = TileModel(pr, device=0, max_batch=B)
+    for label, naive in (("naive", 1), ("tc", 0)):
+        m.set_option("naive_conv", naive)
+        m.write_buffer(0, x)
+        m.write_buffer(1, out0)
+        m.run_ops(B, 0, 1)
+        torch.cuda.synchronize()
+        full = m.read_buffer(1, B).astype(np.float32)
+        got = full[..., op.out_choff:op.out_choff + op.cout]
+        tol = float(np.abs(ref).max()) * 2.0 ** -10
+        err = np.abs(got - ref).max()
+        assert err <= tol, (name, label, err, tol)
+        keep = out0.astype(np.float32).copy()
+        full[..., op.out_choff:op.out_choff + op.cout] = 0
+        keep[..., op.out_choff:op.out_choff + op.cout] = 0
+        assert np.array_equal(full, keep), (name, label, "wrote outside its channel range")
+    m.close()
+
+
 @pytest.mark.parametrize("name", list(conv_cases.DENSE_CASES))
 def test_fused_dense_layer(name):
     """dense_layer_kernel (1x1 -> bottleneck in smem -> 3x3) against fp32 math on the same fp16 operands."""
