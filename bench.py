@@ -34,6 +34,8 @@ METRIC = "tiles_per_sec_256x256_b32"
 UNIT = "tiles/s"
 PATCH, BATCH = 256, 32
 REF_FLOP_PER_TILE = 42316333056  # 21 158 166 528 conv MACs x 2 (reference graph)
+REF_FLOP = {"dense": 42316333056, "inception": 57406652416}   # SURVEY.md 8(d); inception: 28 703 326 208 MACs x 2
+MODEL_DESC = {"dense": "DenseNet-121 U-Net", "inception": "Inception-ResNet-v2 U-Net (--model inception; not the headline config)"}
 
 
 def load_peaks():
@@ -95,14 +97,19 @@ def dist_env():
     return rank, world, local
 
 
-def oracle_tiles_per_sec(n_tiles: int, threads: int, seed: int = 0):
+def oracle_tiles_per_sec(n_tiles: int, threads: int, seed: int = 0, model: str = "dense"):
     """Times the CPU oracle (fp32 PyTorch-CPU restatement of the reference graph + crop/normalise) on a sample."""
     import torch
-    from digipathai_b200.models.densenet import init_densenet_weights
-    from oracle import densenet_ref
     torch.set_num_threads(threads)
     rng = np.random.default_rng(seed)
-    w = init_densenet_weights(0)
+    if model == "inception":
+        from digipathai_b200.models.inception import init_inception_weights
+        from oracle import inception_ref as densenet_ref
+        w = init_inception_weights(0)
+    else:
+        from digipathai_b200.models.densenet import init_densenet_weights
+        from oracle import densenet_ref
+        w = init_densenet_weights(0)
     tiles = rng.integers(0, 256, (n_tiles, PATCH, PATCH, 3)).astype(np.uint8)
     densenet_ref.forward(w, (tiles[:1].astype(np.float32) - 128.0) / 128.0)  # warm-up (thread pools, allocs)
     t0 = time.perf_counter()
@@ -124,18 +131,18 @@ def run_reference(args):
     sample = 8
     vals = []
     for _ in range(max(1, args.warmup and 1)):
-        oracle_tiles_per_sec(4, cores)
+        oracle_tiles_per_sec(4, cores, model=args.model)
     t_all = 0.0
     for _ in range(args.steps):
-        v, dt = oracle_tiles_per_sec(sample, cores)
+        v, dt = oracle_tiles_per_sec(sample, cores, model=args.model)
         vals.append(v); t_all += dt
     value = float(np.mean(vals))
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * t_all / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "configs[1]: DenseNet-121 U-Net forward, 256x256x3 uint8 tiles",
-                   "note": "reference CPU path = oracle port (fp32 torch-CPU restatement of densenet.py; the "
+        "config": {"workload": f"configs[1]: {MODEL_DESC[args.model]} forward, 256x256x3 uint8 tiles",
+                   "note": "reference CPU path = oracle port (fp32 torch-CPU restatement of the Keras graph; the "
                            "reference itself needs TensorFlow 1.x and cannot be installed offline)"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
                          "sample": f"{sample} tiles per step in batches of 4, {args.steps} steps"},
@@ -152,6 +159,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="forward", choices=["forward", "slide"])
+    ap.add_argument("--model", default="dense", choices=["dense", "inception"],
+                    help="graph to run (BASELINE configs[1] names the DenseNet U-Net: the default)")
     ap.add_argument("--slide", type=int, default=8192, help="--workload slide: side of the synthetic slide")
     ap.add_argument("--tta", default="", help="--workload slide: comma separated tta_list")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -195,8 +204,14 @@ def main():
         return float(t.item())
 
     peaks, peak_src = load_peaks()
-    weights = init_densenet_weights(0)
-    model = engine.TileModel(densenet121_unet_program(weights, PATCH), device=local, max_batch=BATCH)
+    if args.model == "inception":
+        from digipathai_b200.models.inception import inception_resnet_v2_unet_program, init_inception_weights
+        model = engine.TileModel(inception_resnet_v2_unet_program(init_inception_weights(0), PATCH), device=local,
+                                 max_batch=BATCH)
+    else:
+        weights = init_densenet_weights(0)
+        model = engine.TileModel(densenet121_unet_program(weights, PATCH), device=local, max_batch=BATCH)
+    ref_flop_per_tile = REF_FLOP[args.model]
 
     if args.split:
         model.set_option("split", args.split)
@@ -288,7 +303,7 @@ def main():
     conv_ms = float(sum(t for t, inf in zip(per_op, infos) if inf["type"] in (3, 6)))
     all_ms = float(per_op.sum())
     n_conv = sum(1 for inf in infos if inf["type"] in (3, 6))
-    flop_step = REF_FLOP_PER_TILE * BATCH
+    flop_step = ref_flop_per_tile * BATCH
     achieved_tf = flop_step / (conv_ms * 1e-3) / 1e12
     exec_macs = model.executed_macs(BATCH)
     peak_tf = peaks["bf16_tflops_sustained"]
@@ -310,7 +325,7 @@ def main():
     cpu_baseline = None
     if rank == 0 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
-        v, dt = oracle_tiles_per_sec(32, threads)
+        v, dt = oracle_tiles_per_sec(32, threads, model=args.model)
         cpu_baseline = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
                         "sample": f"32 tiles (8 batches of 4) of the same workload, {dt:.1f} s of CPU work"}
 
@@ -319,20 +334,20 @@ def main():
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f16 (fp32 accumulate)", "data": "synthetic",
-            "config": {"workload": "configs[1]: DenseNet-121 U-Net forward on synthetic 256x256x3 uint8 tiles, "
+            "config": {"workload": f"configs[1]: {MODEL_DESC[args.model]} forward on synthetic 256x256x3 uint8 tiles, "
                                    "batch 32 per GPU, tiles cropped from an HBM-resident raster",
                        "l2": "flushed between timed steps (256 MiB memset, untimed)",
                        "weights": "random-init (He-normal), BN stats (0,1)",
                        "graph": "off" if args.no_graph else f"one CUDA graph per step, {args.split or 1} sub-batch branch(es), PDL between conv kernels",
                        "executed_gflop_per_tile": 2 * exec_macs / BATCH / 1e9,
-                       "reference_gflop_per_tile": REF_FLOP_PER_TILE / 1e9},
+                       "reference_gflop_per_tile": ref_flop_per_tile / 1e9},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(host_in.numel()),
                     "d2h_bytes_per_step": int(host_out.numel() * 4)},
             "gpu_launches": int(launches),
             "roofline": {"bound": "tensor", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
                          "frac": achieved_tf / peak_tf, "traffic": None,
-                         "kernel": f"conv_tc_kernel + dense_layer_kernel, tcgen05 implicit-GEMM family ({n_conv} launches per step; algorithmic FLOPs of the "
+                         "kernel": f"conv_tc_kernel{' + dense_layer_kernel' if args.model == 'dense' else ''}, tcgen05 implicit-GEMM family ({n_conv} launches per step; algorithmic FLOPs of the "
                                    f"reference graph / summed CUDA-event time of those launches)",
                          "peak_source": f"{peak_src} bf16_tflops_sustained",
                          "conv_ms_per_step": conv_ms, "all_ops_ms_per_step": all_ms, "top_ops": top_desc},

@@ -137,13 +137,17 @@ def load_trained_models(model, path, patch_size=256, *, device=0, max_batch=32):
     """
     from .engine import TileModel
     from .models.densenet import densenet121_unet_program
+    from .models.inception import inception_resnet_v2_unet_program
     if model.__contains__('dense'):
         weights = path if isinstance(path, dict) else _load_npz(path)
         return TileModel(densenet121_unet_program(weights, patch_size), device=device, max_batch=max_batch)
-    if model.__contains__('inception') or model.__contains__('deeplabv3'):
+    if model.__contains__('inception'):
+        weights = path if isinstance(path, dict) else _load_npz(path)
+        return TileModel(inception_resnet_v2_unet_program(weights, patch_size), device=device, max_batch=max_batch)
+    if model.__contains__('deeplabv3'):
         raise NotImplementedError(
-            f"model '{model}': only the DenseNet-121 U-Net graph is built for sm_100a so far "
-            "(Inception-ResNet-v2 U-Net and DeepLabv3+ are SURVEY.md rows a8'/a8'')")
+            f"model '{model}': the DenseNet-121 and Inception-ResNet-v2 U-Nets are built for sm_100a; "
+            "DeepLabv3+ (SURVEY.md row a8'') is not yet")
     raise ValueError("Unknown model provided, allowed models ['dense', 'inception', 'deeplabv3']")
 
 
@@ -221,11 +225,22 @@ def getSegmentation(img_path,
             raise ValueError("Unknown model provided, allowed models ['dense', 'inception', 'deeplabv3']")
         names = [model]
 
+    if 'deeplabv3' in names:
+        # fail before anything is loaded: the third ensemble member (SURVEY.md row a8'') has no sm_100a graph yet
+        raise NotImplementedError(
+            "model 'deeplabv3': the DenseNet-121 and Inception-ResNet-v2 U-Nets are built for sm_100a; DeepLabv3+ "
+            "is not yet, so quick=False (the reference's 3-model ensemble, Segmentation.py:288-291) cannot run. "
+            "Use get_prediction(models={'dense': ..., 'inception': ...}) for the two-model ensemble.")
+
     def weight_source(nm):
         if isinstance(weights, dict) and nm in weights and not isinstance(weights[nm], np.ndarray):
             return weights[nm]
-        if isinstance(weights, dict) and 'conv1/conv' in weights:
-            return weights
+        if isinstance(weights, dict) and ('conv1/conv' in weights or 'conv2d_1' in weights):
+            family = 'dense' if 'conv1/conv' in weights else 'inception'
+            if family != nm:
+                raise ValueError(f"weights= holds a '{family}' weight dict but model '{nm}' was requested; pass "
+                                 "weights={'dense': ..., 'inception': ...}")
+            return weights          # a single flat weight dict for `model`
         if isinstance(weights, str):
             return weights
         return _default_weight_path(mode, nm)

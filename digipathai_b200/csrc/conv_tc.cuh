@@ -188,7 +188,7 @@ __device__ __forceinline__ void trace_close(const ConvParams& p, const TraceCurs
   if (c.base) p.trace[role] = c.n;
 }
 
-template <int MODE, bool PROLOGUE>
+template <int MODE, bool PROLOGUE, bool RESIDUAL = false>
 __global__ void __launch_bounds__(PROLOGUE ? 384 : 256, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                const __grid_constant__ ConvParams p) {
@@ -473,6 +473,59 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     uint32_t as = 0, ap = 0;
     TraceCursor tc;
     if (r == 0) tc = trace_open(p, 2);
+    if constexpr (RESIDUAL) {
+      // Inception-ResNet block tail (MODE_D, sub == 1, one accumulator group): out = act(out_old + acc + shift),
+      // in place.  The old values of this thread's pixel row (<= 256 channels = 16 x 32 B) are fetched BEFORE the
+      // accumulator wait, so their HBM/L2 latency hides behind the item's MMAs instead of serialising the
+      // epilogue (one dependent ~1 us load per 32 columns otherwise).
+      for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+        const WorkItem wi = decode_item(p, item);
+        const int m = wi.m0 + r;
+        const bool valid = m < p.m_total;
+        const int ch0 = wi.nt * p.n_tile;
+        __half* orow = p.out + static_cast<long long>(m) * p.out_ctot + p.out_choff + ch0;
+        uint32_t old[16][8];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) old[j][i] = 0u;
+          if (valid && j * 16 < p.n_tile && ch0 + j * 16 < p.cout) ld_global_v8(orow + j * 16, old[j]);
+        }
+        mbar_wait(&acc_full[as], ap);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * p.n_tile;
+#pragma unroll
+        for (int j2 = 0; j2 < 8; ++j2) {
+          const int cc = 32 * j2;
+          if (cc >= p.n_tile || ch0 + cc >= p.cout) break;
+          uint32_t v[2][16];
+          const bool two = cc + 16 < p.n_tile && ch0 + cc + 16 < p.cout;
+          tmem_ld16(taddr + cc, v[0]);
+          if (two) tmem_ld16(taddr + cc + 16, v[1]);
+          tmem_ld_wait();
+#pragma unroll
+          for (int hsel = 0; hsel < 2; ++hsel) {
+            if (hsel == 1 && !two) break;
+            const int cb = ch0 + cc + 16 * hsel;
+            float f[16];
+            epi_affine16(v[hsel], s_epi_scale + cb, s_epi_shift + cb, has_scale, false, f);
+            uint32_t pk[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const float2 o2 = __half22float2(*reinterpret_cast<const __half2*>(&old[2 * j2 + hsel][i]));
+              float a = f[2 * i] + o2.x, b = f[2 * i + 1] + o2.y;
+              if (p.relu) { a = fmaxf(a, 0.f); b = fmaxf(b, 0.f); }
+              __half2 h2 = __floats2half2_rn(a, b);
+              pk[i] = *reinterpret_cast<uint32_t*>(&h2);
+            }
+            if (valid) st_global_v8(orow + cc + 16 * hsel, pk);
+          }
+        }
+        tc_fence_before();
+        mbar_arrive(&acc_empty[as]);
+        if (++as == p.acc_stages) { as = 0; ap ^= 1; }
+      }
+    } else
     for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
       const WorkItem wi = decode_item(p, item);
       mbar_wait(&acc_full[as], ap);
@@ -556,18 +609,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 if (hsel == 1 && !two) break;
                 const int cb = ch0 + cc + 16 * hsel;
                 float f[16];
-                epi_affine16(v[hsel], s_epi_scale + cb, s_epi_shift + cb, has_scale, p.relu != 0 && !p.residual, f);
-                if (p.residual) {
-                  // the running tensor of the residual chain is updated in place: this thread owns these 16 values
-                  uint32_t old[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-                  if (valid) ld_global_v8(orow + cc + 16 * hsel, old);
-#pragma unroll
-                  for (int i = 0; i < 8; ++i) {
-                    const float2 o2 = __half22float2(*reinterpret_cast<const __half2*>(&old[i]));
-                    f[2 * i] += o2.x; f[2 * i + 1] += o2.y;
-                    if (p.relu) { f[2 * i] = fmaxf(f[2 * i], 0.f); f[2 * i + 1] = fmaxf(f[2 * i + 1], 0.f); }
-                  }
-                }
+                epi_affine16(v[hsel], s_epi_scale + cb, s_epi_shift + cb, has_scale, p.relu != 0, f);
                 uint32_t pk[8];
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {

@@ -247,7 +247,7 @@ int plan_conv(dp_model* m, const BlobOp& op, int img0, int B, Launch& L) {
   fill_entries(op.kind, H, W, kh, kw, stride, table, &n_entries_total, &halo);
   const int OH = (H + stride - 1) / stride, OW = (W + stride - 1) / stride;  // work grid (up2: the low-res grid)
   const int residual = (op.rsv[1] != 0) ? 1 : 0;
-  if (residual && (up2 || op.head)) return fail("conv: residual epilogue needs a plain conv");
+  if (residual && (op.kind != 1 || op.head || op.pro)) return fail("conv: residual epilogue needs a plain 1x1 conv");
 
   // ---- naive description (always built; used when the naive_conv option is on)
   NaiveConvParams& q = L.np;
@@ -356,6 +356,7 @@ int plan_conv(dp_model* m, const BlobOp& op, int img0, int B, Launch& L) {
     while (sub > 1 && (sub * n_tile > kTmemCols ||
                        ((m_total + sub * 128 - 1) / (sub * 128)) * p.n_ntiles < m->num_sms))
       sub >>= 1;
+    if (residual) sub = 1;   // the residual epilogue prefetches one pixel row (<= 256 channels) per thread
     p.sub = sub;
     p.n_mtiles = (int)((m_total + sub * 128 - 1) / (sub * 128));
     p.a_stage_bytes = sub * kATileBytes;
@@ -743,7 +744,8 @@ int run_op(dp_model* m, SubPlan* sp, int i, cudaStream_t st) {
       cudaError_t le;
       switch (cp.mode) {
         case dp::MODE_D:
-          if (L.prologue) le = cudaLaunchKernelEx(&cfg, dp::conv_tc_kernel<dp::MODE_D, true>, L.map_a, L.map_b, cp);
+          if (cp.residual) le = cudaLaunchKernelEx(&cfg, dp::conv_tc_kernel<dp::MODE_D, false, true>, L.map_a, L.map_b, cp);
+          else if (L.prologue) le = cudaLaunchKernelEx(&cfg, dp::conv_tc_kernel<dp::MODE_D, true>, L.map_a, L.map_b, cp);
           else le = cudaLaunchKernelEx(&cfg, dp::conv_tc_kernel<dp::MODE_D, false>, L.map_a, L.map_b, cp);
           break;
         case dp::MODE_T:
@@ -883,9 +885,10 @@ int dp_model_create(const void* blob, size_t nbytes, int device, int max_batch, 
     cudaError_t e2 = cudaFuncSetAttribute(dp::conv_tc_kernel<dp::MODE_D, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
     cudaError_t e3 = cudaFuncSetAttribute(dp::conv_tc_kernel<dp::MODE_T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
     cudaError_t e4 = cudaFuncSetAttribute(dp::conv_tc_kernel<dp::MODE_H, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
+    cudaError_t e7 = cudaFuncSetAttribute(dp::conv_tc_kernel<dp::MODE_D, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
     cudaError_t e5 = cudaFuncSetAttribute(dp::dense_layer_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
     cudaError_t e6 = cudaFuncSetAttribute(dp::dense_layer_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
-    if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess || e4 != cudaSuccess || e5 != cudaSuccess || e6 != cudaSuccess) {
+    if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess || e4 != cudaSuccess || e5 != cudaSuccess || e6 != cudaSuccess || e7 != cudaSuccess) {
       cleanup();
       return fail("cudaFuncSetAttribute(MaxDynamicSharedMemorySize) failed: %s", cudaGetErrorString(cudaGetLastError()));
     }

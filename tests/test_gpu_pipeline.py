@@ -72,3 +72,30 @@ def test_errors_match_the_reference(env):
         getSegmentation(slide, quick=False, weights=w)
     with pytest.raises(FileNotFoundError):
         getSegmentation(slide, batch_size=4)          # no converted weights under ~/.DigiPathAI
+
+
+def test_ensemble_dense_plus_inception_matches_oracle_pipeline(env):
+    """Two-model ensemble (Segmentation.py:150-170: TTA outer, model inner, mean/var over all passes) with the
+    Inception-ResNet-v2 U-Net as the second member, against the oracle loop driving both oracle graphs."""
+    from digipathai_b200.Segmentation import get_prediction, load_trained_models
+    from digipathai_b200.models.inception import init_inception_weights
+    from oracle import inception_ref, pipeline_ref
+    w, slide, omodels = env
+    rng = np.random.default_rng(11)
+    calib = (rng.integers(0, 256, (2, 256, 256, 3)).astype(np.float32) - 128.0) / 128.0
+    wi = inception_ref.calibrate_bn(init_inception_weights(4), calib)
+    both = {"dense": omodels["dense"], "inception": inception_ref.OracleModel(wi)}
+    kw = dict(batch_size=4, patch_size=256, stride_size=256, tta_list=['ROTATE_90'])
+    _, want = pipeline_ref.get_prediction(slide, models=both, **kw)
+    models = {"dense": load_trained_models('dense', w, 256, max_batch=4),
+              "inception": load_trained_models('inception', wi, 256, max_batch=4)}
+    _, got = get_prediction(slide, models=models, **kw)
+    d = np.abs(got['mean'] - want['mean'])
+    touched = want['count'] > 0
+    print(f"\nensemble get_prediction: max|mean-oracle| {d.max():.3e} mean {d[touched].mean():.3e}; "
+          f"max|var-oracle| {np.abs(got['var'] - want['var']).max():.3e}")
+    assert d.max() <= 1e-1 and d[touched].mean() <= 1.5e-2
+    assert np.abs(got['var'] - want['var']).max() <= 5e-2
+    assert np.array_equal(want['mean'] == 0, got['mean'] == 0)
+    for m in models.values():
+        m.close()
