@@ -74,6 +74,11 @@ struct ConvParams {
   int epi_mode, relu;
   int out_ctot, out_choff;  // output NHWC buffer: channel stride and channel offset (elements)
   int desc_base_mode;       // 0: descriptor base_offset field = 0; 1: (addr >> 7) & 7
+  int fast_id;              // MODE_H: 0 = generic tap loop, else (kind, sub, taps per B stage) of a fully unrolled
+                            // issue sequence: fast_id = kind * 100 + sub * 10 + b_group (see issue_chunk_h)
+  int dbg_skip;             // TIMING EXPERIMENTS ONLY (wrong results): bit 0 = weight tiles are fetched only on the
+                            // first pass through the B ring, bit 1 = same for activation tiles, bit 2 = epilogue
+                            // does not store, bit 3 = epilogue does nothing but release the accumulator
   int pro_relu;
   int img0, P;              // EPI_HEAD: first image of this sub-batch within the call; tile side
   float head_b;
@@ -188,10 +193,84 @@ __device__ __forceinline__ void trace_close(const ConvParams& p, const TraceCurs
   if (c.base) p.trace[role] = c.n;
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Fully unrolled MMA issue of one 64-channel chunk in halo mode.  The generic tap loop spends ~250 clocks of
+// scalar work per tap in the single issuing thread (indexed constant loads of the tap table, R2UR moves, 64-bit
+// descriptor adds, loop control) -- more than the 192 clocks four N = 64 MMAs take to execute -- so the
+// high-resolution layers were issue bound, not tensor bound (measured with the tap table stubbed out, TMA and
+// epilogue disabled: same time).  Here every tap offset, accumulator group and first-use flag is a compile-time
+// constant: KIND 3 = 3x3 taps (dy, dx in -1..1), KIND 4 = up2 sub-pixel entries [phase][2x2 tap]; SUB sub-tiles
+// of 8 pixels (box width 8 SUB + 2); BG taps per weight stage (BG == all taps when the weights are resident).
+struct IssueRing {
+  uint64_t* b_full;
+  uint64_t* b_empty;
+  uint32_t sb, pb;
+};
+
+template <int KIND, int SUB, int BG>
+__device__ __forceinline__ void issue_chunk_h(const ConvParams& p, IssueRing& r, uint64_t a_stage_desc, uint64_t b_desc0,
+                                              uint32_t b_stage_u, uint32_t b_ent_u, uint32_t d_stage, uint32_t n_tile,
+                                              uint32_t idesc, uint32_t acc_c, int c, bool b_loaded, TraceCursor& tc,
+                                              int item) {
+  constexpr int NE = (KIND == 3) ? 9 : 16;
+  constexpr int WW = 8 * SUB + 2;
+  static_assert(NE % BG == 0, "taps per weight stage must divide the tap count");
+#pragma unroll
+  for (int g = 0; g < NE / BG; ++g) {
+    if (p.b_resident) {
+      r.sb = c;
+      if (!b_loaded) mbar_wait(&r.b_full[r.sb], 0);
+    } else {
+      mbar_wait(&r.b_full[r.sb], r.pb);
+    }
+    tc_fence_after();
+    trace_ev(tc, 2, item);
+    const uint64_t b_desc = b_desc0 + r.sb * b_stage_u;
+#pragma unroll
+    for (int j = 0; j < BG; ++j) {
+      const int e = g * BG + j;
+      int dy, dx, grp;
+      if (KIND == 3) {
+        dy = e / 3 - 1; dx = e % 3 - 1; grp = 0;
+      } else {
+        const int ph = e >> 2, t = e & 3;
+        dy = (ph >> 1) - 1 + (t >> 1); dx = (ph & 1) - 1 + (t & 1); grp = ph;
+      }
+      const uint32_t a_off = static_cast<uint32_t>(((dy + 1) * WW + dx + 1) * 8);
+      const bool first = (KIND == 3) ? (e == 0) : ((e & 3) == 0);
+      const uint32_t flag = first ? acc_c : 1u;
+#pragma unroll
+      for (int s = 0; s < SUB; ++s)
+        umma_f16_ss_k4(d_stage + static_cast<uint32_t>(grp * SUB + s) * n_tile, a_stage_desc + a_off + s * 64u,
+                       b_desc + static_cast<uint32_t>(j) * b_ent_u, idesc, flag);
+      trace_ev(tc, 4, item);
+    }
+    if (!p.b_resident) {
+      if (p.b_pair) umma_commit_mcast(&r.b_empty[r.sb], 3);
+      else umma_commit(&r.b_empty[r.sb]);
+      trace_ev(tc, 5, item);
+      if (++r.sb == static_cast<uint32_t>(p.b_stages)) { r.sb = 0; r.pb ^= 1; }
+    }
+  }
+}
+
+// Epilogue warp groups of a kernel variant: the plain variants run TWO groups of four warps (warps 4-7 and 8-11; a
+// warp can only read TMEM lanes 32 (w % 4) .. +31, so the groups split an item's (accumulator, 32-column step)
+// units between them).  With one epilogue warp per SM sub-partition the epilogue is issue-latency bound
+// (~0.16 IPC per warp, tensor pipe 25-45 % busy on the high-resolution decoder layers); a second warp per
+// sub-partition hides that latency.  The PROLOGUE variant uses warps 8-11 for the pre-activation transform and
+// the RESIDUAL variant holds a 128-register prefetch per thread: both keep one group.
+template <bool PROLOGUE, bool RESIDUAL>
+struct ConvKernelShape {
+  static constexpr int kEpiGroups = (PROLOGUE || RESIDUAL) ? 1 : 2;
+  static constexpr int kThreads = (PROLOGUE || kEpiGroups == 2) ? 384 : 256;
+};
+
 template <int MODE, bool PROLOGUE, bool RESIDUAL = false>
-__global__ void __launch_bounds__(PROLOGUE ? 384 : 256, 1)
+__global__ void __launch_bounds__((ConvKernelShape<PROLOGUE, RESIDUAL>::kThreads), 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                const __grid_constant__ ConvParams p) {
+  constexpr int kEpiGroups = ConvKernelShape<PROLOGUE, RESIDUAL>::kEpiGroups;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
@@ -236,7 +315,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&acc_full[i], 1);
-      mbar_init(&acc_empty[i], 128);
+      mbar_init(&acc_empty[i], 128 * kEpiGroups);
     }
     fence_barrier_init();
   }
@@ -291,6 +370,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           const int c0 = c * 64;
           if (MODE != MODE_T) {
             mbar_wait(&a_empty[sa], pa ^ 1);
+            if ((p.dbg_skip & 2) && pa) {
+              mbar_expect_tx(&a_full[sa], 0);
+              if (++sa == p.a_stages) { sa = 0; pa ^= 1; }
+              continue;
+            }
             mbar_expect_tx(&a_full[sa], p.a_tx_bytes);
             uint8_t* dst = a_base + sa * p.a_stage_bytes;
             if (MODE == MODE_D) {
@@ -319,7 +403,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   } else if (warp == 3) {
     // ------------------------------------------------------------------ TMA producer: weights (B ring)
     if (elect_one()) {
-      uint32_t sb = 0, pb = 0;
+      uint32_t sb = 0, pb = 0, b_pass = 0;
       if (p.b_resident) {
         // Weight-stationary: the high-resolution decoder layers are L2->SM bandwidth bound when every CTA
         // re-streams the layer's weights for every 128/256-pixel item; when they fit, load them exactly once.
@@ -358,10 +442,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           const int ebase = (rest / p.n_ntiles) * p.n_entries;
           for (int c = 0; c < p.n_chunks; ++c) {
             for (int g = 0; g < n_bgroups; ++g) {
+              if ((p.dbg_skip & 16) && b_pass) { if (++sb == p.b_stages) sb = 0; continue; }
               mbar_wait(&b_empty[sb], pb ^ 1);
-              mbar_expect_tx(&b_full[sb], p.b_stage_bytes);
-              tma_load_3d(&map_b, &b_full[sb], b_base + sb * p.b_stage_bytes, c * 64, n0, ebase + g * p.b_group);
-              if (++sb == p.b_stages) { sb = 0; pb ^= 1; }
+              if ((p.dbg_skip & 1) && pb) {
+                mbar_expect_tx(&b_full[sb], 0);
+              } else {
+                mbar_expect_tx(&b_full[sb], p.b_stage_bytes);
+                tma_load_3d(&map_b, &b_full[sb], b_base + sb * p.b_stage_bytes, c * 64, n0, ebase + g * p.b_group);
+              }
+              if (++sb == p.b_stages) { sb = 0; pb ^= 1; ++b_pass; }
             }
           }
         }
@@ -384,7 +473,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       const uint32_t a_sub_u = (MODE == MODE_D) ? (kATileBytes >> 4) : 64u;  // H: 8 pixels = 8 rows of 128 B
       const uint32_t n_tile = p.n_tile, sub = p.sub, bgroup = p.b_group;
       const uint32_t d_group_stride = sub * n_tile;
-      uint32_t sa = 0, pa = 0, sb = 0, pb = 0, as = 0, ap = 0;
+      uint32_t sa = 0, pa = 0, sb = 0, pb = 0, as = 0, ap = 0, b_pass_m = 0;
       bool b_loaded = false;
       for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
         mbar_wait(&acc_empty[as], ap ^ 1);
@@ -403,7 +492,27 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           }
           int e = ebase;
           const uint32_t first_mask = (c == 0) ? p.tap_first_mask : 0u;
-          for (int g = 0; g < n_bgroups; ++g) {
+          bool fast_done = false;
+          if (MODE == MODE_H && ks == 4 && p.fast_id && !(p.dbg_skip & ~3)) {
+            IssueRing ring{b_full, b_empty, sb, pb};
+            const uint32_t acc_c = (c > 0) ? 1u : 0u;
+#define DP_FAST_CASE(K, S, G)                                                                                      \
+  case (K) * 100 + (S) * 10 + (G):                                                                                   \
+    issue_chunk_h<K, S, G>(p, ring, a_stage_desc, b_desc0, b_stage_u, b_ent_u, d_stage, n_tile, idesc, acc_c, c,   \
+                           b_loaded, tc, item);                                                                      \
+    fast_done = true;                                                                                                \
+    break;
+            switch (p.fast_id) {
+              DP_FAST_CASE(3, 1, 1) DP_FAST_CASE(3, 1, 3) DP_FAST_CASE(3, 1, 9)
+              DP_FAST_CASE(3, 2, 1) DP_FAST_CASE(3, 2, 3) DP_FAST_CASE(3, 2, 9)
+              DP_FAST_CASE(4, 1, 1) DP_FAST_CASE(4, 1, 2) DP_FAST_CASE(4, 1, 4)
+              DP_FAST_CASE(4, 2, 1) DP_FAST_CASE(4, 2, 2) DP_FAST_CASE(4, 2, 4)
+              default: break;
+            }
+#undef DP_FAST_CASE
+            sb = ring.sb; pb = ring.pb;
+          }
+          for (int g = 0; g < (fast_done ? 0 : n_bgroups); ++g) {
             if (MODE == MODE_T) {
               mbar_wait(&a_full[sa], pa);
               a_stage_desc = a_desc0 + sa * a_stage_u;
@@ -411,24 +520,25 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             if (p.b_resident) {
               sb = c;                                   // stage c == channel chunk c, filled once
               if (!b_loaded) mbar_wait(&b_full[sb], 0);
-            } else {
+            } else if (!((p.dbg_skip & 16) && b_pass_m)) {
               mbar_wait(&b_full[sb], pb);
             }
-            tc_fence_after();
+            if (!(p.dbg_skip & 32)) tc_fence_after();
             trace_ev(tc, 2, item);
             uint64_t b_desc = b_desc0 + sb * b_stage_u;
             if (ks == 4) {
               for (uint32_t j = 0; j < bgroup; ++j, ++e, b_desc += b_ent_u) {
                 const uint32_t flag0 = ((first_mask >> e) & 1u) ^ 1u;
-                uint64_t a_desc = a_stage_desc + p.tap_a[e];
+                uint64_t a_desc = a_stage_desc + ((p.dbg_skip & 64) ? 0u : p.tap_a[e]);
                 uint32_t d = d_stage + p.tap_d[e];
                 for (uint32_t s = 0; s < sub; ++s, a_desc += a_sub_u, d += n_tile)
                   umma_f16_ss_k4(d, a_desc, b_desc, idesc, flag0);
+                trace_ev(tc, 4, item);
               }
             } else if (ks == 2) {  // 32-channel tail chunk
               for (uint32_t j = 0; j < bgroup; ++j, ++e, b_desc += b_ent_u) {
                 const uint32_t flag0 = ((first_mask >> e) & 1u) ^ 1u;
-                uint64_t a_desc = a_stage_desc + p.tap_a[e];
+                uint64_t a_desc = a_stage_desc + ((p.dbg_skip & 64) ? 0u : p.tap_a[e]);
                 uint32_t d = d_stage + p.tap_d[e];
                 for (uint32_t s = 0; s < sub; ++s, a_desc += a_sub_u, d += n_tile)
                   umma_f16_ss_k2(d, a_desc, b_desc, idesc, flag0);
@@ -436,7 +546,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             } else {  // other channel tails (Cin % 64 in {16, 48})
               for (uint32_t j = 0; j < bgroup; ++j, ++e, b_desc += b_ent_u) {
                 const uint32_t flag0 = ((first_mask >> e) & 1u) ^ 1u;
-                uint64_t a_desc = a_stage_desc + p.tap_a[e];
+                uint64_t a_desc = a_stage_desc + ((p.dbg_skip & 64) ? 0u : p.tap_a[e]);
                 uint32_t d = d_stage + p.tap_d[e];
                 for (uint32_t s = 0; s < sub; ++s, a_desc += a_sub_u, d += n_tile)
                   for (int k = 0; k < ks; ++k)
@@ -444,9 +554,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
               }
             }
             if (!p.b_resident) {
-              if (p.b_pair) umma_commit_mcast(&b_empty[sb], 3);
+              if ((p.dbg_skip & 16) && b_pass_m) { /* timing experiment: no ring protocol after the first pass */ }
+              else if (p.b_pair) umma_commit_mcast(&b_empty[sb], 3);
               else umma_commit(&b_empty[sb]);
-              if (++sb == p.b_stages) { sb = 0; pb ^= 1; }
+              trace_ev(tc, 5, item);
+              if (++sb == p.b_stages) { sb = 0; pb ^= 1; ++b_pass_m; }
             }
             if (MODE == MODE_T) {
               umma_commit(&a_empty[sa]);
@@ -465,14 +577,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       }
       trace_close(p, tc, 1);
     }
-  } else if (warp >= 4 && warp < 8) {
+  } else if ((warp >= 4 && warp < 8) || (kEpiGroups == 2 && warp >= 8)) {
     // ------------------------------------------------------------------ epilogue
     const int q = warp & 3;
+    const int eg = (warp >= 8) ? 1 : 0;   // epilogue group: takes the work units u with u % kEpiGroups == eg
     const int r = q * 32 + lane;  // accumulator row == TMEM lane == pixel within the sub-tile
     const bool has_scale = p.epi_scale != nullptr;
     uint32_t as = 0, ap = 0;
     TraceCursor tc;
-    if (r == 0) tc = trace_open(p, 2);
+    if (r == 0 && eg == 0) tc = trace_open(p, 2);
     if constexpr (RESIDUAL) {
       // Inception-ResNet block tail (MODE_D, sub == 1, one accumulator group): out = act(out_old + acc + shift),
       // in place.  The old values of this thread's pixel row (<= 256 channels = 16 x 32 B) are fetched BEFORE the
@@ -532,9 +645,17 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       tc_fence_after();
       trace_ev(tc, 0, item);
       const int ch0 = wi.nt * p.n_tile;
-      for (int g = 0; g < p.n_groups; ++g) {
+      int unit = 0;   // (accumulator [, 32-column step]) counter, identical in both groups
+      for (int g = 0; g < ((p.dbg_skip & 8) ? 0 : p.n_groups); ++g) {
         const int ph = (MODE == MODE_H) ? g : wi.ph;
         for (int s = 0; s < p.sub; ++s) {
+          if (kEpiGroups == 2 && (p.epi_mode == EPI_HEAD || !p.epi_direct)) {
+            // whole accumulators are the unit: the head needs a pixel's full channel dot product in one thread, the
+            // staged store path owns per-warp staging rows
+            const bool mine = (p.epi_mode == EPI_HEAD && (p.n_groups * p.sub) % 2 == 0) ? ((unit & 1) == eg) : (eg == 0);
+            ++unit;
+            if (!mine) continue;
+          }
           // ---- where does this accumulator row land?
           bool valid;
           long long opix;  // output pixel index (flat over n, oh, ow)
@@ -599,6 +720,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             // 32 columns per step: TMEM -> registers -> BN shift/ReLU -> fp16 -> two 256-bit stores per thread
             // (each a full 32-byte sector of this pixel's channel run); no shared-memory round trip.
             for (int cc = 0; cc < p.n_tile && ch0 + cc < p.cout; cc += 32) {
+              if (kEpiGroups == 2 && ((unit++ & 1) != eg)) continue;
               uint32_t v[2][16];
               const bool two = cc + 16 < p.n_tile && ch0 + cc + 16 < p.cout;
               tmem_ld16(taddr + cc, v[0]);
@@ -616,7 +738,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                   __half2 h2 = __floats2half2_rn(f[2 * i], f[2 * i + 1]);
                   pk[i] = *reinterpret_cast<uint32_t*>(&h2);
                 }
-                if (valid) st_global_v8(orow + cc + 16 * hsel, pk);
+                if (valid && !(p.dbg_skip & 4)) st_global_v8(orow + cc + 16 * hsel, pk);
               }
             }
           } else {
@@ -693,7 +815,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       trace_ev(tc, 1, item);
       if (++as == p.acc_stages) { as = 0; ap ^= 1; }
     }
-    if (r == 0) trace_close(p, tc, 2);
+    if (r == 0 && eg == 0) trace_close(p, tc, 2);
   } else if (PROLOGUE && warp >= 8) {
     // ------------------------------------------------------------------ A-tile pre-activation (MODE_D only)
     const int t = tid - 256;

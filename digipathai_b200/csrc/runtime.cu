@@ -416,6 +416,15 @@ int plan_conv(dp_model* m, const BlobOp& op, int img0, int B, Launch& L) {
     p.b_stage_bytes = p.n_entries * n_tile * 128;
   }
   p.acc_stages = (2 * p.n_groups * p.sub * n_tile <= kTmemCols) ? 2 : 1;
+  // fully unrolled issue sequence (conv_tc.cuh:issue_chunk_h) where one is instantiated
+  p.fast_id = 0;
+  if (p.mode == MODE_H && !m->halo_pad8 && !getenv("DP_NO_FAST_ISSUE") && (op.kind == 3 || op.kind == 4) &&
+      p.box_w == 8 * p.sub + 2) {
+    const int id = op.kind * 100 + p.sub * 10 + p.b_group;
+    static const int have[] = {311, 313, 319, 321, 323, 329, 411, 412, 414, 421, 422, 424};
+    for (int h : have)
+      if (h == id) p.fast_id = id;
+  }
 
   // shared-memory ring depths
   const int budget = 227 * 1024 - ConvSmemLayout::kBarBytes - 2 * n_tile * n_ntiles * 4 - 2 * p.n_chunks * 64 * 4 - 256 * 4 -
@@ -720,13 +729,16 @@ int run_op(dp_model* m, SubPlan* sp, int i, cudaStream_t st) {
       cp.epi_direct = (m->epi_direct || cp.residual || cp.n_tile * cp.n_ntiles != cp.cout) &&
                       ((cp.out_choff % 16) == 0) && ((cp.out_ctot % 16) == 0);
       cp.trace = (m->trace_op == i) ? m->trace_dev : nullptr;
+      { const char* dbg = getenv("DP_DBG_SKIP"); cp.dbg_skip = dbg ? atoi(dbg) : 0; }
       cp.gt = (m->stamp && m->gt_dev) ? m->gt_dev + 2 * i : nullptr;
       // Programmatic dependent launch: the kernel's setup (barrier init, TMEM alloc, BN constants -> smem)
       // runs before its griddepcontrol.wait and so overlaps the tail of the preceding kernel in the stream.
       cudaLaunchConfig_t cfg;
       memset(&cfg, 0, sizeof cfg);
       cfg.gridDim = dim3(L.grid);
-      cfg.blockDim = dim3(L.prologue ? 384 : 256);
+      cfg.blockDim = dim3(cp.residual ? dp::ConvKernelShape<false, true>::kThreads
+                                      : (L.prologue ? dp::ConvKernelShape<true, false>::kThreads
+                                                    : dp::ConvKernelShape<false, false>::kThreads));
       cfg.dynamicSmemBytes = L.smem;
       cfg.stream = st;
       cudaLaunchAttribute attr[2];
@@ -893,6 +905,8 @@ int dp_model_create(const void* blob, size_t nbytes, int device, int max_batch, 
       return fail("cudaFuncSetAttribute(MaxDynamicSharedMemorySize) failed: %s", cudaGetErrorString(cudaGetLastError()));
     }
   }
+  env = getenv("DP_B_PAIR");
+  if (env) m->b_pair = atoi(env);
   env = getenv("DP_NAIVE_CONV");
   if (env && atoi(env)) m->naive_conv = 1;
   env = getenv("DP_DESC_BASE_MODE");

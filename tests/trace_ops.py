@@ -8,6 +8,10 @@ from digipathai_b200.models.densenet import densenet121_unet_program, init_dense
 ops = [int(a) for a in sys.argv[1:]] or [135, 134, 8, 65, 66, 108]
 prog = densenet121_unet_program(init_densenet_weights(0), 256)
 m = TileModel(prog, 0, 32)
+if os.environ.get("TRACE_FIRST"):
+    show_first = int(os.environ["TRACE_FIRST"])
+else:
+    show_first = 3
 m.set_option("use_graph", 0)
 tiles = torch.randint(0, 256, (32, 256, 256, 3), dtype=torch.uint8, device="cuda")
 for _ in range(2):
@@ -18,7 +22,7 @@ EV_DL = {(0, 1): "A_issued", (1, 1): "A_ready", (1, 2): "B_ready", (1, 3): "ph1_
          (1, 5): "ph2_issued", (2, 0): "mid_start", (2, 2): "mid_done", (2, 3): "final_start", (2, 1): "final_done",
          (3, 1): "xf_start", (3, 0): "xf_done", (9, 0): "setup_done", (9, 2): "kernel_entry", (9, 1): "kernel_end"}
 EV = {(0, 1): "A_issued", (0, 2): "B_issued", (1, 0): "acc_free", (1, 1): "A_ready", (1, 2): "B_ready",
-      (1, 3): "item_issued", (2, 0): "acc_full", (2, 1): "epi_done", (3, 0): "xform_done", (9, 0): "setup_done", (9, 2): "kernel_entry", (9, 1): "kernel_end"}
+      (1, 3): "item_issued", (1, 4): "tap_issued", (1, 5): "B_committed", (2, 0): "acc_full", (2, 1): "epi_done", (3, 0): "xform_done", (9, 0): "setup_done", (9, 2): "kernel_entry", (9, 1): "kernel_end"}
 for op in ops:
     m.set_option("trace_op", op)
     m.forward_tile_batch(tiles)
@@ -32,7 +36,7 @@ for op in ops:
     print(f"=== op {op} {prog.ops[op].name}: {len(tr)} events")
     evmap = EV_DL if prog.ops[op].type == 6 else EV
     items = sorted({it for r, e, it, t in tr if r != 9})
-    show = set(items[:3] + items[-2:])
+    show = set(items[:show_first] + items[-2:])
     last = {}
     for r, e, it, t in tr:
         dt = (t - t0) & 0xFFFFFFFF
