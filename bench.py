@@ -34,8 +34,10 @@ METRIC = "tiles_per_sec_256x256_b32"
 UNIT = "tiles/s"
 PATCH, BATCH = 256, 32
 REF_FLOP_PER_TILE = 42316333056  # 21 158 166 528 conv MACs x 2 (reference graph)
-REF_FLOP = {"dense": 42316333056, "inception": 57406652416}   # SURVEY.md 8(d); inception: 28 703 326 208 MACs x 2
-MODEL_DESC = {"dense": "DenseNet-121 U-Net", "inception": "Inception-ResNet-v2 U-Net (--model inception; not the headline config)"}
+REF_FLOP = {"dense": 42316333056, "inception": 57406652416,   # SURVEY.md 8(d); inception: 28 703 326 208 MACs x 2
+            "deeplabv3": 25603100672}                          # 12 801 550 336 conv + depthwise MACs x 2
+MODEL_DESC = {"dense": "DenseNet-121 U-Net", "inception": "Inception-ResNet-v2 U-Net (--model inception; not the headline config)",
+              "deeplabv3": "DeepLabv3+ Xception OS16 (--model deeplabv3; not the headline config)"}
 
 
 def load_peaks():
@@ -102,7 +104,11 @@ def oracle_tiles_per_sec(n_tiles: int, threads: int, seed: int = 0, model: str =
     import torch
     torch.set_num_threads(threads)
     rng = np.random.default_rng(seed)
-    if model == "inception":
+    if model == "deeplabv3":
+        from digipathai_b200.models.deeplab import init_deeplab_weights
+        from oracle import deeplab_ref as densenet_ref
+        w = init_deeplab_weights(0)
+    elif model == "inception":
         from digipathai_b200.models.inception import init_inception_weights
         from oracle import inception_ref as densenet_ref
         w = init_inception_weights(0)
@@ -159,7 +165,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="forward", choices=["forward", "slide"])
-    ap.add_argument("--model", default="dense", choices=["dense", "inception"],
+    ap.add_argument("--model", default="dense", choices=["dense", "inception", "deeplabv3"],
                     help="graph to run (BASELINE configs[1] names the DenseNet U-Net: the default)")
     ap.add_argument("--slide", type=int, default=8192, help="--workload slide: side of the synthetic slide")
     ap.add_argument("--tta", default="", help="--workload slide: comma separated tta_list")
@@ -204,7 +210,11 @@ def main():
         return float(t.item())
 
     peaks, peak_src = load_peaks()
-    if args.model == "inception":
+    if args.model == "deeplabv3":
+        from digipathai_b200.models.deeplab import deeplabv3plus_xception_program, init_deeplab_weights
+        model = engine.TileModel(deeplabv3plus_xception_program(init_deeplab_weights(0), PATCH), device=local,
+                                 max_batch=BATCH)
+    elif args.model == "inception":
         from digipathai_b200.models.inception import inception_resnet_v2_unet_program, init_inception_weights
         model = engine.TileModel(inception_resnet_v2_unet_program(init_inception_weights(0), PATCH), device=local,
                                  max_batch=BATCH)

@@ -145,9 +145,9 @@ def load_trained_models(model, path, patch_size=256, *, device=0, max_batch=32):
         weights = path if isinstance(path, dict) else _load_npz(path)
         return TileModel(inception_resnet_v2_unet_program(weights, patch_size), device=device, max_batch=max_batch)
     if model.__contains__('deeplabv3'):
-        raise NotImplementedError(
-            f"model '{model}': the DenseNet-121 and Inception-ResNet-v2 U-Nets are built for sm_100a; "
-            "DeepLabv3+ (SURVEY.md row a8'') is not yet")
+        from .models.deeplab import deeplabv3plus_xception_program
+        weights = path if isinstance(path, dict) else _load_npz(path)
+        return TileModel(deeplabv3plus_xception_program(weights, patch_size), device=device, max_batch=max_batch)
     raise ValueError("Unknown model provided, allowed models ['dense', 'inception', 'deeplabv3']")
 
 
@@ -225,21 +225,15 @@ def getSegmentation(img_path,
             raise ValueError("Unknown model provided, allowed models ['dense', 'inception', 'deeplabv3']")
         names = [model]
 
-    if 'deeplabv3' in names:
-        # fail before anything is loaded: the third ensemble member (SURVEY.md row a8'') has no sm_100a graph yet
-        raise NotImplementedError(
-            "model 'deeplabv3': the DenseNet-121 and Inception-ResNet-v2 U-Nets are built for sm_100a; DeepLabv3+ "
-            "is not yet, so quick=False (the reference's 3-model ensemble, Segmentation.py:288-291) cannot run. "
-            "Use get_prediction(models={'dense': ..., 'inception': ...}) for the two-model ensemble.")
-
     def weight_source(nm):
         if isinstance(weights, dict) and nm in weights and not isinstance(weights[nm], np.ndarray):
             return weights[nm]
-        if isinstance(weights, dict) and ('conv1/conv' in weights or 'conv2d_1' in weights):
-            family = 'dense' if 'conv1/conv' in weights else 'inception'
+        if isinstance(weights, dict) and ('conv1/conv' in weights or 'conv2d_1' in weights or
+                                          'entry_flow_conv1_1' in weights):
+            family = 'dense' if 'conv1/conv' in weights else ('inception' if 'conv2d_1' in weights else 'deeplabv3')
             if family != nm:
                 raise ValueError(f"weights= holds a '{family}' weight dict but model '{nm}' was requested; pass "
-                                 "weights={'dense': ..., 'inception': ...}")
+                                 "weights={'dense': ..., 'inception': ..., 'deeplabv3': ...}")
             return weights          # a single flat weight dict for `model`
         if isinstance(weights, str):
             return weights

@@ -235,6 +235,223 @@ __global__ void bn_act_pool_kernel(const __half* __restrict__ in, int in_ctot, i
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// DeepLabv3+ helpers (reference: DigiPathAI/models/deeplabv3.py).  All HBM-bound, 8 channels (16 B) per thread.
+//
+// [ReLU] -> DepthwiseConv2D(3x3, stride 1|2, dilation `rate`) -> + shift (BN scale folded into w) [-> ReLU]
+// (SepConv_BN, deeplabv3.py:62-79).  Padding is symmetric `rate` on each side for both strides (stride 1:
+// padding='same'; stride 2: explicit ZeroPadding2D((1,1)) + 'valid'), so input pixel = stride * o + (k - 1) * rate.
+__global__ void dwconv3x3_kernel(const __half* __restrict__ in, int in_ctot, int in_choff, __half* __restrict__ out,
+                                 int out_ctot, int out_choff, int n_img, int H, int W, int C, int stride, int rate,
+                                 const __half* __restrict__ w, const float* __restrict__ shift, int pre_relu,
+                                 int post_relu) {
+  pdl_wait();
+  pdl_launch_dependents();
+  const int OH = H / stride, OW = W / stride, CG = C / 8;
+  const unsigned total = static_cast<unsigned>(n_img) * OH * OW * CG;
+  for (unsigned idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+    const int cg = idx % CG;
+    unsigned r = idx / CG;
+    const int ow = r % OW; r /= OW;
+    const int oh = r % OH;
+    const int n = r / OH;
+    float acc[8];
+    {
+      const float4 s0 = *reinterpret_cast<const float4*>(shift + cg * 8);
+      const float4 s1 = *reinterpret_cast<const float4*>(shift + cg * 8 + 4);
+      acc[0] = s0.x; acc[1] = s0.y; acc[2] = s0.z; acc[3] = s0.w;
+      acc[4] = s1.x; acc[5] = s1.y; acc[6] = s1.z; acc[7] = s1.w;
+    }
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky) {
+      const int ih = oh * stride + (ky - 1) * rate;
+      if (ih < 0 || ih >= H) continue;
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx) {
+        const int iw = ow * stride + (kx - 1) * rate;
+        if (iw < 0 || iw >= W) continue;
+        const uint4 raw = *reinterpret_cast<const uint4*>(
+            in + ((static_cast<long long>(n) * H + ih) * W + iw) * in_ctot + in_choff + cg * 8);
+        const uint4 wraw = *reinterpret_cast<const uint4*>(w + (ky * 3 + kx) * C + cg * 8);
+        const __half2* hv = reinterpret_cast<const __half2*>(&raw);
+        const __half2* wv = reinterpret_cast<const __half2*>(&wraw);
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          float2 x = __half22float2(hv[t]);
+          const float2 k = __half22float2(wv[t]);
+          if (pre_relu) { x.x = fmaxf(x.x, 0.f); x.y = fmaxf(x.y, 0.f); }
+          acc[2 * t] = fmaf(x.x, k.x, acc[2 * t]);
+          acc[2 * t + 1] = fmaf(x.y, k.y, acc[2 * t + 1]);
+        }
+      }
+    }
+    __align__(16) __half2 o[4];
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      float a = acc[2 * t], b = acc[2 * t + 1];
+      if (post_relu) { a = fmaxf(a, 0.f); b = fmaxf(b, 0.f); }
+      o[t] = __floats2half2_rn(a, b);
+    }
+    *reinterpret_cast<uint4*>(out + ((static_cast<long long>(n) * OH + oh) * OW + ow) * out_ctot + out_choff + cg * 8) =
+        *reinterpret_cast<const uint4*>(o);
+  }
+}
+
+// GlobalAveragePooling2D (deeplabv3.py:378): [n][H][W][C] -> [n][1][1][C], fp32 accumulation.
+__global__ void global_avgpool_kernel(const __half* __restrict__ in, int in_ctot, int in_choff,
+                                      __half* __restrict__ out, int out_ctot, int out_choff, int n_img, int HW, int C) {
+  pdl_wait();
+  pdl_launch_dependents();
+  const int CG = C / 8;
+  const unsigned total = static_cast<unsigned>(n_img) * CG;
+  for (unsigned idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+    const int cg = idx % CG, n = idx / CG;
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    const __half* src = in + static_cast<long long>(n) * HW * in_ctot + in_choff + cg * 8;
+    for (int p = 0; p < HW; ++p) {
+      const uint4 raw = *reinterpret_cast<const uint4*>(src + static_cast<long long>(p) * in_ctot);
+      const __half2* hv = reinterpret_cast<const __half2*>(&raw);
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        const float2 f = __half22float2(hv[t]);
+        acc[2 * t] += f.x;
+        acc[2 * t + 1] += f.y;
+      }
+    }
+    const float inv = 1.f / static_cast<float>(HW);
+    __align__(16) __half2 o[4];
+#pragma unroll
+    for (int t = 0; t < 4; ++t) o[t] = __floats2half2_rn(acc[2 * t] * inv, acc[2 * t + 1] * inv);
+    *reinterpret_cast<uint4*>(out + static_cast<long long>(n) * out_ctot + out_choff + cg * 8) =
+        *reinterpret_cast<const uint4*>(o);
+  }
+}
+
+// Bilinear align_corners resize of a 1x1 map == broadcast (deeplabv3.py:385-388): [n][1][1][C] -> [n][H][W][C range].
+__global__ void broadcast_kernel(const __half* __restrict__ in, int in_ctot, int in_choff, __half* __restrict__ out,
+                                 int out_ctot, int out_choff, int n_img, int HW, int C) {
+  pdl_wait();
+  pdl_launch_dependents();
+  const int CG = C / 8;
+  const unsigned total = static_cast<unsigned>(n_img) * HW * CG;
+  for (unsigned idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+    const int cg = idx % CG;
+    const unsigned r = idx / CG;
+    const int n = r / HW;
+    const uint4 v = *reinterpret_cast<const uint4*>(in + static_cast<long long>(n) * in_ctot + in_choff + cg * 8);
+    *reinterpret_cast<uint4*>(out + static_cast<long long>(r) * out_ctot + out_choff + cg * 8) = v;
+  }
+}
+
+// tf.compat.v1.image.resize(method='bilinear', align_corners=True) (deeplabv3.py:420): src = dst * (in-1)/(out-1),
+// top = floor, bottom = min(top + 1, in - 1), fp32 lerp (rows first, then columns, as TF's kernel does).
+__device__ __forceinline__ void bilinear_ac_coord(int o, int in_size, int out_size, int& i0, int& i1, float& f) {
+  const float scale = (out_size > 1) ? static_cast<float>(in_size - 1) / static_cast<float>(out_size - 1) : 0.f;
+  const float s = static_cast<float>(o) * scale;
+  i0 = static_cast<int>(floorf(s));
+  if (i0 > in_size - 1) i0 = in_size - 1;
+  i1 = (i0 + 1 < in_size) ? i0 + 1 : in_size - 1;
+  f = s - static_cast<float>(i0);
+}
+
+__global__ void resize_bilinear_kernel(const __half* __restrict__ in, int in_ctot, int in_choff,
+                                       __half* __restrict__ out, int out_ctot, int out_choff, int n_img, int H, int W,
+                                       int OH, int OW, int C) {
+  pdl_wait();
+  pdl_launch_dependents();
+  const int CG = C / 8;
+  const unsigned total = static_cast<unsigned>(n_img) * OH * OW * CG;
+  for (unsigned idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+    const int cg = idx % CG;
+    unsigned r = idx / CG;
+    const int ow = r % OW; r /= OW;
+    const int oh = r % OH;
+    const int n = r / OH;
+    int y0, y1, x0, x1;
+    float fy, fx;
+    bilinear_ac_coord(oh, H, OH, y0, y1, fy);
+    bilinear_ac_coord(ow, W, OW, x0, x1, fx);
+    const __half* base = in + static_cast<long long>(n) * H * W * in_ctot + in_choff + cg * 8;
+    const uint4 r00 = *reinterpret_cast<const uint4*>(base + (static_cast<long long>(y0) * W + x0) * in_ctot);
+    const uint4 r01 = *reinterpret_cast<const uint4*>(base + (static_cast<long long>(y0) * W + x1) * in_ctot);
+    const uint4 r10 = *reinterpret_cast<const uint4*>(base + (static_cast<long long>(y1) * W + x0) * in_ctot);
+    const uint4 r11 = *reinterpret_cast<const uint4*>(base + (static_cast<long long>(y1) * W + x1) * in_ctot);
+    const __half2* a = reinterpret_cast<const __half2*>(&r00);
+    const __half2* b = reinterpret_cast<const __half2*>(&r01);
+    const __half2* c = reinterpret_cast<const __half2*>(&r10);
+    const __half2* d = reinterpret_cast<const __half2*>(&r11);
+    __align__(16) __half2 o[4];
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      const float2 va = __half22float2(a[t]), vb = __half22float2(b[t]), vc = __half22float2(c[t]), vd = __half22float2(d[t]);
+      const float tx = va.x + (vb.x - va.x) * fx, bx = vc.x + (vd.x - vc.x) * fx;
+      const float ty = va.y + (vb.y - va.y) * fx, by = vc.y + (vd.y - vc.y) * fx;
+      o[t] = __floats2half2_rn(tx + (bx - tx) * fy, ty + (by - ty) * fy);
+    }
+    *reinterpret_cast<uint4*>(out + ((static_cast<long long>(n) * OH + oh) * OW + ow) * out_ctot + out_choff + cg * 8) =
+        *reinterpret_cast<const uint4*>(o);
+  }
+}
+
+// Logits conv collapsed to the class-1-minus-class-0 difference (softmax over 2 classes == sigmoid of it):
+// one warp per pixel, lanes split the channels 8 at a time, warp-shuffle reduction, fp32 result.
+__global__ void head_dot_kernel(const __half* __restrict__ in, int in_ctot, int in_choff, int C, long long n_pix,
+                                const float* __restrict__ w, float bias, float* __restrict__ out, int out_stride_f) {
+  pdl_wait();
+  pdl_launch_dependents();
+  const int lane = threadIdx.x & 31;
+  const long long warp0 = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) >> 5;
+  const long long n_warps = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
+  for (long long pix = warp0; pix < n_pix; pix += n_warps) {
+    const __half* src = in + pix * in_ctot + in_choff;
+    float acc = 0.f;
+    for (int c0 = lane * 8; c0 < C; c0 += 256) {
+      const uint4 raw = *reinterpret_cast<const uint4*>(src + c0);
+      const __half2* hv = reinterpret_cast<const __half2*>(&raw);
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        const float2 f = __half22float2(hv[t]);
+        acc = fmaf(f.x, w[c0 + 2 * t], acc);
+        acc = fmaf(f.y, w[c0 + 2 * t + 1], acc);
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) out[pix * out_stride_f] = acc + bias;
+  }
+}
+
+// Final bilinear align_corners resize of the logit difference to PxP + sigmoid + inverse TTA (deeplabv3.py:440-456,
+// Segmentation.py:158-167).
+__global__ void head_resize_kernel(const float* __restrict__ z, int z_stride_f, int n_img, int h, int w, int P,
+                                   const PassDesc* __restrict__ pass, int img0) {
+  pdl_wait();
+  pdl_launch_dependents();
+  const int tta_code = pass->tta_out;
+  float* __restrict__ out = pass->probs_out + static_cast<long long>(img0) * P * P;
+  const long long total = static_cast<long long>(n_img) * P * P;
+  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int j = idx % P;
+    const int i = (idx / P) % P;
+    const int n = idx / (static_cast<long long>(P) * P);
+    int y0, y1, x0, x1;
+    float fy, fx;
+    bilinear_ac_coord(i, h, P, y0, y1, fy);
+    bilinear_ac_coord(j, w, P, x0, x1, fx);
+    const float* base = z + static_cast<long long>(n) * h * w * z_stride_f;
+    const float a = base[(static_cast<long long>(y0) * w + x0) * z_stride_f];
+    const float b = base[(static_cast<long long>(y0) * w + x1) * z_stride_f];
+    const float c = base[(static_cast<long long>(y1) * w + x0) * z_stride_f];
+    const float d = base[(static_cast<long long>(y1) * w + x1) * z_stride_f];
+    const float top = a + (b - a) * fx, bot = c + (d - c) * fx;
+    const float zz = top + (bot - top) * fy;
+    int di, dj;
+    d4_src(tta_code, i, j, P, di, dj);
+    out[(static_cast<long long>(n) * P + di) * P + dj] = 1.f / (1.f + expf(-zz));
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // Head for the naive (debug) path: 1x1 conv C->2 + softmax channel 1 + inverse TTA (densenet.py:156).
 __global__ void head_naive_kernel(const __half* __restrict__ in, int in_ctot, int in_choff, int C, int n_img,
                                   int P, const float* __restrict__ w, float bias,

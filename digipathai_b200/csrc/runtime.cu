@@ -99,7 +99,8 @@ struct BlobBuf {
   int32_t H, W, C, pad;
 };
 enum : int { OP_STEM_IM2COL = 1, OP_MAXPOOL = 2, OP_CONV = 3, OP_BNPOOL = 4, OP_STEM_S2D = 5, OP_DENSE_LAYER = 6,
-              OP_AVGPOOL3 = 7 };
+              OP_AVGPOOL3 = 7, OP_DWCONV = 8, OP_GAP = 9, OP_BCAST = 10, OP_RESIZE = 11, OP_HEAD_DOT = 12,
+              OP_HEAD_RESIZE = 13 };
 struct BlobOp {
   int32_t type, in_buf, in_choff, cin, out_buf, out_choff, cout, kind, relu, pro, head, pool;
   float head_b;
@@ -686,6 +687,73 @@ int run_op(dp_model* m, SubPlan* sp, int i, cudaStream_t st) {
       LAUNCH_OK();
       return 0;
     }
+    case OP_DWCONV: {
+      const BlobBuf& ib = m->bufs[op.in_buf];
+      const BlobBuf& ob = m->bufs[op.out_buf];
+      const int stride = op.rsv[0] & 0xff, rate = (op.rsv[0] >> 8) & 0xff;
+      if ((stride != 1 && stride != 2) || rate < 1 || ib.H % stride || ob.H != ib.H / stride || op.cin % 8)
+        return fail("depthwise conv: bad geometry (stride %d rate %d map %d -> %d)", stride, rate, ib.H, ob.H);
+      const long long total = (long long)B * ob.H * ob.W * (op.cin / 8);
+      cudaError_t le = launch_pdl(dp::dwconv3x3_kernel, grid_for(total, 256), 256, st, m->use_pdl != 0, buf_at(op.in_buf),
+                                  ib.C, op.in_choff, buf_at(op.out_buf), ob.C, op.out_choff, B, ib.H, ib.W, op.cin, stride,
+                                  rate, dptr<__half>(m, op.w_off), dptr<float>(m, op.epi_shift_off), op.pro, op.relu);
+      if (le != cudaSuccess) return fail("depthwise conv launch failed: %s", cudaGetErrorString(le));
+      LAUNCH_OK();
+      return 0;
+    }
+    case OP_GAP:
+    case OP_BCAST: {
+      const BlobBuf& ib = m->bufs[op.in_buf];
+      const BlobBuf& ob = m->bufs[op.out_buf];
+      const BlobBuf& small = (op.type == OP_GAP) ? ob : ib;
+      const BlobBuf& big = (op.type == OP_GAP) ? ib : ob;
+      if (small.H != 1 || small.W != 1) return fail("global pool / broadcast needs a 1x1 map on one side");
+      cudaError_t le;
+      if (op.type == OP_GAP)
+        le = launch_pdl(dp::global_avgpool_kernel, grid_for((long long)B * (op.cin / 8), 128), 128, st, m->use_pdl != 0,
+                        buf_at(op.in_buf), ib.C, op.in_choff, buf_at(op.out_buf), ob.C, op.out_choff, B, big.H * big.W, op.cin);
+      else
+        le = launch_pdl(dp::broadcast_kernel, grid_for((long long)B * big.H * big.W * (op.cin / 8), 256), 256, st,
+                        m->use_pdl != 0, buf_at(op.in_buf), ib.C, op.in_choff, buf_at(op.out_buf), ob.C, op.out_choff, B,
+                        big.H * big.W, op.cin);
+      if (le != cudaSuccess) return fail("pool/broadcast launch failed: %s", cudaGetErrorString(le));
+      LAUNCH_OK();
+      return 0;
+    }
+    case OP_RESIZE: {
+      const BlobBuf& ib = m->bufs[op.in_buf];
+      const BlobBuf& ob = m->bufs[op.out_buf];
+      const long long total = (long long)B * ob.H * ob.W * (op.cin / 8);
+      cudaError_t le = launch_pdl(dp::resize_bilinear_kernel, grid_for(total, 256), 256, st, m->use_pdl != 0,
+                                  buf_at(op.in_buf), ib.C, op.in_choff, buf_at(op.out_buf), ob.C, op.out_choff, B, ib.H, ib.W,
+                                  ob.H, ob.W, op.cin);
+      if (le != cudaSuccess) return fail("resize launch failed: %s", cudaGetErrorString(le));
+      LAUNCH_OK();
+      return 0;
+    }
+    case OP_HEAD_DOT: {
+      const BlobBuf& ib = m->bufs[op.in_buf];
+      const BlobBuf& ob = m->bufs[op.out_buf];
+      if (ob.C != 8 || ob.H != ib.H || op.cin % 8) return fail("head dot: output buffer must be [H][W][8] (one fp32 per pixel)");
+      const long long n_pix = (long long)B * ib.H * ib.W;
+      cudaError_t le = launch_pdl(dp::head_dot_kernel, grid_for(n_pix * 32, 256), 256, st, m->use_pdl != 0, buf_at(op.in_buf),
+                                  ib.C, op.in_choff, op.cin, n_pix, dptr<float>(m, op.head_w_off), op.head_b,
+                                  reinterpret_cast<float*>(buf_at(op.out_buf)), 4);
+      if (le != cudaSuccess) return fail("head dot launch failed: %s", cudaGetErrorString(le));
+      LAUNCH_OK();
+      return 0;
+    }
+    case OP_HEAD_RESIZE: {
+      const BlobBuf& ib = m->bufs[op.in_buf];
+      if (ib.C != 8) return fail("head resize: input buffer must be [H][W][8] (one fp32 per pixel)");
+      const long long total = (long long)B * m->patch * m->patch;
+      cudaError_t le = launch_pdl(dp::head_resize_kernel, grid_for(total, 256), 256, st, m->use_pdl != 0,
+                                  reinterpret_cast<const float*>(buf_at(op.in_buf)), 4, B, ib.H, ib.W, m->patch, m->pass_dev,
+                                  img0);
+      if (le != cudaSuccess) return fail("head resize launch failed: %s", cudaGetErrorString(le));
+      LAUNCH_OK();
+      return 0;
+    }
     case OP_AVGPOOL3: {
       const BlobBuf& ib = m->bufs[op.in_buf];
       const BlobBuf& ob = m->bufs[op.out_buf];
@@ -1050,7 +1118,8 @@ static int run_range(dp_model* m, int B, int op_begin, int op_end, const dp::Pas
   for (int i = op_begin; i < op_end; ++i) {
     const BlobOp& op = m->ops[i];
     if ((op.type == OP_STEM_IM2COL || op.type == OP_STEM_S2D) && (!d.slide || !d.coords)) return fail("op %d: stem needs a slide and coordinates", i);
-    if (op.type == OP_CONV && op.head && !d.probs_out) return fail("op %d: head needs a probability output buffer", i);
+    if (((op.type == OP_CONV && op.head) || op.type == OP_HEAD_RESIZE) && !d.probs_out)
+      return fail("op %d: head needs a probability output buffer", i);
     if (m->profile) CU_OK(cudaEventRecord(m->ev[2 * i], st));
     if (run_op(m, &plan->subs[0], i, st)) {
       g_err = "op " + std::to_string(i) + ": " + g_err;

@@ -26,6 +26,9 @@ from typing import List, Optional
 import numpy as np
 
 OP_STEM_IM2COL, OP_MAXPOOL, OP_CONV, OP_BNPOOL, OP_STEM_S2D, OP_DENSE_LAYER, OP_AVGPOOL3 = 1, 2, 3, 4, 5, 6, 7
+# DeepLabv3+ (models/deeplab.py): depthwise 3x3 (stride / dilation), global average pool, broadcast of a 1x1 map,
+# bilinear align_corners resize, logit-difference dot product, and resize + sigmoid + inverse-TTA head
+OP_DWCONV, OP_GAP, OP_BCAST, OP_RESIZE, OP_HEAD_DOT, OP_HEAD_RESIZE = 8, 9, 10, 11, 12, 13
 KIND_1X1, KIND_3X3, KIND_UP2, KIND_STEM4, KIND_TAPS = 1, 3, 4, 5, 6
 POOL_PAD1_ZERO, POOL_TF_SAME = 0, 1   # OP_MAXPOOL `pool` field: ZeroPadding2D(1)+valid (densenet.py:122-123) / padding='same'
 PRO_NONE, PRO_AFFINE, PRO_AFFINE_RELU = 0, 1, 2
@@ -59,6 +62,7 @@ class Op:
     kw: int = 0
     stride: int = 1
     residual: int = 0                       # OP_CONV: out = act(out_old + conv + shift), in place (inception.py:152-160)
+    rate: int = 1                           # OP_DWCONV: dilation rate (stride in `stride`, pre-ReLU in `pro`, post-ReLU in `relu`)
     name: str = ""
 
 
@@ -213,6 +217,9 @@ def serialize(prog: Program) -> bytes:
             put(o.pro_scale, np.float32), put(o.pro_shift, np.float32), put(o.head_w, np.float32),
             put(o.w2, np.float16), 0,
         ]
+        if o.type == OP_DWCONV:
+            assert o.w is not None and o.w.shape == (9, o.cin) and o.epi_shift is not None and o.cin % 8 == 0, o.name
+            assert o.stride in (1, 2) and 1 <= o.rate < 256, o.name
         if o.type == OP_DENSE_LAYER:
             assert o.w is not None and o.w.shape == (1, 128, o.cin) and o.w2 is not None and o.w2.shape == (9, 32, 128)
             assert o.cout == 32 and o.in_buf == o.out_buf and o.pro_scale is not None and o.epi_shift is not None
@@ -220,7 +227,8 @@ def serialize(prog: Program) -> bytes:
             struct.pack(
                 "<12if3i8q", o.type, o.in_buf, o.in_choff, o.cin, o.out_buf, o.out_choff, o.cout, o.kind, o.relu,
                 o.pro, o.head, o.pool, float(o.head_b),
-                (o.kh | (o.kw << 8) | (o.stride << 16)) if o.type == OP_CONV else o.mid_buf,
+                (o.kh | (o.kw << 8) | (o.stride << 16)) if o.type == OP_CONV else
+                ((o.stride | (o.rate << 8)) if o.type == OP_DWCONV else o.mid_buf),
                 o.residual if o.type == OP_CONV else o.safe_cin, 0, *offs,
             )
         )

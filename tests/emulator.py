@@ -10,9 +10,10 @@ import numpy as np
 import torch
 
 from digipathai_b200 import tta
-from digipathai_b200.program import (KIND_1X1, KIND_3X3, KIND_STEM4, KIND_TAPS, KIND_UP2, OP_AVGPOOL3, OP_BNPOOL,
-                                     OP_CONV, OP_MAXPOOL, OP_DENSE_LAYER, OP_STEM_IM2COL, OP_STEM_S2D,
-                                     POOL_TF_SAME, Program, tap_offsets)
+from digipathai_b200.program import (KIND_1X1, KIND_3X3, KIND_STEM4, KIND_TAPS, KIND_UP2, OP_AVGPOOL3, OP_BCAST,
+                                     OP_BNPOOL, OP_CONV, OP_DWCONV, OP_GAP, OP_HEAD_DOT, OP_HEAD_RESIZE, OP_MAXPOOL,
+                                     OP_DENSE_LAYER, OP_RESIZE, OP_STEM_IM2COL, OP_STEM_S2D, POOL_TF_SAME, Program,
+                                     tap_offsets)
 
 
 def entries(kind, op=None, H=0, W=0):
@@ -76,6 +77,26 @@ def maxpool_same(x_nchw: torch.Tensor) -> torch.Tensor:
     return torch.nn.functional.max_pool2d(torch.nn.functional.pad(x_nchw, pad, value=float("-inf")), 3, stride=2)
 
 
+def dwconv_eval(op, x: torch.Tensor) -> torch.Tensor:
+    """[ReLU] -> depthwise 3x3 (stride, dilation; explicit symmetric padding as deeplabv3.py:62-71) + shift [-> ReLU]
+    on fp32 [n,h,w,c]; weights are the packed fp16 [9][C] with the BN scale folded in."""
+    c = op.cin
+    if op.pro:
+        x = torch.relu(x)
+    w = torch.from_numpy(op.w.astype(np.float32)).reshape(3, 3, c).permute(2, 0, 1).unsqueeze(1).contiguous()
+    pad = op.rate  # (3 + 2 (rate - 1) - 1) / 2, both strides
+    y = torch.nn.functional.conv2d(x.permute(0, 3, 1, 2), w, None, stride=op.stride, padding=pad, dilation=op.rate,
+                                   groups=c).permute(0, 2, 3, 1)
+    y = y + torch.from_numpy(np.asarray(op.epi_shift, np.float32))
+    return torch.relu(y) if op.relu else y
+
+
+def resize_bilinear_ac(x_nhwc: torch.Tensor, oh: int, ow: int) -> torch.Tensor:
+    """tf.compat.v1.image.resize(method='bilinear', align_corners=True)."""
+    return torch.nn.functional.interpolate(x_nhwc.permute(0, 3, 1, 2), size=(oh, ow), mode="bilinear",
+                                           align_corners=True).permute(0, 2, 3, 1)
+
+
 def stem_im2col(tiles_u8: np.ndarray, code: int) -> torch.Tensor:
     """tiles uint8 [B,P,P,3] (reference [x,y,c] orientation) -> fp32 [B,P/2,P/2,160]."""
     B, P = tiles_u8.shape[:2]
@@ -134,6 +155,26 @@ def run(prog: Program, tiles_u8: np.ndarray, tta_in: int = 0, tta_out: int = 0, 
             x = bufs[op.in_buf][..., op.in_choff:op.in_choff + op.cin].permute(0, 3, 1, 2)
             y = torch.nn.functional.avg_pool2d(x, 3, stride=1, padding=1, count_include_pad=False)
             bufs[op.out_buf][..., op.out_choff:op.out_choff + op.cin] = q(y.permute(0, 2, 3, 1))
+        elif op.type == OP_DWCONV:
+            x = bufs[op.in_buf][..., op.in_choff:op.in_choff + op.cin]
+            bufs[op.out_buf][..., op.out_choff:op.out_choff + op.cin] = q(dwconv_eval(op, x))
+        elif op.type == OP_GAP:
+            x = bufs[op.in_buf][..., op.in_choff:op.in_choff + op.cin]
+            bufs[op.out_buf][..., op.out_choff:op.out_choff + op.cin] = q(x.mean(dim=(1, 2), keepdim=True))
+        elif op.type == OP_BCAST:
+            x = bufs[op.in_buf][..., op.in_choff:op.in_choff + op.cin]
+            bufs[op.out_buf][..., op.out_choff:op.out_choff + op.cin] = x   # broadcasts over H, W
+        elif op.type == OP_RESIZE:
+            x = bufs[op.in_buf][..., op.in_choff:op.in_choff + op.cin]
+            oh, ow = prog.bufs[op.out_buf][:2]
+            bufs[op.out_buf][..., op.out_choff:op.out_choff + op.cin] = q(resize_bilinear_ac(x, oh, ow))
+        elif op.type == OP_HEAD_DOT:
+            x = bufs[op.in_buf][..., op.in_choff:op.in_choff + op.cin]
+            head_logit = x @ f(op.head_w) + op.head_b          # fp32 [n,h,w], kept in fp32 (not a fp16 buffer)
+        elif op.type == OP_HEAD_RESIZE:
+            z = resize_bilinear_ac(head_logit.unsqueeze(-1), P, P)[..., 0]
+            pr = torch.sigmoid(z).numpy()
+            probs = np.stack([tta.apply(tta.inverse(tta_out), t) for t in pr])
         elif op.type == OP_BNPOOL:
             x = bufs[op.in_buf][..., op.in_choff:op.in_choff + op.cin]
             y = x * f(op.epi_scale) + f(op.epi_shift)

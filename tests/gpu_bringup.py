@@ -136,6 +136,38 @@ def run_full_inception(batch=2, patch=256):
             print(f"     buf {nm:12s} max_abs_diff {d.max():.3e} mean {d.mean():.3e} (ref max {np.abs(want).max():.2f})", flush=True)
 
 
+def run_full_deeplab(batch=2, patch=256):
+    import numpy as np
+    import torch
+    import emulator
+    from digipathai_b200.engine import TileModel
+    from digipathai_b200.models.deeplab import deeplabv3plus_xception_program, init_deeplab_weights
+    from oracle import deeplab_ref as R
+    rng = np.random.default_rng(1)
+    tiles = rng.integers(0, 256, (batch, patch, patch, 3)).astype(np.uint8)
+    w = init_deeplab_weights(0)
+    x = (tiles.astype(np.float32) - 128) / 128
+    R.calibrate_bn(w, x)
+    y = R.forward(w, x)[..., 1]
+    prog = deeplabv3plus_xception_program(w, patch)
+    emu, ebufs = emulator.run(prog, tiles, keep=True)
+    print(f"  emulator(fp16 storage) vs oracle: max {np.abs(emu - y).max():.3e} mean {np.abs(emu - y).mean():.3e}", flush=True)
+    m = TileModel(prog, device=0, max_batch=batch)
+    t = torch.from_numpy(tiles).cuda()
+    for label, naive in (("naive", 1), ("tc", 0)):
+        m.set_option("naive_conv", naive)
+        p = m.forward_tile_batch(t).cpu().numpy()
+        print(f"  deeplab forward {label:5s}: vs oracle max {np.abs(p - y).max():.3e} mean {np.abs(p - y).mean():.3e}  "
+              f"vs emulator max {np.abs(p - emu).max():.3e} mean {np.abs(p - emu).mean():.3e}", flush=True)
+        for bi, nm in enumerate(prog.buf_names):
+            if nm == "LG":
+                continue
+            got = m.read_buffer(bi, batch).astype(np.float32)
+            want = ebufs[bi].numpy()
+            d = np.abs(got - want)
+            print(f"     buf {nm:26s} max_abs_diff {d.max():.3e} mean {d.mean():.3e} (ref max {np.abs(want).max():.2f})", flush=True)
+
+
 def run_full(batch=2, naive_too=True):
     import numpy as np
     import torch
@@ -170,7 +202,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--case")
     ap.add_argument("--timeout", type=int, default=240)
-    ap.add_argument("--set", default="dense", choices=["dense", "inception"])
+    ap.add_argument("--set", default="dense", choices=["dense", "inception", "deeplab"])
     args = ap.parse_args()
     if args.case:
         import conv_cases
@@ -178,6 +210,10 @@ def main():
             run_full()
         elif args.case == "full_inception":
             run_full_inception()
+        elif args.case == "full_deeplab":
+            run_full_deeplab()
+        elif args.case == "full_deeplab64":
+            run_full_deeplab(3, 64)
         elif args.case == "full_inception64":
             run_full_inception(3, 64)
         elif args.case in conv_cases.TAP_CASES:
@@ -187,7 +223,8 @@ def main():
         return
     import conv_cases
     names = list(conv_cases.CASES) + ["full"] if args.set == "dense" else \
-        list(conv_cases.TAP_CASES) + ["full_inception64", "full_inception"]
+        (["full_deeplab64", "full_deeplab"] if args.set == "deeplab" else
+         list(conv_cases.TAP_CASES) + ["full_inception64", "full_inception"])
     for name in names:
         print(f"== {name}", flush=True)
         try:

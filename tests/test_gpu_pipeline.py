@@ -68,8 +68,8 @@ def test_errors_match_the_reference(env):
         getSegmentation(slide, mode='kidney', weights=w)
     with pytest.raises(ValueError, match="Unknown model"):
         getSegmentation(slide, model='resnet', weights=w)
-    with pytest.raises(NotImplementedError):
-        getSegmentation(slide, quick=False, weights=w)
+    with pytest.raises(ValueError, match="holds a 'dense' weight dict"):
+        getSegmentation(slide, quick=False, weights=w)      # the 3-model ensemble needs all three weight sets
     with pytest.raises(FileNotFoundError):
         getSegmentation(slide, batch_size=4)          # no converted weights under ~/.DigiPathAI
 
@@ -99,3 +99,24 @@ def test_ensemble_dense_plus_inception_matches_oracle_pipeline(env):
     assert np.array_equal(want['mean'] == 0, got['mean'] == 0)
     for m in models.values():
         m.close()
+
+
+def test_quick_false_runs_the_three_model_ensemble(env):
+    """quick=False == DenseNet + Inception-ResNet-v2 + DeepLabv3+ (Segmentation.py:288-291), model inner loop order
+    of the reference (dict insertion order), against the oracle loop driving the three oracle graphs."""
+    from digipathai_b200.Segmentation import getSegmentation
+    from digipathai_b200.models.deeplab import init_deeplab_weights
+    from digipathai_b200.models.inception import init_inception_weights
+    from oracle import deeplab_ref, inception_ref, pipeline_ref
+    w, slide, omodels = env
+    rng = np.random.default_rng(12)
+    calib = (rng.integers(0, 256, (2, 256, 256, 3)).astype(np.float32) - 128.0) / 128.0
+    wi = inception_ref.calibrate_bn(init_inception_weights(5), calib)
+    wd = deeplab_ref.calibrate_bn(init_deeplab_weights(6), calib)
+    three = {"dense": omodels["dense"], "inception": inception_ref.OracleModel(wi), "deeplabv3": deeplab_ref.OracleModel(wd)}
+    want_thr, want_mean, want_var = pipeline_ref.getSegmentation(slide, three, 256, 256, 4)
+    got = getSegmentation(slide, patch_size=256, stride_size=256, batch_size=4, quick=False,
+                          weights={"dense": w, "inception": wi, "deeplabv3": wd})
+    mism = got != want_thr
+    print(f"\n3-model ensemble: {int(mism.sum())} / {mism.size} label mismatches")
+    assert (np.abs(want_mean - 0.3)[mism] <= 1e-1).all() and mism.mean() < 0.05
