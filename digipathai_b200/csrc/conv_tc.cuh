@@ -74,6 +74,8 @@ struct ConvParams {
   int epi_mode, relu;
   int out_ctot, out_choff;  // output NHWC buffer: channel stride and channel offset (elements)
   int desc_base_mode;       // 0: descriptor base_offset field = 0; 1: (addr >> 7) & 7
+  int phase_fixed;          // MODE_H up2: item = m_tile * n_phase_items + phase group, n_groups phases per item,
+                            // the CTA's phase group (blockIdx % n_phase_items) never changes -> resident weights
   int fast_id;              // MODE_H: 0 = generic tap loop, else (kind, sub, taps per B stage) of a fully unrolled
                             // issue sequence: fast_id = kind * 100 + sub * 10 + b_group (see issue_chunk_h)
   int dbg_skip;             // TIMING EXPERIMENTS ONLY (wrong results): bit 0 = weight tiles are fetched only on the
@@ -131,6 +133,11 @@ __device__ __forceinline__ WorkItem decode_item(const ConvParams& p, int item) {
   int rest = item / p.n_mtiles;
   wi.nt = rest % p.n_ntiles;
   wi.ph = rest / p.n_ntiles;
+  if (p.phase_fixed) {
+    wi.ph = item % p.n_phase_items;
+    mt = item / p.n_phase_items;
+    wi.nt = 0;
+  }
   wi.m0 = 0; wi.n0 = 0; wi.h0 = 0; wi.w0 = 0;
   if (p.mode == MODE_D) {
     wi.m0 = mt * p.sub * 128;
@@ -207,13 +214,15 @@ struct IssueRing {
   uint32_t sb, pb;
 };
 
-template <int KIND, int SUB, int BG>
+// E0 / NE select a sub-range of the up2 entries (phase-split items: NE = 4 G entries starting at phase group
+// E0 / NE; the resident weight stage then starts at entry E0).
+template <int KIND, int SUB, int BG, int E0 = 0, int NE = ((KIND == 3) ? 9 : 16)>
 __device__ __forceinline__ void issue_chunk_h(const ConvParams& p, IssueRing& r, uint64_t a_stage_desc, uint64_t b_desc0,
                                               uint32_t b_stage_u, uint32_t b_ent_u, uint32_t d_stage, uint32_t n_tile,
                                               uint32_t idesc, uint32_t acc_c, int c, bool b_loaded, TraceCursor& tc,
                                               int item) {
-  constexpr int NE = (KIND == 3) ? 9 : 16;
   constexpr int WW = 8 * SUB + 2;
+  constexpr int G = (KIND == 4) ? ((NE >= 16) ? 4 : NE / 4) : 1;   // accumulator groups (phases per item)
   static_assert(NE % BG == 0, "taps per weight stage must divide the tap count");
 #pragma unroll
   for (int g = 0; g < NE / BG; ++g) {
@@ -228,13 +237,13 @@ __device__ __forceinline__ void issue_chunk_h(const ConvParams& p, IssueRing& r,
     const uint64_t b_desc = b_desc0 + r.sb * b_stage_u;
 #pragma unroll
     for (int j = 0; j < BG; ++j) {
-      const int e = g * BG + j;
+      const int e = E0 + g * BG + j;
       int dy, dx, grp;
       if (KIND == 3) {
         dy = e / 3 - 1; dx = e % 3 - 1; grp = 0;
       } else {
         const int ph = e >> 2, t = e & 3;
-        dy = (ph >> 1) - 1 + (t >> 1); dx = (ph & 1) - 1 + (t & 1); grp = ph;
+        dy = (ph >> 1) - 1 + (t >> 1); dx = (ph & 1) - 1 + (t & 1); grp = ph % G;
       }
       const uint32_t a_off = static_cast<uint32_t>(((dy + 1) * WW + dx + 1) * 8);
       const bool first = (KIND == 3) ? (e == 0) : ((e & 3) == 0);
@@ -266,7 +275,11 @@ struct ConvKernelShape {
   static constexpr int kThreads = (PROLOGUE || kEpiGroups == 2) ? 384 : 256;
 };
 
-template <int MODE, bool PROLOGUE, bool RESIDUAL = false>
+// FAST != 0 compiles exactly one unrolled issue sequence into the kernel (issue_chunk_h): FAST = kind * 100 +
+// sub * 10 + taps-per-weight-stage, or 4000 + 100 G + 10 sub for phase-split up-convs.  One kernel per variant
+// keeps each of them lean: inlining all variants into one kernel cost registers (spills) and instruction-cache
+// footprint and slowed EVERY layer down by 5-10 %.
+template <int MODE, bool PROLOGUE, bool RESIDUAL = false, int FAST = 0>
 __global__ void __launch_bounds__((ConvKernelShape<PROLOGUE, RESIDUAL>::kThreads), 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                const __grid_constant__ ConvParams p) {
@@ -410,7 +423,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         if (blockIdx.x < p.n_items)
           for (int c = 0; c < p.n_chunks; ++c) {
             mbar_expect_tx(&b_full[c], p.b_stage_bytes);
-            tma_load_3d(&map_b, &b_full[c], b_base + c * p.b_stage_bytes, c * 64, 0, 0);
+            tma_load_3d(&map_b, &b_full[c], b_base + c * p.b_stage_bytes, c * 64, 0,
+                        p.phase_fixed ? static_cast<int>(blockIdx.x % p.n_phase_items) * p.n_entries : 0);
           }
       } else if (p.b_pair) {
         // CTA pair: both CTAs walk the same (n-tile, phase, chunk, tap) sequence on neighbouring M tiles.  Each
@@ -480,7 +494,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         tc_fence_after();
         trace_ev(tc, 0, item);
         const uint32_t d_stage = tmem_base + as * p.n_groups * d_group_stride;
-        const int ebase = (MODE == MODE_T) ? (item / (p.n_mtiles * p.n_ntiles)) * p.n_entries : 0;
+        const int ebase = p.phase_fixed ? (item % p.n_phase_items) * p.n_entries
+                                        : ((MODE == MODE_T) ? (item / (p.n_mtiles * p.n_ntiles)) * p.n_entries : 0);
         for (int c = 0; c < p.n_chunks; ++c) {
           int ks = (p.Cin - c * 64 + 15) >> 4;
           ks = ks > 4 ? 4 : ks;
@@ -493,24 +508,30 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           int e = ebase;
           const uint32_t first_mask = (c == 0) ? p.tap_first_mask : 0u;
           bool fast_done = false;
-          if (MODE == MODE_H && ks == 4 && p.fast_id && !(p.dbg_skip & ~3)) {
-            IssueRing ring{b_full, b_empty, sb, pb};
-            const uint32_t acc_c = (c > 0) ? 1u : 0u;
-#define DP_FAST_CASE(K, S, G)                                                                                      \
-  case (K) * 100 + (S) * 10 + (G):                                                                                   \
-    issue_chunk_h<K, S, G>(p, ring, a_stage_desc, b_desc0, b_stage_u, b_ent_u, d_stage, n_tile, idesc, acc_c, c,   \
-                           b_loaded, tc, item);                                                                      \
-    fast_done = true;                                                                                                \
-    break;
-            switch (p.fast_id) {
-              DP_FAST_CASE(3, 1, 1) DP_FAST_CASE(3, 1, 3) DP_FAST_CASE(3, 1, 9)
-              DP_FAST_CASE(3, 2, 1) DP_FAST_CASE(3, 2, 3) DP_FAST_CASE(3, 2, 9)
-              DP_FAST_CASE(4, 1, 1) DP_FAST_CASE(4, 1, 2) DP_FAST_CASE(4, 1, 4)
-              DP_FAST_CASE(4, 2, 1) DP_FAST_CASE(4, 2, 2) DP_FAST_CASE(4, 2, 4)
-              default: break;
+          if constexpr (FAST != 0 && MODE == MODE_H) {
+            if (ks == 4 && !(p.dbg_skip & ~3)) {
+              IssueRing ring{b_full, b_empty, sb, pb};
+              const uint32_t acc_c = (c > 0) ? 1u : 0u;
+#define DP_ISSUE(...) issue_chunk_h<__VA_ARGS__>(p, ring, a_stage_desc, b_desc0, b_stage_u, b_ent_u, d_stage, n_tile, \
+                                                 idesc, acc_c, c, b_loaded, tc, item)
+              if constexpr (FAST < 4000) {
+                DP_ISSUE(FAST / 100, (FAST / 10) % 10, FAST % 10);
+              } else {
+                constexpr int G = (FAST - 4000) / 100, S = ((FAST - 4000) / 10) % 10;
+                const int pg = ebase / p.n_entries;   // this CTA's phase group (constant over its items)
+                if constexpr (G == 2) {
+                  if (pg == 0) DP_ISSUE(4, S, 8, 0, 8); else DP_ISSUE(4, S, 8, 8, 8);
+                } else {
+                  if (pg == 0) DP_ISSUE(4, S, 4, 0, 4);
+                  else if (pg == 1) DP_ISSUE(4, S, 4, 4, 4);
+                  else if (pg == 2) DP_ISSUE(4, S, 4, 8, 4);
+                  else DP_ISSUE(4, S, 4, 12, 4);
+                }
+              }
+#undef DP_ISSUE
+              fast_done = true;
+              sb = ring.sb; pb = ring.pb;
             }
-#undef DP_FAST_CASE
-            sb = ring.sb; pb = ring.pb;
           }
           for (int g = 0; g < (fast_done ? 0 : n_bgroups); ++g) {
             if (MODE == MODE_T) {
@@ -647,7 +668,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       const int ch0 = wi.nt * p.n_tile;
       int unit = 0;   // (accumulator [, 32-column step]) counter, identical in both groups
       for (int g = 0; g < ((p.dbg_skip & 8) ? 0 : p.n_groups); ++g) {
-        const int ph = (MODE == MODE_H) ? g : wi.ph;
+        const int ph = (MODE == MODE_H) ? (p.phase_fixed ? wi.ph * p.n_groups + g : g) : wi.ph;
         for (int s = 0; s < p.sub; ++s) {
           if (kEpiGroups == 2 && (p.epi_mode == EPI_HEAD || !p.epi_direct)) {
             // whole accumulators are the unit: the head needs a pixel's full channel dot product in one thread, the

@@ -177,6 +177,22 @@ const T* dptr(const dp_model* m, int64_t off) {
 
 int round_up(int a, int b) { return (a + b - 1) / b * b; }
 
+// MODE_H kernel variants by unrolled issue sequence (ConvParams::fast_id); 0 = generic tap loop.
+typedef void (*ConvKernelH)(const CUtensorMap, const CUtensorMap, const dp::ConvParams);
+struct FastKernel {
+  int id;
+  ConvKernelH fn;
+};
+#define DP_FK(ID) {ID, dp::conv_tc_kernel<dp::MODE_H, false, false, ID>}
+const FastKernel kFastKernels[] = {DP_FK(0),   DP_FK(311), DP_FK(313), DP_FK(319), DP_FK(321),  DP_FK(323),  DP_FK(329),
+                                   DP_FK(411), DP_FK(412), DP_FK(414), DP_FK(4210), DP_FK(4110), DP_FK(4120)};
+#undef DP_FK
+ConvKernelH fast_kernel(int id) {
+  for (const FastKernel& k : kFastKernels)
+    if (k.id == id) return k.fn;
+  return nullptr;
+}
+
 // TensorFlow padding='same': leading pad along one axis (the odd cell goes behind).
 int same_pad_before(int size, int k, int stride) {
   const int out = (size + stride - 1) / stride;
@@ -323,6 +339,27 @@ int plan_conv(dp_model* m, const BlobOp& op, int img0, int B, Launch& L) {
   memcpy(p.entries, table, sizeof table);
   if (p.mode == MODE_T)
     for (int i = 0; i < kMaxEntries; ++i) p.entries[i].group = 0;
+  // Phase-split up-conv: a work item covers G of the 4 sub-pixel phases and every CTA keeps ONE phase group for
+  // all of its items, so that group's weights (4G taps x all chunks) stay resident in shared memory.  Streaming
+  // the 16 tap tiles per 128-pixel item through a 4-stage ring is what bounded dec10a / dec9a (ring shallower
+  // than MMA-completion lag + TMA latency); the price is loading the (small) activation halo 4/G
+  // times.  Chosen when the resident weights fit beside a two-stage activation ring.
+  p.phase_fixed = 0;
+  if (p.mode == MODE_H && up2 && m->b_resident && op.cout <= 256 && !getenv("DP_NO_PHASE_SPLIT")) {
+    const long long room = 227 * 1024 - 26 * 1024;   // barriers, epilogue constants, staging rows, slack
+    for (int G = 2; G >= 1; --G) {
+      const long long wbytes = 4LL * G * ((op.cin + 63) / 64) * op.cout * 128;
+      const long long a2 = 2LL * round_up(18 * 10 * 128, 1024);   // two sub = 1 halo stages
+      if ((op.cin + 63) / 64 <= kMaxBStages && wbytes + a2 <= room) {
+        p.phase_fixed = 1;
+        p.n_groups = G;
+        p.n_phase_items = 4 / G;
+        p.n_entries = 4 * G;
+        for (int e = 0; e < 16; ++e) p.entries[e].group = (int8_t)((e / 4) % G);
+        break;
+      }
+    }
+  }
 
   // N tile: whole Cout if the accumulators fit; otherwise k equal tiles (multiples of 16) chosen for the least
   // padding, ties to fewer tiles.  A padded last tile (Cout 1088 -> 5 x 224) reads TMA-zero-filled weight rows
@@ -379,6 +416,10 @@ int plan_conv(dp_model* m, const BlobOp& op, int img0, int B, Launch& L) {
       sub = 1;
     // prefer more CTAs over wider regions when the layer cannot fill the GPU
     if (sub == 2 && (long long)B * (H / 16) * (W / 16) * p.n_ntiles < m->num_sms) sub = 1;
+    // resident phase-split weights must leave room for two activation stages
+    if (sub == 2 && p.phase_fixed &&
+        (long long)p.n_entries * p.n_chunks * n_tile * 128 + 2LL * round_up(18 * 18 * 128, 1024) > 227 * 1024 - 26 * 1024)
+      sub = 1;
     p.sub = sub;
     p.box_w = m->halo_pad8 ? round_up(8 * sub + halo.left + halo.right, 8) : 8 * sub + halo.left + halo.right;
     p.halo_top = halo.top;
@@ -410,8 +451,10 @@ int plan_conv(dp_model* m, const BlobOp& op, int img0, int B, Launch& L) {
   p.b_stage_bytes = p.b_group * n_tile * 128;
   // weight-stationary when the whole layer fits beside the activation ring
   p.b_resident = 0;
-  if (m->b_resident && p.mode != MODE_T && p.n_ntiles == 1 && p.n_phase_items == 1 && p.n_chunks <= kMaxBStages &&
-      (long long)p.n_chunks * p.n_entries * n_tile * 128 <= 96 * 1024) {
+  if (p.phase_fixed && p.n_ntiles != 1) return fail("conv: phase-split up-conv needs a single N tile");
+  if (p.phase_fixed ||
+      (m->b_resident && p.mode != MODE_T && p.n_ntiles == 1 && p.n_phase_items == 1 && p.n_chunks <= kMaxBStages &&
+       (long long)p.n_chunks * p.n_entries * n_tile * 128 <= 96 * 1024)) {
     p.b_resident = 1;
     p.b_group = p.n_entries;
     p.b_stage_bytes = p.n_entries * n_tile * 128;
@@ -420,12 +463,13 @@ int plan_conv(dp_model* m, const BlobOp& op, int img0, int B, Launch& L) {
   // fully unrolled issue sequence (conv_tc.cuh:issue_chunk_h) where one is instantiated
   p.fast_id = 0;
   if (p.mode == MODE_H && !m->halo_pad8 && !getenv("DP_NO_FAST_ISSUE") && (op.kind == 3 || op.kind == 4) &&
-      p.box_w == 8 * p.sub + 2) {
+      p.box_w == 8 * p.sub + 2 && !p.phase_fixed) {
     const int id = op.kind * 100 + p.sub * 10 + p.b_group;
-    static const int have[] = {311, 313, 319, 321, 323, 329, 411, 412, 414, 421, 422, 424};
-    for (int h : have)
-      if (h == id) p.fast_id = id;
+    if (fast_kernel(id)) p.fast_id = id;
   }
+  if (p.phase_fixed && p.mode == MODE_H && !m->halo_pad8 && !getenv("DP_NO_FAST_ISSUE") && p.box_w == 8 * p.sub + 2 &&
+      fast_kernel(4000 + p.n_groups * 100 + p.sub * 10))
+    p.fast_id = 4000 + p.n_groups * 100 + p.sub * 10;
 
   // shared-memory ring depths
   const int budget = 227 * 1024 - ConvSmemLayout::kBarBytes - 2 * n_tile * n_ntiles * 4 - 2 * p.n_chunks * 64 * 4 - 256 * 4 -
@@ -441,7 +485,11 @@ int plan_conv(dp_model* m, const BlobOp& op, int img0, int B, Launch& L) {
     b_stages = p.n_chunks;
   }
   if (b_stages < 2 && !p.b_resident) return fail("conv: shared memory budget exceeded (A %d B %d)", p.a_stage_bytes, p.b_stage_bytes);
-  // spend what is left on deeper A rings for the flat modes
+  // spend what is left on deeper A rings: the flat modes, and halo mode when the weights are resident (the halo
+  // box is ~180 separate 128-byte segments, ~3.5k clk of TMA latency under load: two stages do not cover it)
+  if (p.mode == MODE_H && p.b_resident) {
+    while (a_stages < 4 && (a_stages + 1) * p.a_stage_bytes + b_stages * p.b_stage_bytes <= budget) ++a_stages;
+  }
   if (p.mode != MODE_H) {
     while (a_stages < kMaxAStages && (a_stages + 1) * p.a_stage_bytes + b_stages * p.b_stage_bytes <= budget &&
            a_stages < 6)
@@ -453,6 +501,12 @@ int plan_conv(dp_model* m, const BlobOp& op, int img0, int B, Launch& L) {
   if (L.smem > 227 * 1024) return fail("conv: smem %d too large", L.smem);
   const int rounds = (p.n_items + m->num_sms - 1) / m->num_sms;
   L.grid = (p.n_items + rounds - 1) / rounds;
+  if (p.phase_fixed) {
+    // item = m_tile * n_phase_items + phase group: a grid that is a multiple of n_phase_items keeps the phase
+    // group of a CTA fixed across its grid-stride loop
+    L.grid = (m->num_sms / p.n_phase_items) * p.n_phase_items;
+    if (L.grid > p.n_items) L.grid = p.n_items;
+  }
   // CTA pairs with multicast weights: worthwhile where weights are re-streamed per item (not resident) and there
   // is more than one item per CTA; needs lock-step pairs (even items / M tiles / grid) and 1 KB-aligned halves.
   p.b_pair = 0;
@@ -831,9 +885,12 @@ int run_op(dp_model* m, SubPlan* sp, int i, cudaStream_t st) {
         case dp::MODE_T:
           le = cudaLaunchKernelEx(&cfg, dp::conv_tc_kernel<dp::MODE_T, false>, L.map_a, L.map_b, cp);
           break;
-        default:
-          le = cudaLaunchKernelEx(&cfg, dp::conv_tc_kernel<dp::MODE_H, false>, L.map_a, L.map_b, cp);
+        default: {
+          ConvKernelH fn = fast_kernel(cp.fast_id);
+          if (!fn) { fn = fast_kernel(0); cp.fast_id = 0; }
+          le = cudaLaunchKernelEx(&cfg, fn, L.map_a, L.map_b, cp);
           break;
+        }
       }
       if (le != cudaSuccess) return fail("conv launch failed: %s", cudaGetErrorString(le));
       LAUNCH_OK();
@@ -964,7 +1021,11 @@ int dp_model_create(const void* blob, size_t nbytes, int device, int max_batch, 
     cudaError_t e1 = cudaFuncSetAttribute(dp::conv_tc_kernel<dp::MODE_D, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
     cudaError_t e2 = cudaFuncSetAttribute(dp::conv_tc_kernel<dp::MODE_D, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
     cudaError_t e3 = cudaFuncSetAttribute(dp::conv_tc_kernel<dp::MODE_T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
-    cudaError_t e4 = cudaFuncSetAttribute(dp::conv_tc_kernel<dp::MODE_H, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
+    cudaError_t e4 = cudaSuccess;
+    for (const FastKernel& k : kFastKernels) {
+      cudaError_t ek = cudaFuncSetAttribute(k.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
+      if (ek != cudaSuccess) e4 = ek;
+    }
     cudaError_t e7 = cudaFuncSetAttribute(dp::conv_tc_kernel<dp::MODE_D, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
     cudaError_t e5 = cudaFuncSetAttribute(dp::dense_layer_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
     cudaError_t e6 = cudaFuncSetAttribute(dp::dense_layer_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
