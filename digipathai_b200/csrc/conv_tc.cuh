@@ -216,7 +216,7 @@ struct IssueRing {
 
 // E0 / NE select a sub-range of the up2 entries (phase-split items: NE = 4 G entries starting at phase group
 // E0 / NE; the resident weight stage then starts at entry E0).
-template <int KIND, int SUB, int BG, int E0 = 0, int NE = ((KIND == 3) ? 9 : 16)>
+template <int KS, int KIND, int SUB, int BG, int E0 = 0, int NE = ((KIND == 3) ? 9 : 16)>
 __device__ __forceinline__ void issue_chunk_h(const ConvParams& p, IssueRing& r, uint64_t a_stage_desc, uint64_t b_desc0,
                                               uint32_t b_stage_u, uint32_t b_ent_u, uint32_t d_stage, uint32_t n_tile,
                                               uint32_t idesc, uint32_t acc_c, int c, bool b_loaded, TraceCursor& tc,
@@ -232,7 +232,9 @@ __device__ __forceinline__ void issue_chunk_h(const ConvParams& p, IssueRing& r,
     } else {
       mbar_wait(&r.b_full[r.sb], r.pb);
     }
-    tc_fence_after();
+    // no tcgen05.fence here: the operands were written by TMA and published through the mbarrier's transaction
+    // count; the fence after the accumulator hand-off (acc_empty) is the one that orders against other threads'
+    // tcgen05 operations
     trace_ev(tc, 2, item);
     const uint64_t b_desc = b_desc0 + r.sb * b_stage_u;
 #pragma unroll
@@ -249,9 +251,14 @@ __device__ __forceinline__ void issue_chunk_h(const ConvParams& p, IssueRing& r,
       const bool first = (KIND == 3) ? (e == 0) : ((e & 3) == 0);
       const uint32_t flag = first ? acc_c : 1u;
 #pragma unroll
-      for (int s = 0; s < SUB; ++s)
-        umma_f16_ss_k4(d_stage + static_cast<uint32_t>(grp * SUB + s) * n_tile, a_stage_desc + a_off + s * 64u,
-                       b_desc + static_cast<uint32_t>(j) * b_ent_u, idesc, flag);
+      for (int s = 0; s < SUB; ++s) {
+        if (KS == 4)
+          umma_f16_ss_k4(d_stage + static_cast<uint32_t>(grp * SUB + s) * n_tile, a_stage_desc + a_off + s * 64u,
+                         b_desc + static_cast<uint32_t>(j) * b_ent_u, idesc, flag);
+        else
+          umma_f16_ss_k2(d_stage + static_cast<uint32_t>(grp * SUB + s) * n_tile, a_stage_desc + a_off + s * 64u,
+                         b_desc + static_cast<uint32_t>(j) * b_ent_u, idesc, flag);
+      }
       trace_ev(tc, 4, item);
     }
     if (!p.b_resident) {
@@ -509,11 +516,18 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           const uint32_t first_mask = (c == 0) ? p.tap_first_mask : 0u;
           bool fast_done = false;
           if constexpr (FAST != 0 && MODE == MODE_H) {
-            if (ks == 4 && !(p.dbg_skip & ~3)) {
+            if ((ks == 4 || ks == 2) && !(p.dbg_skip & ~3)) {
               IssueRing ring{b_full, b_empty, sb, pb};
               const uint32_t acc_c = (c > 0) ? 1u : 0u;
-#define DP_ISSUE(...) issue_chunk_h<__VA_ARGS__>(p, ring, a_stage_desc, b_desc0, b_stage_u, b_ent_u, d_stage, n_tile, \
-                                                 idesc, acc_c, c, b_loaded, tc, item)
+#define DP_ISSUE(...)                                                                                                 \
+  do {                                                                                                                \
+    if (ks == 4)                                                                                                      \
+      issue_chunk_h<4, __VA_ARGS__>(p, ring, a_stage_desc, b_desc0, b_stage_u, b_ent_u, d_stage, n_tile, idesc, acc_c, \
+                                    c, b_loaded, tc, item);                                                           \
+    else                                                                                                              \
+      issue_chunk_h<2, __VA_ARGS__>(p, ring, a_stage_desc, b_desc0, b_stage_u, b_ent_u, d_stage, n_tile, idesc, acc_c, \
+                                    c, b_loaded, tc, item);                                                           \
+  } while (0)
               if constexpr (FAST < 4000) {
                 DP_ISSUE(FAST / 100, (FAST / 10) % 10, FAST % 10);
               } else {
@@ -544,7 +558,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             } else if (!((p.dbg_skip & 16) && b_pass_m)) {
               mbar_wait(&b_full[sb], pb);
             }
-            if (!(p.dbg_skip & 32)) tc_fence_after();
+            if (p.dbg_skip & 32) tc_fence_after();   // not needed (see issue_chunk_h); kept switchable for experiments
             trace_ev(tc, 2, item);
             uint64_t b_desc = b_desc0 + sb * b_stage_u;
             if (ks == 4) {

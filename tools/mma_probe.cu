@@ -8,16 +8,18 @@ using namespace dp;
 
 // Pattern probe: like the real issue loop, every k4 block may use a different weight tile (b_cycle distinct tiles of
 // n rows), a different A start (a_cycle distinct row offsets) and a different accumulator (d_cycle column groups).
-__global__ void probe_pattern(int n, int sbo, int iters, int a_cycle, int b_cycle, int d_cycle, long long* out) {
+__global__ void probe_pattern(int n, int sbo, int iters, int a_cycle, int b_cycle, int d_cycle, long long* out,
+                              int commit_every = 0) {
   extern __shared__ uint8_t raw[];
   const uint32_t ra = smem_u32(raw);
   uint8_t* smem = raw + (((ra + 1023u) & ~1023u) - ra);
   __shared__ uint64_t bar;
+  __shared__ uint64_t dummy_bar;   // target of the in-loop commits: nobody waits on it
   __shared__ uint32_t slot;
   const int warp = threadIdx.x >> 5;
   for (int i = threadIdx.x; i < 200 * 1024 / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem)[i] = 0x3c003c00u;
   if (warp == 0) { tmem_alloc(&slot, 512); tmem_relinquish(); }
-  if (threadIdx.x == 32) { mbar_init(&bar, 1); fence_barrier_init(); }
+  if (threadIdx.x == 32) { mbar_init(&bar, 1); mbar_init(&dummy_bar, 1); fence_barrier_init(); }
   fence_proxy_async_smem();
   tc_fence_before(); __syncthreads(); tc_fence_after();
   const uint32_t tm = slot;
@@ -35,6 +37,7 @@ __global__ void probe_pattern(int n, int sbo, int iters, int a_cycle, int b_cycl
       if (++ia == a_cycle) ia = 0;
       if (++ib == b_cycle) ib = 0;
       if (++id == d_cycle) id = 0;
+      if (commit_every && (i + 1) % commit_every == 0) umma_commit(&dummy_bar);
     }
     long long t1 = clock64();
     umma_commit(&bar); mbar_wait(&bar, 1);
@@ -112,6 +115,21 @@ int main() {
         if (e != cudaSuccess) { printf("error %s\n", cudaGetErrorString(e)); return 1; }
         const double m = (double)iters * 4 * 4;
         printf("%5d %7d %7d %7d | %10.1f %10.1f\n", n, c[0], c[1], c[2], h[0] / m, h[1] / m);
+      }
+  }
+  printf("commit probe (148 CTAs, k4 blocks): tcgen05.commit to an unwaited mbarrier every C blocks\n");
+  printf("%5s %8s | %10s %10s\n", "N", "every", "issue/mma", "done/mma");
+  {
+    int pn[] = {64, 128, 256};
+    int ev[] = {0, 16, 4, 2, 1};
+    for (int n : pn)
+      for (int c : ev) {
+        probe_pattern<<<148, 128, 220 * 1024>>>(n, 1280, iters * 4, 9, 4 * 128 * n <= 150 * 1024 ? 4 : 2, 1, d, c);
+        long long h[2];
+        cudaError_t e = cudaMemcpy(h, d, 16, cudaMemcpyDeviceToHost);
+        if (e != cudaSuccess) { printf("error %s\n", cudaGetErrorString(e)); return 1; }
+        const double m = (double)iters * 4 * 4;
+        printf("%5d %8d | %10.1f %10.1f\n", n, c, h[0] / m, h[1] / m);
       }
   }
   int ns[] = {64};
