@@ -346,38 +346,47 @@ dense_layer_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
       tc_fence_after();
       dl_trace_ev(tc, 0, k);
       uint8_t* tbuf = t_base + tb * kDlTBuf;
-#pragma unroll 1
-      for (int mb = 0; mb < kMBlk; ++mb) {
+      // 16-column steps, ping-pong register buffers: the tcgen05.ld of step s+1 is in flight while step s is
+      // converted and stored (tcgen05.wait::ld waits for ALL outstanding loads, so the next load is issued right
+      // after the wait).  Measured: this step takes ~5k clk per 16-row item (trace of conv2_block3) and is the
+      // critical resource of the item pipeline, but hiding the load latency this way did NOT shorten it -- the
+      // loads are not latency bound; what the step waits on is still open (TMEM port contention with the
+      // concurrent N = 32 MMAs is the leading suspect).
+      constexpr int kSteps = kMBlk * 4;
+      const uint32_t lane_col = acc1_col + half * 64 + (static_cast<uint32_t>(q * 32) << 16);
+      auto process = [&](int sidx, const uint32_t (&v)[16]) {
+        const int mb = sidx >> 2;
+        const int cb = half * 64 + (sidx & 3) * 16;
         const int prow = mb * 128 + r;                 // halo pixel index
+        if (prow >= kRows) return;
         const int hh = prow / kDlHaloW, ww = prow - hh * kDlHaloW;
         const int ih = h0 - 1 + hh, iw = w0 - 1 + ww;
-        const bool inside = prow < kRows && ih >= 0 && ih < p.H && iw >= 0 && iw < p.W;
-        const uint32_t taddr = acc1_col + mb * 128 + (static_cast<uint32_t>(q * 32) << 16);
+        const bool inside = ih >= 0 && ih < p.H && iw >= 0 && iw < p.W;
+        float f[16];
+        epi_affine16(v, nullptr, s_mid_shift + cb, false, true, f);
+        uint32_t pk[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          __half2 h2 = inside ? __floats2half2_rn(f[2 * i], f[2 * i + 1]) : __float2half2_rn(0.f);
+          pk[i] = *reinterpret_cast<uint32_t*>(&h2);
+        }
+        // channels cb..cb+15 = 16-byte chunks j, j+1 of 64-channel chunk (cb / 64)
+        uint8_t* row = tbuf + (cb >> 6) * kDlTChunk + prow * 128;
+        const int j = (cb & 63) >> 3;
+        *reinterpret_cast<uint4*>(row + (((j) ^ (prow & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        *reinterpret_cast<uint4*>(row + (((j + 1) ^ (prow & 7)) << 4)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+      };
+      {
+        uint32_t v0[16], v1[16];
+        tmem_ld16(lane_col, v0);
 #pragma unroll 1
-        for (int cc = half * 64; cc < half * 64 + 64; cc += 32) {
-          uint32_t v[2][16];
-          tmem_ld16(taddr + cc, v[0]);
-          tmem_ld16(taddr + cc + 16, v[1]);
+        for (int sidx = 0; sidx < kSteps; sidx += 2) {
           tmem_ld_wait();
-          if (prow < kRows) {
-#pragma unroll
-            for (int hsel = 0; hsel < 2; ++hsel) {
-              const int cb = cc + 16 * hsel;
-              float f[16];
-              epi_affine16(v[hsel], nullptr, s_mid_shift + cb, false, true, f);
-              uint32_t pk[8];
-#pragma unroll
-              for (int i = 0; i < 8; ++i) {
-                __half2 h2 = inside ? __floats2half2_rn(f[2 * i], f[2 * i + 1]) : __float2half2_rn(0.f);
-                pk[i] = *reinterpret_cast<uint32_t*>(&h2);
-              }
-              // channels cb..cb+15 = 16-byte chunks j, j+1 of 64-channel chunk (cb / 64)
-              uint8_t* row = tbuf + (cb >> 6) * kDlTChunk + prow * 128;
-              const int j = (cb & 63) >> 3;
-              *reinterpret_cast<uint4*>(row + (((j) ^ (prow & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-              *reinterpret_cast<uint4*>(row + (((j + 1) ^ (prow & 7)) << 4)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
-            }
-          }
+          tmem_ld16(lane_col + ((sidx + 1) >> 2) * 128 + ((sidx + 1) & 3) * 16, v1);
+          process(sidx, v0);
+          tmem_ld_wait();
+          if (sidx + 2 < kSteps) tmem_ld16(lane_col + ((sidx + 2) >> 2) * 128 + ((sidx + 2) & 3) * 16, v0);
+          process(sidx + 1, v1);
         }
       }
       tc_fence_before();
