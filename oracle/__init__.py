@@ -10,4 +10,7 @@ reference's own pure-numpy functions ``apply_tta`` / ``transform_prob`` (DigiPat
 extracted at fixture-generation time by tests/golden/make_golden.py) and committing their outputs as golden
 vectors, and (b) hand-computable known-answer cases for the stitch arithmetic.  Everything that lives inside
 TensorFlow (conv / BN / pooling / softmax semantics) is restated from Keras' documented behaviour.
+
+Modules: ``pipeline_ref`` (numpy restatement of get_prediction / dataset / TTA / tissue mask), ``densenet_ref``,
+``inception_ref``, ``deeplab_ref`` (fp32 PyTorch-CPU restatements of the three Keras graphs of DigiPathAI/models/).
 """
