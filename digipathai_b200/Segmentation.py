@@ -197,13 +197,17 @@ def getSegmentation(img_path,
                     mode='colon',
                     weights=None,
                     device=0,
-                    return_device=False):
+                    return_device=False,
+                    pyramidal=True):
     """Whole-slide segmentation (reference: Segmentation.py:192-356, README.md:79-87).
 
     Returns the thresholded map -- float32 ``[W, H]`` of {0, 255}, NOT transposed -- exactly what the reference
     returns (Segmentation.py:336-337,356); writes probs / mask / uncertainty TIFFs when paths are given
     (``save_path`` is the README's name for ``mask_path``).  ``crf`` and ``mask_level`` are accepted and
     ignored, as in the live reference (Segmentation.py:327-331, dataloader.py:240-241).
+    The three files are written the way the reference leaves them after its ImageMagick pass: tiled (256x256)
+    pyramidal JPEG-q90 TIFFs (tiffio.save_pyramidal; probabilities and uncertainty scaled to 8 bit);
+    ``pyramidal=False`` writes lossless single-level TIFFs instead (float32 probabilities / uncertainty).
     Extensions (keyword only): ``weights`` = dict / ``.npz`` path per model name or a single dict for
     ``model``; ``device``; ``return_device`` returns the uint8 label plane as a CUDA tensor instead.
     """
@@ -264,19 +268,23 @@ def getSegmentation(img_path,
     for m in models.values():
         m.close()
 
-    from .tiffio import save_plane
+    from .tiffio import save_plane, save_pyramidal
+    if pyramidal:
+        _save = lambda path, plane, scale: save_pyramidal(path, plane if scale == 1 else plane * scale)
+    else:
+        _save = lambda path, plane, scale: save_plane(path, plane if scale in (1, 0) else plane * scale)
     if probs_path:
-        save_plane(probs_path, mean.T)                                   # Segmentation.py:333
+        _save(probs_path, mean.T, 255 if pyramidal else 0)               # Segmentation.py:333-334
     if status is not None:
         status['progress'] = 100
     if status is not None:
         status['status'] = "Saving Prediction Mask..."
     if mask_path:
-        save_plane(mask_path, label.T)                                   # Segmentation.py:345
+        _save(mask_path, label.T, 1)                                     # Segmentation.py:345-346
     if status is not None:
         status['status'] = "Saving Prediction Uncertanity..."
     if uncertainty_path:
-        save_plane(uncertainty_path, var.T * 255)                        # Segmentation.py:351
+        _save(uncertainty_path, var.T, 255)                              # Segmentation.py:351-352
     if status is not None:
         status['progress'] = 0
     if return_device:

@@ -46,7 +46,8 @@ def test_get_segmentation_drop_in(env, tmp_path):
     mask_path = str(tmp_path / "mask.tiff")
     probs_path = str(tmp_path / "probs.tiff")
     got = getSegmentation(slide, patch_size=256, stride_size=128, batch_size=4, quick=True, tta_list=None,
-                          crf=False, save_path=mask_path, status=status, probs_path=probs_path, weights=w)
+                          crf=False, save_path=mask_path, status=status, probs_path=probs_path, weights=w,
+                          pyramidal=False)
     assert got.dtype == np.float32 and got.shape == want_thr.shape and set(np.unique(got)) <= {0.0, 255.0}
     mism = got != want_thr
     # labels may only differ where the oracle probability is within the fp16 band of the 0.3 threshold
@@ -120,3 +121,22 @@ def test_quick_false_runs_the_three_model_ensemble(env):
     mism = got != want_thr
     print(f"\n3-model ensemble: {int(mism.sum())} / {mism.size} label mismatches")
     assert (np.abs(want_mean - 0.3)[mism] <= 1e-1).all() and mism.mean() < 0.05
+
+
+def test_get_segmentation_writes_pyramidal_tiffs(env, tmp_path):
+    """Default export = what the reference leaves on disk after its ImageMagick pass (Segmentation.py:333-352): tiled
+    pyramidal JPEG TIFFs; level 0 of the mask file is the returned label map up to JPEG loss."""
+    from PIL import Image
+    from digipathai_b200.Segmentation import getSegmentation
+    w, slide, _ = env
+    mask_path, unc_path = str(tmp_path / "mask.tiff"), str(tmp_path / "unc.tiff")
+    got = getSegmentation(slide, patch_size=256, stride_size=256, batch_size=4, weights=w, mask_path=mask_path,
+                          uncertainty_path=unc_path)
+    Image.MAX_IMAGE_PIXELS = None
+    im = Image.open(mask_path)
+    assert im.n_frames == 3 and im.size == (1024, 768)            # 1024x768 -> 512x384 -> 256x192
+    lvl0 = np.asarray(im).astype(np.float32)
+    assert np.abs(lvl0 - got.T).mean() < 6.0 and ((lvl0 > 127) == (got.T > 127)).mean() > 0.995
+    im.seek(2)
+    assert im.size == (256, 192)
+    assert Image.open(unc_path).n_frames == 3

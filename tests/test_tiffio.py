@@ -1,0 +1,67 @@
+"""Pyramidal tiled JPEG TIFF writer (reference: Segmentation.py:333-352 + ImageMagick `ptif:`)."""
+import struct
+
+import numpy as np
+
+from digipathai_b200 import tiffio
+
+
+def _smooth(rows, cols):
+    y, x = np.mgrid[0:rows, 0:cols]
+    return (127.5 + 127.5 * np.sin(x / 37.0) * np.cos(y / 53.0)).astype(np.float32)
+
+
+def _ifds(path):
+    b = open(path, "rb").read()
+    assert b[:4] == b"II*\0"
+    off = struct.unpack("<I", b[4:8])[0]
+    out = []
+    while off:
+        n = struct.unpack("<H", b[off:off + 2])[0]
+        tags = {}
+        for i in range(n):
+            tag, typ, cnt, val = struct.unpack("<HHII", b[off + 2 + 12 * i: off + 14 + 12 * i])
+            tags[tag] = (typ, cnt, val & 0xFFFF if (typ == 3 and cnt == 1) else val)
+        out.append(tags)
+        off = struct.unpack("<I", b[off + 2 + 12 * n: off + 6 + 12 * n])[0]
+    return out, b
+
+
+def test_pyramid_structure_and_content(tmp_path):
+    from PIL import Image
+    a = _smooth(700, 1000)
+    path = str(tmp_path / "p.tiff")
+    n = tiffio.save_pyramidal(path, a)
+    assert n == 3                                             # 1000x700 -> 500x350 -> 250x175
+    ifds, raw = _ifds(path)
+    assert [(d[256][2], d[257][2]) for d in ifds] == [(1000, 700), (500, 350), (250, 175)]
+    assert [d[254][2] for d in ifds] == [0, 1, 1]             # reduced-resolution flag on the sub-levels
+    for d in ifds:
+        assert d[259][2] == 7 and d[322][2] == 256 and d[323][2] == 256 and d[258][2] == 8 and d[277][2] == 1
+        tiles = -(-d[256][2] // 256) * -(-d[257][2] // 256)
+        assert d[324][1] == tiles and d[325][1] == tiles
+    # every tile is a self-contained JPEG stream
+    d0 = ifds[0]
+    offs = struct.unpack(f"<{d0[324][1]}I", raw[d0[324][2]: d0[324][2] + 4 * d0[324][1]])
+    assert all(raw[o:o + 2] == b"\xff\xd8" for o in offs)
+    im = Image.open(path)
+    assert im.n_frames == 3
+    lvl0 = np.asarray(im).astype(np.float32)
+    assert lvl0.shape == (700, 1000) and np.abs(lvl0 - a).mean() < 1.5
+    im.seek(1)
+    lvl1 = np.asarray(im).astype(np.float32)
+    want1 = 0.25 * (a[0::2, 0::2] + a[0::2, 1::2] + a[1::2, 0::2] + a[1::2, 1::2])
+    assert lvl1.shape == (350, 500) and np.abs(lvl1 - want1).mean() < 1.5
+
+
+def test_small_and_binary_planes(tmp_path):
+    from PIL import Image
+    m = np.zeros((300, 200), np.uint8)
+    m[50:200, 40:160] = 255
+    path = str(tmp_path / "m.tiff")
+    assert tiffio.save_pyramidal(path, m) == 2
+    back = np.asarray(Image.open(path))
+    assert ((back > 127) == (m > 127)).mean() > 0.998
+    one = str(tmp_path / "one.tiff")
+    assert tiffio.save_pyramidal(one, np.full((100, 90), 7, np.uint8)) == 1     # fits one tile: single level
+    assert np.abs(np.asarray(Image.open(one)).astype(int) - 7).max() <= 2
