@@ -117,7 +117,9 @@ __host__ __device__ inline ConvSmemLayout conv_smem_layout(const ConvParams& p) 
   L.pro_off = L.epi_off + 2 * cout * 4;
   L.head_off = L.pro_off + 2 * p.n_chunks * 64 * 4;
   L.stage_off = L.head_off + 256 * 4;
-  L.total = L.stage_off + 4 * kEpiStageBytes + 1024;  // + alignment slack
+  // per-warp staging rows exist only for the staged (non-direct, non-head) store path
+  const bool staged = !(p.epi_direct || p.epi_mode == EPI_HEAD);
+  L.total = L.stage_off + (staged ? 4 * kEpiStageBytes : 0) + 1024;  // + alignment slack
   return L;
 }
 

@@ -185,7 +185,7 @@ struct FastKernel {
 };
 #define DP_FK(ID) {ID, dp::conv_tc_kernel<dp::MODE_H, false, false, ID>}
 const FastKernel kFastKernels[] = {DP_FK(0),   DP_FK(311), DP_FK(313), DP_FK(319), DP_FK(321),  DP_FK(323),  DP_FK(329),
-                                   DP_FK(411), DP_FK(412), DP_FK(414), DP_FK(4210), DP_FK(4110), DP_FK(4120)};
+                                   DP_FK(411), DP_FK(412), DP_FK(414), DP_FK(4210), DP_FK(4220), DP_FK(4110), DP_FK(4120)};
 #undef DP_FK
 ConvKernelH fast_kernel(int id) {
   for (const FastKernel& k : kFastKernels)
@@ -301,6 +301,10 @@ int plan_conv(dp_model* m, const BlobOp& op, int img0, int B, Launch& L) {
   p.pro_relu = op.pro == 2;
   p.desc_base_mode = m->desc_base_mode;
   p.epi_mode = op.head ? EPI_HEAD : EPI_STORE;
+  // store path is fixed at plan time (the shared-memory layout depends on it): 256-bit direct stores whenever the
+  // output placement is 16-channel aligned
+  p.epi_direct = (!op.head && (m->epi_direct || residual) && (op.out_choff % 16) == 0 &&
+                  (m->bufs[op.out_buf].C % 16) == 0) ? 1 : 0;
   p.epi_scale = q.epi_scale; p.epi_shift = q.epi_shift;
   p.pro_scale = q.pro_scale; p.pro_shift = q.pro_shift;
   p.head_w = dptr<float>(m, op.head_w_off);
@@ -346,7 +350,7 @@ int plan_conv(dp_model* m, const BlobOp& op, int img0, int B, Launch& L) {
   // times.  Chosen when the resident weights fit beside a two-stage activation ring.
   p.phase_fixed = 0;
   if (p.mode == MODE_H && up2 && m->b_resident && op.cout <= 256 && !getenv("DP_NO_PHASE_SPLIT")) {
-    const long long room = 227 * 1024 - 26 * 1024;   // barriers, epilogue constants, staging rows, slack
+    const long long room = 227 * 1024 - 8 * 1024 - (p.epi_direct ? 0 : 4 * kEpiStageBytes);   // barriers, constants, slack
     for (int G = 2; G >= 1; --G) {
       const long long wbytes = 4LL * G * ((op.cin + 63) / 64) * op.cout * 128;
       const long long a2 = 2LL * round_up(18 * 10 * 128, 1024);   // two sub = 1 halo stages
@@ -385,6 +389,7 @@ int plan_conv(dp_model* m, const BlobOp& op, int img0, int B, Launch& L) {
   const bool out_aligned = op.head || ((op.out_choff % 16) == 0 && (m->bufs[op.out_buf].C % 16) == 0);
   if ((residual || n_tile * n_ntiles != op.cout) && !out_aligned)
     return fail("conv: residual / clipped-N epilogue needs 16-channel aligned output placement");
+  if (n_tile * n_ntiles != op.cout && !op.head) p.epi_direct = 1;   // the clipped store exists only in the direct path
 
   // sub-tiles per CTA tile
   const long long m_total = (long long)B * OH * OW;
@@ -418,7 +423,8 @@ int plan_conv(dp_model* m, const BlobOp& op, int img0, int B, Launch& L) {
     if (sub == 2 && (long long)B * (H / 16) * (W / 16) * p.n_ntiles < m->num_sms) sub = 1;
     // resident phase-split weights must leave room for two activation stages
     if (sub == 2 && p.phase_fixed &&
-        (long long)p.n_entries * p.n_chunks * n_tile * 128 + 2LL * round_up(18 * 18 * 128, 1024) > 227 * 1024 - 26 * 1024)
+        (long long)p.n_entries * p.n_chunks * n_tile * 128 + 2LL * round_up(18 * 18 * 128, 1024) >
+            227 * 1024 - 8 * 1024 - (p.epi_direct ? 0 : 4 * kEpiStageBytes))
       sub = 1;
     p.sub = sub;
     p.box_w = m->halo_pad8 ? round_up(8 * sub + halo.left + halo.right, 8) : 8 * sub + halo.left + halo.right;
@@ -473,7 +479,7 @@ int plan_conv(dp_model* m, const BlobOp& op, int img0, int B, Launch& L) {
 
   // shared-memory ring depths
   const int budget = 227 * 1024 - ConvSmemLayout::kBarBytes - 2 * n_tile * n_ntiles * 4 - 2 * p.n_chunks * 64 * 4 - 256 * 4 -
-                     4 * kEpiStageBytes - 1024;
+                     ((p.epi_direct || op.head) ? 0 : 4 * kEpiStageBytes) - 1024;
   int a_stages = (p.mode == MODE_H) ? 2 : 4;
   const int b_min = p.b_resident ? p.n_chunks : 2;
   while (a_stages > 1 && a_stages * p.a_stage_bytes + b_min * p.b_stage_bytes > budget) --a_stages;
@@ -848,8 +854,7 @@ int run_op(dp_model* m, SubPlan* sp, int i, cudaStream_t st) {
       }
       dp::ConvParams cp = L.cp;
       cp.desc_base_mode = m->desc_base_mode;
-      cp.epi_direct = (m->epi_direct || cp.residual || cp.n_tile * cp.n_ntiles != cp.cout) &&
-                      ((cp.out_choff % 16) == 0) && ((cp.out_ctot % 16) == 0);
+
       cp.trace = (m->trace_op == i) ? m->trace_dev : nullptr;
       { const char* dbg = getenv("DP_DBG_SKIP"); cp.dbg_skip = dbg ? atoi(dbg) : 0; }
       cp.gt = (m->stamp && m->gt_dev) ? m->gt_dev + 2 * i : nullptr;
@@ -1109,9 +1114,10 @@ int dp_model_set_option(dp_model* m, const char* key, int value) {
     std::lock_guard<std::mutex> lk(m->mu);
     m->epi_direct = value;
     for (auto& kv : m->plans) {
-      if (kv.second.exec) { cudaGraphExecDestroy(kv.second.exec); kv.second.exec = nullptr; }
-      if (kv.second.graph) { cudaGraphDestroy(kv.second.graph); kv.second.graph = nullptr; }
+      if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
+      if (kv.second.graph) cudaGraphDestroy(kv.second.graph);
     }
+    m->plans.clear();   // the store path is part of the plan (shared-memory layout)
   }
   else if (!strcmp(key, "use_pdl")) {
     std::lock_guard<std::mutex> lk(m->mu);
