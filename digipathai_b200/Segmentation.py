@@ -123,6 +123,29 @@ def get_prediction(wsi_path, mask_path=None, label_path=None, batch_size=64, mod
     return (slide, out)
 
 
+def _crf_refine(engine, torch, slide, mean, label, P, batch):
+    """``crf=True``: the reference's intent (Segmentation.py:327-331, commented out there) is
+    ``post_process_crf(img, [1 - mean, mean], 2)`` on the whole slide, which pydensecrf cannot hold in memory at WSI
+    size.  Here the fully connected CRF of utils.py:568-603 is applied per non-overlapping P x P tile (edge tiles
+    clamped inside the slide) wherever the probability map is not identically background; the MAP label replaces
+    the thresholded label ({0, 255}).  Planes are in the reference's [x, y] orientation; the CRF is symmetric in
+    the two image axes, so no transpose is needed."""
+    W, H = mean.shape
+    if W < P or H < P:
+        return
+    raster = upload_xy_raster(slide, 0, W, mean.device)          # uint8 [x, y, c]
+    xs = sorted({min(x, W - P) for x in range(0, W, P)})
+    ys = sorted({min(y, H - P) for y in range(0, H, P)})
+    todo = [(x, y) for x in xs for y in ys if float(mean[x:x + P, y:y + P].max()) > 1e-5]
+    for s in range(0, len(todo), batch):
+        chunk = todo[s:s + batch]
+        rgb = torch.stack([raster[x:x + P, y:y + P] for x, y in chunk]).contiguous()
+        p1 = torch.stack([mean[x:x + P, y:y + P] for x, y in chunk]).contiguous()
+        lab = engine.dense_crf(rgb, p1)
+        for (x, y), l in zip(chunk, lab):
+            label[x:x + P, y:y + P] = l * 255
+
+
 def _default_weight_path(mode, model):
     folder, prefix = _MODEL_SETS[mode]
     suffix = {'dense': 'densenet', 'inception': 'inception', 'deeplabv3': 'deeplabv3'}[model]
@@ -203,8 +226,10 @@ def getSegmentation(img_path,
 
     Returns the thresholded map -- float32 ``[W, H]`` of {0, 255}, NOT transposed -- exactly what the reference
     returns (Segmentation.py:336-337,356); writes probs / mask / uncertainty TIFFs when paths are given
-    (``save_path`` is the README's name for ``mask_path``).  ``crf`` and ``mask_level`` are accepted and
-    ignored, as in the live reference (Segmentation.py:327-331, dataloader.py:240-241).
+    (``save_path`` is the README's name for ``mask_path``).  ``mask_level`` is accepted and ignored, as in the
+    live reference (dataloader.py:240-241).  ``crf=True`` refines the label map with the fully connected CRF of
+    ``post_process_crf`` (utils.py:568-603), tile-wise -- see ``_crf_refine``; the reference accepts the flag but
+    its CRF call is commented out (Segmentation.py:327-331), so ``crf=False`` is the reference-identical path.
     The three files are written the way the reference leaves them after its ImageMagick pass: tiled (256x256)
     pyramidal JPEG-q90 TIFFs (tiffio.save_pyramidal; probabilities and uncertainty scaled to 8 bit);
     ``pyramidal=False`` writes lossless single-level TIFFs instead (float32 probabilities / uncertainty).
@@ -264,6 +289,8 @@ def getSegmentation(img_path,
     label = torch.empty(mean.shape, dtype=torch.uint8, device=mean.device)
     with torch.cuda.device(mean.device):
         engine.finalize(mean, var, count, threshold, label)
+        if crf:
+            _crf_refine(engine, torch, slide, mean, label, int(patch_size), int(batch_size))
         torch.cuda.synchronize()
     for m in models.values():
         m.close()

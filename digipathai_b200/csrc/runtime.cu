@@ -18,6 +18,7 @@
 #include "../../include/digipath_b200.h"
 #include "aux.cuh"
 #include "conv_tc.cuh"
+#include "crf.cuh"
 #include "dense_layer.cuh"
 
 namespace {
@@ -1396,6 +1397,58 @@ int dp_pyramid_down2(const float* in, int64_t w, int64_t h, float* out, void* st
   dp::pyramid_down2_kernel<<<grid_for((w / 2) * (h / 2), 256), 256, 0, st>>>(in, w, h,
                                                                                                           out);
   LAUNCH_OK();
+  return 0;
+}
+
+size_t dp_crf_workspace_bytes(int n_tiles, int h, int w) {
+  if (n_tiles < 1 || h < 1 || w < 1) return 0;
+  return (size_t)n_tiles * dp::CRF_PLANES * (size_t)h * w * sizeof(float);
+}
+
+int dp_crf_tiles(const uint8_t* rgb, const float* p1, int n_tiles, int h, int w, int n_iter, float sdims_gauss,
+                 float compat_gauss, float sdims_bilateral, float schan_bilateral, float compat_bilateral,
+                 void* workspace, size_t workspace_bytes, uint8_t* labels, float* q1_out, void* stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (!rgb || !p1 || !workspace || (!labels && !q1_out)) return fail("null argument");
+  if (n_tiles < 1 || h < 1 || w < 1 || n_iter < 0) return fail("bad CRF geometry");
+  if (!(sdims_gauss > 0) || !(sdims_bilateral > 0) || !(schan_bilateral > 0)) return fail("CRF kernel widths must be positive");
+  if (workspace_bytes < dp_crf_workspace_bytes(n_tiles, h, w))
+    return fail("CRF workspace too small: need %zu bytes", dp_crf_workspace_bytes(n_tiles, h, w));
+  float* ws = static_cast<float*>(workspace);
+  const long long npix = (long long)h * w;
+  const int ew = grid_for(npix * n_tiles, 256);
+  const dim3 bgrid((unsigned)((npix + 255) / 256), (unsigned)n_tiles);
+  auto filters = [&]() {   // AG -> G (separable spatial Gaussian), AB -> B (all-pairs bilateral)
+    dp::crf_gauss_pass_kernel<<<ew, 256, 0, st>>>(n_tiles, h, w, 1, 1.f / sdims_gauss, dp::CRF_AG0, dp::CRF_T0, ws);
+    dp::crf_gauss_pass_kernel<<<ew, 256, 0, st>>>(n_tiles, h, w, 0, 1.f / sdims_gauss, dp::CRF_T0, dp::CRF_G0, ws);
+    dp::crf_bilateral_kernel<<<bgrid, 256, 0, st>>>(h, w, ws);
+    g_launches.fetch_add(3, std::memory_order_relaxed);
+  };
+  dp::crf_init_kernel<<<ew, 256, 0, st>>>(rgb, p1, n_tiles, h, w, 1.f / sdims_bilateral, 1.f / schan_bilateral, ws);
+  LAUNCH_OK();
+  dp::crf_scale_kernel<<<ew, 256, 0, st>>>(n_tiles, npix, ws, 1);
+  LAUNCH_OK();
+  filters();
+  dp::crf_norm_kernel<<<ew, 256, 0, st>>>(n_tiles, npix, ws);
+  LAUNCH_OK();
+  if (n_iter == 0) {   // MAP of the unary alone
+    dp::crf_scale_kernel<<<ew, 256, 0, st>>>(n_tiles, npix, ws, 0);
+    LAUNCH_OK();
+  }
+  for (int it = 0; it < n_iter; ++it) {
+    dp::crf_scale_kernel<<<ew, 256, 0, st>>>(n_tiles, npix, ws, 0);
+    LAUNCH_OK();
+    filters();
+    const bool last = it + 1 == n_iter;
+    dp::crf_update_kernel<<<ew, 256, 0, st>>>(n_tiles, npix, compat_gauss, compat_bilateral, ws, last ? labels : nullptr,
+                                              last ? q1_out : nullptr);
+    LAUNCH_OK();
+  }
+  if (n_iter == 0) {
+    // Q is still softmax(-U): labels from it
+    dp::crf_update_kernel<<<ew, 256, 0, st>>>(n_tiles, npix, 0.f, 0.f, ws, labels, q1_out);
+    LAUNCH_OK();
+  }
   return 0;
 }
 

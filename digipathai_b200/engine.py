@@ -205,5 +205,28 @@ def pyramid_down2(plane: torch.Tensor) -> torch.Tensor:
     return out
 
 
+def dense_crf(rgb: torch.Tensor, p1: torch.Tensor, n_iter: int = 10, sdims_gauss: float = 10.0,
+              compat_gauss: float = 3.0, sdims_bilateral: float = 50.0, schan_bilateral: float = 20.0,
+              compat_bilateral: float = 10.0, return_marginal: bool = False):
+    """Fully connected CRF refinement (``post_process_crf``, DigiPathAI/helpers/utils.py:568-603; defaults = its
+    parameters).  rgb cuda uint8 [n,h,w,3]; p1 cuda float32 [n,h,w]; returns cuda uint8 labels [n,h,w] in {0,1}
+    (and the label-1 marginal when asked)."""
+    assert rgb.is_cuda and rgb.dtype == torch.uint8 and rgb.dim() == 4 and rgb.shape[3] == 3 and rgb.is_contiguous()
+    assert p1.is_cuda and p1.dtype == torch.float32 and p1.shape == rgb.shape[:3] and p1.is_contiguous()
+    n, h, w = p1.shape
+    nbytes = int(_lib.lib.dp_crf_workspace_bytes(n, h, w))
+    ws = torch.empty(nbytes // 4, dtype=torch.float32, device=p1.device)
+    labels = torch.empty((n, h, w), dtype=torch.uint8, device=p1.device)
+    q1 = torch.empty((n, h, w), dtype=torch.float32, device=p1.device) if return_marginal else None
+    _lib.check(
+        _lib.lib.dp_crf_tiles(C.c_void_p(rgb.data_ptr()), C.c_void_p(p1.data_ptr()), n, h, w, int(n_iter),
+                              float(sdims_gauss), float(compat_gauss), float(sdims_bilateral), float(schan_bilateral),
+                              float(compat_bilateral), C.c_void_p(ws.data_ptr()), nbytes,
+                              C.c_void_p(labels.data_ptr()),
+                              C.c_void_p(q1.data_ptr()) if q1 is not None else C.c_void_p(None), _stream_ptr()),
+        "dp_crf_tiles")
+    return (labels, q1) if return_marginal else labels
+
+
 def kernel_launch_count() -> int:
     return int(_lib.lib.dp_kernel_launch_count())

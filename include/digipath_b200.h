@@ -148,6 +148,21 @@ int dp_debug_read_stamps(dp_model* m, unsigned long long* out, int n);
 /* Executed tensor-core MACs of one forward pass over n_tiles tiles (after the sub-pixel rewrite). */
 int dp_model_executed_macs(const dp_model* m, int n_tiles, uint64_t* macs);
 
+/*
+ * Fully connected CRF refinement of probability tiles -- replaces `post_process_crf(image, probs, 2)`
+ * (DigiPathAI/helpers/utils.py:568-603: pydensecrf DenseCRF, unary_from_softmax(clip=1e-5), Gaussian pairwise
+ * sdims (10,10) compat 3, bilateral sdims (50,50) schan (20,20,20) compat 10, DIAG_KERNEL, NORMALIZE_SYMMETRIC,
+ * inference(10), argmax; its call site Segmentation.py:327-331 is commented out in the reference).  Mean-field
+ * inference with the Gaussian filters evaluated exactly (pydensecrf approximates them on a permutohedral lattice).
+ *   rgb   : device uint8 [n_tiles][h][w][3]       p1 : device float32 [n_tiles][h][w] (probability of label 1)
+ *   labels: device uint8 [n_tiles][h][w] in {0,1} (may be NULL)   q1_out: device float32 marginal of label 1 (may be NULL)
+ *   workspace: device scratch of dp_crf_workspace_bytes(n_tiles, h, w) bytes, owned by the caller.
+ */
+size_t dp_crf_workspace_bytes(int n_tiles, int h, int w);
+int dp_crf_tiles(const uint8_t* rgb, const float* p1, int n_tiles, int h, int w, int n_iter, float sdims_gauss,
+                 float compat_gauss, float sdims_bilateral, float schan_bilateral, float compat_bilateral,
+                 void* workspace, size_t workspace_bytes, uint8_t* labels, float* q1_out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -140,3 +140,27 @@ def test_get_segmentation_writes_pyramidal_tiffs(env, tmp_path):
     im.seek(2)
     assert im.size == (256, 192)
     assert Image.open(unc_path).n_frames == 3
+
+
+def test_get_segmentation_crf_flag(env):
+    """crf=True refines the thresholded map tile-wise with the fully connected CRF (the reference's commented-out
+    intent, Segmentation.py:327-331): every touched tile equals engine.dense_crf on that tile's inputs."""
+    import torch
+    from digipathai_b200 import engine
+    from digipathai_b200.Segmentation import getSegmentation, get_prediction, load_trained_models
+    from digipathai_b200.slide import open_slide, upload_xy_raster
+    w, slide, _ = env
+    kw = dict(patch_size=256, stride_size=256, batch_size=4, weights=w)
+    plain = getSegmentation(slide, crf=False, **kw)
+    refined = getSegmentation(slide, crf=True, **kw)
+    assert refined.shape == plain.shape and set(np.unique(refined)) <= {0.0, 255.0}
+    model = load_trained_models('dense', w, 256, max_batch=4)
+    _, pm = get_prediction(slide, models={'dense': model}, batch_size=4, patch_size=256, stride_size=256,
+                           return_device=True)
+    model.close()
+    raster = upload_xy_raster(open_slide(slide), 0, 1024, torch.device("cuda", 0))
+    x, y = 256, 256
+    want = engine.dense_crf(raster[x:x + 256, y:y + 256][None].contiguous(),
+                            pm['mean'][x:x + 256, y:y + 256][None].contiguous())[0].cpu().numpy() * 255.0
+    assert np.array_equal(refined[x:x + 256, y:y + 256], want)
+    assert (refined != plain).any()
