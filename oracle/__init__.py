@@ -12,5 +12,7 @@ vectors, and (b) hand-computable known-answer cases for the stitch arithmetic.  
 TensorFlow (conv / BN / pooling / softmax semantics) is restated from Keras' documented behaviour.
 
 Modules: ``pipeline_ref`` (numpy restatement of get_prediction / dataset / TTA / tissue mask), ``densenet_ref``,
-``inception_ref``, ``deeplab_ref`` (fp32 PyTorch-CPU restatements of the three Keras graphs of DigiPathAI/models/).
+``inception_ref``, ``deeplab_ref`` (fp32 PyTorch-CPU restatements of the three Keras graphs of DigiPathAI/models/),
+``crf_ref`` (exact mean-field inference of the DenseCRF model post_process_crf configures; pydensecrf itself -- a
+permutohedral-lattice approximation of the same model -- is not available: parity unpinned there too).
 """
