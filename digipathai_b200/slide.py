@@ -72,7 +72,18 @@ def open_slide(path_or_obj, n_levels: int | None = None):
     from PIL import Image
     Image.MAX_IMAGE_PIXELS = None
     with Image.open(path) as im:
-        return ArraySlide(np.asarray(im.convert("RGB")), n_levels or 1)
+        if n_levels is None:
+            # a pyramidal TIFF (pages that halve in size, e.g. ImageMagick `ptif:` or tiffio.save_pyramidal) keeps its
+            # level count -- the tissue mask is computed on the lowest level (dataloader.py:241-246); the levels
+            # themselves are re-derived by sub-sampling level 0 like every ArraySlide
+            n_levels, (w, h) = 1, im.size
+            for k in range(1, getattr(im, "n_frames", 1)):
+                im.seek(k)
+                if abs(im.size[0] - (w >> k)) > 1 or abs(im.size[1] - (h >> k)) > 1:
+                    break
+                n_levels = k + 1
+            im.seek(0)
+        return ArraySlide(np.asarray(im.convert("RGB")), n_levels)
 
 
 def level0_xy_raster(slide) -> np.ndarray:

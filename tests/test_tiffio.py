@@ -65,3 +65,14 @@ def test_small_and_binary_planes(tmp_path):
     one = str(tmp_path / "one.tiff")
     assert tiffio.save_pyramidal(one, np.full((100, 90), 7, np.uint8)) == 1     # fits one tile: single level
     assert np.abs(np.asarray(Image.open(one)).astype(int) - 7).max() <= 2
+
+
+def test_pyramidal_tiff_opens_as_a_multi_level_slide(tmp_path):
+    from digipathai_b200.slide import open_slide
+    a = _smooth(600, 900)
+    path = str(tmp_path / "s.tiff")
+    assert tiffio.save_pyramidal(path, a) == 3
+    s = open_slide(path)
+    assert s.level_count == 3 and s.level_dimensions[0] == (900, 600) and s.level_dimensions[2] == (225, 150)
+    region = s.read_region((0, 0), 0, (64, 64))
+    assert region.shape == (64, 64, 3) and np.abs(region[..., 0].astype(np.float32) - a[:64, :64]).mean() < 2.0
