@@ -103,3 +103,22 @@ def test_executed_macs_accounting(setup):
     # conv on their halo rows and, with 8-row regions, issue half-empty M = 128 MMAs for the 3x3 (+14 % overall);
     # the stem runs as a zero-padded 4x4 conv.  Executed work stays below the reference graph's.
     assert 0.75 * ref < ex < 1.0 * ref, (ex, ref)
+
+
+def test_host_batch_pipeline_matches_direct_forward(setup):
+    """engine.HostBatchPipeline (three-stream, double-buffered host front end) returns exactly what the direct call
+    returns, for more batches than it has buffer slots."""
+    from digipathai_b200.engine import HostBatchPipeline
+    s = setup
+    torch = s["torch"]
+    rng = np.random.default_rng(4)
+    batches = [rng.integers(0, 256, (3, 256, 256, 3)).astype(np.uint8) for _ in range(5)]
+    want = [s["model"].forward_tile_batch(torch.from_numpy(b).cuda()).cpu().numpy() for b in batches]
+    pipe = HostBatchPipeline(s["model"], batch=3)
+    ins = [torch.from_numpy(b).pin_memory() for b in batches]
+    outs = [torch.empty((3, 256, 256), dtype=torch.float32).pin_memory() for _ in batches]
+    for i, o in zip(ins, outs):
+        pipe.submit(i, o)
+    pipe.drain()
+    for o, w in zip(outs, want):
+        assert np.array_equal(o.numpy(), w)
