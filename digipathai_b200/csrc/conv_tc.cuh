@@ -278,9 +278,12 @@ __device__ __forceinline__ void issue_chunk_h(const ConvParams& p, IssueRing& r,
 // (~0.16 IPC per warp, tensor pipe 25-45 % busy on the high-resolution decoder layers); a second warp per
 // sub-partition hides that latency.  The PROLOGUE variant uses warps 8-11 for the pre-activation transform and
 // the RESIDUAL variant holds a 128-register prefetch per thread: both keep one group.
+#ifndef DP_EPI_GROUPS
+#define DP_EPI_GROUPS 2
+#endif
 template <bool PROLOGUE, bool RESIDUAL>
 struct ConvKernelShape {
-  static constexpr int kEpiGroups = (PROLOGUE || RESIDUAL) ? 1 : 2;
+  static constexpr int kEpiGroups = (PROLOGUE || RESIDUAL) ? 1 : DP_EPI_GROUPS;
   static constexpr int kThreads = (PROLOGUE || kEpiGroups == 2) ? 384 : 256;
 };
 
