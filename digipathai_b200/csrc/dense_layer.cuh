@@ -33,15 +33,18 @@ namespace dp {
 
 constexpr int kDlHaloW = 10;              // 8-pixel-wide regions + 1-pixel halo each side
 constexpr int kDlBStage = 128 * 128;      // W1 chunk [128 x 64]; W2 groups (3 taps x [32 x 64] = 12 KB) fit too
-constexpr int kDlTChunk = 23 * 1024;      // one 64-channel chunk of the bottleneck tile: 180 rows x 128 B, 1 KB aligned
-constexpr int kDlTBuf = 2 * kDlTChunk;    // 128 channels
-constexpr int kDlTBytes = 2 * kDlTBuf;    // double-buffered
 constexpr int kDlW2Group = 3;             // taps per W2 stage
 
 __host__ __device__ constexpr int dl_rows(int rh) { return kDlHaloW * (rh + 2); }
 // A-stage stride: the halo box rounded up to 1 KB.  The last M-block reads 128 rows regardless, i.e. up to 9 KB
 // past the stage end -- into the next stage or the weight ring, always inside the allocation, never used.
 __host__ __device__ constexpr int dl_a_stage(int rh) { return (dl_rows(rh) * 128 + 1023) / 1024 * 1024; }
+// One 64-channel chunk of the bottleneck tile T (halo rows x 128 B, 1 KB aligned): 23 KB for 16-row regions, 13 KB
+// for 8-row regions.  T = 2 chunks (128 channels) x 2 buffers.  The 3x3 MMAs read 128 rows from every tap offset,
+// i.e. up to ~7 KB past the tile for 8-row regions: T sits FIRST in shared memory so that this over-read lands in
+// the activation ring (don't-care accumulator rows), never outside the allocation.
+__host__ __device__ constexpr int dl_t_chunk(int rh) { return dl_a_stage(rh); }
+__host__ __device__ constexpr int dl_t_bytes(int rh) { return 4 * dl_t_chunk(rh); }
 
 struct DenseLayerParams {
   int n_img, H, W, C;        // map size, input channels of this layer
@@ -67,10 +70,10 @@ struct DenseLayerSmem {
 
 __host__ __device__ inline DenseLayerSmem dense_layer_smem(const DenseLayerParams& p) {
   DenseLayerSmem L;
-  L.a_off = DenseLayerSmem::kBarBytes;
+  L.t_off = DenseLayerSmem::kBarBytes;
+  L.a_off = L.t_off + dl_t_bytes(p.rh);
   L.b_off = L.a_off + p.a_stages * dl_a_stage(p.rh);
-  L.t_off = L.b_off + p.b_stages * kDlBStage;
-  L.pro_off = L.t_off + kDlTBytes;
+  L.pro_off = L.b_off + p.b_stages * kDlBStage;
   L.mid_off = L.pro_off + 2 * p.n_chunks * 64 * 4;
   L.total = L.mid_off + 128 * 4 + 1024;
   return L;
@@ -99,6 +102,7 @@ __global__ void __launch_bounds__(640, 1)
 dense_layer_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w1,
                    const __grid_constant__ CUtensorMap map_w2, const __grid_constant__ DenseLayerParams p) {
   constexpr int kRows = dl_rows(RH), kMBlk = (kRows + 127) / 128, kAStage = dl_a_stage(RH);
+  constexpr int kDlTChunk = dl_t_chunk(RH), kDlTBuf = 2 * kDlTChunk;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
@@ -136,7 +140,7 @@ dense_layer_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < p.a_stages; ++i) {
       mbar_init(&a_full[i], 1);
-      mbar_init(&a_ready[i], 256);
+      mbar_init(&a_ready[i], 8);      // per-warp arrivals (mbar_arrive_warp), 8 transform warps
       mbar_init(&a_empty[i], 1);
     }
     for (int i = 0; i < p.b_stages; ++i) {
@@ -144,12 +148,12 @@ dense_layer_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
       mbar_init(&b_empty[i], 1);
     }
     mbar_init(acc1_full, 1);
-    mbar_init(acc1_empty, 256);
+    mbar_init(acc1_empty, 8);       // 8 epilogue warps
     for (int i = 0; i < 2; ++i) {
-      mbar_init(&t_ready[i], 256);
+      mbar_init(&t_ready[i], 8);
       mbar_init(&t_empty[i], 1);
       mbar_init(&acc2_full[i], 1);
-      mbar_init(&acc2_empty[i], 256);
+      mbar_init(&acc2_empty[i], 8);
     }
     fence_barrier_init();
   }
@@ -391,8 +395,8 @@ dense_layer_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
       }
       tc_fence_before();
       fence_proxy_async_smem();
-      mbar_arrive(acc1_empty);
-      mbar_arrive(&t_ready[tb]);
+      mbar_arrive_warp(acc1_empty);
+      mbar_arrive_warp(&t_ready[tb]);
       dl_trace_ev(tc, 2, k);
     };
     // ---- fin(k): acc2[k & 1] -> fp16 -> the 32 new channels of the concat buffer
@@ -423,7 +427,7 @@ dense_layer_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
         if (valid) st_global_v8(orow + 16 * half, pk);
       }
       tc_fence_before();
-      mbar_arrive(&acc2_empty[tb]);
+      mbar_arrive_warp(&acc2_empty[tb]);
       dl_trace_ev(tc, 1, k);
     };
     if (n_local > 0) mid(0);
@@ -481,7 +485,7 @@ dense_layer_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
           }
         }
         fence_proxy_async_smem();
-        mbar_arrive(&a_ready[sa]);
+        mbar_arrive_warp(&a_ready[sa]);
         dl_trace_ev(tc, 0, k);
         if (++sa == p.a_stages) { sa = 0; pa ^= 1; }
       }

@@ -69,6 +69,15 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
+// One arrival per WARP: all lanes have finished the work the barrier publishes (their own fences included), the warp
+// converges, lane 0 arrives.  256 per-thread arrivals are 256 serialised shared-memory atomics on one word (~3 clk
+// each: ~750 clk per hand-off, measured as the floor of the per-chunk transform and of the mid epilogue); 8 are not.
+// Barriers used this way are initialised with the number of arriving WARPS.
+__device__ __forceinline__ void mbar_arrive_warp(uint64_t* bar) {
+  __syncwarp();
+  if ((threadIdx.x & 31) == 0) mbar_arrive(bar);
+}
+
 // generic-proxy writes to smem -> visible to the async proxy (TMA / tcgen05 operand reads)
 __device__ __forceinline__ void fence_proxy_async_smem() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");

@@ -614,10 +614,20 @@ int plan_dense_layer(dp_model* m, const BlobOp& op, int img0, int B, Launch& L) 
   if (p.n_safe_chunks > p.n_chunks) p.n_safe_chunks = p.n_chunks;
   p.pro_scale = a.pro_scale; p.pro_shift = a.pro_shift; p.mid_shift = a.epi_shift;
   p.out = buf_at(op.in_buf);
-  const int budget = 227 * 1024 - DenseLayerSmem::kBarBytes - kDlTBytes - 2 * p.n_chunks * 64 * 4 - 128 * 4 - 1024 -
+  const int budget = 227 * 1024 - DenseLayerSmem::kBarBytes - dl_t_bytes(p.rh) - 2 * p.n_chunks * 64 * 4 - 128 * 4 - 1024 -
                      10 * 1024;   // the last A stage's M-block over-read must stay inside the allocation
   const int a_stage = dl_a_stage(p.rh);
-  p.a_stages = 4; p.b_stages = 4;
+  // Activation ring as deep as shared memory allows (up to 8): a halo chunk is 100-180 separate 128-byte segments,
+  // ~3.5k clk of TMA latency under load, and phase 1 of the small-map layers consumed one chunk per ~950 clk with
+  // 4 stages in flight -- TMA-latency bound, not transform or MMA bound (halving the transform math or dropping
+  // its proxy fence changed nothing).
+  p.a_stages = kMaxAStages; p.b_stages = 4;
+  {
+    const char* env = getenv("DP_DL_A_STAGES");
+    if (env && atoi(env) >= 2 && atoi(env) <= kMaxAStages) p.a_stages = atoi(env);
+    env = getenv("DP_DL_B_STAGES");
+    if (env && atoi(env) >= 2 && atoi(env) <= kMaxBStages) p.b_stages = atoi(env);
+  }
   while (p.a_stages * a_stage + p.b_stages * kDlBStage > budget && p.a_stages > 2) --p.a_stages;
   while (p.a_stages * a_stage + p.b_stages * kDlBStage > budget && p.b_stages > 2) --p.b_stages;
   if (p.a_stages * a_stage + p.b_stages * kDlBStage > budget) return fail("dense layer: shared memory budget exceeded");
