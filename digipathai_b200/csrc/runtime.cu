@@ -1433,12 +1433,13 @@ int dp_crf_tiles(const uint8_t* rgb, const float* p1, int n_tiles, int h, int w,
     dp::crf_gauss_pass_kernel<<<ew, 256, 0, st>>>(n_tiles, h, w, 0, 1.f / sdims_gauss, dp::CRF_T0, dp::CRF_G0, ws);
     dp::crf_bilateral_kernel<<<bgrid, 256, 0, st>>>(h, w, ws);
     g_launches.fetch_add(3, std::memory_order_relaxed);
+    return cudaGetLastError();
   };
   dp::crf_init_kernel<<<ew, 256, 0, st>>>(rgb, p1, n_tiles, h, w, 1.f / sdims_bilateral, 1.f / schan_bilateral, ws);
   LAUNCH_OK();
   dp::crf_scale_kernel<<<ew, 256, 0, st>>>(n_tiles, npix, ws, 1);
   LAUNCH_OK();
-  filters();
+  CU_OK(filters());
   dp::crf_norm_kernel<<<ew, 256, 0, st>>>(n_tiles, npix, ws);
   LAUNCH_OK();
   if (n_iter == 0) {   // MAP of the unary alone
@@ -1448,7 +1449,7 @@ int dp_crf_tiles(const uint8_t* rgb, const float* p1, int n_tiles, int h, int w,
   for (int it = 0; it < n_iter; ++it) {
     dp::crf_scale_kernel<<<ew, 256, 0, st>>>(n_tiles, npix, ws, 0);
     LAUNCH_OK();
-    filters();
+    CU_OK(filters());
     const bool last = it + 1 == n_iter;
     dp::crf_update_kernel<<<ew, 256, 0, st>>>(n_tiles, npix, compat_gauss, compat_bilateral, ws, last ? labels : nullptr,
                                               last ? q1_out : nullptr);
