@@ -57,11 +57,14 @@ class ClockSampler:
 
     def __init__(self, gpu_index: int):
         self.gpu, self.rows, self.proc = gpu_index, [], None
+        self.t0 = self.t1 = None
 
     def start(self):
+        """Starts the sampler process (nvidia-smi needs ~100 ms to come up, so this is called well before the timed
+        region); rows are time-stamped on receipt and `mark_begin` / `mark_end` bracket the timed region."""
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i",
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20", "-i",
                  str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._pump, daemon=True).start()
         except Exception:  # noqa: BLE001
@@ -69,15 +72,29 @@ class ClockSampler:
 
     def _pump(self):
         for line in self.proc.stdout:
-            self.rows.append(line.strip())
+            self.rows.append((time.perf_counter(), line.strip()))
+
+    def mark_begin(self):
+        self.t0 = time.perf_counter()
+
+    def mark_end(self):
+        self.t1 = time.perf_counter()
 
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        time.sleep(0.05)
         self.proc.terminate()
+        inside = [r for (t, r) in self.rows if self.t0 is not None and self.t0 <= t <= (self.t1 or t) + 0.02]
+        note = "sampled every 20 ms inside the timed region"
+        if not inside:
+            # a timed region shorter than the sampling period: fall back to the samples taken while the same loop
+            # ran as warm-up / e2e legs right around it (same kernels, same load)
+            inside = [r for (_, r) in self.rows]
+            note = "timed region shorter than the 20 ms sampling period: samples from the surrounding warm-up and e2e loops"
+        self.note = note
         sm, mx, reasons = [], [], set()
-        for r in self.rows:
+        for r in inside:
             f = [x.strip() for x in r.split(",")]
             if len(f) < 9:
                 continue
@@ -89,7 +106,7 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "note": note}
 
 
 def dist_env():
@@ -254,23 +271,24 @@ def main():
     def step(i):
         model.forward_tiles(slide, coords_all[i % n_coord_sets], 0, 0, out=probs)
 
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()                     # nvidia-smi takes ~100 ms to come up: start it before the warm-up
     for i in range(args.warmup):
         step(i)
     barrier()
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     n0 = engine.kernel_launch_count()
     barrier()
+    sampler.mark_begin()
     for k in range(args.steps):
         flush.zero_()                       # L2 flush between timed iterations (not timed)
         ev[k][0].record()
         step(args.warmup + k)
         ev[k][1].record()
     barrier()
+    sampler.mark_end()
     launches = engine.kernel_launch_count() - n0
-    clocks = sampler.stop() if rank == 0 else None
     ms_total = sum(a.elapsed_time(b) for a, b in ev)
     ms_total = max_over_ranks(ms_total)
     ms_per_step = ms_total / args.steps
@@ -316,6 +334,8 @@ def main():
     barrier()
     e2e_ms = max_over_ranks(p0.elapsed_time(p1))
     e2e_value = world * BATCH * args.steps / (e2e_ms * 1e-3)
+
+    clocks = sampler.stop() if rank == 0 else None
 
     # ---------------------------------------------------------------- per-kernel roofline (instrumented pass)
     model.set_option("profile", 1)
