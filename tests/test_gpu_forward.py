@@ -122,3 +122,24 @@ def test_host_batch_pipeline_matches_direct_forward(setup):
     pipe.drain()
     for o, w in zip(outs, want):
         assert np.array_equal(o.numpy(), w)
+
+
+def test_early_tensors_agree_with_the_emulator_to_fp16_rounding(setup):
+    """Before rounding noise has accumulated through the dense blocks, the CUDA path and the CPU emulator of the same
+    layer program agree to fp16 rounding: pins the stem gather, the 4x4 space-to-depth stem conv, the zero-padded
+    max pool, the first fused dense layers and the first transition end to end."""
+    import emulator
+    s = setup
+    t = s["torch"].from_numpy(s["tiles"]).cuda()
+    s["model"].forward_tile_batch(t)
+    s["torch"].cuda.synchronize()
+    _, ebufs = emulator.run(s["prog"], s["tiles"], keep=True)
+    prog = s["prog"]
+    n = len(s["tiles"])
+    # (buffer, channel range, tolerance relative to the tensor's max): D1[96:160) = conv1, D2[128:384) = pool1 + block 2
+    for name, lo, hi, tol in (("stem_s2d", 0, 64, 0.0), ("D1", 96, 160, 1e-3), ("D2", 128, 192, 1e-3),
+                              ("D2", 192, 256, 4e-3), ("D2", 256, 384, 8e-3), ("Q2", 0, 256, 8e-3)):
+        bi = prog.buf(name)
+        a = s["model"].read_buffer(bi, n).astype(np.float32)[..., lo:hi]
+        b = ebufs[bi].numpy()[..., lo:hi]
+        assert np.abs(a - b).max() <= tol * max(1.0, np.abs(b).max()), (name, lo, np.abs(a - b).max(), np.abs(b).max())
