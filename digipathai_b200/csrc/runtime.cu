@@ -396,10 +396,26 @@ int plan_conv(dp_model* m, const BlobOp& op, int img0, int B, Launch& L) {
   const long long m_total = (long long)B * OH * OW;
   if (p.mode == MODE_D) {
     p.m_total = (int)m_total;
-    int sub = 4;
-    while (sub > 1 && (sub * n_tile > kTmemCols ||
-                       ((m_total + sub * 128 - 1) / (sub * 128)) * p.n_ntiles < m->num_sms))
-      sub >>= 1;
+    // Sub-tiles of 128 pixels per item: minimise  waves x time-per-item  with the measured per-chunk costs: MMA time
+    // sub x 4 x max(64, N/2) clk (N/2 only above the 48-64 clk floor) plus ~700 clk of fixed per-chunk hand-off
+    // (two barrier waits, two commits, issue).  Fewer, larger items win whenever they do not add a wave.
+    int sub = 1;
+    if (!getenv("DP_D_SUB_BY_ITEMS")) {
+      double best = 0;
+      for (int cand = 1; cand <= 4; cand <<= 1) {
+        if (cand * n_tile > kTmemCols) break;
+        const long long items = ((m_total + cand * 128 - 1) / (cand * 128)) * p.n_ntiles;
+        const long long waves = (items + m->num_sms - 1) / m->num_sms;
+        const double per_item = (double)p.n_chunks * (cand * 4.0 * (n_tile / 2 > 64 ? n_tile / 2 : 64) + 700.0) + 3000.0;
+        const double cost = waves * per_item;
+        if (best == 0 || cost < best) { best = cost; sub = cand; }
+      }
+    } else {
+      sub = 4;
+      while (sub > 1 && (sub * n_tile > kTmemCols ||
+                         ((m_total + sub * 128 - 1) / (sub * 128)) * p.n_ntiles < m->num_sms))
+        sub >>= 1;
+    }
     if (residual) sub = 1;   // the residual epilogue prefetches one pixel row (<= 256 channels) per thread
     p.sub = sub;
     p.n_mtiles = (int)((m_total + sub * 128 - 1) / (sub * 128));
