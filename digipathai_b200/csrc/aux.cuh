@@ -242,7 +242,8 @@ __global__ void bn_act_pool_kernel(const __half* __restrict__ in, int in_ctot, i
 // padding='same'; stride 2: explicit ZeroPadding2D((1,1)) + 'valid'), so input pixel = stride * o + (k - 1) * rate.
 // Measured (ncu, round 1): instruction-issue bound (80 % issue-active, ~1.3 TB/s), not HBM bound -- fp16 unpack +
 // fp32 FMA per tap.  A 4-pixels-per-thread register-window variant (half the loads) was NOT faster (128 registers,
-// 22 % occupancy, latency bound) and was dropped; next step is packed-half2 unpack sharing across taps.
+// 22 % occupancy, latency bound) and was dropped; so was an instruction-lean variant (fp32 weights, half2 ReLU,
+// template-resolved activations, 48 registers): also not faster -- the issue slots are not what it waits on after all.
 __global__ void dwconv3x3_kernel(const __half* __restrict__ in, int in_ctot, int in_choff, __half* __restrict__ out,
                                  int out_ctot, int out_choff, int n_img, int H, int W, int C, int stride, int rate,
                                  const __half* __restrict__ w, const float* __restrict__ shift, int pre_relu,
