@@ -32,21 +32,30 @@ def dense_crf(image_hw3: np.ndarray, p1_hw: np.ndarray, n_iter: int = 10, sdims_
               sdims_bil=50.0, schan_bil=20.0, compat_bil=10.0):
     """image uint8 [h,w,3], p1 float [h,w] (probability of label 1) -> (labels int64 [h,w], q1 float64 [h,w])."""
     h, w = p1_hw.shape
+    p = np.stack([1.0 - p1_hw.ravel(), p1_hw.ravel()], axis=1).astype(np.float64)
+    U = -np.log(np.clip(p, 1e-5, 1.0))
+    Q = _mean_field(image_hw3, U, n_iter, sdims_gauss, compat_gauss, sdims_bil, schan_bil, compat_bil)
+    return Q.argmax(1).reshape(h, w), Q[:, 1].reshape(h, w)
+
+
+def _mean_field(img, U, n_iter, sdims_gauss, compat_gauss, sdims_bil, schan_bil, compat_bil):
+    """Marginals float64 [h*w, n_labels] after ``n_iter`` mean-field updates; ``U`` energies [h*w, n_labels]
+    (stored as float32, as pydensecrf does); ``compat_bil=None`` leaves the bilateral term out."""
+    h, w = img.shape[:2]
     yy, xx = np.mgrid[0:h, 0:w]
     coords = np.stack([yy.ravel(), xx.ravel()], axis=1).astype(np.float64)
-    rgb = image_hw3.reshape(-1, 3).astype(np.float64)
-    p = np.stack([1.0 - p1_hw.ravel(), p1_hw.ravel()], axis=1).astype(np.float64)
-    U = -np.log(np.clip(p, 1e-5, 1.0)).astype(np.float32).astype(np.float64)   # pydensecrf stores the unary as float32
+    rgb = img.reshape(-1, 3).astype(np.float64)
+    U = np.asarray(U).astype(np.float32).astype(np.float64)
+    terms = [(coords / sdims_gauss, compat_gauss)]
+    if compat_bil is not None:
+        terms.append((np.concatenate([coords / sdims_bil, rgb / schan_bil], axis=1), compat_bil))
     kernels = []
-    for feats, wgt in ((coords / sdims_gauss, compat_gauss),
-                       (np.concatenate([coords / sdims_bil, rgb / schan_bil], axis=1), compat_bil)):
+    for feats, wgt in terms:
         K = _kernel(feats)
-        norm = 1.0 / np.sqrt(K.sum(1) + 1e-20)
-        kernels.append((K, norm, wgt))
+        kernels.append((K, 1.0 / np.sqrt(K.sum(1) + 1e-20), wgt))
 
     def softmax(t):
-        t = t - t.max(1, keepdims=True)
-        e = np.exp(t)
+        e = np.exp(t - t.max(1, keepdims=True))
         return e / e.sum(1, keepdims=True)
 
     Q = softmax(-U)
@@ -55,4 +64,38 @@ def dense_crf(image_hw3: np.ndarray, p1_hw: np.ndarray, n_iter: int = 10, sdims_
         for K, norm, wgt in kernels:
             t = t + wgt * (norm[:, None] * (K @ (norm[:, None] * Q)))
         Q = softmax(t)
-    return Q.argmax(1).reshape(h, w), Q[:, 1].reshape(h, w)
+    return Q
+
+
+def unary_from_labels(labels: np.ndarray, n_labels: int, gt_prob: float, zero_unsure: bool = True) -> np.ndarray:
+    """pydensecrf.utils.unary_from_labels restated (called at DigiPathAI/helpers/utils.py:553): energies
+    float32 [n_pixels, n_labels].  The labelled class costs -log(gt_prob), every other class
+    -log((1 - gt_prob) / (n_labels - 1)).  With ``zero_unsure`` label 0 means "unknown" (uniform energy
+    -log(1 / n_labels)) and label k > 0 names class k - 1."""
+    lab = np.asarray(labels).ravel().astype(np.int64)
+    U = np.full((lab.size, n_labels), -np.log((1.0 - gt_prob) / (n_labels - 1)), dtype=np.float32)
+    idx = np.arange(lab.size)
+    if zero_unsure:
+        known = lab > 0
+        U[idx[known], lab[known] - 1] = -np.log(gt_prob)
+        U[~known, :] = -np.log(1.0 / n_labels)
+    else:
+        U[idx, lab] = -np.log(gt_prob)
+    return U
+
+
+def do_crf(im, mask: np.ndarray, n_labels: int, enable_color: bool = False, zero_unsure: bool = True):
+    """``do_crf`` (DigiPathAI/helpers/utils.py:548-566; never called by the reference) with exact filters:
+    unary from the hard labels (gt_prob 0.7), Gaussian sxy 3 compat 3, optional bilateral sxy 80 srgb 13 compat 10,
+    5 mean-field iterations, MAP index mapped back through the sorted distinct mask values one index after the
+    other (utils.py:563-565: a later index can re-map pixels an earlier one already rewrote).
+    Returns (MAP [h, w] in mask values, marginals float64 [h*w, n_labels])."""
+    colors, labels = np.unique(mask, return_inverse=True)
+    h, w = mask.shape[:2]
+    U = unary_from_labels(labels, n_labels, 0.7, zero_unsure)
+    img = np.zeros((h, w, 3), np.uint8) if im is None else np.asarray(im).astype(np.uint8)
+    Q = _mean_field(img, U, 5, 3.0, 3.0, 80.0, 13.0, 10.0 if enable_color else None)
+    MAP = Q.argmax(1).reshape(h, w)
+    for u in np.unique(MAP):
+        MAP[MAP == u] = colors[u]
+    return MAP, Q
