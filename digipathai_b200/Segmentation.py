@@ -46,7 +46,7 @@ def _torch():
 
 def get_prediction(wsi_path, mask_path=None, label_path=None, batch_size=64, models=None, tta_list=None,
                    num_workers=8, verbose=0, patch_size=256, stride_size=256, mask_level=-1, status=None,
-                   *, device=0, tile_range=None, return_device=False, finalize=True, tissue_mask=None):
+                   *, device=0, tile_range=None, return_device=False, finalize=True, tissue_mask=None, grid=None):
     """Patch based segmentor (reference: Segmentation.py:65-189).
 
     ``models`` maps a name to a ``TileModel`` (engine.py) -- the object that replaces the Keras model.
@@ -54,7 +54,9 @@ def get_prediction(wsi_path, mask_path=None, label_path=None, batch_size=64, mod
     of memmaps).  Keyword-only extensions: ``device`` (CUDA ordinal), ``tile_range=(lo, hi)`` restricts the run
     to a slice of the post-``drop_last`` tile list (multi-GPU sharding, dist.py), ``return_device`` keeps the
     planes as torch CUDA tensors, ``finalize=False`` skips the normalisation (sharded runs normalise after the
-    halo exchange), ``tissue_mask`` supplies a precomputed [x, y] mask instead of the Otsu/HSV heuristic.
+    halo exchange), ``tissue_mask`` supplies a precomputed RAW [x, y] mask instead of the Otsu/HSV heuristic (the
+    morphology of utils.py:200-219 is still applied to it), ``grid`` a ready ``TileGrid`` of this slide (sharded
+    runs build it once and index it with ``tile_range``).
     ``mask_path`` / ``label_path`` / ``num_workers`` / ``mask_level`` are accepted for signature
     compatibility; the live reference passes None for the first two and ignores the last (dataloader.py:240-241).
     """
@@ -63,8 +65,11 @@ def get_prediction(wsi_path, mask_path=None, label_path=None, batch_size=64, mod
     if not models:
         raise ValueError("get_prediction needs at least one model")
     slide = open_slide(wsi_path)
-    grid = TileGrid(slide, patch_size=patch_size, stride_size=stride_size, batch_size=batch_size,
-                    roi_masking=True, mask=tissue_mask)
+    if grid is None:
+        grid = TileGrid(slide, patch_size=patch_size, stride_size=stride_size, batch_size=batch_size,
+                        roi_masking=True, mask=tissue_mask)
+    elif (grid.patch_size, grid.stride_size, grid.batch_size) != (int(patch_size), int(stride_size), int(batch_size)):
+        raise ValueError("grid= was built for another patch / stride / batch size")
     n_batches = len(grid)
     print("Length of DataLoader: {}".format(n_batches))
     passes = _tta.pass_codes(tta_list)

@@ -132,6 +132,26 @@ def gather_planes(planes, stripes, rank: int, world_size: int, W: int, group=Non
     return None
 
 
+def local_part(slide, models, rank: int, world: int, batch_size=32, tta_list=None, patch_size=256, stride_size=128,
+               status=None, device=None, tissue_mask=None):
+    """One rank's share before the halo exchange: ``(grid, [mean, var, count] partial-sum planes over this rank's
+    stripe, stripes of all ranks, (b_lo, b_hi))``.  The grid is built once here and handed to ``get_prediction``
+    as is (``tissue_mask`` is a RAW mask, see TileGrid)."""
+    from .Segmentation import get_prediction
+    from .tissue import TileGrid
+    grid = TileGrid(slide, patch_size, stride_size, batch_size, True, tissue_mask)
+    parts, stripes = stripes_for(grid.coords, batch_size, world, patch_size)
+    lo, hi = parts[rank]
+    _, out = get_prediction(slide, batch_size=batch_size, models=models, tta_list=tta_list,
+                            patch_size=patch_size, stride_size=stride_size, status=status, device=device,
+                            tile_range=(lo * batch_size, hi * batch_size), return_device=True, finalize=False,
+                            grid=grid)
+    if hi > lo and tuple(out['x_range']) != tuple(stripes[rank]):
+        # mismatched geometry would turn into mismatched P2P sizes in halo_exchange, i.e. a hang: fail here instead
+        raise RuntimeError(f"rank {rank}: planes cover x {out['x_range']}, stripe plan says {stripes[rank]}")
+    return grid, [out['mean'], out['var'], out['count']], stripes, (lo, hi)
+
+
 def sharded_get_prediction(wsi_path, models, batch_size=32, tta_list=None, patch_size=256, stride_size=128,
                            status=None, device=None, gather=False, tissue_mask=None):
     """``get_prediction`` across the ranks of the default process group (one process per GPU).
@@ -143,21 +163,13 @@ def sharded_get_prediction(wsi_path, models, batch_size=32, tta_list=None, patch
     import torch
     import torch.distributed as dist
     from . import engine
-    from .Segmentation import get_prediction
     from .slide import open_slide
-    from .tissue import TileGrid
     rank, world = dist.get_rank(), dist.get_world_size()
     if device is None:
         device = torch.cuda.current_device()
     slide = open_slide(wsi_path)
-    grid = TileGrid(slide, patch_size, stride_size, batch_size, True, tissue_mask)
-    parts, stripes = stripes_for(grid.coords, batch_size, world, patch_size)
-    lo, hi = parts[rank]
-    _, out = get_prediction(slide, batch_size=batch_size, models=models, tta_list=tta_list,
-                            patch_size=patch_size, stride_size=stride_size, status=status, device=device,
-                            tile_range=(lo * batch_size, hi * batch_size), return_device=True, finalize=False,
-                            tissue_mask=grid.mask if tissue_mask is None else tissue_mask)
-    planes = [out['mean'], out['var'], out['count']]
+    grid, planes, stripes, (lo, hi) = local_part(slide, models, rank, world, batch_size, tta_list, patch_size,
+                                                 stride_size, status, device, tissue_mask)
     sent = halo_exchange(planes, stripes, rank) if hi > lo else 0
     with torch.cuda.device(planes[0].device):
         engine.finalize(planes[0], planes[1], planes[2], 0.0, None)

@@ -114,12 +114,15 @@ class TileGrid:
 
     ``coords`` is int32 [n, 2] (x, y) for the tiles that WILL be predicted: ``DataLoader(drop_last=True)``
     (Segmentation.py:92) silently drops the final ``n mod batch`` tiles.
+    ``mask`` is a RAW tissue mask (the dataset applies its morphology to whatever mask it is given,
+    dataloader.py:256-270): feeding ``self.mask`` back in dilates twice -- pass ``self.raw_mask``.
     """
 
     def __init__(self, slide, patch_size: int = 256, stride_size: int = 128, batch_size: int = 32,
                  roi_masking: bool = True, mask: np.ndarray | None = None):
         self.slide = slide
         self.patch_size = int(patch_size)
+        self.stride_size = int(stride_size)
         self.level = len(slide.level_dimensions) - 1                       # dataloader.py:241 (mask_level ignored)
         self.factor = int(stride_size) // int(slide.level_downsamples[self.level])  # dataloader.py:242
         if self.factor < 1:
@@ -127,6 +130,7 @@ class TileGrid:
         X_slide, Y_slide = slide.level_dimensions[0]
         if mask is None:
             mask = tissue_mask(slide, self.level)
+        self.raw_mask = mask                                               # before morphology: what ``mask=`` takes
         self.mask = morpho_process(np.uint8(mask), self.level)
         X_mask, Y_mask = self.mask.shape
         if X_slide // X_mask != Y_slide // Y_mask:

@@ -87,6 +87,66 @@ def test_sharded_tile_ranges_equal_unsharded():
     model.close()
 
 
+def test_local_parts_of_every_rank_sum_to_the_unsharded_planes():
+    """dist.local_part (what each rank of sharded_get_prediction computes before the halo exchange) for world
+    sizes 2 and 3, run one rank after the other on this GPU: the stripes it reports tile the unsharded result,
+    with the default tissue heuristic and with a caller-supplied raw mask."""
+    from digipathai_b200 import dist as dpd
+    from digipathai_b200.Segmentation import get_prediction, load_trained_models
+    from digipathai_b200.models.densenet import init_densenet_weights
+    from digipathai_b200.slide import synthetic_slide
+    from digipathai_b200.tissue import TileGrid
+    slide = synthetic_slide(2048, 1536, seed=3, n_levels=2)
+    model = load_trained_models('dense', init_densenet_weights(0), 256, max_batch=8)
+    kw = dict(batch_size=8, patch_size=256, stride_size=128)
+    raw = TileGrid(slide, 256, 128, 8).raw_mask
+    for mask in (None, raw):
+        _, full = get_prediction(slide, models={'dense': model}, finalize=False, tissue_mask=mask, **kw)
+        assert int(full['count'].max()) > 0
+        for world in (2, 3):
+            acc = {k: np.zeros_like(full[k]) for k in ('mean', 'var', 'count')}
+            n_tiles = 0
+            for rank in range(world):
+                grid, planes, stripes, (lo, hi) = dpd.local_part(slide, {'dense': model}, rank, world, device=0,
+                                                                 tissue_mask=mask, **kw)
+                x0, x1 = stripes[rank]
+                n_tiles += (hi - lo) * 8
+                if hi > lo:
+                    for k, p in zip(('mean', 'var', 'count'), planes):
+                        assert p.shape[0] == x1 - x0
+                        acc[k][x0:x1] += p.cpu().numpy()
+            assert n_tiles == len(grid.coords)
+            assert np.array_equal(acc['count'], full['count'])
+            assert np.abs(acc['mean'] - full['mean']).max() <= 4e-7 * max(1.0, float(full['mean'].max()))
+            assert np.abs(acc['var'] - full['var']).max() <= 1e-6
+    model.close()
+
+
+def test_sharded_get_prediction_in_a_world_of_one_is_get_prediction(tmp_path):
+    import torch
+    import torch.distributed as dist
+    from digipathai_b200 import dist as dpd
+    from digipathai_b200.Segmentation import get_prediction, load_trained_models
+    from digipathai_b200.models.densenet import init_densenet_weights
+    from digipathai_b200.slide import synthetic_slide
+    slide = synthetic_slide(1536, 1280, seed=4, n_levels=2)
+    model = load_trained_models('dense', init_densenet_weights(0), 256, max_batch=8)
+    kw = dict(batch_size=8, patch_size=256, stride_size=128, tta_list=['FLIP_LEFT_RIGHT'])
+    _, want = get_prediction(slide, models={'dense': model}, **kw)
+    assert not dist.is_initialized()
+    dist.init_process_group('gloo', init_method=f'file://{tmp_path}/pg', rank=0, world_size=1)
+    try:
+        grid, got, info = dpd.sharded_get_prediction(slide, {'dense': model}, device=0, gather=True, **kw)
+    finally:
+        dist.destroy_process_group()
+    assert info['halo_bytes_sent'] == 0 and info['batches'] == (0, len(grid))
+    x0, x1 = info['stripe']
+    assert np.array_equal(got['mean'].cpu().numpy()[x0:x1], want['mean'][x0:x1])
+    assert np.array_equal(got['var'].cpu().numpy()[x0:x1], want['var'][x0:x1])
+    assert not want['mean'][:x0].any() and not want['mean'][x1:].any()
+    model.close()
+
+
 def test_stitch_on_a_large_plane_matches_numpy_windows():
     import torch
     from digipathai_b200 import engine

@@ -115,3 +115,17 @@ def test_array_slide_read_region_and_levels():
     assert np.array_equal(s.read_region((8, 4), 1, (4, 4)), r[::2, ::2][2:6, 4:8])
     edge = s.read_region((60, 44), 0, (8, 8))
     assert np.array_equal(edge[:4, :4], r[44:, 60:]) and edge[4:, :].sum() == 0
+
+
+def test_grid_raw_mask_round_trips_and_the_processed_mask_does_not():
+    """``mask=`` takes a RAW mask (the dataset applies its morphology to any mask it is given,
+    dataloader.py:256-270): rebuilding from ``raw_mask`` reproduces the grid, from ``mask`` it dilates twice.
+    The multi-GPU path (dist.local_part) therefore hands the grid object over, never the processed mask."""
+    from digipathai_b200.slide import synthetic_slide
+    s = synthetic_slide(4096, 3072, seed=0, n_levels=3)
+    g = TileGrid(s, 256, 128, 8)
+    again = TileGrid(s, 256, 128, 8, mask=g.raw_mask)
+    assert np.array_equal(again.coords, g.coords) and np.array_equal(again.mask, g.mask)
+    twice = TileGrid(s, 256, 128, 8, mask=g.mask)
+    assert twice.mask.sum() > g.mask.sum()
+    assert (g.stride_size, g.patch_size, g.batch_size) == (128, 256, 8)
