@@ -1,0 +1,168 @@
+"""The multi-GPU orchestration (dist.sharded_get_prediction -> get_prediction(tile_range, grid) -> halo exchange ->
+normalise -> gather) end to end on CPU: world_size 2 and 3 over gloo, with TEST DOUBLES for the three device entry
+points the loop calls (TileModel.forward_tiles, engine.stitch, engine.finalize) -- numpy restatements of
+Segmentation.py:162-177 living in this file only.  The doubles emit dyadic values, so every fp32 sum is exact and
+the sharded planes must equal the single-process planes bit for bit.
+
+This is host-logic coverage (which tiles a rank runs, which stripe it owns, what it swaps); the CUDA kernels
+themselves are covered by the ``-m gpu`` tests.
+"""
+import contextlib
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+P, STRIDE, BATCH = 64, 32, 4
+
+
+class _FakeModel:
+    """forward_tiles double: 'probability' = red channel / 256, scaled by a per-pass dyadic factor."""
+    patch, max_batch = P, 32
+
+    def forward_tiles(self, raster, coords, t_in=0, t_out=0, out=None):
+        for b, (x, y) in enumerate(coords.tolist()):
+            out[b] = raster[x:x + P, y:y + P, 0].to(torch.float32) / 256.0 / (1 + (t_in > 0) + 2 * (t_out > 4))
+        return out
+
+    def close(self):
+        pass
+
+
+def _stitch(probs, coords, mean, var, count, x_lo=0):
+    m = probs.mean(0)                                        # Segmentation.py:162-163
+    v = ((probs - m[None]) ** 2).mean(0)
+    for b, (x, y) in enumerate(coords.tolist()):
+        mean[x - x_lo:x - x_lo + P, y:y + P] += m[b]          # :164-173
+        var[x - x_lo:x - x_lo + P, y:y + P] += v[b]
+        count[x - x_lo:x - x_lo + P, y:y + P] += 1
+
+
+def _finalize(mean, var, count, threshold, label=None):
+    c = count.clone()
+    c[c == 0] = 1                                            # :175-177
+    mean /= c.to(torch.float32)
+    var /= (c * c).to(torch.float32)
+
+
+class _TorchShim:
+    """What Segmentation._torch() returns in this test: torch, with 'cuda' devices mapped to the CPU."""
+
+    def __getattr__(self, name):
+        return getattr(torch, name)
+
+    @staticmethod
+    def device(*_):
+        return torch.device("cpu")
+
+
+def _install_doubles():
+    from digipathai_b200 import Segmentation, engine
+    Segmentation._torch = lambda: _TorchShim()
+    engine.stitch, engine.finalize = _stitch, _finalize
+    torch.cuda.device = lambda *_: contextlib.nullcontext()
+    torch.cuda.synchronize = lambda *_: None
+
+
+def _slide(seed):
+    from digipathai_b200.slide import ArraySlide
+    rng = np.random.default_rng(seed)
+    W, H = 640, 448
+    img = np.full((H, W, 3), 240, np.uint8)
+    yy, xx = np.mgrid[0:H, 0:W]
+    blob = ((yy - 230) / 170.0) ** 2 + ((xx - 300) / 260.0) ** 2 < 1
+    img[blob] = (170, 90, 160)
+    img = np.clip(img.astype(np.int16) + rng.integers(-8, 9, img.shape), 0, 255).astype(np.uint8)
+    return ArraySlide(img, 1)
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, tta_list, use_raw_mask, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        _install_doubles()
+        from digipathai_b200 import dist as dpd
+        from digipathai_b200.tissue import TileGrid
+        slide = _slide(0)
+        mask = TileGrid(slide, P, STRIDE, BATCH).raw_mask if use_raw_mask else None
+        grid, res, info = dpd.sharded_get_prediction(slide, {"m": _FakeModel()}, BATCH, tta_list, P, STRIDE,
+                                                     device=0, gather=True, tissue_mask=mask)
+        q.put((rank, info, len(grid.coords), res["mean"].numpy(), res["var"].numpy(), res["x_range"]))
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,tta_list,use_raw_mask", [(2, None, False), (2, ["FLIP_LEFT_RIGHT"], True),
+                                                         (3, ["FLIP_LEFT_RIGHT", "ROTATE_90"], False)])
+def test_sharded_get_prediction_equals_single_process(world, tta_list, use_raw_mask):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, tta_list, use_raw_mask, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = {}
+    for _ in range(world):
+        item = q.get(timeout=180)
+        got[item[0]] = item[1:]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+
+    # single-process result through the same doubles
+    from digipathai_b200 import Segmentation, engine
+    saved = (Segmentation._torch, engine.stitch, engine.finalize, torch.cuda.device, torch.cuda.synchronize)
+    try:
+        _install_doubles()
+        _, want = Segmentation.get_prediction(_slide(0), batch_size=BATCH, models={"m": _FakeModel()},
+                                              tta_list=tta_list, patch_size=P, stride_size=STRIDE)
+    finally:
+        Segmentation._torch, engine.stitch, engine.finalize, torch.cuda.device, torch.cuda.synchronize = saved
+
+    infos = [got[r][0] for r in range(world)]
+    n_tiles = got[0][1]
+    assert sum(b - a for a, b in (i["batches"] for i in infos)) * BATCH == n_tiles > 4 * BATCH * world
+    assert all(i["halo_bytes_sent"] > 0 for i in infos)          # 50 % overlap: neighbouring stripes intersect
+    mean, var, x_range = got[0][2], got[0][3], got[0][4]
+    assert x_range == (0, 640) and mean.shape == want["mean"].shape
+    assert want["mean"].max() > 0.3 and (not tta_list or want["var"].max() > 0)
+    assert np.array_equal(mean, want["mean"])
+    assert np.array_equal(var, want["var"])
+    # every rank's own (un-gathered) stripe agrees too
+    for r in range(1, world):
+        x0, x1 = got[r][4]
+        assert (x0, x1) == infos[r]["stripe"]
+        assert np.array_equal(got[r][2], want["mean"][x0:x1])
+        assert np.array_equal(got[r][3], want["var"][x0:x1])
+
+
+def test_local_part_refuses_a_grid_for_other_geometry():
+    from digipathai_b200 import Segmentation, engine
+    from digipathai_b200.tissue import TileGrid
+    saved = (Segmentation._torch, engine.stitch, engine.finalize, torch.cuda.device, torch.cuda.synchronize)
+    try:
+        _install_doubles()
+        slide = _slide(1)
+        grid = TileGrid(slide, P, STRIDE, BATCH)
+        with pytest.raises(ValueError):
+            Segmentation.get_prediction(slide, batch_size=BATCH * 2, models={"m": _FakeModel()}, patch_size=P,
+                                        stride_size=STRIDE, grid=grid)
+        with pytest.raises(ValueError):
+            Segmentation.get_prediction(slide, batch_size=BATCH, models={"m": _FakeModel()}, patch_size=P,
+                                        stride_size=STRIDE, grid=grid, tile_range=(1, 5))
+    finally:
+        Segmentation._torch, engine.stitch, engine.finalize, torch.cuda.device, torch.cuda.synchronize = saved
