@@ -129,3 +129,17 @@ def test_grid_raw_mask_round_trips_and_the_processed_mask_does_not():
     twice = TileGrid(s, 256, 128, 8, mask=g.mask)
     assert twice.mask.sum() > g.mask.sum()
     assert (g.stride_size, g.patch_size, g.batch_size) == (128, 256, 8)
+
+
+def test_exact_histograms_across_float32_chunks():
+    """_hist_u8 feeds OpenCV's float32 histogram at most 2**24 pixels at a time: a constant 4200 x 4200 plane
+    (17.6 M pixels in one bin, beyond float32's exact integers) must still count exactly."""
+    from digipathai_b200.tissue import _hist_u8
+    a = np.full((4200, 4200), 7, np.uint8)
+    a[0, :3] = (0, 255, 255)
+    h = _hist_u8(a)
+    assert h.dtype == np.int64 and h[7] == 4200 * 4200 - 3 and h[0] == 1 and h[255] == 2 and h.sum() == a.size
+    rng = np.random.default_rng(0)
+    u, v = rng.integers(0, 256, (2, 37, 53)).astype(np.uint8)
+    assert np.array_equal(_hist_u8(u, v), np.bincount((u.astype(np.int64) * 256 + v).ravel(), minlength=65536))
+    assert threshold_otsu(u) == threshold_otsu(u.astype(np.int64))       # uint8 fast path == generic integer path
