@@ -73,8 +73,8 @@ def halo_exchange(planes, stripes, rank: int, group=None):
     for w in dist.batch_isend_irecv(ops):
         w.wait()
     # ascending-rank summation over every intersected region; regions of different peers may overlap each
-    # other (stripes narrower than a patch), so rebuild each peer region from the ORIGINAL partials.
-    mine = [p.clone() for p in planes]
+    # other (stripes narrower than a patch), so the x axis is cut at every region boundary and each segment is
+    # rebuilt from the original partials (a segment is read before it is written and never read again).
     order = sorted([s for (s, _, _) in peers] + [rank])
     bounds = {s: (a, b) for (s, a, b) in peers}
     xs = sorted({my_lo, my_hi, *[v for ab in bounds.values() for v in ab]})
@@ -86,7 +86,7 @@ def halo_exchange(planes, stripes, rank: int, group=None):
             acc = None
             for s in contributors:
                 if s == rank:
-                    part = mine[k][x0 - my_lo:x1 - my_lo]
+                    part = p[x0 - my_lo:x1 - my_lo]
                 else:
                     a, _ = bounds[s]
                     part = recv[s][k][x0 - a:x1 - a]
