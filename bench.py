@@ -205,6 +205,12 @@ def main():
         return run_reference(args)
     if args.warmup < 3:
         args.warmup = 3
+    # The library reads a few DP_* environment variables (planner experiments, and DP_DBG_SKIP / DP_NAIVE_CONV which
+    # switch work off or swap kernels for bring-up).  A bench line taken with a work-skipping knob set is not a
+    # measurement: refuse.  Every other DP_* override in effect is written into the line's config.
+    if os.environ.get("DP_DBG_SKIP", "0") not in ("", "0"):
+        raise SystemExit("bench.py: DP_DBG_SKIP is set (it disables parts of the conv kernel); unset it")
+    env_overrides = {k: v for k, v in sorted(os.environ.items()) if k.startswith("DP_")}
 
     import torch
     import torch.distributed as dist
@@ -392,6 +398,7 @@ def main():
             "config": {"workload": f"configs[1]: {MODEL_DESC[args.model]} forward on synthetic 256x256x3 uint8 tiles, "
                                    "batch 32 per GPU, tiles cropped from an HBM-resident raster",
                        "l2": "flushed between timed steps (256 MiB memset, untimed)",
+                       "env_overrides": env_overrides,
                        "weights": "random-init (He-normal), BN stats (0,1)",
                        "graph": "off" if args.no_graph else f"one CUDA graph per step, {args.split or 1} sub-batch branch(es), PDL between conv kernels",
                        "executed_gflop_per_tile": 2 * exec_macs / BATCH / 1e9,
