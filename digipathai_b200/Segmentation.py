@@ -57,14 +57,22 @@ def get_prediction(wsi_path, mask_path=None, label_path=None, batch_size=64, mod
     halo exchange), ``tissue_mask`` supplies a precomputed RAW [x, y] mask instead of the Otsu/HSV heuristic (the
     morphology of utils.py:200-219 is still applied to it), ``grid`` a ready ``TileGrid`` of this slide (sharded
     runs build it once and index it with ``tile_range``).
-    ``mask_path`` / ``label_path`` / ``num_workers`` / ``mask_level`` are accepted for signature
-    compatibility; the live reference passes None for the first two and ignores the last (dataloader.py:240-241).
+    ``mask_path`` names a ``.tiff`` tissue mask read at the slide's top level instead of running the heuristic
+    (dataloader.py:256-263; any other extension leaves the reference's dataset without a mask -- AttributeError --
+    and does so here); ``label_path`` / ``num_workers`` / ``mask_level`` are accepted for signature compatibility:
+    the live reference passes None for the first and ignores the last (dataloader.py:240-241).
     """
     from . import engine
     torch = _torch()
     if not models:
         raise ValueError("get_prediction needs at least one model")
     slide = open_slide(wsi_path)
+    if grid is None and tissue_mask is None and mask_path is not None:
+        from .tissue import mask_from_slide
+        if not os.path.basename(mask_path).endswith('.tiff'):
+            raise AttributeError("mask_path must name a .tiff file: the reference's dataset is left without a "
+                                 "'_mask' attribute for any other extension (dataloader.py:256-263)")
+        tissue_mask = mask_from_slide(open_slide(mask_path), len(slide.level_dimensions) - 1)
     if grid is None:
         grid = TileGrid(slide, patch_size=patch_size, stride_size=stride_size, batch_size=batch_size,
                         roi_masking=True, mask=tissue_mask)

@@ -111,6 +111,20 @@ def tissue_mask(slide, level: int, rgb_min: int = 50) -> np.ndarray:
     return np.ascontiguousarray((tissue_s & ~bg & above).T)
 
 
+def mask_from_slide(mask_slide, level: int) -> np.ndarray:
+    """uint8 [x, y] raw mask in {0, 255} from a mask image opened like a slide (dataloader.py:256-263): the whole
+    ``level`` is read, reduced to PIL's 'L' luma, transposed, and every non-zero pixel set to 255."""
+    region = mask_slide.read_region((0, 0), level, mask_slide.level_dimensions[level])
+    if hasattr(region, "convert"):
+        g = np.asarray(region.convert("L"))
+    else:                                        # PIL's RGB -> L: ITU-R 601 luma in 16.16 fixed point, rounded
+        rgb = np.asarray(region).astype(np.uint32)
+        g = (rgb[..., 0] * 19595 + rgb[..., 1] * 38470 + rgb[..., 2] * 7471 + 0x8000) >> 16
+    m = np.ascontiguousarray(g.T).astype(np.uint8)
+    m[m > 0] = 255
+    return m
+
+
 def morpho_process(mask_u8: np.ndarray, level: int) -> np.ndarray:
     """close 20x20, open 5x5, dilate 60/35/10 by level; level > 4 raises like utils.py:200-219."""
     import cv2

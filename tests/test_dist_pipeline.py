@@ -166,3 +166,31 @@ def test_local_part_refuses_a_grid_for_other_geometry():
                                         stride_size=STRIDE, grid=grid, tile_range=(1, 5))
     finally:
         Segmentation._torch, engine.stitch, engine.finalize, torch.cuda.device, torch.cuda.synchronize = saved
+
+
+def test_mask_path_tiff_replaces_the_tissue_heuristic(tmp_path):
+    """get_prediction(mask_path=<.tiff>) (dataloader.py:256-263) through the same doubles: equals a run with the
+    mask handed over directly, differs from the heuristic run, and a non-.tiff name fails like the reference."""
+    from PIL import Image
+    from digipathai_b200 import Segmentation, engine
+    saved = (Segmentation._torch, engine.stitch, engine.finalize, torch.cuda.device, torch.cuda.synchronize)
+    try:
+        _install_doubles()
+        slide = _slide(0)                                           # 640 x 448, one level
+        m = np.zeros((448, 640, 3), np.uint8)                       # image layout [y, x, c]
+        m[100:300, 200:520] = (0, 0, 3)                             # luma of (0, 0, 3) rounds to 0 ...
+        m[150:250, 250:400] = (0, 0, 5)                             # ... of (0, 0, 5) to 1: only this box counts
+        path = str(tmp_path / "mask.tiff")
+        Image.fromarray(m).save(path)
+        kw = dict(batch_size=BATCH, models={"m": _FakeModel()}, patch_size=P, stride_size=STRIDE)
+        _, got = Segmentation.get_prediction(slide, mask_path=path, **kw)
+        raw = np.zeros((640, 448), np.uint8)
+        raw[250:400, 150:250] = 255
+        _, want = Segmentation.get_prediction(slide, tissue_mask=raw, **kw)
+        _, auto = Segmentation.get_prediction(slide, **kw)
+        assert got["mean"].max() > 0 and np.array_equal(got["mean"], want["mean"])
+        assert not np.array_equal(got["mean"], auto["mean"])
+        with pytest.raises(AttributeError):
+            Segmentation.get_prediction(slide, mask_path=str(tmp_path / "mask.png"), **kw)
+    finally:
+        Segmentation._torch, engine.stitch, engine.finalize, torch.cuda.device, torch.cuda.synchronize = saved

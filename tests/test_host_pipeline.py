@@ -143,3 +143,15 @@ def test_exact_histograms_across_float32_chunks():
     u, v = rng.integers(0, 256, (2, 37, 53)).astype(np.uint8)
     assert np.array_equal(_hist_u8(u, v), np.bincount((u.astype(np.int64) * 256 + v).ravel(), minlength=65536))
     assert threshold_otsu(u) == threshold_otsu(u.astype(np.int64))       # uint8 fast path == generic integer path
+
+
+def test_mask_from_slide_luma_is_pil_L():
+    from PIL import Image
+    from digipathai_b200.tissue import mask_from_slide
+    rng = np.random.default_rng(3)
+    img = rng.integers(0, 256, (40, 56, 3)).astype(np.uint8)
+    img[:20] = rng.integers(0, 6, (20, 56, 3))                       # many values whose luma rounds to 0 or 1
+    want = np.asarray(Image.fromarray(img).convert("L")).T
+    got = mask_from_slide(ArraySlide(img), 0)
+    assert got.shape == (56, 40) and set(np.unique(got)) <= {0, 255}
+    assert np.array_equal(got > 0, want > 0) and (want == 0).any()
