@@ -11,7 +11,9 @@ the whole B200 segmentation.  ``save_pyramidal`` writes the final file directly 
   * every level is a TIFF page of 256x256 JPEG-compressed tiles (Compression = 7, quality 90, one self-contained
     JPEG stream per tile, edge tiles padded by border replication), reduced levels flagged NewSubfileType = 1 -- the layout ImageMagick's
     ``ptif:`` coder produces and OpenSlide's generic-TIFF backend reads;
-  * tiles are encoded by Pillow's libjpeg on a thread pool (the encoder releases the GIL); classic TIFF offsets
+  * tiles are encoded by Pillow's libjpeg on a thread pool (the encoder releases the GIL); constant tiles -- most
+    of a result plane: background 0, saturated mask 255 -- are detected and share ONE JPEG stream per value
+    (TileOffsets may alias; libtiff / Pillow / OpenSlide address tiles purely by offset and byte count); classic TIFF offsets
     (the compressed planes of this path stay far below 4 GiB; larger files raise).
 
 ``save_plane`` keeps the lossless single-level export (float32 'F' / uint8 'L').
@@ -57,7 +59,8 @@ def pyramid_levels(plane, min_side: int = TILE):
         from . import engine
         cur = plane.to(torch.float32).contiguous()
         while True:
-            levels.append(_to_uint8(cur.cpu().numpy()))
+            # 8-bit conversion on the device (round-half-even like np.rint): a quarter of the bytes to download
+            levels.append(cur.round().clamp_(0, 255).to(torch.uint8).cpu().numpy())
             if max(cur.shape) <= min_side or min(cur.shape) < 2:
                 break
             with torch.cuda.device(cur.device):
@@ -74,12 +77,24 @@ def pyramid_levels(plane, min_side: int = TILE):
     return levels
 
 
-def _encode_tile(args):
+def _jpeg(tile: np.ndarray, quality: int) -> bytes:
     from PIL import Image
-    tile, quality = args
     buf = io.BytesIO()
     Image.fromarray(tile, mode="L").save(buf, format="JPEG", quality=quality)
     return buf.getvalue()
+
+
+def _encode_tile(args):
+    """One tile of level ``a`` -> JPEG bytes, or the tile's value (int) when it is constant: result planes are mostly
+    flat (background 0, saturated mask 255), and the writer stores one shared JPEG stream per constant value."""
+    a, j, i, tile, quality = args
+    t = a[j * tile:(j + 1) * tile, i * tile:(i + 1) * tile]
+    lo = t.min()
+    if lo == t.max():
+        return int(lo)
+    if t.shape != (tile, tile):       # edge tile: replicate the border (zero padding would ring into the image)
+        t = np.pad(t, ((0, tile - t.shape[0]), (0, tile - t.shape[1])), mode="edge")
+    return _jpeg(np.ascontiguousarray(t), quality)
 
 
 def save_pyramidal(path: str, plane, quality: int = 90, tile: int = TILE, threads: int = 8) -> int:
@@ -88,26 +103,31 @@ def save_pyramidal(path: str, plane, quality: int = 90, tile: int = TILE, thread
     levels = pyramid_levels(plane, tile)
     out = bytearray(b"II*\0\0\0\0\0")            # little-endian classic TIFF, first-IFD offset patched below
     ifd_offset_pos = 4
+    const_at = {}                                # value -> (offset, byte count) of the shared constant-tile stream
     with ThreadPoolExecutor(max_workers=threads) as pool:
         for li, a in enumerate(levels):
             rows, cols = a.shape
             ty, tx = -(-rows // tile), -(-cols // tile)
-            jobs = []
-            for j in range(ty):
-                for i in range(tx):
-                    t = a[j * tile:(j + 1) * tile, i * tile:(i + 1) * tile]
-                    if t.shape != (tile, tile):   # edge tile: replicate the border (zero padding would ring into the image)
-                        t = np.pad(t, ((0, tile - t.shape[0]), (0, tile - t.shape[1])), mode="edge")
-                    jobs.append((np.ascontiguousarray(t), quality))
-            blobs = list(pool.map(_encode_tile, jobs, chunksize=16))
+            jobs = ((a, j, i, tile, quality) for j in range(ty) for i in range(tx))
             offsets, counts = [], []
-            for b in blobs:
+            for b in pool.map(_encode_tile, jobs, chunksize=16):
+                if isinstance(b, int):            # constant tile: every such tile points at one stream per value
+                    if b not in const_at:
+                        blob = _jpeg(np.full((tile, tile), b, np.uint8), quality)
+                        if len(out) & 1:
+                            out.append(0)
+                        const_at[b] = (len(out), len(blob))
+                        out.extend(blob)
+                    off, cnt = const_at[b]
+                    offsets.append(off)
+                    counts.append(cnt)
+                    continue
                 if len(out) & 1:
                     out.append(0)
                 offsets.append(len(out))
                 counts.append(len(b))
                 out.extend(b)
-            n = len(blobs)
+            n = len(offsets)
 
             def arr(vals):
                 """Offset of an out-of-line LONG array (or the value itself when it fits the entry)."""

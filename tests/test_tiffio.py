@@ -76,3 +76,33 @@ def test_pyramidal_tiff_opens_as_a_multi_level_slide(tmp_path):
     assert s.level_count == 3 and s.level_dimensions[0] == (900, 600) and s.level_dimensions[2] == (225, 150)
     region = s.read_region((0, 0), 0, (64, 64))
     assert region.shape == (64, 64, 3) and np.abs(region[..., 0].astype(np.float32) - a[:64, :64]).mean() < 2.0
+
+
+def test_constant_tiles_share_one_stream_per_value(tmp_path):
+    """A mask-like plane (flat 0 / flat 255 with one ragged blob edge): every flat tile points at one shared JPEG
+    stream per value, the file stays small, and the image reads back exactly on the flat tiles."""
+    from PIL import Image
+    m = np.zeros((2100, 2600), np.uint8)                      # 9 x 11 tiles on level 0, ragged right / bottom edge
+    m[300:1700, 500:2600] = 255
+    m[1000, 1000] = 0                                          # one non-flat tile inside the blob
+    path = str(tmp_path / "flat.tiff")
+    assert tiffio.save_pyramidal(path, m) == 5
+    ifds, raw = _ifds(path)
+    d0 = ifds[0]
+    n = d0[324][1]
+    offs = struct.unpack(f"<{n}I", raw[d0[324][2]: d0[324][2] + 4 * n])
+    cnts = struct.unpack(f"<{n}I", raw[d0[325][2]: d0[325][2] + 4 * n])
+    assert n == 99 and len(set(offs)) < 45                    # 99 tiles, the flat ones aliased to two streams
+    assert all(raw[o:o + 2] == b"\xff\xd8" and raw[o + c - 2:o + c] == b"\xff\xd9" for o, c in zip(offs, cnts))
+    flat = [(j, i) for j in range(9) for i in range(11)
+            if m[j * 256:(j + 1) * 256, i * 256:(i + 1) * 256].min() == m[j * 256:(j + 1) * 256, i * 256:(i + 1) * 256].max()]
+    assert len({offs[j * 11 + i] for j, i in flat}) == 2
+    im = Image.open(path)
+    back = np.asarray(im)
+    for j, i in flat:
+        assert np.array_equal(back[j * 256:(j + 1) * 256, i * 256:(i + 1) * 256],
+                              m[j * 256:(j + 1) * 256, i * 256:(i + 1) * 256])
+    assert ((back > 127) == (m > 127)).mean() > 0.9999
+    im.seek(4)
+    assert np.asarray(im).shape == (131, 162)
+    assert len(raw) < 200_000
