@@ -50,7 +50,8 @@ class ArraySlide:
 
 
 def open_slide(path_or_obj, n_levels: int | None = None):
-    """Path (``.npy`` raster, any PIL-readable image, or a WSI if openslide is installed) or slide-like object."""
+    """Path (``.npy`` raster, any PIL-readable image, a WSI if openslide is installed, or -- with
+    ``DIGIPATH_DEVICE_INGEST=1`` -- a JPEG-tiled TIFF / SVS kept compressed for GPU decode) or slide-like object."""
     if hasattr(path_or_obj, "read_region") and hasattr(path_or_obj, "level_dimensions"):
         return path_or_obj
     if isinstance(path_or_obj, np.ndarray):
@@ -68,6 +69,18 @@ def open_slide(path_or_obj, n_levels: int | None = None):
         try:
             return openslide.OpenSlide(path)
         except Exception:  # noqa: BLE001 -- fall through to PIL for plain images
+            pass
+    if n_levels is None and os.environ.get("DIGIPATH_DEVICE_INGEST", "0") not in ("", "0") \
+            and path.lower().endswith((".tif", ".tiff", ".svs")):
+        # JPEG-tiled TIFF / SVS: keep the tiles compressed and decode level 0 on the GPU (ingest.py).
+        # Opt-in until the nvJPEG path has been verified on hardware; a TiffSlide object can also be passed directly.
+        from .wsi_tiff import TiffSlide
+        try:
+            ts = TiffSlide(path)
+            if ts.device_decodable(0):
+                return ts
+            ts.close()
+        except ValueError:
             pass
     from PIL import Image
     Image.MAX_IMAGE_PIXELS = None
@@ -167,6 +180,10 @@ def upload_xy_raster(slide, x_lo: int, x_hi: int, device, rows_per_chunk: int = 
         if slide.raster_xy.device != torch.device(device):
             return slide.raster_xy[x_lo:x_hi].to(device)
         return slide.raster_xy[x_lo:x_hi]      # contiguous row slice of the resident raster: no copy
+    from .wsi_tiff import TiffSlide
+    if isinstance(slide, TiffSlide) and slide.device_decodable(0):
+        from .ingest import upload_tiff_raster      # compressed tiles -> nvJPEG -> scatter, no host pixels
+        return upload_tiff_raster(slide, x_lo, x_hi, device)
     W, H = slide.level_dimensions[0]
     out = torch.empty((x_hi - x_lo, H, 3), dtype=torch.uint8, device=device)
     for y0 in range(0, H, rows_per_chunk):

@@ -23,6 +23,21 @@ def test_library_exports_every_declared_symbol():
     assert set(syms) == set(_lib.EXPORTED_SYMBOLS), "ctypes binding and header out of sync"
 
 
+def test_ingest_library_exports_every_declared_symbol():
+    from digipathai_b200 import ingest
+    src = open(os.path.join(ROOT, "include", "digipath_ingest.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    syms = sorted(set(re.findall(r"\b(dp_[a-z0-9_]+)\s*\(", src)))
+    assert len(syms) == 6
+    for s in syms:
+        assert hasattr(ingest.lib, s), f"{s} declared in include/digipath_ingest.h but not exported"
+    assert set(syms) == set(ingest.EXPORTED_SYMBOLS)
+    assert ingest.lib.dp_ingest_abi_version() == 1
+    # argument checks that need no GPU
+    assert ingest.lib.dp_jpeg_decoder_create(0, None) != 0 and b"null" in ingest.lib.dp_ingest_last_error()
+    assert ingest.lib.dp_scatter_tiles_xy(None, 1, 8, 8, None, None, 0, 8, 8, None) != 0
+
+
 def test_abi_version_and_error_channel():
     from digipathai_b200 import _lib
     assert _lib.lib.dp_abi_version() == 1

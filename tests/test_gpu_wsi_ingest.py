@@ -1,0 +1,99 @@
+"""GPU side of the slide ingest: the scatter kernel bit-exact against numpy, and nvJPEG tile decode
+against Pillow's libjpeg decode of the same streams.
+
+Tolerance for the decode: two conforming JPEG decoders may differ by a level or two per sample (IDCT rounding) and by
+more where chroma is upsampled (libjpeg's "fancy" triangle filter vs a box filter) -- stated per case below.
+
+The nvJPEG cases are marked xfail(strict=False): they were written after round 1's GPU budget was spent and have not
+run on hardware yet, so the suite must not depend on them; an XPASS in the report is the signal to drop the marker.
+"""
+import io
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+_unverified = pytest.mark.xfail(strict=False, reason="nvJPEG ingest path not yet run on a GPU (written after the "
+                                                     "round's GPU budget was spent)")
+
+
+def test_scatter_tiles_xy_is_exact_with_clipping_and_stripes():
+    import torch
+    from digipathai_b200 import ingest
+    rng = np.random.default_rng(0)
+    W, H, tw, th = 300, 210, 96, 80                        # ragged: tiles hang over the right and bottom edges
+    tiles_x, tiles_y = -(-W // tw), -(-H // th)
+    n = tiles_x * tiles_y
+    tiles = rng.integers(0, 256, (n, th, tw, 3)).astype(np.uint8)
+    org = np.array([[(k % tiles_x) * tw, (k // tiles_x) * th] for k in range(n)], np.int32)
+    full = np.zeros((W, H, 3), np.uint8)
+    for k in range(n):
+        x0, y0 = org[k]
+        w, h = min(tw, W - x0), min(th, H - y0)
+        full[x0:x0 + w, y0:y0 + h] = tiles[k, :h, :w].transpose(1, 0, 2)
+    t_dev, o_dev = torch.from_numpy(tiles).cuda(), torch.from_numpy(org).cuda()
+    out = torch.zeros((W, H, 3), dtype=torch.uint8, device="cuda")
+    ingest.scatter_tiles_xy(t_dev, o_dev, out, 0)
+    assert np.array_equal(out.cpu().numpy(), full)
+    for x_lo, x_hi in ((0, 100), (100, 233), (233, 300)):  # the stripes of a sharded run: other columns are dropped
+        part = torch.zeros((x_hi - x_lo, H, 3), dtype=torch.uint8, device="cuda")
+        ingest.scatter_tiles_xy(t_dev, o_dev, part, x_lo)
+        assert np.array_equal(part.cpu().numpy(), full[x_lo:x_hi])
+
+
+def _rgb(h, w):
+    y, x = np.mgrid[0:h, 0:w]
+    return np.stack([127 + 120 * np.sin(x / 23.0), 127 + 120 * np.cos(y / 31.0), (x + y) * 0.3 % 256], -1).astype(np.uint8)
+
+
+@_unverified
+def test_nvjpeg_decode_matches_libjpeg_on_tile_streams():
+    import torch
+    from PIL import Image
+    from digipathai_b200 import ingest
+    img = _rgb(256, 256)
+    streams, want, tol = [], [], []
+    for kw, t in ((dict(quality=90, subsampling=0), (3, 0.6)), (dict(quality=75, subsampling=0), (3, 0.6)),
+                  (dict(quality=90, subsampling=2), (40, 2.0))):       # 4:2:0: chroma upsampling filters differ
+        b = io.BytesIO()
+        Image.fromarray(img).save(b, format="JPEG", **kw)
+        streams.append(b.getvalue())
+        want.append(np.asarray(Image.open(io.BytesIO(b.getvalue())).convert("RGB")))
+        tol.append(t)
+    g = io.BytesIO()
+    Image.fromarray(img[..., 0], mode="L").save(g, format="JPEG", quality=90)
+    streams.append(g.getvalue())
+    want.append(np.repeat(np.asarray(Image.open(io.BytesIO(g.getvalue())))[..., None], 3, axis=2))
+    tol.append((3, 0.6))
+    dec = ingest.JpegTileDecoder(0)
+    got = dec.decode(streams, 256, 256).cpu().numpy()
+    dec.close()
+    for k in range(len(streams)):
+        d = np.abs(got[k].astype(int) - want[k].astype(int))
+        assert d.max() <= tol[k][0] and d.mean() <= tol[k][1], (k, d.max(), d.mean())
+
+
+@_unverified
+def test_tiff_slide_raster_on_device_matches_host_decode(tmp_path):
+    import torch
+    from PIL import Image
+    from digipathai_b200 import tiffio
+    from digipathai_b200.slide import upload_xy_raster
+    from digipathai_b200.wsi_tiff import TiffSlide
+    # (a) Pillow / libtiff: stripped RGB JPEG with JPEGTables; (b) this repo's own tiled grey result plane
+    a_path, b_path = str(tmp_path / "a.tiff"), str(tmp_path / "b.tiff")
+    Image.fromarray(_rgb(300, 500)).save(a_path, compression="jpeg", quality=90)
+    tiffio.save_pyramidal(b_path, _rgb(700, 900)[..., 0])
+    for path in (a_path, b_path):
+        s = TiffSlide(path)
+        W, H = s.dimensions
+        want = s.read_region((0, 0), 0, (W, H)).transpose(1, 0, 2)           # host libjpeg decode, [x, y, c]
+        got = upload_xy_raster(s, 0, W, torch.device("cuda", 0)).cpu().numpy()
+        assert got.shape == (W, H, 3)
+        d = np.abs(got.astype(int) - want.astype(int))
+        assert d.max() <= 3 and d.mean() <= 0.6, (path, d.max(), d.mean())
+        lo, hi = W // 3, W // 3 + 130                                        # a stripe, as a sharded rank asks for
+        part = upload_xy_raster(s, lo, hi, torch.device("cuda", 0)).cpu().numpy()
+        assert np.array_equal(part, got[lo:hi])
+        s.close()
