@@ -4,18 +4,22 @@ against Pillow's libjpeg decode of the same streams.
 Tolerance for the decode: two conforming JPEG decoders may differ by a level or two per sample (IDCT rounding) and by
 more where chroma is upsampled (libjpeg's "fancy" triangle filter vs a box filter) -- stated per case below.
 
-The nvJPEG cases are marked xfail(strict=False): they were written after round 1's GPU budget was spent and have not
-run on hardware yet, so the suite must not depend on them; an XPASS in the report is the signal to drop the marker.
+The nvJPEG cases are opt-in (DP_TEST_UNVERIFIED=1): they were written after round 1's GPU budget was spent and have
+not run on hardware yet; a misuse of a closed library can crash the interpreter rather than fail a test, so the
+regular suite must not depend on them.  Run them with
+
+    timeout 600 env DP_TEST_UNVERIFIED=1 python -m pytest tests/test_gpu_wsi_ingest.py -m gpu -q
 """
 import io
+import os
 
 import numpy as np
 import pytest
 
 pytestmark = pytest.mark.gpu
 
-_unverified = pytest.mark.xfail(strict=False, reason="nvJPEG ingest path not yet run on a GPU (written after the "
-                                                     "round's GPU budget was spent)")
+_unverified = pytest.mark.skipif(os.environ.get("DP_TEST_UNVERIFIED") != "1",
+                                 reason="nvJPEG ingest path not yet run on a GPU: opt in with DP_TEST_UNVERIFIED=1")
 
 
 def test_scatter_tiles_xy_is_exact_with_clipping_and_stripes():

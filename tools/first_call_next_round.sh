@@ -14,6 +14,8 @@ timeout 60 tools/mma_probe_cta2 > "$OUT/mma_probe_cta2.txt" 2>&1; echo "cta2 pro
 # 3. the stacked-tap dense layer: parity first, then its effect on the step time
 timeout 600 env DP_TEST_UNVERIFIED=1 python -m pytest tests/test_gpu_stack_dense.py -m gpu -q > "$OUT/pytest_stack.log" 2>&1
 echo "stacked dense layer tests rc=$?" | tee -a "$OUT/summary.txt"
+timeout 600 env DP_TEST_UNVERIFIED=1 python -m pytest tests/test_gpu_wsi_ingest.py -m gpu -q > "$OUT/pytest_ingest.log" 2>&1
+echo "nvJPEG ingest tests rc=$?" | tee -a "$OUT/summary.txt"
 timeout 300 python bench.py --steps 50 --warmup 5 --dump-ops "$OUT/ops.csv" > "$OUT/bench.json" 2> "$OUT/bench.err"
 for mode in 1 2; do
   timeout 300 env DP_DL_STACK=$mode python bench.py --steps 50 --warmup 5 --no-cpu-baseline --dump-ops "$OUT/ops_stack$mode.csv" \
