@@ -47,6 +47,8 @@ def _finalize(mean, var, count, threshold, label=None):
     c[c == 0] = 1                                            # :175-177
     mean /= c.to(torch.float32)
     var /= (c * c).to(torch.float32)
+    if label is not None:                                    # :336-337
+        label[...] = (mean >= threshold).to(torch.uint8) * 255
 
 
 class _TorchShim:
@@ -194,3 +196,46 @@ def test_mask_path_tiff_replaces_the_tissue_heuristic(tmp_path):
             Segmentation.get_prediction(slide, mask_path=str(tmp_path / "mask.png"), **kw)
     finally:
         Segmentation._torch, engine.stitch, engine.finalize, torch.cuda.device, torch.cuda.synchronize = saved
+
+
+def test_get_segmentation_orchestration_status_files_and_return(tmp_path, monkeypatch):
+    """getSegmentation end to end through the doubles: status protocol (the strings and the final progress the
+    viewer polls, Segmentation.py:292-354), the three result files, and the returned {0, 255} map."""
+    from PIL import Image
+    from digipathai_b200 import Segmentation, engine
+    saved = (Segmentation._torch, engine.stitch, engine.finalize, torch.cuda.device, torch.cuda.synchronize)
+    try:
+        _install_doubles()
+        monkeypatch.setattr(Segmentation, "load_trained_models", lambda *a, **k: _FakeModel())
+        slide = _slide(0)
+
+        class Status(dict):
+            log = []
+
+            def __setitem__(self, k, v):
+                if k == "status":
+                    self.log.append(v)
+                super().__setitem__(k, v)
+
+        status = Status()
+        paths = {k: str(tmp_path / f"{k}.tiff") for k in ("probs", "mask", "unc")}
+        out = Segmentation.getSegmentation(slide, patch_size=P, stride_size=STRIDE, batch_size=BATCH, quick=True,
+                                           tta_list=["FLIP_LEFT_RIGHT"], crf=False, status=status,
+                                           probs_path=paths["probs"], mask_path=paths["mask"],
+                                           uncertainty_path=paths["unc"], weights={"conv1/conv": np.zeros(1)})
+        _, want = Segmentation.get_prediction(slide, batch_size=BATCH, models={"m": _FakeModel()},
+                                              tta_list=["FLIP_LEFT_RIGHT"], patch_size=P, stride_size=STRIDE)
+    finally:
+        Segmentation._torch, engine.stitch, engine.finalize, torch.cuda.device, torch.cuda.synchronize = saved
+    assert out.dtype == np.float32 and out.shape == (640, 448) and set(np.unique(out)) == {0.0, 255.0}
+    assert np.array_equal(out, np.where(want["mean"] >= np.float32(0.3), 255, 0))
+    assert Status.log == ["Found Trained Models, Skipping download", "Loading Trained weights", "Running segmentation",
+                          "Saving Prediction Mask...", "Saving Prediction Uncertanity..."]
+    assert status["progress"] == 0
+    for k, path in paths.items():
+        im = Image.open(path)
+        assert im.size == (640, 448) and im.n_frames == 3          # [W, H] planes are written transposed: image layout
+    mask = np.asarray(Image.open(paths["mask"]))
+    assert ((mask > 127) == (out.T > 127)).mean() > 0.999
+    probs = np.asarray(Image.open(paths["probs"])).astype(np.float32) / 255.0
+    assert np.abs(probs - want["mean"].T).mean() < 0.01
