@@ -97,9 +97,12 @@ def _encode_tile(args):
     return _jpeg(np.ascontiguousarray(t), quality)
 
 
-def save_pyramidal(path: str, plane, quality: int = 90, tile: int = TILE, threads: int = 8) -> int:
+def save_pyramidal(path: str, plane, quality: int = 90, tile: int = TILE, threads: int | None = None) -> int:
     """Writes ``plane`` ([rows, cols], uint8 or float in [0, 255]) as a tiled pyramidal JPEG TIFF; returns the
-    number of levels."""
+    number of levels.  ``threads`` = JPEG encoder threads (default: every host core, at most 32)."""
+    if threads is None:
+        import os
+        threads = max(1, min(32, os.cpu_count() or 1))
     levels = pyramid_levels(plane, tile)
     out = bytearray(b"II*\0\0\0\0\0")            # little-endian classic TIFF, first-IFD offset patched below
     ifd_offset_pos = 4
