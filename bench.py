@@ -223,7 +223,9 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        import datetime
+        # a collective that cannot complete (mismatched sizes, a dead rank) aborts after 5 min instead of hanging
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(minutes=5))
 
     def barrier():
         if world > 1:
