@@ -385,7 +385,7 @@ def main():
                         f"{t:.4f},{tf:.1f}\n")
 
     cpu_baseline = None
-    if rank == 0 and not args.no_cpu_baseline:
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:      # reported at N = 1 only (the host cores are shared)
         threads = os.cpu_count() or 1
         v, dt = oracle_tiles_per_sec(32, threads, model=args.model, budget_s=12.0)
         cpu_baseline = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
