@@ -7,7 +7,7 @@ TAG=${1:-r2s1}
 OUT=gpurun_out/$TAG
 mkdir -p "$OUT"
 # 1. the regular GPU suite (includes the late-written CRF helper / local_part / world-of-one / ingest tests)
-timeout 900 python -m pytest tests -m gpu -q -x > "$OUT/pytest_gpu.log" 2>&1; echo "pytest -m gpu rc=$?" | tee -a "$OUT/summary.txt"
+timeout 900 python -m pytest tests -m gpu -q > "$OUT/pytest_gpu.log" 2>&1; echo "pytest -m gpu rc=$?" | tee -a "$OUT/summary.txt"
 # 2. cta_group::2 MMA probe
 ( cd tools && nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o mma_probe_cta2 mma_probe_cta2.cu ) > "$OUT/probe_build.log" 2>&1
 timeout 60 tools/mma_probe_cta2 > "$OUT/mma_probe_cta2.txt" 2>&1; echo "cta2 probe rc=$?" | tee -a "$OUT/summary.txt"
