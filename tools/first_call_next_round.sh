@@ -22,6 +22,10 @@ for mode in 1 2; do
       > "$OUT/bench_stack$mode.json" 2>> "$OUT/bench.err"
   echo "bench DP_DL_STACK=$mode rc=$?" | tee -a "$OUT/summary.txt"
 done
+# 3b. role timelines of one 16x16 and one 8x8 dense layer (what bounds conv4 / conv5: L2 -> SM streaming or the
+#     ph1 -> mid loop?), default kernel and stacked variant
+timeout 120 python tests/trace_ops.py 36 58 > "$OUT/trace_conv4_conv5.txt" 2>&1
+timeout 120 env DP_DL_STACK=1 python tests/trace_ops.py 36 58 > "$OUT/trace_conv4_conv5_stack.txt" 2>&1
 # 4. slide-level run (tissue mask, grid, forward, stitch) -- the sharded variant needs `gpurun --gpus 2`:
 #    torchrun --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --workload slide --slide 16384 --steps 2
 timeout 300 python bench.py --workload slide --slide 16384 --steps 2 > "$OUT/slide_16k_n1.json" 2> "$OUT/slide.err"
