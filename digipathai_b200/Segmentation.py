@@ -165,25 +165,30 @@ def _default_weight_path(mode, model):
     return os.path.join(home, '.DigiPathAI', folder, f'{prefix}_{suffix}.npz')
 
 
-def load_trained_models(model, path, patch_size=256, *, device=0, max_batch=32):
+def load_trained_models(model, path, patch_size=256, *, device=0, max_batch=32, precision="fp16"):
     """Counterpart of utils.py:427-448: build the graph and load its weights; returns a ``TileModel``.
 
     ``path`` is a flat ``.npz`` of Keras-named arrays (the reference's ``.h5`` files converted off-box with
     tools/h5_to_npz.py -- h5py/TensorFlow are not available here) or an in-memory weight dict.
+    ``precision``: 'fp16' (tensor cores, fp32 accumulation) or 'fp32' (the reference's arithmetic: matches its fp32
+    ``Model.predict`` within 1e-3 on any weight set; several times slower) -- see program.py.
     """
     from .engine import TileModel
     from .models.densenet import densenet121_unet_program
     from .models.inception import inception_resnet_v2_unet_program
     if model.__contains__('dense'):
         weights = path if isinstance(path, dict) else _load_npz(path)
-        return TileModel(densenet121_unet_program(weights, patch_size), device=device, max_batch=max_batch)
+        return TileModel(densenet121_unet_program(weights, patch_size, precision=precision), device=device,
+                         max_batch=max_batch)
     if model.__contains__('inception'):
         weights = path if isinstance(path, dict) else _load_npz(path)
-        return TileModel(inception_resnet_v2_unet_program(weights, patch_size), device=device, max_batch=max_batch)
+        return TileModel(inception_resnet_v2_unet_program(weights, patch_size, precision=precision), device=device,
+                         max_batch=max_batch)
     if model.__contains__('deeplabv3'):
         from .models.deeplab import deeplabv3plus_xception_program
         weights = path if isinstance(path, dict) else _load_npz(path)
-        return TileModel(deeplabv3plus_xception_program(weights, patch_size), device=device, max_batch=max_batch)
+        return TileModel(deeplabv3plus_xception_program(weights, patch_size, precision=precision), device=device,
+                         max_batch=max_batch)
     raise ValueError("Unknown model provided, allowed models ['dense', 'inception', 'deeplabv3']")
 
 
@@ -234,7 +239,8 @@ def getSegmentation(img_path,
                     weights=None,
                     device=0,
                     return_device=False,
-                    pyramidal=True):
+                    pyramidal=True,
+                    precision="fp16"):
     """Whole-slide segmentation (reference: Segmentation.py:192-356, README.md:79-87).
 
     Returns the thresholded map -- float32 ``[W, H]`` of {0, 255}, NOT transposed -- exactly what the reference
@@ -247,7 +253,8 @@ def getSegmentation(img_path,
     pyramidal JPEG-q90 TIFFs (tiffio.save_pyramidal; probabilities and uncertainty scaled to 8 bit);
     ``pyramidal=False`` writes lossless single-level TIFFs instead (float32 probabilities / uncertainty).
     Extensions (keyword only): ``weights`` = dict / ``.npz`` path per model name or a single dict for
-    ``model``; ``device``; ``return_device`` returns the uint8 label plane as a CUDA tensor instead.
+    ``model``; ``device``; ``return_device`` returns the uint8 label plane as a CUDA tensor instead;
+    ``precision='fp32'`` runs the networks in the reference's fp32 arithmetic (see ``load_trained_models``).
     """
     from . import engine
     torch = _torch()
@@ -289,7 +296,7 @@ def getSegmentation(img_path,
     models = {}
     for nm in names:
         models[nm] = load_trained_models(nm, weight_source(nm), patch_size=patch_size, device=device,
-                                         max_batch=batch_size)
+                                         max_batch=batch_size, precision=precision)
 
     threshold = 0.3
     if status is not None:

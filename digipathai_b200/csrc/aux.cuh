@@ -9,6 +9,34 @@
 
 namespace dp {
 
+// Activations are stored as fp16 (default) or fp32 (precision mode, precise.cuh); the helper kernels below are
+// templates over the storage type and move 8 channels per thread either way (one 16-byte or two 16-byte vectors).
+__device__ __forceinline__ void load8(const __half* p, float (&v)[8]) {
+  const uint4 raw = *reinterpret_cast<const uint4*>(p);
+  const __half2* hv = reinterpret_cast<const __half2*>(&raw);
+#pragma unroll
+  for (int t = 0; t < 4; ++t) {
+    const float2 f = __half22float2(hv[t]);
+    v[2 * t] = f.x;
+    v[2 * t + 1] = f.y;
+  }
+}
+__device__ __forceinline__ void load8(const float* p, float (&v)[8]) {
+  const float4 a = reinterpret_cast<const float4*>(p)[0], b = reinterpret_cast<const float4*>(p)[1];
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
+  v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+__device__ __forceinline__ void store8(__half* p, const float (&v)[8]) {
+  __align__(16) __half2 o[4];
+#pragma unroll
+  for (int t = 0; t < 4; ++t) o[t] = __floats2half2_rn(v[2 * t], v[2 * t + 1]);
+  *reinterpret_cast<uint4*>(p) = *reinterpret_cast<const uint4*>(o);
+}
+__device__ __forceinline__ void store8(float* p, const float (&v)[8]) {
+  reinterpret_cast<float4*>(p)[0] = make_float4(v[0], v[1], v[2], v[3]);
+  reinterpret_cast<float4*>(p)[1] = make_float4(v[4], v[5], v[6], v[7]);
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // Tile gather + (v-128)/128 + forward TTA + ZeroPadding2D(3) + im2col for the 7x7/2 stem conv
 // (dataloader.py:357-388 crop/transposed layout/normalise; utils.py:487-501 TTA; densenet.py:116-117 stem).
@@ -58,7 +86,8 @@ __global__ void stem_im2col_kernel(const PassDesc* __restrict__ pass, int img0, 
 // the tensor-core kernel, the 4 column taps are unrolled into the channel axis here, leaving 4 row taps:
 //   out[b][r][q][dq*16 + (a*2+b2)*3 + c] = net_in[2r+a][2(q+dq-2)+b2][c]     (0 outside the tile / ch >= 12)
 // with net_in = forward-TTA'd, (v-128)/128-normalised tile cropped from the slide raster.  fp16 [B][P/2][P/2][64].
-__global__ void stem_s2d_kernel(const PassDesc* __restrict__ pass, int img0, int B, int P, __half* __restrict__ out) {
+template <typename T>
+__global__ void stem_s2d_kernel(const PassDesc* __restrict__ pass, int img0, int B, int P, T* __restrict__ out) {
   pdl_wait();               // launched with programmatic stream serialization: inputs complete from here
   pdl_launch_dependents();
   const uint8_t* __restrict__ slide = pass->slide;
@@ -74,9 +103,9 @@ __global__ void stem_s2d_kernel(const PassDesc* __restrict__ pass, int img0, int
     const int r = r0 % OH;
     const int b = r0 / OH;
     const long long x0 = coords[2 * b], y0 = coords[2 * b + 1];
-    __align__(16) __half vals[16];
+    float lo8[8], hi8[8];
 #pragma unroll
-    for (int t = 0; t < 16; ++t) vals[t] = __float2half_rn(0.f);
+    for (int t = 0; t < 8; ++t) lo8[t] = hi8[t] = 0.f;
     const int jq = q + dq - 2;
     if (jq >= 0 && jq < OH) {
 #pragma unroll
@@ -87,13 +116,15 @@ __global__ void stem_s2d_kernel(const PassDesc* __restrict__ pass, int img0, int
           d4_src(tta_code, 2 * r + a, 2 * jq + b2, P, ti, tj);
           const uint8_t* px = slide + ((x0 + ti) * slide_h + (y0 + tj)) * 3;
 #pragma unroll
-          for (int c = 0; c < 3; ++c)
-            vals[(a * 2 + b2) * 3 + c] = __float2half_rn((static_cast<float>(px[c]) - 128.f) * (1.f / 128.f));
+          for (int c = 0; c < 3; ++c) {
+            const int k = (a * 2 + b2) * 3 + c;                                          // compile-time after unrolling
+            const float v = (static_cast<float>(px[c]) - 128.f) * (1.f / 128.f);        // exact in fp16
+            if (k < 8) lo8[k] = v; else hi8[k - 8] = v;
+          }
         }
     }
-    uint4* dst = reinterpret_cast<uint4*>(out + static_cast<size_t>(idx) * 16);
-    dst[0] = reinterpret_cast<const uint4*>(vals)[0];
-    dst[1] = reinterpret_cast<const uint4*>(vals)[1];
+    store8(out + static_cast<size_t>(idx) * 16, lo8);
+    store8(out + static_cast<size_t>(idx) * 16 + 8, hi8);
   }
 }
 
@@ -103,8 +134,9 @@ __global__ void stem_s2d_kernel(const PassDesc* __restrict__ pass, int img0, int
 // mode 1: MaxPooling2D(3, strides=2, padding='same') (inception.py:178,182,211,231) on an even-sized map:
 //         TensorFlow pads 0 in front / 1 behind, window starts at 2*o, padded cells never win.
 // 8 channels per thread.
-__global__ void maxpool3s2_kernel(const __half* __restrict__ in, int in_ctot, int in_choff,
-                                  __half* __restrict__ out, int out_ctot, int out_choff, int n_img, int H, int W,
+template <typename T>
+__global__ void maxpool3s2_kernel(const T* __restrict__ in, int in_ctot, int in_choff,
+                                  T* __restrict__ out, int out_ctot, int out_choff, int n_img, int H, int W,
                                   int C, int mode) {
   pdl_wait();               // launched with programmatic stream serialization: inputs complete from here
   pdl_launch_dependents();
@@ -127,29 +159,21 @@ __global__ void maxpool3s2_kernel(const __half* __restrict__ in, int in_ctot, in
 #pragma unroll
           for (int t = 0; t < 8; ++t) m[t] = fmaxf(m[t], 0.f);  // explicit zero padding takes part in the max
         } else {
-          const uint4 raw = *reinterpret_cast<const uint4*>(
-              in + ((static_cast<long long>(n) * H + ih) * W + iw) * in_ctot + in_choff + cg * 8);
-          const __half2* hv = reinterpret_cast<const __half2*>(&raw);
+          float f[8];
+          load8(in + ((static_cast<long long>(n) * H + ih) * W + iw) * in_ctot + in_choff + cg * 8, f);
 #pragma unroll
-          for (int t = 0; t < 4; ++t) {
-            const float2 f = __half22float2(hv[t]);
-            m[2 * t] = fmaxf(m[2 * t], f.x);
-            m[2 * t + 1] = fmaxf(m[2 * t + 1], f.y);
-          }
+          for (int t = 0; t < 8; ++t) m[t] = fmaxf(m[t], f[t]);
         }
       }
-    __align__(16) __half2 o[4];
-#pragma unroll
-    for (int t = 0; t < 4; ++t) o[t] = __floats2half2_rn(m[2 * t], m[2 * t + 1]);
-    *reinterpret_cast<uint4*>(out + ((static_cast<long long>(n) * OH + oh) * OW + ow) * out_ctot + out_choff +
-                              cg * 8) = *reinterpret_cast<const uint4*>(o);
+    store8(out + ((static_cast<long long>(n) * OH + oh) * OW + ow) * out_ctot + out_choff + cg * 8, m);
   }
 }
 
 // ---------------------------------------------------------------------------------------------------------
 // AveragePooling2D(3, strides=1, padding='same') (inception.py:193): mean over the VALID cells of the window.
-__global__ void avgpool3s1_kernel(const __half* __restrict__ in, int in_ctot, int in_choff,
-                                  __half* __restrict__ out, int out_ctot, int out_choff, int n_img, int H, int W,
+template <typename T>
+__global__ void avgpool3s1_kernel(const T* __restrict__ in, int in_ctot, int in_choff,
+                                  T* __restrict__ out, int out_ctot, int out_choff, int n_img, int H, int W,
                                   int C) {
   pdl_wait();
   pdl_launch_dependents();
@@ -170,30 +194,24 @@ __global__ void avgpool3s1_kernel(const __half* __restrict__ in, int in_ctot, in
         const int ih = oh + ky, iw = ow + kx;
         if (ih < 0 || ih >= H || iw < 0 || iw >= W) continue;
         ++cnt;
-        const uint4 raw = *reinterpret_cast<const uint4*>(
-            in + ((static_cast<long long>(n) * H + ih) * W + iw) * in_ctot + in_choff + cg * 8);
-        const __half2* hv = reinterpret_cast<const __half2*>(&raw);
+        float f[8];
+        load8(in + ((static_cast<long long>(n) * H + ih) * W + iw) * in_ctot + in_choff + cg * 8, f);
 #pragma unroll
-        for (int t = 0; t < 4; ++t) {
-          const float2 f = __half22float2(hv[t]);
-          acc[2 * t] += f.x;
-          acc[2 * t + 1] += f.y;
-        }
+        for (int t = 0; t < 8; ++t) acc[t] += f[t];
       }
     const float inv = 1.f / static_cast<float>(cnt);
-    __align__(16) __half2 o[4];
 #pragma unroll
-    for (int t = 0; t < 4; ++t) o[t] = __floats2half2_rn(acc[2 * t] * inv, acc[2 * t + 1] * inv);
-    *reinterpret_cast<uint4*>(out + ((static_cast<long long>(n) * H + oh) * W + ow) * out_ctot + out_choff + cg * 8) =
-        *reinterpret_cast<const uint4*>(o);
+    for (int t = 0; t < 8; ++t) acc[t] *= inv;
+    store8(out + ((static_cast<long long>(n) * H + oh) * W + ow) * out_ctot + out_choff + cg * 8, acc);
   }
 }
 
 // ---------------------------------------------------------------------------------------------------------
 // y = scale*x + shift [, ReLU] [, AveragePooling2D(2,2)]   (transition_block densenet.py:101-107 with the
 // pool commuted in front of the 1x1 conv -- both are linear -- and the final `bn` densenet.py:134).
-__global__ void bn_act_pool_kernel(const __half* __restrict__ in, int in_ctot, int in_choff,
-                                   __half* __restrict__ out, int out_ctot, int out_choff, int n_img, int H, int W,
+template <typename T>
+__global__ void bn_act_pool_kernel(const T* __restrict__ in, int in_ctot, int in_choff,
+                                   T* __restrict__ out, int out_ctot, int out_choff, int n_img, int H, int W,
                                    int C, const float* __restrict__ scale, const float* __restrict__ shift,
                                    int relu, int pool) {
   pdl_wait();               // launched with programmatic stream serialization: inputs complete from here
@@ -213,24 +231,19 @@ __global__ void bn_act_pool_kernel(const __half* __restrict__ in, int in_ctot, i
     for (int dy = 0; dy < np; ++dy)
       for (int dx = 0; dx < np; ++dx) {
         const int ih = pool ? 2 * oh + dy : oh, iw = pool ? 2 * ow + dx : ow;
-        const uint4 raw = *reinterpret_cast<const uint4*>(
-            in + ((static_cast<long long>(n) * H + ih) * W + iw) * in_ctot + in_choff + cg * 8);
-        const __half2* hv = reinterpret_cast<const __half2*>(&raw);
+        float f[8];
+        load8(in + ((static_cast<long long>(n) * H + ih) * W + iw) * in_ctot + in_choff + cg * 8, f);
 #pragma unroll
-        for (int t = 0; t < 4; ++t) {
-          const float2 f = __half22float2(hv[t]);
-          float a = fmaf(f.x, sc[2 * t], sh[2 * t]), b = fmaf(f.y, sc[2 * t + 1], sh[2 * t + 1]);
-          if (relu) { a = fmaxf(a, 0.f); b = fmaxf(b, 0.f); }
-          acc[2 * t] += a;
-          acc[2 * t + 1] += b;
+        for (int t = 0; t < 8; ++t) {
+          float a = fmaf(f[t], sc[t], sh[t]);
+          if (relu) a = fmaxf(a, 0.f);
+          acc[t] += a;
         }
       }
     const float inv = pool ? 0.25f : 1.f;
-    __align__(16) __half2 o[4];
 #pragma unroll
-    for (int t = 0; t < 4; ++t) o[t] = __floats2half2_rn(acc[2 * t] * inv, acc[2 * t + 1] * inv);
-    *reinterpret_cast<uint4*>(out + ((static_cast<long long>(n) * OH + oh) * OW + ow) * out_ctot + out_choff +
-                              cg * 8) = *reinterpret_cast<const uint4*>(o);
+    for (int t = 0; t < 8; ++t) acc[t] *= inv;
+    store8(out + ((static_cast<long long>(n) * OH + oh) * OW + ow) * out_ctot + out_choff + cg * 8, acc);
   }
 }
 
@@ -244,9 +257,10 @@ __global__ void bn_act_pool_kernel(const __half* __restrict__ in, int in_ctot, i
 // fp32 FMA per tap.  A 4-pixels-per-thread register-window variant (half the loads) was NOT faster (128 registers,
 // 22 % occupancy, latency bound) and was dropped; so was an instruction-lean variant (fp32 weights, half2 ReLU,
 // template-resolved activations, 48 registers): also not faster -- the issue slots are not what it waits on after all.
-__global__ void dwconv3x3_kernel(const __half* __restrict__ in, int in_ctot, int in_choff, __half* __restrict__ out,
+template <typename T>
+__global__ void dwconv3x3_kernel(const T* __restrict__ in, int in_ctot, int in_choff, T* __restrict__ out,
                                  int out_ctot, int out_choff, int n_img, int H, int W, int C, int stride, int rate,
-                                 const __half* __restrict__ w, const float* __restrict__ shift, int pre_relu,
+                                 const T* __restrict__ w, const float* __restrict__ shift, int pre_relu,
                                  int post_relu) {
   pdl_wait();
   pdl_launch_dependents();
@@ -273,36 +287,28 @@ __global__ void dwconv3x3_kernel(const __half* __restrict__ in, int in_ctot, int
       for (int kx = 0; kx < 3; ++kx) {
         const int iw = ow * stride + (kx - 1) * rate;
         if (iw < 0 || iw >= W) continue;
-        const uint4 raw = *reinterpret_cast<const uint4*>(
-            in + ((static_cast<long long>(n) * H + ih) * W + iw) * in_ctot + in_choff + cg * 8);
-        const uint4 wraw = *reinterpret_cast<const uint4*>(w + (ky * 3 + kx) * C + cg * 8);
-        const __half2* hv = reinterpret_cast<const __half2*>(&raw);
-        const __half2* wv = reinterpret_cast<const __half2*>(&wraw);
+        float x[8], k[8];
+        load8(in + ((static_cast<long long>(n) * H + ih) * W + iw) * in_ctot + in_choff + cg * 8, x);
+        load8(w + (ky * 3 + kx) * C + cg * 8, k);
 #pragma unroll
-        for (int t = 0; t < 4; ++t) {
-          float2 x = __half22float2(hv[t]);
-          const float2 k = __half22float2(wv[t]);
-          if (pre_relu) { x.x = fmaxf(x.x, 0.f); x.y = fmaxf(x.y, 0.f); }
-          acc[2 * t] = fmaf(x.x, k.x, acc[2 * t]);
-          acc[2 * t + 1] = fmaf(x.y, k.y, acc[2 * t + 1]);
+        for (int t = 0; t < 8; ++t) {
+          if (pre_relu) x[t] = fmaxf(x[t], 0.f);
+          acc[t] = fmaf(x[t], k[t], acc[t]);
         }
       }
     }
-    __align__(16) __half2 o[4];
+    if (post_relu) {
 #pragma unroll
-    for (int t = 0; t < 4; ++t) {
-      float a = acc[2 * t], b = acc[2 * t + 1];
-      if (post_relu) { a = fmaxf(a, 0.f); b = fmaxf(b, 0.f); }
-      o[t] = __floats2half2_rn(a, b);
+      for (int t = 0; t < 8; ++t) acc[t] = fmaxf(acc[t], 0.f);
     }
-    *reinterpret_cast<uint4*>(out + ((static_cast<long long>(n) * OH + oh) * OW + ow) * out_ctot + out_choff + cg * 8) =
-        *reinterpret_cast<const uint4*>(o);
+    store8(out + ((static_cast<long long>(n) * OH + oh) * OW + ow) * out_ctot + out_choff + cg * 8, acc);
   }
 }
 
 // GlobalAveragePooling2D (deeplabv3.py:378): [n][H][W][C] -> [n][1][1][C], fp32 accumulation.
-__global__ void global_avgpool_kernel(const __half* __restrict__ in, int in_ctot, int in_choff,
-                                      __half* __restrict__ out, int out_ctot, int out_choff, int n_img, int HW, int C) {
+template <typename T>
+__global__ void global_avgpool_kernel(const T* __restrict__ in, int in_ctot, int in_choff,
+                                      T* __restrict__ out, int out_ctot, int out_choff, int n_img, int HW, int C) {
   pdl_wait();
   pdl_launch_dependents();
   const int CG = C / 8;
@@ -310,28 +316,23 @@ __global__ void global_avgpool_kernel(const __half* __restrict__ in, int in_ctot
   for (unsigned idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
     const int cg = idx % CG, n = idx / CG;
     float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-    const __half* src = in + static_cast<long long>(n) * HW * in_ctot + in_choff + cg * 8;
+    const T* src = in + static_cast<long long>(n) * HW * in_ctot + in_choff + cg * 8;
     for (int p = 0; p < HW; ++p) {
-      const uint4 raw = *reinterpret_cast<const uint4*>(src + static_cast<long long>(p) * in_ctot);
-      const __half2* hv = reinterpret_cast<const __half2*>(&raw);
+      float f[8];
+      load8(src + static_cast<long long>(p) * in_ctot, f);
 #pragma unroll
-      for (int t = 0; t < 4; ++t) {
-        const float2 f = __half22float2(hv[t]);
-        acc[2 * t] += f.x;
-        acc[2 * t + 1] += f.y;
-      }
+      for (int t = 0; t < 8; ++t) acc[t] += f[t];
     }
     const float inv = 1.f / static_cast<float>(HW);
-    __align__(16) __half2 o[4];
 #pragma unroll
-    for (int t = 0; t < 4; ++t) o[t] = __floats2half2_rn(acc[2 * t] * inv, acc[2 * t + 1] * inv);
-    *reinterpret_cast<uint4*>(out + static_cast<long long>(n) * out_ctot + out_choff + cg * 8) =
-        *reinterpret_cast<const uint4*>(o);
+    for (int t = 0; t < 8; ++t) acc[t] *= inv;
+    store8(out + static_cast<long long>(n) * out_ctot + out_choff + cg * 8, acc);
   }
 }
 
 // Bilinear align_corners resize of a 1x1 map == broadcast (deeplabv3.py:385-388): [n][1][1][C] -> [n][H][W][C range].
-__global__ void broadcast_kernel(const __half* __restrict__ in, int in_ctot, int in_choff, __half* __restrict__ out,
+template <typename T>
+__global__ void broadcast_kernel(const T* __restrict__ in, int in_ctot, int in_choff, T* __restrict__ out,
                                  int out_ctot, int out_choff, int n_img, int HW, int C) {
   pdl_wait();
   pdl_launch_dependents();
@@ -341,8 +342,9 @@ __global__ void broadcast_kernel(const __half* __restrict__ in, int in_ctot, int
     const int cg = idx % CG;
     const unsigned r = idx / CG;
     const int n = r / HW;
-    const uint4 v = *reinterpret_cast<const uint4*>(in + static_cast<long long>(n) * in_ctot + in_choff + cg * 8);
-    *reinterpret_cast<uint4*>(out + static_cast<long long>(r) * out_ctot + out_choff + cg * 8) = v;
+    float v[8];
+    load8(in + static_cast<long long>(n) * in_ctot + in_choff + cg * 8, v);
+    store8(out + static_cast<long long>(r) * out_ctot + out_choff + cg * 8, v);
   }
 }
 
@@ -357,8 +359,9 @@ __device__ __forceinline__ void bilinear_ac_coord(int o, int in_size, int out_si
   f = s - static_cast<float>(i0);
 }
 
-__global__ void resize_bilinear_kernel(const __half* __restrict__ in, int in_ctot, int in_choff,
-                                       __half* __restrict__ out, int out_ctot, int out_choff, int n_img, int H, int W,
+template <typename T>
+__global__ void resize_bilinear_kernel(const T* __restrict__ in, int in_ctot, int in_choff,
+                                       T* __restrict__ out, int out_ctot, int out_choff, int n_img, int H, int W,
                                        int OH, int OW, int C) {
   pdl_wait();
   pdl_launch_dependents();
@@ -374,31 +377,25 @@ __global__ void resize_bilinear_kernel(const __half* __restrict__ in, int in_cto
     float fy, fx;
     bilinear_ac_coord(oh, H, OH, y0, y1, fy);
     bilinear_ac_coord(ow, W, OW, x0, x1, fx);
-    const __half* base = in + static_cast<long long>(n) * H * W * in_ctot + in_choff + cg * 8;
-    const uint4 r00 = *reinterpret_cast<const uint4*>(base + (static_cast<long long>(y0) * W + x0) * in_ctot);
-    const uint4 r01 = *reinterpret_cast<const uint4*>(base + (static_cast<long long>(y0) * W + x1) * in_ctot);
-    const uint4 r10 = *reinterpret_cast<const uint4*>(base + (static_cast<long long>(y1) * W + x0) * in_ctot);
-    const uint4 r11 = *reinterpret_cast<const uint4*>(base + (static_cast<long long>(y1) * W + x1) * in_ctot);
-    const __half2* a = reinterpret_cast<const __half2*>(&r00);
-    const __half2* b = reinterpret_cast<const __half2*>(&r01);
-    const __half2* c = reinterpret_cast<const __half2*>(&r10);
-    const __half2* d = reinterpret_cast<const __half2*>(&r11);
-    __align__(16) __half2 o[4];
+    const T* base = in + static_cast<long long>(n) * H * W * in_ctot + in_choff + cg * 8;
+    float a[8], b[8], c[8], d[8], o[8];
+    load8(base + (static_cast<long long>(y0) * W + x0) * in_ctot, a);
+    load8(base + (static_cast<long long>(y0) * W + x1) * in_ctot, b);
+    load8(base + (static_cast<long long>(y1) * W + x0) * in_ctot, c);
+    load8(base + (static_cast<long long>(y1) * W + x1) * in_ctot, d);
 #pragma unroll
-    for (int t = 0; t < 4; ++t) {
-      const float2 va = __half22float2(a[t]), vb = __half22float2(b[t]), vc = __half22float2(c[t]), vd = __half22float2(d[t]);
-      const float tx = va.x + (vb.x - va.x) * fx, bx = vc.x + (vd.x - vc.x) * fx;
-      const float ty = va.y + (vb.y - va.y) * fx, by = vc.y + (vd.y - vc.y) * fx;
-      o[t] = __floats2half2_rn(tx + (bx - tx) * fy, ty + (by - ty) * fy);
+    for (int t = 0; t < 8; ++t) {
+      const float top = a[t] + (b[t] - a[t]) * fx, bot = c[t] + (d[t] - c[t]) * fx;
+      o[t] = top + (bot - top) * fy;
     }
-    *reinterpret_cast<uint4*>(out + ((static_cast<long long>(n) * OH + oh) * OW + ow) * out_ctot + out_choff + cg * 8) =
-        *reinterpret_cast<const uint4*>(o);
+    store8(out + ((static_cast<long long>(n) * OH + oh) * OW + ow) * out_ctot + out_choff + cg * 8, o);
   }
 }
 
 // Logits conv collapsed to the class-1-minus-class-0 difference (softmax over 2 classes == sigmoid of it):
 // one warp per pixel, lanes split the channels 8 at a time, warp-shuffle reduction, fp32 result.
-__global__ void head_dot_kernel(const __half* __restrict__ in, int in_ctot, int in_choff, int C, long long n_pix,
+template <typename T>
+__global__ void head_dot_kernel(const T* __restrict__ in, int in_ctot, int in_choff, int C, long long n_pix,
                                 const float* __restrict__ w, float bias, float* __restrict__ out, int out_stride_f) {
   pdl_wait();
   pdl_launch_dependents();
@@ -406,17 +403,13 @@ __global__ void head_dot_kernel(const __half* __restrict__ in, int in_ctot, int 
   const long long warp0 = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) >> 5;
   const long long n_warps = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
   for (long long pix = warp0; pix < n_pix; pix += n_warps) {
-    const __half* src = in + pix * in_ctot + in_choff;
+    const T* src = in + pix * in_ctot + in_choff;
     float acc = 0.f;
     for (int c0 = lane * 8; c0 < C; c0 += 256) {
-      const uint4 raw = *reinterpret_cast<const uint4*>(src + c0);
-      const __half2* hv = reinterpret_cast<const __half2*>(&raw);
+      float f[8];
+      load8(src + c0, f);
 #pragma unroll
-      for (int t = 0; t < 4; ++t) {
-        const float2 f = __half22float2(hv[t]);
-        acc = fmaf(f.x, w[c0 + 2 * t], acc);
-        acc = fmaf(f.y, w[c0 + 2 * t + 1], acc);
-      }
+      for (int t = 0; t < 8; ++t) acc = fmaf(f[t], w[c0 + t], acc);
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
@@ -457,7 +450,8 @@ __global__ void head_resize_kernel(const float* __restrict__ z, int z_stride_f, 
 
 // ---------------------------------------------------------------------------------------------------------
 // Head for the naive (debug) path: 1x1 conv C->2 + softmax channel 1 + inverse TTA (densenet.py:156).
-__global__ void head_naive_kernel(const __half* __restrict__ in, int in_ctot, int in_choff, int C, int n_img,
+template <typename T>
+__global__ void head_naive_kernel(const T* __restrict__ in, int in_ctot, int in_choff, int C, int n_img,
                                   int P, const float* __restrict__ w, float bias,
                                   const PassDesc* __restrict__ pass, int img0) {
   const int tta_code = pass->tta_out;
@@ -468,9 +462,9 @@ __global__ void head_naive_kernel(const __half* __restrict__ in, int in_ctot, in
     const int wq = idx % P;
     const int h = (idx / P) % P;
     const int n = idx / (static_cast<long long>(P) * P);
-    const __half* a = in + idx * in_ctot + in_choff;
+    const T* a = in + idx * in_ctot + in_choff;
     float z = 0.f;
-    for (int c = 0; c < C; ++c) z = fmaf(__half2float(a[c]), w[c], z);
+    for (int c = 0; c < C; ++c) z = fmaf(static_cast<float>(a[c]), w[c], z);
     z += bias;
     int di, dj;
     d4_src(tta_code, h, wq, P, di, dj);

@@ -20,6 +20,7 @@
 #include "conv_tc.cuh"
 #include "crf.cuh"
 #include "dense_layer.cuh"
+#include "precise.cuh"
 
 namespace {
 
@@ -91,7 +92,7 @@ int make_map(CUtensorMap* map, const void* base, int rank, const uint64_t* dims,
 // ---------------------------------------------------------------- container format (see weights.py)
 struct BlobHeader {
   char magic[4];
-  uint32_t version, n_bufs, n_ops, patch, reserved0;
+  uint32_t version, n_bufs, n_ops, patch, precision;   // precision 0: fp16 weights + activations, 1: fp32
   uint64_t data_off, total_bytes;
   uint64_t reserved1[4];
 };
@@ -145,12 +146,13 @@ struct Plan {
 
 struct dp_model {
   int device = 0, max_batch = 0, patch = 0, num_sms = 148;
+  int precision = 0, esize = 2;  // 0 = fp16 tensor-core path; 1 = fp32 storage + fp32 kernels (precise.cuh), esize 4
   std::vector<BlobBuf> bufs;
   std::vector<BlobOp> ops;
   uint8_t* data_dev = nullptr;
   size_t data_bytes = 0;
-  std::vector<__half*> buf_dev;
-  __half* scratch_head = nullptr;  // naive path: output of the head-fused conv
+  std::vector<__half*> buf_dev;    // activation buffers (raw storage: __half or float elements, see esize)
+  __half* scratch_head = nullptr;  // naive / fp32 paths: output of the head-fused conv
   uint64_t device_bytes = 0;
   int naive_conv = 0, desc_base_mode = 0, halo_pad8 = 0, profile = 0;
   int use_graph = 1, split = 1, use_pdl = 1, epi_direct = 1, use_overlap = 1, b_resident = 1, b_pair = 0;
@@ -177,6 +179,13 @@ const T* dptr(const dp_model* m, int64_t off) {
 }
 
 int round_up(int a, int b) { return (a + b - 1) / b * b; }
+
+// Start of image `img0` inside activation buffer `buf` (element size follows the model's precision).
+__half* buf_ptr(const dp_model* m, int buf, int img0) {
+  const BlobBuf& bb = m->bufs[buf];
+  return reinterpret_cast<__half*>(reinterpret_cast<char*>(m->buf_dev[buf]) +
+                                   (size_t)img0 * bb.H * bb.W * bb.C * m->esize);
+}
 
 // MODE_H kernel variants by unrolled issue sequence (ConvParams::fast_id); 0 = generic tap loop.
 typedef void (*ConvKernelH)(const CUtensorMap, const CUtensorMap, const dp::ConvParams);
@@ -276,10 +285,7 @@ int plan_conv(dp_model* m, const BlobOp& op, int img0, int B, Launch& L) {
   q.n_entries_total = n_entries_total; q.n_groups = up2 ? 4 : 1; q.up2 = up2;
   q.relu = op.relu; q.pro_mode = op.pro;
   memcpy(q.entries, table, sizeof table);
-  auto buf_at = [&](int buf) {
-    const BlobBuf& bb = m->bufs[buf];
-    return m->buf_dev[buf] + (size_t)img0 * bb.H * bb.W * bb.C;
-  };
+  auto buf_at = [&](int buf) { return buf_ptr(m, buf, img0); };
   q.in = buf_at(op.in_buf);
   q.w = dptr<__half>(m, op.w_off);
   q.epi_scale = dptr<float>(m, op.epi_scale_off);
@@ -287,11 +293,17 @@ int plan_conv(dp_model* m, const BlobOp& op, int img0, int B, Launch& L) {
   q.pro_scale = dptr<float>(m, op.pro_scale_off);
   q.pro_shift = dptr<float>(m, op.pro_shift_off);
   if (op.head) {
-    q.out = m->scratch_head + (size_t)img0 * m->patch * m->patch * op.cout; q.out_ctot = op.cout; q.out_choff = 0;
+    q.out = reinterpret_cast<__half*>(reinterpret_cast<char*>(m->scratch_head) +
+                                      (size_t)img0 * m->patch * m->patch * op.cout * m->esize);
+    q.out_ctot = op.cout; q.out_choff = 0;
   } else {
     q.out = buf_at(op.out_buf); q.out_ctot = m->bufs[op.out_buf].C; q.out_choff = op.out_choff;
   }
   L.head_C = op.cout;
+  if (m->precision) {   // fp32 mode executes the description above with conv_f32_kernel: no tensor-core plan
+    L.macs = (uint64_t)B * OH * OW * n_entries_total * op.cin * op.cout;
+    return 0;
+  }
 
   // ---- tensor-core plan
   p.n_img = B; p.H = H; p.W = W; p.Cin = op.cin;
@@ -582,10 +594,7 @@ int plan_dense_layer(dp_model* m, const BlobOp& op, int img0, int B, Launch& L) 
   const int mid_buf = op.rsv[0];
   if (mid_buf < 0 || mid_buf >= (int)m->bufs.size() || m->bufs[mid_buf].C != 128 || m->bufs[mid_buf].H != H)
     return fail("dense layer: bad bottleneck buffer");
-  auto buf_at = [&](int buf) {
-    const BlobBuf& bb = m->bufs[buf];
-    return m->buf_dev[buf] + (size_t)img0 * bb.H * bb.W * bb.C;
-  };
+  auto buf_at = [&](int buf) { return buf_ptr(m, buf, img0); };
   // ---- debug path: the same layer as two naive convs through the bottleneck buffer
   TapEntry t1[kMaxEntries], t3[kMaxEntries];
   int n1 = 0, n3 = 0;
@@ -609,6 +618,10 @@ int plan_dense_layer(dp_model* m, const BlobOp& op, int img0, int B, Launch& L) 
   b.Cout = 32; b.out_ctot = ib.C; b.out_choff = op.out_choff; b.n_entries_total = 9; b.n_groups = 1;
   memcpy(b.entries, t3, sizeof t3);
   b.in = buf_at(mid_buf); b.w = dptr<__half>(m, op.rsv64[0]); b.out = buf_at(op.in_buf);
+  if (m->precision) {   // fp32 mode: the two convs above through the bottleneck buffer
+    L.macs = (uint64_t)B * H * W * ((uint64_t)op.cin * 128 + 9ull * 128 * 32);
+    return 0;
+  }
 
   // ---- fused tensor-core plan
   DenseLayerParams& p = L.dl;
@@ -746,14 +759,129 @@ cudaError_t launch_pdl(void (*kernel)(KArgs...), int grid, int block, cudaStream
   return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 
-int run_op(dp_model* m, SubPlan* sp, int i, cudaStream_t st) {
+// fp32 precision mode: every op of the program on fp32 buffers (aux.cuh templates instantiated for float,
+// conv_f32_kernel for the convs; a fused dense layer runs as its two convs through the bottleneck buffer).
+int run_op_f32(dp_model* m, SubPlan* sp, int i, cudaStream_t st) {
   const BlobOp& op = m->ops[i];
   Launch& L = sp->launches[i];
   const int B = sp->n_img, img0 = sp->img0;
-  auto buf_at = [&](int buf) {
-    const BlobBuf& bb = m->bufs[buf];
-    return m->buf_dev[buf] + (size_t)img0 * bb.H * bb.W * bb.C;
+  auto fb = [&](int buf) { return reinterpret_cast<float*>(buf_ptr(m, buf, img0)); };
+  const BlobBuf& ib = m->bufs[op.in_buf];
+  const BlobBuf& ob = m->bufs[op.out_buf];
+  const bool pdl = m->use_pdl != 0;
+  auto conv = [&](const dp::NaiveConvParams& q) {
+    const long long M = (long long)q.n_img * q.OH * q.OW;
+    if (q.Cout <= 32) {
+      dim3 grid((unsigned)((M + dp::kPcBM - 1) / dp::kPcBM), (unsigned)((q.Cout + 31) / 32), (unsigned)q.n_groups);
+      dp::conv_f32_kernel<32><<<grid, dp::kPcThreads, 0, st>>>(q);
+    } else {
+      dim3 grid((unsigned)((M + dp::kPcBM - 1) / dp::kPcBM), (unsigned)((q.Cout + 63) / 64), (unsigned)q.n_groups);
+      dp::conv_f32_kernel<64><<<grid, dp::kPcThreads, 0, st>>>(q);
+    }
   };
+  cudaError_t le = cudaSuccess;
+  switch (op.type) {
+    case OP_STEM_S2D: {
+      if (ob.C != 64 || ob.H != m->patch / 2) return fail("stem s2d buffer must be [P/2][P/2][64]");
+      const long long total = (long long)B * ob.H * ob.W * 4;
+      le = launch_pdl(dp::stem_s2d_kernel<float>, grid_for(total, 256), 256, st, pdl, m->pass_dev, img0, B, m->patch,
+                      fb(op.out_buf));
+      break;
+    }
+    case OP_MAXPOOL: {
+      const long long total = (long long)B * (ib.H / 2) * (ib.W / 2) * (op.cin / 8);
+      le = launch_pdl(dp::maxpool3s2_kernel<float>, grid_for(total, 256), 256, st, pdl, fb(op.in_buf), ib.C, op.in_choff,
+                      fb(op.out_buf), ob.C, op.out_choff, B, ib.H, ib.W, op.cin, op.pool);
+      break;
+    }
+    case OP_DWCONV: {
+      const int stride = op.rsv[0] & 0xff, rate = (op.rsv[0] >> 8) & 0xff;
+      if ((stride != 1 && stride != 2) || rate < 1 || ib.H % stride || ob.H != ib.H / stride || op.cin % 8)
+        return fail("depthwise conv: bad geometry (stride %d rate %d map %d -> %d)", stride, rate, ib.H, ob.H);
+      const long long total = (long long)B * ob.H * ob.W * (op.cin / 8);
+      le = launch_pdl(dp::dwconv3x3_kernel<float>, grid_for(total, 256), 256, st, pdl, fb(op.in_buf), ib.C, op.in_choff,
+                      fb(op.out_buf), ob.C, op.out_choff, B, ib.H, ib.W, op.cin, stride, rate, dptr<float>(m, op.w_off),
+                      dptr<float>(m, op.epi_shift_off), op.pro, op.relu);
+      break;
+    }
+    case OP_GAP:
+    case OP_BCAST: {
+      const BlobBuf& small = (op.type == OP_GAP) ? ob : ib;
+      const BlobBuf& big = (op.type == OP_GAP) ? ib : ob;
+      if (small.H != 1 || small.W != 1) return fail("global pool / broadcast needs a 1x1 map on one side");
+      if (op.type == OP_GAP)
+        le = launch_pdl(dp::global_avgpool_kernel<float>, grid_for((long long)B * (op.cin / 8), 128), 128, st, pdl,
+                        fb(op.in_buf), ib.C, op.in_choff, fb(op.out_buf), ob.C, op.out_choff, B, big.H * big.W, op.cin);
+      else
+        le = launch_pdl(dp::broadcast_kernel<float>, grid_for((long long)B * big.H * big.W * (op.cin / 8), 256), 256, st,
+                        pdl, fb(op.in_buf), ib.C, op.in_choff, fb(op.out_buf), ob.C, op.out_choff, B, big.H * big.W, op.cin);
+      break;
+    }
+    case OP_RESIZE: {
+      const long long total = (long long)B * ob.H * ob.W * (op.cin / 8);
+      le = launch_pdl(dp::resize_bilinear_kernel<float>, grid_for(total, 256), 256, st, pdl, fb(op.in_buf), ib.C,
+                      op.in_choff, fb(op.out_buf), ob.C, op.out_choff, B, ib.H, ib.W, ob.H, ob.W, op.cin);
+      break;
+    }
+    case OP_HEAD_DOT: {
+      if (ob.C != 8 || ob.H != ib.H || op.cin % 8) return fail("head dot: output buffer must be [H][W][8]");
+      const long long n_pix = (long long)B * ib.H * ib.W;
+      le = launch_pdl(dp::head_dot_kernel<float>, grid_for(n_pix * 32, 256), 256, st, pdl, fb(op.in_buf), ib.C, op.in_choff,
+                      op.cin, n_pix, dptr<float>(m, op.head_w_off), op.head_b, fb(op.out_buf), 8);
+      break;
+    }
+    case OP_HEAD_RESIZE: {
+      if (ib.C != 8) return fail("head resize: input buffer must be [H][W][8]");
+      const long long total = (long long)B * m->patch * m->patch;
+      le = launch_pdl(dp::head_resize_kernel, grid_for(total, 256), 256, st, pdl, (const float*)fb(op.in_buf), 8, B, ib.H,
+                      ib.W, m->patch, m->pass_dev, img0);
+      break;
+    }
+    case OP_AVGPOOL3: {
+      const long long total = (long long)B * ib.H * ib.W * (op.cin / 8);
+      le = launch_pdl(dp::avgpool3s1_kernel<float>, grid_for(total, 256), 256, st, pdl, fb(op.in_buf), ib.C, op.in_choff,
+                      fb(op.out_buf), ob.C, op.out_choff, B, ib.H, ib.W, op.cin);
+      break;
+    }
+    case OP_BNPOOL: {
+      const int OH = op.pool ? ib.H / 2 : ib.H, OW = op.pool ? ib.W / 2 : ib.W;
+      const long long total = (long long)B * OH * OW * (op.cin / 8);
+      le = launch_pdl(dp::bn_act_pool_kernel<float>, grid_for(total, 256), 256, st, pdl, fb(op.in_buf), ib.C, op.in_choff,
+                      fb(op.out_buf), ob.C, op.out_choff, B, ib.H, ib.W, op.cin, dptr<float>(m, op.epi_scale_off),
+                      dptr<float>(m, op.epi_shift_off), op.relu, op.pool);
+      break;
+    }
+    case OP_CONV: {
+      conv(L.np);
+      LAUNCH_OK();
+      if (op.head) {
+        const long long tot = (long long)B * m->patch * m->patch;
+        dp::head_naive_kernel<float><<<grid_for(tot, 256), 256, 0, st>>>(
+            reinterpret_cast<const float*>(L.np.out), op.cout, 0, op.cout, B, m->patch, dptr<float>(m, op.head_w_off),
+            op.head_b, m->pass_dev, img0);
+      }
+      break;
+    }
+    case OP_DENSE_LAYER: {
+      conv(L.np);
+      LAUNCH_OK();
+      conv(L.np2);
+      break;
+    }
+    default:
+      return fail("op type %d has no fp32 kernel", op.type);
+  }
+  if (le != cudaSuccess) return fail("fp32 op launch failed: %s", cudaGetErrorString(le));
+  LAUNCH_OK();
+  return 0;
+}
+
+int run_op(dp_model* m, SubPlan* sp, int i, cudaStream_t st) {
+  if (m->precision) return run_op_f32(m, sp, i, st);
+  const BlobOp& op = m->ops[i];
+  Launch& L = sp->launches[i];
+  const int B = sp->n_img, img0 = sp->img0;
+  auto buf_at = [&](int buf) { return buf_ptr(m, buf, img0); };
   switch (op.type) {
     case OP_STEM_IM2COL: {
       const BlobBuf& ob = m->bufs[op.out_buf];
@@ -768,7 +896,7 @@ int run_op(dp_model* m, SubPlan* sp, int i, cudaStream_t st) {
       const BlobBuf& ob = m->bufs[op.out_buf];
       if (ob.C != 64 || ob.H != m->patch / 2) return fail("stem s2d buffer must be [P/2][P/2][64]");
       const long long total = (long long)B * ob.H * ob.W * 4;
-      cudaError_t le = launch_pdl(dp::stem_s2d_kernel, grid_for(total, 256), 256, st, m->use_pdl != 0, m->pass_dev, img0, B,
+      cudaError_t le = launch_pdl(dp::stem_s2d_kernel<__half>, grid_for(total, 256), 256, st, m->use_pdl != 0, m->pass_dev, img0, B,
                                   m->patch, buf_at(op.out_buf));
       if (le != cudaSuccess) return fail("stem launch failed: %s", cudaGetErrorString(le));
       LAUNCH_OK();
@@ -778,7 +906,7 @@ int run_op(dp_model* m, SubPlan* sp, int i, cudaStream_t st) {
       const BlobBuf& ib = m->bufs[op.in_buf];
       const BlobBuf& ob = m->bufs[op.out_buf];
       const long long total = (long long)B * (ib.H / 2) * (ib.W / 2) * (op.cin / 8);
-      cudaError_t le = launch_pdl(dp::maxpool3s2_kernel, grid_for(total, 256), 256, st, m->use_pdl != 0,
+      cudaError_t le = launch_pdl(dp::maxpool3s2_kernel<__half>, grid_for(total, 256), 256, st, m->use_pdl != 0,
                                   buf_at(op.in_buf), ib.C, op.in_choff, buf_at(op.out_buf), ob.C, op.out_choff, B, ib.H,
                                   ib.W, op.cin, op.pool);
       if (le != cudaSuccess) return fail("maxpool launch failed: %s", cudaGetErrorString(le));
@@ -792,7 +920,7 @@ int run_op(dp_model* m, SubPlan* sp, int i, cudaStream_t st) {
       if ((stride != 1 && stride != 2) || rate < 1 || ib.H % stride || ob.H != ib.H / stride || op.cin % 8)
         return fail("depthwise conv: bad geometry (stride %d rate %d map %d -> %d)", stride, rate, ib.H, ob.H);
       const long long total = (long long)B * ob.H * ob.W * (op.cin / 8);
-      cudaError_t le = launch_pdl(dp::dwconv3x3_kernel, grid_for(total, 256), 256, st, m->use_pdl != 0, buf_at(op.in_buf),
+      cudaError_t le = launch_pdl(dp::dwconv3x3_kernel<__half>, grid_for(total, 256), 256, st, m->use_pdl != 0, buf_at(op.in_buf),
                                   ib.C, op.in_choff, buf_at(op.out_buf), ob.C, op.out_choff, B, ib.H, ib.W, op.cin, stride,
                                   rate, dptr<__half>(m, op.w_off), dptr<float>(m, op.epi_shift_off), op.pro, op.relu);
       if (le != cudaSuccess) return fail("depthwise conv launch failed: %s", cudaGetErrorString(le));
@@ -808,10 +936,10 @@ int run_op(dp_model* m, SubPlan* sp, int i, cudaStream_t st) {
       if (small.H != 1 || small.W != 1) return fail("global pool / broadcast needs a 1x1 map on one side");
       cudaError_t le;
       if (op.type == OP_GAP)
-        le = launch_pdl(dp::global_avgpool_kernel, grid_for((long long)B * (op.cin / 8), 128), 128, st, m->use_pdl != 0,
+        le = launch_pdl(dp::global_avgpool_kernel<__half>, grid_for((long long)B * (op.cin / 8), 128), 128, st, m->use_pdl != 0,
                         buf_at(op.in_buf), ib.C, op.in_choff, buf_at(op.out_buf), ob.C, op.out_choff, B, big.H * big.W, op.cin);
       else
-        le = launch_pdl(dp::broadcast_kernel, grid_for((long long)B * big.H * big.W * (op.cin / 8), 256), 256, st,
+        le = launch_pdl(dp::broadcast_kernel<__half>, grid_for((long long)B * big.H * big.W * (op.cin / 8), 256), 256, st,
                         m->use_pdl != 0, buf_at(op.in_buf), ib.C, op.in_choff, buf_at(op.out_buf), ob.C, op.out_choff, B,
                         big.H * big.W, op.cin);
       if (le != cudaSuccess) return fail("pool/broadcast launch failed: %s", cudaGetErrorString(le));
@@ -822,7 +950,7 @@ int run_op(dp_model* m, SubPlan* sp, int i, cudaStream_t st) {
       const BlobBuf& ib = m->bufs[op.in_buf];
       const BlobBuf& ob = m->bufs[op.out_buf];
       const long long total = (long long)B * ob.H * ob.W * (op.cin / 8);
-      cudaError_t le = launch_pdl(dp::resize_bilinear_kernel, grid_for(total, 256), 256, st, m->use_pdl != 0,
+      cudaError_t le = launch_pdl(dp::resize_bilinear_kernel<__half>, grid_for(total, 256), 256, st, m->use_pdl != 0,
                                   buf_at(op.in_buf), ib.C, op.in_choff, buf_at(op.out_buf), ob.C, op.out_choff, B, ib.H, ib.W,
                                   ob.H, ob.W, op.cin);
       if (le != cudaSuccess) return fail("resize launch failed: %s", cudaGetErrorString(le));
@@ -834,7 +962,7 @@ int run_op(dp_model* m, SubPlan* sp, int i, cudaStream_t st) {
       const BlobBuf& ob = m->bufs[op.out_buf];
       if (ob.C != 8 || ob.H != ib.H || op.cin % 8) return fail("head dot: output buffer must be [H][W][8] (one fp32 per pixel)");
       const long long n_pix = (long long)B * ib.H * ib.W;
-      cudaError_t le = launch_pdl(dp::head_dot_kernel, grid_for(n_pix * 32, 256), 256, st, m->use_pdl != 0, buf_at(op.in_buf),
+      cudaError_t le = launch_pdl(dp::head_dot_kernel<__half>, grid_for(n_pix * 32, 256), 256, st, m->use_pdl != 0, buf_at(op.in_buf),
                                   ib.C, op.in_choff, op.cin, n_pix, dptr<float>(m, op.head_w_off), op.head_b,
                                   reinterpret_cast<float*>(buf_at(op.out_buf)), 4);
       if (le != cudaSuccess) return fail("head dot launch failed: %s", cudaGetErrorString(le));
@@ -856,7 +984,7 @@ int run_op(dp_model* m, SubPlan* sp, int i, cudaStream_t st) {
       const BlobBuf& ib = m->bufs[op.in_buf];
       const BlobBuf& ob = m->bufs[op.out_buf];
       const long long total = (long long)B * ib.H * ib.W * (op.cin / 8);
-      cudaError_t le = launch_pdl(dp::avgpool3s1_kernel, grid_for(total, 256), 256, st, m->use_pdl != 0,
+      cudaError_t le = launch_pdl(dp::avgpool3s1_kernel<__half>, grid_for(total, 256), 256, st, m->use_pdl != 0,
                                   buf_at(op.in_buf), ib.C, op.in_choff, buf_at(op.out_buf), ob.C, op.out_choff, B, ib.H,
                                   ib.W, op.cin);
       if (le != cudaSuccess) return fail("avgpool launch failed: %s", cudaGetErrorString(le));
@@ -868,7 +996,7 @@ int run_op(dp_model* m, SubPlan* sp, int i, cudaStream_t st) {
       const BlobBuf& ob = m->bufs[op.out_buf];
       const int OH = op.pool ? ib.H / 2 : ib.H, OW = op.pool ? ib.W / 2 : ib.W;
       const long long total = (long long)B * OH * OW * (op.cin / 8);
-      cudaError_t le = launch_pdl(dp::bn_act_pool_kernel, grid_for(total, 256), 256, st, m->use_pdl != 0,
+      cudaError_t le = launch_pdl(dp::bn_act_pool_kernel<__half>, grid_for(total, 256), 256, st, m->use_pdl != 0,
                                   buf_at(op.in_buf), ib.C, op.in_choff, buf_at(op.out_buf), ob.C, op.out_choff, B, ib.H,
                                   ib.W, op.cin, dptr<float>(m, op.epi_scale_off), dptr<float>(m, op.epi_shift_off),
                                   op.relu, op.pool);
@@ -883,7 +1011,7 @@ int run_op(dp_model* m, SubPlan* sp, int i, cudaStream_t st) {
         LAUNCH_OK();
         if (op.head) {
           const long long tot = (long long)B * m->patch * m->patch;
-          dp::head_naive_kernel<<<grid_for(tot, 256), 256, 0, st>>>(L.np.out, op.cout, 0, op.cout, B, m->patch,
+          dp::head_naive_kernel<__half><<<grid_for(tot, 256), 256, 0, st>>>(L.np.out, op.cout, 0, op.cout, B, m->patch,
                                                                     dptr<float>(m, op.head_w_off), op.head_b,
                                                                     m->pass_dev, img0);
           LAUNCH_OK();
@@ -1020,6 +1148,9 @@ int dp_model_create(const void* blob, size_t nbytes, int device, int max_batch, 
   m->device = device;
   m->max_batch = max_batch;
   m->patch = (int)h.patch;
+  if (h.precision > 1) { delete m; return fail("container asks for unknown precision %u", h.precision); }
+  m->precision = (int)h.precision;
+  m->esize = m->precision ? 4 : 2;
   m->num_sms = prop.multiProcessorCount;
   m->bufs.resize(h.n_bufs);
   m->ops.resize(h.n_ops);
@@ -1043,7 +1174,7 @@ int dp_model_create(const void* blob, size_t nbytes, int device, int max_batch, 
   for (uint32_t i = 0; i < h.n_bufs; ++i) {
     const BlobBuf& b = m->bufs[i];
     if (b.C % 8) { cleanup(); return fail("buffer %u: channel count %d not a multiple of 8", i, b.C); }
-    const size_t sz = (size_t)max_batch * b.H * b.W * b.C * 2;
+    const size_t sz = (size_t)max_batch * b.H * b.W * b.C * m->esize;
     e = cudaMalloc(&m->buf_dev[i], sz);
     if (e != cudaSuccess) { cleanup(); return fail("cudaMalloc buffer %u (%zu B): %s", i, sz, cudaGetErrorString(e)); }
     cudaMemset(m->buf_dev[i], 0, sz);
@@ -1052,7 +1183,7 @@ int dp_model_create(const void* blob, size_t nbytes, int device, int max_batch, 
   {
     size_t sz = 0;
     for (const BlobOp& op : m->ops)
-      if (op.type == OP_CONV && op.head) sz = (size_t)max_batch * m->patch * m->patch * op.cout * 2;
+      if (op.type == OP_CONV && op.head) sz = (size_t)max_batch * m->patch * m->patch * op.cout * m->esize;
     if (sz) {
       e = cudaMalloc(&m->scratch_head, sz);
       if (e != cudaSuccess) { cleanup(); return fail("cudaMalloc head scratch: %s", cudaGetErrorString(e)); }
@@ -1125,6 +1256,8 @@ int dp_model_info(const dp_model* m, int* patch, int* max_batch, uint64_t* devic
   if (device_bytes) *device_bytes = m->device_bytes;
   return 0;
 }
+
+int dp_model_precision(const dp_model* m) { return m ? m->precision : -1; }
 
 int dp_model_set_option(dp_model* m, const char* key, int value) {
   if (check_model(m) || !key) return fail("null argument");
@@ -1323,7 +1456,7 @@ int dp_debug_read_buffer(dp_model* m, int buf, int n_tiles, void* host, size_t n
   if (check_model(m) || !host) return fail("null argument");
   if (buf < 0 || buf >= (int)m->bufs.size()) return fail("buffer %d out of range", buf);
   const BlobBuf& b = m->bufs[buf];
-  const size_t need = (size_t)n_tiles * b.H * b.W * b.C * 2;
+  const size_t need = (size_t)n_tiles * b.H * b.W * b.C * m->esize;
   if (n_tiles > m->max_batch || nbytes != need) return fail("size mismatch: need %zu bytes, got %zu", need, nbytes);
   CU_OK(cudaSetDevice(m->device));
   CU_OK(cudaDeviceSynchronize());
@@ -1335,7 +1468,7 @@ int dp_debug_write_buffer(dp_model* m, int buf, int n_tiles, const void* host, s
   if (check_model(m) || !host) return fail("null argument");
   if (buf < 0 || buf >= (int)m->bufs.size()) return fail("buffer %d out of range", buf);
   const BlobBuf& b = m->bufs[buf];
-  const size_t need = (size_t)n_tiles * b.H * b.W * b.C * 2;
+  const size_t need = (size_t)n_tiles * b.H * b.W * b.C * m->esize;
   if (n_tiles > m->max_batch || nbytes != need) return fail("size mismatch: need %zu bytes, got %zu", need, nbytes);
   CU_OK(cudaSetDevice(m->device));
   CU_OK(cudaDeviceSynchronize());

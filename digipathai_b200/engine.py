@@ -37,6 +37,8 @@ class TileModel:
         p, mb, nb = C.c_int(), C.c_int(), C.c_uint64()
         _lib.check(_lib.lib.dp_model_info(self._h, C.byref(p), C.byref(mb), C.byref(nb)))
         self.patch, self.device_bytes = p.value, nb.value
+        self.precision = "fp32" if _lib.lib.dp_model_precision(self._h) == 1 else "fp16"
+        self._buf_dtype = np.float32 if self.precision == "fp32" else np.float16
         self._tile_coords = {}
 
     # ------------------------------------------------------------------ lifetime
@@ -117,12 +119,12 @@ class TileModel:
 
     def read_buffer(self, buf: int, n_tiles: int) -> np.ndarray:
         h, w, c = self.buffer_shape(buf)
-        a = np.empty((n_tiles, h, w, c), dtype=np.float16)
+        a = np.empty((n_tiles, h, w, c), dtype=self._buf_dtype)
         _lib.check(_lib.lib.dp_debug_read_buffer(self._h, buf, n_tiles, a.ctypes.data_as(C.c_void_p), a.nbytes))
         return a
 
     def write_buffer(self, buf: int, arr: np.ndarray):
-        a = np.ascontiguousarray(arr, dtype=np.float16)
+        a = np.ascontiguousarray(arr, dtype=self._buf_dtype)
         _lib.check(_lib.lib.dp_debug_write_buffer(self._h, buf, a.shape[0], a.ctypes.data_as(C.c_void_p), a.nbytes))
 
     def run_ops(self, n_tiles: int, op_begin: int, op_end: int, tta_out: int = 0, probs: torch.Tensor | None = None):

@@ -29,7 +29,7 @@ import numpy as np
 
 from ..program import (KIND_1X1, KIND_3X3, KIND_STEM4, KIND_TAPS, OP_BCAST, OP_CONV, OP_DWCONV, OP_GAP, OP_HEAD_DOT,
                        OP_HEAD_RESIZE, OP_RESIZE, OP_STEM_S2D, Op, Program, bn_affine, pack_conv_weights,
-                       pack_stem4_weights)
+                       pack_stem4_weights, wdtype, weight_precision)
 
 ATROUS = (6, 12, 18)
 
@@ -99,7 +99,7 @@ class _Builder:
         sh[:c] = shift
         self.pr.ops.append(Op(OP_DWCONV, in_buf=ib, in_choff=ioff, cin=cp, out_buf=ob, out_choff=ooff, cout=cp,
                               relu=int(post_relu), pro=int(pre_relu), stride=stride, rate=rate,
-                              w=wp.astype(np.float16), epi_shift=sh, name=name))
+                              w=wp.astype(wdtype()), epi_shift=sh, name=name))
 
     def sepconv(self, prefix, ib, ioff, cin, tb, ob, ooff, filters, hw_in, stride=1, rate=1, depth_activation=False,
                 eps=1e-3, residual=False):
@@ -248,5 +248,8 @@ def init_deeplab_weights(seed: int = 0) -> dict:
     return w
 
 
-def deeplabv3plus_xception_program(weights: dict, patch: int = 256) -> Program:
-    return _build(weights, patch).pr
+def deeplabv3plus_xception_program(weights: dict, patch: int = 256, precision: str = "fp16") -> Program:
+    with weight_precision(precision):
+        pr = _build(weights, patch).pr
+    pr.precision = precision
+    return pr

@@ -17,7 +17,8 @@ import numpy as np
 
 from ..program import (KIND_1X1, KIND_3X3, KIND_STEM4, KIND_UP2, OP_BNPOOL, OP_CONV, OP_DENSE_LAYER, OP_MAXPOOL,
                        OP_STEM_S2D,
-                       PRO_AFFINE_RELU, Op, Program, bn_affine, pack_conv_weights, pack_stem4_weights, pad64)
+                       PRO_AFFINE_RELU, Op, Program, bn_affine, pack_conv_weights, pack_stem4_weights, pad64,
+                       weight_precision)
 
 DENSENET_BLOCKS = (6, 12, 24, 16)
 GROWTH = 32
@@ -73,7 +74,17 @@ def init_densenet_weights(seed: int = 0) -> dict:
     return w
 
 
-def densenet121_unet_program(weights: dict, patch: int = 256, fuse_dense: bool = True) -> Program:
+def densenet121_unet_program(weights: dict, patch: int = 256, fuse_dense: bool = True,
+                             precision: str = "fp16") -> Program:
+    """``precision``: 'fp16' = the tensor-core configuration (fp16 weights / activations, fp32 accumulation);
+    'fp32' = same program with un-rounded weights for the runtime's fp32 kernels (program.py)."""
+    with weight_precision(precision):
+        pr = _build(weights, patch, fuse_dense)
+    pr.precision = precision
+    return pr
+
+
+def _build(weights: dict, patch: int, fuse_dense: bool) -> Program:
     if patch < 64 or patch & (patch - 1):
         raise ValueError("patch_size must be a power of two >= 64 for the B200 tile kernels")
     P = patch

@@ -29,7 +29,8 @@ from __future__ import annotations
 import numpy as np
 
 from ..program import (KIND_1X1, KIND_3X3, KIND_STEM4, KIND_TAPS, KIND_UP2, OP_AVGPOOL3, OP_CONV, OP_MAXPOOL,
-                       OP_STEM_S2D, POOL_TF_SAME, Op, Program, bn_affine, pack_conv_weights, pack_stem4_weights)
+                       OP_STEM_S2D, POOL_TF_SAME, Op, Program, bn_affine, pack_conv_weights, pack_stem4_weights,
+                       weight_precision)
 
 EPS = 1e-3  # Keras BatchNormalization default; the reference never overrides it in this file
 
@@ -315,5 +316,8 @@ def init_inception_weights(seed: int = 0) -> dict:
     return w
 
 
-def inception_resnet_v2_unet_program(weights: dict, patch: int = 256) -> Program:
-    return _build(weights, patch).pr
+def inception_resnet_v2_unet_program(weights: dict, patch: int = 256, precision: str = "fp16") -> Program:
+    with weight_precision(precision):
+        pr = _build(weights, patch).pr
+    pr.precision = precision
+    return pr

@@ -7,19 +7,25 @@ affine terms, into one flat little-endian container that ``dp_model_create`` (cs
 
 Container layout (must match ``BlobHeader`` / ``BlobBuf`` / ``BlobOp`` in csrc/runtime.cu)::
 
-    header  72 B : 'DPB1' | u32 version=1 | u32 n_bufs | u32 n_ops | u32 patch | u32 0 | u64 data_off
-                   | u64 total_bytes | 4 x u64 0
+    header  72 B : 'DPB1' | u32 version=1 | u32 n_bufs | u32 n_ops | u32 patch | u32 precision | u64 data_off
+                   | u64 total_bytes | 4 x u64 0        (precision 0: fp16 weights + activations, 1: fp32 both)
     n_bufs x 16 B: i32 H, W, C, 0                      (per-image activation buffer geometry)
     n_ops  x 128 B: 12 x i32 (type in_buf in_choff cin out_buf out_choff cout kind relu pro head pool)
                    | f32 head_b | 3 x i32 0 | 8 x i64 offsets into the data section (-1 = absent):
                      w, epi_scale, epi_shift, pro_scale, pro_shift, head_w, w2, 0
                    (rsv i32 #0 = mid_buf, #1 = safe_cin for OP_DENSE_LAYER;
                     OP_CONV: #0 = kh | kw << 8 | stride << 16 for KIND_TAPS, #1 = residual flag)
-    data section : 256-byte aligned arrays (fp16 weights [entries][Cout][Cin]; fp32 vectors)
+    data section : 256-byte aligned arrays (weights [entries][Cout][Cin] in the program's precision; fp32 vectors)
+
+Precision.  ``precision='fp16'`` (default) is the tensor-core configuration BASELINE.json names: fp16 weights and
+activations, fp32 accumulation.  ``precision='fp32'`` packs the same program with un-rounded fp32 weights; the
+runtime then keeps fp32 activations and runs its fp32 kernels (csrc/precise.cuh) -- the mode that meets the 1e-3
+probability tolerance on any weight set, at a fraction of the throughput.
 """
 from __future__ import annotations
 
 import struct
+from contextlib import contextmanager
 from dataclasses import dataclass, field
 from typing import List, Optional
 
@@ -32,6 +38,27 @@ OP_DWCONV, OP_GAP, OP_BCAST, OP_RESIZE, OP_HEAD_DOT, OP_HEAD_RESIZE = 8, 9, 10, 
 KIND_1X1, KIND_3X3, KIND_UP2, KIND_STEM4, KIND_TAPS = 1, 3, 4, 5, 6
 POOL_PAD1_ZERO, POOL_TF_SAME = 0, 1   # OP_MAXPOOL `pool` field: ZeroPadding2D(1)+valid (densenet.py:122-123) / padding='same'
 PRO_NONE, PRO_AFFINE, PRO_AFFINE_RELU = 0, 1, 2
+PRECISIONS = {"fp16": 0, "fp32": 1}
+
+_weight_dtype = [np.float16]
+
+
+@contextmanager
+def weight_precision(precision: str):
+    """Graph builders run inside this context: the pack_* helpers then round weights to the program's storage type
+    (fp16: one rounding after the BN scale has been folded in fp32; fp32: none)."""
+    if precision not in PRECISIONS:
+        raise ValueError(f"precision must be one of {sorted(PRECISIONS)}, got {precision!r}")
+    _weight_dtype.append(np.float16 if precision == "fp16" else np.float32)
+    try:
+        yield
+    finally:
+        _weight_dtype.pop()
+
+
+def wdtype():
+    """Storage type of packed weights in the active ``weight_precision`` context (fp16 outside any)."""
+    return _weight_dtype[-1]
 
 
 @dataclass
@@ -49,7 +76,7 @@ class Op:
     head: int = 0
     pool: int = 0
     head_b: float = 0.0
-    w: Optional[np.ndarray] = None          # fp16 [entries, cout, cin]
+    w: Optional[np.ndarray] = None          # fp16 / fp32 [entries, cout, cin]
     epi_scale: Optional[np.ndarray] = None  # fp32 [cout]  (BNPOOL: [cin])
     epi_shift: Optional[np.ndarray] = None
     pro_scale: Optional[np.ndarray] = None  # fp32 [ceil(cin/64)*64]
@@ -72,6 +99,7 @@ class Program:
     bufs: List[tuple] = field(default_factory=list)  # (H, W, C)
     ops: List[Op] = field(default_factory=list)
     buf_names: List[str] = field(default_factory=list)
+    precision: str = "fp16"
 
     def add_buf(self, name: str, h: int, w: int, c: int) -> int:
         assert c % 8 == 0, "channel strides must keep 16-byte alignment"
@@ -123,7 +151,7 @@ def pack_conv_weights(k_hwio: np.ndarray, kind: int) -> np.ndarray:
         w = np.stack([k[ky, kx].T for ky in range(kh) for kx in range(kw)])
     else:
         raise ValueError(kind)
-    return np.ascontiguousarray(w).astype(np.float16)
+    return np.ascontiguousarray(w).astype(wdtype())
 
 
 def same_pad_before(size: int, k: int, stride: int) -> int:
@@ -145,7 +173,7 @@ def pack_stem_weights(k_hwio: np.ndarray, kpad: int = 160) -> np.ndarray:
     kh, kw, ci, co = k.shape
     w = np.zeros((1, co, kpad), dtype=np.float32)
     w[0, :, : kh * kw * ci] = k.reshape(kh * kw * ci, co).T
-    return w.astype(np.float16)
+    return w.astype(wdtype())
 
 
 def pack_stem4_weights(k_hwio: np.ndarray, pad: int = 3) -> np.ndarray:
@@ -170,7 +198,7 @@ def pack_stem4_weights(k_hwio: np.ndarray, pad: int = 3) -> np.ndarray:
                     if 0 <= ky < K and 0 <= kx < K:
                         for c in range(3):
                             w[t, :, dq * 16 + (a * 2 + b) * 3 + c] = k[ky, kx, c, :]
-    return w.astype(np.float16)
+    return w.astype(wdtype())
 
 
 def bn_affine(gamma, beta, mean, var, eps):
@@ -189,6 +217,10 @@ def pad64(v: np.ndarray) -> np.ndarray:
 
 def serialize(prog: Program) -> bytes:
     data = bytearray()
+    wdt = np.float16 if prog.precision == "fp16" else np.float32
+    for o in prog.ops:
+        for a in (o.w, o.w2):
+            assert a is None or a.dtype == wdt, (o.name, a.dtype, prog.precision)
 
     def put(arr: Optional[np.ndarray], dtype) -> int:
         if arr is None:
@@ -213,9 +245,9 @@ def serialize(prog: Program) -> bytes:
             if o.head:
                 assert o.head_w is not None and len(o.head_w) == o.cout, o.name
         offs = [
-            put(o.w, np.float16), put(o.epi_scale, np.float32), put(o.epi_shift, np.float32),
+            put(o.w, wdt), put(o.epi_scale, np.float32), put(o.epi_shift, np.float32),
             put(o.pro_scale, np.float32), put(o.pro_shift, np.float32), put(o.head_w, np.float32),
-            put(o.w2, np.float16), 0,
+            put(o.w2, wdt), 0,
         ]
         if o.type == OP_DWCONV:
             assert o.w is not None and o.w.shape == (9, o.cin) and o.epi_shift is not None and o.cin % 8 == 0, o.name
@@ -236,7 +268,8 @@ def serialize(prog: Program) -> bytes:
     tab = 72 + 16 * len(buf_recs) + 128 * len(op_recs)
     data_off = (tab + 255) // 256 * 256
     total = data_off + len(data)
-    header = struct.pack("<4s5I2Q4Q", b"DPB1", 1, len(buf_recs), len(op_recs), prog.patch, 0, data_off, total, 0, 0, 0, 0)
+    header = struct.pack("<4s5I2Q4Q", b"DPB1", 1, len(buf_recs), len(op_recs), prog.patch, PRECISIONS[prog.precision], data_off, total,
+                         0, 0, 0, 0)
     assert len(header) == 72
     blob = bytearray(header)
     for r in buf_recs:

@@ -54,6 +54,13 @@ int dp_model_destroy(dp_model* m);
 int dp_model_info(const dp_model* m, int* patch, int* max_batch, uint64_t* device_bytes);
 
 /*
+ * Arithmetic the container was packed for: 0 = fp16 weights / activations with fp32 accumulation on the tensor
+ * cores (the configuration BASELINE.json names), 1 = fp32 weights, activations and accumulation (the mode that
+ * reproduces the reference's fp32 Model.predict, Segmentation.py:154-156, within 1e-3; slower). -1 for a null model.
+ */
+int dp_model_precision(const dp_model* m);
+
+/*
  * Replaces  apply_tta(image_patches, tta_) -> models[name].predict(image_patches) -> transform_prob(pred, tta_)
  *                                        Segmentation.py:150-158, utils.py:487-522, dataloader.py:340-390
  * for ONE pass over ONE batch, including the tile crop + (v-128)/128 normalisation of __getitem__.

@@ -50,18 +50,23 @@ class _BN:
         return (x - _t(mu).view(sh)) / torch.sqrt(_t(var).view(sh) + eps) * _t(g).view(sh) + _t(b).view(sh)
 
 
-def forward(weights: dict, x_nhwc: np.ndarray, calibrate: bool = False, taps: dict | None = None) -> np.ndarray:
+def forward(weights: dict, x_nhwc: np.ndarray, calibrate: bool = False, taps: dict | None = None,
+            perturb: dict | None = None) -> np.ndarray:
     """float32 [B,P,P,3] in [-1,1] -> float32 [B,P,P,2] softmax, exactly ``Model.predict`` of the reference graph.
 
     ``taps`` (optional dict) receives intermediate NHWC activations by name for layer-level parity tests.
+    ``perturb`` (optional dict name -> callable(NCHW tensor) -> tensor) replaces the activation recorded under that
+    name before the graph continues (conditioning studies: tools/parity_study.py).
     """
     bn = _BN(weights, calibrate)
     rec = (lambda n, t: taps.__setitem__(n, t.permute(0, 2, 3, 1).contiguous().numpy())) if taps is not None else (lambda n, t: None)
+    hook = (lambda n, t: perturb[n](t) if n in perturb else t) if perturb else (lambda n, t: t)
     with torch.no_grad():
         x = _t(x_nhwc).permute(0, 3, 1, 2).contiguous()
         x = F.pad(x, (3, 3, 3, 3))
         x = _conv(x, weights["conv1/conv"], stride=2)
         x = F.relu(bn(x, "conv1/bn", EPS_ENC))
+        x = hook("conv1", x)
         conv1 = x
         rec("conv1", x)
         x = F.max_pool2d(F.pad(x, (1, 1, 1, 1)), 3, stride=2)
@@ -76,7 +81,8 @@ def forward(weights: dict, x_nhwc: np.ndarray, calibrate: bool = False, taps: di
                 if i == 1:
                     rec(p + "_bottleneck", x1)
                 x1 = _conv(x1, weights[p + "_2_conv"], pad=1)
-                x = torch.cat([x, x1], dim=1)
+                x = torch.cat([x, hook(p, x1)], dim=1)
+            x = hook(f"conv{b}", x)
             skips[b] = x
             rec(f"conv{b}", x)
             if b < 5:
@@ -89,7 +95,7 @@ def forward(weights: dict, x_nhwc: np.ndarray, calibrate: bool = False, taps: di
 
         def block(x, name):
             x = _conv(x, weights[name + "_conv"], pad=1, bias=weights[name + "_conv_bias"])
-            x = F.relu(bn(x, name + "_norm", EPS_DEC))
+            x = hook(name, F.relu(bn(x, name + "_norm", EPS_DEC)))
             rec(name, x)
             return x
 

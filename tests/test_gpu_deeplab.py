@@ -117,7 +117,11 @@ def test_forward_matches_oracle_and_emulator(full):
     d, de = np.abs(got - s["oracle"]), np.abs(got - s["emu"])
     print(f"\ndeeplab forward 2 tiles: vs oracle max {d.max():.3e} mean {d.mean():.3e}; vs emulator max {de.max():.3e} "
           f"mean {de.mean():.3e}")
-    assert d.mean() <= 6e-2 and de.mean() <= 6e-2
+    # fp16 mode, measured on the B200: 2.2e-1 max / 2.9e-2 mean against the fp32 oracle (the sixteen middle-flow units
+    # amplify rounding 10x; the fp32 precision mode reaches 2.7e-4, tests/test_gpu_precision.py).  Bounds = 1.5 x measured.
+    assert d.max() <= 3.3e-1 and d.mean() <= 4.4e-2 and de.max() <= 3.3e-1 and de.mean() <= 4.4e-2
+    mism = (got >= 0.3) != (s["oracle"] >= 0.3)
+    assert (np.abs(s["oracle"] - 0.3)[mism] <= d.max()).all()
     prog = s["prog"]
     for name, tol in (("stem_s2d", 0.0), ("A1", 1e-3), ("A2", 1e-3), ("entry_flow_block1_d1", 2e-3), ("B1", 2e-3),
                       ("skip1", 4e-3), ("B2", 4e-3), ("entry_flow_block3_d3", 8e-3)):
@@ -130,7 +134,7 @@ def test_forward_matches_oracle_and_emulator(full):
     s["model"].set_option("naive_conv", 1)
     naive = s["model"].forward_tile_batch(t).cpu().numpy()
     s["model"].set_option("naive_conv", 0)
-    assert np.abs(naive - s["oracle"]).mean() <= 6e-2
+    assert np.abs(naive - s["oracle"]).mean() <= 4.4e-2 and np.abs(naive - s["oracle"]).max() <= 3.3e-1
 
 
 def test_executed_macs_accounting(full):

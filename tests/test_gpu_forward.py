@@ -1,12 +1,14 @@
 """GPU parity of the whole DenseNet-121 U-Net forward (through dp_forward_tiles) against the fp32 oracle.
 
-Tolerance.  BASELINE.json asks for 1e-3 max-abs on the probability.  With fp16 storage of weights and
-activations (the configuration BASELINE.json names) that is not reachable on this 121-layer random-init
-network: the CPU emulator, which performs the SAME arithmetic with the same fp16 rounding points in torch-CPU
-fp32, deviates from the fp32 oracle by ~2e-2 max / ~2e-3 mean, and two fp16 evaluations that differ only in
-fp32 accumulation order deviate from each other by ~1e-2 (rounding differences are amplified through 58
-sequential dense layers).  The asserted bounds are therefore: max-abs <= 5e-2 and mean-abs <= 5e-3 against
-the oracle, the same against the emulator, and label (p >= 0.3) mismatches only inside the +-max-abs band.
+Tolerance.  BASELINE.json asks for 1e-3 max-abs on the probability; that bound is asserted on the library's fp32
+precision mode in tests/test_gpu_precision.py (measured 2e-5 .. 5e-5).  THIS file covers the fp16 tensor-core mode
+(the configuration BASELINE.json's configs[1] names), which cannot reach 1e-3 on this 121-layer random-init
+stand-in network whatever the kernels do: profiles/r2_parity_conditioning.md shows the fp32 oracle itself moving by
+2.3e-2 max / 2e-3 mean when ONE activation tensor (the stem output) is perturbed by a single 10-bit-mantissa
+rounding, and profiles/r2_parity_drift.md shows the same 1000x depth amplification acting on the fp32 mode's own
+rounding (1e-7 at conv1 -> 1e-4 at conv5).  Measured on the B200 (rounds 1-2): 2.0e-2 .. 2.2e-2 max, 2.2e-3 mean.
+Asserted: 1.5 x measured = max-abs <= 3.3e-2 and mean-abs <= 3.3e-3 against the oracle, the same against the CPU
+emulator of the fp16 program, and label (p >= 0.3) mismatches only inside the +-max-abs band.
 Kernel correctness proper is asserted per layer in test_gpu_conv.py at fp16-ulp tolerance.
 """
 import numpy as np
@@ -14,7 +16,7 @@ import pytest
 
 pytestmark = pytest.mark.gpu
 
-MAX_ABS, MEAN_ABS = 5e-2, 5e-3
+MAX_ABS, MEAN_ABS = 3.3e-2, 3.3e-3     # 1.5 x the measured 2.2e-2 / 2.2e-3 (see above)
 
 
 @pytest.fixture(scope="module")

@@ -28,8 +28,9 @@ def test_get_prediction_matches_oracle_pipeline(env):
     touched = want['count'] > 0
     print(f"\nget_prediction: max|mean-oracle| {d.max():.3e} mean {d[touched].mean():.3e}; "
           f"max|var-oracle| {np.abs(got['var'] - want['var']).max():.3e}")
-    assert d.max() <= 5e-2 and d[touched].mean() <= 2.5e-2
-    assert np.abs(got['var'] - want['var']).max() <= 2.5e-2
+    # fp16 mode: the per-tile bound of test_gpu_forward.py (1.5 x measured) carries over to the stitched mean
+    assert d.max() <= 3.3e-2 and d[touched].mean() <= 3.3e-3
+    assert np.abs(got['var'] - want['var']).max() <= 1e-2
     # pixels no tile touched stay exactly zero on both sides; zero pattern of the planes is identical
     zero_w, zero_g = want['mean'] == 0, got['mean'] == 0
     assert np.array_equal(zero_w, zero_g)
@@ -51,9 +52,9 @@ def test_get_segmentation_drop_in(env, tmp_path):
     assert got.dtype == np.float32 and got.shape == want_thr.shape and set(np.unique(got)) <= {0.0, 255.0}
     mism = got != want_thr
     # labels may only differ where the oracle probability is within the fp16 band of the 0.3 threshold
-    assert (np.abs(want_mean - 0.3)[mism] <= 5e-2).all()
-    print(f"\ngetSegmentation: {int(mism.sum())} / {mism.size} label mismatches, all inside the +-5e-2 band "
-          f"({int((np.abs(want_mean - 0.3) <= 5e-2).sum())} pixels in band)")
+    assert (np.abs(want_mean - 0.3)[mism] <= 3.3e-2).all()
+    print(f"\ngetSegmentation: {int(mism.sum())} / {mism.size} label mismatches, all inside the +-3.3e-2 band "
+          f"({int((np.abs(want_mean - 0.3) <= 3.3e-2).sum())} pixels in band)")
     assert mism.mean() < 0.02
     assert status['status'] == "Saving Prediction Uncertanity..." and status['progress'] == 0
     from PIL import Image
@@ -121,6 +122,33 @@ def test_quick_false_runs_the_three_model_ensemble(env):
     mism = got != want_thr
     print(f"\n3-model ensemble: {int(mism.sum())} / {mism.size} label mismatches")
     assert (np.abs(want_mean - 0.3)[mism] <= 1e-1).all() and mism.mean() < 0.05
+
+
+def test_get_segmentation_fp32_mode_returns_the_reference_label_map(env):
+    """precision='fp32': the returned {0, 255} map equals the oracle's except where the oracle's own probability lies
+    within 1e-3 of the threshold (BASELINE.json: 1e-3 on the mask probabilities, identical label map) -- single model
+    and the quick=False three-model ensemble."""
+    from digipathai_b200.Segmentation import getSegmentation
+    from digipathai_b200.models.deeplab import init_deeplab_weights
+    from digipathai_b200.models.inception import init_inception_weights
+    from oracle import deeplab_ref, inception_ref, pipeline_ref
+    w, slide, omodels = env
+    want_thr, want_mean, _ = pipeline_ref.getSegmentation(slide, omodels, 256, 128, 4)
+    got = getSegmentation(slide, patch_size=256, stride_size=128, batch_size=4, quick=True, weights=w, precision="fp32")
+    mism = got != want_thr
+    print(f"\ngetSegmentation fp32 mode: {int(mism.sum())} / {mism.size} label mismatches")
+    assert (np.abs(want_mean - 0.3)[mism] <= 1e-3).all() and mism.sum() <= (np.abs(want_mean - 0.3) <= 1e-3).sum()
+    rng = np.random.default_rng(12)
+    calib = (rng.integers(0, 256, (2, 256, 256, 3)).astype(np.float32) - 128.0) / 128.0
+    wi = inception_ref.calibrate_bn(init_inception_weights(5), calib)
+    wd = deeplab_ref.calibrate_bn(init_deeplab_weights(6), calib)
+    three = {"dense": omodels["dense"], "inception": inception_ref.OracleModel(wi), "deeplabv3": deeplab_ref.OracleModel(wd)}
+    want_thr, want_mean, _ = pipeline_ref.getSegmentation(slide, three, 256, 256, 4)
+    got = getSegmentation(slide, patch_size=256, stride_size=256, batch_size=4, quick=False,
+                          weights={"dense": w, "inception": wi, "deeplabv3": wd}, precision="fp32")
+    mism = got != want_thr
+    print(f"3-model ensemble fp32 mode: {int(mism.sum())} / {mism.size} label mismatches")
+    assert (np.abs(want_mean - 0.3)[mism] <= 1e-3).all()
 
 
 def test_get_segmentation_writes_pyramidal_tiffs(env, tmp_path):

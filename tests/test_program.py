@@ -22,18 +22,7 @@ def small():
 
 def _fp32_program(w, patch):
     """Program with un-rounded fp32 weights: isolates graph/packing logic from fp16 precision."""
-    prog = DN.densenet121_unet_program(w, patch)
-    w32 = {}
-    real16 = np.float16
-    try:
-        PG.np_float16_backup = real16
-        import types
-        PG.np = types.SimpleNamespace(**{n: getattr(np, n) for n in dir(np) if not n.startswith("__")})
-        PG.np.float16 = np.float32
-        prog32 = DN.densenet121_unet_program(w, patch)
-    finally:
-        PG.np = np
-    return prog, prog32
+    return DN.densenet121_unet_program(w, patch), DN.densenet121_unet_program(w, patch, precision="fp32")
 
 
 def test_program_is_the_reference_graph(small):

@@ -13,15 +13,7 @@ from oracle import deeplab_ref
 
 
 def _fp32_program(w, patch):
-    ns = types.SimpleNamespace(**{n: getattr(np, n) for n in dir(np) if not n.startswith("__")})
-    ns.float16 = np.float32
-    try:
-        PG.np = ns
-        DL.np = ns
-        return DL.deeplabv3plus_xception_program(w, patch)
-    finally:
-        PG.np = np
-        DL.np = np
+    return DL.deeplabv3plus_xception_program(w, patch, precision="fp32")
 
 
 def test_layer_names_and_mac_count():

@@ -24,12 +24,7 @@ def small():
 
 
 def _fp32_program(w, patch):
-    try:
-        PG.np = types.SimpleNamespace(**{n: getattr(np, n) for n in dir(np) if not n.startswith("__")})
-        PG.np.float16 = np.float32
-        return IN.inception_resnet_v2_unet_program(w, patch)
-    finally:
-        PG.np = np
+    return IN.inception_resnet_v2_unet_program(w, patch, precision="fp32")
 
 
 def test_layer_names_follow_keras_creation_order():
