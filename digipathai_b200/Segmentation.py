@@ -46,7 +46,8 @@ def _torch():
 
 def get_prediction(wsi_path, mask_path=None, label_path=None, batch_size=64, models=None, tta_list=None,
                    num_workers=8, verbose=0, patch_size=256, stride_size=256, mask_level=-1, status=None,
-                   *, device=0, tile_range=None, return_device=False, finalize=True, tissue_mask=None, grid=None):
+                   *, device=0, tile_range=None, return_device=False, finalize=True, tissue_mask=None, grid=None,
+                   timings=None):
     """Patch based segmentor (reference: Segmentation.py:65-189).
 
     ``models`` maps a name to a ``TileModel`` (engine.py) -- the object that replaces the Keras model.
@@ -56,7 +57,8 @@ def get_prediction(wsi_path, mask_path=None, label_path=None, batch_size=64, mod
     planes as torch CUDA tensors, ``finalize=False`` skips the normalisation (sharded runs normalise after the
     halo exchange), ``tissue_mask`` supplies a precomputed RAW [x, y] mask instead of the Otsu/HSV heuristic (the
     morphology of utils.py:200-219 is still applied to it), ``grid`` a ready ``TileGrid`` of this slide (sharded
-    runs build it once and index it with ``tile_range``).
+    runs build it once and index it with ``tile_range``), ``timings`` a dict that receives this call's phase times in
+    milliseconds (grid, raster upload, tile loop; each phase ends with a device synchronisation).
     ``mask_path`` names a ``.tiff`` tissue mask read at the slide's top level instead of running the heuristic
     (dataloader.py:256-263; any other extension leaves the reference's dataset without a mask -- AttributeError --
     and does so here); ``label_path`` / ``num_workers`` / ``mask_level`` are accepted for signature compatibility:
@@ -73,9 +75,13 @@ def get_prediction(wsi_path, mask_path=None, label_path=None, batch_size=64, mod
             raise AttributeError("mask_path must name a .tiff file: the reference's dataset is left without a "
                                  "'_mask' attribute for any other extension (dataloader.py:256-263)")
         tissue_mask = mask_from_slide(open_slide(mask_path), len(slide.level_dimensions) - 1)
+    import time
+    _t0 = time.perf_counter()
     if grid is None:
         grid = TileGrid(slide, patch_size=patch_size, stride_size=stride_size, batch_size=batch_size,
-                        roi_masking=True, mask=tissue_mask)
+                        roi_masking=True, mask=tissue_mask, device=device)
+        if timings is not None:
+            timings['grid_ms'] = (time.perf_counter() - _t0) * 1e3
     elif (grid.patch_size, grid.stride_size, grid.batch_size) != (int(patch_size), int(stride_size), int(batch_size)):
         raise ValueError("grid= was built for another patch / stride / batch size")
     n_batches = len(grid)
@@ -105,7 +111,12 @@ def get_prediction(wsi_path, mask_path=None, label_path=None, batch_size=64, mod
         sel = coords_all[b_lo * batch_size:b_hi * batch_size, 0]
         x_lo, x_hi = int(sel.min()), int(sel.max()) + P
     with torch.cuda.device(dev):
+        _t0 = time.perf_counter()
         raster = upload_xy_raster(slide, x_lo, x_hi, dev)                          # uint8 [x, y, c] stripe in HBM
+        if timings is not None:
+            torch.cuda.synchronize(dev)
+            timings['upload_ms'] = (time.perf_counter() - _t0) * 1e3
+            _t0 = time.perf_counter()
         mean = torch.zeros((x_hi - x_lo, H), dtype=torch.float32, device=dev)
         var = torch.zeros_like(mean)
         count = torch.zeros((x_hi - x_lo, H), dtype=torch.uint8, device=dev)
@@ -124,6 +135,9 @@ def get_prediction(wsi_path, mask_path=None, label_path=None, batch_size=64, mod
                     models[nm].forward_tiles(raster, c_local, t_in, t_out, out=probs[k])
                     k += 1
             engine.stitch(probs, coords_abs[ii * batch_size:(ii + 1) * batch_size], mean, var, count, x_lo=x_lo)
+        if timings is not None:
+            torch.cuda.synchronize(dev)
+            timings['loop_ms'] = (time.perf_counter() - _t0) * 1e3
         if finalize:
             engine.finalize(mean, var, count, 0.0, None)
         torch.cuda.synchronize(dev)

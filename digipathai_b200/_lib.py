@@ -40,6 +40,10 @@ _SIGS = {
     ),
     "dp_finalize": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_float, C.c_void_p, C.c_void_p]),
     "dp_pyramid_down2": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p]),
+    "dp_tissue_hist": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
+    "dp_tissue_mask": (C.c_int, [C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
+                                 C.c_void_p]),
+    "dp_morph_rect": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "dp_crf_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
     "dp_crf_tiles": (
         C.c_int,

@@ -37,6 +37,14 @@ __device__ __forceinline__ void store8(float* p, const float (&v)[8]) {
   reinterpret_cast<float4*>(p)[1] = make_float4(v[4], v[5], v[6], v[7]);
 }
 
+// Tile origins are clamped into the raster exactly as the reference clamps them (dataloader.py:351-353:
+// x = max(0, min(x, X_slide - P))), so a caller of the C ABI that passes an origin outside the slide reads the border
+// tile instead of out-of-bounds memory.  Callers on the path (tissue.TileGrid) pass clamped origins already.
+__device__ __forceinline__ long long clamp_origin(long long v, long long extent, int P) {
+  const long long hi = extent - P;
+  return v < 0 ? 0 : (v > hi ? (hi > 0 ? hi : 0) : v);
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // Tile gather + (v-128)/128 + forward TTA + ZeroPadding2D(3) + im2col for the 7x7/2 stem conv
 // (dataloader.py:357-388 crop/transposed layout/normalise; utils.py:487-501 TTA; densenet.py:116-117 stem).
@@ -57,7 +65,7 @@ __global__ void stem_im2col_kernel(const PassDesc* __restrict__ pass, int img0, 
     const int ow = r % OH; r /= OH;
     const int oh = r % OH;
     const int b = r / OH;
-    const long long x0 = coords[2 * b], y0 = coords[2 * b + 1];
+    const long long x0 = clamp_origin(coords[2 * b], pass->slide_w, P), y0 = clamp_origin(coords[2 * b + 1], slide_h, P);
     __align__(16) __half vals[8];
 #pragma unroll
     for (int t = 0; t < 8; ++t) {
@@ -102,7 +110,7 @@ __global__ void stem_s2d_kernel(const PassDesc* __restrict__ pass, int img0, int
     const int q = r0 % OH; r0 /= OH;
     const int r = r0 % OH;
     const int b = r0 / OH;
-    const long long x0 = coords[2 * b], y0 = coords[2 * b + 1];
+    const long long x0 = clamp_origin(coords[2 * b], pass->slide_w, P), y0 = clamp_origin(coords[2 * b + 1], slide_h, P);
     float lo8[8], hi8[8];
 #pragma unroll
     for (int t = 0; t < 8; ++t) lo8[t] = hi8[t] = 0.f;
@@ -151,20 +159,30 @@ __global__ void maxpool3s2_kernel(const T* __restrict__ in, int in_ctot, int in_
     float m[8];
 #pragma unroll
     for (int t = 0; t < 8; ++t) m[t] = -INFINITY;
-    for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky) {
+      // one window row at a time: its three loads are in flight together (latency bound otherwise)
+      const int ih = 2 * oh - (mode ? 0 : 1) + ky;
+      const bool row_in = ih >= 0 && ih < H;
+      float f[3][8];
+      bool in_map[3];
+#pragma unroll
       for (int kx = 0; kx < 3; ++kx) {
-        const int ih = 2 * oh - (mode ? 0 : 1) + ky, iw = 2 * ow - (mode ? 0 : 1) + kx;
-        if (ih < 0 || ih >= H || iw < 0 || iw >= W) {
-          if (mode) continue;
+        const int iw = 2 * ow - (mode ? 0 : 1) + kx;
+        in_map[kx] = row_in && iw >= 0 && iw < W;
+        if (in_map[kx]) load8(in + ((static_cast<long long>(n) * H + ih) * W + iw) * in_ctot + in_choff + cg * 8, f[kx]);
+      }
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx) {
+        if (in_map[kx]) {
+#pragma unroll
+          for (int t = 0; t < 8; ++t) m[t] = fmaxf(m[t], f[kx][t]);
+        } else if (!mode) {
 #pragma unroll
           for (int t = 0; t < 8; ++t) m[t] = fmaxf(m[t], 0.f);  // explicit zero padding takes part in the max
-        } else {
-          float f[8];
-          load8(in + ((static_cast<long long>(n) * H + ih) * W + iw) * in_ctot + in_choff + cg * 8, f);
-#pragma unroll
-          for (int t = 0; t < 8; ++t) m[t] = fmaxf(m[t], f[t]);
         }
       }
+    }
     store8(out + ((static_cast<long long>(n) * OH + oh) * OW + ow) * out_ctot + out_choff + cg * 8, m);
   }
 }
@@ -227,19 +245,33 @@ __global__ void bn_act_pool_kernel(const T* __restrict__ in, int in_ctot, int in
     float sc[8], sh[8], acc[8];
 #pragma unroll
     for (int t = 0; t < 8; ++t) { sc[t] = scale[cg * 8 + t]; sh[t] = shift[cg * 8 + t]; acc[t] = 0.f; }
-    const int np = pool ? 2 : 1;
-    for (int dy = 0; dy < np; ++dy)
-      for (int dx = 0; dx < np; ++dx) {
-        const int ih = pool ? 2 * oh + dy : oh, iw = pool ? 2 * ow + dx : ow;
-        float f[8];
-        load8(in + ((static_cast<long long>(n) * H + ih) * W + iw) * in_ctot + in_choff + cg * 8, f);
+    const T* base = in + ((static_cast<long long>(n) * H + (pool ? 2 * oh : oh)) * W + (pool ? 2 * ow : ow)) * in_ctot +
+                    in_choff + cg * 8;
+    if (pool) {
+      // all four window loads in flight before the first use (the kernel is latency bound otherwise)
+      float f[4][8];
+      load8(base, f[0]);
+      load8(base + in_ctot, f[1]);
+      load8(base + static_cast<long long>(W) * in_ctot, f[2]);
+      load8(base + static_cast<long long>(W + 1) * in_ctot, f[3]);
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
 #pragma unroll
         for (int t = 0; t < 8; ++t) {
-          float a = fmaf(f[t], sc[t], sh[t]);
+          float a = fmaf(f[q][t], sc[t], sh[t]);
           if (relu) a = fmaxf(a, 0.f);
           acc[t] += a;
         }
+    } else {
+      float f[8];
+      load8(base, f);
+#pragma unroll
+      for (int t = 0; t < 8; ++t) {
+        float a = fmaf(f[t], sc[t], sh[t]);
+        if (relu) a = fmaxf(a, 0.f);
+        acc[t] += a;
       }
+    }
     const float inv = pool ? 0.25f : 1.f;
 #pragma unroll
     for (int t = 0; t < 8; ++t) acc[t] *= inv;
@@ -480,15 +512,94 @@ __global__ void head_naive_kernel(const T* __restrict__ in, int in_ctot, int in_
 // is bit-identical to the numpy loop given identical probabilities; no atomics.
 // numpy semantics reproduced: mean = (sequential fp32 sum over N) / N; var = sum((p-mean)^2)/N (ddof 0);
 // count is uint8 and wraps.
+// One covering tile's contribution to one pixel: mean and population variance over the N passes, in numpy's order.
+__device__ __forceinline__ void stitch_stats(const float* __restrict__ pp, int N, long long pass_stride, float& mu,
+                                             float& vr) {
+  float s = pp[0];
+  for (int k = 1; k < N; ++k) s = __fadd_rn(s, pp[k * pass_stride]);
+  mu = __fdiv_rn(s, static_cast<float>(N));
+  const float d0 = __fsub_rn(pp[0], mu);
+  float ss = __fmul_rn(d0, d0);
+  for (int k = 1; k < N; ++k) {
+    const float d = __fsub_rn(pp[k * pass_stride], mu);
+    ss = __fadd_rn(ss, __fmul_rn(d, d));
+  }
+  vr = __fdiv_rn(ss, static_cast<float>(N));
+}
+
+// Vector path (every tile origin's y, the patch and the plane height are multiples of 4 -- any stride-128 grid):
+// a thread owns 4 consecutive y of one plane row; the four pixels are covered by exactly the same tiles, so the
+// ownership test runs once per group and every access is 16 bytes (probabilities, mean, var) or 4 bytes (count).
+// Scalar path: one pixel per thread, any geometry.  Both do the same arithmetic in the same order.
 __global__ void stitch_kernel(const float* __restrict__ probs, int N, int B, int P,
                               const int* __restrict__ coords, float* __restrict__ mean,
-                              float* __restrict__ var, uint8_t* __restrict__ count, long long plane_h,
-                              int x_lo) {
+                              float* __restrict__ var, uint8_t* __restrict__ count, long long plane_w,
+                              long long plane_h, int x_lo) {
   extern __shared__ int s_xy[];  // [B][2]
-  for (int i = threadIdx.x; i < 2 * B; i += blockDim.x) s_xy[i] = coords[i];
-  __syncthreads();
+  int ok = ((P | static_cast<int>(plane_h & 3)) & 3) == 0;
+  for (int i = threadIdx.x; i < 2 * B; i += blockDim.x) {
+    const int v = coords[i];
+    s_xy[i] = v;
+    if ((i & 1) && (v & 3)) ok = 0;
+  }
+  const bool vec = __syncthreads_and(ok) != 0;
   const int i = blockIdx.y;
   const int xi = s_xy[2 * i], yi = s_xy[2 * i + 1];
+  const long long pass_stride = static_cast<long long>(B) * P * P;
+  if (vec) {
+    const int PQ = P / 4;
+    for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < P * PQ; q += gridDim.x * blockDim.x) {
+      const int a = q / PQ, b = (q - a * PQ) * 4;
+      const int gx = xi + a, gy = yi + b;
+      bool owner = true;
+      for (int j = 0; j < i; ++j) {
+        const int dx = gx - s_xy[2 * j], dy = gy - s_xy[2 * j + 1];
+        if (dx >= 0 && dx < P && dy >= 0 && dy < P) { owner = false; break; }
+      }
+      if (!owner) continue;
+      if (gx < x_lo || gx - x_lo >= plane_w || gy < 0 || gy + 3 >= plane_h) continue;
+      const long long off = static_cast<long long>(gx - x_lo) * plane_h + gy;
+      float4 m4 = *reinterpret_cast<const float4*>(mean + off);
+      float4 v4 = *reinterpret_cast<const float4*>(var + off);
+      uchar4 c4 = *reinterpret_cast<const uchar4*>(count + off);
+      for (int j = i; j < B; ++j) {
+        const int dx = gx - s_xy[2 * j], dy = gy - s_xy[2 * j + 1];
+        if (dx < 0 || dx >= P || dy < 0 || dy >= P) continue;
+        const float* pp = probs + (static_cast<long long>(j) * P + dx) * P + dy;
+        // two sweeps over the passes (the second one hits L1): sequential fp32 sum, then sum of squared deviations
+        float4 s4 = __ldg(reinterpret_cast<const float4*>(pp));
+        for (int k = 1; k < N; ++k) {
+          const float4 p4 = __ldg(reinterpret_cast<const float4*>(pp + k * pass_stride));
+          s4.x = __fadd_rn(s4.x, p4.x); s4.y = __fadd_rn(s4.y, p4.y);
+          s4.z = __fadd_rn(s4.z, p4.z); s4.w = __fadd_rn(s4.w, p4.w);
+        }
+        const float fn = static_cast<float>(N);
+        const float4 mu4 = make_float4(__fdiv_rn(s4.x, fn), __fdiv_rn(s4.y, fn), __fdiv_rn(s4.z, fn), __fdiv_rn(s4.w, fn));
+        float4 ss4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int k = 0; k < N; ++k) {
+          const float4 p4 = __ldg(reinterpret_cast<const float4*>(pp + k * pass_stride));
+          const float dx0 = __fsub_rn(p4.x, mu4.x), dx1 = __fsub_rn(p4.y, mu4.y);
+          const float dx2 = __fsub_rn(p4.z, mu4.z), dx3 = __fsub_rn(p4.w, mu4.w);
+          if (k == 0) {
+            ss4 = make_float4(__fmul_rn(dx0, dx0), __fmul_rn(dx1, dx1), __fmul_rn(dx2, dx2), __fmul_rn(dx3, dx3));
+          } else {
+            ss4.x = __fadd_rn(ss4.x, __fmul_rn(dx0, dx0)); ss4.y = __fadd_rn(ss4.y, __fmul_rn(dx1, dx1));
+            ss4.z = __fadd_rn(ss4.z, __fmul_rn(dx2, dx2)); ss4.w = __fadd_rn(ss4.w, __fmul_rn(dx3, dx3));
+          }
+        }
+        m4.x = __fadd_rn(m4.x, mu4.x); m4.y = __fadd_rn(m4.y, mu4.y);
+        m4.z = __fadd_rn(m4.z, mu4.z); m4.w = __fadd_rn(m4.w, mu4.w);
+        v4.x = __fadd_rn(v4.x, __fdiv_rn(ss4.x, fn)); v4.y = __fadd_rn(v4.y, __fdiv_rn(ss4.y, fn));
+        v4.z = __fadd_rn(v4.z, __fdiv_rn(ss4.z, fn)); v4.w = __fadd_rn(v4.w, __fdiv_rn(ss4.w, fn));
+        c4.x = static_cast<uint8_t>(c4.x + 1); c4.y = static_cast<uint8_t>(c4.y + 1);
+        c4.z = static_cast<uint8_t>(c4.z + 1); c4.w = static_cast<uint8_t>(c4.w + 1);
+      }
+      *reinterpret_cast<float4*>(mean + off) = m4;
+      *reinterpret_cast<float4*>(var + off) = v4;
+      *reinterpret_cast<uchar4*>(count + off) = c4;
+    }
+    return;
+  }
   for (int pix = blockIdx.x * blockDim.x + threadIdx.x; pix < P * P; pix += gridDim.x * blockDim.x) {
     const int a = pix / P, b = pix - a * P;
     const int gx = xi + a, gy = yi + b;
@@ -498,24 +609,15 @@ __global__ void stitch_kernel(const float* __restrict__ probs, int N, int B, int
       if (dx >= 0 && dx < P && dy >= 0 && dy < P) { owner = false; break; }
     }
     if (!owner) continue;
+    if (gx < x_lo || gx - x_lo >= plane_w || gy < 0 || gy >= plane_h) continue;   // tile hangs over the plane: drop
     const long long off = static_cast<long long>(gx - x_lo) * plane_h + gy;
     float m = mean[off], v = var[off];
     uint8_t cnt = count[off];
     for (int j = i; j < B; ++j) {
       const int dx = gx - s_xy[2 * j], dy = gy - s_xy[2 * j + 1];
       if (dx < 0 || dx >= P || dy < 0 || dy >= P) continue;
-      const float* pp = probs + (static_cast<long long>(j) * P + dx) * P + dy;
-      const long long pass_stride = static_cast<long long>(B) * P * P;
-      float s = pp[0];
-      for (int k = 1; k < N; ++k) s = __fadd_rn(s, pp[k * pass_stride]);
-      const float mu = __fdiv_rn(s, static_cast<float>(N));
-      float d0 = __fsub_rn(pp[0], mu);
-      float ss = __fmul_rn(d0, d0);
-      for (int k = 1; k < N; ++k) {
-        const float d = __fsub_rn(pp[k * pass_stride], mu);
-        ss = __fadd_rn(ss, __fmul_rn(d, d));
-      }
-      const float vr = __fdiv_rn(ss, static_cast<float>(N));
+      float mu, vr;
+      stitch_stats(probs + (static_cast<long long>(j) * P + dx) * P + dy, N, pass_stride, mu, vr);
       m = __fadd_rn(m, mu);
       v = __fadd_rn(v, vr);
       cnt = static_cast<uint8_t>(cnt + 1);

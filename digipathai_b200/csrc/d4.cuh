@@ -21,6 +21,7 @@ __host__ __device__ __forceinline__ void d4_src(int code, int i, int j, int P, i
 struct PassDesc {
   const unsigned char* slide;  // uint8 [x][y][3]
   long long slide_h;
+  long long slide_w;           // extent along x: tile origins are clamped to [0, slide_w - P] x [0, slide_h - P] by the gather
   const int* coords;           // int32 [n_tiles][2]
   float* probs_out;            // float32 [n_tiles][P][P]
   int tta_in, tta_out;

@@ -21,6 +21,7 @@
 #include "crf.cuh"
 #include "dense_layer.cuh"
 #include "precise.cuh"
+#include "tissue.cuh"
 
 namespace {
 
@@ -1022,7 +1023,11 @@ int run_op(dp_model* m, SubPlan* sp, int i, cudaStream_t st) {
       cp.desc_base_mode = m->desc_base_mode;
 
       cp.trace = (m->trace_op == i) ? m->trace_dev : nullptr;
-      { const char* dbg = getenv("DP_DBG_SKIP"); cp.dbg_skip = dbg ? atoi(dbg) : 0; }
+#ifdef DP_EXPERIMENTS   // work-skipping timing switches (wrong results): experiment builds only, never in the shipped library
+      { static const int dbg = getenv("DP_DBG_SKIP") ? atoi(getenv("DP_DBG_SKIP")) : 0; cp.dbg_skip = dbg; }
+#else
+      cp.dbg_skip = 0;
+#endif
       cp.gt = (m->stamp && m->gt_dev) ? m->gt_dev + 2 * i : nullptr;
       // Programmatic dependent launch: the kernel's setup (barrier init, TMEM alloc, BN constants -> smem)
       // runs before its griddepcontrol.wait and so overlaps the tail of the preceding kernel in the stream.
@@ -1438,7 +1443,9 @@ int dp_forward_tiles(dp_model* m, const uint8_t* slide, int64_t slide_w, int64_t
   if ((tta_in | tta_out) & ~7) return fail("D4 codes must be in [0, 8)");
   if (n_tiles < 1 || n_tiles > m->max_batch) return fail("n_tiles %d outside [1, %d]", n_tiles, m->max_batch);
   dp::PassDesc d;
-  d.slide = slide; d.slide_h = slide_h; d.coords = coords; d.probs_out = probs_out;
+  if (slide_w < m->patch || slide_h < m->patch)
+    return fail("raster %lld x %lld is smaller than the %d-pixel patch", (long long)slide_w, (long long)slide_h, m->patch);
+  d.slide = slide; d.slide_h = slide_h; d.slide_w = slide_w; d.coords = coords; d.probs_out = probs_out;
   d.tta_in = tta_in; d.tta_out = tta_out;
   if (m->use_graph && !m->profile && !m->naive_conv) return run_graph(m, n_tiles, d, stream);
   return run_range(m, n_tiles, 0, (int)m->ops.size(), d, stream);
@@ -1549,7 +1556,7 @@ int dp_stitch(const float* probs, int n_pass, int n_tiles, int patch, const int3
   if (n_tiles > 4096) return fail("at most 4096 tiles per stitch call");
   dim3 grid((patch * patch + 255) / 256, n_tiles);
   dp::stitch_kernel<<<grid, 256, 2 * n_tiles * sizeof(int), st>>>(
-      probs, n_pass, n_tiles, patch, coords, mean, var, count, plane_h, (int)x_lo);
+      probs, n_pass, n_tiles, patch, coords, mean, var, count, plane_w, plane_h, (int)x_lo);
   LAUNCH_OK();
   return 0;
 }
@@ -1573,6 +1580,39 @@ int dp_pyramid_down2(const float* in, int64_t w, int64_t h, float* out, void* st
   if (w < 2 || h < 2) return fail("plane too small");
   dp::pyramid_down2_kernel<<<grid_for((w / 2) * (h / 2), 256), 256, 0, st>>>(in, w, h,
                                                                                                           out);
+  LAUNCH_OK();
+  return 0;
+}
+
+int dp_tissue_hist(const uint8_t* rgb, int64_t n_pix, uint32_t* hist, void* stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (!rgb || !hist) return fail("null argument");
+  if (n_pix < 1) return fail("empty image");
+  CU_OK(cudaMemsetAsync(hist, 0, dp::kTissueHistBins * sizeof(uint32_t), st));
+  dp::tissue_hist_kernel<<<grid_for(n_pix, 256), 256, 0, st>>>(rgb, n_pix, hist);
+  LAUNCH_OK();
+  return 0;
+}
+
+int dp_tissue_mask(const uint8_t* rgb, int64_t n_pix, int thr_r, int thr_g, int thr_b, int rgb_min,
+                   const uint8_t* sat_lut, uint8_t* mask, void* stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (!rgb || !sat_lut || !mask) return fail("null argument");
+  if (n_pix < 1) return fail("empty image");
+  dp::tissue_mask_kernel<<<grid_for(n_pix, 256), 256, 0, st>>>(rgb, n_pix, thr_r, thr_g, thr_b, rgb_min, sat_lut, mask);
+  LAUNCH_OK();
+  return 0;
+}
+
+int dp_morph_rect(const uint8_t* in, uint8_t* out, uint8_t* tmp, int n0, int n1, int k, int dilate, void* stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (!in || !out || !tmp) return fail("null argument");
+  if (n0 < 1 || n1 < 1 || k < 1) return fail("bad morphology geometry");
+  if (tmp == in || tmp == out) return fail("tmp must not alias in / out");
+  const long long total = (long long)n0 * n1;
+  dp::morph_line_kernel<<<grid_for(total, 256), 256, 0, st>>>(in, tmp, n0, n1, k, 1, dilate ? 1 : 0);
+  LAUNCH_OK();
+  dp::morph_line_kernel<<<grid_for(total, 256), 256, 0, st>>>(tmp, out, n0, n1, k, 0, dilate ? 1 : 0);
   LAUNCH_OK();
   return 0;
 }

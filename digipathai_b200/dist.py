@@ -133,51 +133,88 @@ def gather_planes(planes, stripes, rank: int, world_size: int, W: int, group=Non
 
 
 def local_part(slide, models, rank: int, world: int, batch_size=32, tta_list=None, patch_size=256, stride_size=128,
-               status=None, device=None, tissue_mask=None):
+               status=None, device=None, tissue_mask=None, grid=None, timings=None):
     """One rank's share before the halo exchange: ``(grid, [mean, var, count] partial-sum planes over this rank's
-    stripe, stripes of all ranks, (b_lo, b_hi))``.  The grid is built once here and handed to ``get_prediction``
-    as is (``tissue_mask`` is a RAW mask, see TileGrid)."""
+    stripe, stripes of all ranks, (b_lo, b_hi))``.  The grid is built once here (or handed in) and passed to
+    ``get_prediction`` as is (``tissue_mask`` is a RAW mask, see TileGrid).  A rank whose batch range is empty
+    (more ranks than batches) holds zero-width planes and never touches the raster."""
+    import time
+    import torch
     from .Segmentation import get_prediction
     from .tissue import TileGrid
-    grid = TileGrid(slide, patch_size, stride_size, batch_size, True, tissue_mask)
+    t0 = time.perf_counter()
+    if grid is None:
+        grid = TileGrid(slide, patch_size, stride_size, batch_size, True, tissue_mask, device=device)
+    if timings is not None:
+        timings['grid_ms'] = (time.perf_counter() - t0) * 1e3
     parts, stripes = stripes_for(grid.coords, batch_size, world, patch_size)
     lo, hi = parts[rank]
+    if hi <= lo:
+        H = slide.level_dimensions[0][1]
+        dev = torch.device("cuda", device if device is not None else torch.cuda.current_device())
+        planes = [torch.zeros((0, H), dtype=dt, device=dev) for dt in (torch.float32, torch.float32, torch.uint8)]
+        return grid, planes, stripes, (lo, hi)
     _, out = get_prediction(slide, batch_size=batch_size, models=models, tta_list=tta_list,
                             patch_size=patch_size, stride_size=stride_size, status=status, device=device,
                             tile_range=(lo * batch_size, hi * batch_size), return_device=True, finalize=False,
-                            grid=grid)
-    if hi > lo and tuple(out['x_range']) != tuple(stripes[rank]):
+                            grid=grid, timings=timings)
+    if tuple(out['x_range']) != tuple(stripes[rank]):
         # mismatched geometry would turn into mismatched P2P sizes in halo_exchange, i.e. a hang: fail here instead
         raise RuntimeError(f"rank {rank}: planes cover x {out['x_range']}, stripe plan says {stripes[rank]}")
     return grid, [out['mean'], out['var'], out['count']], stripes, (lo, hi)
 
 
 def sharded_get_prediction(wsi_path, models, batch_size=32, tta_list=None, patch_size=256, stride_size=128,
-                           status=None, device=None, gather=False, tissue_mask=None):
-    """``get_prediction`` across the ranks of the default process group (one process per GPU).
+                           status=None, device=None, gather=False, tissue_mask=None, shard=None):
+    """``get_prediction`` across the ranks of the default process group (one process per GPU; a process without an
+    initialised group is a world of one; ``shard=(rank, world)`` overrides both -- ``shard=(0, 1)`` runs the whole
+    slide on the calling rank alone, which is how bench.py measures the one-GPU time beside an N-GPU run).
 
-    Every rank computes the same tile grid (cheap, deterministic), takes its contiguous range of batches, runs
-    the device loop on its stripe, swaps halos, then normalises its stripe.  Returns
-    ``(grid, planes_dict, info)``; with ``gather=True`` rank 0's dict holds the full planes.
+    Every rank computes the same tile grid (deterministic; on the GPU when the slide's raster is resident there),
+    takes its contiguous range of batches, runs the device loop on its stripe, swaps halos, then normalises its
+    stripe.  Returns ``(grid, planes_dict, info)``; with ``gather=True`` rank 0's dict holds the full planes.
+    ``info['timings_ms']`` splits this rank's wall time into grid / raster upload / tile loop / halo / normalise
+    (each phase ends with a device synchronisation).
     """
+    import time
     import torch
     import torch.distributed as dist
     from . import engine
     from .slide import open_slide
-    rank, world = dist.get_rank(), dist.get_world_size()
+    if shard is not None:
+        rank, world = int(shard[0]), int(shard[1])
+    elif dist.is_available() and dist.is_initialized():
+        rank, world = dist.get_rank(), dist.get_world_size()
+    else:
+        rank, world = 0, 1
     if device is None:
         device = torch.cuda.current_device()
     slide = open_slide(wsi_path)
+    tm = {}
     grid, planes, stripes, (lo, hi) = local_part(slide, models, rank, world, batch_size, tta_list, patch_size,
-                                                 stride_size, status, device, tissue_mask)
-    sent = halo_exchange(planes, stripes, rank) if hi > lo else 0
-    with torch.cuda.device(planes[0].device):
-        engine.finalize(planes[0], planes[1], planes[2], 0.0, None)
-    info = {'rank': rank, 'world': world, 'batches': (lo, hi), 'stripe': stripes[rank], 'halo_bytes_sent': sent}
+                                                 stride_size, status, device, tissue_mask, timings=tm)
+    t0 = time.perf_counter()
+    sent = halo_exchange(planes, stripes, rank) if (hi > lo and world > 1) else 0
+    if hi > lo:
+        torch.cuda.synchronize(planes[0].device)
+    tm['halo_ms'] = (time.perf_counter() - t0) * 1e3
+    t0 = time.perf_counter()
+    if hi > lo:
+        with torch.cuda.device(planes[0].device):
+            engine.finalize(planes[0], planes[1], planes[2], 0.0, None)
+            torch.cuda.synchronize()
+    tm['normalise_ms'] = (time.perf_counter() - t0) * 1e3
+    info = {'rank': rank, 'world': world, 'batches': (lo, hi), 'stripe': stripes[rank], 'halo_bytes_sent': sent,
+            'timings_ms': tm}
     res = {'mean': planes[0], 'var': planes[1], 'x_range': stripes[rank]}
     if gather:
         W = slide.level_dimensions[0][0]
-        full = gather_planes(planes[:2], stripes, rank, world, W)
+        full = gather_planes(planes[:2], stripes, rank, world, W) if world > 1 else planes[:2]
         if rank == 0:
+            if world == 1 and tuple(stripes[0]) != (0, W):      # a world of one still owns only its stripe
+                a, b = stripes[0]
+                full = [torch.zeros((W,) + tuple(p.shape[1:]), dtype=p.dtype, device=p.device) for p in planes[:2]]
+                for f, p in zip(full, planes[:2]):
+                    f[a:b] = p
             res = {'mean': full[0], 'var': full[1], 'x_range': (0, W)}
     return grid, res, info

@@ -1,4 +1,11 @@
-"""Tissue mask and tile grid: the host-side prologue of the hot path (one-off per slide, CPU).
+"""Tissue mask and tile grid: the prologue of the hot path (one-off per slide).
+
+Two evaluations of the same arithmetic: the host one (numpy + OpenCV, this module's original) and -- when a CUDA
+device is named -- the device one (``tissue_mask_device`` / ``morpho_process_device``: histogram, mask and
+rectangular min/max kernels of csrc/tissue.cuh through the C ABI), bit-identical to each other
+(tests/test_gpu_tissue.py) and, for the morphology, to the reference's own cv2 calls (tests/golden/morph_golden.npz).
+On a sharded run every rank needs the grid before it can start; on the device it costs a few milliseconds instead of
+~0.2 s of host time per rank.
 
 Mirrors ``TissueMaskGenerationOS`` (DigiPathAI/helpers/utils.py:336-354), ``BinMorphoProcessMaskOS``
 (utils.py:200-219) and ``WSIStridedPatchDataset._preprocess`` / ``__getitem__`` coordinate logic
@@ -79,6 +86,101 @@ def _otsu_from_hist(hist: np.ndarray, centers: np.ndarray) -> float:
     return float(centers[:-1][int(np.argmax(var12))])
 
 
+def _saturation_lut():
+    """float64 saturation of every (max, max - min) pair of a uint8 RGB pixel: ``(max/255 - min/255) / (max/255)``,
+    the literal expression of skimage's rgb2hsv on the [0, 1]-scaled image (utils.py:339), 0 where max == min."""
+    vv, dd = np.divmod(np.arange(65536), 256)
+    mn = vv - dd                                  # negative for impossible pairs (never present in a histogram)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        lut = (vv / 255.0 - mn / 255.0) / (vv / 255.0)
+    lut[dd == 0] = 0.0
+    lut[np.isnan(lut)] = 0.0
+    return lut
+
+
+def _saturation_threshold_table(joint: np.ndarray) -> np.ndarray:
+    """bool [65536] table ``S > otsu(S)`` from the joint (max, max - min) histogram (int64 [65536])."""
+    lut = _saturation_lut()
+    present = joint > 0
+    lo, hi = lut[present].min(), lut[present].max()
+    if lo == hi:
+        raise ValueError("threshold_otsu is expected to work with images having more than one color")
+    hist, edges = np.histogram(lut[present], bins=256, range=(lo, hi), weights=joint[present])
+    thr = _otsu_from_hist(hist, (edges[:-1] + edges[1:]) / 2.0)
+    return lut > thr
+
+
+def _otsu_u8_from_full_hist(full: np.ndarray) -> float:
+    present = np.flatnonzero(full)
+    lo, hi = int(present[0]), int(present[-1])
+    if lo == hi:
+        raise ValueError("threshold_otsu is expected to work with images having more than one color")
+    return _otsu_from_hist(full[lo:hi + 1], np.arange(lo, hi + 1, dtype=np.float64))
+
+
+def tissue_mask_device(rgb_dev, rgb_min: int = 50):
+    """``tissue_mask`` for a level image already in HBM: ``rgb_dev`` cuda uint8 [a, b, 3] (any orientation) ->
+    cuda uint8 [a, b] in {0, 1}.  Histograms and the mask run on the device (csrc/tissue.cuh); the four Otsu
+    thresholds are derived on the host from 66 k counters with the same float64 code as the host path."""
+    import ctypes as C
+    import torch
+    from . import _lib
+    assert rgb_dev.is_cuda and rgb_dev.dtype == torch.uint8 and rgb_dev.dim() == 3 and rgb_dev.shape[2] == 3
+    rgb_dev = rgb_dev.contiguous()
+    n_pix = rgb_dev.shape[0] * rgb_dev.shape[1]
+    st = C.c_void_p(torch.cuda.current_stream(rgb_dev.device).cuda_stream)
+    with torch.cuda.device(rgb_dev.device):
+        hist = torch.empty(768 + 65536, dtype=torch.int32, device=rgb_dev.device)
+        _lib.check(_lib.lib.dp_tissue_hist(C.c_void_p(rgb_dev.data_ptr()), n_pix, C.c_void_p(hist.data_ptr()), st),
+                   "dp_tissue_hist")
+        h = hist.cpu().numpy().astype(np.int64)
+        thr = [int(_otsu_u8_from_full_hist(h[256 * c:256 * (c + 1)])) for c in range(3)]   # integer bin centres
+        table = torch.from_numpy(_saturation_threshold_table(h[768:]).astype(np.uint8)).to(rgb_dev.device)
+        mask = torch.empty(rgb_dev.shape[:2], dtype=torch.uint8, device=rgb_dev.device)
+        _lib.check(_lib.lib.dp_tissue_mask(C.c_void_p(rgb_dev.data_ptr()), n_pix, thr[0], thr[1], thr[2], int(rgb_min),
+                                           C.c_void_p(table.data_ptr()), C.c_void_p(mask.data_ptr()), st),
+                   "dp_tissue_mask")
+    return mask
+
+
+def morpho_process_device(mask_dev, level: int):
+    """``morpho_process`` on a cuda uint8 [a, b] mask: close 20, open 5, dilate 60 / 35 / 10 (utils.py:200-219)."""
+    import ctypes as C
+    import torch
+    from . import _lib
+    if level <= 2:
+        k_last = 60
+    elif level == 3:
+        k_last = 35
+    elif level == 4:
+        k_last = 10
+    else:
+        print(level)
+        raise ValueError("Kernel for this level not fixed")
+    assert mask_dev.is_cuda and mask_dev.dtype == torch.uint8 and mask_dev.dim() == 2
+    m = mask_dev.contiguous().clone()
+    tmp = torch.empty_like(m)
+    st = C.c_void_p(torch.cuda.current_stream(m.device).cuda_stream)
+    n0, n1 = m.shape
+    with torch.cuda.device(m.device):
+        for k, dil in ((20, 1), (20, 0), (5, 0), (5, 1), (k_last, 1)):      # close = dilate, erode; open = erode, dilate
+            _lib.check(_lib.lib.dp_morph_rect(C.c_void_p(m.data_ptr()), C.c_void_p(m.data_ptr()),
+                                              C.c_void_p(tmp.data_ptr()), n0, n1, k, dil, st), "dp_morph_rect")
+    return m
+
+
+def _level_rgb_device(slide, level: int, device):
+    """Lowest-level RGB image as a cuda uint8 [x, y, 3] tensor, or None when the slide cannot provide one cheaply."""
+    import torch
+    from .slide import DeviceSlide
+    if isinstance(slide, DeviceSlide):
+        s = 2 ** int(level)
+        w, h = slide.level_dimensions[level]
+        dev = torch.device("cuda", device) if isinstance(device, int) else torch.device(device)
+        return slide.raster_xy[::s, ::s][:w, :h].contiguous().to(dev)
+    return None
+
+
 def tissue_mask(slide, level: int, rgb_min: int = 50) -> np.ndarray:
     """bool [x, y] mask at pyramid ``level`` (utils.py:336-354).
 
@@ -95,18 +197,7 @@ def tissue_mask(slide, level: int, rgb_min: int = 50) -> np.ndarray:
     delta = v - np.minimum(np.minimum(r, g), b)
     idx = v.astype(np.uint16) * 256 + delta
     joint = _hist_u8(v, delta)
-    vv, dd = np.divmod(np.arange(65536), 256)
-    with np.errstate(divide="ignore", invalid="ignore"):
-        lut = (dd / 255.0) / (vv / 255.0)        # identical float64 arithmetic to saturation()
-    lut[dd == 0] = 0.0
-    lut[np.isnan(lut)] = 0.0
-    present = joint > 0
-    lo, hi = lut[present].min(), lut[present].max()
-    if lo == hi:
-        raise ValueError("threshold_otsu is expected to work with images having more than one color")
-    hist, edges = np.histogram(lut[present], bins=256, range=(lo, hi), weights=joint[present])
-    thr = _otsu_from_hist(hist, (edges[:-1] + edges[1:]) / 2.0)
-    tissue_s = (lut > thr)[idx]
+    tissue_s = _saturation_threshold_table(joint)[idx]
     above = (r > rgb_min) & (g > rgb_min) & (b > rgb_min)
     return np.ascontiguousarray((tissue_s & ~bg & above).T)
 
@@ -153,7 +244,7 @@ class TileGrid:
     """
 
     def __init__(self, slide, patch_size: int = 256, stride_size: int = 128, batch_size: int = 32,
-                 roi_masking: bool = True, mask: np.ndarray | None = None):
+                 roi_masking: bool = True, mask: np.ndarray | None = None, device=None):
         self.slide = slide
         self.patch_size = int(patch_size)
         self.stride_size = int(stride_size)
@@ -162,10 +253,20 @@ class TileGrid:
         if self.factor < 1:
             raise ValueError("stride_size smaller than the mask level's downsample")
         X_slide, Y_slide = slide.level_dimensions[0]
-        if mask is None:
-            mask = tissue_mask(slide, self.level)
-        self.raw_mask = mask                                               # before morphology: what ``mask=`` takes
-        self.mask = morpho_process(np.uint8(mask), self.level)
+        strided_dev = None
+        rgb_dev = _level_rgb_device(slide, self.level, device) if (mask is None and device is not None) else None
+        if rgb_dev is not None:
+            # raster resident in HBM: histogram, mask, morphology and the stride sub-sampling on the device
+            raw_dev = tissue_mask_device(rgb_dev)
+            mask_dev = morpho_process_device(raw_dev, self.level)
+            self.raw_mask = raw_dev.cpu().numpy().astype(bool)
+            self.mask = mask_dev.cpu().numpy()
+            strided_dev = mask_dev
+        else:
+            if mask is None:
+                mask = tissue_mask(slide, self.level)
+            self.raw_mask = mask                                           # before morphology: what ``mask=`` takes
+            self.mask = morpho_process(np.uint8(mask), self.level)
         X_mask, Y_mask = self.mask.shape
         if X_slide // X_mask != Y_slide // Y_mask:
             raise Exception('Slide/Mask dimension does not match ,'
@@ -175,10 +276,15 @@ class TileGrid:
         if not np.log2(self.resolution).is_integer():
             raise Exception('Resolution (X_slide / X_mask) is not power of 2 :'
                             ' {}'.format(self.resolution))
-        ones = np.zeros_like(self.mask)
-        ones[::self.factor, ::self.factor] = 1
-        strided = ones * self.mask if roi_masking else ones
-        self.X_idcs, self.Y_idcs = np.where(strided)                       # x-major order (dataloader.py:311)
+        if strided_dev is not None and roi_masking:
+            import torch
+            nz = torch.nonzero(strided_dev[::self.factor, ::self.factor]).cpu().numpy()   # row-major = x-major order
+            self.X_idcs, self.Y_idcs = nz[:, 0] * self.factor, nz[:, 1] * self.factor
+        else:
+            ones = np.zeros_like(self.mask)
+            ones[::self.factor, ::self.factor] = 1
+            strided = ones * self.mask if roi_masking else ones
+            self.X_idcs, self.Y_idcs = np.where(strided)                   # x-major order (dataloader.py:311)
         P = self.patch_size
         x = np.trunc(self.X_idcs * self.resolution - P // 2).astype(np.int64)   # int(...) of dataloader.py:348-349
         y = np.trunc(self.Y_idcs * self.resolution - P // 2).astype(np.int64)

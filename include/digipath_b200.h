@@ -156,6 +156,27 @@ int dp_debug_read_stamps(dp_model* m, unsigned long long* out, int n);
 int dp_model_executed_macs(const dp_model* m, int n_tiles, uint64_t* macs);
 
 /*
+ * Replaces TissueMaskGenerationOS                                  DigiPathAI/helpers/utils.py:336-354
+ * (the part that touches pixels).  `rgb` is the slide's lowest pyramid level, device uint8 [n_pix][3].
+ * dp_tissue_hist fills `hist` (device uint32 [768 + 65536]): the 256-bin histograms of R, G and B followed by the
+ * joint 256 x 256 histogram of (max(R,G,B), max - min), row = max.  The caller derives the four Otsu thresholds from
+ * them on the host (256-bin float64 arithmetic, skimage.filters.threshold_otsu) and calls dp_tissue_mask with the
+ * three channel thresholds, the `> 50` floor and a 65 536-entry table `sat_lut[max * 256 + (max - min)]` = 1 where the
+ * HSV saturation (max-min)/max exceeds its threshold.  mask (device uint8 [n_pix]) = 1 for tissue, else 0.
+ */
+int dp_tissue_hist(const uint8_t* rgb, int64_t n_pix, uint32_t* hist, void* stream);
+int dp_tissue_mask(const uint8_t* rgb, int64_t n_pix, int thr_r, int thr_g, int thr_b, int rgb_min,
+                   const uint8_t* sat_lut, uint8_t* mask, void* stream);
+
+/*
+ * Replaces cv2.dilate / cv2.erode with a k x k rectangular kernel (np.ones((k, k))), the building block of
+ * BinMorphoProcessMaskOS                                           DigiPathAI/helpers/utils.py:200-219
+ * (close 20 = dilate, erode; open 5 = erode, dilate; dilate 60 / 35 / 10).  in / out / tmp: device uint8 [n0][n1];
+ * OpenCV's default anchor (k/2) and border rule (cells outside the image are ignored); out may alias in.
+ */
+int dp_morph_rect(const uint8_t* in, uint8_t* out, uint8_t* tmp, int n0, int n1, int k, int dilate, void* stream);
+
+/*
  * Fully connected CRF refinement of probability tiles -- replaces `post_process_crf(image, probs, 2)`
  * (DigiPathAI/helpers/utils.py:568-603: pydensecrf DenseCRF, unary_from_softmax(clip=1e-5), Gaussian pairwise
  * sdims (10,10) compat 3, bilateral sdims (50,50) schan (20,20,20) compat 10, DIAG_KERNEL, NORMALIZE_SYMMETRIC,

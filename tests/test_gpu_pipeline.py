@@ -28,9 +28,9 @@ def test_get_prediction_matches_oracle_pipeline(env):
     touched = want['count'] > 0
     print(f"\nget_prediction: max|mean-oracle| {d.max():.3e} mean {d[touched].mean():.3e}; "
           f"max|var-oracle| {np.abs(got['var'] - want['var']).max():.3e}")
-    # fp16 mode: the per-tile bound of test_gpu_forward.py (1.5 x measured) carries over to the stitched mean
-    assert d.max() <= 3.3e-2 and d[touched].mean() <= 3.3e-3
-    assert np.abs(got['var'] - want['var']).max() <= 1e-2
+    # fp16 mode, 1.5 x measured on the B200 (2.6e-2 max / 8.3e-4 mean on the stitched mean, 1.0e-2 on the variance)
+    assert d.max() <= 3.9e-2 and d[touched].mean() <= 1.3e-3
+    assert np.abs(got['var'] - want['var']).max() <= 1.5e-2
     # pixels no tile touched stay exactly zero on both sides; zero pattern of the planes is identical
     zero_w, zero_g = want['mean'] == 0, got['mean'] == 0
     assert np.array_equal(zero_w, zero_g)
@@ -96,8 +96,9 @@ def test_ensemble_dense_plus_inception_matches_oracle_pipeline(env):
     touched = want['count'] > 0
     print(f"\nensemble get_prediction: max|mean-oracle| {d.max():.3e} mean {d[touched].mean():.3e}; "
           f"max|var-oracle| {np.abs(got['var'] - want['var']).max():.3e}")
-    assert d.max() <= 1e-1 and d[touched].mean() <= 1.5e-2
-    assert np.abs(got['var'] - want['var']).max() <= 5e-2
+    # fp16 mode, 1.5 x measured (1.3e-2 max / 2.6e-4 mean; variance 5.8e-3)
+    assert d.max() <= 2e-2 and d[touched].mean() <= 4e-4
+    assert np.abs(got['var'] - want['var']).max() <= 9e-3
     assert np.array_equal(want['mean'] == 0, got['mean'] == 0)
     for m in models.values():
         m.close()
