@@ -23,14 +23,10 @@
 // Cross-layer overlap: only the activation producer executes griddepcontrol.wait, and only before the first
 // chunk that contains the preceding layer's 32 new channels; older chunks are consumed while that layer runs.
 //
-// STACK variant (template flag, off by default; planner: DP_DL_STACK -- NOT YET RUN ON A GPU): an N = 32 MMA costs
-// ~46 clk (the 4 KB A-operand read) for 16 clk of math, and phase 2 issues 72 of them per item.  With STACK the
-// three dy taps of one dx are stacked along N (B = [W(-1,dx); W(0,dx); W(+1,dx)], N = 96): 24 MMAs per item whose
-// A rows are ALL halo rows of the region (row offset dx only), accumulating D'[(hr, x)][32 j + co] =
-// sum_dx,k T[hr][x + 1 + dx][k] W(j - 1, dx)[co][k].  The final epilogue then forms
-//   out[y][x] = D'[(y, x)][0:32] + D'[(y + 1, x)][32:64] + D'[(y + 2, x)][64:96],
-// i.e. TMEM lanes r, r + 8, r + 16: warp shuffles plus an 8 / 16-lane exchange with the next warp through shared
-// memory.  Needs (RH + 2) * 8 <= 128 accumulator rows: RH = 8 or RH = 14 (16 halo rows = exactly one M block).
+// Tried and removed (round 2): a STACK variant that stacked the three dy taps of one dx along N (N = 96, 24 MMAs per
+// item instead of 72) and recombined the row-shifted accumulator groups in the final epilogue.  It ran correctly on
+// the B200 but did not shorten the step (17 075 vs 17 147 tiles/s with 8-row regions, 16 089 with 14-row regions:
+// profiles/r2_bench_stack*.json) -- the item period is set by the ph1 -> mid -> ph1 loop, not by phase 2.
 //
 // Warp roles: 0 = TMA producer (activation halo chunks), 1 = MMA issuer, 2 = TMEM allocator, 3 = TMA producer
 // (W1 chunks / W2 tap groups, one ring, in MMA order), 4-7 and 16-19 = epilogue (mid + final), 8-15 =
@@ -61,9 +57,7 @@ struct DenseLayerParams {
   int tiles_w, tiles_h, n_items;
   int n_safe_chunks;         // leading channel chunks not written by the immediately preceding kernel: they are
                              // consumed BEFORE griddepcontrol.wait, i.e. while the previous layer still runs
-  int rh;                    // region height: 16 (180 halo rows, 2 M-blocks) or 8 (100 halo rows, 1 M-block);
-                             // 14 (160 halo rows) only with `stack`
-  int stack;                 // 1: phase 2 with the dy taps stacked along N (see header); 0: nine N = 32 taps
+  int rh;                    // region height: 16 (180 halo rows, 2 M-blocks) or 8 (100 halo rows, 1 M-block)
   int a_stages, b_stages;
   int out_ctot, out_choff;   // concat buffer channel stride, offset of the 32 new channels
   const float* pro_scale;    // BN1 [n_chunks * 64]
@@ -76,8 +70,7 @@ struct DenseLayerParams {
 
 struct DenseLayerSmem {
   static constexpr int kBarBytes = 1024;
-  static constexpr int kXchBytes = 8 * 24 * 16 * 4;   // STACK: per epilogue warp, 8 + 16 lanes x 16 fp32 columns
-  int a_off, b_off, t_off, pro_off, mid_off, xch_off, total;
+  int a_off, b_off, t_off, pro_off, mid_off, total;
 };
 
 __host__ __device__ inline DenseLayerSmem dense_layer_smem(const DenseLayerParams& p) {
@@ -87,8 +80,7 @@ __host__ __device__ inline DenseLayerSmem dense_layer_smem(const DenseLayerParam
   L.b_off = L.a_off + p.a_stages * dl_a_stage(p.rh);
   L.pro_off = L.b_off + p.b_stages * kDlBStage;
   L.mid_off = L.pro_off + 2 * p.n_chunks * 64 * 4;
-  L.xch_off = L.mid_off + 128 * 4;
-  L.total = L.xch_off + (p.stack ? DenseLayerSmem::kXchBytes : 0) + 1024;
+  L.total = L.mid_off + 128 * 4 + 1024;
   return L;
 }
 
@@ -110,14 +102,13 @@ __device__ __forceinline__ void dl_trace_close(unsigned long long* trace, const 
   if (c.base) trace[role] = c.n;
 }
 
-template <int RH, bool STACK = false>
+template <int RH>
 __global__ void __launch_bounds__(640, 1)
 dense_layer_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w1,
                    const __grid_constant__ CUtensorMap map_w2, const __grid_constant__ DenseLayerParams p) {
   constexpr int kRows = dl_rows(RH), kMBlk = (kRows + 127) / 128, kAStage = dl_a_stage(RH);
   constexpr int kDlTChunk = dl_t_chunk(RH), kDlTBuf = 2 * kDlTChunk;
-  constexpr int kAcc2Cols = STACK ? 96 : 32;       // accumulator columns of one 3x3 buffer
-  static_assert(!STACK || (RH + 2) * 8 <= 128, "stacked phase 2 needs every halo row of the region in one M block");
+  constexpr int kAcc2Cols = 32;                    // accumulator columns of one 3x3 buffer
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
@@ -194,7 +185,7 @@ dense_layer_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
   const uint32_t tmem_base = *tmem_slot;
   if (tid == 0 && p.trace && blockIdx.x == 0) { p.trace[8 + 2000 * 4] = clock64() & 0xFFFFFFFFull; p.trace[4] = 2; }
   const uint32_t acc1_col = tmem_base;        // kMBlk x 128 columns
-  const uint32_t acc2_col = tmem_base + 256;  // 2 x 32 columns (2 x 96 when STACK)
+  const uint32_t acc2_col = tmem_base + 256;  // 2 x 32 columns
   const int first = blockIdx.x;
   const int n_local = (first < p.n_items) ? (p.n_items - first + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x) : 0;
 
@@ -251,13 +242,7 @@ dense_layer_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
           for (int g = 0; g < 9 / kDlW2Group; ++g) {
             mbar_wait(&b_empty[sb], pb ^ 1);
             mbar_expect_tx(&b_full[sb], kDlW2Group * 32 * 128);
-            if constexpr (STACK) {
-              // group = dx; rows 32 j .. 32 j + 31 of the stage = tap (dy = j, dx = g); map_w2's box holds one tap
-              for (int j = 0; j < 3; ++j)
-                tma_load_3d(&map_w2, &b_full[sb], b_base + sb * kDlBStage + j * 32 * 128, c * 64, 0, j * 3 + g);
-            } else {
-              tma_load_3d(&map_w2, &b_full[sb], b_base + sb * kDlBStage, c * 64, 0, g * kDlW2Group);
-            }
+            tma_load_3d(&map_w2, &b_full[sb], b_base + sb * kDlBStage, c * 64, 0, g * kDlW2Group);
             if (++sb == p.b_stages) { sb = 0; pb ^= 1; }
           }
       };
@@ -328,17 +313,11 @@ dense_layer_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
             mbar_wait(&b_full[sb], pb);
             tc_fence_after();
             uint64_t b_desc = b_desc0 + sb * (kDlBStage >> 4);
-            if constexpr (STACK) {
-              // one N = 96 MMA set per dx: A = all halo rows (8-row groups at a 10-row stride from halo row 0),
-              // columns x + g; the stage holds [W(dy=0,g); W(dy=1,g); W(dy=2,g)] as one 96-row K-major tile
-              umma_f16_ss_k4(d2, t_desc + g * 8, b_desc, idesc2, (c | g) ? 1u : 0u);
-            } else {
 #pragma unroll
-              for (int j = 0; j < kDlW2Group; ++j, b_desc += (32 * 128) >> 4) {
-                const int tap = g * kDlW2Group + j;
-                const int dy = tap / 3, dx = tap - dy * 3;  // (dy+1, dx+1) with dy,dx in -1..1
-                umma_f16_ss_k4(d2, t_desc + (dy * kDlHaloW + dx) * 8, b_desc, idesc2, (c | tap) ? 1u : 0u);
-              }
+            for (int j = 0; j < kDlW2Group; ++j, b_desc += (32 * 128) >> 4) {
+              const int tap = g * kDlW2Group + j;
+              const int dy = tap / 3, dx = tap - dy * 3;  // (dy+1, dx+1) with dy,dx in -1..1
+              umma_f16_ss_k4(d2, t_desc + (dy * kDlHaloW + dx) * 8, b_desc, idesc2, (c | tap) ? 1u : 0u);
             }
             umma_commit(&b_empty[sb]);
             if (++sb == p.b_stages) { sb = 0; pb ^= 1; }
@@ -443,43 +422,7 @@ dense_layer_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
       uint32_t v[16];
       const uint32_t taddr = acc2_col + tb * kAcc2Cols + half * 16 + (static_cast<uint32_t>(q * 32) << 16);
       tmem_ld16(taddr, v);
-      if constexpr (STACK) {
-        // out[row r] = D'[r][0:32] + D'[r + 8][32:64] + D'[r + 16][64:96] (this half: 16 of the 32 columns)
-        uint32_t v1[16], v2[16];
-        tmem_ld16(taddr + 32, v1);
-        tmem_ld16(taddr + 64, v2);
-        tmem_ld_wait();
-        float* xch = reinterpret_cast<float*>(smem + L.xch_off);
-        float* mine = xch + (half * 4 + q) * 24 * 16;         // lanes 0-7 of v1, then lanes 0-15 of v2
-        const float* next = mine + 24 * 16;                   // the same slots of warp q + 1 (rows r + 32)
-        auto group_sync = [&]() {                             // the four warps of this half (named barrier 1 / 2)
-          if (half) asm volatile("bar.sync 2, 128;" ::: "memory");
-          else asm volatile("bar.sync 1, 128;" ::: "memory");
-        };
-        group_sync();                                         // fin(k - 1)'s reads are done
-        if (lane < 8) {
-#pragma unroll
-          for (int i = 0; i < 16; i += 4)
-            *reinterpret_cast<uint4*>(mine + lane * 16 + i) = make_uint4(v1[i], v1[i + 1], v1[i + 2], v1[i + 3]);
-        }
-        if (lane < 16) {
-#pragma unroll
-          for (int i = 0; i < 16; i += 4)
-            *reinterpret_cast<uint4*>(mine + (8 + lane) * 16 + i) = make_uint4(v2[i], v2[i + 1], v2[i + 2], v2[i + 3]);
-        }
-        group_sync();
-        const bool nxt = q < 3;                               // rows >= 128 do not exist (and are never valid)
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          float a1 = __shfl_down_sync(0xffffffffu, __uint_as_float(v1[i]), 8);
-          float a2 = __shfl_down_sync(0xffffffffu, __uint_as_float(v2[i]), 16);
-          if (lane >= 24) a1 = nxt ? next[(lane - 24) * 16 + i] : 0.f;
-          if (lane >= 16) a2 = nxt ? next[(8 + lane - 16) * 16 + i] : 0.f;
-          v[i] = __float_as_uint(__uint_as_float(v[i]) + a1 + a2);
-        }
-      } else {
-        tmem_ld_wait();
-      }
+      tmem_ld_wait();
       {
         uint32_t pk[8];
 #pragma unroll

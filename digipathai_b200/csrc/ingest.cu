@@ -1,6 +1,9 @@
 // libdigipath_ingest.so: nvJPEG batch decode of whole-slide-image tiles + scatter into the [x][y][c] raster
-// (C ABI in include/digipath_ingest.h).  NOT YET RUN ON A GPU (written after round 1's GPU budget
-// was spent): tests/test_gpu_wsi_ingest.py is its parity test against Pillow's decode of the same streams.
+// (C ABI in include/digipath_ingest.h).  tests/test_gpu_wsi_ingest.py is its parity test against
+// Pillow's (libjpeg) decode of the same streams.  First hardware run (round 2): streams whose three components ARE
+// R, G, B (TIFF photometric = RGB, what libtiff writes for RGB input) came back colour-transformed -- nvJPEG applies the
+// YCbCr -> RGB matrix to any 3-component stream and ignores the Adobe APP14 "no transform" flag libjpeg honours -- so
+// such pages are decoded with NVJPEG_OUTPUT_UNCHANGED (component planes as stored) and interleaved by a kernel here.
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -63,6 +66,20 @@ __global__ void __launch_bounds__(256) scatter_tiles_xy_kernel(const uint8_t* __
   }
 }
 
+// planes uint8 [n][3][h][w] -> interleaved uint8 [n][h][w][3]; one thread per pixel.
+__global__ void interleave_planes_kernel(const uint8_t* __restrict__ planes, uint8_t* __restrict__ rgb, long long n_pix_tile,
+                                         long long total) {
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long t = i / n_pix_tile, p = i - t * n_pix_tile;
+    const uint8_t* src = planes + t * 3 * n_pix_tile + p;
+    uint8_t* dst = rgb + i * 3;
+    dst[0] = src[0];
+    dst[1] = src[n_pix_tile];
+    dst[2] = src[2 * n_pix_tile];
+  }
+}
+
 }  // namespace
 
 struct dp_jpeg_decoder {
@@ -70,6 +87,9 @@ struct dp_jpeg_decoder {
   nvjpegHandle_t handle = nullptr;
   nvjpegJpegState_t state = nullptr;
   int batch_ready = 0;   // batch size nvjpegDecodeBatchedInitialize was last called with
+  int fmt_ready = -1;    // ... and output format
+  uint8_t* planes = nullptr;   // scratch for NVJPEG_OUTPUT_UNCHANGED decodes
+  size_t planes_bytes = 0;
 };
 
 extern "C" {
@@ -98,17 +118,25 @@ int dp_jpeg_decoder_destroy(dp_jpeg_decoder* d) {
   if (!d) return 0;
   if (d->state) nvjpegJpegStateDestroy(d->state);
   if (d->handle) nvjpegDestroy(d->handle);
+  if (d->planes) cudaFree(d->planes);
   delete d;
   return 0;
 }
 
-int dp_jpeg_decode_tiles(dp_jpeg_decoder* d, const uint8_t* const* streams, const size_t* lengths, int n, int tile_w,
-                         int tile_h, uint8_t* out_rgb, void* stream) {
+int dp_jpeg_decode_tiles_ex(dp_jpeg_decoder* d, const uint8_t* const* streams, const size_t* lengths, int n, int tile_w,
+                            int tile_h, uint8_t* out_rgb, int components_are_rgb, void* stream) {
   if (!d || !streams || !lengths || !out_rgb) return fail("null argument");
   if (n < 1 || tile_w < 1 || tile_h < 1) return fail("bad tile geometry");
   CU_OK(cudaSetDevice(d->device));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
   std::vector<nvjpegImage_t> dst(n);
-  const size_t slot = static_cast<size_t>(tile_w) * tile_h * 3;
+  const size_t npix = static_cast<size_t>(tile_w) * tile_h, slot = npix * 3;
+  if (components_are_rgb && d->planes_bytes < slot * n) {
+    if (d->planes) { CU_OK(cudaStreamSynchronize(st)); CU_OK(cudaFree(d->planes)); d->planes = nullptr; }
+    CU_OK(cudaMalloc(&d->planes, slot * n));
+    d->planes_bytes = slot * n;
+  }
+  if (components_are_rgb) CU_OK(cudaMemsetAsync(d->planes, 0, slot * n, st));
   for (int i = 0; i < n; ++i) {
     int comps = 0, w[NVJPEG_MAX_COMPONENT] = {0}, h[NVJPEG_MAX_COMPONENT] = {0};
     nvjpegChromaSubsampling_t ss;
@@ -116,15 +144,37 @@ int dp_jpeg_decode_tiles(dp_jpeg_decoder* d, const uint8_t* const* streams, cons
     if (comps != 1 && comps != 3) return fail("stream %d has %d components (1 or 3 supported)", i, comps);
     if (w[0] > tile_w || h[0] > tile_h) return fail("stream %d is %d x %d, larger than the %d x %d tile", i, w[0], h[0], tile_w, tile_h);
     memset(&dst[i], 0, sizeof(nvjpegImage_t));
-    dst[i].channel[0] = out_rgb + slot * i;
-    dst[i].pitch[0] = static_cast<size_t>(tile_w) * 3;
+    if (components_are_rgb) {
+      if (comps != 3 || ss != NVJPEG_CSS_444)
+        return fail("stream %d: RGB-component pages must hold three full-resolution components", i);
+      for (int c = 0; c < 3; ++c) {
+        dst[i].channel[c] = d->planes + slot * i + npix * c;
+        dst[i].pitch[c] = static_cast<size_t>(tile_w);
+      }
+    } else {
+      dst[i].channel[0] = out_rgb + slot * i;
+      dst[i].pitch[0] = static_cast<size_t>(tile_w) * 3;
+    }
   }
-  if (d->batch_ready != n) {
-    NJ_OK(nvjpegDecodeBatchedInitialize(d->handle, d->state, n, 1, NVJPEG_OUTPUT_RGBI));
+  const nvjpegOutputFormat_t fmt = components_are_rgb ? NVJPEG_OUTPUT_UNCHANGED : NVJPEG_OUTPUT_RGBI;
+  if (d->batch_ready != n || d->fmt_ready != (int)fmt) {
+    NJ_OK(nvjpegDecodeBatchedInitialize(d->handle, d->state, n, 1, fmt));
     d->batch_ready = n;
+    d->fmt_ready = (int)fmt;
   }
-  NJ_OK(nvjpegDecodeBatched(d->handle, d->state, streams, lengths, dst.data(), static_cast<cudaStream_t>(stream)));
+  NJ_OK(nvjpegDecodeBatched(d->handle, d->state, streams, lengths, dst.data(), st));
+  if (components_are_rgb) {
+    const long long total = static_cast<long long>(npix) * n;
+    const int grid = static_cast<int>(total / 256 + 1 > 148 * 32 ? 148 * 32 : total / 256 + 1);
+    interleave_planes_kernel<<<grid, 256, 0, st>>>(d->planes, out_rgb, static_cast<long long>(npix), total);
+    CU_OK(cudaGetLastError());
+  }
   return 0;
+}
+
+int dp_jpeg_decode_tiles(dp_jpeg_decoder* d, const uint8_t* const* streams, const size_t* lengths, int n, int tile_w,
+                         int tile_h, uint8_t* out_rgb, void* stream) {
+  return dp_jpeg_decode_tiles_ex(d, streams, lengths, n, tile_w, tile_h, out_rgb, 0, stream);
 }
 
 int dp_scatter_tiles_xy(const uint8_t* tiles, int n, int tile_w, int tile_h, const int32_t* origins, uint8_t* raster,

@@ -637,15 +637,6 @@ int plan_dense_layer(dp_model* m, const BlobOp& op, int img0, int B, Launch& L) 
     const long long min_items = env ? atoll(env) : m->num_sms;
     if (H % 16 || (long long)B * (W / 8) * (H / 16) < min_items) p.rh = 8;
   }
-  {
-    // Experimental (not yet run on hardware, off by default): phase 2 with the dy taps stacked along N = 96
-    // (dense_layer.cuh header).  DP_DL_STACK=1: where the planner chose 8-row regions; =2: everywhere, with 14-row
-    // regions (16 halo rows = one M block) on maps of 28 rows or more and 8-row regions below.
-    const char* env = getenv("DP_DL_STACK");
-    const int mode = env ? atoi(env) : 0;
-    if (mode >= 2) { p.stack = 1; p.rh = (H >= 28) ? 14 : 8; }
-    else if (mode == 1 && p.rh == 8) p.stack = 1;
-  }
   p.tiles_w = W / 8; p.tiles_h = (H + p.rh - 1) / p.rh;
   p.n_items = B * p.tiles_w * p.tiles_h;
   p.out_ctot = ib.C; p.out_choff = op.out_choff;
@@ -654,7 +645,6 @@ int plan_dense_layer(dp_model* m, const BlobOp& op, int img0, int B, Launch& L) 
   p.pro_scale = a.pro_scale; p.pro_shift = a.pro_shift; p.mid_shift = a.epi_shift;
   p.out = buf_at(op.in_buf);
   const int budget = 227 * 1024 - DenseLayerSmem::kBarBytes - dl_t_bytes(p.rh) - 2 * p.n_chunks * 64 * 4 - 128 * 4 - 1024 -
-                     (p.stack ? DenseLayerSmem::kXchBytes : 0) -
                      10 * 1024;   // the last A stage's M-block over-read must stay inside the allocation
   const int a_stage = dl_a_stage(p.rh);
   // Activation ring as deep as shared memory allows (up to 8): a halo chunk is 100-180 separate 128-byte segments,
@@ -682,7 +672,7 @@ int plan_dense_layer(dp_model* m, const BlobOp& op, int img0, int B, Launch& L) 
     }
     // executed: 1x1 on 256 rows per 128-pixel region (halo recompute + padding rows), 3x3 on 128 rows
     L.macs = (uint64_t)p.n_items * ((dl_rows(p.rh) > 128 ? 256ull : 128ull) * 128 * ksteps * 16 +
-                                    (p.stack ? 128ull * 96 * 3 * 128 : 128ull * 32 * 9 * 128));
+                                    128ull * 32 * 9 * 128);
   }
   {
     uint64_t dims[4] = {(uint64_t)op.cin, (uint64_t)W, (uint64_t)H, (uint64_t)B};
@@ -700,7 +690,7 @@ int plan_dense_layer(dp_model* m, const BlobOp& op, int img0, int B, Launch& L) 
   {
     uint64_t dims[3] = {128, 32, 9};
     uint64_t str[2] = {128 * 2, 128 * 2 * 32};
-    uint32_t box[3] = {64, 32, (uint32_t)(p.stack ? 1 : kDlW2Group)};   // stacked: one tap per load (dy-major order)
+    uint32_t box[3] = {64, 32, (uint32_t)kDlW2Group};
     if (make_map(&L.map_w2, b.w, 3, dims, str, box)) return 1;
   }
   return 0;
@@ -1097,12 +1087,8 @@ int run_op(dp_model* m, SubPlan* sp, int i, cudaStream_t st) {
       cfg.attrs = attr;
       cfg.numAttrs = m->use_pdl ? 1 : 0;
       cudaError_t le;
-      if (dl.stack)
-        le = (dl.rh == 14) ? cudaLaunchKernelEx(&cfg, dp::dense_layer_kernel<14, true>, L.map_a, L.map_b, L.map_w2, dl)
-                           : cudaLaunchKernelEx(&cfg, dp::dense_layer_kernel<8, true>, L.map_a, L.map_b, L.map_w2, dl);
-      else
-        le = (dl.rh == 16) ? cudaLaunchKernelEx(&cfg, dp::dense_layer_kernel<16>, L.map_a, L.map_b, L.map_w2, dl)
-                           : cudaLaunchKernelEx(&cfg, dp::dense_layer_kernel<8>, L.map_a, L.map_b, L.map_w2, dl);
+      le = (dl.rh == 16) ? cudaLaunchKernelEx(&cfg, dp::dense_layer_kernel<16>, L.map_a, L.map_b, L.map_w2, dl)
+                         : cudaLaunchKernelEx(&cfg, dp::dense_layer_kernel<8>, L.map_a, L.map_b, L.map_w2, dl);
       if (le != cudaSuccess) return fail("dense layer launch failed: %s", cudaGetErrorString(le));
       LAUNCH_OK();
       return 0;
@@ -1213,8 +1199,6 @@ int dp_model_create(const void* blob, size_t nbytes, int device, int max_batch, 
     cudaError_t e7 = cudaFuncSetAttribute(dp::conv_tc_kernel<dp::MODE_D, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
     cudaError_t e5 = cudaFuncSetAttribute(dp::dense_layer_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
     cudaError_t e6 = cudaFuncSetAttribute(dp::dense_layer_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
-    if (e6 == cudaSuccess) e6 = cudaFuncSetAttribute(dp::dense_layer_kernel<8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
-    if (e6 == cudaSuccess) e6 = cudaFuncSetAttribute(dp::dense_layer_kernel<14, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
     if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess || e4 != cudaSuccess || e5 != cudaSuccess || e6 != cudaSuccess || e7 != cudaSuccess) {
       cleanup();
       return fail("cudaFuncSetAttribute(MaxDynamicSharedMemorySize) failed: %s", cudaGetErrorString(cudaGetLastError()));

@@ -6,9 +6,9 @@ patch on 8 CPU processes, DigiPathAI/loaders/dataloader.py:239,357-358; Segmenta
 nvJPEG in batches as compressed streams and are scattered on the device into the ``[x, y, c]`` raster that
 ``dp_forward_tiles`` crops from.  No fallback: without the library this module raises on import.
 
-Status: compiled and container-side logic tested on CPU (tests/test_wsi_tiff.py); the decode + scatter have NOT
-run on a GPU yet (tests/test_gpu_wsi_ingest.py), which is why ``slide.open_slide`` only returns a ``TiffSlide`` when
-asked to (``DIGIPATH_DEVICE_INGEST=1``).
+Status: container-side logic tested on CPU (tests/test_wsi_tiff.py); decode + scatter parity on the B200 in
+tests/test_gpu_wsi_ingest.py.  ``slide.open_slide`` returns a ``TiffSlide`` when asked to
+(``DIGIPATH_DEVICE_INGEST=1``) or when handed one.
 """
 from __future__ import annotations
 
@@ -32,6 +32,8 @@ _SIGS = {
     "dp_jpeg_decoder_destroy": (C.c_int, [C.c_void_p]),
     "dp_jpeg_decode_tiles": (C.c_int, [C.c_void_p, C.POINTER(C.c_char_p), C.POINTER(C.c_size_t), C.c_int, C.c_int,
                                        C.c_int, C.c_void_p, C.c_void_p]),
+    "dp_jpeg_decode_tiles_ex": (C.c_int, [C.c_void_p, C.POINTER(C.c_char_p), C.POINTER(C.c_size_t), C.c_int, C.c_int,
+                                          C.c_int, C.c_void_p, C.c_int, C.c_void_p]),
     "dp_scatter_tiles_xy": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int64,
                                       C.c_int64, C.c_int64, C.c_void_p]),
 }
@@ -70,9 +72,10 @@ class JpegTileDecoder:
         except Exception:  # noqa: BLE001 -- interpreter shutdown
             pass
 
-    def decode(self, streams, tile_w: int, tile_h: int, out=None):
+    def decode(self, streams, tile_w: int, tile_h: int, out=None, components_are_rgb: bool = False):
         """``streams``: list of self-contained JPEG byte strings -> cuda uint8 ``[n, tile_h, tile_w, 3]`` (RGB).
-        Slots of streams smaller than the tile keep whatever ``out`` held (zeros when allocated here)."""
+        Slots of streams smaller than the tile keep whatever ``out`` held (zeros when allocated here).
+        ``components_are_rgb``: the stored components are R, G, B (TIFF photometric 2), not YCbCr."""
         import torch
         n = len(streams)
         dev = torch.device("cuda", self.device)
@@ -83,8 +86,9 @@ class JpegTileDecoder:
         lens = (C.c_size_t * n)(*[len(s) for s in streams])
         with torch.cuda.device(dev):
             st = torch.cuda.current_stream().cuda_stream
-            _check(lib.dp_jpeg_decode_tiles(self._h, ptrs, lens, n, int(tile_w), int(tile_h),
-                                            C.c_void_p(out.data_ptr()), C.c_void_p(st)), "dp_jpeg_decode_tiles")
+            _check(lib.dp_jpeg_decode_tiles_ex(self._h, ptrs, lens, n, int(tile_w), int(tile_h),
+                                               C.c_void_p(out.data_ptr()), int(bool(components_are_rgb)),
+                                               C.c_void_p(st)), "dp_jpeg_decode_tiles_ex")
         return out
 
 
@@ -120,7 +124,7 @@ def upload_tiff_raster(slide, x_lo: int, x_hi: int, device, batch: int = 256):
             idx = todo[s:s + batch]
             streams = [slide.jpeg_stream(0, k) for k in idx]
             org = torch.tensor([slide.tile_origin(0, k) for k in idx], dtype=torch.int32).to(dev)
-            tiles = dec.decode(streams, tw, th, out=buf[:len(idx)])
+            tiles = dec.decode(streams, tw, th, out=buf[:len(idx)], components_are_rgb=slide.components_are_rgb(0))
             scatter_tiles_xy(tiles, org, out, x_lo)
         torch.cuda.synchronize(dev)
     finally:

@@ -130,6 +130,11 @@ class TiffSlide:
         p = self.pages[level]
         return p.compression == 7 and p.samples in (1, 3) and all(b == 8 for b in p.bits)
 
+    def components_are_rgb(self, level: int = 0) -> bool:
+        """True when the page stores R, G, B components directly (photometric 2) rather than YCbCr (6)."""
+        p = self.pages[level]
+        return p.photometric == 2 and p.samples == 3
+
     def tile_grid(self, level: int = 0):
         p = self.pages[level]
         return p.tiles_x, p.tiles_y, p.tile_w, p.tile_h

@@ -37,6 +37,13 @@ int dp_jpeg_decoder_destroy(dp_jpeg_decoder* dec);
 int dp_jpeg_decode_tiles(dp_jpeg_decoder* dec, const uint8_t* const* streams, const size_t* lengths, int n,
                          int tile_w, int tile_h, uint8_t* out_rgb, void* stream);
 
+/* Same, for pages whose TIFF PhotometricInterpretation is RGB (2): `components_are_rgb` != 0 says the three stored
+ * components ARE R, G, B (no YCbCr transform; what libtiff writes for RGB input and what OpenSlide / libjpeg decode
+ * through the Adobe APP14 marker or the 'R','G','B' component ids).  nvJPEG would colour-transform them, so they are
+ * decoded as stored component planes and interleaved on the device.  All three components must be full resolution. */
+int dp_jpeg_decode_tiles_ex(dp_jpeg_decoder* dec, const uint8_t* const* streams, const size_t* lengths, int n,
+                            int tile_w, int tile_h, uint8_t* out_rgb, int components_are_rgb, void* stream);
+
 /* Scatters decoded tiles into the raster stripe the forward path reads.
  *   tiles   : DEVICE uint8 [n][tile_h][tile_w][3]   (image layout: row = y)
  *   origins : DEVICE int32 [n][2], level-0 (x, y) of each tile's top-left pixel

@@ -28,7 +28,7 @@ def test_ingest_library_exports_every_declared_symbol():
     src = open(os.path.join(ROOT, "include", "digipath_ingest.h")).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
     syms = sorted(set(re.findall(r"\b(dp_[a-z0-9_]+)\s*\(", src)))
-    assert len(syms) == 6
+    assert len(syms) == 7
     for s in syms:
         assert hasattr(ingest.lib, s), f"{s} declared in include/digipath_ingest.h but not exported"
     assert set(syms) == set(ingest.EXPORTED_SYMBOLS)

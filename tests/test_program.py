@@ -71,43 +71,3 @@ def test_up2_weight_rewrite_is_exact_on_small_case():
     for e, (dy, dx, g) in enumerate(emulator.entries(PG.KIND_UP2)):
         got[:, (g >> 1)::2, (g & 1)::2] += (emulator._shift(xt, dy, dx) @ torch.from_numpy(w[e].T)).numpy()
     assert np.abs(got - want).max() < 2e-2   # only fp16 weight rounding separates them
-
-
-def test_stacked_tap_formulation_of_the_dense_layer_3x3():
-    """The arithmetic the STACK variant of dense_layer_kernel performs (csrc/dense_layer.cuh header), restated in
-    numpy with the kernel's own indexing -- M rows = (halo row, x), B = the three dy taps of one dx stacked along N,
-    output = accumulator rows r, r + 8, r + 16 -- equals the plain 3x3 'same' convolution, for 14-row regions on a
-    map they do not divide (32 rows) and 8-row regions."""
-    import emulator
-    rng = np.random.default_rng(0)
-    w2 = rng.standard_normal((9, 32, 128)).astype(np.float32)                 # [tap = dy * 3 + dx][cout][k]
-    taps = list(emulator.entries(3))
-    assert [(dy, dx) for dy, dx, _ in taps] == [(dy, dx) for dy in (-1, 0, 1) for dx in (-1, 0, 1)]
-    for H, W, RH in ((32, 16, 14), (16, 8, 8), (8, 8, 8)):
-        t = rng.standard_normal((H, W, 128)).astype(np.float32)
-        ref = np.zeros((H, W, 32), np.float32)
-        tp = np.pad(t, ((1, 1), (1, 1), (0, 0)))
-        for e, (dy, dx, _) in enumerate(taps):
-            ref += tp[1 + dy:1 + dy + H, 1 + dx:1 + dx + W] @ w2[e].T
-        out = np.full((H, W, 32), np.nan, np.float32)
-        for h0 in range(0, H, RH):
-            for w0 in range(0, W, 8):
-                halo = np.zeros((RH + 2, 10, 128), np.float32)               # T tile, zero outside the image
-                for hr in range(RH + 2):
-                    for c in range(10):
-                        ih, iw = h0 - 1 + hr, w0 - 1 + c
-                        if 0 <= ih < H and 0 <= iw < W:
-                            halo[hr, c] = t[ih, iw]
-                acc = np.zeros((128, 96), np.float32)                         # D'
-                for g in range(3):                                            # dx index
-                    A = np.zeros((128, 128), np.float32)
-                    for m in range((RH + 2) * 8):
-                        A[m] = halo[m >> 3, (m & 7) + g]
-                    B = np.concatenate([w2[j * 3 + g] for j in range(3)], axis=0)   # [96][k]
-                    acc += A @ B.T
-                for r in range(RH * 8):
-                    h, w = h0 + (r >> 3), w0 + (r & 7)
-                    if h < H and w < W:
-                        out[h, w] = acc[r, 0:32] + acc[r + 8, 32:64] + acc[r + 16, 64:96]
-        assert not np.isnan(out).any()
-        assert np.abs(out - ref).max() < 1e-3 * np.abs(ref).max()
