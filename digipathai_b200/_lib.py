@@ -61,6 +61,7 @@ _SIGS = {
     "dp_model_op_times": (C.c_int, [c_model_p, C.POINTER(C.c_float), C.c_int]),
     "dp_model_op_info": (C.c_int, [c_model_p, C.c_int] + [C.POINTER(C.c_int)] * 6 + [C.POINTER(C.c_uint64)]),
     "dp_debug_read_stamps": (C.c_int, [c_model_p, C.POINTER(C.c_uint64), C.c_int]),
+    "dp_debug_read_cta_stamps": (C.c_int, [c_model_p, C.c_int, C.POINTER(C.c_uint64), C.c_int]),
     "dp_debug_read_trace": (C.c_int, [c_model_p, C.POINTER(C.c_uint64), C.c_int]),
     "dp_model_executed_macs": (C.c_int, [c_model_p, C.c_int, C.POINTER(C.c_uint64)]),
 }

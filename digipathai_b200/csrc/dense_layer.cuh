@@ -66,6 +66,7 @@ struct DenseLayerParams {
   __half* out;               // concat buffer base (same tensor the A map reads)
   unsigned long long* trace;
   unsigned long long* gt;    // debug: [0]/[1] receive %globaltimer at entry / exit of CTA 0
+  unsigned long long* gt_all;  // debug (option "stamp_ctas"): per CTA [entry, grid-dependency wait returned, exit, SM id]
 };
 
 struct DenseLayerSmem {
@@ -137,6 +138,12 @@ dense_layer_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (tid == 0 && p.trace && blockIdx.x == 0) p.trace[8 + 2000 * 4 + 1] = (2ull << 48) | (clock64() & 0xFFFFFFFFull);
   if (tid == 0 && p.gt && blockIdx.x == 0) p.gt[0] = globaltimer_ns();
+  if (tid == 0 && p.gt_all) {
+    unsigned smid;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    p.gt_all[4 * blockIdx.x] = globaltimer_ns();
+    p.gt_all[4 * blockIdx.x + 3] = smid;
+  }
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&map_x);
@@ -214,6 +221,7 @@ dense_layer_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
             pdl_wait();
             pdl_launch_dependents();
             waited = true;
+            if (p.gt_all) p.gt_all[4 * blockIdx.x + 1] = globaltimer_ns();
           }
           mbar_wait(&a_empty[sa], pa ^ 1);
           mbar_expect_tx(&a_full[sa], kRows * 128);
@@ -490,7 +498,9 @@ dense_layer_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
             if (rr < kRows) *reinterpret_cast<uint4*>(stage_base + rr * 128 + ((i ^ (rr & 7)) << 4)) = raw[j];
           }
         }
+        dl_trace_ev(tc, 2, k);
         fence_proxy_async_smem();
+        dl_trace_ev(tc, 3, k);
         mbar_arrive_warp(&a_ready[sa]);
         dl_trace_ev(tc, 0, k);
         if (++sa == p.a_stages) { sa = 0; pa ^= 1; }
@@ -505,6 +515,7 @@ dense_layer_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
     tc_fence_after();
     tmem_dealloc(tmem_base, kTmemCols);
     if (lane == 0 && p.gt && blockIdx.x == 0) p.gt[1] = globaltimer_ns();
+    if (lane == 0 && p.gt_all) p.gt_all[4 * blockIdx.x + 2] = globaltimer_ns();
     if (lane == 0 && p.trace && blockIdx.x == 0) { p.trace[8 + 2000 * 4 + 2] = (1ull << 48) | (clock64() & 0xFFFFFFFFull); p.trace[4] = 3; }
   }
 }

@@ -11,6 +11,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <map>
+#include <memory>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -20,6 +21,7 @@
 #include "conv_tc.cuh"
 #include "crf.cuh"
 #include "dense_layer.cuh"
+#include "dense_block.cuh"
 #include "precise.cuh"
 #include "tissue.cuh"
 
@@ -127,11 +129,19 @@ struct Launch {
   CUtensorMap map_w2;
   dp::DenseLayerParams dl;
   dp::NaiveConvParams np2;  // debug path: the 3x3 half (np holds the 1x1 half)
+  // persistent dense-block kernel (dense_block.cuh): set on the FIRST layer of a run of dense layers on small maps;
+  // the other layers of the run carry block_member and launch nothing when the whole program is executed
+  int block_len = 0;
+  bool block_member = false;
+  CUtensorMap map_x_block;
+  dp::DenseBlockParams db;
+  int block_smem = 0;
 };
 
 struct SubPlan {
   int img0 = 0, n_img = 0;       // slice of the call's tile batch this sub-plan covers
   std::vector<Launch> launches;  // one per op
+  std::vector<std::shared_ptr<void>> dev_allocs;   // layer tables of the dense-block kernels (cudaFree'd with the plan)
 };
 
 // A plan for one tile count: the batch is cut into `subs.size()` independent sub-batches whose op chains are
@@ -157,10 +167,13 @@ struct dp_model {
   uint64_t device_bytes = 0;
   int naive_conv = 0, desc_base_mode = 0, halo_pad8 = 0, profile = 0;
   int use_graph = 1, split = 1, use_pdl = 1, epi_direct = 1, use_overlap = 1, b_resident = 1, b_pair = 0;
+  int dense_block = 1;   // runs of dense layers on 16x16 / 8x8 maps as one persistent kernel (dense_block.cuh)
   unsigned long long* gt_dev = nullptr;     // debug: per-op %globaltimer stamps (option "stamp")
   int stamp = 0;
+  unsigned long long* gt_all_dev = nullptr; // debug: per-CTA stamps of the dense layers [n_ops][256][4] (option "stamp_ctas")
+  int stamp_ctas = 0;
   unsigned long long* trace_dev = nullptr;  // debug timeline buffer (option "trace_op")
-  int trace_op = -1;
+  int trace_op = -1, trace_block = -1;
   dp::PassDesc* pass_dev = nullptr;          // per-call arguments read by the stem and head kernels
   std::vector<cudaStream_t> branch_streams;  // capture-time fork/join streams
   std::vector<cudaEvent_t> branch_events;
@@ -696,6 +709,78 @@ int plan_dense_layer(dp_model* m, const BlobOp& op, int img0, int B, Launch& L) 
   return 0;
 }
 
+// Groups runs of consecutive fused dense layers that (a) extend the same concat buffer layer by layer, (b) use 8-row
+// regions and (c) have 1, 2, 4 or 8 regions per image (one thread-block cluster) into one persistent kernel launch each.
+int plan_dense_blocks(dp_model* m, SubPlan& sp) {
+  using namespace dp;
+  const int n = (int)m->ops.size();
+  struct Run { int first, len; };
+  std::vector<Run> runs;
+  for (int i = 0; i < n;) {
+    const int per_img = (m->ops[i].type == OP_DENSE_LAYER) ? sp.launches[i].dl.tiles_w * sp.launches[i].dl.tiles_h : 0;
+    if (m->ops[i].type != OP_DENSE_LAYER || sp.launches[i].dl.rh != 8 ||
+        !(per_img == 1 || per_img == 2 || per_img == 4 || per_img == 8)) { ++i; continue; }
+    int j = i + 1;
+    while (j < n && m->ops[j].type == OP_DENSE_LAYER && m->ops[j].in_buf == m->ops[i].in_buf &&
+           m->ops[j].in_choff == m->ops[i].in_choff && m->ops[j].cin == m->ops[j - 1].cin + 32 &&
+           m->ops[j].out_choff == m->ops[j].in_choff + m->ops[j].cin && sp.launches[j].dl.rh == 8 &&
+           sp.launches[j].dl.n_items == sp.launches[i].dl.n_items)
+      ++j;
+    if (j - i >= 2) runs.push_back({i, j - i});
+    i = j;
+  }
+  if (runs.empty()) return 0;
+  for (const Run& r : runs) {
+    Launch& L0 = sp.launches[r.first];
+    const BlobOp& op0 = m->ops[r.first];
+    const BlobOp& opl = m->ops[r.first + r.len - 1];
+    const BlobBuf& ib = m->bufs[op0.in_buf];
+    std::vector<DenseBlockLayer> tab(r.len);
+    int a_stages = kMaxAStages, b_stages = kMaxBStages;
+    for (int l = 0; l < r.len; ++l) {
+      const Launch& Ll = sp.launches[r.first + l];
+      memset(&tab[l], 0, sizeof(DenseBlockLayer));
+      tab[l].map_w1 = Ll.map_b;
+      tab[l].map_w2 = Ll.map_w2;
+      tab[l].pro_scale = Ll.dl.pro_scale;
+      tab[l].pro_shift = Ll.dl.pro_shift;
+      tab[l].mid_shift = Ll.dl.mid_shift;
+      tab[l].C = Ll.dl.C;
+      tab[l].n_chunks = Ll.dl.n_chunks;
+      tab[l].out_choff = Ll.dl.out_choff;
+      if (Ll.dl.a_stages < a_stages) a_stages = Ll.dl.a_stages;
+      if (Ll.dl.b_stages < b_stages) b_stages = Ll.dl.b_stages;
+    }
+    DenseBlockLayer* tab_dev = nullptr;
+    CU_OK(cudaMalloc(&tab_dev, tab.size() * sizeof(DenseBlockLayer)));
+    sp.dev_allocs.emplace_back(tab_dev, [](void* q) { cudaFree(q); });
+    CU_OK(cudaMemcpy(tab_dev, tab.data(), tab.size() * sizeof(DenseBlockLayer), cudaMemcpyHostToDevice));
+    DenseBlockParams& p = L0.db;
+    memset(&p, 0, sizeof p);
+    p.n_img = L0.dl.n_img; p.H = L0.dl.H; p.W = L0.dl.W;
+    p.tiles_w = L0.dl.tiles_w; p.tiles_h = L0.dl.tiles_h; p.n_items = L0.dl.n_items;
+    p.n_layers = r.len;
+    p.a_stages = a_stages; p.b_stages = b_stages;
+    p.out_ctot = L0.dl.out_ctot;
+    p.out = L0.dl.out;
+    p.layers = tab_dev;
+    p.cluster_size = p.tiles_w * p.tiles_h;
+    {
+      // one activation map for the whole block: channels beyond a layer's C (later layers' slots) may hold values of
+      // an earlier forward, but the K-steps issued per layer stop at C, so they never reach the tensor cores
+      uint64_t dims[4] = {(uint64_t)opl.cin, (uint64_t)ib.W, (uint64_t)ib.H, (uint64_t)sp.n_img};
+      const uint64_t cs = (uint64_t)ib.C * 2;
+      uint64_t str[3] = {cs, cs * ib.W, cs * ib.W * ib.H};
+      uint32_t box[4] = {64, (uint32_t)kDlHaloW, 10, 1};
+      if (make_map(&L0.map_x_block, buf_ptr(m, op0.in_buf, sp.img0) + op0.in_choff, 4, dims, str, box)) return 1;
+    }
+    L0.block_smem = dense_block_smem(p).total;
+    L0.block_len = r.len;
+    for (int l = 1; l < r.len; ++l) sp.launches[r.first + l].block_member = true;
+  }
+  return 0;
+}
+
 int get_plan(dp_model* m, int B, int split, Plan** out) {
   std::lock_guard<std::mutex> lk(m->mu);
   if (split < 1 || B % split || B / split < 1) split = 1;
@@ -724,6 +809,9 @@ int get_plan(dp_model* m, int B, int split, Plan** out) {
       }
     }
   }
+  if (m->dense_block && !m->precision)
+    for (SubPlan& sp : plan.subs)
+      if (plan_dense_blocks(m, sp)) return 1;
   auto res = m->plans.emplace(key, std::move(plan));
   *out = &res.first->second;
   return 0;
@@ -867,7 +955,7 @@ int run_op_f32(dp_model* m, SubPlan* sp, int i, cudaStream_t st) {
   return 0;
 }
 
-int run_op(dp_model* m, SubPlan* sp, int i, cudaStream_t st) {
+int run_op(dp_model* m, SubPlan* sp, int i, cudaStream_t st, bool whole_program = false) {
   if (m->precision) return run_op_f32(m, sp, i, st);
   const BlobOp& op = m->ops[i];
   Launch& L = sp->launches[i];
@@ -1072,9 +1160,41 @@ int run_op(dp_model* m, SubPlan* sp, int i, cudaStream_t st) {
         LAUNCH_OK();
         return 0;
       }
+      // whole-program runs execute a run of small-map dense layers as one persistent kernel (debug options that
+      // inspect single layers keep the per-layer kernels)
+      const bool use_block = whole_program && m->dense_block && m->trace_op < 0 && !m->stamp_ctas;
+      if (use_block && L.block_member) return 0;
+      if (use_block && L.block_len > 0) {
+        dp::DenseBlockParams db = L.db;
+        db.gt_layers = (m->stamp && m->gt_dev) ? m->gt_dev + 2 * i : nullptr;
+        db.trace = (m->trace_block == i) ? m->trace_dev : nullptr;
+        cudaLaunchConfig_t cfg;
+        memset(&cfg, 0, sizeof cfg);
+        cfg.gridDim = dim3(db.n_items);
+        cfg.blockDim = dim3(640);
+        cfg.dynamicSmemBytes = L.block_smem;
+        cfg.stream = st;
+        cudaLaunchAttribute attr[2];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = m->use_pdl ? 1 : 0;
+        if (db.cluster_size > 1) {
+          attr[cfg.numAttrs].id = cudaLaunchAttributeClusterDimension;
+          attr[cfg.numAttrs].val.clusterDim.x = (unsigned)db.cluster_size;
+          attr[cfg.numAttrs].val.clusterDim.y = 1;
+          attr[cfg.numAttrs].val.clusterDim.z = 1;
+          ++cfg.numAttrs;
+        }
+        cudaError_t le = cudaLaunchKernelEx(&cfg, dp::dense_block_kernel, L.map_x_block, db);
+        if (le != cudaSuccess) return fail("dense block launch failed: %s", cudaGetErrorString(le));
+        LAUNCH_OK();
+        return 0;
+      }
       dp::DenseLayerParams dl = L.dl;
       dl.trace = (m->trace_op == i) ? m->trace_dev : nullptr;
       dl.gt = (m->stamp && m->gt_dev) ? m->gt_dev + 2 * i : nullptr;
+      dl.gt_all = (m->stamp_ctas && m->gt_all_dev && L.grid <= 256) ? m->gt_all_dev + (size_t)i * 1024 : nullptr;
       cudaLaunchConfig_t cfg;
       memset(&cfg, 0, sizeof cfg);
       cfg.gridDim = dim3(L.grid);
@@ -1198,6 +1318,7 @@ int dp_model_create(const void* blob, size_t nbytes, int device, int max_batch, 
     }
     cudaError_t e7 = cudaFuncSetAttribute(dp::conv_tc_kernel<dp::MODE_D, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
     cudaError_t e5 = cudaFuncSetAttribute(dp::dense_layer_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
+    if (e5 == cudaSuccess) e5 = cudaFuncSetAttribute(dp::dense_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
     cudaError_t e6 = cudaFuncSetAttribute(dp::dense_layer_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
     if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess || e4 != cudaSuccess || e5 != cudaSuccess || e6 != cudaSuccess || e7 != cudaSuccess) {
       cleanup();
@@ -1206,6 +1327,8 @@ int dp_model_create(const void* blob, size_t nbytes, int device, int max_batch, 
   }
   env = getenv("DP_B_PAIR");
   if (env) m->b_pair = atoi(env);
+  env = getenv("DP_DENSE_BLOCK");
+  if (env) m->dense_block = atoi(env);
   env = getenv("DP_NAIVE_CONV");
   if (env && atoi(env)) m->naive_conv = 1;
   env = getenv("DP_DESC_BASE_MODE");
@@ -1230,6 +1353,7 @@ int dp_model_destroy(dp_model* m) {
   if (m->pass_dev) cudaFree(m->pass_dev);
   if (m->trace_dev) cudaFree(m->trace_dev);
   if (m->gt_dev) cudaFree(m->gt_dev);
+  if (m->gt_all_dev) cudaFree(m->gt_all_dev);
   for (__half* p : m->buf_dev)
     if (p) cudaFree(p);
   if (m->scratch_head) cudaFree(m->scratch_head);
@@ -1259,6 +1383,12 @@ int dp_model_set_option(dp_model* m, const char* key, int value) {
     CU_OK(cudaMemset(m->gt_dev, 0, 2 * m->ops.size() * sizeof(unsigned long long)));
     m->stamp = value;
   }
+  else if (!strcmp(key, "stamp_ctas")) {
+    const size_t nb = m->ops.size() * 1024 * sizeof(unsigned long long);
+    if (!m->gt_all_dev) CU_OK(cudaMalloc(&m->gt_all_dev, nb));
+    CU_OK(cudaMemset(m->gt_all_dev, 0, nb));
+    m->stamp_ctas = value;
+  }
   else if (!strcmp(key, "b_resident") || !strcmp(key, "b_pair")) {
     std::lock_guard<std::mutex> lk(m->mu);
     if (!strcmp(key, "b_pair")) m->b_pair = value; else m->b_resident = value;
@@ -1268,9 +1398,9 @@ int dp_model_set_option(dp_model* m, const char* key, int value) {
     }
     m->plans.clear();
   }
-  else if (!strcmp(key, "use_overlap")) {
+  else if (!strcmp(key, "use_overlap") || !strcmp(key, "dense_block")) {
     std::lock_guard<std::mutex> lk(m->mu);
-    m->use_overlap = value;
+    if (!strcmp(key, "dense_block")) m->dense_block = value; else m->use_overlap = value;
     for (auto& kv : m->plans) {
       if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
       if (kv.second.graph) cudaGraphDestroy(kv.second.graph);
@@ -1294,10 +1424,10 @@ int dp_model_set_option(dp_model* m, const char* key, int value) {
       if (kv.second.graph) { cudaGraphDestroy(kv.second.graph); kv.second.graph = nullptr; }
     }
   }
-  else if (!strcmp(key, "trace_op")) {
+  else if (!strcmp(key, "trace_op") || !strcmp(key, "trace_block")) {
     if (!m->trace_dev) CU_OK(cudaMalloc(&m->trace_dev, 10016 * sizeof(unsigned long long)));
     CU_OK(cudaMemset(m->trace_dev, 0, 10016 * sizeof(unsigned long long)));
-    m->trace_op = value;
+    if (!strcmp(key, "trace_op")) m->trace_op = value; else m->trace_block = value;
   }
   else if (!strcmp(key, "split")) m->split = value < 1 ? 1 : value;
   else if (!strcmp(key, "halo_pad8")) {
@@ -1344,6 +1474,7 @@ static int run_range(dp_model* m, int B, int op_begin, int op_end, const dp::Pas
   Plan* plan = nullptr;
   if (get_plan(m, B, 1, &plan)) return 1;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const bool whole = op_begin == 0 && op_end == (int)m->ops.size();   // persistent block kernels need the whole block
   if (upload_pass(m, d, st)) return 1;
   if (m->profile && m->ev.empty()) {
     m->ev.resize(2 * m->ops.size());
@@ -1355,7 +1486,7 @@ static int run_range(dp_model* m, int B, int op_begin, int op_end, const dp::Pas
     if (((op.type == OP_CONV && op.head) || op.type == OP_HEAD_RESIZE) && !d.probs_out)
       return fail("op %d: head needs a probability output buffer", i);
     if (m->profile) CU_OK(cudaEventRecord(m->ev[2 * i], st));
-    if (run_op(m, &plan->subs[0], i, st)) {
+    if (run_op(m, &plan->subs[0], i, st, whole)) {
       g_err = "op " + std::to_string(i) + ": " + g_err;
       return 1;
     }
@@ -1392,7 +1523,7 @@ static int run_graph(dp_model* m, int B, const dp::PassDesc& d, void* stream) {
       for (int s = 0; s < ns && !rc && ce == cudaSuccess; ++s) {
         cudaStream_t bs = (s == 0) ? m->cap_stream : m->branch_streams[s];
         if (s) ce = cudaStreamWaitEvent(bs, m->fork_event, 0);
-        for (int i = 0; i < (int)m->ops.size() && !rc && ce == cudaSuccess; ++i) rc = run_op(m, &plan->subs[s], i, bs);
+        for (int i = 0; i < (int)m->ops.size() && !rc && ce == cudaSuccess; ++i) rc = run_op(m, &plan->subs[s], i, bs, true);
         if (s && !rc && ce == cudaSuccess) {
           ce = cudaEventRecord(m->branch_events[s], bs);
           if (ce == cudaSuccess) ce = cudaStreamWaitEvent(m->cap_stream, m->branch_events[s], 0);
@@ -1487,6 +1618,16 @@ int dp_debug_read_stamps(dp_model* m, unsigned long long* out, int n) {
   CU_OK(cudaSetDevice(m->device));
   CU_OK(cudaDeviceSynchronize());
   CU_OK(cudaMemcpy(out, m->gt_dev, (size_t)n * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+int dp_debug_read_cta_stamps(dp_model* m, int op, unsigned long long* out, int n) {
+  if (check_model(m) || !out) return fail("null argument");
+  if (!m->gt_all_dev) return fail("no per-CTA stamps (set option 'stamp_ctas')");
+  if (op < 0 || op >= (int)m->ops.size() || n != 1024) return fail("expected op in range and room for 1024 values");
+  CU_OK(cudaSetDevice(m->device));
+  CU_OK(cudaDeviceSynchronize());
+  CU_OK(cudaMemcpy(out, m->gt_all_dev + (size_t)op * 1024, 1024 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
   return 0;
 }
 

@@ -158,6 +158,13 @@ class TileModel:
         _lib.check(_lib.lib.dp_debug_read_stamps(self._h, arr, n))
         return np.array(arr[:], dtype=np.int64).reshape(-1, 2)
 
+    def read_cta_stamps(self, op: int) -> np.ndarray:
+        """[256, 4] per CTA of dense-layer op ``op``: %globaltimer at entry, when the grid-dependency wait returned, at
+        exit, and the SM id (option 'stamp_ctas'; rows of CTAs that did not run are zero)."""
+        arr = (C.c_uint64 * 1024)()
+        _lib.check(_lib.lib.dp_debug_read_cta_stamps(self._h, int(op), arr, 1024))
+        return np.array(arr[:], dtype=np.int64).reshape(256, 4)
+
     def read_trace(self):
         """[(role, event, item, clock32)] of CTA 0 for the op selected with set_option('trace_op', i)."""
         arr = (C.c_uint64 * 10016)()

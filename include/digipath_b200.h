@@ -146,6 +146,7 @@ int dp_model_op_info(const dp_model* m, int op, int* type, int* kind, int* cin, 
 /* Debug timeline of CTA 0 of the conv op selected with option "trace_op" (direct-launch path only):
  * out[r] = entries of role r (0 producer, 1 MMA, 2 epilogue, 3 transform, 4 setup); role r's entries start at
  * out[8 + 2000 r], each event<<48 | item<<32 | clock32. */
+int dp_debug_read_cta_stamps(dp_model* m, int op, unsigned long long* out, int n);   /* option "stamp_ctas": [256][4] */
 int dp_debug_read_trace(dp_model* m, unsigned long long* out, int n);
 
 /* %globaltimer (ns) at entry / exit of CTA 0 of every tensor-core op of the last direct-launch run made with

@@ -50,7 +50,7 @@ def test_graph_and_direct_paths_agree(model32):
     g = torch.Generator(device="cuda"); g.manual_seed(9)
     tiles = torch.randint(0, 256, (8, 256, 256, 3), dtype=torch.uint8, device="cuda", generator=g)
     a = m.forward_tile_batch(tiles).clone()
-    for key in ("use_graph", "use_pdl", "use_overlap", "b_resident", "epi_direct"):
+    for key in ("use_graph", "use_pdl", "use_overlap", "b_resident", "epi_direct", "dense_block"):
         m.set_option(key, 0)
         b = m.forward_tile_batch(tiles).clone()
         m.set_option(key, 1)
@@ -59,6 +59,31 @@ def test_graph_and_direct_paths_agree(model32):
     b = m.forward_tile_batch(tiles).clone()
     m.set_option("b_pair", 0)
     assert torch.equal(a, b)
+
+
+def test_persistent_dense_block_kernel_is_bit_identical_to_the_per_layer_kernels(model32):
+    """conv4 / conv5 (16x16 / 8x8 maps) run as one persistent kernel per block (csrc/dense_block.cuh: regions pinned to
+    CTAs, neighbour flags instead of kernel boundaries).  Same arithmetic in the same order: every probability and the
+    block outputs themselves must equal the one-launch-per-layer path bit for bit -- at batch 32 (128 / 32 regions),
+    at a ragged batch, under TTA, with and without the CUDA graph, and on repeated calls (flags are re-armed)."""
+    m, torch = model32
+    g = torch.Generator(device="cuda"); g.manual_seed(21)
+    prog = m.program
+    for B in (32, 5, 1):
+        tiles = torch.randint(0, 256, (B, 256, 256, 3), dtype=torch.uint8, device="cuda", generator=g)
+        m.set_option("dense_block", 0)
+        want = m.forward_tile_batch(tiles, 5, 4).clone()
+        want_d4 = m.read_buffer(prog.buf("D4"), B)
+        want_d5 = m.read_buffer(prog.buf("D5"), B)
+        m.set_option("dense_block", 1)
+        for graph in (1, 0, 1):
+            m.set_option("use_graph", graph)
+            for _ in range(2):
+                got = m.forward_tile_batch(tiles, 5, 4).clone()
+                assert torch.equal(got, want), (B, graph)
+            assert np.array_equal(m.read_buffer(prog.buf("D4"), B), want_d4)
+            assert np.array_equal(m.read_buffer(prog.buf("D5"), B), want_d5)
+        m.set_option("use_graph", 1)
 
 
 def test_sharded_tile_ranges_equal_unsharded():

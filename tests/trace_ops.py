@@ -20,7 +20,7 @@ torch.cuda.synchronize()
 ROLE = {0: "prod", 1: "mma", 2: "epi", 3: "xform", 9: "setup"}
 EV_DL = {(0, 1): "A_issued", (1, 1): "A_ready", (1, 2): "B_ready", (1, 3): "ph1_issued", (1, 4): "ph2_start",
          (1, 5): "ph2_issued", (2, 0): "mid_start", (2, 2): "mid_done", (2, 3): "final_start", (2, 1): "final_done",
-         (3, 1): "xf_start", (3, 0): "xf_done", (9, 0): "setup_done", (9, 2): "kernel_entry", (9, 1): "kernel_end"}
+         (3, 1): "xf_start", (3, 0): "xf_done", (3, 2): "xf_stored", (3, 3): "xf_fenced", (9, 0): "setup_done", (9, 2): "kernel_entry", (9, 1): "kernel_end"}
 EV = {(0, 1): "A_issued", (0, 2): "B_issued", (1, 0): "acc_free", (1, 1): "A_ready", (1, 2): "B_ready",
       (1, 3): "item_issued", (1, 4): "tap_issued", (1, 5): "B_committed", (2, 0): "acc_full", (2, 1): "epi_done", (3, 0): "xform_done", (9, 0): "setup_done", (9, 2): "kernel_entry", (9, 1): "kernel_end"}
 for op in ops:
