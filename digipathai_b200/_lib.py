@@ -50,6 +50,12 @@ _SIGS = {
         [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, C.c_float, C.c_float,
          C.c_float, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p],
     ),
+    "dp_crf_lattice_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
+    "dp_crf_tiles_lattice": (
+        C.c_int,
+        [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, C.c_float, C.c_float,
+         C.c_float, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p],
+    ),
     "dp_d4_src": (None, [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "dp_kernel_launch_count": (C.c_uint64, []),
     "dp_model_set_option": (C.c_int, [c_model_p, C.c_char_p, C.c_int]),

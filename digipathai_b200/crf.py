@@ -1,13 +1,13 @@
 """The reference's two fully connected CRF helpers on the B200 mean-field kernels (``dp_crf_tiles``).
 
 Same names, argument meaning and return types as DigiPathAI/helpers/utils.py:548-603 (numpy in, numpy out), so a
-caller of ``utils.post_process_crf`` / ``utils.do_crf`` can switch imports.  Both run the exact-filter mean-field
-inference of ``csrc/crf.cuh`` (SURVEY.md 8(a) rows a13 / a13'); the reference delegates to pydensecrf's
-permutohedral-lattice approximation of the same model (parity unpinned against the lattice).
+caller of ``utils.post_process_crf`` / ``utils.do_crf`` can switch imports.  Default ``method='lattice'``: mean-field
+inference with the Gaussian filters on the permutohedral lattice (``csrc/crf_lattice.cuh``), which is what the
+reference gets from pydensecrf; ``method='exact'`` evaluates the same filters exactly (``csrc/crf.cuh``, all pairs,
+~15x slower).  SURVEY.md 8(a) rows a13 / a13'; parity against a pydensecrf binary is unpinned.
 
 The kernels hold two labels -- the path's masks are binary -- so ``num_cl`` / ``n_labels`` other than 2 raise.
-The all-pairs bilateral filter is quadratic in the pixel count: these are tile-sized calls (256 x 256 takes
-about 30 ms); ``getSegmentation(crf=True)`` tiles a slide itself.
+These are tile-sized calls; ``getSegmentation(crf=True)`` tiles a slide itself.
 """
 from __future__ import annotations
 
@@ -26,7 +26,7 @@ def _run(image, p1, **kw):
     return lab[0].cpu().numpy()
 
 
-def post_process_crf(image, final_probabilities, num_cl):
+def post_process_crf(image, final_probabilities, num_cl, method="lattice"):
     """utils.py:568-603: ``image`` uint8 [h, w, 3], ``final_probabilities`` float [h, w, num_cl] (singleton axes
     squeezed away, as the reference does) -> int64 labels [h, w]."""
     if num_cl != 2:
@@ -38,7 +38,7 @@ def post_process_crf(image, final_probabilities, num_cl):
     # two-label mean field only sees the unary difference U1 - U0 = log(clip(p0)) - log(clip(p1)); dp_crf_tiles
     # forms both energies from p1 and 1 - p1, which equals the reference's unary whenever the two channels sum to 1
     # (they are a softmax).
-    return _run(image, probs[..., 1]).astype(np.int64)
+    return _run(image, probs[..., 1], method=method).astype(np.int64)
 
 
 def _prior_from_mask(mask, n_labels, zero_unsure):
@@ -55,7 +55,7 @@ def _prior_from_mask(mask, n_labels, zero_unsure):
     return colors, p1.reshape(mask.shape[:2])
 
 
-def do_crf(im, mask, n_labels, enable_color=False, zero_unsure=True):
+def do_crf(im, mask, n_labels, enable_color=False, zero_unsure=True, method="lattice"):
     """utils.py:548-566 (never called by the reference): refine a hard label ``mask`` [h, w]; returns the MAP in
     the mask's own values.
 
@@ -74,7 +74,7 @@ def do_crf(im, mask, n_labels, enable_color=False, zero_unsure=True):
         image = np.zeros((h, w, 3), np.uint8)               # unused: the bilateral term carries weight 0
         compat_bilateral = 0.0
     MAP = _run(image, p1, n_iter=5, sdims_gauss=3.0, compat_gauss=3.0, sdims_bilateral=80.0, schan_bilateral=13.0,
-               compat_bilateral=compat_bilateral).astype(np.int64)
+               compat_bilateral=compat_bilateral, method=method).astype(np.int64)
     for u in np.unique(MAP):                                # index -> original value, one index after the other
         MAP[MAP == u] = colors[u]
     return MAP

@@ -110,8 +110,8 @@ dense_block_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
   uint64_t* b_empty = b_full + kMaxBStages;
   uint64_t* acc1_full = b_empty + kMaxBStages;
   uint64_t* acc1_empty = acc1_full + 1;
-  uint64_t* t_ready = acc1_empty + 1;    // [2]
-  uint64_t* t_empty = t_ready + 2;       // [2]
+  uint64_t* t_ready = acc1_empty + 1;    // [2 buffers][2 channel chunks]
+  uint64_t* t_empty = t_ready + 4;       // [2]
   uint64_t* acc2_full = t_empty + 2;     // [2]
   uint64_t* acc2_empty = acc2_full + 2;  // [2]
   uint64_t* nb_bar = acc2_empty + 2;     // [2] "every region of my image has published layer l" (l & 1)
@@ -139,7 +139,8 @@ dense_block_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
     mbar_init(acc1_full, 1);
     mbar_init(acc1_empty, 8);         // 8 epilogue warps
     for (int i = 0; i < 2; ++i) {
-      mbar_init(&t_ready[i], 8);
+      mbar_init(&t_ready[2 * i], 8);
+      mbar_init(&t_ready[2 * i + 1], 8);
       mbar_init(&t_empty[i], 1);
       mbar_init(&acc2_full[i], 1);
       mbar_init(&acc2_empty[i], 8);
@@ -271,12 +272,12 @@ dense_block_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
       auto ph2 = [&](int l) {
         const int tb = l & 1;
         const uint32_t u = (l >> 1) & 1;
-        mbar_wait(&t_ready[tb], u);
         mbar_wait(&acc2_empty[tb], u ^ 1);
-        tc_fence_after();
-        dl_trace_ev(tc, 4, l);
         const uint32_t d2 = acc2_col + tb * 32;
         for (int c = 0; c < 2; ++c) {
+          mbar_wait(&t_ready[2 * tb + c], u);     // the 64-channel half of T this pass reads (mid publishes them one by one)
+          tc_fence_after();
+          if (c == 0) dl_trace_ev(tc, 4, l);
           const uint64_t t_desc = t_desc0 + ((tb * kDlTBuf + c * kDlTChunk) >> 4);
           for (int g = 0; g < 9 / kDlW2Group; ++g) {
             mbar_wait(&b_full[sb], pb);
@@ -331,13 +332,15 @@ dense_block_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
       dl_trace_ev(tc, 0, l);
       {
         uint8_t* tbuf = t_base + tb * kDlTBuf;
-        const uint32_t lane_col = acc1_col + half * 64 + (static_cast<uint32_t>(q * 32) << 16);
+        // step s covers bottleneck channels (s >> 1) * 64 + half * 32 + (s & 1) * 16 .. + 15: both warp groups finish
+        // T chunk 0 (channels 0-63) after two steps, so the 3x3 MMAs on chunk 0 overlap the conversion of chunk 1
+        const uint32_t lane_col = acc1_col + half * 32 + (static_cast<uint32_t>(q * 32) << 16);
         const int prow = r;
         const int hh = prow / kDlHaloW, ww = prow - hh * kDlHaloW;
         const int ih = h0 - 1 + hh, iw = w0 - 1 + ww;
         const bool inside = ih >= 0 && ih < p.H && iw >= 0 && iw < p.W;
         auto process = [&](int sidx, const uint32_t (&v)[16]) {
-          const int cb = half * 64 + sidx * 16;
+          const int cb = (sidx >> 1) * 64 + half * 32 + (sidx & 1) * 16;
           if (prow >= kRows) return;
           float f[16];
           epi_affine16(v, nullptr, mid_shift + cb, false, true, f);
@@ -358,10 +361,12 @@ dense_block_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
         tmem_ld16(lane_col + 16, v1);
         process(0, v0);
         tmem_ld_wait();
-        tmem_ld16(lane_col + 32, v0);
+        tmem_ld16(lane_col + 64, v0);
         process(1, v1);
+        fence_proxy_async_smem();
+        mbar_arrive_warp(&t_ready[2 * tb]);
         tmem_ld_wait();
-        tmem_ld16(lane_col + 48, v1);
+        tmem_ld16(lane_col + 80, v1);
         process(2, v0);
         tmem_ld_wait();
         process(3, v1);
@@ -369,7 +374,7 @@ dense_block_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
       tc_fence_before();
       fence_proxy_async_smem();
       mbar_arrive_warp(acc1_empty);
-      mbar_arrive_warp(&t_ready[tb]);
+      mbar_arrive_warp(&t_ready[2 * tb + 1]);
       dl_trace_ev(tc, 2, l);
       // ---- fin(l): acc2[l & 1] -> fp16 -> the 32 new channels of the concat buffer
       mbar_wait(&acc2_full[tb], u);

@@ -20,6 +20,7 @@
 #include "aux.cuh"
 #include "conv_tc.cuh"
 #include "crf.cuh"
+#include "crf_lattice.cuh"
 #include "dense_layer.cuh"
 #include "dense_block.cuh"
 #include "precise.cuh"
@@ -1739,6 +1740,145 @@ int dp_morph_rect(const uint8_t* in, uint8_t* out, uint8_t* tmp, int n0, int n1,
   LAUNCH_OK();
   dp::morph_line_kernel<<<grid_for(total, 256), 256, 0, st>>>(tmp, out, n0, n1, k, 0, dilate ? 1 : 0);
   LAUNCH_OK();
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ lattice CRF
+namespace {
+struct LatGeom {
+  int D, log2cap, cap, m_max;
+  size_t bytes;   // per tile
+};
+LatGeom lat_geom(int D, int N) {
+  LatGeom g;
+  g.D = D;
+  g.m_max = N * (D + 1);
+  g.log2cap = 1;
+  while ((1 << g.log2cap) < 2 * g.m_max) ++g.log2cap;
+  g.cap = 1 << g.log2cap;
+  auto al = [](size_t b) { return (b + 255) / 256 * 256; };
+  g.bytes = al(8ull * g.cap) + al(4ull * g.cap) + al(8ull * g.m_max) + 2 * al(4ull * g.m_max) +
+            al(8ull * (D + 1) * g.m_max) + al(16ull * g.m_max) + 2 * al(8ull * g.m_max) + 256;
+  return g;
+}
+size_t lat_pixel_bytes(int N) { return (size_t)N * (8 + 4 + 4 + 4 + 8 + 8 + 8) + 8 * 256; }
+const int kCrfChunk = 8;
+}  // namespace
+
+size_t dp_crf_lattice_workspace_bytes(int n_tiles, int h, int w) {
+  if (n_tiles < 1 || h < 1 || w < 1) return 0;
+  const int N = h * w, chunk = n_tiles < kCrfChunk ? n_tiles : kCrfChunk;
+  return (size_t)chunk * (lat_geom(2, N).bytes + lat_geom(5, N).bytes + lat_pixel_bytes(N)) +
+         2 * (size_t)chunk * sizeof(dp::LatticeTile) + 1024;
+}
+
+int dp_crf_tiles_lattice(const uint8_t* rgb, const float* p1, int n_tiles, int h, int w, int n_iter, float sdims_gauss,
+                         float compat_gauss, float sdims_bilateral, float schan_bilateral, float compat_bilateral,
+                         void* workspace, size_t workspace_bytes, uint8_t* labels, float* q1_out, void* stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (!rgb || !p1 || !workspace || (!labels && !q1_out)) return fail("null argument");
+  if (n_tiles < 1 || h < 1 || w < 1 || n_iter < 0) return fail("bad CRF geometry");
+  if (!(sdims_gauss > 0) || !(sdims_bilateral > 0) || !(schan_bilateral > 0)) return fail("CRF kernel widths must be positive");
+  if (workspace_bytes < dp_crf_lattice_workspace_bytes(n_tiles, h, w))
+    return fail("CRF workspace too small: need %zu bytes", dp_crf_lattice_workspace_bytes(n_tiles, h, w));
+  if ((reinterpret_cast<uintptr_t>(workspace) & 255) != 0) return fail("CRF workspace must be 256-byte aligned");
+  const int N = h * w;
+  // packed keys hold 12 bits per coordinate: |feature| * scale stays far below 2048 for tile-sized inputs
+  if ((float)(h > w ? h : w) / sdims_gauss > 300.f || 255.f / schan_bilateral > 100.f)
+    return fail("CRF kernel widths too small for the lattice key range");
+  const bool use_bil = compat_bilateral != 0.f;
+  const LatGeom g2 = lat_geom(2, N), g5 = lat_geom(5, N);
+  const int chunk = n_tiles < kCrfChunk ? n_tiles : kCrfChunk;
+  uint8_t* base = static_cast<uint8_t*>(workspace);
+  auto al = [](size_t b) { return (b + 255) / 256 * 256; };
+  // carve: tile structs | per-chunk pixel arrays | lattices
+  dp::LatticeTile* t2_dev = reinterpret_cast<dp::LatticeTile*>(base);
+  dp::LatticeTile* t5_dev = t2_dev + chunk;
+  size_t off = al(2 * (size_t)chunk * sizeof(dp::LatticeTile));
+  auto take = [&](size_t bytes) { uint8_t* q = base + off; off += al(bytes); return q; };
+  float* u = reinterpret_cast<float*>(take((size_t)chunk * N * 8));
+  float* q1 = reinterpret_cast<float*>(take((size_t)chunk * N * 4));
+  float* norm_g = reinterpret_cast<float*>(take((size_t)chunk * N * 4));
+  float* norm_b = reinterpret_cast<float*>(take((size_t)chunk * N * 4));
+  float* fin = reinterpret_cast<float*>(take((size_t)chunk * N * 8));
+  float* fg = reinterpret_cast<float*>(take((size_t)chunk * N * 8));
+  float* fb = reinterpret_cast<float*>(take((size_t)chunk * N * 8));
+  const size_t lat_off = off;
+  std::vector<dp::LatticeTile> t2(chunk), t5(chunk);
+  auto carve_lat = [&](const LatGeom& g, dp::LatticeTile& L) {
+    L.keys = reinterpret_cast<unsigned long long*>(take(8ull * g.cap));
+    L.ids = reinterpret_cast<int*>(take(4ull * g.cap));
+    L.ckeys = reinterpret_cast<unsigned long long*>(take(8ull * g.m_max));
+    L.offset = reinterpret_cast<int*>(take(4ull * g.m_max));
+    L.bary = reinterpret_cast<float*>(take(4ull * g.m_max));
+    L.nb = reinterpret_cast<int*>(take(8ull * (g.D + 1) * g.m_max));
+    L.fix = reinterpret_cast<long long*>(take(16ull * g.m_max));
+    L.val_a = reinterpret_cast<float*>(take(8ull * g.m_max));
+    L.val_b = reinterpret_cast<float*>(take(8ull * g.m_max));
+    L.count = reinterpret_cast<int*>(take(256));
+  };
+  for (int t = 0; t < chunk; ++t) { carve_lat(g2, t2[t]); carve_lat(g5, t5[t]); }
+  const size_t lat_bytes = off - lat_off;
+  if (off > workspace_bytes) return fail("internal: CRF workspace carve exceeds the buffer");
+  CU_OK(cudaMemcpyAsync(t2_dev, t2.data(), chunk * sizeof(dp::LatticeTile), cudaMemcpyHostToDevice, st));
+  CU_OK(cudaMemcpyAsync(t5_dev, t5.data(), chunk * sizeof(dp::LatticeTile), cudaMemcpyHostToDevice, st));
+
+  auto blocks = [](long long n) { return (unsigned)((n + 255) / 256); };
+  for (int t0 = 0; t0 < n_tiles; t0 += chunk) {
+    const int nt = (n_tiles - t0 < chunk) ? n_tiles - t0 : chunk;
+    const long long total = (long long)nt * N;
+    const int ew = grid_for(total, 256);
+    const uint8_t* rgb_c = rgb + (size_t)t0 * N * 3;
+    // keys = empty (all ones), everything else of the lattices (counts, accumulators) = 0
+    CU_OK(cudaMemsetAsync(base + lat_off, 0, lat_bytes, st));
+    for (int t = 0; t < nt; ++t) {
+      CU_OK(cudaMemsetAsync(t2[t].keys, 0xFF, 8ull * g2.cap, st));
+      if (use_bil) CU_OK(cudaMemsetAsync(t5[t].keys, 0xFF, 8ull * g5.cap, st));
+    }
+    auto build = [&](auto Dtag, const LatGeom& g, dp::LatticeTile* tiles, float inv_sd, float inv_sc) {
+      constexpr int D = decltype(Dtag)::value;
+      dp::lat_build_kernel<D><<<dim3(blocks(N), nt), 256, 0, st>>>(rgb_c, h, w, inv_sd, inv_sc, tiles, g.log2cap);
+      dp::lat_compact_kernel<<<dim3(blocks(g.cap), nt), 256, 0, st>>>(tiles, g.cap);
+      dp::lat_remap_kernel<<<dim3(blocks(g.m_max), nt), 256, 0, st>>>(tiles, g.m_max);
+      dp::lat_neighbors_kernel<D><<<dim3(blocks(g.m_max), nt), 256, 0, st>>>(tiles, g.log2cap, g.m_max);
+      g_launches.fetch_add(4, std::memory_order_relaxed);
+    };
+    auto filter = [&](auto Dtag, const LatGeom& g, dp::LatticeTile* tiles, const float* in, float* out) {
+      constexpr int D = decltype(Dtag)::value;
+      dp::lat_splat_kernel<D><<<dim3(blocks(g.m_max), nt), 256, 0, st>>>(tiles, in, N);
+      dp::lat_fix2f_kernel<<<dim3(blocks(g.m_max), nt), 256, 0, st>>>(tiles);
+      for (int j = 0; j <= D; ++j) dp::lat_blur_kernel<<<dim3(blocks(g.m_max), nt), 256, 0, st>>>(tiles, j, g.m_max);
+      dp::lat_slice_kernel<D><<<dim3(blocks(N), nt), 256, 0, st>>>(tiles, out, N);
+      g_launches.fetch_add(D + 4, std::memory_order_relaxed);
+    };
+    using D2 = std::integral_constant<int, 2>;
+    using D5 = std::integral_constant<int, 5>;
+    build(D2{}, g2, t2_dev, 1.f / sdims_gauss, 0.f);
+    if (use_bil) build(D5{}, g5, t5_dev, 1.f / sdims_bilateral, 1.f / schan_bilateral);
+    dp::mf_init_kernel<<<ew, 256, 0, st>>>(p1 + (size_t)t0 * N, total, u, q1, fin);
+    filter(D2{}, g2, t2_dev, fin, fg);
+    dp::mf_norm_kernel<<<ew, 256, 0, st>>>(fg, total, norm_g);
+    if (use_bil) {
+      filter(D5{}, g5, t5_dev, fin, fb);
+      dp::mf_norm_kernel<<<ew, 256, 0, st>>>(fb, total, norm_b);
+    }
+    uint8_t* lab_c = labels ? labels + (size_t)t0 * N : nullptr;
+    float* q_c = q1_out ? q1_out + (size_t)t0 * N : nullptr;
+    if (n_iter == 0)
+      dp::mf_update_kernel<<<ew, 256, 0, st>>>(u, nullptr, nullptr, 0.f, nullptr, nullptr, 0.f, total, q1, lab_c, q_c);
+    for (int it = 0; it < n_iter; ++it) {
+      dp::mf_scale_kernel<<<ew, 256, 0, st>>>(q1, norm_g, total, fin);
+      filter(D2{}, g2, t2_dev, fin, fg);
+      if (use_bil) {
+        dp::mf_scale_kernel<<<ew, 256, 0, st>>>(q1, norm_b, total, fin);
+        filter(D5{}, g5, t5_dev, fin, fb);
+      }
+      const bool last = it + 1 == n_iter;
+      dp::mf_update_kernel<<<ew, 256, 0, st>>>(u, fg, norm_g, compat_gauss, use_bil ? fb : nullptr, norm_b, compat_bilateral,
+                                               total, q1, last ? lab_c : nullptr, last ? q_c : nullptr);
+    }
+    LAUNCH_OK();
+  }
   return 0;
 }
 

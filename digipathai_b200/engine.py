@@ -272,24 +272,30 @@ def pyramid_down2(plane: torch.Tensor) -> torch.Tensor:
 
 def dense_crf(rgb: torch.Tensor, p1: torch.Tensor, n_iter: int = 10, sdims_gauss: float = 10.0,
               compat_gauss: float = 3.0, sdims_bilateral: float = 50.0, schan_bilateral: float = 20.0,
-              compat_bilateral: float = 10.0, return_marginal: bool = False):
+              compat_bilateral: float = 10.0, return_marginal: bool = False, method: str = "lattice"):
     """Fully connected CRF refinement (``post_process_crf``, DigiPathAI/helpers/utils.py:568-603; defaults = its
     parameters).  rgb cuda uint8 [n,h,w,3]; p1 cuda float32 [n,h,w]; returns cuda uint8 labels [n,h,w] in {0,1}
-    (and the label-1 marginal when asked)."""
+    (and the label-1 marginal when asked).  ``method='lattice'``: Gaussian filters on the permutohedral lattice, as
+    pydensecrf evaluates them (csrc/crf_lattice.cuh); ``'exact'``: all-pairs evaluation of the same filters
+    (csrc/crf.cuh, ~15x slower)."""
     assert rgb.is_cuda and rgb.dtype == torch.uint8 and rgb.dim() == 4 and rgb.shape[3] == 3 and rgb.is_contiguous()
     assert p1.is_cuda and p1.dtype == torch.float32 and p1.shape == rgb.shape[:3] and p1.is_contiguous()
     n, h, w = p1.shape
-    nbytes = int(_lib.lib.dp_crf_workspace_bytes(n, h, w))
-    ws = torch.empty(nbytes // 4, dtype=torch.float32, device=p1.device)
+    if method not in ("lattice", "exact"):
+        raise ValueError("method must be 'lattice' or 'exact'")
+    ws_fn, run_fn = ((_lib.lib.dp_crf_lattice_workspace_bytes, _lib.lib.dp_crf_tiles_lattice) if method == "lattice"
+                     else (_lib.lib.dp_crf_workspace_bytes, _lib.lib.dp_crf_tiles))
+    nbytes = int(ws_fn(n, h, w))
+    ws = torch.empty((nbytes + 3) // 4, dtype=torch.float32, device=p1.device)
     labels = torch.empty((n, h, w), dtype=torch.uint8, device=p1.device)
     q1 = torch.empty((n, h, w), dtype=torch.float32, device=p1.device) if return_marginal else None
     _lib.check(
-        _lib.lib.dp_crf_tiles(C.c_void_p(rgb.data_ptr()), C.c_void_p(p1.data_ptr()), n, h, w, int(n_iter),
+        run_fn(C.c_void_p(rgb.data_ptr()), C.c_void_p(p1.data_ptr()), n, h, w, int(n_iter),
                               float(sdims_gauss), float(compat_gauss), float(sdims_bilateral), float(schan_bilateral),
                               float(compat_bilateral), C.c_void_p(ws.data_ptr()), nbytes,
                               C.c_void_p(labels.data_ptr()),
                               C.c_void_p(q1.data_ptr()) if q1 is not None else C.c_void_p(None), _stream_ptr()),
-        "dp_crf_tiles")
+        "dp_crf_tiles" if method == "exact" else "dp_crf_tiles_lattice")
     return (labels, q1) if return_marginal else labels
 
 

@@ -192,6 +192,18 @@ int dp_crf_tiles(const uint8_t* rgb, const float* p1, int n_tiles, int h, int w,
                  float compat_gauss, float sdims_bilateral, float schan_bilateral, float compat_bilateral,
                  void* workspace, size_t workspace_bytes, uint8_t* labels, float* q1_out, void* stream);
 
+/*
+ * The same inference with the Gaussian filters evaluated on the permutohedral lattice (splat / blur / slice), i.e.
+ * the approximation pydensecrf itself uses -- what post_process_crf / do_crf of DigiPathAI/helpers/utils.py:548-603
+ * compute through `d.inference(n)`.  Same arguments as dp_crf_tiles; the workspace is larger (hash tables, blur
+ * neighbours: dp_crf_lattice_workspace_bytes, ~75 MB per tile for up to 8 tiles processed at a time) and must be
+ * 256-byte aligned.  compat_bilateral == 0 leaves the bilateral term (and its lattice) out.  Bit-reproducible.
+ */
+size_t dp_crf_lattice_workspace_bytes(int n_tiles, int h, int w);
+int dp_crf_tiles_lattice(const uint8_t* rgb, const float* p1, int n_tiles, int h, int w, int n_iter, float sdims_gauss,
+                         float compat_gauss, float sdims_bilateral, float schan_bilateral, float compat_bilateral,
+                         void* workspace, size_t workspace_bytes, uint8_t* labels, float* q1_out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
