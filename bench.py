@@ -195,7 +195,7 @@ def main():
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="forward", choices=["forward", "slide"])
+    ap.add_argument("--workload", default="forward", choices=["forward", "slide", "config5"])
     ap.add_argument("--model", default="dense", choices=["dense", "inception", "deeplabv3"],
                     help="graph to run (BASELINE configs[1] names the DenseNet U-Net: the default)")
     ap.add_argument("--slide", type=int, default=8192, help="--workload slide: side of the synthetic slide")
@@ -254,6 +254,18 @@ def main():
         return float(t.item())
 
     peaks, peak_src = load_peaks()
+    if args.workload == "config5":
+        rec = config5_record(args, rank, world, local, dev, barrier, max_over_ranks)
+        if rank == 0:
+            print(json.dumps({"metric": "ensemble_tiles_per_sec_256x256_b64_crf", "value": rec["tiles_per_s"], "unit": UNIT,
+                              "n_gpus": world, "steps": rec["reps"], "warmup": 1, "ms_per_step": rec["seconds"] * 1e3,
+                              "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+                              "dtype": DTYPE[args.precision], "data": "synthetic",
+                              "config": {"workload": rec["workload"]}, "config5": rec,
+                              "gpu_launches": rec["gpu_launches"]}))
+        if world > 1:
+            dist.destroy_process_group()
+        return
     if args.model == "deeplabv3":
         from digipathai_b200.models.deeplab import deeplabv3plus_xception_program, init_deeplab_weights
         model = engine.TileModel(deeplabv3plus_xception_program(init_deeplab_weights(0), PATCH, precision=args.precision),
@@ -541,6 +553,57 @@ def parity_and_fp32_records(local, fp16_model):
                  "achieved_tflops_fp32": REF_FLOP["dense"] * BATCH / (ms * 1e-3) / 1e12,
                  "what": "precision='fp32': fp32 weights / activations / FMA accumulation (csrc/precise.cuh), batch 32"}
     return parity, fp32_mode
+
+
+def config5_record(args, rank, world, local, dev, barrier, max_over_ranks):
+    """BASELINE configs[4]: the reference's ensemble (quick=False: DenseNet + Inception-ResNet-v2 + DeepLabv3+ U-Nets,
+    Segmentation.py:288-291) at batch 64 on one synthetic slide, threshold 0.3, then crf=True (post_process_crf on the
+    permutohedral lattice, per 256 x 256 block), sharded by x-stripes over the ranks.  One untimed run, then timed
+    runs (host wall clock between device-synchronising barriers, max over ranks)."""
+    import torch
+    from digipathai_b200 import engine
+    from digipathai_b200.dist import sharded_get_prediction
+    from digipathai_b200.models.deeplab import deeplabv3plus_xception_program, init_deeplab_weights
+    from digipathai_b200.models.densenet import densenet121_unet_program, init_densenet_weights
+    from digipathai_b200.models.inception import inception_resnet_v2_unet_program, init_inception_weights
+    from digipathai_b200.slide import synthetic_slide_device
+    B5, S = 64, args.slide
+    prec = args.precision
+    models = {
+        "dense": engine.TileModel(densenet121_unet_program(init_densenet_weights(0), PATCH, precision=prec), local, B5),
+        "inception": engine.TileModel(inception_resnet_v2_unet_program(init_inception_weights(0), PATCH, precision=prec), local, B5),
+        "deeplabv3": engine.TileModel(deeplabv3plus_xception_program(init_deeplab_weights(0), PATCH, precision=prec), local, B5),
+    }
+    levels = 1
+    while S // (2 ** (levels - 1)) > 2500 and levels < 5:
+        levels += 1
+    slide = synthetic_slide_device(S, S, dev, seed=0, n_levels=levels)
+    reps = max(1, min(args.steps, 3))
+    n0 = engine.kernel_launch_count()
+    times, info, grid = [], None, None
+    for it in range(reps + 1):
+        barrier()
+        t0 = time.perf_counter()
+        grid, out, info = sharded_get_prediction(slide, models, B5, None, PATCH, 128, device=local, threshold=0.3, crf=True)
+        barrier()
+        times.append(max_over_ranks(time.perf_counter() - t0))
+        del out
+    best = min(times[1:])
+    tm = info["timings_ms"]
+    n_tiles = len(grid.coords)
+    crf_tiles = int(max_over_ranks(float(info["crf_tiles"])))
+    rec = {"workload": f"configs[4]: 3-model ensemble (DenseNet-121 / Inception-ResNet-v2 / DeepLabv3+ U-Nets) + crf=True "
+                       f"on one synthetic {S}x{S} slide, patch 256 stride 128 batch 64, 1 pass, {n_tiles} tiles = "
+                       f"{3 * n_tiles} tile-forwards, x-stripe sharding over {world} rank(s)",
+           "n_gpus": world, "tiles": n_tiles, "seconds": best, "tiles_per_s": n_tiles / best, "reps": reps,
+           "all_seconds": [round(t, 4) for t in times], "crf_blocks_max_rank": crf_tiles,
+           "loop_ms": max_over_ranks(float(tm.get("loop_ms", 0.0))), "crf_ms": max_over_ranks(float(tm.get("crf_ms", 0.0))),
+           "halo_ms": max_over_ranks(float(tm.get("halo_ms", 0.0))), "grid_ms": max_over_ranks(float(tm.get("grid_ms", 0.0))),
+           "crf": "permutohedral lattice (dp_crf_tiles_lattice), 10 mean-field iterations, non-overlapping 256x256 blocks",
+           "gpu_launches": int(engine.kernel_launch_count() - n0)}
+    for m in models.values():
+        m.close()
+    return rec
 
 
 def slide_record(model, S, tta_list, rank, world, local, dev, barrier, max_over_ranks, reps=1, with_n1=False):

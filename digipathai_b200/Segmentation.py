@@ -150,27 +150,39 @@ def get_prediction(wsi_path, mask_path=None, label_path=None, batch_size=64, mod
     return (slide, out)
 
 
-def _crf_refine(engine, torch, slide, mean, label, P, batch):
+def _crf_refine(engine, torch, slide, mean, label, P, batch, x_lo=0, own=None):
     """``crf=True``: the reference's intent (Segmentation.py:327-331, commented out there) is
     ``post_process_crf(img, [1 - mean, mean], 2)`` on the whole slide, which pydensecrf cannot hold in memory at WSI
-    size.  Here the fully connected CRF of utils.py:568-603 is applied per non-overlapping P x P tile (edge tiles
-    clamped inside the slide) wherever the probability map is not identically background; the MAP label replaces
-    the thresholded label ({0, 255}).  Planes are in the reference's [x, y] orientation; the CRF is symmetric in
-    the two image axes, so no transpose is needed."""
-    W, H = mean.shape
+    size.  Here the fully connected CRF of utils.py:568-603 is applied per non-overlapping P x P block of the slide
+    (blocks at the far edges clamped inside) wherever the probability map is not identically background; the MAP label
+    replaces the thresholded label ({0, 255}).  Planes are in the reference's [x, y] orientation; the CRF is symmetric
+    in the two image axes, so no transpose is needed.
+
+    ``mean`` / ``label`` may be a stripe of the slide starting at column ``x_lo`` (sharded runs); ``own=(lo, hi)``
+    restricts the work to the blocks whose first column lies in ``[lo, hi)`` -- every block has exactly one owner."""
+    Ws, H = mean.shape
+    W = slide.level_dimensions[0][0]
     if W < P or H < P:
-        return
-    raster = upload_xy_raster(slide, 0, W, mean.device)          # uint8 [x, y, c]
-    xs = sorted({min(x, W - P) for x in range(0, W, P)})
+        return 0
+    lo, hi = (0, W) if own is None else own
+    xs = sorted({min(x, W - P) for x in range(0, W, P) if lo <= x < hi})
+    xs = [x for x in xs if x >= x_lo and x + P <= x_lo + Ws]         # the block must lie inside this stripe
     ys = sorted({min(y, H - P) for y in range(0, H, P)})
-    todo = [(x, y) for x in xs for y in ys if float(mean[x:x + P, y:y + P].max()) > 1e-5]
+    if not xs:
+        return 0
+    raster = upload_xy_raster(slide, x_lo, x_lo + Ws, mean.device)    # uint8 [x, y, c] of the stripe
+    # block maxima in one pass: blocks whose probability map is identically background are skipped
+    col_max = torch.stack([mean[x - x_lo:x - x_lo + P].amax(0) for x in xs])              # [nx, H]
+    blk_max = torch.stack([col_max[:, y:y + P].amax(1) for y in ys], 1).cpu().numpy()     # [nx, ny]
+    todo = [(xs[i], ys[j]) for i in range(len(xs)) for j in range(len(ys)) if blk_max[i, j] > 1e-5]
     for s in range(0, len(todo), batch):
         chunk = todo[s:s + batch]
-        rgb = torch.stack([raster[x:x + P, y:y + P] for x, y in chunk]).contiguous()
-        p1 = torch.stack([mean[x:x + P, y:y + P] for x, y in chunk]).contiguous()
+        rgb = torch.stack([raster[x - x_lo:x - x_lo + P, y:y + P] for x, y in chunk]).contiguous()
+        p1 = torch.stack([mean[x - x_lo:x - x_lo + P, y:y + P] for x, y in chunk]).contiguous()
         lab = engine.dense_crf(rgb, p1)
         for (x, y), l in zip(chunk, lab):
-            label[x:x + P, y:y + P] = l * 255
+            label[x - x_lo:x - x_lo + P, y:y + P] = l * 255
+    return len(todo)
 
 
 def _default_weight_path(mode, model):

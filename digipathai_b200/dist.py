@@ -165,7 +165,8 @@ def local_part(slide, models, rank: int, world: int, batch_size=32, tta_list=Non
 
 
 def sharded_get_prediction(wsi_path, models, batch_size=32, tta_list=None, patch_size=256, stride_size=128,
-                           status=None, device=None, gather=False, tissue_mask=None, shard=None):
+                           status=None, device=None, gather=False, tissue_mask=None, shard=None, threshold=None,
+                           crf=False):
     """``get_prediction`` across the ranks of the default process group (one process per GPU; a process without an
     initialised group is a world of one; ``shard=(rank, world)`` overrides both -- ``shard=(0, 1)`` runs the whole
     slide on the calling rank alone, which is how bench.py measures the one-GPU time beside an N-GPU run).
@@ -174,7 +175,9 @@ def sharded_get_prediction(wsi_path, models, batch_size=32, tta_list=None, patch
     takes its contiguous range of batches, runs the device loop on its stripe, swaps halos, then normalises its
     stripe.  Returns ``(grid, planes_dict, info)``; with ``gather=True`` rank 0's dict holds the full planes.
     ``info['timings_ms']`` splits this rank's wall time into grid / raster upload / tile loop / halo / normalise
-    (each phase ends with a device synchronisation).
+    (each phase ends with a device synchronisation).  ``threshold`` (getSegmentation's 0.3) adds the rank's uint8
+    label stripe ``res['label']``; ``crf=True`` then refines it tile-wise (Segmentation._crf_refine) on the P x P blocks
+    this rank owns (first column inside its owned range; every block of the slide has exactly one owner).
     """
     import time
     import torch
@@ -199,14 +202,28 @@ def sharded_get_prediction(wsi_path, models, batch_size=32, tta_list=None, patch
         torch.cuda.synchronize(planes[0].device)
     tm['halo_ms'] = (time.perf_counter() - t0) * 1e3
     t0 = time.perf_counter()
+    label = None
     if hi > lo:
         with torch.cuda.device(planes[0].device):
-            engine.finalize(planes[0], planes[1], planes[2], 0.0, None)
+            if threshold is not None:
+                label = torch.empty(planes[0].shape, dtype=torch.uint8, device=planes[0].device)
+            engine.finalize(planes[0], planes[1], planes[2], float(threshold) if threshold is not None else 0.0, label)
             torch.cuda.synchronize()
     tm['normalise_ms'] = (time.perf_counter() - t0) * 1e3
+    n_crf = 0
+    if crf and label is not None:
+        from .Segmentation import _crf_refine
+        t0 = time.perf_counter()
+        with torch.cuda.device(planes[0].device):
+            n_crf = _crf_refine(engine, torch, slide, planes[0], label, int(patch_size), int(batch_size),
+                                x_lo=stripes[rank][0], own=owned_ranges(stripes)[rank])
+            torch.cuda.synchronize()
+        tm['crf_ms'] = (time.perf_counter() - t0) * 1e3
     info = {'rank': rank, 'world': world, 'batches': (lo, hi), 'stripe': stripes[rank], 'halo_bytes_sent': sent,
-            'timings_ms': tm}
+            'timings_ms': tm, 'crf_tiles': n_crf}
     res = {'mean': planes[0], 'var': planes[1], 'x_range': stripes[rank]}
+    if label is not None:
+        res['label'] = label
     if gather:
         W = slide.level_dimensions[0][0]
         full = gather_planes(planes[:2], stripes, rank, world, W) if world > 1 else planes[:2]

@@ -152,6 +152,46 @@ def test_get_segmentation_fp32_mode_returns_the_reference_label_map(env):
     assert (np.abs(want_mean - 0.3)[mism] <= 1e-3).all()
 
 
+def test_config5_ensemble_plus_crf_matches_the_oracle_pipeline(env):
+    """BASELINE configs[4] in miniature: quick=False (the reference's three-model ensemble, Segmentation.py:288-291) +
+    crf=True, precision='fp32'.  Oracle = pipeline_ref.getSegmentation on the three oracle graphs, then the lattice
+    restatement of post_process_crf (oracle/lattice_ref.py, utils.py:568-603) on the same non-overlapping 256 x 256
+    blocks.  The label map must be identical wherever the oracle's CRF marginal is further than 1e-3 from 0.5."""
+    from digipathai_b200.Segmentation import getSegmentation
+    from digipathai_b200.models.deeplab import init_deeplab_weights
+    from digipathai_b200.models.inception import init_inception_weights
+    from digipathai_b200.slide import level0_xy_raster
+    from oracle import deeplab_ref, inception_ref, lattice_ref, pipeline_ref
+    w, slide, omodels = env                       # 1024 x 768, one level: 4 x 3 CRF blocks
+    rng = np.random.default_rng(12)
+    calib = (rng.integers(0, 256, (2, 256, 256, 3)).astype(np.float32) - 128.0) / 128.0
+    wi = inception_ref.calibrate_bn(init_inception_weights(5), calib)
+    wd = deeplab_ref.calibrate_bn(init_deeplab_weights(6), calib)
+    three = {"dense": omodels["dense"], "inception": inception_ref.OracleModel(wi), "deeplabv3": deeplab_ref.OracleModel(wd)}
+    want_thr, want_mean, _ = pipeline_ref.getSegmentation(slide, three, 256, 256, 4)
+    got = getSegmentation(slide, patch_size=256, stride_size=256, batch_size=4, quick=False, crf=True,
+                          weights={"dense": w, "inception": wi, "deeplabv3": wd}, precision="fp32")
+    raster = level0_xy_raster(slide)
+    want = want_thr.copy()
+    sure = np.ones(want.shape, bool)
+    n_blocks = 0
+    for x in range(0, want.shape[0], 256):
+        for y in range(0, want.shape[1], 256):
+            blk = want_mean[x:x + 256, y:y + 256]
+            if blk.max() <= 1e-5:
+                continue
+            lab, q = lattice_ref.dense_crf(raster[x:x + 256, y:y + 256], blk)
+            want[x:x + 256, y:y + 256] = lab * 255
+            sure[x:x + 256, y:y + 256] = np.abs(q - 0.5) > 1e-3
+            n_blocks += 1
+    assert n_blocks > 0 and sure.mean() > 0.95
+    mism = (got != want) & sure
+    print(f"\nconfig-5 miniature: {n_blocks} CRF blocks, {int((got != want).sum())} label differences, "
+          f"{int(mism.sum())} outside the |q - 0.5| < 1e-3 band")
+    assert mism.sum() == 0
+    assert (want != want_thr).sum() > 0          # the CRF changed labels
+
+
 def test_get_segmentation_writes_pyramidal_tiffs(env, tmp_path):
     """Default export = what the reference leaves on disk after its ImageMagick pass (Segmentation.py:333-352): tiled
     pyramidal JPEG TIFFs; level 0 of the mask file is the returned label map up to JPEG loss."""
