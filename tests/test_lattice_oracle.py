@@ -21,7 +21,7 @@ def test_lattice_impulse_response_is_a_gaussian_of_the_requested_width():
         assert abs(sigma - sd) / sd < 0.12, (sd, sigma)                  # measured 3.12 / 6.41
         py, px = divmod(int(out.argmax()), w)                             # the lattice is not centred on pixels:
         tol = sd / 2 + 1                                                   # ... the peak sits within half a cell
-        assert abs(py - h // 2) <= tol and abs(px - w // 2) <= tol and (out >= 0).all()
+        assert abs(py - h // 2) <= tol and abs(px - w // 2) <= tol and out.min() > -1e-6
 
 
 def test_lattice_bilateral_filter_tracks_the_exact_filter_and_the_crf_labels_agree():
