@@ -20,6 +20,15 @@
 //   * per-layer facts (tensor maps of W1 / W2, BN vectors, channel count) come from a table in global memory; the
 //     BN vectors are read through L1 (prefetched at layer start) instead of being staged in shared memory.
 // Clusters are independent of each other (images are), so there is no grid-wide residency requirement.
+//   * the chunk that holds layer l's 32 new channels does not make the round trip through L2 at all: the block's input
+//     channel count is a multiple of 64, so that chunk is always one that was OPENED inside this kernel, and it lives
+//     as a raw fp16 "tail tile" (100 halo rows x 64 channels, two buffers by chunk parity) in shared memory.  The
+//     final epilogue writes a region's new channels into its own tail tile and -- for pixels on a region border --
+//     into the halo rows of the neighbouring CTAs' tail tiles through distributed shared memory
+//     (st.shared::cluster), then arrives on the cluster barriers; the transform warps wait for that barrier and read
+//     the tail tile instead of a TMA-filled stage.  Global memory still receives every new channel (later layers load
+//     it as an ordinary "safe" chunk, the decoder reads the block's output); the producer waits for layer l-2's
+//     barrier -- one whole layer of slack -- before the TMA load that first touches layer l-2's channels.
 //
 // MMA issue order: ph1(0) | ph2(0) ph1(1) | ph2(1) ph1(2) | ...   (ph2(l) gates everything downstream, so it goes
 // first; the tensor pipe then works through layer l+1's prefetched chunks while layer l is stored and published).
@@ -54,14 +63,15 @@ struct DenseBlockParams {
 struct DenseBlockSmem {
   static constexpr int kBarBytes = 1024;
   static constexpr int kMidBytes = 2 * 128 * 4;   // BN2 shift of the current and the next layer
-  int a_off, b_off, t_off, mid_off, total;
+  int a_off, b_off, t_off, mid_off, tail_off, total;
 };
 
 __host__ __device__ inline DenseBlockSmem dense_block_smem(const DenseBlockParams& p) {
   DenseBlockSmem L;
   L.mid_off = DenseBlockSmem::kBarBytes;
   L.t_off = L.mid_off + DenseBlockSmem::kMidBytes;
-  L.a_off = L.t_off + dl_t_bytes(8);
+  L.tail_off = L.t_off + dl_t_bytes(8) / 2;     // ONE bottleneck tile (2 chunks): see the note at `tbuf`
+  L.a_off = L.tail_off + 2 * dl_a_stage(8);
   L.b_off = L.a_off + p.a_stages * dl_a_stage(8);
   L.total = L.b_off + p.b_stages * kDlBStage + 1024;
   return L;
@@ -89,6 +99,17 @@ __device__ __forceinline__ bool mbar_try_wait_acquire_cluster(uint64_t* bar, uin
       : "r"(smem_u32(bar)), "r"(parity)
       : "memory");
   return ok != 0;
+}
+// 16-byte store into the shared memory of CTA `rank` of this cluster, at the address `local` has in this CTA
+__device__ __forceinline__ void st_cluster_v4(const void* local, uint32_t rank, uint32_t a, uint32_t b, uint32_t c,
+                                              uint32_t d) {
+  asm volatile(
+      "{\n\t"
+      ".reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "st.shared::cluster.v4.b32 [ra], {%2, %3, %4, %5};\n\t"
+      "}\n" ::"r"(smem_u32(local)), "r"(rank), "r"(a), "r"(b), "r"(c), "r"(d)
+      : "memory");
 }
 __device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
 __device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
@@ -121,8 +142,10 @@ dense_block_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
   uint8_t* a_base = smem + L.a_off;
   uint8_t* b_base = smem + L.b_off;
   uint8_t* t_base = smem + L.t_off;
+  uint8_t* tail_base = smem + L.tail_off;      // [2][kAStage] raw fp16 tail tiles (see header)
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  for (int i = tid; i < 2 * kAStage / 16; i += blockDim.x) reinterpret_cast<uint4*>(tail_base)[i] = make_uint4(0, 0, 0, 0);
   if (tid == 0 && p.gt_layers && blockIdx.x == 0) p.gt_layers[0] = globaltimer_ns();
 
   if (warp == 0 && lane == 0) tma_prefetch_desc(&map_x);
@@ -178,29 +201,29 @@ dense_block_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
       const int n_safe = (l == 0) ? 0 : (C - 32) / 64;     // chunks made only of channels older than layer l-1's output
       if (l == NL - 1 && lane == 0) pdl_launch_dependents();
       for (int c = 0; c < n_chunks; ++c) {
-        if (c == n_safe) {
-          if (l == 0) {
-            if (lane == 0) pdl_wait();            // the block's input comes from the preceding kernel
-          } else {
-            if (lane == 0) {
-              uint32_t spins = 0;
-              while (!mbar_try_wait_acquire_cluster(&nb_bar[(l - 1) & 1], ((l - 1) >> 1) & 1)) {
-                if (++spins > (1u << 26)) {
-                  printf("dp: dense block neighbour barrier timeout block %d layer %d\n", blockIdx.x, l);
-                  __trap();
-                }
-              }
-              fence_proxy_async_all();            // the acquired generic-proxy writes are read by TMA (async proxy)
+        if (l == 0 && c == 0 && lane == 0) pdl_wait();      // the block's input comes from the preceding kernel
+        if (l >= 2 && c == (n_safe > 0 ? n_safe - 1 : 0) && lane == 0) {
+          // the last safe chunk may hold layer l-2's channels: they must be visible in global memory (all CTAs of
+          // the image published layer l-2 a whole layer ago: this wait is off the critical path)
+          uint32_t spins = 0;
+          while (!mbar_try_wait_acquire_cluster(&nb_bar[(l - 2) & 1], ((l - 2) >> 1) & 1)) {
+            if (++spins > (1u << 26)) {
+              printf("dp: dense block barrier timeout (producer) block %d layer %d\n", blockIdx.x, l);
+              __trap();
             }
-            __syncwarp();
-            if (lane == 0) dl_trace_ev(tc0, 2, l);
           }
+          fence_proxy_async_all();                // the acquired generic-proxy writes are read by TMA (async proxy)
         }
         if (lane == 0) {
           mbar_wait(&a_empty[sa], pa ^ 1);
-          mbar_expect_tx(&a_full[sa], kRows * 128);
-          tma_load_4d(&map_x, &a_full[sa], a_base + sa * kAStage, c * 64, w0 - 1, h0 - 1, n0);
-          dl_trace_ev(tc0, 1, l);
+          if (l > 0 && c == n_safe) {
+            mbar_arrive(&a_full[sa]);             // slot is free; its data comes from the tail tile (transform warps)
+            dl_trace_ev(tc0, 2, l);
+          } else {
+            mbar_expect_tx(&a_full[sa], kRows * 128);
+            tma_load_4d(&map_x, &a_full[sa], a_base + sa * kAStage, c * 64, w0 - 1, h0 - 1, n0);
+            dl_trace_ev(tc0, 1, l);
+          }
         }
         if (++sa == static_cast<uint32_t>(p.a_stages)) { sa = 0; pa ^= 1; }
         __syncwarp();
@@ -278,7 +301,7 @@ dense_block_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
           mbar_wait(&t_ready[2 * tb + c], u);     // the 64-channel half of T this pass reads (mid publishes them one by one)
           tc_fence_after();
           if (c == 0) dl_trace_ev(tc, 4, l);
-          const uint64_t t_desc = t_desc0 + ((tb * kDlTBuf + c * kDlTChunk) >> 4);
+          const uint64_t t_desc = t_desc0 + ((c * kDlTChunk) >> 4);
           for (int g = 0; g < 9 / kDlW2Group; ++g) {
             mbar_wait(&b_full[sb], pb);
             tc_fence_after();
@@ -331,7 +354,9 @@ dense_block_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
       tc_fence_after();
       dl_trace_ev(tc, 0, l);
       {
-        uint8_t* tbuf = t_base + tb * kDlTBuf;
+        // One T tile is enough here: mid(l+1) starts on acc1_full(l+1), a tcgen05.commit issued after ph2(l)'s MMAs by
+        // the same thread, so every 3x3 read of layer l's tile has completed before layer l+1's tile is written.
+        uint8_t* tbuf = t_base;
         // step s covers bottleneck channels (s >> 1) * 64 + half * 32 + (s & 1) * 16 .. + 15: both warp groups finish
         // T chunk 0 (channels 0-63) after two steps, so the 3x3 MMAs on chunk 0 overlap the conversion of chunk 1
         const uint32_t lane_col = acc1_col + half * 32 + (static_cast<uint32_t>(q * 32) << 16);
@@ -394,14 +419,41 @@ dense_block_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
           __half2 h2 = __floats2half2_rn(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1]));
           pk[i] = *reinterpret_cast<uint32_t*>(&h2);
         }
-        if (valid) st_global_v8(orow + 16 * half, pk);
+        if (valid) {
+          st_global_v8(orow + 16 * half, pk);
+          // the same 16 channels into the tail tiles: chunk C / 64, 16-byte chunks (C % 64) / 8 + 2 half, +1
+          const int C = Lr->C;
+          uint8_t* tail = tail_base + ((C >> 6) & 1) * kAStage;
+          const int j = ((C & 63) >> 3) + 2 * half;
+          const int y = r >> 3, x = r & 7;
+          {
+            const int row = (y + 1) * kDlHaloW + (x + 1);
+            *reinterpret_cast<uint4*>(tail + row * 128 + ((j ^ (row & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+            *reinterpret_cast<uint4*>(tail + row * 128 + (((j + 1) ^ (row & 7)) << 4)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+          }
+          if (p.cluster_size > 1) {
+#pragma unroll
+            for (int dy = -1; dy <= 1; ++dy)
+#pragma unroll
+              for (int dx = -1; dx <= 1; ++dx) {
+                if (dy == 0 && dx == 0) continue;
+                if ((dy < 0 && y != 0) || (dy > 0 && y != RH - 1) || (dx < 0 && x != 0) || (dx > 0 && x != 7)) continue;
+                const int r2 = trow + dy, c2 = tw + dx;
+                if (r2 < 0 || r2 >= p.tiles_h || c2 < 0 || c2 >= p.tiles_w) continue;
+                const uint32_t peer = static_cast<uint32_t>(r2 * p.tiles_w + c2);
+                const int row = (y + 1 - RH * dy) * kDlHaloW + (x + 1 - 8 * dx);     // my pixel in the peer's halo frame
+                st_cluster_v4(tail + row * 128 + ((j ^ (row & 7)) << 4), peer, pk[0], pk[1], pk[2], pk[3]);
+                st_cluster_v4(tail + row * 128 + (((j + 1) ^ (row & 7)) << 4), peer, pk[4], pk[5], pk[6], pk[7]);
+              }
+          }
+        }
       }
       tc_fence_before();
       mbar_arrive_warp(&acc2_empty[tb]);
       dl_trace_ev(tc, 1, l);
       // ---- publish: CTA barrier over the epilogue warps, then one release-arrive per cluster CTA (thread r -> CTA r):
-      //      the barrier orders every warp's stores before the arrive, the release makes them visible at cluster
-      //      scope (the pattern of a cooperative-groups grid sync; 256 per-thread fences cost 3.6k clk here)
+      //      the barrier orders every warp's global, local and remote stores before the arrive, the release makes them
+      //      visible at cluster scope (the pattern of a cooperative-groups grid sync)
       asm volatile("bar.sync 1, 256;" ::: "memory");
       if (r < p.cluster_size && half == 0) mbar_arrive_remote_release(&nb_bar[l & 1], static_cast<uint32_t>(r));
       if (r == 0 && half == 0) {
@@ -440,15 +492,28 @@ dense_block_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
         const float4 sh0 = __ldg(reinterpret_cast<const float4*>(pro_shift + ch));
         const float4 sh1 = __ldg(reinterpret_cast<const float4*>(pro_shift + ch + 4));
         mbar_wait(&a_full[sa], pa);
+        uint8_t* stage_base = a_base + sa * kAStage;
+        const uint8_t* src_base = stage_base;
+        if (l > 0 && c == (Lr->C - 32) / 64) {
+          // the chunk with layer l-1's channels: raw data sits in the tail tile once every CTA of the image has
+          // published layer l-1 (their border pixels are written straight into this CTA's tile)
+          uint32_t spins = 0;
+          while (!mbar_try_wait_acquire_cluster(&nb_bar[(l - 1) & 1], ((l - 1) >> 1) & 1)) {
+            if (++spins > (1u << 26)) {
+              printf("dp: dense block barrier timeout (transform) block %d layer %d\n", blockIdx.x, l);
+              __trap();
+            }
+          }
+          src_base = tail_base + (c & 1) * kAStage;
+        }
         dl_trace_ev(tc, 1, l);
         {
-          uint8_t* stage_base = a_base + sa * kAStage;
           constexpr int kIter = (kRows + 31) / 32;
           uint4 raw[kIter];
 #pragma unroll
           for (int j = 0; j < kIter; ++j) {
             const int rr = (t >> 3) + 32 * j;
-            if (rr < kRows) raw[j] = *reinterpret_cast<const uint4*>(stage_base + rr * 128 + ((i ^ (rr & 7)) << 4));
+            if (rr < kRows) raw[j] = *reinterpret_cast<const uint4*>(src_base + rr * 128 + ((i ^ (rr & 7)) << 4));
           }
 #pragma unroll
           for (int j = 0; j < kIter; ++j) {

@@ -711,7 +711,8 @@ int plan_dense_layer(dp_model* m, const BlobOp& op, int img0, int B, Launch& L) 
 }
 
 // Groups runs of consecutive fused dense layers that (a) extend the same concat buffer layer by layer, (b) use 8-row
-// regions and (c) have 1, 2, 4 or 8 regions per image (one thread-block cluster) into one persistent kernel launch each.
+// regions, (c) have 1, 2, 4 or 8 regions per image (one thread-block cluster) and (d) start at a channel count that is
+// a multiple of 64 (the kernel's tail tiles) into one persistent kernel launch each.
 int plan_dense_blocks(dp_model* m, SubPlan& sp) {
   using namespace dp;
   const int n = (int)m->ops.size();
@@ -719,7 +720,7 @@ int plan_dense_blocks(dp_model* m, SubPlan& sp) {
   std::vector<Run> runs;
   for (int i = 0; i < n;) {
     const int per_img = (m->ops[i].type == OP_DENSE_LAYER) ? sp.launches[i].dl.tiles_w * sp.launches[i].dl.tiles_h : 0;
-    if (m->ops[i].type != OP_DENSE_LAYER || sp.launches[i].dl.rh != 8 ||
+    if (m->ops[i].type != OP_DENSE_LAYER || sp.launches[i].dl.rh != 8 || (m->ops[i].cin % 64) != 0 ||
         !(per_img == 1 || per_img == 2 || per_img == 4 || per_img == 8)) { ++i; continue; }
     int j = i + 1;
     while (j < n && m->ops[j].type == OP_DENSE_LAYER && m->ops[j].in_buf == m->ops[i].in_buf &&
@@ -761,6 +762,14 @@ int plan_dense_blocks(dp_model* m, SubPlan& sp) {
     p.n_img = L0.dl.n_img; p.H = L0.dl.H; p.W = L0.dl.W;
     p.tiles_w = L0.dl.tiles_w; p.tiles_h = L0.dl.tiles_h; p.n_items = L0.dl.n_items;
     p.n_layers = r.len;
+    {
+      // shared memory: barriers + BN2 staging + T (2 buffers) + 2 tail tiles + rings; the last A stage's M-block
+      // over-read must stay inside the allocation (10 KB of slack, as in the per-layer kernel)
+      const int fixed = DenseBlockSmem::kBarBytes + DenseBlockSmem::kMidBytes + dl_t_bytes(8) / 2 + 2 * dl_a_stage(8) + 1024 + 10 * 1024;
+      while (a_stages > 2 && fixed + a_stages * dl_a_stage(8) + b_stages * kDlBStage > 227 * 1024) --a_stages;
+      while (b_stages > 2 && fixed + a_stages * dl_a_stage(8) + b_stages * kDlBStage > 227 * 1024) --b_stages;
+      if (fixed + a_stages * dl_a_stage(8) + b_stages * kDlBStage > 227 * 1024) return fail("dense block: shared memory budget exceeded");
+    }
     p.a_stages = a_stages; p.b_stages = b_stages;
     p.out_ctot = L0.dl.out_ctot;
     p.out = L0.dl.out;

@@ -20,7 +20,7 @@ m.forward_tile_batch(tiles)
 torch.cuda.synchronize()
 tr = m.read_trace()
 ROLE = {0: "prod", 1: "mma", 2: "epi", 3: "xform"}
-EV = {(0, 1): "A_issued", (0, 2): "flags_seen", (1, 1): "A_ready", (1, 3): "ph1_issued", (1, 4): "ph2_start",
+EV = {(0, 1): "A_issued", (0, 2): "tail_slot", (1, 1): "A_ready", (1, 3): "ph1_issued", (1, 4): "ph2_start",
       (1, 5): "ph2_issued", (2, 0): "mid_start", (2, 2): "mid_done", (2, 3): "final_start", (2, 1): "final_done",
       (2, 4): "published", (3, 1): "xf_start", (3, 0): "xf_done"}
 t0 = min(t for _, _, _, t in tr)
