@@ -30,6 +30,7 @@ namespace {
 
 thread_local std::string g_err;
 std::atomic<uint64_t> g_launches{0};
+thread_local uint64_t g_captured = 0;   // kernel launches recorded into the graph being captured on this thread
 
 int fail(const char* fmt, ...) {
   char buf[1024];
@@ -56,6 +57,7 @@ int fail(const char* fmt, ...) {
       cudaStreamCaptureStatus cs__ = cudaStreamCaptureStatusNone;                                          \
       cudaStreamIsCapturing(st, &cs__);                                                                    \
       if (cs__ == cudaStreamCaptureStatusNone) g_launches.fetch_add(1, std::memory_order_relaxed);         \
+      else ++g_captured;                                                                                   \
     }                                                                                                      \
   } while (0)
 
@@ -152,6 +154,7 @@ struct Plan {
   std::vector<SubPlan> subs;
   cudaGraphExec_t exec = nullptr;
   cudaGraph_t graph = nullptr;
+  uint64_t n_launches = 0;   // kernel nodes of the captured graph
 };
 
 }  // namespace
@@ -168,7 +171,8 @@ struct dp_model {
   uint64_t device_bytes = 0;
   int naive_conv = 0, desc_base_mode = 0, halo_pad8 = 0, profile = 0;
   int use_graph = 1, split = 1, use_pdl = 1, epi_direct = 1, use_overlap = 1, b_resident = 1, b_pair = 0;
-  int dense_block = 1;   // runs of dense layers on 16x16 / 8x8 maps as one persistent kernel (dense_block.cuh)
+  int dense_block = 1;   // runs of dense layers on small maps as one persistent kernel (dense_block.cuh); 2 = wherever
+                         // the kernel applies, 1 = only where per-layer kernels cannot overlap (plan_dense_blocks)
   unsigned long long* gt_dev = nullptr;     // debug: per-op %globaltimer stamps (option "stamp")
   int stamp = 0;
   unsigned long long* gt_all_dev = nullptr; // debug: per-CTA stamps of the dense layers [n_ops][256][4] (option "stamp_ctas")
@@ -720,7 +724,11 @@ int plan_dense_blocks(dp_model* m, SubPlan& sp) {
   std::vector<Run> runs;
   for (int i = 0; i < n;) {
     const int per_img = (m->ops[i].type == OP_DENSE_LAYER) ? sp.launches[i].dl.tiles_w * sp.launches[i].dl.tiles_h : 0;
-    if (m->ops[i].type != OP_DENSE_LAYER || sp.launches[i].dl.rh != 8 || (m->ops[i].cin % 64) != 0 ||
+    // (e) only where two consecutive per-layer kernels cannot be resident together (2 x regions > SMs): there the
+    //     per-layer path loses its cross-layer overlap (measured: 16x16 maps at batch 32, 268 -> 189 us); where they
+    //     can (8x8 maps: 32 regions) the per-layer kernels are as fast or faster (138 vs 150 us) and stay.
+    const bool crowded = (m->ops[i].type == OP_DENSE_LAYER) && (2 * sp.launches[i].dl.n_items > m->num_sms || m->dense_block > 1);
+    if (m->ops[i].type != OP_DENSE_LAYER || sp.launches[i].dl.rh != 8 || (m->ops[i].cin % 64) != 0 || !crowded ||
         !(per_img == 1 || per_img == 2 || per_img == 4 || per_img == 8)) { ++i; continue; }
     int j = i + 1;
     while (j < n && m->ops[j].type == OP_DENSE_LAYER && m->ops[j].in_buf == m->ops[i].in_buf &&
@@ -1528,6 +1536,7 @@ static int run_graph(dp_model* m, int B, const dp::PassDesc& d, void* stream) {
         m->branch_events.push_back(be);
       }
       CU_OK(cudaStreamBeginCapture(m->cap_stream, cudaStreamCaptureModeThreadLocal));
+      g_captured = 0;
       int rc = 0;
       cudaError_t ce = cudaEventRecord(m->fork_event, m->cap_stream);
       for (int s = 0; s < ns && !rc && ce == cudaSuccess; ++s) {
@@ -1547,16 +1556,13 @@ static int run_graph(dp_model* m, int B, const dp::PassDesc& d, void* stream) {
       cudaGraphExec_t ex = nullptr;
       CU_OK(cudaGraphInstantiate(&ex, g, 0));
       plan->graph = g;
+      plan->n_launches = g_captured;
       plan->exec = ex;
     }
   }
   if (upload_pass(m, d, st)) return 1;
   CU_OK(cudaGraphLaunch(plan->exec, st));
-  {
-    uint64_t n = 0;
-    for (const SubPlan& sp : plan->subs) n += sp.launches.size();
-    g_launches.fetch_add(n, std::memory_order_relaxed);
-  }
+  g_launches.fetch_add(plan->n_launches, std::memory_order_relaxed);
   return 0;
 }
 

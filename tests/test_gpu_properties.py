@@ -75,7 +75,7 @@ def test_persistent_dense_block_kernel_is_bit_identical_to_the_per_layer_kernels
         want = m.forward_tile_batch(tiles, 5, 4).clone()
         want_d4 = m.read_buffer(prog.buf("D4"), B)
         want_d5 = m.read_buffer(prog.buf("D5"), B)
-        m.set_option("dense_block", 1)
+        m.set_option("dense_block", 2)           # 2 = every block the kernel applies to (1 = planner's choice)
         for graph in (1, 0, 1):
             m.set_option("use_graph", graph)
             for _ in range(2):
@@ -84,6 +84,8 @@ def test_persistent_dense_block_kernel_is_bit_identical_to_the_per_layer_kernels
             assert np.array_equal(m.read_buffer(prog.buf("D4"), B), want_d4)
             assert np.array_equal(m.read_buffer(prog.buf("D5"), B), want_d5)
         m.set_option("use_graph", 1)
+        m.set_option("dense_block", 1)
+        assert torch.equal(m.forward_tile_batch(tiles, 5, 4), want), B
 
 
 def test_sharded_tile_ranges_equal_unsharded():
