@@ -150,7 +150,12 @@ def get_prediction(wsi_path, mask_path=None, label_path=None, batch_size=64, mod
     return (slide, out)
 
 
-def _crf_refine(engine, torch, slide, mean, label, P, batch, x_lo=0, own=None):
+def crf_block_starts(W, P):
+    """First columns of the non-overlapping P-wide CRF blocks of a slide W columns wide (the last one clamped inside)."""
+    return sorted({min(x, W - P) for x in range(0, W, P)})
+
+
+def _crf_refine(engine, torch, slide, mean, label, P, batch, x_lo=0, block_xs=None):
     """``crf=True``: the reference's intent (Segmentation.py:327-331, commented out there) is
     ``post_process_crf(img, [1 - mean, mean], 2)`` on the whole slide, which pydensecrf cannot hold in memory at WSI
     size.  Here the fully connected CRF of utils.py:568-603 is applied per non-overlapping P x P block of the slide
@@ -158,14 +163,13 @@ def _crf_refine(engine, torch, slide, mean, label, P, batch, x_lo=0, own=None):
     replaces the thresholded label ({0, 255}).  Planes are in the reference's [x, y] orientation; the CRF is symmetric
     in the two image axes, so no transpose is needed.
 
-    ``mean`` / ``label`` may be a stripe of the slide starting at column ``x_lo`` (sharded runs); ``own=(lo, hi)``
-    restricts the work to the blocks whose first column lies in ``[lo, hi)`` -- every block has exactly one owner."""
+    ``mean`` / ``label`` may be a stripe of the slide starting at column ``x_lo`` (sharded runs); ``block_xs`` then
+    lists the first columns of the blocks this call owns (dist.py assigns every block to exactly one rank)."""
     Ws, H = mean.shape
     W = slide.level_dimensions[0][0]
     if W < P or H < P:
         return 0
-    lo, hi = (0, W) if own is None else own
-    xs = sorted({min(x, W - P) for x in range(0, W, P) if lo <= x < hi})
+    xs = crf_block_starts(W, P) if block_xs is None else sorted(block_xs)
     xs = [x for x in xs if x >= x_lo and x + P <= x_lo + Ws]         # the block must lie inside this stripe
     ys = sorted({min(y, H - P) for y in range(0, H, P)})
     if not xs:

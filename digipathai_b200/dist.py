@@ -105,6 +105,19 @@ def owned_ranges(stripes):
     return out
 
 
+def crf_blocks_of(stripes, rank: int, W: int, patch: int):
+    """First columns of the CRF blocks rank ``rank`` refines: a block belongs to the LOWEST rank whose stripe contains
+    it entirely (stripes overlap by patch - stride columns, and after the halo exchange both ranks hold identical
+    values there); blocks no stripe contains lie outside every tile (probability 0) and are nobody's."""
+    from .Segmentation import crf_block_starts
+    mine = []
+    for bx in crf_block_starts(W, patch):
+        owner = next((r for r, (lo, hi) in enumerate(stripes) if hi > lo and lo <= bx and bx + patch <= hi), None)
+        if owner == rank:
+            mine.append(bx)
+    return mine
+
+
 def gather_planes(planes, stripes, rank: int, world_size: int, W: int, group=None):
     """Rank 0 returns full [W, H] planes (zeros where no tile touched), other ranks None."""
     import torch
@@ -177,7 +190,7 @@ def sharded_get_prediction(wsi_path, models, batch_size=32, tta_list=None, patch
     ``info['timings_ms']`` splits this rank's wall time into grid / raster upload / tile loop / halo / normalise
     (each phase ends with a device synchronisation).  ``threshold`` (getSegmentation's 0.3) adds the rank's uint8
     label stripe ``res['label']``; ``crf=True`` then refines it tile-wise (Segmentation._crf_refine) on the P x P blocks
-    this rank owns (first column inside its owned range; every block of the slide has exactly one owner).
+    this rank owns (``crf_blocks_of``: every block of the slide has exactly one owner).
     """
     import time
     import torch
@@ -216,7 +229,8 @@ def sharded_get_prediction(wsi_path, models, batch_size=32, tta_list=None, patch
         t0 = time.perf_counter()
         with torch.cuda.device(planes[0].device):
             n_crf = _crf_refine(engine, torch, slide, planes[0], label, int(patch_size), int(batch_size),
-                                x_lo=stripes[rank][0], own=owned_ranges(stripes)[rank])
+                                x_lo=stripes[rank][0],
+                                block_xs=crf_blocks_of(stripes, rank, slide.level_dimensions[0][0], int(patch_size)))
             torch.cuda.synchronize()
         tm['crf_ms'] = (time.perf_counter() - t0) * 1e3
     info = {'rank': rank, 'world': world, 'batches': (lo, hi), 'stripe': stripes[rank], 'halo_bytes_sent': sent,

@@ -89,3 +89,26 @@ def test_halo_exchange_gloo(stripes):
         assert res[0][3] == 0 and res[1][3] == 0        # disjoint stripes exchange nothing
     else:
         assert res[0][3] > 0
+
+
+def test_every_crf_block_inside_the_tiled_area_has_exactly_one_owner():
+    """dist.crf_blocks_of: with x-stripes that overlap by patch - stride, each 256-wide CRF block that any stripe contains
+    is refined by exactly one rank, and a single stripe owns the same set of blocks the ranks own together."""
+    from digipathai_b200 import dist as dpd
+    rng = np.random.default_rng(0)
+    P, stride, W = 256, 128, 5000
+    xs = np.sort(rng.choice(np.arange(0, W - P + 1, stride), 30, replace=False))
+    coords = np.stack([np.repeat(xs, 4), np.tile(np.arange(4) * stride, len(xs))], 1).astype(np.int32)
+    whole = dpd.crf_blocks_of([dpd.stripe_of(coords, 0, len(coords), P)], 0, W, P)
+    for world in (2, 3, 5):
+        parts, stripes = dpd.stripes_for(coords, 4, world, P)
+        owned = [dpd.crf_blocks_of(stripes, r, W, P) for r in range(world)]
+        flat = [b for o in owned for b in o]
+        assert len(flat) == len(set(flat))                       # no block has two owners
+        for r, o in enumerate(owned):
+            lo, hi = stripes[r]
+            assert all(lo <= b and b + P <= hi for b in o)       # an owner holds the whole block
+        assert set(flat) <= set(whole)
+        for b in set(whole) - set(flat):                         # a block nobody owns straddles a gap between stripes:
+            lo_hi = [(lo, hi) for lo, hi in stripes if hi > lo]  # it is not inside any rank's tiled area
+            assert not any(lo <= b and b + P <= hi for lo, hi in lo_hi)

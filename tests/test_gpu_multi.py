@@ -40,8 +40,18 @@ def _worker(rank, world, port, q):
         grid, res, info = dpd.sharded_get_prediction(slide, {'dense': model}, 8, ['FLIP_LEFT_RIGHT'], 256, 128,
                                                      device=rank, gather=True)
         torch.cuda.synchronize()
+        # second run: threshold + tile-wise CRF on the blocks each rank owns (config-5 shape)
+        _, res2, info2 = dpd.sharded_get_prediction(slide, {'dense': model}, 8, None, 256, 128, device=rank,
+                                                    threshold=0.3, crf=True)
+        from digipathai_b200.dist import crf_blocks_of
+        torch.cuda.synchronize()
+        stripes = dpd.stripes_for(grid.coords, 8, world, 256)[1]
+        mine = crf_blocks_of(stripes, rank, 3072, 256)
+        lab = res2['label'].cpu().numpy()
+        blocks = {bx: lab[bx - info2['stripe'][0]: bx - info2['stripe'][0] + 256] for bx in mine}
         q.put((rank, info, len(grid.coords),
-               res['mean'].cpu().numpy() if rank == 0 else None, res['var'].cpu().numpy() if rank == 0 else None))
+               res['mean'].cpu().numpy() if rank == 0 else None, res['var'].cpu().numpy() if rank == 0 else None,
+               blocks, info2['crf_tiles']))
         dist.barrier()
         model.close()
     finally:
@@ -87,3 +97,18 @@ def test_two_gpu_sharded_slide_equals_single_gpu():
     assert np.array_equal(var[outside], want['var'][outside])
     assert np.abs(mean[a:b] - want['mean'][a:b]).max() <= 4e-7
     assert np.abs(var[a:b] - want['var'][a:b]).max() <= 1e-6
+    # sharded threshold + CRF: every block is refined by exactly one rank, and (up to the <= 4e-7 halo re-association
+    # feeding the CRF) its labels are those of the one-GPU run
+    from digipathai_b200 import dist as dpd
+    model = load_trained_models('dense', init_densenet_weights(0), 256, max_batch=8)
+    _, one, info_one = dpd.sharded_get_prediction(slide, {'dense': model}, 8, None, 256, 128, device=0, threshold=0.3,
+                                                  crf=True, shard=(0, 1))
+    lab_one, lo_one = one['label'].cpu().numpy(), info_one['stripe'][0]
+    model.close()
+    blocks = {**got[0][4], **got[1][4]}
+    assert len(blocks) == len(got[0][4]) + len(got[1][4]) and got[0][5] + got[1][5] == info_one['crf_tiles'] > 0
+    same = total = 0
+    for bx, lab in blocks.items():
+        ref = lab_one[bx - lo_one: bx - lo_one + 256]
+        same += int((lab == ref).sum()); total += lab.size
+    assert same / total > 0.9999, same / total
