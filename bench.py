@@ -207,6 +207,9 @@ def main():
     ap.add_argument("--no-parity", action="store_true", help="skip the parity record of the default line")
     ap.add_argument("--line-slide", type=int, default=40000, help="side of the slide behind the line's `slide` record")
     ap.add_argument("--split", type=int, default=0, help="sub-batches captured as parallel graph branches (0 = library default)")
+    ap.add_argument("--lanes", type=int, default=3,
+                    help="forward steps in flight on the GPU (engine.ForwardLanes: one stream + one model clone per lane; "
+                         "1 = one stream, L2 flushed between steps as in round 1)")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-pdl", action="store_true")
     ap.add_argument("--epi-direct", action="store_true")
@@ -312,7 +315,7 @@ def main():
 
     # ---------------------------------------------------------------- synthetic input, resident in HBM
     g = torch.Generator(device=dev); g.manual_seed(1234 + rank)
-    SW = SH = 4096
+    SW = SH = 16384                          # 805 MB raster: the tiles of a step come from far more than L2 holds
     slide = torch.randint(0, 256, (SW, SH, 3), dtype=torch.uint8, device=dev, generator=g)   # [x, y, c]
     n_coord_sets = args.steps + args.warmup + 8
     cg = torch.Generator(); cg.manual_seed(99 + rank)
@@ -329,22 +332,58 @@ def main():
     for i in range(args.warmup):
         step(i)
     barrier()
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    # ---- one stream, L2 flushed between steps (the round-1 / round-2 definition; kept as `single_stream`)
+    n_single = args.steps if args.lanes <= 1 else min(args.steps, 50)
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n_single)]
     n0 = engine.kernel_launch_count()
     barrier()
-    sampler.mark_begin()
-    for k in range(args.steps):
+    if args.lanes <= 1:
+        sampler.mark_begin()
+    for k in range(n_single):
         flush.zero_()                       # L2 flush between timed iterations (not timed)
         ev[k][0].record()
         step(args.warmup + k)
         ev[k][1].record()
     barrier()
-    sampler.mark_end()
+    if args.lanes <= 1:
+        sampler.mark_end()
     launches = engine.kernel_launch_count() - n0
-    ms_total = sum(a.elapsed_time(b) for a, b in ev)
-    ms_total = max_over_ranks(ms_total)
-    ms_per_step = ms_total / args.steps
-    value = world * BATCH * args.steps / (ms_total * 1e-3)
+    ms_single = max_over_ranks(sum(a.elapsed_time(b) for a, b in ev)) / n_single
+    single_stream = {"value": world * BATCH / (ms_single * 1e-3), "ms_per_step": ms_single, "steps": n_single,
+                     "l2": "flushed between timed steps (256 MiB memset, untimed)"}
+    ms_per_step, value = ms_single, single_stream["value"]
+    if args.lanes > 1:
+        # ---- the headline: the same K steps with `lanes` of them in flight (one stream + one model clone per lane).
+        # Steps are independent tile batches, as in a slide run; the whole region is timed on the device from the
+        # first launch to the completion of the last step.  No flush is possible between overlapping steps: every
+        # step's tiles come from random origins of an 805 MB raster and every lane cycles ~1 GB of activations, both
+        # far beyond the 126 MB L2 (only the 35 MB of weights stay resident, as they do on a slide).
+        pool = engine.ForwardLanes({"m": model}, args.lanes)
+        probs_l = [torch.empty((BATCH, PATCH, PATCH), dtype=torch.float32, device=dev) for _ in range(args.lanes)]
+
+        def lane_step(i):
+            pool.forward("m", slide, coords_all[i % n_coord_sets], 0, 0, out=probs_l[i % args.lanes])
+
+        pool.begin()
+        for i in range(max(args.warmup, 2 * args.lanes)):
+            lane_step(i)
+        pool.join()
+        barrier()
+        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        n0 = engine.kernel_launch_count()
+        sampler.mark_begin()
+        t0.record()
+        pool.begin()
+        for k in range(args.steps):
+            lane_step(args.warmup + k)
+        pool.join()
+        t1.record()
+        barrier()
+        sampler.mark_end()
+        launches = engine.kernel_launch_count() - n0
+        ms_total = max_over_ranks(t0.elapsed_time(t1))
+        ms_per_step = ms_total / args.steps
+        value = world * BATCH * args.steps / (ms_total * 1e-3)
 
     # ---------------------------------------------------------------- end to end through the host API
     host_in = torch.randint(0, 256, (BATCH, PATCH, PATCH, 3), dtype=torch.uint8).pin_memory()
@@ -371,7 +410,7 @@ def main():
     # step's inputs leave pinned host memory, every step's probabilities land in pinned host memory), but H2D of
     # batch k+1 / forward of batch k / D2H of batch k-1 overlap on three streams.  Timed from the first H2D to the
     # completion of the last D2H.
-    pipe = engine.HostBatchPipeline(model, BATCH)
+    pipe = engine.HostBatchPipeline(model, BATCH, lanes=max(1, args.lanes))
     host_out_flat = host_out
     for _ in range(3):
         pipe.submit(host_in, host_out_flat)
@@ -384,6 +423,7 @@ def main():
     p1.record(pipe.s_out)
     pipe.drain()
     barrier()
+    torch.cuda.synchronize()
     e2e_ms = max_over_ranks(p0.elapsed_time(p1))
     e2e_value = world * BATCH * args.steps / (e2e_ms * 1e-3)
 
@@ -409,7 +449,9 @@ def main():
     # The conv family's time is taken from the TIMED step, not from the instrumented pass: inside the CUDA graph the
     # kernels overlap through programmatic dependent launch, so event-bracketed launches sum to more than the step
     # they decompose.  family time = ms_per_step - (helper kernels' time)  <=  ms_per_step.
-    family_ms = max(ms_per_step - aux_ms, 1e-6)
+    # With several steps in flight the helper kernels of one step overlap the conv kernels of another, so nothing is
+    # subtracted: achieved = algorithmic FLOPs / the whole timed step.
+    family_ms = max(ms_per_step - aux_ms, 1e-6) if args.lanes <= 1 else ms_per_step
     achieved_tf = flop_step / (family_ms * 1e-3) / 1e12
     exec_macs = model.executed_macs(BATCH)
     peak_tf = peaks["bf16_tflops_sustained"]
@@ -465,7 +507,11 @@ def main():
             "vs_baseline": None, "dtype": DTYPE[args.precision], "data": "synthetic",
             "config": {"workload": f"configs[1]: {MODEL_DESC[args.model]} forward on synthetic 256x256x3 uint8 tiles, "
                                    "batch 32 per GPU, tiles cropped from an HBM-resident raster",
-                       "l2": "flushed between timed steps (256 MiB memset, untimed)",
+                       "l2": ("flushed between timed steps (256 MiB memset, untimed)" if args.lanes <= 1 else
+                              "inputs larger than L2: tiles cropped at random origins of an 805 MB raster, ~1 GB of "
+                              "activations per lane; steps overlap, so no flush between them (single_stream has the "
+                              "flushed one-stream figure)"),
+                       "lanes": args.lanes,
                        "env_overrides": env_overrides,
                        "weights": "random-init (He-normal), BN stats (0,1)",
                        "graph": "off" if args.no_graph else f"one CUDA graph per step, {args.split or 1} sub-batch branch(es), PDL between conv kernels",
@@ -474,8 +520,9 @@ def main():
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(host_in.numel()),
                     "d2h_bytes_per_step": int(host_out.numel() * 4),
-                    "api": "engine.HostBatchPipeline: pinned host buffers, H2D / forward / D2H on three streams, "
-                           "double-buffered; every step copies its own inputs and results",
+                    "api": f"engine.HostBatchPipeline(lanes={max(1, args.lanes)}): pinned host buffers, H2D / forward / "
+                           "D2H on separate streams, one device buffer pair per step in flight; every step copies its "
+                           "own inputs and results",
                     "serial_value": e2e_serial_value,
                     "serial_api": "copy in, TileModel.forward_tile_batch, copy out on one stream (no overlap)"},
             "gpu_launches": int(launches),
@@ -484,13 +531,15 @@ def main():
                          "kernel": (f"conv_tc_kernel{' + dense_layer_kernel' if args.model == 'dense' else ''}, tcgen05 implicit-GEMM family"
                                     if args.precision == "fp16" else "conv_f32_kernel (fp32 FMA implicit GEMM)") +
                                    f" ({n_conv} launches per step); achieved = algorithmic FLOPs of the reference graph per step "
-                                   "/ (timed ms_per_step - helper-kernel ms)",
+                                   + ("/ (timed ms_per_step - helper-kernel ms)" if args.lanes <= 1 else
+                                      f"/ timed ms_per_step ({args.lanes} steps in flight; helper kernels not subtracted)"),
                          "peak_source": f"{peak_src} bf16_tflops_sustained",
                          "family_ms_per_step": family_ms, "aux_ms_per_step": aux_ms,
                          "frac_whole_step": flop_step / (ms_per_step * 1e-3) / 1e12 / peak_tf,
                          "instrumented_conv_ms": conv_ms, "instrumented_all_ops_ms": all_ms,
                          "traffic_note": traffic_note, "top_ops": top_desc},
             "cpu_baseline": cpu_baseline,
+            "single_stream": single_stream,
         }
         if parity is not None:
             line["parity"] = parity

@@ -47,7 +47,7 @@ def _torch():
 def get_prediction(wsi_path, mask_path=None, label_path=None, batch_size=64, models=None, tta_list=None,
                    num_workers=8, verbose=0, patch_size=256, stride_size=256, mask_level=-1, status=None,
                    *, device=0, tile_range=None, return_device=False, finalize=True, tissue_mask=None, grid=None,
-                   timings=None):
+                   timings=None, lanes=None):
     """Patch based segmentor (reference: Segmentation.py:65-189).
 
     ``models`` maps a name to a ``TileModel`` (engine.py) -- the object that replaces the Keras model.
@@ -58,7 +58,10 @@ def get_prediction(wsi_path, mask_path=None, label_path=None, batch_size=64, mod
     halo exchange), ``tissue_mask`` supplies a precomputed RAW [x, y] mask instead of the Otsu/HSV heuristic (the
     morphology of utils.py:200-219 is still applied to it), ``grid`` a ready ``TileGrid`` of this slide (sharded
     runs build it once and index it with ``tile_range``), ``timings`` a dict that receives this call's phase times in
-    milliseconds (grid, raster upload, tile loop; each phase ends with a device synchronisation).
+    milliseconds (grid, raster upload, tile loop; each phase ends with a device synchronisation), ``lanes`` the number
+    of forwards kept in flight on the GPU (engine.ForwardLanes: the passes / models of a batch and consecutive batches
+    run on ``lanes`` streams, each with its own clone of every model; default ``DIGIPATH_LANES`` or 3; the planes do
+    not depend on it, bit for bit).
     ``mask_path`` names a ``.tiff`` tissue mask read at the slide's top level instead of running the heuristic
     (dataloader.py:256-263; any other extension leaves the reference's dataset without a mask -- AttributeError --
     and does so here); ``label_path`` / ``num_workers`` / ``mask_level`` are accepted for signature compatibility:
@@ -121,20 +124,37 @@ def get_prediction(wsi_path, mask_path=None, label_path=None, batch_size=64, mod
         var = torch.zeros_like(mean)
         count = torch.zeros((x_hi - x_lo, H), dtype=torch.uint8, device=dev)
         n_pass = len(passes) * len(names)
-        probs = torch.empty((n_pass, batch_size, P, P), dtype=torch.float32, device=dev)
+        if lanes is None:
+            lanes = int(os.environ.get("DIGIPATH_LANES", "3"))
+        if b_hi <= b_lo or not all(hasattr(m, "clone") for m in models.values()):
+            lanes = 1
+        pool = engine.ForwardLanes(models, lanes)
+        # one probability buffer per batch in flight (+1 being stitched): [slot][pass x model][tile][P][P]
+        n_slots = 1 if pool.L == 1 else max(2, -(-pool.L // n_pass) + 1)
+        probs = [torch.empty((n_pass, batch_size, P, P), dtype=torch.float32, device=dev) for _ in range(n_slots)]
+        stitched = [None] * n_slots
         coords_dev = torch.from_numpy(coords_all - np.array([x_lo, 0], np.int32)).to(dev) if len(coords_all) else None
         coords_abs = torch.from_numpy(coords_all).to(dev) if len(coords_all) else None
+        pool.begin()                                 # the lanes start after the raster upload and the plane memsets
         for ii in range(b_lo, b_hi):
             if status is not None:
                 # same arithmetic as Segmentation.py:139 (an ensemble therefore tops out below 100 %)
                 status['progress'] = int(ii * 100.0 / (len(names) * n_batches))
             c_local = coords_dev[ii * batch_size:(ii + 1) * batch_size]
+            slot = (ii - b_lo) % n_slots
+            if stitched[slot] is not None:
+                pool.wait_event(stitched[slot])      # the stitch that last read probs[slot] has finished
             k = 0
             for (t_in, t_out) in passes:            # Segmentation.py:150-160: tta outer, model inner
                 for nm in names:
-                    models[nm].forward_tiles(raster, c_local, t_in, t_out, out=probs[k])
+                    pool.forward(nm, raster, c_local, t_in, t_out, out=probs[slot][k])
                     k += 1
-            engine.stitch(probs, coords_abs[ii * batch_size:(ii + 1) * batch_size], mean, var, count, x_lo=x_lo)
+            pool.join()
+            engine.stitch(probs[slot], coords_abs[ii * batch_size:(ii + 1) * batch_size], mean, var, count, x_lo=x_lo)
+            if pool.L > 1:
+                stitched[slot] = torch.cuda.Event()
+                stitched[slot].record()
+        pool.close()
         if timings is not None:
             torch.cuda.synchronize(dev)
             timings['loop_ms'] = (time.perf_counter() - _t0) * 1e3
@@ -198,8 +218,8 @@ def _default_weight_path(mode, model):
 def load_trained_models(model, path, patch_size=256, *, device=0, max_batch=32, precision="fp16"):
     """Counterpart of utils.py:427-448: build the graph and load its weights; returns a ``TileModel``.
 
-    ``path`` is a flat ``.npz`` of Keras-named arrays (the reference's ``.h5`` files converted off-box with
-    tools/h5_to_npz.py -- h5py/TensorFlow are not available here) or an in-memory weight dict.
+    ``path`` is one of the reference's Keras ``.h5`` checkpoints (read in pure Python: h5lite.py + keras_h5.py), a
+    flat ``.npz`` of Keras-named arrays (tools/h5_to_npz.py output) or an in-memory weight dict.
     ``precision``: 'fp16' (tensor cores, fp32 accumulation) or 'fp32' (the reference's arithmetic: matches its fp32
     ``Model.predict`` within 1e-3 on any weight set; several times slower) -- see program.py.
     """
@@ -207,19 +227,34 @@ def load_trained_models(model, path, patch_size=256, *, device=0, max_batch=32, 
     from .models.densenet import densenet121_unet_program
     from .models.inception import inception_resnet_v2_unet_program
     if model.__contains__('dense'):
-        weights = path if isinstance(path, dict) else _load_npz(path)
+        weights = path if isinstance(path, dict) else _load_weights('dense', path)
         return TileModel(densenet121_unet_program(weights, patch_size, precision=precision), device=device,
                          max_batch=max_batch)
     if model.__contains__('inception'):
-        weights = path if isinstance(path, dict) else _load_npz(path)
+        weights = path if isinstance(path, dict) else _load_weights('inception', path)
         return TileModel(inception_resnet_v2_unet_program(weights, patch_size, precision=precision), device=device,
                          max_batch=max_batch)
     if model.__contains__('deeplabv3'):
         from .models.deeplab import deeplabv3plus_xception_program
-        weights = path if isinstance(path, dict) else _load_npz(path)
+        weights = path if isinstance(path, dict) else _load_weights('deeplabv3', path)
         return TileModel(deeplabv3plus_xception_program(weights, patch_size, precision=precision), device=device,
                          max_batch=max_batch)
     raise ValueError("Unknown model provided, allowed models ['dense', 'inception', 'deeplabv3']")
+
+
+def _load_weights(model, path):
+    """``.h5`` / ``.hdf5`` -> Keras checkpoint (what utils.py:447 hands to ``load_weights``); anything else -> ``.npz``.
+    When the ``.npz`` the default paths name is missing but the reference's ``.h5`` sits beside it, that is read."""
+    path = str(path)
+    h5 = path if path.endswith(('.h5', '.hdf5')) else None
+    if h5 is None and not os.path.exists(path) and os.path.exists(os.path.splitext(path)[0] + '.h5'):
+        h5 = os.path.splitext(path)[0] + '.h5'
+    if h5 is not None:
+        if not os.path.exists(h5):
+            raise FileNotFoundError(f"{h5} not found (the reference downloads it, DigiPathAI/helpers/utils.py:58-98)")
+        from .keras_h5 import load_keras_h5
+        return load_keras_h5(model, h5)
+    return _load_npz(path)
 
 
 def _load_npz(path):

@@ -26,6 +26,7 @@ _SIGS = {
     "dp_abi_version": (C.c_int, []),
     "dp_last_error": (C.c_char_p, []),
     "dp_model_create": (C.c_int, [C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.POINTER(c_model_p)]),
+    "dp_model_clone": (C.c_int, [c_model_p, C.POINTER(c_model_p)]),
     "dp_model_destroy": (C.c_int, [c_model_p]),
     "dp_model_info": (C.c_int, [c_model_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_uint64)]),
     "dp_model_precision": (C.c_int, [c_model_p]),

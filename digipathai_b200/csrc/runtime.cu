@@ -164,7 +164,8 @@ struct dp_model {
   int precision = 0, esize = 2;  // 0 = fp16 tensor-core path; 1 = fp32 storage + fp32 kernels (precise.cuh), esize 4
   std::vector<BlobBuf> bufs;
   std::vector<BlobOp> ops;
-  uint8_t* data_dev = nullptr;
+  uint8_t* data_dev = nullptr;             // container data section (weights, BN vectors) on the device
+  std::shared_ptr<void> data_owner;        // ... shared between a model and its lanes (dp_model_clone)
   size_t data_bytes = 0;
   std::vector<__half*> buf_dev;    // activation buffers (raw storage: __half or float elements, see esize)
   __half* scratch_head = nullptr;  // naive / fp32 paths: output of the head-fused conv
@@ -1243,6 +1244,67 @@ int check_model(const dp_model* m) {
 
 }  // namespace
 
+// Everything a model owns besides the container's data section: activation buffers, the head scratch, the per-call
+// argument record, kernel attributes and the environment overrides.  Shared by dp_model_create and dp_model_clone.
+static int alloc_lane_state(dp_model* m) {
+  cudaError_t e;
+  const uint32_t n_bufs = (uint32_t)m->bufs.size();
+  const int max_batch = m->max_batch;
+  const char* env = nullptr;
+  m->buf_dev.assign(n_bufs, nullptr);
+  for (uint32_t i = 0; i < n_bufs; ++i) {
+    const BlobBuf& b = m->bufs[i];
+    if (b.C % 8) { return fail("buffer %u: channel count %d not a multiple of 8", i, b.C); }
+    const size_t sz = (size_t)max_batch * b.H * b.W * b.C * m->esize;
+    e = cudaMalloc(&m->buf_dev[i], sz);
+    if (e != cudaSuccess) { return fail("cudaMalloc buffer %u (%zu B): %s", i, sz, cudaGetErrorString(e)); }
+    cudaMemset(m->buf_dev[i], 0, sz);
+    m->device_bytes += sz;
+  }
+  {
+    size_t sz = 0;
+    for (const BlobOp& op : m->ops)
+      if (op.type == OP_CONV && op.head) sz = (size_t)max_batch * m->patch * m->patch * op.cout * m->esize;
+    if (sz) {
+      e = cudaMalloc(&m->scratch_head, sz);
+      if (e != cudaSuccess) { return fail("cudaMalloc head scratch: %s", cudaGetErrorString(e)); }
+      m->device_bytes += sz;
+    }
+  }
+  e = cudaMalloc(&m->pass_dev, sizeof(dp::PassDesc));
+  if (e != cudaSuccess) { return fail("cudaMalloc pass descriptor: %s", cudaGetErrorString(e)); }
+  cudaMemset(m->pass_dev, 0, sizeof(dp::PassDesc));
+  env = getenv("DP_SPLIT");
+  if (env && atoi(env) > 0) m->split = atoi(env);
+  {
+    const int kMaxSmem = 227 * 1024;
+    cudaError_t e1 = cudaFuncSetAttribute(dp::conv_tc_kernel<dp::MODE_D, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
+    cudaError_t e2 = cudaFuncSetAttribute(dp::conv_tc_kernel<dp::MODE_D, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
+    cudaError_t e3 = cudaFuncSetAttribute(dp::conv_tc_kernel<dp::MODE_T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
+    cudaError_t e4 = cudaSuccess;
+    for (const FastKernel& k : kFastKernels) {
+      cudaError_t ek = cudaFuncSetAttribute(k.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
+      if (ek != cudaSuccess) e4 = ek;
+    }
+    cudaError_t e7 = cudaFuncSetAttribute(dp::conv_tc_kernel<dp::MODE_D, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
+    cudaError_t e5 = cudaFuncSetAttribute(dp::dense_layer_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
+    if (e5 == cudaSuccess) e5 = cudaFuncSetAttribute(dp::dense_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
+    cudaError_t e6 = cudaFuncSetAttribute(dp::dense_layer_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
+    if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess || e4 != cudaSuccess || e5 != cudaSuccess || e6 != cudaSuccess || e7 != cudaSuccess) {
+      return fail("cudaFuncSetAttribute(MaxDynamicSharedMemorySize) failed: %s", cudaGetErrorString(cudaGetLastError()));
+    }
+  }
+  env = getenv("DP_B_PAIR");
+  if (env) m->b_pair = atoi(env);
+  env = getenv("DP_DENSE_BLOCK");
+  if (env) m->dense_block = atoi(env);
+  env = getenv("DP_NAIVE_CONV");
+  if (env && atoi(env)) m->naive_conv = 1;
+  env = getenv("DP_DESC_BASE_MODE");
+  if (env) m->desc_base_mode = atoi(env);
+  return 0;
+}
+
 extern "C" {
 
 int dp_abi_version(void) { return 1; }
@@ -1295,62 +1357,28 @@ int dp_model_create(const void* blob, size_t nbytes, int device, int max_batch, 
   auto cleanup = [&]() { dp_model_destroy(m); };
   cudaError_t e = cudaMalloc(&m->data_dev, m->data_bytes ? m->data_bytes : 256);
   if (e != cudaSuccess) { cleanup(); return fail("cudaMalloc weights: %s", cudaGetErrorString(e)); }
+  m->data_owner = std::shared_ptr<void>(m->data_dev, [](void* p) { cudaFree(p); });
   m->device_bytes += m->data_bytes;
   e = cudaMemcpy(m->data_dev, bytes + h.data_off, m->data_bytes, cudaMemcpyHostToDevice);
   if (e != cudaSuccess) { cleanup(); return fail("cudaMemcpy weights: %s", cudaGetErrorString(e)); }
-  const char* env = nullptr;
-  m->buf_dev.assign(h.n_bufs, nullptr);
-  for (uint32_t i = 0; i < h.n_bufs; ++i) {
-    const BlobBuf& b = m->bufs[i];
-    if (b.C % 8) { cleanup(); return fail("buffer %u: channel count %d not a multiple of 8", i, b.C); }
-    const size_t sz = (size_t)max_batch * b.H * b.W * b.C * m->esize;
-    e = cudaMalloc(&m->buf_dev[i], sz);
-    if (e != cudaSuccess) { cleanup(); return fail("cudaMalloc buffer %u (%zu B): %s", i, sz, cudaGetErrorString(e)); }
-    cudaMemset(m->buf_dev[i], 0, sz);
-    m->device_bytes += sz;
-  }
-  {
-    size_t sz = 0;
-    for (const BlobOp& op : m->ops)
-      if (op.type == OP_CONV && op.head) sz = (size_t)max_batch * m->patch * m->patch * op.cout * m->esize;
-    if (sz) {
-      e = cudaMalloc(&m->scratch_head, sz);
-      if (e != cudaSuccess) { cleanup(); return fail("cudaMalloc head scratch: %s", cudaGetErrorString(e)); }
-      m->device_bytes += sz;
-    }
-  }
-  e = cudaMalloc(&m->pass_dev, sizeof(dp::PassDesc));
-  if (e != cudaSuccess) { cleanup(); return fail("cudaMalloc pass descriptor: %s", cudaGetErrorString(e)); }
-  cudaMemset(m->pass_dev, 0, sizeof(dp::PassDesc));
-  env = getenv("DP_SPLIT");
-  if (env && atoi(env) > 0) m->split = atoi(env);
-  {
-    const int kMaxSmem = 227 * 1024;
-    cudaError_t e1 = cudaFuncSetAttribute(dp::conv_tc_kernel<dp::MODE_D, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
-    cudaError_t e2 = cudaFuncSetAttribute(dp::conv_tc_kernel<dp::MODE_D, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
-    cudaError_t e3 = cudaFuncSetAttribute(dp::conv_tc_kernel<dp::MODE_T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
-    cudaError_t e4 = cudaSuccess;
-    for (const FastKernel& k : kFastKernels) {
-      cudaError_t ek = cudaFuncSetAttribute(k.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
-      if (ek != cudaSuccess) e4 = ek;
-    }
-    cudaError_t e7 = cudaFuncSetAttribute(dp::conv_tc_kernel<dp::MODE_D, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
-    cudaError_t e5 = cudaFuncSetAttribute(dp::dense_layer_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
-    if (e5 == cudaSuccess) e5 = cudaFuncSetAttribute(dp::dense_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
-    cudaError_t e6 = cudaFuncSetAttribute(dp::dense_layer_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
-    if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess || e4 != cudaSuccess || e5 != cudaSuccess || e6 != cudaSuccess || e7 != cudaSuccess) {
-      cleanup();
-      return fail("cudaFuncSetAttribute(MaxDynamicSharedMemorySize) failed: %s", cudaGetErrorString(cudaGetLastError()));
-    }
-  }
-  env = getenv("DP_B_PAIR");
-  if (env) m->b_pair = atoi(env);
-  env = getenv("DP_DENSE_BLOCK");
-  if (env) m->dense_block = atoi(env);
-  env = getenv("DP_NAIVE_CONV");
-  if (env && atoi(env)) m->naive_conv = 1;
-  env = getenv("DP_DESC_BASE_MODE");
-  if (env) m->desc_base_mode = atoi(env);
+  if (alloc_lane_state(m)) { cleanup(); return 1; }
+  *out = m;
+  return 0;
+}
+
+int dp_model_clone(const dp_model* src, dp_model** out) {
+  if (check_model(src) || !out) return fail("null argument");
+  CU_OK(cudaSetDevice(src->device));
+  dp_model* m = new dp_model;
+  m->device = src->device; m->max_batch = src->max_batch; m->patch = src->patch; m->num_sms = src->num_sms;
+  m->precision = src->precision; m->esize = src->esize;
+  m->bufs = src->bufs; m->ops = src->ops;
+  m->data_dev = src->data_dev; m->data_owner = src->data_owner; m->data_bytes = src->data_bytes;
+  if (alloc_lane_state(m)) { dp_model_destroy(m); return 1; }
+  m->use_graph = src->use_graph; m->split = src->split; m->use_pdl = src->use_pdl; m->epi_direct = src->epi_direct;
+  m->use_overlap = src->use_overlap; m->b_resident = src->b_resident; m->b_pair = src->b_pair;
+  m->dense_block = src->dense_block; m->naive_conv = src->naive_conv; m->desc_base_mode = src->desc_base_mode;
+  m->halo_pad8 = src->halo_pad8;
   *out = m;
   return 0;
 }
@@ -1375,7 +1403,7 @@ int dp_model_destroy(dp_model* m) {
   for (__half* p : m->buf_dev)
     if (p) cudaFree(p);
   if (m->scratch_head) cudaFree(m->scratch_head);
-  if (m->data_dev) cudaFree(m->data_dev);
+  m->data_owner.reset();   // frees the data section with its last user
   delete m;
   return 0;
 }

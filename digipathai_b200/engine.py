@@ -23,17 +23,21 @@ def _stream_ptr():
 
 
 class TileModel:
-    def __init__(self, program: Program | bytes, device: int = 0, max_batch: int = 32):
+    def __init__(self, program: Program | bytes | None, device: int = 0, max_batch: int = 32, *, _clone_of=None):
         if not torch.cuda.is_available():
             raise RuntimeError("digipathai_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
-        blob = program if isinstance(program, (bytes, bytearray)) else serialize(program)
-        self.program = program if isinstance(program, Program) else None
-        self.device = int(device)
-        self.max_batch = int(max_batch)
         self._h = _lib.c_model_p()
-        buf = (C.c_char * len(blob)).from_buffer_copy(blob)
-        _lib.check(_lib.lib.dp_model_create(buf, len(blob), self.device, self.max_batch, C.byref(self._h)),
-                   "dp_model_create")
+        if _clone_of is not None:
+            self.program, self.device, self.max_batch = _clone_of.program, _clone_of.device, _clone_of.max_batch
+            _lib.check(_lib.lib.dp_model_clone(_clone_of._h, C.byref(self._h)), "dp_model_clone")
+        else:
+            blob = program if isinstance(program, (bytes, bytearray)) else serialize(program)
+            self.program = program if isinstance(program, Program) else None
+            self.device = int(device)
+            self.max_batch = int(max_batch)
+            buf = (C.c_char * len(blob)).from_buffer_copy(blob)
+            _lib.check(_lib.lib.dp_model_create(buf, len(blob), self.device, self.max_batch, C.byref(self._h)),
+                       "dp_model_create")
         p, mb, nb = C.c_int(), C.c_int(), C.c_uint64()
         _lib.check(_lib.lib.dp_model_info(self._h, C.byref(p), C.byref(mb), C.byref(nb)))
         self.patch, self.device_bytes = p.value, nb.value
@@ -42,7 +46,24 @@ class TileModel:
         self._tile_coords = {}
 
     # ------------------------------------------------------------------ lifetime
+    def clone(self) -> "TileModel":
+        """Another execution lane of this model (dp_model_clone): shares the weights in HBM, owns its activation
+        buffers and captured graphs, so it can run a different tile batch on another stream at the same time."""
+        return TileModel(None, _clone_of=self)
+
+    def lane(self, i: int) -> "TileModel":
+        """Lane ``i`` of this model: the model itself for 0, otherwise a clone created on first use and kept until
+        ``close`` (so repeated slide runs do not re-allocate ~1 GB of activations per lane)."""
+        if i == 0:
+            return self
+        lanes = self.__dict__.setdefault("_lanes", [])
+        while len(lanes) < i:
+            lanes.append(self.clone())
+        return lanes[i - 1]
+
     def close(self):
+        for m in self.__dict__.pop("_lanes", []):
+            m.close()
         if getattr(self, "_h", None) is not None and self._h.value:
             _lib.lib.dp_model_destroy(self._h)
             self._h = _lib.c_model_p()
@@ -183,6 +204,66 @@ class TileModel:
         return v.value
 
 
+class ForwardLanes:
+    """``lanes`` tile batches in flight on one GPU.
+
+    The batches of a slide (and the TTA passes / ensemble members of one batch, Segmentation.py:150-160) are
+    independent, while a batch-32 forward has long stretches that cannot fill 148 SMs (the 16x16 / 8x8 dense blocks run
+    128 / 32 CTAs, every kernel has a tail).  Lane ``s`` is a CUDA stream plus one clone of every model
+    (``TileModel.clone``: shared weights, own activations); consecutive ``forward`` calls go to consecutive lanes, so
+    the hardware overlaps one batch's thin kernels with another batch's wide ones.  Results are bit-identical to the
+    single-stream order (same kernels on the same data).  ``lanes=1`` issues on the caller's stream, unchanged.
+
+        lanes = ForwardLanes({'dense': model}, lanes=3)
+        lanes.begin()                                  # lanes wait for what the caller's stream has queued
+        lanes.forward('dense', raster, coords, t_in, t_out, out=probs[k])
+        lanes.join()                                   # caller's stream waits for every lane
+    """
+
+    def __init__(self, models: dict, lanes: int = 3):
+        self.L = max(1, int(lanes))
+        self.models = {nm: [m.lane(i) for i in range(self.L)] if self.L > 1 else [m] for nm, m in models.items()}
+        self.streams = []
+        if self.L > 1:
+            with torch.cuda.device(torch.device("cuda", next(iter(models.values())).device)):
+                self.streams = [torch.cuda.Stream() for _ in range(self.L)]
+        self.j = 0
+
+    def begin(self):
+        self.wait_event(None)
+
+    def wait_event(self, ev=None):
+        """Every lane waits for ``ev`` (default: for the work queued on the caller's stream so far)."""
+        if self.L == 1:
+            return
+        if ev is None:
+            ev = torch.cuda.Event()
+            ev.record()
+        for st in self.streams:
+            st.wait_event(ev)
+
+    def forward(self, name, slide, coords, tta_in=0, tta_out=0, out=None):
+        if self.L == 1:
+            return self.models[name][0].forward_tiles(slide, coords, tta_in, tta_out, out=out)
+        s = self.j % self.L
+        self.j += 1
+        with torch.cuda.stream(self.streams[s]):
+            return self.models[name][s].forward_tiles(slide, coords, tta_in, tta_out, out=out)
+
+    def join(self):
+        if self.L == 1:
+            return
+        cur = torch.cuda.current_stream()
+        for st in self.streams:
+            ev = torch.cuda.Event()
+            ev.record(st)
+            cur.wait_event(ev)
+
+    def close(self):
+        """Lanes are owned by their models (TileModel.lane) and live until those are closed; this only waits."""
+        self.join()
+
+
 class HostBatchPipeline:
     """Host-buffer front end for a stream of tile batches (what stands where a loop of ``model.predict`` calls
     stood, Segmentation.py:150-156): the H2D copy of batch k+1, the forward of batch k and the D2H copy of batch
@@ -195,19 +276,26 @@ class HostBatchPipeline:
         pipe.drain()                             # results are in the host buffers after this returns
     """
 
-    def __init__(self, model: "TileModel", batch: int | None = None, tta_in: int = 0, tta_out: int = 0):
+    def __init__(self, model: "TileModel", batch: int | None = None, tta_in: int = 0, tta_out: int = 0,
+                 lanes: int = 1):
         self.model, self.B, self.P = model, int(batch or model.max_batch), model.patch
         assert self.B <= model.max_batch
         self.tta = (int(tta_in), int(tta_out))
         dev = torch.device("cuda", model.device)
         self.dev = dev
+        self.L = max(1, int(lanes))                      # forwards in flight (ForwardLanes: one model clone each)
+        self.n_slots = 2 * self.L                        # device buffers: one being filled + one in flight per lane
+        self.lane_models = [model.lane(i) for i in range(self.L)]
         with torch.cuda.device(dev):
-            self.s_in, self.s_comp, self.s_out = (torch.cuda.Stream(), torch.cuda.Stream(), torch.cuda.Stream())
-            self.d_in = [torch.empty((self.B, self.P, self.P, 3), dtype=torch.uint8, device=dev) for _ in range(2)]
-            self.d_out = [torch.empty((self.B, self.P, self.P), dtype=torch.float32, device=dev) for _ in range(2)]
-            self.in_ready = [torch.cuda.Event() for _ in range(2)]
-            self.comp_done = [torch.cuda.Event() for _ in range(2)]
-            self.out_done = [torch.cuda.Event() for _ in range(2)]
+            self.s_in, self.s_out = torch.cuda.Stream(), torch.cuda.Stream()
+            self.s_lanes = [torch.cuda.Stream() for _ in range(self.L)]
+            self.s_comp = self.s_lanes[0]
+            n = self.n_slots
+            self.d_in = [torch.empty((self.B, self.P, self.P, 3), dtype=torch.uint8, device=dev) for _ in range(n)]
+            self.d_out = [torch.empty((self.B, self.P, self.P), dtype=torch.float32, device=dev) for _ in range(n)]
+            self.in_ready = [torch.cuda.Event() for _ in range(n)]
+            self.comp_done = [torch.cuda.Event() for _ in range(n)]
+            self.out_done = [torch.cuda.Event() for _ in range(n)]
         self.k = 0
 
     def submit(self, tiles_u8: torch.Tensor, probs_out: torch.Tensor) -> None:
@@ -215,19 +303,22 @@ class HostBatchPipeline:
         assert not tiles_u8.is_cuda and tiles_u8.is_pinned() and tiles_u8.dtype == torch.uint8
         assert not probs_out.is_cuda and probs_out.is_pinned() and probs_out.dtype == torch.float32
         assert tuple(tiles_u8.shape) == (self.B, self.P, self.P, 3) and probs_out.numel() == self.B * self.P * self.P
-        slot, reuse = self.k & 1, self.k >= 2
+        slot, reuse = self.k % self.n_slots, self.k >= self.n_slots
+        lane = self.k % self.L
+        s_comp = self.s_lanes[lane]
         with torch.cuda.device(self.dev):
             with torch.cuda.stream(self.s_in):
                 if reuse:
-                    self.s_in.wait_event(self.comp_done[slot])     # the forward of batch k-2 has consumed d_in[slot]
+                    self.s_in.wait_event(self.comp_done[slot])     # the forward that last used d_in[slot] has consumed it
                 self.d_in[slot].copy_(tiles_u8, non_blocking=True)
                 self.in_ready[slot].record(self.s_in)
-            with torch.cuda.stream(self.s_comp):
-                self.s_comp.wait_event(self.in_ready[slot])
+            with torch.cuda.stream(s_comp):
+                s_comp.wait_event(self.in_ready[slot])
                 if reuse:
-                    self.s_comp.wait_event(self.out_done[slot])    # the D2H of batch k-2 has drained d_out[slot]
-                self.model.forward_tile_batch(self.d_in[slot], self.tta[0], self.tta[1], out=self.d_out[slot])
-                self.comp_done[slot].record(self.s_comp)
+                    s_comp.wait_event(self.out_done[slot])         # the D2H that last used d_out[slot] has drained it
+                self.lane_models[lane].forward_tile_batch(self.d_in[slot], self.tta[0], self.tta[1],
+                                                          out=self.d_out[slot])
+                self.comp_done[slot].record(s_comp)
             with torch.cuda.stream(self.s_out):
                 self.s_out.wait_event(self.comp_done[slot])
                 probs_out.view(self.B, self.P, self.P).copy_(self.d_out[slot], non_blocking=True)
@@ -235,8 +326,11 @@ class HostBatchPipeline:
         self.k += 1
 
     def drain(self) -> None:
-        for st in (self.s_in, self.s_comp, self.s_out):
+        for st in [self.s_in, *self.s_lanes, self.s_out]:
             st.synchronize()
+
+    def close(self) -> None:
+        self.drain()
 
 
 # ---------------------------------------------------------------------- slide-plane kernels

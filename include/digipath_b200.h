@@ -47,6 +47,17 @@ const char* dp_last_error(void);
  */
 int dp_model_create(const void* blob, size_t nbytes, int device, int max_batch, dp_model** out);
 
+/*
+ * A second execution lane of `src`: a model that SHARES the container's data section (weights, BatchNorm vectors) with
+ * `src` on the device and owns its own activation buffers, per-call argument record and captured graphs.  Lanes of one
+ * model may run dp_forward_tiles concurrently on different streams: consecutive tile batches (or the TTA passes of one
+ * batch, the `for transform_index in range(...)` loop of Segmentation.py:150-160) are independent, and the kernels of
+ * one batch fill the SMs another batch's small-map layers leave idle.  The reference has no counterpart (it runs one
+ * `Model.predict` at a time, Segmentation.py:154).  Destroy every lane with dp_model_destroy; the data section is
+ * freed with its last user.  Options set on `src` so far are copied.
+ */
+int dp_model_clone(const dp_model* src, dp_model** out);
+
 /* Frees everything owned by the model (synchronises the device first). */
 int dp_model_destroy(dp_model* m);
 

@@ -201,3 +201,40 @@ def test_stitch_on_a_large_plane_matches_numpy_windows():
     before = mean.clone()
     engine.finalize(mean, var, ones, 0.3, None)
     assert torch.equal(before, mean)
+
+
+def test_lanes_do_not_change_a_bit(model32):
+    """Several forwards in flight (engine.ForwardLanes: model clones sharing the weights, one stream each) give the
+    planes of the one-stream loop bit for bit -- with TTA passes, with one pass per batch (more lanes than passes) and
+    for the two-model ensemble; a clone's forward equals its parent's; the host pipeline with lanes equals predict."""
+    m, torch = model32
+    from digipathai_b200 import engine
+    from digipathai_b200.Segmentation import get_prediction
+    from digipathai_b200.slide import synthetic_slide
+    g = torch.Generator(device="cuda"); g.manual_seed(21)
+    tiles = torch.randint(0, 256, (32, 256, 256, 3), dtype=torch.uint8, device="cuda", generator=g)
+    want = m.forward_tile_batch(tiles).clone()
+    c = m.clone()
+    assert c.device_bytes < m.device_bytes                                  # the clone holds no second copy of the weights
+    assert torch.equal(c.forward_tile_batch(tiles), want)
+    c.close()
+    assert torch.equal(m.forward_tile_batch(tiles), want)                   # the parent survives its clone
+
+    slide = synthetic_slide(2048, 1536, seed=4, n_levels=2)
+    for tta_list in (['FLIP_LEFT_RIGHT', 'ROTATE_90'], None):
+        kw = dict(batch_size=8, patch_size=256, stride_size=128, models={'dense': m}, tta_list=tta_list)
+        _, one = get_prediction(slide, lanes=1, **kw)
+        for lanes in (2, 3, 4):
+            _, many = get_prediction(slide, lanes=lanes, **kw)
+            assert np.array_equal(one['mean'], many['mean']) and np.array_equal(one['var'], many['var']), (tta_list, lanes)
+
+    # host pipeline: 7 different batches through 3 lanes
+    pipe = engine.HostBatchPipeline(m, 32, lanes=3)
+    ins = [torch.randint(0, 256, (32, 256, 256, 3), dtype=torch.uint8).pin_memory() for _ in range(7)]
+    outs = [torch.empty((32, 256, 256), dtype=torch.float32).pin_memory() for _ in range(7)]
+    for a, b in zip(ins, outs):
+        pipe.submit(a, b)
+    pipe.drain()
+    for a, b in zip(ins, outs):
+        assert torch.equal(m.forward_tile_batch(a.cuda()).cpu(), b)
+    pipe.close()
