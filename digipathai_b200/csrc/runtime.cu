@@ -24,6 +24,7 @@
 #include "dense_layer.cuh"
 #include "dense_block.cuh"
 #include "precise.cuh"
+#include "precise_tc.cuh"
 #include "tissue.cuh"
 
 namespace {
@@ -161,7 +162,8 @@ struct Plan {
 
 struct dp_model {
   int device = 0, max_batch = 0, patch = 0, num_sms = 148;
-  int precision = 0, esize = 2;  // 0 = fp16 tensor-core path; 1 = fp32 storage + fp32 kernels (precise.cuh), esize 4
+  int precision = 0, esize = 2;  // 0 = fp16 tensor-core path; 1 = fp32 storage + fp32 FMA kernels (precise.cuh), esize 4;
+                                 // 2 = fp32 storage, convs as 3xTF32 on the tensor cores (precise_tc.cuh)
   std::vector<BlobBuf> bufs;
   std::vector<BlobOp> ops;
   uint8_t* data_dev = nullptr;             // container data section (weights, BN vectors) on the device
@@ -869,6 +871,14 @@ int run_op_f32(dp_model* m, SubPlan* sp, int i, cudaStream_t st) {
   const bool pdl = m->use_pdl != 0;
   auto conv = [&](const dp::NaiveConvParams& q) {
     const long long M = (long long)q.n_img * q.OH * q.OW;
+    if (m->precision == 2) {   // 3xTF32 on the tensor cores (precise_tc.cuh): N tiles of <= 256 couts, multiples of 16
+      const int n_ntiles = (q.Cout + dp::kTxMaxN - 1) / dp::kTxMaxN;
+      const int n_tile = round_up((q.Cout + n_ntiles - 1) / n_ntiles, 16);
+      dim3 grid((unsigned)((M + 127) / 128), (unsigned)n_ntiles, (unsigned)q.n_groups);
+      static const int tx_dbg = getenv("DP_TX_DBG") ? atoi(getenv("DP_TX_DBG")) : 0;   // TEMP
+      dp::conv_tf32x3_kernel<<<grid, dp::kTxThreads, dp::tx_smem_bytes(n_tile), st>>>(q, n_tile | (tx_dbg << 16));
+      return;
+    }
     if (q.Cout <= 32) {
       dim3 grid((unsigned)((M + dp::kPcBM - 1) / dp::kPcBM), (unsigned)((q.Cout + 31) / 32), (unsigned)q.n_groups);
       dp::conv_f32_kernel<32><<<grid, dp::kPcThreads, 0, st>>>(q);
@@ -1290,6 +1300,7 @@ static int alloc_lane_state(dp_model* m) {
     cudaError_t e5 = cudaFuncSetAttribute(dp::dense_layer_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
     if (e5 == cudaSuccess) e5 = cudaFuncSetAttribute(dp::dense_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
     cudaError_t e6 = cudaFuncSetAttribute(dp::dense_layer_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
+    if (e6 == cudaSuccess) e6 = cudaFuncSetAttribute(dp::conv_tf32x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
     if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess || e4 != cudaSuccess || e5 != cudaSuccess || e6 != cudaSuccess || e7 != cudaSuccess) {
       return fail("cudaFuncSetAttribute(MaxDynamicSharedMemorySize) failed: %s", cudaGetErrorString(cudaGetLastError()));
     }
@@ -1339,7 +1350,7 @@ int dp_model_create(const void* blob, size_t nbytes, int device, int max_batch, 
   m->device = device;
   m->max_batch = max_batch;
   m->patch = (int)h.patch;
-  if (h.precision > 1) { delete m; return fail("container asks for unknown precision %u", h.precision); }
+  if (h.precision > 2) { delete m; return fail("container asks for unknown precision %u", h.precision); }
   m->precision = (int)h.precision;
   m->esize = m->precision ? 4 : 2;
   m->num_sms = prop.multiProcessorCount;

@@ -41,8 +41,8 @@ class TileModel:
         p, mb, nb = C.c_int(), C.c_int(), C.c_uint64()
         _lib.check(_lib.lib.dp_model_info(self._h, C.byref(p), C.byref(mb), C.byref(nb)))
         self.patch, self.device_bytes = p.value, nb.value
-        self.precision = "fp32" if _lib.lib.dp_model_precision(self._h) == 1 else "fp16"
-        self._buf_dtype = np.float32 if self.precision == "fp32" else np.float16
+        self.precision = {0: "fp16", 1: "fp32", 2: "tf32x3"}[_lib.lib.dp_model_precision(self._h)]
+        self._buf_dtype = np.float16 if self.precision == "fp16" else np.float32
         self._tile_coords = {}
 
     # ------------------------------------------------------------------ lifetime

@@ -8,7 +8,7 @@ affine terms, into one flat little-endian container that ``dp_model_create`` (cs
 Container layout (must match ``BlobHeader`` / ``BlobBuf`` / ``BlobOp`` in csrc/runtime.cu)::
 
     header  72 B : 'DPB1' | u32 version=1 | u32 n_bufs | u32 n_ops | u32 patch | u32 precision | u64 data_off
-                   | u64 total_bytes | 4 x u64 0        (precision 0: fp16 weights + activations, 1: fp32 both)
+                   | u64 total_bytes | 4 x u64 0        (precision 0: fp16 weights + activations, 1: fp32 both, 2: fp32 both + 3xTF32 convs)
     n_bufs x 16 B: i32 H, W, C, 0                      (per-image activation buffer geometry)
     n_ops  x 128 B: 12 x i32 (type in_buf in_choff cin out_buf out_choff cout kind relu pro head pool)
                    | f32 head_b | 3 x i32 0 | 8 x i64 offsets into the data section (-1 = absent):
@@ -20,7 +20,9 @@ Container layout (must match ``BlobHeader`` / ``BlobBuf`` / ``BlobOp`` in csrc/r
 Precision.  ``precision='fp16'`` (default) is the tensor-core configuration BASELINE.json names: fp16 weights and
 activations, fp32 accumulation.  ``precision='fp32'`` packs the same program with un-rounded fp32 weights; the
 runtime then keeps fp32 activations and runs its fp32 kernels (csrc/precise.cuh) -- the mode that meets the 1e-3
-probability tolerance on any weight set, at a fraction of the throughput.
+probability tolerance on any weight set, at a fraction of the throughput.  ``precision='tf32x3'`` is the same fp32
+program with its convs on the tensor cores: every operand split into two TF32 numbers, three tcgen05 MMAs per product
+(csrc/precise_tc.cuh; ~2^-21 relative per product instead of fp32's 2^-24).
 """
 from __future__ import annotations
 
@@ -38,7 +40,7 @@ OP_DWCONV, OP_GAP, OP_BCAST, OP_RESIZE, OP_HEAD_DOT, OP_HEAD_RESIZE = 8, 9, 10, 
 KIND_1X1, KIND_3X3, KIND_UP2, KIND_STEM4, KIND_TAPS = 1, 3, 4, 5, 6
 POOL_PAD1_ZERO, POOL_TF_SAME = 0, 1   # OP_MAXPOOL `pool` field: ZeroPadding2D(1)+valid (densenet.py:122-123) / padding='same'
 PRO_NONE, PRO_AFFINE, PRO_AFFINE_RELU = 0, 1, 2
-PRECISIONS = {"fp16": 0, "fp32": 1}
+PRECISIONS = {"fp16": 0, "fp32": 1, "tf32x3": 2}
 
 _weight_dtype = [np.float16]
 
