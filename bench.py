@@ -34,7 +34,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-DTYPE = {"fp16": "f16 (fp32 accumulate)", "fp32": "f32"}
+DTYPE = {"fp16": "f16 (fp32 accumulate)", "fp32": "f32", "tf32x3": "f32 storage, 3xTF32 tensor-core products (fp32 accumulate)"}
 METRIC = "tiles_per_sec_256x256_b32"
 UNIT = "tiles/s"
 PATCH, BATCH = 256, 32
@@ -201,8 +201,9 @@ def main():
     ap.add_argument("--slide", type=int, default=8192, help="--workload slide: side of the synthetic slide")
     ap.add_argument("--tta", default="", help="--workload slide: comma separated tta_list")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--precision", default="fp16", choices=["fp16", "fp32"],
-                    help="fp16 = tensor cores (BASELINE configs[1]); fp32 = the library's 1e-3 precision mode")
+    ap.add_argument("--precision", default="fp16", choices=["fp16", "fp32", "tf32x3"],
+                    help="fp16 = tensor cores (BASELINE configs[1]); fp32 / tf32x3 = the library's 1e-3 precision modes "
+                         "(fp32 FMA on the CUDA cores / 3xTF32 split products on the tensor cores)")
     ap.add_argument("--no-slide", action="store_true", help="skip the 40 000^2 slide record of the default line")
     ap.add_argument("--no-parity", action="store_true", help="skip the parity record of the default line")
     ap.add_argument("--line-slide", type=int, default=40000, help="side of the slide behind the line's `slide` record")
@@ -578,29 +579,35 @@ def parity_and_fp32_records(local, fp16_model):
     m16 = engine.TileModel(densenet121_unet_program(w, PATCH), device=local, max_batch=4)
     r16 = rec(m16.forward_tile_batch(t).cpu().numpy())
     m16.close()
-    m32 = engine.TileModel(densenet121_unet_program(w, PATCH, precision="fp32"), device=local, max_batch=BATCH)
-    r32 = rec(m32.forward_tile_batch(t).cpu().numpy())
     tb = torch.randint(0, 256, (BATCH, PATCH, PATCH, 3), dtype=torch.uint8, device=f"cuda:{local}")
     out = torch.empty((BATCH, PATCH, PATCH), dtype=torch.float32, device=f"cuda:{local}")
-    for _ in range(2):
-        m32.forward_tile_batch(tb, out=out)
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    torch.cuda.synchronize()
-    n = 5
-    e0.record()
-    for _ in range(n):
-        m32.forward_tile_batch(tb, out=out)
-    e1.record()
-    torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / n
-    m32.close()
+    recs, modes = {}, {}
+    what = {"fp32": "precision='fp32': fp32 weights / activations / FMA accumulation on the CUDA cores (csrc/precise.cuh), batch 32",
+            "tf32x3": "precision='tf32x3': fp32 weights / activations, every product as three tcgen05 kind::tf32 MMAs on "
+                      "hi/lo split operands, chunked accumulation (csrc/precise_tc.cuh), batch 32"}
+    for prec in ("fp32", "tf32x3"):
+        m32 = engine.TileModel(densenet121_unet_program(w, PATCH, precision=prec), device=local, max_batch=BATCH)
+        recs[prec] = rec(m32.forward_tile_batch(t).cpu().numpy())
+        for _ in range(2):
+            m32.forward_tile_batch(tb, out=out)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        n = 5
+        e0.record()
+        for _ in range(n):
+            m32.forward_tile_batch(tb, out=out)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / n
+        m32.close()
+        modes[prec] = {"tiles_per_s": BATCH / (ms * 1e-3), "ms_per_step": ms, "unit": UNIT,
+                       "achieved_tflops_fp32": REF_FLOP["dense"] * BATCH / (ms * 1e-3) / 1e12, "what": what[prec]}
     parity = {"against": "fp32 oracle (oracle/densenet_ref.py) on calibrated seed-0 weights, 4 uniform-noise tiles",
-              "threshold": 0.3, "fp16": r16, "fp32": r32,
+              "threshold": 0.3, "fp16": r16, "fp32": recs["fp32"], "tf32x3": recs["tf32x3"],
               "note": "the fp16 figure is this random-init instance's own amplification of one 10-bit-mantissa rounding "
-                      "(profiles/r2_parity_conditioning.md), not a kernel error; the fp32 mode carries BASELINE's 1e-3"}
-    fp32_mode = {"tiles_per_s": BATCH / (ms * 1e-3), "ms_per_step": ms, "unit": UNIT,
-                 "achieved_tflops_fp32": REF_FLOP["dense"] * BATCH / (ms * 1e-3) / 1e12,
-                 "what": "precision='fp32': fp32 weights / activations / FMA accumulation (csrc/precise.cuh), batch 32"}
+                      "(profiles/r2_parity_conditioning.md), not a kernel error; the fp32 and tf32x3 modes carry BASELINE's 1e-3"}
+    fp32_mode = modes["fp32"]
+    fp32_mode["tf32x3"] = modes["tf32x3"]
     return parity, fp32_mode
 
 

@@ -220,8 +220,9 @@ def load_trained_models(model, path, patch_size=256, *, device=0, max_batch=32, 
 
     ``path`` is one of the reference's Keras ``.h5`` checkpoints (read in pure Python: h5lite.py + keras_h5.py), a
     flat ``.npz`` of Keras-named arrays (tools/h5_to_npz.py output) or an in-memory weight dict.
-    ``precision``: 'fp16' (tensor cores, fp32 accumulation) or 'fp32' (the reference's arithmetic: matches its fp32
-    ``Model.predict`` within 1e-3 on any weight set; several times slower) -- see program.py.
+    ``precision``: 'fp16' (tensor cores, fp32 accumulation), 'fp32' (the reference's arithmetic on the CUDA cores:
+    matches its fp32 ``Model.predict`` within 1e-3 on any weight set; ~20x slower) or 'tf32x3' (fp32 storage, every
+    product as three TF32 tensor-core MMAs: same tolerance, ~2x faster than 'fp32') -- see program.py.
     """
     from .engine import TileModel
     from .models.densenet import densenet121_unet_program

@@ -67,18 +67,16 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-// x -> (hi, lo): both representable in TF32 (low 13 mantissa bits zero), hi + lo = x up to 2^-22 |x|.
+// x -> (hi, lo): hi = x rounded to TF32 (nearest, ties away: add half an ulp to the magnitude bits and clear the 13 low
+// bits -- two integer instructions; cvt.rna.tf32.f32 costs five with its inf / nan handling, and activations are finite),
+// lo = x - hi (exact) rounded the same way, so that hi + lo = x up to 2^-22 |x| without the bias the tensor core's own
+// truncation of an unrounded lo would add.
 __device__ __forceinline__ void tf32_split(float x, float& hi, float& lo) {
-  uint32_t h, l;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(x));
-  hi = __uint_as_float(h);
-  const float r = x - hi;                            // exact
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(l) : "f"(r));
-  lo = __uint_as_float(l);
+  hi = __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);
+  lo = __uint_as_float((__float_as_uint(x - hi) + 0x1000u) & 0xFFFFE000u);
 }
 
-__global__ void __launch_bounds__(kTxThreads, 1) conv_tf32x3_kernel(const NaiveConvParams p, const int n_tile_dbg) {
-  const int n_tile = n_tile_dbg & 0xFFFF, dbg = n_tile_dbg >> 16;   // TEMP timing switches
+__global__ void __launch_bounds__(kTxThreads, 1) conv_tf32x3_kernel(const NaiveConvParams p, const int n_tile) {
   extern __shared__ uint8_t tx_smem_raw[];
   const uint32_t raw_addr = smem_u32(tx_smem_raw);
   uint8_t* smem = tx_smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
@@ -220,11 +218,11 @@ __global__ void __launch_bounds__(kTxThreads, 1) conv_tf32x3_kernel(const NaiveC
     uint8_t* a_lo = a_hi + kTxATile;
     uint8_t* b_hi = a_lo + kTxATile;
     uint8_t* b_lo = b_hi + n_tile * 128;
-    if (s + 2 < n_slices && !(dbg & 8)) issue((s + 2) % kTxRaw);   // that slot was read back by this thread in iteration s - 1
+    if (s + 2 < n_slices) issue((s + 2) % kTxRaw);   // that slot was read back by this thread in iteration s - 1
     cp_async_commit();
     cp_async_wait<2>();                              // this thread's pieces of slice s have landed
     if (s >= 2) mbar_wait(&bars[st], ((s >> 1) - 1) & 1);      // the MMAs of slice s-2 have read this operand stage
-    if (!(dbg & 4)) {
+    {
       const TapEntry ent = p.entries[cv_e];
       const uint8_t* rs = raw_ring + (s % kTxRaw) * raw_bytes + tid * 16;
       const int c = cv_c + 4 * j;
@@ -253,7 +251,7 @@ __global__ void __launch_bounds__(kTxThreads, 1) conv_tf32x3_kernel(const NaiveC
     }
     // chunk (s >> 1) - 1 finished issuing one iteration ago: fold it into the register sums before its accumulator
     // is reused by chunk (s >> 1) + 1
-    if ((s & 1) && s >= 3 && !(dbg & 16)) drain(drained++);
+    if ((s & 1) && s >= 3) drain(drained++);
     fence_proxy_async_smem();
     __syncthreads();
     if (warp == 0 && elect_one()) {
@@ -263,16 +261,16 @@ __global__ void __launch_bounds__(kTxThreads, 1) conv_tf32x3_kernel(const NaiveC
       const uint64_t dbh = make_sw128_desc(smem_u32(b_hi), 1024, 0), dbl = make_sw128_desc(smem_u32(b_lo), 1024, 0);
 #pragma unroll
       for (int k = 0; k < 4; ++k) {                  // 8 fp32 = 32 B = 2 descriptor units per K-step
-        if (!(dbg & 2)) umma_tf32_ss(d, dah + 2 * k, dbh + 2 * k, idesc, ((s & 1) | k) ? 1u : 0u);
-        if (!(dbg & 3)) umma_tf32_ss(d, dal + 2 * k, dbh + 2 * k, idesc, 1u);
-        if (!(dbg & 3)) umma_tf32_ss(d, dah + 2 * k, dbl + 2 * k, idesc, 1u);
+        umma_tf32_ss(d, dah + 2 * k, dbh + 2 * k, idesc, ((s & 1) | k) ? 1u : 0u);
+        umma_tf32_ss(d, dal + 2 * k, dbh + 2 * k, idesc, 1u);
+        umma_tf32_ss(d, dah + 2 * k, dbl + 2 * k, idesc, 1u);
       }
       umma_commit(&bars[st]);
       if ((s & 1) || s == n_slices - 1) umma_commit(&bars[2 + ((s >> 1) & 1)]);
     }
     __syncwarp();
   }
-  while (drained < n_chunks && !(dbg & 16)) drain(drained++);
+  while (drained < n_chunks) drain(drained++);
 
   // ---- epilogue
   const long long mm = m0 + quad * 32 + lane;
@@ -320,6 +318,273 @@ __global__ void __launch_bounds__(kTxThreads, 1) conv_tf32x3_kernel(const NaiveC
   tc_fence_before();
   __syncthreads();
   if (warp == 0) tmem_dealloc(tmem_base, tmem_cols);
+}
+
+
+// ---------------------------------------------------------------------------------------------------------------
+// Halo variant for 3x3 / up2 convs without prologue (every decoder conv and the 3x3 of every dense layer: > 90 % of the
+// fp32 program's MACs).  Work item = 16 rows x 8 columns of output pixels of one image.  Per 32-channel slice the
+// (16+2) x (8+2) input halo arrives as ONE 4-D TMA box (zero fill outside the image = the conv's padding) straight into
+// the swizzled operand tile of 180 rows, is split in place (hi stays, lo goes to a second tile) by the worker warps, and
+// every tap (dy, dx) is a UMMA descriptor into that tile at row (dy+1) * 10 + (dx+1) with an 8-row-group stride of 10
+// rows (the 128-byte swizzle is a function of absolute shared-memory address bits, so unaligned starts are fine:
+// tools/mma_probe.cu).  Weights come PRE-SPLIT (hi / lo copies of the container's data section made at model creation)
+// through two 3-D TMA boxes per tap into a ring of tap stages.  One elected thread of a control warp issues every TMA
+// and every MMA; eight worker warps convert, drain finished accumulator chunks (3 taps; 2 for up2) into registers and
+// run the epilogue.  All hand-offs are mbarriers; there is no block-wide barrier inside the loop.
+constexpr int kThHaloW = 10, kThHaloH = 18, kThRows = 180;
+constexpr int kThATile = 23 * 1024;                 // 180 rows x 128 B, rounded up to 1 KB
+constexpr int kThItems = 6;                         // ceil(180 * 8 chunks / 256 worker threads)
+constexpr int kThBStages = 4;
+constexpr int kThThreads = 288;                     // 8 worker warps + 1 control warp
+
+__host__ __device__ inline int th_smem_bytes(int n) { return 1024 + 2 * 2 * kThATile + kThBStages * 2 * n * 128 + 256; }
+
+__global__ void __launch_bounds__(kThThreads, 1)
+conv_halo_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_wh,
+                        const __grid_constant__ CUtensorMap map_wl, const NaiveConvParams p, const int n_tile) {
+  extern __shared__ uint8_t tx_smem_raw[];
+  const uint32_t raw_addr = smem_u32(tx_smem_raw);
+  uint8_t* smem = tx_smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
+  constexpr int SB = kThBStages;
+  const int b_stage_bytes = 2 * n_tile * 128;
+  uint8_t* a_op = smem;                              // [2 stages][hi | lo]
+  uint8_t* b_op = smem + 4 * kThATile;               // [SB stages][hi | lo]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(b_op + SB * b_stage_bytes);
+  uint64_t* b_full = bars;                           // [SB] TMA landed
+  uint64_t* b_empty = bars + SB;                     // [SB] MMAs have read the stage
+  uint64_t* a_full = bars + 2 * SB;                  // [2] raw halo slice landed
+  uint64_t* a_ready = a_full + 2;                    // [2] split done (8 worker warps)
+  uint64_t* a_empty = a_ready + 2;                   // [2] MMAs have read the stage
+  uint64_t* acc_full = a_empty + 2;                  // [2] chunk complete in TMEM
+  uint64_t* acc_empty = acc_full + 2;                // [2] chunk drained (8 worker warps)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  int* s_tap_e = reinterpret_cast<int*>(tmem_slot + 1);                      // [9] entry index of tap i of this group
+  uint32_t* s_tap_a = reinterpret_cast<uint32_t*>(s_tap_e + 9);              // [9] byte offset of tap i inside the halo tile
+
+  float* __restrict__ out = reinterpret_cast<float*>(p.out);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tiles_w = p.W / 8, tiles_h = p.H / 16;
+  const int item = blockIdx.x;
+  const int img = item / (tiles_w * tiles_h), rem = item % (tiles_w * tiles_h);
+  const int y0 = (rem / tiles_w) * 16, x0 = (rem % tiles_w) * 8;
+  const int n0 = blockIdx.y * n_tile, g = blockIdx.z;
+
+  uint32_t tmem_cols = 32;
+  while (tmem_cols < static_cast<uint32_t>(2 * n_tile)) tmem_cols <<= 1;
+  if (warp == 0) {
+    tmem_alloc(tmem_slot, tmem_cols);
+    tmem_relinquish();
+  }
+  if (tid == 256) {
+    for (int i = 0; i < SB; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&a_full[i], 1); mbar_init(&a_ready[i], 8); mbar_init(&a_empty[i], 1);
+      mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 8);
+    }
+    fence_barrier_init();
+    int n = 0;
+    for (int e = 0; e < p.n_entries_total && n < 9; ++e)
+      if (p.entries[e].group == g) {
+        s_tap_e[n] = e;
+        s_tap_a[n] = static_cast<uint32_t>(((p.entries[e].dy + 1) * kThHaloW + p.entries[e].dx + 1) * 128);
+        ++n;
+      }
+    tma_prefetch_desc(&map_a);
+    tma_prefetch_desc(&map_wh);
+    tma_prefetch_desc(&map_wl);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int n_taps = p.n_entries_total / p.n_groups;               // the dispatcher guarantees 3..9 taps, all in the halo
+  const int chunk_taps = (n_taps % 3 == 0) ? 3 : ((n_taps % 2 == 0) ? 2 : 1);
+  const int cph = n_taps / chunk_taps;                             // accumulator chunks per halo slice
+  const int n_hs = (p.Cin + kTxSliceK - 1) / kTxSliceK;            // halo slices
+  const int n_steps = n_hs * n_taps;
+
+  if (warp == 8) {
+    // ================================================= control: every TMA and every MMA of this work item
+    if (elect_one()) {
+      const uint32_t idesc = make_idesc_tf32(static_cast<uint32_t>(n_tile));
+      const uint32_t a_op_addr = smem_u32(a_op), b_op_addr = smem_u32(b_op);
+      const uint32_t b_desc_hi = sw128_desc_hi(1024), a_desc_hi = sw128_desc_hi(kThHaloW * 128);
+      const uint32_t b_tx = static_cast<uint32_t>(b_stage_bytes), a_tx = kThRows * 128;
+      auto load_a = [&](int hs) {
+        uint64_t* bar = &a_full[hs & 1];
+        mbar_expect_tx(bar, a_tx);
+        tma_load_4d(&map_a, bar, a_op + (hs & 1) * 2 * kThATile, p.in_choff + hs * kTxSliceK, x0 - 1, y0 - 1, img);
+      };
+      int ld_tap = 0, ld_c0 = 0, ld_left = n_steps;
+      auto load_b = [&](int stage) {                 // next tap in (slice, tap) order -> `stage`
+        uint64_t* bar = &b_full[stage];
+        uint8_t* dst = b_op + stage * b_stage_bytes;
+        mbar_expect_tx(bar, b_tx);
+        tma_load_3d(&map_wh, bar, dst, ld_c0, n0, s_tap_e[ld_tap]);
+        tma_load_3d(&map_wl, bar, dst + n_tile * 128, ld_c0, n0, s_tap_e[ld_tap]);
+        --ld_left;
+        if (++ld_tap == n_taps) { ld_tap = 0; ld_c0 += kTxSliceK; }
+      };
+      load_a(0);
+      if (n_hs > 1) load_a(1);
+      for (int i = 0; i < SB && ld_left > 0; ++i) load_b(i);
+      int st = 0, use = 0;                           // tap stage of the current step and how often it has been used
+      int r_st = -1, r_use = 0;                      // stage of the previous step: refilled once its MMAs are done
+      int chunk = 0, cpos = 0;
+      for (int hs = 0; hs < n_hs; ++hs) {
+        mbar_wait(&a_ready[hs & 1], (hs >> 1) & 1);
+        tc_fence_after();
+        const uint32_t a_hi_addr = a_op_addr + static_cast<uint32_t>((hs & 1) * 2 * kThATile);
+        for (int tap = 0; tap < n_taps; ++tap) {
+          if (cpos == 0 && chunk >= 2) {
+            mbar_wait(&acc_empty[chunk & 1], ((chunk >> 1) - 1) & 1);       // chunk - 2 has been drained
+            tc_fence_after();
+          }
+          mbar_wait(&b_full[st], use & 1);
+          const uint32_t d = tmem_base + static_cast<uint32_t>((chunk & 1) * n_tile);
+          const uint32_t ta = a_hi_addr + s_tap_a[tap];
+          const uint32_t tb = b_op_addr + static_cast<uint32_t>(st * b_stage_bytes);
+          const uint64_t dah = (static_cast<uint64_t>(a_desc_hi) << 32) | sw128_desc_lo(ta);
+          const uint64_t dal = (static_cast<uint64_t>(a_desc_hi) << 32) | sw128_desc_lo(ta + kThATile);
+          const uint64_t dbh = (static_cast<uint64_t>(b_desc_hi) << 32) | sw128_desc_lo(tb);
+          const uint64_t dbl = (static_cast<uint64_t>(b_desc_hi) << 32) | sw128_desc_lo(tb + n_tile * 128);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {              // 8 fp32 = 32 B = 2 descriptor units per K-step
+            umma_tf32_ss(d, dah + 2 * k, dbh + 2 * k, idesc, (cpos == 0 && k == 0) ? 0u : 1u);
+            umma_tf32_ss(d, dal + 2 * k, dbh + 2 * k, idesc, 1u);
+            umma_tf32_ss(d, dah + 2 * k, dbl + 2 * k, idesc, 1u);
+          }
+          umma_commit(&b_empty[st]);
+          if (tap == n_taps - 1) umma_commit(&a_empty[hs & 1]);
+          if (cpos == chunk_taps - 1) { umma_commit(&acc_full[chunk & 1]); cpos = 0; ++chunk; } else { ++cpos; }
+          // refill the PREVIOUS step's stage: its MMAs ran ahead of the ones just issued, so the wait is short
+          if (r_st >= 0 && ld_left > 0) {
+            mbar_wait(&b_empty[r_st], r_use & 1);
+            load_b(r_st);
+          }
+          r_st = st; r_use = use;
+          if (++st == SB) { st = 0; ++use; }
+          // raw halo of the next slice into the other A stage, once the MMAs of slice hs - 1 have left it
+          if (tap == 0 && hs >= 1 && hs + 1 < n_hs) {
+            mbar_wait(&a_empty[(hs + 1) & 1], ((hs - 1) >> 1) & 1);
+            load_a(hs + 1);
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else {
+    // ================================================= workers: split, drain, epilogue
+    uint32_t a_sw[kThItems];
+#pragma unroll
+    for (int i = 0; i < kThItems; ++i) {
+      const int q = tid + 256 * i;
+      const int R = q >> 3, j = q & 7;
+      a_sw[i] = static_cast<uint32_t>((R >> 3) * 1024 + (R & 7) * 128 + ((j ^ (R & 7)) << 4));
+    }
+    auto convert = [&](int hs) {                     // hi tile (raw, as TMA delivered it) -> hi in place, lo beside it
+      uint8_t* hi_tile = a_op + (hs & 1) * 2 * kThATile;
+      uint8_t* lo_tile = hi_tile + kThATile;
+      mbar_wait(&a_full[hs & 1], (hs >> 1) & 1);
+#pragma unroll
+      for (int i = 0; i < kThItems; ++i) {
+        if (tid + 256 * i < kThRows * 8) {
+          const float4 v = *reinterpret_cast<const float4*>(hi_tile + a_sw[i]);
+          float4 h, l;
+          tf32_split(v.x, h.x, l.x); tf32_split(v.y, h.y, l.y); tf32_split(v.z, h.z, l.z); tf32_split(v.w, h.w, l.w);
+          *reinterpret_cast<float4*>(hi_tile + a_sw[i]) = h;
+          *reinterpret_cast<float4*>(lo_tile + a_sw[i]) = l;
+        }
+      }
+      fence_proxy_async_smem();
+      mbar_arrive_warp(&a_ready[hs & 1]);
+    };
+    const int quad = warp & 3, half = warp >> 2;
+    float sum[4][16];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+      for (int b = 0; b < 16; ++b) sum[a][b] = 0.f;
+    auto drain = [&](int chunk) {                    // acc[chunk & 1] -> sum (round-to-nearest adds)
+      mbar_wait(&acc_full[chunk & 1], (chunk >> 1) & 1);
+      tc_fence_after();
+      const uint32_t t0 = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + static_cast<uint32_t>((chunk & 1) * n_tile);
+#pragma unroll
+      for (int a = 0; a < 4; ++a) {
+        const int u = half + 2 * a;
+        if (u * 16 < n_tile) {
+          uint32_t v[16];
+          tmem_ld16(t0 + static_cast<uint32_t>(u * 16), v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int b = 0; b < 16; ++b) sum[a][b] += __uint_as_float(v[b]);
+        }
+      }
+      tc_fence_before();
+      mbar_arrive_warp(&acc_empty[chunk & 1]);
+    };
+    convert(0);
+    int chunk = 0;
+    for (int hs = 0; hs < n_hs; ++hs)
+      for (int ci = 0; ci < cph; ++ci) {
+        drain(chunk++);
+        if (ci == 0 && hs + 1 < n_hs) convert(hs + 1);             // while the tensor pipe works on the rest of slice hs
+      }
+
+    // ---- epilogue: accumulator row m = 8 g + x  ->  output pixel (y0 + g, x0 + x)
+    const int m = quad * 32 + lane;
+    const int oy = y0 + (m >> 3), ox = x0 + (m & 7);
+    const long long opix = p.up2 ? (static_cast<long long>(img) * 2 * p.H + 2 * oy + (g >> 1)) * (2 * p.W) + 2 * ox + (g & 1)
+                                 : (static_cast<long long>(img) * p.H + oy) * p.W + ox;
+    float* orow = out + opix * p.out_ctot + p.out_choff;
+    const bool vec_ok = ((p.out_ctot | p.out_choff) & 3) == 0;
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+      const int u = half + 2 * a;
+      if (u * 16 >= n_tile) continue;
+#pragma unroll
+      for (int j4 = 0; j4 < 4; ++j4) {
+        const int co = n0 + u * 16 + 4 * j4;
+        if (co >= p.Cout) continue;
+        float y[4];
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          const int c = co + t;
+          float val = sum[a][4 * j4 + t];
+          if (c < p.Cout) {
+            val = fmaf(val, p.epi_scale ? p.epi_scale[c] : 1.f, p.epi_shift ? p.epi_shift[c] : 0.f);
+            if (p.residual) val += orow[c];
+            if (p.relu) val = fmaxf(val, 0.f);
+          }
+          y[t] = val;
+        }
+        if (co + 3 < p.Cout && vec_ok) {
+          *reinterpret_cast<float4*>(orow + co) = make_float4(y[0], y[1], y[2], y[3]);
+        } else {
+#pragma unroll
+          for (int t = 0; t < 4; ++t)
+            if (co + t < p.Cout) orow[co + t] = y[t];
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_base, tmem_cols);
+}
+
+// data section -> hi / lo copies (run once at model creation for precision 2): hi and lo both rounded to TF32
+__global__ void tf32_presplit_kernel(const float* __restrict__ x, float* __restrict__ hi, float* __restrict__ lo, size_t n) {
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n; i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const float v = x[i];
+    uint32_t b = __float_as_uint(v);
+    const bool finite = (b & 0x7F800000u) != 0x7F800000u;
+    const float h = finite ? __uint_as_float((b + 0x1000u) & 0xFFFFE000u) : v;
+    const float r = finite ? v - h : 0.f;
+    hi[i] = h;
+    lo[i] = __uint_as_float((__float_as_uint(r) + 0x1000u) & 0xFFFFE000u);
+  }
 }
 
 }  // namespace dp

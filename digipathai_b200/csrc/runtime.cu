@@ -80,12 +80,12 @@ PFN_cuTensorMapEncodeTiled_v12000 get_encode() {
 // `pix_stride` > 1 sets the traversal (element) stride of dims 1 and 2 (W, H of an NHWC map): the box then
 // covers box[i] input elements and delivers ceil(box[i] / pix_stride) of them -- a strided conv's operand tile.
 int make_map(CUtensorMap* map, const void* base, int rank, const uint64_t* dims, const uint64_t* strides,
-             const uint32_t* box, int pix_stride = 1) {
+             const uint32_t* box, int pix_stride = 1, CUtensorMapDataType dtype = CU_TENSOR_MAP_DATA_TYPE_FLOAT16) {
   auto enc = get_encode();
   if (!enc) return fail("cuTensorMapEncodeTiled entry point not available (driver too old?)");
   uint32_t estr[5] = {1, 1, 1, 1, 1};
   if (pix_stride > 1 && rank >= 3) estr[1] = estr[2] = (uint32_t)pix_stride;
-  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, rank, const_cast<void*>(base), dims, strides, box, estr,
+  CUresult r = enc(map, dtype, rank, const_cast<void*>(base), dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS)
@@ -133,6 +133,8 @@ struct Launch {
   CUtensorMap map_w2;
   dp::DenseLayerParams dl;
   dp::NaiveConvParams np2;  // debug path: the 3x3 half (np holds the 1x1 half)
+  // 3xTF32 mode (precision 2): TMA maps of the halo kernel for np (tx[0]) / np2 (tx[1]); n_tile 0 = generic kernel
+  struct TxPlan { CUtensorMap a, wh, wl; int n_tile = 0, n_ntiles = 0; } tx[2];
   // persistent dense-block kernel (dense_block.cuh): set on the FIRST layer of a run of dense layers on small maps;
   // the other layers of the run carry block_member and launch nothing when the whole program is executed
   int block_len = 0;
@@ -168,6 +170,9 @@ struct dp_model {
   std::vector<BlobOp> ops;
   uint8_t* data_dev = nullptr;             // container data section (weights, BN vectors) on the device
   std::shared_ptr<void> data_owner;        // ... shared between a model and its lanes (dp_model_clone)
+  float* data_hi_dev = nullptr;            // precision 2: TF32 hi / lo copies of the data section (precise_tc.cuh)
+  float* data_lo_dev = nullptr;
+  std::shared_ptr<void> data_hi_owner, data_lo_owner;
   size_t data_bytes = 0;
   std::vector<__half*> buf_dev;    // activation buffers (raw storage: __half or float elements, see esize)
   __half* scratch_head = nullptr;  // naive / fp32 paths: output of the head-fused conv
@@ -277,6 +282,36 @@ void fill_entries(int kind, int H, int W, int kh, int kw, int stride, dp::TapEnt
   if (halo) *halo = hl;
 }
 
+// 3xTF32 mode: N tiling of a conv, and -- for 3x3 / up2 convs without prologue on maps the 16 x 8 regions tile -- the
+// TMA maps of conv_halo_tf32x3_kernel (activation halo box, pre-split weight boxes).
+int plan_tx(dp_model* m, const dp::NaiveConvParams& q, Launch::TxPlan& t) {
+  t.n_ntiles = (q.Cout + dp::kTxMaxN - 1) / dp::kTxMaxN;
+  const int n_tile = round_up((q.Cout + t.n_ntiles - 1) / t.n_ntiles, 16);
+  t.n_tile = 0;
+  const int epg = q.n_groups ? q.n_entries_total / q.n_groups : 0;
+  bool halo = m->precision == 2 && q.stride == 1 && !q.pro_mode && !q.residual && q.H % 16 == 0 && q.W % 8 == 0 &&
+              q.Cin % 4 == 0 && (q.up2 || (q.OH == q.H && q.OW == q.W)) && epg >= 3 && epg <= 9 && m->data_hi_dev &&
+              !getenv("DP_TX_NO_HALO");
+  for (int e = 0; e < q.n_entries_total && halo; ++e)
+    halo = q.entries[e].dy >= -1 && q.entries[e].dy <= 1 && q.entries[e].dx >= -1 && q.entries[e].dx <= 1;
+  if (!halo) return 0;
+  {
+    uint64_t dims[4] = {(uint64_t)(q.in_choff + q.Cin), (uint64_t)q.W, (uint64_t)q.H, (uint64_t)q.n_img};
+    const uint64_t cs = (uint64_t)q.in_ctot * 4;
+    uint64_t str[3] = {cs, cs * q.W, cs * q.W * q.H};
+    uint32_t box[4] = {32, (uint32_t)dp::kThHaloW, (uint32_t)dp::kThHaloH, 1};
+    if (make_map(&t.a, q.in, 4, dims, str, box, 1, CU_TENSOR_MAP_DATA_TYPE_FLOAT32)) return 1;
+  }
+  const size_t woff = reinterpret_cast<const uint8_t*>(q.w) - m->data_dev;
+  uint64_t dims[3] = {(uint64_t)q.Cin, (uint64_t)q.Cout, (uint64_t)q.n_entries_total};
+  uint64_t str[2] = {(uint64_t)q.Cin * 4, (uint64_t)q.Cin * q.Cout * 4};
+  uint32_t box[3] = {32, (uint32_t)n_tile, 1};
+  if (make_map(&t.wh, reinterpret_cast<const uint8_t*>(m->data_hi_dev) + woff, 3, dims, str, box, 1, CU_TENSOR_MAP_DATA_TYPE_FLOAT32)) return 1;
+  if (make_map(&t.wl, reinterpret_cast<const uint8_t*>(m->data_lo_dev) + woff, 3, dims, str, box, 1, CU_TENSOR_MAP_DATA_TYPE_FLOAT32)) return 1;
+  t.n_tile = n_tile;
+  return 0;
+}
+
 int plan_conv(dp_model* m, const BlobOp& op, int img0, int B, Launch& L) {
   using namespace dp;
   const BlobBuf& ib = m->bufs[op.in_buf];
@@ -322,9 +357,9 @@ int plan_conv(dp_model* m, const BlobOp& op, int img0, int B, Launch& L) {
     q.out = buf_at(op.out_buf); q.out_ctot = m->bufs[op.out_buf].C; q.out_choff = op.out_choff;
   }
   L.head_C = op.cout;
-  if (m->precision) {   // fp32 mode executes the description above with conv_f32_kernel: no tensor-core plan
+  if (m->precision) {   // fp32 modes execute the description above with conv_f32_kernel / the 3xTF32 kernels
     L.macs = (uint64_t)B * OH * OW * n_entries_total * op.cin * op.cout;
-    return 0;
+    return plan_tx(m, q, L.tx[0]);
   }
 
   // ---- tensor-core plan
@@ -640,9 +675,9 @@ int plan_dense_layer(dp_model* m, const BlobOp& op, int img0, int B, Launch& L) 
   b.Cout = 32; b.out_ctot = ib.C; b.out_choff = op.out_choff; b.n_entries_total = 9; b.n_groups = 1;
   memcpy(b.entries, t3, sizeof t3);
   b.in = buf_at(mid_buf); b.w = dptr<__half>(m, op.rsv64[0]); b.out = buf_at(op.in_buf);
-  if (m->precision) {   // fp32 mode: the two convs above through the bottleneck buffer
+  if (m->precision) {   // fp32 modes: the two convs above through the bottleneck buffer
     L.macs = (uint64_t)B * H * W * ((uint64_t)op.cin * 128 + 9ull * 128 * 32);
-    return 0;
+    return plan_tx(m, L.np, L.tx[0]) || plan_tx(m, L.np2, L.tx[1]);
   }
 
   // ---- fused tensor-core plan
@@ -869,14 +904,17 @@ int run_op_f32(dp_model* m, SubPlan* sp, int i, cudaStream_t st) {
   const BlobBuf& ib = m->bufs[op.in_buf];
   const BlobBuf& ob = m->bufs[op.out_buf];
   const bool pdl = m->use_pdl != 0;
-  auto conv = [&](const dp::NaiveConvParams& q) {
+  auto conv = [&](const dp::NaiveConvParams& q, const Launch::TxPlan& t) {
     const long long M = (long long)q.n_img * q.OH * q.OW;
-    if (m->precision == 2) {   // 3xTF32 on the tensor cores (precise_tc.cuh): N tiles of <= 256 couts, multiples of 16
-      const int n_ntiles = (q.Cout + dp::kTxMaxN - 1) / dp::kTxMaxN;
-      const int n_tile = round_up((q.Cout + n_ntiles - 1) / n_ntiles, 16);
-      dim3 grid((unsigned)((M + 127) / 128), (unsigned)n_ntiles, (unsigned)q.n_groups);
-      static const int tx_dbg = getenv("DP_TX_DBG") ? atoi(getenv("DP_TX_DBG")) : 0;   // TEMP
-      dp::conv_tf32x3_kernel<<<grid, dp::kTxThreads, dp::tx_smem_bytes(n_tile), st>>>(q, n_tile | (tx_dbg << 16));
+    if (m->precision == 2) {   // 3xTF32 on the tensor cores (precise_tc.cuh): N tiles of <= 128 couts, multiples of 16
+      if (t.n_tile) {          // 3x3 / up2 without prologue: TMA halo tile per channel slice, taps as descriptor offsets
+        dim3 hgrid((unsigned)(q.n_img * (q.H / 16) * (q.W / 8)), (unsigned)t.n_ntiles, (unsigned)q.n_groups);
+        dp::conv_halo_tf32x3_kernel<<<hgrid, dp::kThThreads, dp::th_smem_bytes(t.n_tile), st>>>(t.a, t.wh, t.wl, q, t.n_tile);
+        return;
+      }
+      const int n_tile = round_up((q.Cout + t.n_ntiles - 1) / t.n_ntiles, 16);
+      dim3 grid((unsigned)((M + 127) / 128), (unsigned)t.n_ntiles, (unsigned)q.n_groups);
+      dp::conv_tf32x3_kernel<<<grid, dp::kTxThreads, dp::tx_smem_bytes(n_tile), st>>>(q, n_tile);
       return;
     }
     if (q.Cout <= 32) {
@@ -960,7 +998,7 @@ int run_op_f32(dp_model* m, SubPlan* sp, int i, cudaStream_t st) {
       break;
     }
     case OP_CONV: {
-      conv(L.np);
+      conv(L.np, L.tx[0]);
       LAUNCH_OK();
       if (op.head) {
         const long long tot = (long long)B * m->patch * m->patch;
@@ -971,9 +1009,9 @@ int run_op_f32(dp_model* m, SubPlan* sp, int i, cudaStream_t st) {
       break;
     }
     case OP_DENSE_LAYER: {
-      conv(L.np);
+      conv(L.np, L.tx[0]);
       LAUNCH_OK();
-      conv(L.np2);
+      conv(L.np2, L.tx[1]);
       break;
     }
     default:
@@ -1301,6 +1339,7 @@ static int alloc_lane_state(dp_model* m) {
     if (e5 == cudaSuccess) e5 = cudaFuncSetAttribute(dp::dense_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
     cudaError_t e6 = cudaFuncSetAttribute(dp::dense_layer_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
     if (e6 == cudaSuccess) e6 = cudaFuncSetAttribute(dp::conv_tf32x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
+    if (e6 == cudaSuccess) e6 = cudaFuncSetAttribute(dp::conv_halo_tf32x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
     if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess || e4 != cudaSuccess || e5 != cudaSuccess || e6 != cudaSuccess || e7 != cudaSuccess) {
       return fail("cudaFuncSetAttribute(MaxDynamicSharedMemorySize) failed: %s", cudaGetErrorString(cudaGetLastError()));
     }
@@ -1372,6 +1411,18 @@ int dp_model_create(const void* blob, size_t nbytes, int device, int max_batch, 
   m->device_bytes += m->data_bytes;
   e = cudaMemcpy(m->data_dev, bytes + h.data_off, m->data_bytes, cudaMemcpyHostToDevice);
   if (e != cudaSuccess) { cleanup(); return fail("cudaMemcpy weights: %s", cudaGetErrorString(e)); }
+  if (m->precision == 2 && m->data_bytes >= 4) {   // TF32 hi / lo copies of the weights for the pre-split operand path
+    e = cudaMalloc(&m->data_hi_dev, m->data_bytes);
+    if (e == cudaSuccess) m->data_hi_owner = std::shared_ptr<void>(m->data_hi_dev, [](void* q) { cudaFree(q); });
+    if (e == cudaSuccess) e = cudaMalloc(&m->data_lo_dev, m->data_bytes);
+    if (e == cudaSuccess) m->data_lo_owner = std::shared_ptr<void>(m->data_lo_dev, [](void* q) { cudaFree(q); });
+    if (e != cudaSuccess) { cleanup(); return fail("cudaMalloc TF32 weight copies: %s", cudaGetErrorString(e)); }
+    dp::tf32_presplit_kernel<<<1024, 256>>>(reinterpret_cast<const float*>(m->data_dev), m->data_hi_dev, m->data_lo_dev,
+                                            m->data_bytes / 4);
+    e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) { cleanup(); return fail("TF32 weight split: %s", cudaGetErrorString(e)); }
+    m->device_bytes += 2 * m->data_bytes;
+  }
   if (alloc_lane_state(m)) { cleanup(); return 1; }
   *out = m;
   return 0;
@@ -1385,6 +1436,8 @@ int dp_model_clone(const dp_model* src, dp_model** out) {
   m->precision = src->precision; m->esize = src->esize;
   m->bufs = src->bufs; m->ops = src->ops;
   m->data_dev = src->data_dev; m->data_owner = src->data_owner; m->data_bytes = src->data_bytes;
+  m->data_hi_dev = src->data_hi_dev; m->data_hi_owner = src->data_hi_owner;
+  m->data_lo_dev = src->data_lo_dev; m->data_lo_owner = src->data_lo_owner;
   if (alloc_lane_state(m)) { dp_model_destroy(m); return 1; }
   m->use_graph = src->use_graph; m->split = src->split; m->use_pdl = src->use_pdl; m->epi_direct = src->epi_direct;
   m->use_overlap = src->use_overlap; m->b_resident = src->b_resident; m->b_pair = src->b_pair;
@@ -1415,6 +1468,8 @@ int dp_model_destroy(dp_model* m) {
     if (p) cudaFree(p);
   if (m->scratch_head) cudaFree(m->scratch_head);
   m->data_owner.reset();   // frees the data section with its last user
+  m->data_hi_owner.reset();
+  m->data_lo_owner.reset();
   delete m;
   return 0;
 }

@@ -145,3 +145,92 @@ def test_deeplab_fp32_mode_meets_1e3():
     model.close()
     mx, mn, mm = _check(got, want)
     print(f"\ndeeplab fp32 mode: max|p-oracle| {mx:.2e} mean {mn:.2e} label mismatches {mm}")
+
+
+# ------------------------------------------------------------------------------------------------ 3xTF32 mode
+def test_tf32x3_single_convs_are_fp32_accurate():
+    """One conv at a time against a float64 evaluation: the 3xTF32 kernels (csrc/precise_tc.cuh) must stay within a few
+    fp32 ulps of the exact result for reductions up to K = 9216 -- which is what the chunked accumulation is for: a
+    single TMEM accumulator loses ~1e-8 x K relative to the tensor core's truncating adds (tools/tf32x3_accuracy.py).
+    Covers the generic kernel (1x1; 3x3 on an 8x8 map; pre-activation prologue; Cout tail) and the halo kernel (3x3 and
+    up2 on 16x16 / 32x32 maps, N tiles of 112 and 128)."""
+    import torch
+    from digipathai_b200.engine import TileModel
+    from digipathai_b200.program import (KIND_1X1, KIND_3X3, KIND_UP2, OP_CONV, PRO_AFFINE_RELU, Op, Program,
+                                         pack_conv_weights, pad64, weight_precision)
+    rng = np.random.default_rng(3)
+    #        kind      H   Cin   Cout  prologue
+    cases = [(KIND_1X1, 16, 2048, 128, False), (KIND_1X1, 16, 96, 80, True), (KIND_3X3, 8, 256, 64, False),
+             (KIND_3X3, 16, 1024, 128, False), (KIND_3X3, 32, 64, 320, False), (KIND_UP2, 16, 128, 96, False)]
+    for kind, H, cin, cout, pro in cases:
+        k = 1 if kind == KIND_1X1 else 3
+        kern = np.abs(rng.standard_normal((k, k, cin, cout)) * np.sqrt(2.0 / (k * k * cin))).astype(np.float32)
+        x = np.abs(rng.standard_normal((2, H, H, cin))).astype(np.float32)      # positive: sums do not cancel
+        up = 2 if kind == KIND_UP2 else 1
+        with weight_precision("tf32x3"):
+            pr = Program(patch=64)
+            pr.precision = "tf32x3"
+            ib, ob = pr.add_buf("in", H, H, cin), pr.add_buf("out", H * up, H * up, cout)
+            op = Op(OP_CONV, in_buf=ib, in_choff=0, cin=cin, out_buf=ob, out_choff=0, cout=cout, kind=kind, relu=0,
+                    w=pack_conv_weights(kern, kind), name="c", epi_shift=np.zeros(cout, np.float32))
+            if pro:
+                op.pro = PRO_AFFINE_RELU
+                op.pro_scale = pad64(rng.uniform(0.5, 1.5, cin).astype(np.float32))
+                op.pro_shift = pad64((0.3 * rng.standard_normal(cin)).astype(np.float32))
+            pr.ops.append(op)
+        m = TileModel(pr, device=0, max_batch=2)
+        assert m.precision == "tf32x3"
+        m.write_buffer(0, x)
+        m.write_buffer(1, np.zeros((2, H * up, H * up, cout), np.float32))
+        m.run_ops(2, 0, 1)
+        torch.cuda.synchronize()
+        got = m.read_buffer(1, 2).astype(np.float64)
+        m.close()
+        xa = x.astype(np.float64)
+        if pro:
+            xa = np.maximum(xa * op.pro_scale[:cin].astype(np.float64) + op.pro_shift[:cin].astype(np.float64), 0.0)
+        if kind == KIND_UP2:
+            xa = xa.repeat(2, axis=1).repeat(2, axis=2)                          # UpSampling2D() then the 3x3 conv
+        Ho = H * up
+        xp = np.pad(xa, ((0, 0), (k // 2, k // 2), (k // 2, k // 2), (0, 0)))
+        ref = np.zeros((2, Ho, Ho, cout))
+        for dy in range(k):
+            for dx in range(k):
+                ref += xp[:, dy:dy + Ho, dx:dx + Ho] @ kern[dy, dx].astype(np.float64)
+        rel = np.abs(got - ref).max() / np.abs(ref).max()
+        # up2 sums taps of the 3x3 kernel in fp32 when packing (program.pack_conv_weights): one more rounding
+        assert rel <= (6e-6 if kind == KIND_UP2 else 3e-6), (kind, H, cin, cout, rel)
+
+
+@pytest.mark.parametrize("name", ["dense", "inception", "deeplabv3"])
+def test_tf32x3_mode_meets_1e3(name, calibrated_weights):
+    """BASELINE's tolerance on the tensor-core precision mode: every conv as three TF32 MMAs on split operands."""
+    import torch
+    from digipathai_b200.engine import TileModel
+    rng = np.random.default_rng(7)
+    if name == "dense":
+        from digipathai_b200.models.densenet import densenet121_unet_program as build
+        from oracle import densenet_ref as ref
+        w, tiles = calibrated_weights
+        tiles = np.concatenate([tiles, rng.integers(0, 256, (2, 256, 256, 3)).astype(np.uint8)])
+    else:
+        if name == "inception":
+            from digipathai_b200.models.inception import inception_resnet_v2_unet_program as build, init_inception_weights as init
+            from oracle import inception_ref as ref
+        else:
+            from digipathai_b200.models.deeplab import deeplabv3plus_xception_program as build, init_deeplab_weights as init
+            from oracle import deeplab_ref as ref
+        tiles = rng.integers(0, 256, (2, 256, 256, 3)).astype(np.uint8)
+        w = init(0)
+        ref.calibrate_bn(w, (tiles.astype(np.float32) - 128.0) / 128.0)
+    want = ref.forward(w, (tiles.astype(np.float32) - 128.0) / 128.0)[..., 1]
+    model = TileModel(build(w, 256, precision="tf32x3"), device=0, max_batch=len(tiles))
+    assert model.precision == "tf32x3"
+    got = model.forward_tile_batch(torch.from_numpy(tiles).cuda()).cpu().numpy()
+    lane = model.clone()                                     # a lane shares the pre-split weight copies
+    got2 = lane.forward_tile_batch(torch.from_numpy(tiles).cuda()).cpu().numpy()
+    lane.close()
+    model.close()
+    assert np.array_equal(got, got2)
+    mx, mn, mm = _check(got, want)
+    print(f"\n{name} tf32x3 mode: max|p-oracle| {mx:.2e} mean {mn:.2e} label mismatches {mm}")
