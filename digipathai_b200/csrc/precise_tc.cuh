@@ -329,14 +329,16 @@ __global__ void __launch_bounds__(kTxThreads, 1) conv_tf32x3_kernel(const NaiveC
 // every tap (dy, dx) is a UMMA descriptor into that tile at row (dy+1) * 10 + (dx+1) with an 8-row-group stride of 10
 // rows (the 128-byte swizzle is a function of absolute shared-memory address bits, so unaligned starts are fine:
 // tools/mma_probe.cu).  Weights come PRE-SPLIT (hi / lo copies of the container's data section made at model creation)
-// through two 3-D TMA boxes per tap into a ring of tap stages.  One elected thread of a control warp issues every TMA
-// and every MMA; eight worker warps convert, drain finished accumulator chunks (3 taps; 2 for up2) into registers and
-// run the epilogue.  All hand-offs are mbarriers; there is no block-wide barrier inside the loop.
+// through two 3-D TMA boxes per tap into a ring of tap stages.  Warp 9 (one elected thread) issues every TMA, warp 8
+// every MMA -- one thread doing both spent 1.5 k clk per tap on its serial chain of barrier waits (~200 clk each) and
+// commits (~200 clk each) against 0.6-0.8 k clk of MMA time; eight worker warps convert, drain finished accumulator
+// chunks (3 taps; 2 for up2) into registers and run the epilogue.  All hand-offs are mbarriers; there is no
+// block-wide barrier inside the loop.
 constexpr int kThHaloW = 10, kThHaloH = 18, kThRows = 180;
 constexpr int kThATile = 23 * 1024;                 // 180 rows x 128 B, rounded up to 1 KB
 constexpr int kThItems = 6;                         // ceil(180 * 8 chunks / 256 worker threads)
 constexpr int kThBStages = 4;
-constexpr int kThThreads = 288;                     // 8 worker warps + 1 control warp
+constexpr int kThThreads = 320;                     // 8 worker warps + MMA warp + TMA producer warp
 
 __host__ __device__ inline int th_smem_bytes(int n) { return 1024 + 2 * 2 * kThATile + kThBStages * 2 * n * 128 + 256; }
 
@@ -365,9 +367,17 @@ conv_halo_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_
   float* __restrict__ out = reinterpret_cast<float*>(p.out);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int tiles_w = p.W / 8, tiles_h = p.H / 16;
-  const int item = blockIdx.x;
-  const int img = item / (tiles_w * tiles_h), rem = item % (tiles_w * tiles_h);
-  const int y0 = (rem / tiles_w) * 16, x0 = (rem % tiles_w) * 8;
+  const int n_items_all = p.n_img * tiles_w * tiles_h;
+  // persistent: this CTA walks items blockIdx.x, blockIdx.x + gridDim.x, ... ; stage / chunk counters run on across
+  // items, so the producer and the MMA thread start the next item while the workers are still in the epilogue
+  const int my_items = (n_items_all - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
+  auto item_origin = [&](int k, int& img, int& y0, int& x0) {      // k-th item of this CTA
+    const int item = blockIdx.x + k * gridDim.x;
+    img = item / (tiles_w * tiles_h);
+    const int rem = item - img * (tiles_w * tiles_h);
+    y0 = (rem / tiles_w) * 16;
+    x0 = (rem % tiles_w) * 8;
+  };
   const int n0 = blockIdx.y * n_tile, g = blockIdx.z;
 
   uint32_t tmem_cols = 32;
@@ -401,41 +411,59 @@ conv_halo_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_
   const int n_taps = p.n_entries_total / p.n_groups;               // the dispatcher guarantees 3..9 taps, all in the halo
   const int chunk_taps = (n_taps % 3 == 0) ? 3 : ((n_taps % 2 == 0) ? 2 : 1);
   const int cph = n_taps / chunk_taps;                             // accumulator chunks per halo slice
-  const int n_hs = (p.Cin + kTxSliceK - 1) / kTxSliceK;            // halo slices
-  const int n_steps = n_hs * n_taps;
+  const int n_hs = (p.Cin + kTxSliceK - 1) / kTxSliceK;            // halo slices per item
+  const int n_gs = my_items * n_hs;                                // halo slices of this CTA (global slice index gs)
 
-  if (warp == 8) {
-    // ================================================= control: every TMA and every MMA of this work item
+  if (warp == 9) {
+    // ================================================= producer: every TMA of this CTA
+    if (elect_one()) {
+      const uint32_t b_tx = static_cast<uint32_t>(b_stage_bytes), a_tx = kThRows * 128;
+      int l_k = 0, l_hs = 0, l_gs = 0;               // next halo slice to load: item index, slice in item, global index
+      auto load_next_a = [&]() {
+        if (l_gs < n_gs) {
+          int img, y0, x0;
+          item_origin(l_k, img, y0, x0);
+          uint64_t* bar = &a_full[l_gs & 1];
+          mbar_expect_tx(bar, a_tx);
+          tma_load_4d(&map_a, bar, a_op + (l_gs & 1) * 2 * kThATile, p.in_choff + l_hs * kTxSliceK, x0 - 1, y0 - 1, img);
+          ++l_gs;
+          if (++l_hs == n_hs) { l_hs = 0; ++l_k; }
+        }
+      };
+      load_next_a();
+      load_next_a();
+      int st = 0, use = 0;                           // tap stage being filled and how often it has been filled before
+      int hs = 0;
+      for (int gs = 0; gs < n_gs; ++gs) {
+        if (gs >= 1 && gs + 1 < n_gs) {              // raw halo of slice gs + 1, once the MMAs of slice gs - 1 have left its stage
+          mbar_wait(&a_empty[(gs + 1) & 1], ((gs - 1) >> 1) & 1);
+          load_next_a();
+        }
+        for (int tap = 0; tap < n_taps; ++tap) {
+          if (use >= 1) mbar_wait(&b_empty[st], (use - 1) & 1);              // the MMAs that last read this stage are done
+          uint64_t* bar = &b_full[st];
+          uint8_t* dst = b_op + st * b_stage_bytes;
+          mbar_expect_tx(bar, b_tx);
+          tma_load_3d(&map_wh, bar, dst, hs * kTxSliceK, n0, s_tap_e[tap]);
+          tma_load_3d(&map_wl, bar, dst + n_tile * 128, hs * kTxSliceK, n0, s_tap_e[tap]);
+          if (++st == SB) { st = 0; ++use; }
+        }
+        if (++hs == n_hs) hs = 0;
+      }
+    }
+    __syncwarp();
+  } else if (warp == 8) {
+    // ================================================= MMA issuer
     if (elect_one()) {
       const uint32_t idesc = make_idesc_tf32(static_cast<uint32_t>(n_tile));
       const uint32_t a_op_addr = smem_u32(a_op), b_op_addr = smem_u32(b_op);
       const uint32_t b_desc_hi = sw128_desc_hi(1024), a_desc_hi = sw128_desc_hi(kThHaloW * 128);
-      const uint32_t b_tx = static_cast<uint32_t>(b_stage_bytes), a_tx = kThRows * 128;
-      auto load_a = [&](int hs) {
-        uint64_t* bar = &a_full[hs & 1];
-        mbar_expect_tx(bar, a_tx);
-        tma_load_4d(&map_a, bar, a_op + (hs & 1) * 2 * kThATile, p.in_choff + hs * kTxSliceK, x0 - 1, y0 - 1, img);
-      };
-      int ld_tap = 0, ld_c0 = 0, ld_left = n_steps;
-      auto load_b = [&](int stage) {                 // next tap in (slice, tap) order -> `stage`
-        uint64_t* bar = &b_full[stage];
-        uint8_t* dst = b_op + stage * b_stage_bytes;
-        mbar_expect_tx(bar, b_tx);
-        tma_load_3d(&map_wh, bar, dst, ld_c0, n0, s_tap_e[ld_tap]);
-        tma_load_3d(&map_wl, bar, dst + n_tile * 128, ld_c0, n0, s_tap_e[ld_tap]);
-        --ld_left;
-        if (++ld_tap == n_taps) { ld_tap = 0; ld_c0 += kTxSliceK; }
-      };
-      load_a(0);
-      if (n_hs > 1) load_a(1);
-      for (int i = 0; i < SB && ld_left > 0; ++i) load_b(i);
       int st = 0, use = 0;                           // tap stage of the current step and how often it has been used
-      int r_st = -1, r_use = 0;                      // stage of the previous step: refilled once its MMAs are done
       int chunk = 0, cpos = 0;
-      for (int hs = 0; hs < n_hs; ++hs) {
-        mbar_wait(&a_ready[hs & 1], (hs >> 1) & 1);
+      for (int gs = 0; gs < n_gs; ++gs) {
+        mbar_wait(&a_ready[gs & 1], (gs >> 1) & 1);
         tc_fence_after();
-        const uint32_t a_hi_addr = a_op_addr + static_cast<uint32_t>((hs & 1) * 2 * kThATile);
+        const uint32_t a_hi_addr = a_op_addr + static_cast<uint32_t>((gs & 1) * 2 * kThATile);
         for (int tap = 0; tap < n_taps; ++tap) {
           if (cpos == 0 && chunk >= 2) {
             mbar_wait(&acc_empty[chunk & 1], ((chunk >> 1) - 1) & 1);       // chunk - 2 has been drained
@@ -456,20 +484,9 @@ conv_halo_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_
             umma_tf32_ss(d, dah + 2 * k, dbl + 2 * k, idesc, 1u);
           }
           umma_commit(&b_empty[st]);
-          if (tap == n_taps - 1) umma_commit(&a_empty[hs & 1]);
+          if (tap == n_taps - 1) umma_commit(&a_empty[gs & 1]);
           if (cpos == chunk_taps - 1) { umma_commit(&acc_full[chunk & 1]); cpos = 0; ++chunk; } else { ++cpos; }
-          // refill the PREVIOUS step's stage: its MMAs ran ahead of the ones just issued, so the wait is short
-          if (r_st >= 0 && ld_left > 0) {
-            mbar_wait(&b_empty[r_st], r_use & 1);
-            load_b(r_st);
-          }
-          r_st = st; r_use = use;
           if (++st == SB) { st = 0; ++use; }
-          // raw halo of the next slice into the other A stage, once the MMAs of slice hs - 1 have left it
-          if (tap == 0 && hs >= 1 && hs + 1 < n_hs) {
-            mbar_wait(&a_empty[(hs + 1) & 1], ((hs - 1) >> 1) & 1);
-            load_a(hs + 1);
-          }
         }
       }
     }
@@ -483,10 +500,10 @@ conv_halo_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_
       const int R = q >> 3, j = q & 7;
       a_sw[i] = static_cast<uint32_t>((R >> 3) * 1024 + (R & 7) * 128 + ((j ^ (R & 7)) << 4));
     }
-    auto convert = [&](int hs) {                     // hi tile (raw, as TMA delivered it) -> hi in place, lo beside it
-      uint8_t* hi_tile = a_op + (hs & 1) * 2 * kThATile;
+    auto convert = [&](int gs) {                     // hi tile (raw, as TMA delivered it) -> hi in place, lo beside it
+      uint8_t* hi_tile = a_op + (gs & 1) * 2 * kThATile;
       uint8_t* lo_tile = hi_tile + kThATile;
-      mbar_wait(&a_full[hs & 1], (hs >> 1) & 1);
+      mbar_wait(&a_full[gs & 1], (gs >> 1) & 1);
 #pragma unroll
       for (int i = 0; i < kThItems; ++i) {
         if (tid + 256 * i < kThRows * 8) {
@@ -498,14 +515,10 @@ conv_halo_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_
         }
       }
       fence_proxy_async_smem();
-      mbar_arrive_warp(&a_ready[hs & 1]);
+      mbar_arrive_warp(&a_ready[gs & 1]);
     };
     const int quad = warp & 3, half = warp >> 2;
     float sum[4][16];
-#pragma unroll
-    for (int a = 0; a < 4; ++a)
-#pragma unroll
-      for (int b = 0; b < 16; ++b) sum[a][b] = 0.f;
     auto drain = [&](int chunk) {                    // acc[chunk & 1] -> sum (round-to-nearest adds)
       mbar_wait(&acc_full[chunk & 1], (chunk >> 1) & 1);
       tc_fence_after();
@@ -524,47 +537,54 @@ conv_halo_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_
       tc_fence_before();
       mbar_arrive_warp(&acc_empty[chunk & 1]);
     };
-    convert(0);
-    int chunk = 0;
-    for (int hs = 0; hs < n_hs; ++hs)
-      for (int ci = 0; ci < cph; ++ci) {
-        drain(chunk++);
-        if (ci == 0 && hs + 1 < n_hs) convert(hs + 1);             // while the tensor pipe works on the rest of slice hs
-      }
-
-    // ---- epilogue: accumulator row m = 8 g + x  ->  output pixel (y0 + g, x0 + x)
-    const int m = quad * 32 + lane;
-    const int oy = y0 + (m >> 3), ox = x0 + (m & 7);
-    const long long opix = p.up2 ? (static_cast<long long>(img) * 2 * p.H + 2 * oy + (g >> 1)) * (2 * p.W) + 2 * ox + (g & 1)
-                                 : (static_cast<long long>(img) * p.H + oy) * p.W + ox;
-    float* orow = out + opix * p.out_ctot + p.out_choff;
     const bool vec_ok = ((p.out_ctot | p.out_choff) & 3) == 0;
+    if (n_gs > 0) convert(0);
+    int chunk = 0, gs = 0;
+    for (int k = 0; k < my_items; ++k) {
 #pragma unroll
-    for (int a = 0; a < 4; ++a) {
-      const int u = half + 2 * a;
-      if (u * 16 >= n_tile) continue;
+      for (int a = 0; a < 4; ++a)
 #pragma unroll
-      for (int j4 = 0; j4 < 4; ++j4) {
-        const int co = n0 + u * 16 + 4 * j4;
-        if (co >= p.Cout) continue;
-        float y[4];
-#pragma unroll
-        for (int t = 0; t < 4; ++t) {
-          const int c = co + t;
-          float val = sum[a][4 * j4 + t];
-          if (c < p.Cout) {
-            val = fmaf(val, p.epi_scale ? p.epi_scale[c] : 1.f, p.epi_shift ? p.epi_shift[c] : 0.f);
-            if (p.residual) val += orow[c];
-            if (p.relu) val = fmaxf(val, 0.f);
-          }
-          y[t] = val;
+        for (int b = 0; b < 16; ++b) sum[a][b] = 0.f;
+      for (int hs = 0; hs < n_hs; ++hs, ++gs)
+        for (int ci = 0; ci < cph; ++ci) {
+          drain(chunk++);
+          if (ci == 0 && gs + 1 < n_gs) convert(gs + 1);             // while the tensor pipe works on the rest of slice gs
         }
-        if (co + 3 < p.Cout && vec_ok) {
-          *reinterpret_cast<float4*>(orow + co) = make_float4(y[0], y[1], y[2], y[3]);
-        } else {
+      // ---- epilogue of item k: accumulator row m = 8 r + x  ->  output pixel (y0 + r, x0 + x)
+      int img, y0, x0;
+      item_origin(k, img, y0, x0);
+      const int m = quad * 32 + lane;
+      const int oy = y0 + (m >> 3), ox = x0 + (m & 7);
+      const long long opix = p.up2 ? (static_cast<long long>(img) * 2 * p.H + 2 * oy + (g >> 1)) * (2 * p.W) + 2 * ox + (g & 1)
+                                   : (static_cast<long long>(img) * p.H + oy) * p.W + ox;
+      float* orow = out + opix * p.out_ctot + p.out_choff;
 #pragma unroll
-          for (int t = 0; t < 4; ++t)
-            if (co + t < p.Cout) orow[co + t] = y[t];
+      for (int a = 0; a < 4; ++a) {
+        const int u = half + 2 * a;
+        if (u * 16 >= n_tile) continue;
+#pragma unroll
+        for (int j4 = 0; j4 < 4; ++j4) {
+          const int co = n0 + u * 16 + 4 * j4;
+          if (co >= p.Cout) continue;
+          float y[4];
+#pragma unroll
+          for (int t = 0; t < 4; ++t) {
+            const int c = co + t;
+            float val = sum[a][4 * j4 + t];
+            if (c < p.Cout) {
+              val = fmaf(val, p.epi_scale ? p.epi_scale[c] : 1.f, p.epi_shift ? p.epi_shift[c] : 0.f);
+              if (p.residual) val += orow[c];
+              if (p.relu) val = fmaxf(val, 0.f);
+            }
+            y[t] = val;
+          }
+          if (co + 3 < p.Cout && vec_ok) {
+            *reinterpret_cast<float4*>(orow + co) = make_float4(y[0], y[1], y[2], y[3]);
+          } else {
+#pragma unroll
+            for (int t = 0; t < 4; ++t)
+              if (co + t < p.Cout) orow[co + t] = y[t];
+          }
         }
       }
     }

@@ -908,7 +908,12 @@ int run_op_f32(dp_model* m, SubPlan* sp, int i, cudaStream_t st) {
     const long long M = (long long)q.n_img * q.OH * q.OW;
     if (m->precision == 2) {   // 3xTF32 on the tensor cores (precise_tc.cuh): N tiles of <= 128 couts, multiples of 16
       if (t.n_tile) {          // 3x3 / up2 without prologue: TMA halo tile per channel slice, taps as descriptor offsets
-        dim3 hgrid((unsigned)(q.n_img * (q.H / 16) * (q.W / 8)), (unsigned)t.n_ntiles, (unsigned)q.n_groups);
+        // persistent CTAs: about one per SM in total, each walking its share of the 16 x 8 regions
+        const int n_items = q.n_img * (q.H / 16) * (q.W / 8), per_x = t.n_ntiles * q.n_groups;
+        int gx = (m->num_sms + per_x - 1) / per_x;
+        if (gx > n_items) gx = n_items;
+        if (getenv("DP_TX_NO_PERSIST")) gx = n_items;
+        dim3 hgrid((unsigned)gx, (unsigned)t.n_ntiles, (unsigned)q.n_groups);
         dp::conv_halo_tf32x3_kernel<<<hgrid, dp::kThThreads, dp::th_smem_bytes(t.n_tile), st>>>(t.a, t.wh, t.wl, q, t.n_tile);
         return;
       }
