@@ -340,22 +340,27 @@ constexpr int kThItems = 6;                         // ceil(180 * 8 chunks / 256
 constexpr int kThBStages = 4;
 constexpr int kThThreads = 320;                     // 8 worker warps + MMA warp + TMA producer warp
 
-__host__ __device__ inline int th_smem_bytes(int n) { return 1024 + 2 * 2 * kThATile + kThBStages * 2 * n * 128 + 256; }
+__host__ __device__ inline int th_smem_bytes(int n, int tps) {
+  return 1024 + 2 * 2 * kThATile + (tps > 1 ? 2 * tps : kThBStages) * 2 * n * 128 + 256;
+}
 
 __global__ void __launch_bounds__(kThThreads, 1)
 conv_halo_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_wh,
-                        const __grid_constant__ CUtensorMap map_wl, const NaiveConvParams p, const int n_tile) {
+                        const __grid_constant__ CUtensorMap map_wl, const NaiveConvParams p, const int n_tile, const int tps) {
   extern __shared__ uint8_t tx_smem_raw[];
   const uint32_t raw_addr = smem_u32(tx_smem_raw);
   uint8_t* smem = tx_smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
-  constexpr int SB = kThBStages;
-  const int b_stage_bytes = 2 * n_tile * 128;
+  // a weight stage holds `tps` taps: 1 (ring of 4 stages), or one accumulator chunk (ring of 2) where that fits -- the
+  // per-stage hand-offs (a barrier wait ~200 clk, a commit ~200 clk in the issuing thread) then happen once per chunk
+  const int SB = tps > 1 ? 2 : kThBStages;
+  const int b_tap_bytes = 2 * n_tile * 128;
+  const int b_stage_bytes = tps * b_tap_bytes;
   uint8_t* a_op = smem;                              // [2 stages][hi | lo]
   uint8_t* b_op = smem + 4 * kThATile;               // [SB stages][hi | lo]
   uint64_t* bars = reinterpret_cast<uint64_t*>(b_op + SB * b_stage_bytes);
-  uint64_t* b_full = bars;                           // [SB] TMA landed
-  uint64_t* b_empty = bars + SB;                     // [SB] MMAs have read the stage
-  uint64_t* a_full = bars + 2 * SB;                  // [2] raw halo slice landed
+  uint64_t* b_full = bars;                           // [<= 4] TMA landed
+  uint64_t* b_empty = bars + kThBStages;             // [<= 4] MMAs have read the stage
+  uint64_t* a_full = bars + 2 * kThBStages;          // [2] raw halo slice landed
   uint64_t* a_ready = a_full + 2;                    // [2] split done (8 worker warps)
   uint64_t* a_empty = a_ready + 2;                   // [2] MMAs have read the stage
   uint64_t* acc_full = a_empty + 2;                  // [2] chunk complete in TMEM
@@ -417,7 +422,7 @@ conv_halo_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_
   if (warp == 9) {
     // ================================================= producer: every TMA of this CTA
     if (elect_one()) {
-      const uint32_t b_tx = static_cast<uint32_t>(b_stage_bytes), a_tx = kThRows * 128;
+      const uint32_t a_tx = kThRows * 128;
       int l_k = 0, l_hs = 0, l_gs = 0;               // next halo slice to load: item index, slice in item, global index
       auto load_next_a = [&]() {
         if (l_gs < n_gs) {
@@ -439,13 +444,15 @@ conv_halo_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_
           mbar_wait(&a_empty[(gs + 1) & 1], ((gs - 1) >> 1) & 1);
           load_next_a();
         }
-        for (int tap = 0; tap < n_taps; ++tap) {
+        for (int tap = 0; tap < n_taps; tap += tps) {
           if (use >= 1) mbar_wait(&b_empty[st], (use - 1) & 1);              // the MMAs that last read this stage are done
           uint64_t* bar = &b_full[st];
           uint8_t* dst = b_op + st * b_stage_bytes;
-          mbar_expect_tx(bar, b_tx);
-          tma_load_3d(&map_wh, bar, dst, hs * kTxSliceK, n0, s_tap_e[tap]);
-          tma_load_3d(&map_wl, bar, dst + n_tile * 128, hs * kTxSliceK, n0, s_tap_e[tap]);
+          mbar_expect_tx(bar, static_cast<uint32_t>(b_stage_bytes));
+          for (int i = 0; i < tps; ++i) {
+            tma_load_3d(&map_wh, bar, dst + i * b_tap_bytes, hs * kTxSliceK, n0, s_tap_e[tap + i]);
+            tma_load_3d(&map_wl, bar, dst + i * b_tap_bytes + n_tile * 128, hs * kTxSliceK, n0, s_tap_e[tap + i]);
+          }
           if (++st == SB) { st = 0; ++use; }
         }
         if (++hs == n_hs) hs = 0;
@@ -458,7 +465,7 @@ conv_halo_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_
       const uint32_t idesc = make_idesc_tf32(static_cast<uint32_t>(n_tile));
       const uint32_t a_op_addr = smem_u32(a_op), b_op_addr = smem_u32(b_op);
       const uint32_t b_desc_hi = sw128_desc_hi(1024), a_desc_hi = sw128_desc_hi(kThHaloW * 128);
-      int st = 0, use = 0;                           // tap stage of the current step and how often it has been used
+      int st = 0, use = 0, spos = 0;                 // weight stage of the current tap, how often it has been used, tap inside it
       int chunk = 0, cpos = 0;
       for (int gs = 0; gs < n_gs; ++gs) {
         mbar_wait(&a_ready[gs & 1], (gs >> 1) & 1);
@@ -469,10 +476,10 @@ conv_halo_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_
             mbar_wait(&acc_empty[chunk & 1], ((chunk >> 1) - 1) & 1);       // chunk - 2 has been drained
             tc_fence_after();
           }
-          mbar_wait(&b_full[st], use & 1);
+          if (spos == 0) mbar_wait(&b_full[st], use & 1);
           const uint32_t d = tmem_base + static_cast<uint32_t>((chunk & 1) * n_tile);
           const uint32_t ta = a_hi_addr + s_tap_a[tap];
-          const uint32_t tb = b_op_addr + static_cast<uint32_t>(st * b_stage_bytes);
+          const uint32_t tb = b_op_addr + static_cast<uint32_t>(st * b_stage_bytes + spos * b_tap_bytes);
           const uint64_t dah = (static_cast<uint64_t>(a_desc_hi) << 32) | sw128_desc_lo(ta);
           const uint64_t dal = (static_cast<uint64_t>(a_desc_hi) << 32) | sw128_desc_lo(ta + kThATile);
           const uint64_t dbh = (static_cast<uint64_t>(b_desc_hi) << 32) | sw128_desc_lo(tb);
@@ -483,10 +490,13 @@ conv_halo_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_
             umma_tf32_ss(d, dal + 2 * k, dbh + 2 * k, idesc, 1u);
             umma_tf32_ss(d, dah + 2 * k, dbl + 2 * k, idesc, 1u);
           }
-          umma_commit(&b_empty[st]);
+          if (++spos == tps) {
+            umma_commit(&b_empty[st]);
+            spos = 0;
+            if (++st == SB) { st = 0; ++use; }
+          }
           if (tap == n_taps - 1) umma_commit(&a_empty[gs & 1]);
           if (cpos == chunk_taps - 1) { umma_commit(&acc_full[chunk & 1]); cpos = 0; ++chunk; } else { ++cpos; }
-          if (++st == SB) { st = 0; ++use; }
         }
       }
     }

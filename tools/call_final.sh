@@ -1,15 +1,34 @@
 #!/usr/bin/env bash
-# Round-end evidence on one B200: full GPU suite, smoke, bench (both arms), launch list + one ncu --set full capture.
+# Round-end evidence on one B200: full GPU suite, smoke, bench (both arms, precision modes, other ensemble members),
+# config 5, lanes timeline, ncu launch list + one ncu --set full capture.   Usage (on the box): tools/call_final.sh <tag>
 set -u
 TAG=${1:-r2final}; OUT=gpurun_out/$TAG; mkdir -p "$OUT"
-timeout 900 python -m pytest tests -m gpu -q -s > "$OUT/pytest_gpu.log" 2>&1; echo "pytest -m gpu rc=$?" | tee -a "$OUT/summary.txt"
+timeout 1200 python -m pytest tests -m gpu -q -s > "$OUT/pytest_gpu.log" 2>&1; echo "pytest -m gpu rc=$?" | tee -a "$OUT/summary.txt"
 grep -E "passed|failed|FAILED" "$OUT/pytest_gpu.log" | tail -5
-python -c "import __graft_entry__ as g; g.smoke()" > "$OUT/smoke.log" 2>&1; echo "smoke rc=$?" | tee -a "$OUT/summary.txt"; tail -2 "$OUT/smoke.log"
+python -c "import __graft_entry__ as g; g.smoke()" > "$OUT/smoke.log" 2>&1; echo "smoke rc=$?" | tee -a "$OUT/summary.txt"; tail -3 "$OUT/smoke.log"
 timeout 600 python bench.py --dump-ops "$OUT/ops.csv" > "$OUT/bench.json" 2> "$OUT/bench.err"; echo "bench rc=$?" | tee -a "$OUT/summary.txt"
 timeout 300 python bench.py --impl reference --steps 3 --warmup 1 > "$OUT/bench_reference.json" 2>> "$OUT/bench.err"; echo "bench ref rc=$?" | tee -a "$OUT/summary.txt"
-timeout 300 python bench.py --precision fp32 --steps 10 --no-slide --no-parity --no-cpu-baseline > "$OUT/bench_fp32.json" 2>> "$OUT/bench.err"; echo "bench fp32 rc=$?" | tee -a "$OUT/summary.txt"
+for P in fp32 tf32x3; do
+  timeout 300 python bench.py --precision $P --steps 10 --no-slide --no-parity --no-cpu-baseline > "$OUT/bench_$P.json" 2>> "$OUT/bench.err"; echo "bench $P rc=$?" | tee -a "$OUT/summary.txt"
+done
+for M in inception deeplabv3; do
+  timeout 300 python bench.py --model $M --steps 60 --no-slide --no-parity --no-cpu-baseline > "$OUT/bench_$M.json" 2>> "$OUT/bench.err"; echo "bench $M rc=$?" | tee -a "$OUT/summary.txt"
+done
+timeout 400 python bench.py --workload config5 --slide 8192 --steps 2 > "$OUT/config5_n1.json" 2>> "$OUT/bench.err"; echo "config5 rc=$?" | tee -a "$OUT/summary.txt"
+timeout 100 python tools/lanes_timeline.py 3 > "$OUT/lanes_timeline.txt" 2>&1
 timeout 100 python tests/stamp_ops.py > "$OUT/timeline.txt" 2>&1
-timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file "$OUT/launches.csv" python bench.py --steps 2 --warmup 3 --no-slide --no-parity --no-cpu-baseline > "$OUT/bench_under_ncu.log" 2>&1; echo "ncu launches rc=$?" | tee -a "$OUT/summary.txt"
-timeout 400 ncu --set full --clock-control none --import-source on -k regex:'dense_block_kernel|conv_tc_kernel' --launch-skip 32 --launch-count 6 -o "$OUT/top_kernels" python tools/one_step.py > "$OUT/ncu_full.log" 2>&1; echo "ncu full rc=$?" | tee -a "$OUT/summary.txt"
-ncu -i "$OUT/top_kernels.ncu-rep" --page raw --csv > "$OUT/top_kernels_raw.csv" 2>/dev/null
-cut -c1-400 "$OUT/bench.json"; tail -3 "$OUT/bench.err"
+timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file "$OUT/launches.csv" python bench.py --steps 2 --warmup 3 --lanes 1 --no-slide --no-parity --no-cpu-baseline > "$OUT/bench_under_ncu.log" 2>&1; echo "ncu launches rc=$?" | tee -a "$OUT/summary.txt"
+timeout 400 ncu --set full --clock-control none --import-source on -k regex:'conv_halo_tf32x3_kernel|conv_tf32x3_kernel' --launch-skip 40 --launch-count 8 -o "$OUT/tf32x3_kernels" python tools/tf32x3_bringup.py dense > "$OUT/ncu_full.log" 2>&1; echo "ncu full rc=$?" | tee -a "$OUT/summary.txt"
+ncu -i "$OUT/tf32x3_kernels.ncu-rep" --page raw --csv > "$OUT/tf32x3_kernels_raw.csv" 2>/dev/null
+rm -f "$OUT/tf32x3_kernels.ncu-rep"
+python - <<PY
+import json
+for f in ("bench", "bench_fp32", "bench_tf32x3", "bench_inception", "bench_deeplabv3", "config5_n1", "bench_reference"):
+    try:
+        d = json.loads(open("$OUT/%s.json" % f).read().strip().splitlines()[-1])
+        print(f, round(d["value"], 1), "e2e", d.get("e2e", {}).get("value"), "frac", (d.get("roofline") or {}).get("frac"),
+              "single", (d.get("single_stream") or {}).get("value"), "slide", (d.get("slide") or {}).get("tiles_per_s"))
+    except Exception as e:
+        print(f, "no line", e)
+PY
+tail -3 "$OUT/bench.err"

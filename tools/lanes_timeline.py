@@ -1,6 +1,6 @@
 """Evidence for engine.ForwardLanes: %globaltimer entry / exit of every tensor-core kernel of three batch-32 forwards
-issued on three lanes (CUDA-graph replays captured with the stamps on), against forwards on one stream.  Prints how much of
-the wall time has kernels of 1, 2 and 3 different batches running at the same time and which ops overlap.
+issued together on three lanes (CUDA-graph replays captured with the stamps on), against one forward alone.  Prints how
+much of the burst's wall time has kernels of 1, 2 and 3 different batches running at the same time and which ops overlap.
     python tools/lanes_timeline.py [lanes=3] > profiles/r2_lanes_timeline.txt"""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -22,11 +22,16 @@ def run(lanes, rounds):
     for mm in models:
         mm.set_option("stamp", 1)
     pool.begin()
-    for k in range(rounds * lanes):
+    for k in range(rounds * lanes):                   # warm-up (graph capture with the stamps on, clocks, L2)
         pool.forward("m", slide, coords[k % 64], 0, 0, out=outs[k % lanes])
     pool.join()
     torch.cuda.synchronize()
-    st = [mm.read_stamps() for mm in models]          # last forward of every lane
+    pool.begin()
+    for k in range(lanes):                            # the burst that is analysed: ONE forward per lane, all stamped
+        pool.forward("m", slide, coords[(7 + k) % 64], 0, 0, out=outs[k])
+    pool.join()
+    torch.cuda.synchronize()
+    st = [mm.read_stamps() for mm in models]
     m.close()
     return st
 
@@ -58,5 +63,5 @@ def report(st, label):
         print(f"      overlap {' + '.join(names):40s} {t / 1e3:7.1f} us")
 
 
-report(run(1, 6), "1 lane (last forward of the stream)")
-report(run(L, 6), f"{L} lanes (last forward of every lane)")
+report(run(1, 6), "1 lane: one forward alone")
+report(run(L, 6), f"{L} lanes: a burst of {L} forwards issued together, one per lane (includes the ramp-up and the drain of the burst)")

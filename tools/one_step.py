@@ -5,7 +5,8 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from digipathai_b200.engine import TileModel, kernel_launch_count
 from digipathai_b200.models.densenet import densenet121_unet_program, init_densenet_weights
-m = TileModel(densenet121_unet_program(init_densenet_weights(0), 256), device=0, max_batch=32)
+precision = sys.argv[1] if len(sys.argv) > 1 else "fp16"        # fp16 | fp32 | tf32x3
+m = TileModel(densenet121_unet_program(init_densenet_weights(0), 256, precision=precision), device=0, max_batch=32)
 m.set_option("use_graph", 0)
 g = torch.Generator(device="cuda"); g.manual_seed(1)
 slide = torch.randint(0, 256, (4096, 4096, 3), dtype=torch.uint8, device="cuda", generator=g)
