@@ -1880,7 +1880,13 @@ LatGeom lat_geom(int D, int N) {
   return g;
 }
 size_t lat_pixel_bytes(int N) { return (size_t)N * (8 + 4 + 4 + 4 + 8 + 8 + 8) + 8 * 256; }
-const int kCrfChunk = 8;
+// tiles per pass through the lattice kernels: every launch then covers chunk x 65 536 pixels / lattice points (the
+// kernels are small and latency bound: ~200 launches per chunk), ~75 MB of workspace per tile of the chunk
+static int crf_chunk() {
+  static const int v = [] { const char* e = getenv("DP_CRF_CHUNK"); const int c = e ? atoi(e) : 32; return c < 1 ? 1 : (c > 256 ? 256 : c); }();
+  return v;
+}
+#define kCrfChunk crf_chunk()
 }  // namespace
 
 size_t dp_crf_lattice_workspace_bytes(int n_tiles, int h, int w) {
