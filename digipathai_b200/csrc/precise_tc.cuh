@@ -604,6 +604,224 @@ conv_halo_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_
   if (warp == 0) tmem_dealloc(tmem_base, tmem_cols);
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// 1x1 variant (stride 1): the dense layers' bottleneck convs with their BN-ReLU prologue, the transition convs and the
+// pointwise convs of DeepLab / Inception.  The activation tensor is the flat [pixels, C] matrix: a 2-D TMA box of
+// 128 pixels x 32 channels lands in the swizzled `hi` tile of a ring stage together with the pre-split weight boxes of
+// the slice; the worker warps apply the prologue and split in place, the MMA warp issues 12 MMAs per slice, accumulator
+// chunks are two slices.  Same roles and barriers as the halo kernel; CTAs are persistent over 128-pixel tiles.
+constexpr int kT1Stages = 3;
+constexpr int kT1Lag = 2;                           // worker drains run this many slices behind their conversions
+
+__host__ __device__ inline int t1_stage_bytes(int n) { return 2 * kTxATile + 2 * n * 128; }
+__host__ __device__ inline int t1_smem_bytes(int n) { return 1024 + kT1Stages * t1_stage_bytes(n) + 256; }
+
+__global__ void __launch_bounds__(kThThreads, 1)
+conv_1x1_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_wh,
+                       const __grid_constant__ CUtensorMap map_wl, const NaiveConvParams p, const int n_tile) {
+  extern __shared__ uint8_t tx_smem_raw[];
+  const uint32_t raw_addr = smem_u32(tx_smem_raw);
+  uint8_t* smem = tx_smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
+  constexpr int S = kT1Stages;
+  const int stage_bytes = t1_stage_bytes(n_tile);    // [A hi | A lo | B hi | B lo]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S * stage_bytes);
+  uint64_t* raw_full = bars;                         // [S] TMA landed (activations + weights)
+  uint64_t* ready = bars + S;                        // [S] split done (8 worker warps)
+  uint64_t* empty = bars + 2 * S;                    // [S] MMAs have read the stage
+  uint64_t* acc_full = bars + 3 * S;                 // [2]
+  uint64_t* acc_empty = acc_full + 2;                // [2] (8 worker warps)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+
+  float* __restrict__ out = reinterpret_cast<float*>(p.out);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const long long M = static_cast<long long>(p.n_img) * p.H * p.W;
+  const int n_mtiles = static_cast<int>((M + 127) / 128);
+  const int my_tiles = (n_mtiles - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
+  const int n0 = blockIdx.y * n_tile;
+  const int n_s = (p.Cin + kTxSliceK - 1) / kTxSliceK;             // slices per tile
+  const int n_gs = my_tiles * n_s;
+
+  uint32_t tmem_cols = 32;
+  while (tmem_cols < static_cast<uint32_t>(2 * n_tile)) tmem_cols <<= 1;
+  if (warp == 0) {
+    tmem_alloc(tmem_slot, tmem_cols);
+    tmem_relinquish();
+  }
+  if (tid == 256) {
+    for (int i = 0; i < S; ++i) { mbar_init(&raw_full[i], 1); mbar_init(&ready[i], 8); mbar_init(&empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 8); }
+    fence_barrier_init();
+    tma_prefetch_desc(&map_a);
+    tma_prefetch_desc(&map_wh);
+    tma_prefetch_desc(&map_wl);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 9) {
+    // ================================================= producer
+    if (elect_one()) {
+      const uint32_t tx = static_cast<uint32_t>(kTxATile + 2 * n_tile * 128);
+      int st = 0, use = 0, hs = 0, k = 0;
+      for (int gs = 0; gs < n_gs; ++gs) {
+        if (use >= 1) mbar_wait(&empty[st], (use - 1) & 1);
+        uint8_t* base = smem + st * stage_bytes;
+        const int m0 = (static_cast<int>(blockIdx.x) + k * static_cast<int>(gridDim.x)) * 128;
+        mbar_expect_tx(&raw_full[st], tx);
+        tma_load_2d(&map_a, &raw_full[st], base, p.in_choff + hs * kTxSliceK, m0);
+        tma_load_3d(&map_wh, &raw_full[st], base + 2 * kTxATile, hs * kTxSliceK, n0, 0);
+        tma_load_3d(&map_wl, &raw_full[st], base + 2 * kTxATile + n_tile * 128, hs * kTxSliceK, n0, 0);
+        if (++st == S) { st = 0; ++use; }
+        if (++hs == n_s) { hs = 0; ++k; }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 8) {
+    // ================================================= MMA issuer
+    if (elect_one()) {
+      const uint32_t idesc = make_idesc_tf32(static_cast<uint32_t>(n_tile));
+      const uint32_t smem_addr = smem_u32(smem), desc_hi = sw128_desc_hi(1024);
+      int st = 0, use = 0, hs = 0, chunk = 0;
+      for (int gs = 0; gs < n_gs; ++gs) {
+        const bool chunk_start = (hs & 1) == 0, chunk_end = (hs & 1) == 1 || hs == n_s - 1;
+        if (chunk_start && chunk >= 2) {
+          mbar_wait(&acc_empty[chunk & 1], ((chunk >> 1) - 1) & 1);
+          tc_fence_after();
+        }
+        mbar_wait(&ready[st], use & 1);
+        tc_fence_after();
+        const uint32_t d = tmem_base + static_cast<uint32_t>((chunk & 1) * n_tile);
+        const uint32_t ta = smem_addr + static_cast<uint32_t>(st * stage_bytes);
+        const uint64_t dah = (static_cast<uint64_t>(desc_hi) << 32) | sw128_desc_lo(ta);
+        const uint64_t dal = (static_cast<uint64_t>(desc_hi) << 32) | sw128_desc_lo(ta + kTxATile);
+        const uint64_t dbh = (static_cast<uint64_t>(desc_hi) << 32) | sw128_desc_lo(ta + 2 * kTxATile);
+        const uint64_t dbl = (static_cast<uint64_t>(desc_hi) << 32) | sw128_desc_lo(ta + 2 * kTxATile + n_tile * 128);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          umma_tf32_ss(d, dah + 2 * k, dbh + 2 * k, idesc, (chunk_start && k == 0) ? 0u : 1u);
+          umma_tf32_ss(d, dal + 2 * k, dbh + 2 * k, idesc, 1u);
+          umma_tf32_ss(d, dah + 2 * k, dbl + 2 * k, idesc, 1u);
+        }
+        umma_commit(&empty[st]);
+        if (chunk_end) { umma_commit(&acc_full[chunk & 1]); ++chunk; }
+        if (++st == S) { st = 0; ++use; }
+        if (++hs == n_s) hs = 0;
+      }
+    }
+    __syncwarp();
+  } else {
+    // ================================================= workers: prologue + split, drain, epilogue
+    // thread -> 16-byte chunk j (4 channels) of rows (tid >> 3) + 32 i: the prologue terms depend on j only
+    const int j = tid & 7, r0 = tid >> 3;
+    const uint32_t sw_row = static_cast<uint32_t>((r0 >> 3) * 1024 + (r0 & 7) * 128 + ((j ^ (r0 & 7)) << 4));
+    const int quad = warp & 3, half = warp >> 2;
+    const bool vec_ok = ((p.out_ctot | p.out_choff) & 3) == 0;
+    float sum[4][16];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+      for (int b = 0; b < 16; ++b) sum[a][b] = 0.f;
+    auto drain = [&](int chunk) {
+      mbar_wait(&acc_full[chunk & 1], (chunk >> 1) & 1);
+      tc_fence_after();
+      const uint32_t t0 = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + static_cast<uint32_t>((chunk & 1) * n_tile);
+#pragma unroll
+      for (int a = 0; a < 4; ++a) {
+        const int u = half + 2 * a;
+        if (u * 16 < n_tile) {
+          uint32_t v[16];
+          tmem_ld16(t0 + static_cast<uint32_t>(u * 16), v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int b = 0; b < 16; ++b) sum[a][b] += __uint_as_float(v[b]);
+        }
+      }
+      tc_fence_before();
+      mbar_arrive_warp(&acc_empty[chunk & 1]);
+    };
+    auto epilogue = [&](int k) {                     // k-th tile of this CTA; clears the sums
+      const long long mm = (static_cast<long long>(blockIdx.x) + static_cast<long long>(k) * gridDim.x) * 128 + quad * 32 + lane;
+      float* orow = out + mm * p.out_ctot + p.out_choff;
+#pragma unroll
+      for (int a = 0; a < 4; ++a) {
+        const int u = half + 2 * a;
+        if (u * 16 < n_tile && mm < M) {
+#pragma unroll
+          for (int j4 = 0; j4 < 4; ++j4) {
+            const int co = n0 + u * 16 + 4 * j4;
+            if (co >= p.Cout) continue;
+            float y[4];
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+              const int c = co + t;
+              float val = sum[a][4 * j4 + t];
+              if (c < p.Cout) {
+                val = fmaf(val, p.epi_scale ? p.epi_scale[c] : 1.f, p.epi_shift ? p.epi_shift[c] : 0.f);
+                if (p.residual) val += orow[c];
+                if (p.relu) val = fmaxf(val, 0.f);
+              }
+              y[t] = val;
+            }
+            if (co + 3 < p.Cout && vec_ok) {
+              *reinterpret_cast<float4*>(orow + co) = make_float4(y[0], y[1], y[2], y[3]);
+            } else {
+#pragma unroll
+              for (int t = 0; t < 4; ++t)
+                if (co + t < p.Cout) orow[co + t] = y[t];
+            }
+          }
+        }
+#pragma unroll
+        for (int b = 0; b < 16; ++b) sum[a][b] = 0.f;
+      }
+    };
+    // slices are converted in order; the slice `kT1Lag` behind is "retired": its chunk drained, its tile written
+    int st = 0, use = 0, hs = 0;                     // conversion cursor
+    int r_hs = 0, r_k = 0, r_chunk = 0, retired = 0; // retire cursor
+    auto retire_one = [&]() {
+      const bool chunk_end = (r_hs & 1) == 1 || r_hs == n_s - 1;
+      if (chunk_end) drain(r_chunk++);
+      if (++r_hs == n_s) { r_hs = 0; epilogue(r_k++); }
+      ++retired;
+    };
+    for (int gs = 0; gs < n_gs; ++gs) {
+      uint8_t* hi_tile = smem + st * stage_bytes;
+      uint8_t* lo_tile = hi_tile + kTxATile;
+      const int c = hs * kTxSliceK + 4 * j;
+      float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (p.pro_mode && c < p.Cin) {
+        sc = *reinterpret_cast<const float4*>(p.pro_scale + c);
+        sh = *reinterpret_cast<const float4*>(p.pro_shift + c);
+      }
+      mbar_wait(&raw_full[st], use & 1);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const uint32_t off = static_cast<uint32_t>(i * 4 * 1024) + sw_row;
+        float4 v = *reinterpret_cast<const float4*>(hi_tile + off);
+        if (p.pro_mode) {
+          v.x = fmaf(v.x, sc.x, sh.x); v.y = fmaf(v.y, sc.y, sh.y); v.z = fmaf(v.z, sc.z, sh.z); v.w = fmaf(v.w, sc.w, sh.w);
+          if (p.pro_mode == 2) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+        }
+        float4 h, l;
+        tf32_split(v.x, h.x, l.x); tf32_split(v.y, h.y, l.y); tf32_split(v.z, h.z, l.z); tf32_split(v.w, h.w, l.w);
+        *reinterpret_cast<float4*>(hi_tile + off) = h;
+        *reinterpret_cast<float4*>(lo_tile + off) = l;
+      }
+      fence_proxy_async_smem();
+      mbar_arrive_warp(&ready[st]);
+      if (++st == S) { st = 0; ++use; }
+      if (++hs == n_s) hs = 0;
+      if (gs + 1 - retired > kT1Lag) retire_one();
+    }
+    while (retired < n_gs) retire_one();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_base, tmem_cols);
+}
+
 // data section -> hi / lo copies (run once at model creation for precision 2): hi and lo both rounded to TF32
 __global__ void tf32_presplit_kernel(const float* __restrict__ x, float* __restrict__ hi, float* __restrict__ lo, size_t n) {
   for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n; i += static_cast<size_t>(gridDim.x) * blockDim.x) {

@@ -134,7 +134,7 @@ struct Launch {
   dp::DenseLayerParams dl;
   dp::NaiveConvParams np2;  // debug path: the 3x3 half (np holds the 1x1 half)
   // 3xTF32 mode (precision 2): TMA maps of the halo kernel for np (tx[0]) / np2 (tx[1]); n_tile 0 = generic kernel
-  struct TxPlan { CUtensorMap a, wh, wl; int n_tile = 0, n_ntiles = 0; } tx[2];
+  struct TxPlan { CUtensorMap a, wh, wl; int n_tile = 0, n_ntiles = 0, kind = 0; } tx[2];   // kind 1: halo kernel, 2: 1x1 kernel
   // persistent dense-block kernel (dense_block.cuh): set on the FIRST layer of a run of dense layers on small maps;
   // the other layers of the run carry block_member and launch nothing when the whole program is executed
   int block_len = 0;
@@ -287,21 +287,30 @@ void fill_entries(int kind, int H, int W, int kh, int kw, int stride, dp::TapEnt
 int plan_tx(dp_model* m, const dp::NaiveConvParams& q, Launch::TxPlan& t) {
   t.n_ntiles = (q.Cout + dp::kTxMaxN - 1) / dp::kTxMaxN;
   const int n_tile = round_up((q.Cout + t.n_ntiles - 1) / t.n_ntiles, 16);
-  t.n_tile = 0;
+  t.n_tile = 0; t.kind = 0;
   const int epg = q.n_groups ? q.n_entries_total / q.n_groups : 0;
   bool halo = m->precision == 2 && q.stride == 1 && !q.pro_mode && !q.residual && q.H % 16 == 0 && q.W % 8 == 0 &&
               q.Cin % 4 == 0 && (q.up2 || (q.OH == q.H && q.OW == q.W)) && epg >= 3 && epg <= 9 && m->data_hi_dev &&
               !getenv("DP_TX_NO_HALO");
   for (int e = 0; e < q.n_entries_total && halo; ++e)
     halo = q.entries[e].dy >= -1 && q.entries[e].dy <= 1 && q.entries[e].dx >= -1 && q.entries[e].dx <= 1;
-  if (!halo) return 0;
-  {
+  const bool one = m->precision == 2 && !halo && q.n_entries_total == 1 && q.n_groups == 1 && q.stride == 1 && !q.up2 &&
+                   q.entries[0].dy == 0 && q.entries[0].dx == 0 && q.OH == q.H && q.OW == q.W && q.Cin % 4 == 0 &&
+                   m->data_hi_dev && !getenv("DP_TX_NO_1X1");
+  if (!halo && !one) return 0;
+  if (halo) {
     uint64_t dims[4] = {(uint64_t)(q.in_choff + q.Cin), (uint64_t)q.W, (uint64_t)q.H, (uint64_t)q.n_img};
     const uint64_t cs = (uint64_t)q.in_ctot * 4;
     uint64_t str[3] = {cs, cs * q.W, cs * q.W * q.H};
     uint32_t box[4] = {32, (uint32_t)dp::kThHaloW, (uint32_t)dp::kThHaloH, 1};
     if (make_map(&t.a, q.in, 4, dims, str, box, 1, CU_TENSOR_MAP_DATA_TYPE_FLOAT32)) return 1;
+  } else {   // flat [pixels, C] view
+    uint64_t dims[2] = {(uint64_t)(q.in_choff + q.Cin), (uint64_t)q.n_img * q.H * q.W};
+    uint64_t str[1] = {(uint64_t)q.in_ctot * 4};
+    uint32_t box[2] = {32, 128};
+    if (make_map(&t.a, q.in, 2, dims, str, box, 1, CU_TENSOR_MAP_DATA_TYPE_FLOAT32)) return 1;
   }
+  t.kind = halo ? 1 : 2;
   const size_t woff = reinterpret_cast<const uint8_t*>(q.w) - m->data_dev;
   uint64_t dims[3] = {(uint64_t)q.Cin, (uint64_t)q.Cout, (uint64_t)q.n_entries_total};
   uint64_t str[2] = {(uint64_t)q.Cin * 4, (uint64_t)q.Cin * q.Cout * 4};
@@ -907,6 +916,14 @@ int run_op_f32(dp_model* m, SubPlan* sp, int i, cudaStream_t st) {
   auto conv = [&](const dp::NaiveConvParams& q, const Launch::TxPlan& t) {
     const long long M = (long long)q.n_img * q.OH * q.OW;
     if (m->precision == 2) {   // 3xTF32 on the tensor cores (precise_tc.cuh): N tiles of <= 128 couts, multiples of 16
+      if (t.n_tile && t.kind == 2) {   // 1x1, stride 1: flat [pixels, C] TMA tiles, prologue + split in place
+        const int n_mtiles = (int)((M + 127) / 128);
+        int gx = (m->num_sms + t.n_ntiles - 1) / t.n_ntiles;
+        if (gx > n_mtiles) gx = n_mtiles;
+        dim3 ogrid((unsigned)gx, (unsigned)t.n_ntiles, 1);
+        dp::conv_1x1_tf32x3_kernel<<<ogrid, dp::kThThreads, dp::t1_smem_bytes(t.n_tile), st>>>(t.a, t.wh, t.wl, q, t.n_tile);
+        return;
+      }
       if (t.n_tile) {          // 3x3 / up2 without prologue: TMA halo tile per channel slice, taps as descriptor offsets
         // persistent CTAs: about one per SM in total, each walking its share of the 16 x 8 regions
         const int n_items = q.n_img * (q.H / 16) * (q.W / 8), per_x = t.n_ntiles * q.n_groups;
@@ -1349,6 +1366,7 @@ static int alloc_lane_state(dp_model* m) {
     cudaError_t e6 = cudaFuncSetAttribute(dp::dense_layer_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
     if (e6 == cudaSuccess) e6 = cudaFuncSetAttribute(dp::conv_tf32x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
     if (e6 == cudaSuccess) e6 = cudaFuncSetAttribute(dp::conv_halo_tf32x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
+    if (e6 == cudaSuccess) e6 = cudaFuncSetAttribute(dp::conv_1x1_tf32x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
     if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess || e4 != cudaSuccess || e5 != cudaSuccess || e6 != cudaSuccess || e7 != cudaSuccess) {
       return fail("cudaFuncSetAttribute(MaxDynamicSharedMemorySize) failed: %s", cudaGetErrorString(cudaGetLastError()));
     }
