@@ -18,9 +18,9 @@ timeout 400 python bench.py --workload config5 --slide 8192 --steps 2 > "$OUT/co
 timeout 100 python tools/lanes_timeline.py 3 > "$OUT/lanes_timeline.txt" 2>&1
 timeout 100 python tests/stamp_ops.py > "$OUT/timeline.txt" 2>&1
 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file "$OUT/launches.csv" python bench.py --steps 2 --warmup 3 --lanes 1 --no-slide --no-parity --no-cpu-baseline > "$OUT/bench_under_ncu.log" 2>&1; echo "ncu launches rc=$?" | tee -a "$OUT/summary.txt"
-timeout 400 ncu --set full --clock-control none --import-source on -k regex:'conv_halo_tf32x3_kernel|conv_tf32x3_kernel' --launch-skip 40 --launch-count 8 -o "$OUT/tf32x3_kernels" python tools/tf32x3_bringup.py dense > "$OUT/ncu_full.log" 2>&1; echo "ncu full rc=$?" | tee -a "$OUT/summary.txt"
-ncu -i "$OUT/tf32x3_kernels.ncu-rep" --page raw --csv > "$OUT/tf32x3_kernels_raw.csv" 2>/dev/null
-rm -f "$OUT/tf32x3_kernels.ncu-rep"
+true
+true
+true
 python - <<PY
 import json
 for f in ("bench", "bench_fp32", "bench_tf32x3", "bench_inception", "bench_deeplabv3", "config5_n1", "bench_reference"):
