@@ -25,6 +25,7 @@
 #include "dense_block.cuh"
 #include "precise.cuh"
 #include "precise_tc.cuh"
+#include "jpeg_enc.cuh"
 #include "tissue.cuh"
 
 namespace {
@@ -2074,6 +2075,53 @@ int dp_crf_tiles(const uint8_t* rgb, const float* p1, int n_tiles, int h, int w,
     dp::crf_update_kernel<<<ew, 256, 0, st>>>(n_tiles, npix, 0.f, 0.f, ws, labels, q1_out);
     LAUNCH_OK();
   }
+  return 0;
+}
+
+// ---------------------------------------------------------------- JPEG tile encoder of the pyramidal writer (jpeg_enc.cuh)
+size_t dp_jpeg_encode_workspace_bytes(int n_tiles, int scratch_bytes_per_tile) {
+  if (n_tiles < 1 || scratch_bytes_per_tile < 1024) return 0;
+  return 4096 + (size_t)n_tiles * (size_t)((scratch_bytes_per_tile + 3) / 4 * 4);
+}
+
+int dp_jpeg_encode_gray_tiles(const uint8_t* plane, int64_t rows, int64_t cols, int tile0, int n_tiles, const void* tables_host,
+                              size_t tables_bytes, void* workspace, size_t workspace_bytes, int scratch_bytes_per_tile,
+                              uint8_t* out, int out_cap, int32_t* sizes, int32_t* flags, void* stream) {
+  if (!plane || !tables_host || !workspace || !out || !sizes || !flags) return fail("null argument");
+  if (rows < 1 || cols < 1 || rows > (1 << 30) || cols > (1 << 30)) return fail("bad plane extent");
+  if (tables_bytes != sizeof(dp::JpegTables)) return fail("JPEG tables: expected %zu bytes, got %zu", sizeof(dp::JpegTables), tables_bytes);
+  const int tiles_x = (int)((cols + dp::kJpTile - 1) / dp::kJpTile), tiles_y = (int)((rows + dp::kJpTile - 1) / dp::kJpTile);
+  if (n_tiles < 1 || tile0 < 0 || (long long)tile0 + n_tiles > (long long)tiles_x * tiles_y) return fail("tile range outside the plane");
+  if (out_cap < 1024) return fail("out_cap too small");
+  if (workspace_bytes < dp_jpeg_encode_workspace_bytes(n_tiles, scratch_bytes_per_tile) || scratch_bytes_per_tile < 1024)
+    return fail("JPEG workspace too small: need %zu bytes", dp_jpeg_encode_workspace_bytes(n_tiles, scratch_bytes_per_tile));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  static std::once_flag once;
+  static cudaError_t attr_err = cudaSuccess;
+  const int smem = dp::kJpBlocks * 64 * 2 + dp::kJpTile * dp::kJpTile;
+  std::call_once(once, [&] { attr_err = cudaFuncSetAttribute(dp::jpeg_encode_tiles_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); });
+  if (attr_err != cudaSuccess) return fail("cudaFuncSetAttribute(jpeg encoder): %s", cudaGetErrorString(attr_err));
+  uint8_t* ws = static_cast<uint8_t*>(workspace);
+  const int scratch_words = (scratch_bytes_per_tile + 3) / 4;
+  // the tables are 1.3 KB: a synchronous copy keeps the caller's host buffer free to go away after the call
+  CU_OK(cudaStreamSynchronize(st));
+  CU_OK(cudaMemcpy(ws, tables_host, sizeof(dp::JpegTables), cudaMemcpyHostToDevice));
+  CU_OK(cudaMemsetAsync(ws + 4096, 0, (size_t)n_tiles * scratch_words * 4, st));
+  dp::jpeg_encode_tiles_kernel<<<n_tiles, dp::kJpThreads, smem, st>>>(plane, (int)rows, (int)cols, tiles_x, tile0, n_tiles,
+                                                                     reinterpret_cast<const dp::JpegTables*>(ws),
+                                                                     reinterpret_cast<uint32_t*>(ws + 4096), scratch_words, out,
+                                                                     out_cap, sizes, flags);
+  LAUNCH_OK();
+  return 0;
+}
+
+int dp_jpeg_compact(const uint8_t* in, int cap, const int32_t* sizes, const int64_t* offsets, uint8_t* out, int n_tiles,
+                    void* stream) {
+  if (!in || !sizes || !offsets || !out || n_tiles < 1) return fail("null argument");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  dp::jpeg_compact_kernel<<<n_tiles, 256, 0, st>>>(
+      in, cap, sizes, reinterpret_cast<const long long*>(offsets), out, n_tiles);
+  LAUNCH_OK();
   return 0;
 }
 

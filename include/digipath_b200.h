@@ -112,6 +112,26 @@ int dp_finalize(float* mean, float* var, uint8_t* count, int64_t n, float thresh
 /* One 2x mean-pool level of an [w][h] float32 plane into [w/2][h/2] (in-HBM probability pyramid). */
 int dp_pyramid_down2(const float* in, int64_t w, int64_t h, float* out, void* stream);
 
+/*
+ * JPEG tile encoder of the pyramidal result files.  Replaces the ImageMagick pass of the reference --
+ * `convert <p> -compress jpeg -quality 90 -define tiff:tile-geometry=256x256 ptif:<p>`    DigiPathAI/Segmentation.py:333-334,
+ * 345-346, 351-352 (helpers/convert_to_pyramidal.py:32-37) -- for one pyramid level resident in HBM:
+ * `plane` device uint8 [rows][cols]; tiles of 256 x 256 (border replicated at the plane's edges), row-major tile indices
+ * tile0 .. tile0 + n_tiles - 1.  `tables_host`: the packed table block (quantiser reciprocals in natural order + DC / AC
+ * Huffman codes) the host side builds from the JPEG header it writes in front of every tile (tiffio._jpeg_tables).
+ * Per tile t: `out + t * out_cap` receives the entropy-coded scan (byte-stuffed, padded; no markers), sizes[t] its length;
+ * flags[t] bit 0 = constant tile (value in bits 8..15; nothing written), bit 1 = stream larger than the capacities (nothing
+ * written: encode it on the host).  `workspace`: device, dp_jpeg_encode_workspace_bytes(n_tiles, scratch_bytes_per_tile).
+ * dp_jpeg_compact gathers the fixed-stride streams into one buffer at `offsets` (device int64, exclusive scan of sizes).
+ */
+size_t dp_jpeg_encode_workspace_bytes(int n_tiles, int scratch_bytes_per_tile);
+int dp_jpeg_encode_gray_tiles(const uint8_t* plane, int64_t rows, int64_t cols, int tile0, int n_tiles, const void* tables_host,
+                              size_t tables_bytes, void* workspace, size_t workspace_bytes, int scratch_bytes_per_tile,
+                              uint8_t* out, int out_cap, int32_t* sizes, int32_t* flags, void* stream);
+int dp_jpeg_compact(const uint8_t* in, int cap, const int32_t* sizes, const int64_t* offsets, uint8_t* out, int n_tiles,
+                    void* stream);
+
+
 /* D4 helpers shared with the host code: source map of transform `code` on a P x P tile. */
 void dp_d4_src(int code, int i, int j, int P, int* a, int* b);
 
