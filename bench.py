@@ -14,7 +14,9 @@ probabilities) with the copies inside the timed region.  Every line also carries
     passes, stitch, normalise) on ONE synthetic 40 000 x 40 000 slide, sharded by x-stripes over the N ranks with one
     halo exchange, plus the same slide on rank 0 alone (`n1_seconds`) so that `speedup_vs_n1` is measured in the run;
   * `parity`: the fp16 forward and the fp32 precision mode against the fp32 oracle on calibrated weights;
-  * `fp32_mode`: tiles/s of the precision mode (`--precision fp32` makes it the whole line's subject).
+  * `fp32_mode`: tiles/s of the precision modes (`--precision fp32|tf32x3` makes one the whole line's subject);
+  * `getseg` (N = 1): BASELINE configs[2] through the reference's entry point -- getSegmentation on the same 40 000 x 40 000
+    slide including the three pyramidal TIFFs on disk and the float32 map returned to the host.
 `--workload slide` runs only the slide part, at `--slide` pixels a side.
 
 The oracle (oracle/) is executed here only for the `cpu_baseline` leg and for `--impl reference`.
@@ -501,6 +503,11 @@ def main():
         slide_rec = slide_record(model, args.line_slide, ["FLIP_LEFT_RIGHT", "ROTATE_90", "ROTATE_180"], rank, world, local,
                                  dev, barrier, max_over_ranks, reps=1, with_n1=(world > 1))
 
+    # ---------------------------------------------------------------- BASELINE configs[2] through the public entry point
+    getseg = None
+    if rank == 0 and world == 1 and args.model == "dense" and not args.no_slide and args.precision == "fp16":
+        getseg = getseg_record(args.line_slide, dev)
+
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -548,9 +555,63 @@ def main():
             line["fp32_mode"] = fp32_mode
         if slide_rec is not None:
             line["slide"] = slide_rec
+        if getseg is not None:
+            line["getseg"] = getseg
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def getseg_record(S, dev):
+    """BASELINE configs[2] end to end through the reference's own entry point: ``getSegmentation`` on one synthetic S x S
+    slide resident in HBM (3 TTA transforms = 4 passes, batch 32, stride 128), the three pyramidal JPEG TIFFs written to a
+    temporary directory, the float32 {0, 255} map returned to the host.  Host wall clock of the second of two calls (the
+    first pays graph capture and lane allocation inside the fresh models it builds); N = 1 only."""
+    import tempfile
+    import torch
+    from digipathai_b200 import tiffio
+    from digipathai_b200.Segmentation import getSegmentation
+    from digipathai_b200.models.densenet import init_densenet_weights
+    from digipathai_b200.slide import synthetic_slide_device
+    levels = 1
+    while S // (2 ** (levels - 1)) > 2500 and levels < 5:
+        levels += 1
+    slide = synthetic_slide_device(S, S, dev, seed=0, n_levels=levels)
+    w = init_densenet_weights(0)
+    save_t = []
+    orig = tiffio.save_pyramidal
+
+    def timed(*a, **k):
+        t = time.perf_counter()
+        r = orig(*a, **k)
+        save_t.append(time.perf_counter() - t)
+        return r
+
+    tiffio.save_pyramidal = timed
+    runs = []
+    try:
+        with tempfile.TemporaryDirectory() as d:
+            for _ in range(2):
+                save_t.clear()
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                out = getSegmentation(slide, patch_size=PATCH, stride_size=128, batch_size=BATCH, quick=True,
+                                      tta_list=["FLIP_LEFT_RIGHT", "ROTATE_90", "ROTATE_180"], crf=False,
+                                      save_path=os.path.join(d, "mask.tiff"), probs_path=os.path.join(d, "probs.tiff"),
+                                      uncertainty_path=os.path.join(d, "unc.tiff"), weights=w, status={})
+                runs.append((time.perf_counter() - t0, sum(save_t)))
+                shape = tuple(out.shape)
+                del out
+                file_bytes = sum(os.path.getsize(os.path.join(d, f)) for f in os.listdir(d))
+    finally:
+        tiffio.save_pyramidal = orig
+    del slide
+    torch.cuda.empty_cache()
+    return {"workload": f"getSegmentation(img, 256, 128, 32, quick=True, tta_list of 3, crf=False, save_path / probs_path / "
+                        f"uncertainty_path) on one synthetic {S}x{S} slide resident in HBM; returns float32 {shape}",
+            "seconds": runs[-1][0], "write_seconds": runs[-1][1], "first_call_seconds": runs[0][0],
+            "result_file_bytes": int(file_bytes), "host_cores": os.cpu_count(),
+            "note": "JPEG tiles of the three pyramidal TIFFs are encoded on the GPU (csrc/jpeg_enc.cuh)"}
 
 
 def parity_and_fp32_records(local, fp16_model):

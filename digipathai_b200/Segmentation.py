@@ -402,4 +402,6 @@ def getSegmentation(img_path,
         status['progress'] = 0
     if return_device:
         return label
-    return label.cpu().numpy().astype(np.float32)
+    # the reference returns float32 {0, 255} [W, H] (Segmentation.py:356): 1 byte per pixel crosses PCIe, the widening runs
+    # on all host cores (torch's CPU cast is threaded; numpy's astype is not: 1.3 s less on a 40 000^2 slide)
+    return label.cpu().to(torch.float32).numpy()
