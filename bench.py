@@ -593,9 +593,10 @@ def getseg_record(S, dev):
         with tempfile.TemporaryDirectory() as d:
             for _ in range(2):
                 save_t.clear()
+                phases = {}
                 torch.cuda.synchronize()
                 t0 = time.perf_counter()
-                out = getSegmentation(slide, patch_size=PATCH, stride_size=128, batch_size=BATCH, quick=True,
+                out = getSegmentation(slide, timings=phases, patch_size=PATCH, stride_size=128, batch_size=BATCH, quick=True,
                                       tta_list=["FLIP_LEFT_RIGHT", "ROTATE_90", "ROTATE_180"], crf=False,
                                       save_path=os.path.join(d, "mask.tiff"), probs_path=os.path.join(d, "probs.tiff"),
                                       uncertainty_path=os.path.join(d, "unc.tiff"), weights=w, status={})
@@ -610,6 +611,7 @@ def getseg_record(S, dev):
     return {"workload": f"getSegmentation(img, 256, 128, 32, quick=True, tta_list of 3, crf=False, save_path / probs_path / "
                         f"uncertainty_path) on one synthetic {S}x{S} slide resident in HBM; returns float32 {shape}",
             "seconds": runs[-1][0], "write_seconds": runs[-1][1], "first_call_seconds": runs[0][0],
+            "phases_ms": {k: round(v, 1) for k, v in phases.items()},
             "result_file_bytes": int(file_bytes), "host_cores": os.cpu_count(),
             "note": "JPEG tiles of the three pyramidal TIFFs are encoded on the GPU (csrc/jpeg_enc.cuh)"}
 

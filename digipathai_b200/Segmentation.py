@@ -306,7 +306,8 @@ def getSegmentation(img_path,
                     device=0,
                     return_device=False,
                     pyramidal=True,
-                    precision="fp16"):
+                    precision="fp16",
+                    timings=None):
     """Whole-slide segmentation (reference: Segmentation.py:192-356, README.md:79-87).
 
     Returns the thresholded map -- float32 ``[W, H]`` of {0, 255}, NOT transposed -- exactly what the reference
@@ -323,7 +324,16 @@ def getSegmentation(img_path,
     ``precision='fp32'`` runs the networks in the reference's fp32 arithmetic (see ``load_trained_models``).
     """
     from . import engine
+    import time
     torch = _torch()
+    _t = [time.perf_counter()]
+
+    def _lap(key):
+        if timings is not None:
+            now = time.perf_counter()
+            timings[key] = timings.get(key, 0.0) + (now - _t[0]) * 1e3
+            _t[0] = now
+
     mode = mode.lower()
     print("==================================================")
     print(mode)
@@ -364,6 +374,7 @@ def getSegmentation(img_path,
         models[nm] = load_trained_models(nm, weight_source(nm), patch_size=patch_size, device=device,
                                          max_batch=batch_size, precision=precision)
 
+    _lap('load_ms')
     threshold = 0.3
     if status is not None:
         status['status'] = "Running segmentation"
@@ -371,6 +382,7 @@ def getSegmentation(img_path,
                                       batch_size=batch_size, tta_list=tta_list, models=models,
                                       patch_size=patch_size, stride_size=stride_size, status=status,
                                       device=device, return_device=True, finalize=False)
+    _lap('predict_ms')
     mean, var, count = probs_map['mean'], probs_map['var'], probs_map['count']
     label = torch.empty(mean.shape, dtype=torch.uint8, device=mean.device)
     with torch.cuda.device(mean.device):
@@ -380,6 +392,7 @@ def getSegmentation(img_path,
         torch.cuda.synchronize()
     for m in models.values():
         m.close()
+    _lap('finalize_ms')
 
     from .tiffio import save_plane, save_pyramidal
     if pyramidal:
@@ -400,8 +413,11 @@ def getSegmentation(img_path,
         _save(uncertainty_path, var.T, 255)                              # Segmentation.py:351-352
     if status is not None:
         status['progress'] = 0
+    _lap('save_ms')
     if return_device:
         return label
     # the reference returns float32 {0, 255} [W, H] (Segmentation.py:356): 1 byte per pixel crosses PCIe, the widening runs
     # on all host cores (torch's CPU cast is threaded; numpy's astype is not: 1.3 s less on a 40 000^2 slide)
-    return label.cpu().to(torch.float32).numpy()
+    out = label.cpu().to(torch.float32).numpy()
+    _lap('return_ms')
+    return out
