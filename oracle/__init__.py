@@ -14,5 +14,7 @@ TensorFlow (conv / BN / pooling / softmax semantics) is restated from Keras' doc
 Modules: ``pipeline_ref`` (numpy restatement of get_prediction / dataset / TTA / tissue mask), ``densenet_ref``,
 ``inception_ref``, ``deeplab_ref`` (fp32 PyTorch-CPU restatements of the three Keras graphs of DigiPathAI/models/),
 ``crf_ref`` (exact mean-field inference of the DenseCRF model post_process_crf configures; pydensecrf itself -- a
-permutohedral-lattice approximation of the same model -- is not available: parity unpinned there too).
+permutohedral-lattice approximation of the same model -- is not available: parity unpinned there too), ``lattice_ref``
+(the permutohedral-lattice filter restated from the published algorithm), ``jpeg_ref`` (baseline-JPEG tile encoder of the
+result files; pinned: its streams are decoded by libjpeg and compared with libjpeg's own encoder).
 """
