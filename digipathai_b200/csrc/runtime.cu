@@ -2096,11 +2096,9 @@ int dp_jpeg_encode_gray_tiles(const uint8_t* plane, int64_t rows, int64_t cols, 
   if (workspace_bytes < dp_jpeg_encode_workspace_bytes(n_tiles, scratch_bytes_per_tile) || scratch_bytes_per_tile < 1024)
     return fail("JPEG workspace too small: need %zu bytes", dp_jpeg_encode_workspace_bytes(n_tiles, scratch_bytes_per_tile));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  static std::once_flag once;
-  static cudaError_t attr_err = cudaSuccess;
   const int smem = dp::kJpBlocks * 64 * 2 + dp::kJpTile * dp::kJpTile;
-  std::call_once(once, [&] { attr_err = cudaFuncSetAttribute(dp::jpeg_encode_tiles_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); });
-  if (attr_err != cudaSuccess) return fail("cudaFuncSetAttribute(jpeg encoder): %s", cudaGetErrorString(attr_err));
+  // per call, not once per process: the attribute belongs to the current device
+  CU_OK(cudaFuncSetAttribute(dp::jpeg_encode_tiles_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   uint8_t* ws = static_cast<uint8_t*>(workspace);
   const int scratch_words = (scratch_bytes_per_tile + 3) / 4;
   // the tables are 1.3 KB: a synchronous copy keeps the caller's host buffer free to go away after the call
