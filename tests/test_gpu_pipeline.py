@@ -126,7 +126,7 @@ def test_quick_false_runs_the_three_model_ensemble(env):
 
 
 def test_get_segmentation_fp32_mode_returns_the_reference_label_map(env):
-    """precision='fp32': the returned {0, 255} map equals the oracle's except where the oracle's own probability lies
+    """precision='fp32' / 'tf32x3': the returned {0, 255} map equals the oracle's except where the oracle's own probability lies
     within 1e-3 of the threshold (BASELINE.json: 1e-3 on the mask probabilities, identical label map) -- single model
     and the quick=False three-model ensemble."""
     from digipathai_b200.Segmentation import getSegmentation
@@ -135,10 +135,11 @@ def test_get_segmentation_fp32_mode_returns_the_reference_label_map(env):
     from oracle import deeplab_ref, inception_ref, pipeline_ref
     w, slide, omodels = env
     want_thr, want_mean, _ = pipeline_ref.getSegmentation(slide, omodels, 256, 128, 4)
-    got = getSegmentation(slide, patch_size=256, stride_size=128, batch_size=4, quick=True, weights=w, precision="fp32")
-    mism = got != want_thr
-    print(f"\ngetSegmentation fp32 mode: {int(mism.sum())} / {mism.size} label mismatches")
-    assert (np.abs(want_mean - 0.3)[mism] <= 1e-3).all() and mism.sum() <= (np.abs(want_mean - 0.3) <= 1e-3).sum()
+    for prec in ("fp32", "tf32x3"):               # CUDA-core FMA mode and the 3xTF32 tensor-core mode
+        got = getSegmentation(slide, patch_size=256, stride_size=128, batch_size=4, quick=True, weights=w, precision=prec)
+        mism = got != want_thr
+        print(f"\ngetSegmentation {prec} mode: {int(mism.sum())} / {mism.size} label mismatches")
+        assert (np.abs(want_mean - 0.3)[mism] <= 1e-3).all() and mism.sum() <= (np.abs(want_mean - 0.3) <= 1e-3).sum()
     rng = np.random.default_rng(12)
     calib = (rng.integers(0, 256, (2, 256, 256, 3)).astype(np.float32) - 128.0) / 128.0
     wi = inception_ref.calibrate_bn(init_inception_weights(5), calib)
