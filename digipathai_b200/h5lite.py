@@ -12,7 +12,9 @@ directly, following the public "HDF5 File Format Specification Version 3.0":
 * attributes (message versions 1-3) of those types and of variable-length strings (global heap), which is how Keras
   stores ``layer_names`` / ``weight_names`` / ``keras_version``.
 
-Only reading is implemented.  **Pinning:** no libhdf5-written file exists in this image, so the reader is checked
+Only reading is implemented.  The version-2 paths (superblock 2/3, ``OHDR`` headers, link messages: files written with
+``libver='latest'``) are written from the specification but NOT exercised by any test -- the independent writer emits
+the classic layout only, which is what Keras files of the reference's era use.  **Pinning:** no libhdf5-written file exists in this image, so the reader is checked
 against an independent minimal writer (tests/h5_writer.py) that emits the classic layout byte by byte from the same
 specification -- the first run against a real checkpoint is still outstanding.
 """
