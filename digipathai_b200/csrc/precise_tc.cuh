@@ -440,10 +440,6 @@ conv_halo_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_
       int st = 0, use = 0;                           // tap stage being filled and how often it has been filled before
       int hs = 0;
       for (int gs = 0; gs < n_gs; ++gs) {
-        if (gs >= 1 && gs + 1 < n_gs) {              // raw halo of slice gs + 1, once the MMAs of slice gs - 1 have left its stage
-          mbar_wait(&a_empty[(gs + 1) & 1], ((gs - 1) >> 1) & 1);
-          load_next_a();
-        }
         for (int tap = 0; tap < n_taps; tap += tps) {
           if (use >= 1) mbar_wait(&b_empty[st], (use - 1) & 1);              // the MMAs that last read this stage are done
           uint64_t* bar = &b_full[st];
@@ -454,6 +450,13 @@ conv_halo_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_
             tma_load_3d(&map_wl, bar, dst + i * b_tap_bytes + n_tile * 128, hs * kTxSliceK, n0, s_tap_e[tap + i]);
           }
           if (++st == SB) { st = 0; ++use; }
+          if (tap == 0 && gs >= 1 && gs + 1 < n_gs) {
+            // raw halo of slice gs + 1, once the MMAs of slice gs - 1 have left its stage -- AFTER the first weight stage
+            // of this slice: waiting here first kept those weights from being requested until slice gs - 1 had finished
+            // (1.2-1.5 k clk of exposed TMA latency at every slice start, traced)
+            mbar_wait(&a_empty[(gs + 1) & 1], ((gs - 1) >> 1) & 1);
+            load_next_a();
+          }
         }
         if (++hs == n_hs) hs = 0;
       }
@@ -468,15 +471,15 @@ conv_halo_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_
       int st = 0, use = 0, spos = 0;                 // weight stage of the current tap, how often it has been used, tap inside it
       int chunk = 0, cpos = 0;
       for (int gs = 0; gs < n_gs; ++gs) {
-        mbar_wait(&a_ready[gs & 1], (gs >> 1) & 1);
+        mbar_wait_probe(&a_ready[gs & 1], (gs >> 1) & 1);
         tc_fence_after();
         const uint32_t a_hi_addr = a_op_addr + static_cast<uint32_t>((gs & 1) * 2 * kThATile);
         for (int tap = 0; tap < n_taps; ++tap) {
           if (cpos == 0 && chunk >= 2) {
-            mbar_wait(&acc_empty[chunk & 1], ((chunk >> 1) - 1) & 1);       // chunk - 2 has been drained
+            mbar_wait_probe(&acc_empty[chunk & 1], ((chunk >> 1) - 1) & 1);       // chunk - 2 has been drained
             tc_fence_after();
           }
-          if (spos == 0) mbar_wait(&b_full[st], use & 1);
+          if (spos == 0) mbar_wait_probe(&b_full[st], use & 1);
           const uint32_t d = tmem_base + static_cast<uint32_t>((chunk & 1) * n_tile);
           const uint32_t ta = a_hi_addr + s_tap_a[tap];
           const uint32_t tb = b_op_addr + static_cast<uint32_t>(st * b_stage_bytes + spos * b_tap_bytes);
@@ -687,10 +690,10 @@ conv_1x1_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
       for (int gs = 0; gs < n_gs; ++gs) {
         const bool chunk_start = (hs & 1) == 0, chunk_end = (hs & 1) == 1 || hs == n_s - 1;
         if (chunk_start && chunk >= 2) {
-          mbar_wait(&acc_empty[chunk & 1], ((chunk >> 1) - 1) & 1);
+          mbar_wait_probe(&acc_empty[chunk & 1], ((chunk >> 1) - 1) & 1);
           tc_fence_after();
         }
-        mbar_wait(&ready[st], use & 1);
+        mbar_wait_probe(&ready[st], use & 1);
         tc_fence_after();
         const uint32_t d = tmem_base + static_cast<uint32_t>((chunk & 1) * n_tile);
         const uint32_t ta = smem_addr + static_cast<uint32_t>(st * stage_bytes);

@@ -69,6 +69,31 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
+// Spin on the NON-blocking probe (mbarrier.test_wait) instead of try_wait: for a single latency-critical thread (the MMA
+// issuer of precise_tc.cuh) whose barriers are usually already complete when it looks.
+__device__ __forceinline__ bool mbar_test_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_probe(uint64_t* bar, uint32_t parity) {
+  uint32_t spins = 0;
+  while (!mbar_test_wait(bar, parity)) {
+    if (++spins > (1u << 28)) {
+      printf("dp: mbarrier timeout (probe) block %d thread %d bar %u parity %u\n", blockIdx.x, threadIdx.x, smem_u32(bar), parity);
+      __trap();
+    }
+  }
+}
+
 // One arrival per WARP: all lanes have finished the work the barrier publishes (their own fences included), the warp
 // converges, lane 0 arrives.  256 per-thread arrivals are 256 serialised shared-memory atomics on one word (~3 clk
 // each: ~750 clk per hand-off, measured as the floor of the per-chunk transform and of the mid epilogue); 8 are not.
