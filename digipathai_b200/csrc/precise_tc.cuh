@@ -329,8 +329,8 @@ __global__ void __launch_bounds__(kTxThreads, 1) conv_tf32x3_kernel(const NaiveC
 // every tap (dy, dx) is a UMMA descriptor into that tile at row (dy+1) * 10 + (dx+1) with an 8-row-group stride of 10
 // rows (the 128-byte swizzle is a function of absolute shared-memory address bits, so unaligned starts are fine:
 // tools/mma_probe.cu).  Weights come PRE-SPLIT (hi / lo copies of the container's data section made at model creation)
-// through two 3-D TMA boxes per tap into a ring of tap stages.  Warp 9 (one elected thread) issues every TMA, warp 8
-// every MMA -- one thread doing both spent 1.5 k clk per tap on its serial chain of barrier waits (~200 clk each) and
+// through two 3-D TMA boxes per tap into a ring of tap stages.  Warp 9 (one elected thread) issues every TMA, warps 8 and
+// 10 the MMAs of alternate accumulator chunks -- one thread doing both spent 1.5 k clk per tap on its serial chain of barrier waits (~200 clk each) and
 // commits (~200 clk each) against 0.6-0.8 k clk of MMA time; eight worker warps convert, drain finished accumulator
 // chunks (3 taps; 2 for up2) into registers and run the epilogue.  All hand-offs are mbarriers; there is no
 // block-wide barrier inside the loop.
@@ -338,13 +338,14 @@ constexpr int kThHaloW = 10, kThHaloH = 18, kThRows = 180;
 constexpr int kThATile = 23 * 1024;                 // 180 rows x 128 B, rounded up to 1 KB
 constexpr int kThItems = 6;                         // ceil(180 * 8 chunks / 256 worker threads)
 constexpr int kThBStages = 4;
-constexpr int kThThreads = 320;                     // 8 worker warps + MMA warp + TMA producer warp
+constexpr int kThThreads = 320;                     // 8 worker warps + MMA warp + TMA producer warp (1x1 kernel)
+constexpr int kThHaloThreads = 352;                 // halo kernel: a second MMA warp (chunks alternate between the two)
 
 __host__ __device__ inline int th_smem_bytes(int n, int tps) {
   return 1024 + 2 * 2 * kThATile + (tps > 1 ? 2 * tps : kThBStages) * 2 * n * 128 + 256;
 }
 
-__global__ void __launch_bounds__(kThThreads, 1)
+__global__ void __launch_bounds__(kThHaloThreads, 1)
 conv_halo_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_wh,
                         const __grid_constant__ CUtensorMap map_wl, const NaiveConvParams p, const int n_tile, const int tps) {
   extern __shared__ uint8_t tx_smem_raw[];
@@ -391,10 +392,14 @@ conv_halo_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_
     tmem_alloc(tmem_slot, tmem_cols);
     tmem_relinquish();
   }
+  // two MMA-issuing threads (warps 8 and 10) take alternate accumulator chunks: one thread's serial chain per chunk -- three
+  // barrier waits of ~250 clk, 36 MMA issues, two commits -- is longer than the chunk's execution on the narrow layers
+  const int n_taps_e = p.n_entries_total / p.n_groups;
+  const bool two_issuers = (n_taps_e % 3 == 0 ? n_taps_e / 3 : (n_taps_e % 2 == 0 ? n_taps_e / 2 : n_taps_e)) >= 2;
   if (tid == 256) {
     for (int i = 0; i < SB; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
     for (int i = 0; i < 2; ++i) {
-      mbar_init(&a_full[i], 1); mbar_init(&a_ready[i], 8); mbar_init(&a_empty[i], 1);
+      mbar_init(&a_full[i], 1); mbar_init(&a_ready[i], 8); mbar_init(&a_empty[i], two_issuers ? 2 : 1);
       mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 8);
     }
     fence_barrier_init();
@@ -462,9 +467,10 @@ conv_halo_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_
       }
     }
     __syncwarp();
-  } else if (warp == 8) {
-    // ================================================= MMA issuer
-    if (elect_one()) {
+  } else if (warp == 8 || warp == 10) {
+    // ================================================= MMA issuers
+    const int which = warp == 8 ? 0 : 1;
+    if ((which == 0 || two_issuers) && elect_one()) {
       const uint32_t idesc = make_idesc_tf32(static_cast<uint32_t>(n_tile));
       const uint32_t a_op_addr = smem_u32(a_op), b_op_addr = smem_u32(b_op);
       const uint32_t b_desc_hi = sw128_desc_hi(1024), a_desc_hi = sw128_desc_hi(kThHaloW * 128);
@@ -475,31 +481,43 @@ conv_halo_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_
         tc_fence_after();
         const uint32_t a_hi_addr = a_op_addr + static_cast<uint32_t>((gs & 1) * 2 * kThATile);
         for (int tap = 0; tap < n_taps; ++tap) {
-          if (cpos == 0 && chunk >= 2) {
-            mbar_wait_probe(&acc_empty[chunk & 1], ((chunk >> 1) - 1) & 1);       // chunk - 2 has been drained
-            tc_fence_after();
-          }
-          if (spos == 0) mbar_wait_probe(&b_full[st], use & 1);
-          const uint32_t d = tmem_base + static_cast<uint32_t>((chunk & 1) * n_tile);
-          const uint32_t ta = a_hi_addr + s_tap_a[tap];
-          const uint32_t tb = b_op_addr + static_cast<uint32_t>(st * b_stage_bytes + spos * b_tap_bytes);
-          const uint64_t dah = (static_cast<uint64_t>(a_desc_hi) << 32) | sw128_desc_lo(ta);
-          const uint64_t dal = (static_cast<uint64_t>(a_desc_hi) << 32) | sw128_desc_lo(ta + kThATile);
-          const uint64_t dbh = (static_cast<uint64_t>(b_desc_hi) << 32) | sw128_desc_lo(tb);
-          const uint64_t dbl = (static_cast<uint64_t>(b_desc_hi) << 32) | sw128_desc_lo(tb + n_tile * 128);
+          const bool mine = !two_issuers || (chunk & 1) == which;
+          if (mine) {
+            if (cpos == 0 && chunk >= 2) {
+              mbar_wait_probe(&acc_empty[chunk & 1], ((chunk >> 1) - 1) & 1);       // chunk - 2 has been drained
+              tc_fence_after();
+            }
+            if (spos == 0) mbar_wait_probe(&b_full[st], use & 1);
+            const uint32_t d = tmem_base + static_cast<uint32_t>((chunk & 1) * n_tile);
+            const uint32_t ta = a_hi_addr + s_tap_a[tap];
+            const uint32_t tb = b_op_addr + static_cast<uint32_t>(st * b_stage_bytes + spos * b_tap_bytes);
+            const uint64_t dah = (static_cast<uint64_t>(a_desc_hi) << 32) | sw128_desc_lo(ta);
+            const uint64_t dal = (static_cast<uint64_t>(a_desc_hi) << 32) | sw128_desc_lo(ta + kThATile);
+            const uint64_t dbh = (static_cast<uint64_t>(b_desc_hi) << 32) | sw128_desc_lo(tb);
+            const uint64_t dbl = (static_cast<uint64_t>(b_desc_hi) << 32) | sw128_desc_lo(tb + n_tile * 128);
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {              // 8 fp32 = 32 B = 2 descriptor units per K-step
-            umma_tf32_ss(d, dah + 2 * k, dbh + 2 * k, idesc, (cpos == 0 && k == 0) ? 0u : 1u);
-            umma_tf32_ss(d, dal + 2 * k, dbh + 2 * k, idesc, 1u);
-            umma_tf32_ss(d, dah + 2 * k, dbl + 2 * k, idesc, 1u);
+            for (int k = 0; k < 4; ++k) {              // 8 fp32 = 32 B = 2 descriptor units per K-step
+              umma_tf32_ss(d, dah + 2 * k, dbh + 2 * k, idesc, (cpos == 0 && k == 0) ? 0u : 1u);
+              umma_tf32_ss(d, dal + 2 * k, dbh + 2 * k, idesc, 1u);
+              umma_tf32_ss(d, dah + 2 * k, dbl + 2 * k, idesc, 1u);
+            }
           }
           if (++spos == tps) {
-            umma_commit(&b_empty[st]);
+            if (mine) umma_commit(&b_empty[st]);
             spos = 0;
             if (++st == SB) { st = 0; ++use; }
           }
-          if (tap == n_taps - 1) umma_commit(&a_empty[gs & 1]);
-          if (cpos == chunk_taps - 1) { umma_commit(&acc_full[chunk & 1]); cpos = 0; ++chunk; } else { ++cpos; }
+          if (cpos == chunk_taps - 1) {
+            if (mine) {
+              umma_commit(&acc_full[chunk & 1]);
+              // this thread's last chunk of the slice: its MMAs are out of the A stage once this commit fires
+              const int left = cph - 1 - (tap / chunk_taps);             // chunks of this slice after this one
+              if (!two_issuers ? left == 0 : left <= 1) umma_commit(&a_empty[gs & 1]);
+            }
+            cpos = 0; ++chunk;
+          } else {
+            ++cpos;
+          }
         }
       }
     }

@@ -936,7 +936,7 @@ int run_op_f32(dp_model* m, SubPlan* sp, int i, cudaStream_t st) {
         const int epg = q.n_entries_total / q.n_groups;
         const int chunk_taps = epg % 3 == 0 ? 3 : (epg % 2 == 0 ? 2 : 1);
         const int tps = (t.n_tile <= 64 && !getenv("DP_TX_TPS1")) ? chunk_taps : 1;
-        dp::conv_halo_tf32x3_kernel<<<hgrid, dp::kThThreads, dp::th_smem_bytes(t.n_tile, tps), st>>>(t.a, t.wh, t.wl, q, t.n_tile, tps);
+        dp::conv_halo_tf32x3_kernel<<<hgrid, dp::kThHaloThreads, dp::th_smem_bytes(t.n_tile, tps), st>>>(t.a, t.wh, t.wl, q, t.n_tile, tps);
         return;
       }
       const int n_tile = round_up((q.Cout + t.n_ntiles - 1) / t.n_ntiles, 16);
