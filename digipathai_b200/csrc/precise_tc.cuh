@@ -342,7 +342,7 @@ constexpr int kThThreads = 320;                     // 8 worker warps + MMA warp
 constexpr int kThHaloThreads = 352;                 // halo kernel: a second MMA warp (chunks alternate between the two)
 
 __host__ __device__ inline int th_smem_bytes(int n, int tps) {
-  return 1024 + 2 * 2 * kThATile + (tps > 1 ? 2 * tps : kThBStages) * 2 * n * 128 + 256;
+  return 1024 + 2 * 2 * kThATile + (tps > 1 ? 2 * tps : kThBStages) * 2 * n * 128 + 256 + 1024;   // + epilogue constants
 }
 
 __global__ void __launch_bounds__(kThHaloThreads, 1)
@@ -369,6 +369,7 @@ conv_halo_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
   int* s_tap_e = reinterpret_cast<int*>(tmem_slot + 1);                      // [9] entry index of tap i of this group
   uint32_t* s_tap_a = reinterpret_cast<uint32_t*>(s_tap_e + 9);              // [9] byte offset of tap i inside the halo tile
+  float* s_epi = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 256);   // [2][n_tile] epilogue scale, shift
 
   float* __restrict__ out = reinterpret_cast<float*>(p.out);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -413,6 +414,11 @@ conv_halo_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_
     tma_prefetch_desc(&map_a);
     tma_prefetch_desc(&map_wh);
     tma_prefetch_desc(&map_wl);
+  }
+  for (int i = tid; i < n_tile; i += blockDim.x) {   // epilogue constants of this N tile (identity beyond Cout)
+    const int c = n0 + i;
+    s_epi[i] = (p.epi_scale && c < p.Cout) ? p.epi_scale[c] : 1.f;
+    s_epi[n_tile + i] = (p.epi_shift && c < p.Cout) ? p.epi_shift[c] : 0.f;
   }
   tc_fence_before();
   __syncthreads();
@@ -603,7 +609,7 @@ conv_halo_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_
             const int c = co + t;
             float val = sum[a][4 * j4 + t];
             if (c < p.Cout) {
-              val = fmaf(val, p.epi_scale ? p.epi_scale[c] : 1.f, p.epi_shift ? p.epi_shift[c] : 0.f);
+              val = fmaf(val, s_epi[c - n0], s_epi[n_tile + c - n0]);
               if (p.residual) val += orow[c];
               if (p.relu) val = fmaxf(val, 0.f);
             }
@@ -635,7 +641,7 @@ constexpr int kT1Stages = 3;
 constexpr int kT1Lag = 2;                           // worker drains run this many slices behind their conversions
 
 __host__ __device__ inline int t1_stage_bytes(int n) { return 2 * kTxATile + 2 * n * 128; }
-__host__ __device__ inline int t1_smem_bytes(int n) { return 1024 + kT1Stages * t1_stage_bytes(n) + 256; }
+__host__ __device__ inline int t1_smem_bytes(int n) { return 1024 + kT1Stages * t1_stage_bytes(n) + 256 + 1024; }
 
 __global__ void __launch_bounds__(kThThreads, 1)
 conv_1x1_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_wh,
@@ -652,6 +658,7 @@ conv_1x1_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
   uint64_t* acc_full = bars + 3 * S;                 // [2]
   uint64_t* acc_empty = acc_full + 2;                // [2] (8 worker warps)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  float* s_epi = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 256);   // [2][n_tile] epilogue scale, shift
 
   float* __restrict__ out = reinterpret_cast<float*>(p.out);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -675,6 +682,11 @@ conv_1x1_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
     tma_prefetch_desc(&map_a);
     tma_prefetch_desc(&map_wh);
     tma_prefetch_desc(&map_wl);
+  }
+  for (int i = tid; i < n_tile; i += blockDim.x) {   // epilogue constants of this N tile (identity beyond Cout)
+    const int c = n0 + i;
+    s_epi[i] = (p.epi_scale && c < p.Cout) ? p.epi_scale[c] : 1.f;
+    s_epi[n_tile + i] = (p.epi_shift && c < p.Cout) ? p.epi_shift[c] : 0.f;
   }
   tc_fence_before();
   __syncthreads();
@@ -779,7 +791,7 @@ conv_1x1_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
               const int c = co + t;
               float val = sum[a][4 * j4 + t];
               if (c < p.Cout) {
-                val = fmaf(val, p.epi_scale ? p.epi_scale[c] : 1.f, p.epi_shift ? p.epi_shift[c] : 0.f);
+                val = fmaf(val, s_epi[c - n0], s_epi[n_tile + c - n0]);
                 if (p.residual) val += orow[c];
                 if (p.relu) val = fmaxf(val, 0.f);
               }
