@@ -14,9 +14,12 @@ directly, following the public "HDF5 File Format Specification Version 3.0":
 
 Only reading is implemented.  The version-2 paths (superblock 2/3, ``OHDR`` headers, link messages: files written with
 ``libver='latest'``) are written from the specification but NOT exercised by any test -- the independent writer emits
-the classic layout only, which is what Keras files of the reference's era use.  **Pinning:** no libhdf5-written file exists in this image, so the reader is checked
-against an independent minimal writer (tests/h5_writer.py) that emits the classic layout byte by byte from the same
-specification -- the first run against a real checkpoint is still outstanding.
+the classic layout only, which is what Keras files of the reference's era use.  **Pinning:** (1) a file libhdf5 itself wrote -- scipy's MATLAB-7.4 v7.3 fixture (HDF5 1.x behind a 512-byte user block),
+committed as tests/golden/testhdf5_7.4_GLNX86.mat: group walk, dataset values (known answer 0:pi/4:2*pi) and string
+attribute are read back exactly; (2) an independent minimal writer (tests/h5_writer.py) that emits the classic layout
+byte by byte from the same specification, for everything that small file does not contain (multi-level B-trees, chunked
+/ deflated data, continuation blocks, variable-length strings, the Keras layout).  A real Keras checkpoint has still not
+been available.
 """
 from __future__ import annotations
 
@@ -459,8 +462,12 @@ class File(Group):
             root_addr = b.off()
         else:
             raise H5Error(f"superblock version {version}")
-        if self.base not in (0, UNDEF) or base:
-            raise H5Error("files with a non-zero base address / user block are not supported")
+        if self.base == UNDEF:
+            self.base = 0
+        if self.base != base:
+            raise H5Error(f"superblock at {base} but base address {self.base}: not supported")
+        if base:                                            # user block (e.g. MATLAB v7.3 files): addresses are relative
+            data = data[base:]                              # to the base address = the superblock's position
         self.buf = _Buf(data, 0, osz, lsz)
         self._heaps = {}
         super().__init__(self, _Object(self, root_addr), "/")

@@ -131,3 +131,21 @@ def test_load_weights_dispatches_on_the_extension(tmp_path):
         assert np.array_equal(got[k], w[k])
     with pytest.raises(FileNotFoundError):
         Segmentation._load_weights("deeplabv3", str(tmp_path / "other.h5"))
+
+
+def test_reads_a_file_written_by_libhdf5():
+    """The one libhdf5-written file this image holds: scipy's test fixture ``testhdf5_7.4_GLNX86.mat`` (a MATLAB 7.4 v7.3
+    MAT-file = HDF5 1.x behind a 512-byte user block; copied to tests/golden/ from
+    site-packages/scipy/io/matlab/tests/data, BSD licence).  It pins the classic-layout parsing -- superblock 0, version-1
+    object header, symbol-table group (B-tree + local heap + SNOD), dataspace / datatype / layout messages, a
+    fixed-length string attribute -- against bytes libhdf5 itself produced.  Known answer: MATLAB's ``0:pi/4:2*pi``."""
+    path = os.path.join(ROOT, "tests", "golden", "testhdf5_7.4_GLNX86.mat")
+    f = h5lite.File(path)
+    assert f.keys() == ["testdouble"]
+    ds = f["testdouble"]
+    assert ds.attrs["MATLAB_class"] == b"double"
+    a = np.asarray(ds)
+    assert a.dtype == np.float64 and a.shape == (9, 1)
+    assert np.array_equal(a[:, 0], np.arange(9) * (np.pi / 4))
+    with pytest.raises(h5lite.H5Error):
+        h5lite.File(open(path, "rb").read()[:600])            # truncated behind the user block
