@@ -9,7 +9,9 @@ exist in this image, so it cannot be executed here.  The restatement is pinned i
 reference's own pure-numpy functions ``apply_tta`` / ``transform_prob`` (DigiPathAI/helpers/utils.py:487-522,
 extracted at fixture-generation time by tests/golden/make_golden.py) and committing their outputs as golden
 vectors, and (b) hand-computable known-answer cases for the stitch arithmetic.  Everything that lives inside
-TensorFlow (conv / BN / pooling / softmax semantics) is restated from Keras' documented behaviour.
+TensorFlow (conv / BN / pooling / softmax semantics) is restated from Keras' documented behaviour; (c) the
+DenseNet-121 encoder of ``densenet_ref`` agrees stage by stage (2e-5) with an independent implementation present in
+this image, ``torchvision.models.densenet121``, loaded with the same weights (tests/test_oracle_vs_torchvision.py).
 
 Modules: ``pipeline_ref`` (numpy restatement of get_prediction / dataset / TTA / tissue mask), ``densenet_ref``,
 ``inception_ref``, ``deeplab_ref`` (fp32 PyTorch-CPU restatements of the three Keras graphs of DigiPathAI/models/),
