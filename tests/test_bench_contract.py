@@ -36,3 +36,28 @@ def test_reference_arm_other_ranks_exit_quietly():
     r = _run({"RANK": "1", "LOCAL_RANK": "1", "WORLD_SIZE": "2"})
     assert r.returncode == 0, r.stderr[-2000:]
     assert not [l for l in r.stdout.splitlines() if l.startswith("{")]
+
+
+def test_committed_bench_line_carries_the_contract_keys():
+    """The bench line committed as evidence (profiles/r2s5_bench.json, produced by `python bench.py` on a B200) has every
+    key of the driver's contract, with consistent values."""
+    import json
+    p = os.path.join(ROOT, "profiles", "r2s5_bench.json")
+    d = json.loads(open(p).read().strip().splitlines()[-1])
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+              "vs_baseline", "dtype", "data", "config", "clocks", "e2e", "gpu_launches", "roofline", "cpu_baseline"):
+        assert k in d, k
+    assert d["metric"] == "tiles_per_sec_256x256_b32" and d["unit"] == "tiles/s" and d["higher_is_better"] is True
+    assert d["n_gpus"] == 1 and d["warmup"] >= 3 and d["vs_baseline"] is None and d["data"] == "synthetic"
+    assert "workload" in d["config"] and "l2" in d["config"] and "model" not in d["config"]
+    assert abs(d["value"] - 32 * 1e3 / d["ms_per_step"]) <= 1e-6 * d["value"]
+    e = d["e2e"]
+    assert e["h2d_bytes_per_step"] == 32 * 256 * 256 * 3 and e["d2h_bytes_per_step"] == 32 * 256 * 256 * 4 and e["value"] > 0
+    r = d["roofline"]
+    assert r["bound"] == "tensor" and r["unit"] == "TFLOP/s" and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9
+    assert r["traffic"] is not None and r["achieved"] * 1e12 * d["ms_per_step"] * 1e-3 <= 1.3541e12 * 1.001
+    c = d["cpu_baseline"]
+    assert c["kind"] == "port" and c["cores"] >= 1 and c["value"] > 0 and "sample" in c
+    assert d["gpu_launches"] > 0 and not set(d["clocks"]["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
+    for k in ("single_stream", "parity", "fp32_mode", "slide", "getseg"):
+        assert k in d, k
