@@ -44,3 +44,46 @@ def test_three_products_reproduce_the_fp32_product():
     assert rel.max() <= 2.0 ** -20 and rel.mean() <= 2.0 ** -23            # dropped al*wl ~ 2^-22, lo roundings 2^-22 each
     one = f(ah) * f(wh)
     assert (np.abs(one - exact) / np.maximum(np.abs(exact), 1e-300)).mean() >= 2.0 ** -13   # a single TF32 product is not enough
+
+
+def test_truncating_accumulate_model_explains_the_measured_bias():
+    """What was measured on the B200 with ONE TMEM accumulator per conv (profiles/r2s5_tf32x3_accuracy_single_accumulator.txt:
+    positive operands, result low by ~1.0e-8 x K relative) against a numpy model of the accumulate: the 8 products of an
+    MMA instruction summed exactly, the sum added to the fp32 accumulator and TRUNCATED toward zero.  The model predicts
+    -0.6e-8 ... -0.8e-8 x K; the hardware loses a little more (it also truncates inside the product tree), a
+    round-to-nearest accumulate would lose ~100x less.  This is why the kernels fold chunks of <= 36 instructions into
+    registers with round-to-nearest adds."""
+    import os
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    txt = open(os.path.join(root, "profiles", "r2s5_tf32x3_accuracy_single_accumulator.txt")).read()
+    pos = txt.split("inputs signed")[0]
+    measured = {int(m.group(1)): float(m.group(2)) for m in
+                re.finditer(r"1x1 Cin\s+\d+\s+K\s+(\d+)\s+fp32:.*?tf32x3: max \S+ bias (\S+)", pos)}
+    assert set(measured) >= {128, 512, 2048}
+
+    def trunc32(x64):
+        f = x64.astype(np.float32)
+        over = np.abs(f.astype(np.float64)) > np.abs(x64)
+        return np.where(over, np.nextafter(f, np.float32(0)), f).astype(np.float32)
+
+    rng = np.random.default_rng(0)
+    for K in (128, 512, 2048):
+        n = 600
+        a = np.abs(rng.standard_normal((n, K))).astype(np.float32)
+        w = np.abs(rng.standard_normal((n, K)) * np.sqrt(2.0 / K)).astype(np.float32)
+        (ah, al), (wh, wl) = _split(a), _split(w)
+        f = lambda t: t.astype(np.float64)
+        exact = (f(a) * f(w)).sum(1)
+        acc_t = np.zeros(n, np.float32)
+        acc_n = np.zeros(n, np.float32)
+        for k0 in range(0, K, 8):
+            s = slice(k0, k0 + 8)
+            for x, y in ((ah, wh), (al, wh), (ah, wl)):
+                p = (f(x[:, s]) * f(y[:, s])).sum(1)
+                acc_t = trunc32(acc_t.astype(np.float64) + p)
+                acc_n = (acc_n.astype(np.float64) + p).astype(np.float32)
+        bias_t = ((acc_t.astype(np.float64) - exact) / np.abs(exact).max()).mean()
+        bias_n = ((acc_n.astype(np.float64) - exact) / np.abs(exact).max()).mean()
+        assert bias_t < 0 and 1.0 <= measured[K] / bias_t <= 1.7, (K, measured[K], bias_t)
+        assert abs(bias_n) < abs(bias_t) / 20
